@@ -1,0 +1,327 @@
+"""CPU ORACLE -- TEST INFRASTRUCTURE ONLY (see econpdes_oracle.py).
+
+Vectorised numpy restatements of the model functors named by the configs, each citing the
+reference body it follows, plus the grids/guesses the examples build.  Expression order is
+kept exactly as written in the reference (Julia evaluates left to right and never
+contracts a*b+c into an fma; ``x^2`` with a literal exponent is ``x*x``).
+"""
+from __future__ import annotations
+
+import math
+from fractions import Fraction
+from typing import Dict, Tuple
+
+import numpy as np
+
+
+def julia_range(a: float, b: float, n: int) -> np.ndarray:
+    """``range(a, b, length=n)``: Julia evaluates a + (i-1)*step in twice precision, i.e.
+    (to the last bit in all but pathological cases) the correctly rounded exact value."""
+    fa, fb = Fraction(float(a)), Fraction(float(b))
+    step = (fb - fa) / (n - 1)
+    out = np.array([float(fa + i * step) for i in range(n)], dtype=np.float64)
+    out[-1] = float(b)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# C1  README quickstart (README.md:48-67)
+# --------------------------------------------------------------------------------------
+def readme_linear(rho=0.05, kappa=0.2):
+    def pde(state, u):
+        x = state["x"]
+        mu = -kappa * (x - 0.5)
+        vt = -(x + mu * np.where(mu >= 0, u["vx_up"], u["vx_down"]) - rho * u["v"])
+        return {"vt": vt}
+    return pde
+
+
+def readme_linear_problem(n=50):
+    grid = {"x": julia_range(0.0, 1.0, n)}
+    guess = {"v": np.zeros(n)}
+    return grid, guess
+
+
+# --------------------------------------------------------------------------------------
+# C4  Campbell-Cochrane habit model (examples/asset_pricing/campbell_cochrane.jl:28-84)
+# --------------------------------------------------------------------------------------
+CC_DEFAULT = dict(mu=0.0189, sigma=0.015, gamma=2.0, rho=0.116, kappa_s=0.138, b=0.0)
+
+
+def campbell_cochrane_grid(mu, sigma, gamma, rho, kappa_s, b, sn=1000) -> np.ndarray:
+    """initialize_stategrid, campbell_cochrane.jl:40-48."""
+    Sbar = sigma * math.sqrt(gamma / (kappa_s - b / gamma))
+    sbar = math.log(Sbar)
+    smax = sbar + 0.5 * (1 - Sbar * Sbar)
+    nh = sn // 10
+    with np.errstate(divide="ignore"):
+        shigh = np.log(julia_range(0.0, math.exp(smax), nh))
+    slow = julia_range(-300.0, shigh[1], sn - nh)
+    return np.concatenate([slow[:-1], shigh[1:]])
+
+
+def campbell_cochrane(mu, sigma, gamma, rho, kappa_s, b):
+    def pde(state, u):
+        s = state["s"]
+        p, ps_up, ps_down, pss = u["p"], u["ps_up"], u["ps_down"], u["pss"]
+        Sbar = sigma * math.sqrt(gamma / (kappa_s - b / gamma))
+        sbar = math.log(Sbar)
+        lam = 1 / Sbar * np.sqrt(1 - 2 * (s - sbar)) - 1
+        mus = -kappa_s * (s - sbar)
+        sigs = lam * sigma
+        mus_eff = mus + sigs * (sigma - gamma * (sigma + sigs))
+        ps = np.where(mus_eff >= 0, ps_up, ps_down)
+        sigp = ps / p * sigs
+        mup = ps / p * mus + 0.5 * pss / p * (sigs * sigs)
+        kap = gamma * (sigma + sigs)
+        r = rho + gamma * mu - (gamma * kappa_s - b) / 2 + b * (sbar - s)
+        pt = -p * (1 / p + mu + mup + sigp * sigma - r - kap * (sigma + sigp))
+        return {"pt": pt}
+    return pde
+
+
+def campbell_cochrane_problem(params=None, sn=1000):
+    prm = dict(CC_DEFAULT if params is None else params)
+    s = campbell_cochrane_grid(sn=sn, **prm)
+    return {"s": s}, {"p": np.ones(s.shape[0])}, prm
+
+
+def splitmix64_uniforms(seed: int, count: int) -> np.ndarray:
+    """language-independent parameter draws for the C4 sweep."""
+    M = (1 << 64) - 1
+    state = seed & M
+    out = np.empty(count)
+    for i in range(count):
+        state = (state + 0x9E3779B97F4A7C15) & M
+        z = state
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        z = z ^ (z >> 31)
+        out[i] = (z >> 11) * 2.0 ** -53
+    return out
+
+
+def campbell_cochrane_sweep_params(index: int) -> Dict[str, float]:
+    """Problem ``index`` of the batched calibration sweep (config C4)."""
+    u = splitmix64_uniforms(0xEC0DE5 + index, 5)
+    return dict(mu=0.015 + (0.023 - 0.015) * u[0], sigma=0.012 + (0.018 - 0.012) * u[1],
+                gamma=1.5 + (2.5 - 1.5) * u[2], rho=0.09 + (0.14 - 0.09) * u[3],
+                kappa_s=0.11 + (0.17 - 0.11) * u[4], b=0.0)
+
+
+# --------------------------------------------------------------------------------------
+# C3  Bansal-Yaron long-run risk (examples/asset_pricing/bansal_yaron.jl:22-95)
+# --------------------------------------------------------------------------------------
+BY_DEFAULT = dict(mubar=0.018, vbar=0.00073, kappa_mu=0.252, nu_mu=0.528, kappa_v=0.156,
+                  nu_v=0.00354, rho=0.024, gamma=7.5, psi=1.5)
+
+
+def bansal_yaron(mubar, vbar, kappa_mu, nu_mu, kappa_v, nu_v, rho, gamma, psi):
+    def pde(state, u):
+        mu, v = state["mu"], state["v"]
+        p = u["p"]
+        muc = mu
+        sigc = np.sqrt(v)
+        mumu = kappa_mu * (mubar - mu)
+        sigmu = nu_mu * np.sqrt(v)
+        muv = kappa_v * (vbar - v)
+        sigv = nu_v * np.sqrt(v)
+        pmu = np.where(mumu >= 0, u["pmu_up"], u["pmu_down"])
+        pv = np.where(muv >= 0, u["pv_up"], u["pv_down"])
+        sigp_Zmu = pmu / p * sigmu
+        sigp_Zv = pv / p * sigv
+        sigp2 = sigp_Zmu * sigp_Zmu + sigp_Zv * sigp_Zv
+        mup = (pmu / p * mumu + pv / p * muv + 0.5 * u["pmumu"] / p * (sigmu * sigmu)
+               + 0.5 * u["pvv"] / p * (sigv * sigv))
+        kap_Zc = gamma * sigc
+        kap_Zmu = -(1 - gamma * psi) / (psi - 1) * sigp_Zmu
+        kap_Zv = -(1 - gamma * psi) / (psi - 1) * sigp_Zv
+        r = rho + muc / psi - (1 + 1 / psi) / 2 * gamma * (sigc * sigc) - (gamma * psi - 1) / (2 * (psi - 1)) * sigp2
+        pt = -p * (1 / p + muc + mup - r - kap_Zc * sigc - kap_Zmu * sigp_Zmu - kap_Zv * sigp_Zv)
+        return {"pt": pt}
+    return pde
+
+
+def bansal_yaron_problem(n_mu=30, n_v=30, params=None):
+    from scipy import stats
+    prm = dict(BY_DEFAULT if params is None else params)
+    sd = math.sqrt(prm["nu_mu"] ** 2 * prm["vbar"] / (2 * prm["kappa_mu"]))
+    mus = julia_range(stats.norm.ppf(0.01, prm["mubar"], sd), stats.norm.ppf(0.99, prm["mubar"], sd), n_mu)
+    shape = 2 * prm["kappa_v"] * prm["vbar"] / prm["nu_v"] ** 2
+    scale = prm["nu_v"] ** 2 / (2 * prm["kappa_v"])
+    vs = julia_range(0.0, stats.gamma.ppf(0.99, shape, scale=scale), n_v)
+    return {"mu": mus, "v": vs}, {"p": np.ones((n_mu, n_v))}, prm
+
+
+# --------------------------------------------------------------------------------------
+# C2  consumption-saving with diffusive income
+#     (examples/consumption_saving/consumption_saving_diffusion_income.jl:25-106)
+# --------------------------------------------------------------------------------------
+AHLM_DEFAULT = dict(kappa_y=0.1, ybar=1.0, sigma_y=0.07, r=0.03, rho=0.05, gamma=2.0, amin=0.0, amax=100.0)
+
+
+def ahlm_diffusion(kappa_y, ybar, sigma_y, r, rho, gamma, amin, amax):
+    def pde(state, u):
+        y, a = state["y"], state["a"]
+        v, vy_up, vy_down, va_up, va_down, vyy = u["v"], u["vy_up"], u["vy_down"], u["va_up"], u["va_down"], u["vyy"]
+        muy = kappa_y * (ybar - y)
+        cmax = 100.0 * (y + r * np.maximum(a, 0.0))
+        vy = np.where(muy >= 0, vy_up, vy_down)
+        c_up = np.where(va_up > 0, np.minimum(va_up ** (-1 / gamma), cmax), cmax)
+        mua_up = y + r * a - c_up
+        c_down = np.where(va_down > 0, np.minimum(va_down ** (-1 / gamma), cmax), cmax)
+        mua_down = y + r * a - c_down
+        case1 = mua_up >= 0.0
+        case2 = (~case1) & (mua_down <= 0.0) & (a > amin)
+        c3 = y + r * a
+        va3 = c3 ** (-gamma)
+        c = np.where(case1, c_up, np.where(case2, c_down, c3))
+        va = np.where(case1, va_up, np.where(case2, va_down, va3))
+        mua = np.where(case1, mua_up, np.where(case2, mua_down, 0.0))
+        vt = -(c ** (1 - gamma) / (1 - gamma) + mua * va + muy * vy + 0.5 * vyy * (sigma_y * sigma_y) - rho * v)
+        return {"vt": vt}, {"mua": mua, "c": c}
+    return pde
+
+
+def ahlm_diffusion_problem(n_y=10, n_a=1000, params=None):
+    from scipy import stats
+    prm = dict(AHLM_DEFAULT if params is None else params)
+    shape = 2 * prm["kappa_y"] * prm["ybar"] / prm["sigma_y"] ** 2
+    scale = prm["sigma_y"] ** 2 / (2 * prm["kappa_y"])
+    ys = julia_range(stats.gamma.ppf(0.001, shape, scale=scale), stats.gamma.ppf(0.999, shape, scale=scale), n_y)
+    as_ = julia_range(prm["amin"], prm["amax"], n_a)
+    g, rr, rho = prm["gamma"], prm["r"], prm["rho"]
+    Y, A = np.meshgrid(ys, as_, indexing="ij")
+    guess = (rho / g + (1 - 1 / g) * rr) ** (-g) * (A + Y / rr) ** (1 - g) / (1 - g)
+    return {"y": ys, "a": as_}, {"v": guess}, prm
+
+
+# --------------------------------------------------------------------------------------
+# C5  synthetic 3-state HJB (this repo's own definition, shared
+#     verbatim with the CUDA functor in econpdes.jl_b200/csrc/models.cuh)
+# --------------------------------------------------------------------------------------
+HJB3D_DEFAULT = dict(kx=0.2, ky=0.3, kz=0.4, sx=0.1, sy=0.1, sz=0.1, corr=0.5, rho=0.05, theta=1e-3)
+
+
+def hjb3d_synth(kx, ky, kz, sx, sy, sz, corr, rho, theta):
+    def pde(state, u):
+        x, y, z = state["x"], state["y"], state["z"]
+        v = u["v"]
+        mx = -kx * (x - 0.5)
+        my = -ky * (y - 0.5)
+        mz = -kz * (z - 0.5)
+        vx = np.where(mx >= 0, u["vx_up"], u["vx_down"])
+        vy = np.where(my >= 0, u["vy_up"], u["vy_down"])
+        vz = np.where(mz >= 0, u["vz_up"], u["vz_down"])
+        drift = mx * vx + my * vy + mz * vz
+        diff = 0.5 * (sx * sx) * u["vxx"] + 0.5 * (sy * sy) * u["vyy"] + 0.5 * (sz * sz) * u["vzz"]
+        cross = corr * sx * sy * u["vxy_up"]
+        vt = -(x + y + z + drift + diff + cross - rho * v - theta * (v * v))
+        return {"vt": vt}
+    return pde
+
+
+def hjb3d_problem(n=16, params=None):
+    prm = dict(HJB3D_DEFAULT if params is None else params)
+    g = julia_range(0.0, 1.0, n)
+    return {"x": g, "y": g.copy(), "z": g.copy()}, {"v": np.zeros((n, n, n))}, prm
+
+
+# --------------------------------------------------------------------------------------
+# Neoclassical growth: example version (examples/neoclassical_growth.jl:25-84; the 11
+# outer iterations of details.tex:173 pin the FiniteDiff epsilon rule) and the test-suite
+# version (test/runtests.jl:17-44).
+# --------------------------------------------------------------------------------------
+def growth_example_params():
+    gamma = 4.0
+    delta, alpha, A = 0.05, 0.3, 0.5
+    return dict(A=A, alpha=alpha, delta=delta, rho=delta * (alpha * gamma - 1), gamma=gamma)
+
+
+def neoclassical_growth(A, alpha, delta, rho, gamma):
+    def pde(state, u):
+        k = state["k"]
+        v, vk_up, vk_down = u["v"], u["vk_up"], u["vk_down"]
+        cap = 10 * A * k ** alpha
+        c_up = np.where(vk_up >= 0, np.minimum(vk_up ** (-1 / gamma), cap), cap)
+        muk_up = A * k ** alpha - delta * k - c_up
+        c_down = np.where(vk_down >= 0, np.minimum(vk_down ** (-1 / gamma), cap), cap)
+        muk_down = A * k ** alpha - delta * k - c_down
+        case1 = muk_up > 0
+        case2 = (~case1) & (muk_down < 0)
+        c3 = A * k ** alpha - delta * k
+        c = np.where(case1, c_up, np.where(case2, c_down, c3))
+        vk = np.where(case1, vk_up, np.where(case2, vk_down, c3 ** (-gamma)))
+        muk = np.where(case1, muk_up, np.where(case2, muk_down, 0.0))
+        vt = -(c ** (1 - gamma) / (1 - gamma) + muk * vk - rho * v)
+        return {"vt": vt}, {"c": c, "muk": muk}
+    return pde
+
+
+def neoclassical_growth_problem(n=1000, params=None):
+    prm = growth_example_params() if params is None else dict(params)
+    A, alpha, delta, rho, gamma = (prm[k] for k in ("A", "alpha", "delta", "rho", "gamma"))
+    kbar = (alpha * A / (rho + delta)) ** (1 / (1 - alpha))
+    ks = julia_range(0.1 * kbar, 5 * kbar, n)
+    guess = (A * ks ** alpha) ** (1 - gamma) / (1 - gamma) / rho
+    return {"k": ks}, {"v": guess}, prm
+
+
+GROWTH_TEST = dict(A=0.5, alpha=0.3, delta=0.05, rho=0.05, gamma=2.0)
+
+
+def growth_test_hjb(A=0.5, alpha=0.3, delta=0.05, rho=0.05, gamma=2.0):
+    """test/runtests.jl:28-44 (note: differs from the example in its branch structure)."""
+    def pde(state, u):
+        k = state["k"]
+        cmax = 10 * A * k ** alpha
+        c_up = np.where(u["vk_up"] > 0, np.minimum(u["vk_up"] ** (-1 / gamma), cmax), cmax)
+        mu_up = A * k ** alpha - delta * k - c_up
+        c_down = np.where(u["vk_down"] > 0, np.minimum(u["vk_down"] ** (-1 / gamma), cmax), cmax)
+        mu_down = A * k ** alpha - delta * k - c_down
+        case1 = mu_up > 0
+        case2 = (~case1) & (mu_down < 0)
+        c3 = A * k ** alpha - delta * k
+        c = np.where(case1, c_up, np.where(case2, c_down, c3))
+        vk = np.where(case1, u["vk_up"], np.where(case2, u["vk_down"], c3 ** (-gamma)))
+        muk = np.where(case1, mu_up, np.where(case2, mu_down, 0.0))
+        vt = -(c ** (1 - gamma) / (1 - gamma) + muk * vk - rho * u["v"])
+        return {"vt": vt}, {"c": c, "muk": muk}
+    return pde
+
+
+def growth_test_problem(n=200):
+    A, alpha, delta, rho, gamma = (GROWTH_TEST[k] for k in ("A", "alpha", "delta", "rho", "gamma"))
+    kbar = (alpha * A / (rho + delta)) ** (1 / (1 - alpha))
+    ks = julia_range(0.1 * kbar, 5.0 * kbar, n)
+    guess = (A * ks ** alpha) ** (1 - gamma) / (1 - gamma) / rho
+    return {"k": ks}, {"v": guess}, kbar
+
+
+# --------------------------------------------------------------------------------------
+# Closed-form test models (test/runtests.jl:276-281, 314-319, 379-389, 225-232)
+# --------------------------------------------------------------------------------------
+def linear_sum(statenames):
+    """vt = -(v - x - z - ...)  -> v = sum of the coordinates."""
+    def pde(state, u):
+        acc = u["v"]
+        for s in statenames:
+            acc = acc - state[s]
+        return {"vt": -acc}
+    return pde
+
+
+def forward_price():
+    """test/runtests.jl:379-384: v = 2x, p = x."""
+    def pde(state, u):
+        vt = -(state["x"] + u["p"] - u["v"])
+        pt = u["v"] / 2 - u["p"]
+        return {"vt": vt, "pt": pt}
+    return pde
+
+
+def v_minus_two():
+    """test/runtests.jl:227: vt = v - 2."""
+    def pde(state, u):
+        return {"vt": u["v"] - 2.0 + 0.0 * state["x"]}
+    return pde

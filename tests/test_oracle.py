@@ -1,0 +1,257 @@
+"""Pins the CPU oracle (oracle/) against everything the reference publishes for the hot
+path: the two iteration traces, the closed-form answers and structural facts of
+test/runtests.jl, and the 11-outer-iteration growth run of examples/details.tex:173."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import econpdes_oracle as eo
+from oracle import models as M
+
+INF = math.inf
+
+
+def _trace(res):
+    return [("%8.2e" % d, "%8.2e" % r) for (_, d, r, st, _) in res.log.rows if st == eo.ACCEPTED]
+
+
+def test_readme_quickstart_trace():
+    # README.md:72-82
+    g, gu = M.readme_linear_problem()
+    res = eo.pdesolve(M.readme_linear(), g, gu)
+    tr = _trace(res)
+    assert [t[0] for t in tr] == ["1.00e+00", "1.09e+01", "1.85e+03", "1.76e+08"]
+    assert [t[1] for t in tr[:3]] == ["7.51e-02", "4.45e-02", "4.67e-04"]
+    # last row is pure round-off of the linear solve: published 1.22e-10
+    assert abs(res.residual_norm - 1.22e-10) < 0.03e-10
+    assert res.converged and res.log.n_outer == 4 and res.tolerance == eo.SQRT_EPS
+    assert "%.2e" % res.tolerance == "1.49e-08"
+
+
+def test_campbell_cochrane_trace():
+    # docs/src/solver.md:66-73, result block :96-101
+    g, gu, prm = M.campbell_cochrane_problem()
+    assert g["s"].shape == (998,)
+    res = eo.pdesolve(M.campbell_cochrane(**prm), g, gu)
+    assert _trace(res) == [("1.00e+00", "2.51e-02"), ("1.12e+01", "1.21e-02"),
+                           ("2.33e+03", "8.01e-05"), ("3.50e+08", "3.45e-12")]
+    assert res.converged and res.log.n_newton == 8
+
+
+def test_growth_example_eleven_outer_iterations():
+    # examples/details.tex:173 -- pins the FiniteDiff per-color epsilon rule (a per-column
+    # epsilon takes 15 outer iterations)
+    g, gu, prm = M.neoclassical_growth_problem(1000)
+    res = eo.pdesolve(M.neoclassical_growth(**prm), g, gu)
+    assert res.converged and res.log.n_outer == 11
+    assert sum(1 for r in res.log.rows if r[3] != eo.ACCEPTED) == 3
+
+
+def test_growth_testset_shape_properties():
+    # test/runtests.jl:46-65
+    g, gu, kbar = M.growth_test_problem(200)
+    res = eo.pdesolve(M.growth_test_hjb(), g, gu)
+    v, c, muk = res.solution["v"], res.saved["c"], res.saved["muk"]
+    assert res.residual_norm <= 1e-6
+    assert np.all(np.diff(v) > 0) and np.all(np.diff(np.diff(v)) < 1e-8) and np.all(np.diff(c) > 0)
+    icross = int(np.argmax(muk < 0))
+    assert abs(g["k"][icross] - kbar) < 0.05 * kbar
+    assert np.array_equal(res.saved["v"], v)
+
+
+def test_mixed_grid_known_answer_2d():
+    # test/runtests.jl:269-281
+    grid = {"x": M.julia_range(0, 1, 4), "z": M.julia_range(0, 1, 5)}
+    res = eo.pdesolve(M.linear_sum(("x", "z")), grid, {"v": np.zeros((4, 5))}, delta=INF)
+    assert res.residual_norm <= 1e-8
+    np.testing.assert_allclose(res.solution["v"], grid["x"][:, None] + grid["z"][None, :], rtol=1e-12)
+    assert res.saved == {}
+
+
+def test_nd_coloring_and_4d_known_answer():
+    # test/runtests.jl:294-320
+    S = (2, 2, 2, 2)
+    colptr, rowval = eo.local_stencil_jacobian(S, 1)
+    colors = eo.stencil_colors(S, 1)
+    assert colptr.shape[0] == 17 and colors.max() == 16
+    _check_distance2(colptr, rowval, colors)
+    g4 = {k: M.julia_range(0, 1, 2) for k in "xzqr"}
+    res = eo.pdesolve(M.linear_sum(tuple("xzqr")), g4, {"v": np.zeros(S)}, delta=INF)
+    x = g4["x"]
+    want = x[:, None, None, None] + x[None, :, None, None] + x[None, None, :, None] + x[None, None, None, :]
+    assert res.converged
+    np.testing.assert_allclose(res.solution["v"], want, rtol=1e-12)
+
+
+def test_signed_per_function_delta():
+    # test/runtests.jl:375-394
+    g = {"x": M.julia_range(0.1, 1.0, 5)}
+    guess = {"v": np.zeros(5), "p": np.zeros(5)}
+    res = eo.pdesolve(M.forward_price(), g, guess, delta={"v": 1.0, "p": -1.0})
+    assert res.converged
+    np.testing.assert_allclose(res.solution["v"], 2 * g["x"], atol=1e-6)
+    np.testing.assert_allclose(res.solution["p"], g["x"], atol=1e-6)
+    res = eo.pdesolve(M.forward_price(), g, guess, delta={"v": INF, "p": -1.0})
+    assert res.converged
+    np.testing.assert_allclose(res.solution["p"], g["x"], atol=1e-6)
+    with pytest.raises(ValueError):
+        eo.pdesolve(M.forward_price(), g, guess, delta={"v": 1.0, "p": 0.0})
+
+
+def _scalar_cache(n):
+    return eo.JacobianCache((n,), 1, colptr=np.arange(1, n + 2), rowval=np.arange(1, n + 1),
+                            colors=np.ones(n, dtype=np.int64))
+
+
+def test_vector_and_negative_delta_finiteschemesolve():
+    # test/runtests.jl:404-416
+    G = lambda y: np.array([y[0] - 2.0, 3.0 - y[1]])
+    y, rn, _ = eo.finiteschemesolve(G, np.zeros(2), _scalar_cache(2), delta=np.array([1.0, -1.0]))
+    np.testing.assert_allclose(y, [2.0, 3.0], atol=1e-6)
+    assert rn <= 1e-6
+    y, rn, _ = eo.finiteschemesolve(lambda y: 3.0 - y, np.zeros(1), _scalar_cache(1), delta=-1.0)
+    np.testing.assert_allclose(y, [3.0], atol=1e-6)
+    with pytest.raises(ValueError):
+        eo.finiteschemesolve(G, np.zeros(2), _scalar_cache(2), delta=np.array([1.0]))
+    with pytest.raises(ValueError):
+        eo.finiteschemesolve(G, np.zeros(2), _scalar_cache(2), delta=0.0)
+
+
+def test_residual_growth_guard():
+    # test/runtests.jl:422-431
+    hump = lambda y: y - y ** 3
+    _, rn, _ = eo.finiteschemesolve(hump, np.array([0.6]), _scalar_cache(1), delta=0.1)
+    assert rn <= eo.SQRT_EPS
+    _, rn, log = eo.finiteschemesolve(hump, np.array([0.6]), _scalar_cache(1), delta=0.1, max_residual_growth=1.0)
+    assert not (rn <= eo.SQRT_EPS) and log.exit_reason == eo.EXIT_BELOW_MIN_DELTA
+
+
+def test_mcp_lower_bound_known_answer():
+    # test/runtests.jl:225-232 and :440-450
+    g = {"x": M.julia_range(0, 1, 5)}
+    res = eo.pdesolve(M.v_minus_two(), g, {"v": np.zeros(5)}, delta=INF, lower_bound={"v": np.full(5, 3.0)})
+    np.testing.assert_allclose(res.solution["v"], 3.0)
+    y, rn, _ = eo.finiteschemesolve(lambda y: y - 2.0, np.array([0.5]), _scalar_cache(1), delta=INF,
+                                    lower_bound=np.array([0.0]), upper_bound=np.array([1.0]))
+    assert abs(y[0] - 1.0) < 1e-6 and rn <= 1e-6
+
+
+def test_nan_at_guess_raises():
+    # src/finiteschemesolve.jl:372
+    with pytest.raises(ValueError, match="NaN"):
+        eo.finiteschemesolve(lambda y: y * np.nan, np.ones(1), _scalar_cache(1))
+
+
+def test_already_zero():
+    # src/finiteschemesolve.jl:373-376
+    y, rn, log = eo.finiteschemesolve(lambda y: y * 0.0, np.ones(1), _scalar_cache(1))
+    assert log.exit_reason == eo.EXIT_ALREADY_ZERO and rn == 0.0
+
+
+def test_maxiters_one_does_not_converge():
+    # test/runtests.jl:162-192 (converged flag false with maxiters = 1)
+    g, gu, _ = M.growth_test_problem(50)
+    res = eo.pdesolve(M.growth_test_hjb(), g, gu, maxiters=1)
+    assert not res.converged and res.log.exit_reason == eo.EXIT_MAXITERS
+
+
+def _check_distance2(colptr, rowval, colors):
+    n = colptr.shape[0] - 1
+    col_of = np.repeat(np.arange(n), np.diff(colptr))
+    order = np.argsort(rowval, kind="stable")
+    rows_sorted, cols_sorted = rowval[order], col_of[order]
+    bounds = np.flatnonzero(np.diff(rows_sorted)) + 1
+    for cols in np.split(cols_sorted, bounds):
+        cc = colors[cols]
+        assert len(set(cc.tolist())) == len(cc)
+
+
+def test_2d_multifunction_sparsity_520():
+    # test/runtests.jl:491-502
+    colptr, rowval = eo.local_stencil_jacobian((4, 5), 2)
+    assert colptr.shape[0] - 1 == 40 and rowval.shape[0] == 520
+
+
+@pytest.mark.parametrize("S,F", [((5,), 1), ((2,), 2), ((4, 5), 2), ((2, 5), 1), ((3, 4, 5), 2)])
+def test_stencil_colors(S, F):
+    # test/runtests.jl:509-524
+    colptr, rowval = eo.local_stencil_jacobian(S, F)
+    colors = eo.stencil_colors(S, F)
+    _check_distance2(colptr, rowval, colors)
+    assert colors.max() == F * int(np.prod([min(3, s) for s in S]))
+    assert sorted(set(colors.tolist())) == list(range(1, colors.max() + 1))
+    assert rowval.shape[0] == F * F * int(np.prod([3 * s - 2 for s in S]))
+    # rows sorted inside every column, 1-based
+    for j in range(colptr.shape[0] - 1):
+        r = rowval[colptr[j] - 1:colptr[j + 1] - 1]
+        assert np.all(np.diff(r) > 0) and r.min() >= 1
+
+
+def test_pattern_matches_bruteforce():
+    # literal transcription of coloring.jl:18-35 on a small 3-D case
+    import itertools
+    S, F = (3, 2, 4), 2
+    l = int(np.prod(S))
+    lin = lambda c: c[0] + S[0] * (c[1] + S[1] * c[2])
+    ent = set()
+    for fout in range(F):
+        for ci in itertools.product(*[range(s) for s in S]):
+            row = lin(ci) + fout * l
+            for fin in range(F):
+                for nb in itertools.product(*[range(max(c - 1, 0), min(c + 1, s - 1) + 1) for c, s in zip(ci, S)]):
+                    ent.add((row, lin(nb) + fin * l))
+    colptr, rowval = eo.local_stencil_jacobian(S, F)
+    got = set()
+    for j in range(l * F):
+        for r in rowval[colptr[j] - 1:colptr[j + 1] - 1]:
+            got.add((int(r) - 1, j))
+    assert got == ent
+
+
+@pytest.mark.parametrize("S,F", [((6,), 1), ((4, 5), 2), ((3, 4, 3), 1), ((2, 3), 1)])
+def test_vectorised_stencils_match_pointwise(S, F):
+    rng = np.random.default_rng(7)
+    N = len(S)
+    statenames = ["x", "z", "q"][:N]
+    solnames = ["v", "w"][:F]
+    grids = [np.cumsum(rng.uniform(0.1, 1.0, s)) for s in S]   # non-uniform
+    y = rng.normal(size=S + (F,))
+    bc = rng.normal(size=S + (F,))
+    u = eo.differentiate(solnames, statenames, grids, y, bc)
+    for icar in np.ndindex(*S):
+        up = eo.differentiate_point(solnames, statenames, grids, y, icar, bc)
+        assert set(up) == set(u)
+        for key, val in up.items():
+            assert u[key][icar] == val, (key, icar)
+    nfields = 1 + 3 * N + 3 * N * (N - 1) // 2
+    assert len(u) == F * nfields
+
+
+def test_bc_array_quirk():
+    # src/pdesolve.jl:312-335: one slot per (point, unknown); later dimensions overwrite
+    out = eo.bc_array({"vx": (1.0, 2.0), "vz": (3.0, 4.0)}, ("v",), ("x", "z"), (3, 4))
+    assert out[0, 1, 0] == 1.0 and out[2, 1, 0] == 2.0
+    assert out[0, 0, 0] == 3.0 and out[2, 3, 0] == 4.0   # corners: z wins
+    assert out[1, 1, 0] == 0.0
+    with pytest.raises(ValueError):
+        eo.bc_array({"vk": (0, 0)}, ("v",), ("x",), (3,))
+
+
+def test_splitmix_sweep_params_are_in_range():
+    p0 = M.campbell_cochrane_sweep_params(0)
+    p1 = M.campbell_cochrane_sweep_params(1)
+    assert p0 != p1
+    assert 0.015 <= p0["mu"] <= 0.023 and 0.11 <= p0["kappa_s"] <= 0.17 and p0["b"] == 0.0
+    # splitmix64 known answer: seed 0 -> first output 0xE220A8397B1DCDAF
+    z = M.splitmix64_uniforms(0, 1)[0]
+    assert z == (0xE220A8397B1DCDAF >> 11) * 2.0 ** -53
+
+
+def test_sweep_problems_converge_like_the_default():
+    # every sweep problem takes 4 outer steps / 8 Newton iterations
+    for idx in (0, 1, 17):
+        prm = M.campbell_cochrane_sweep_params(idx)
+        g, gu, _ = M.campbell_cochrane_problem(prm)
+        res = eo.pdesolve(M.campbell_cochrane(**prm), g, gu)
+        assert res.converged and res.log.n_outer == 4 and res.log.n_newton == 8
