@@ -1,0 +1,222 @@
+// Per-grid-point building blocks shared by every kernel of the hot path:
+//   * gather the +-1 box of an unknown around a point            (pde!, pdesolve.jl:443-447)
+//   * evaluate the model residual there                          (pdesolve.jl:448-454)
+//   * the implicit-Euler / MCP residual                          (finiteschemesolve.jl:158-162, 197-203)
+//   * one block-row of the colored finite-difference Jacobian    (FiniteDiff forward mode,
+//     called at finiteschemesolve.jl:184) in the fused row-wise form: because the coloring
+//     of coloring.jl:52-70 is distance-2, a row sees at most one perturbed column per
+//     color, so perturbing the box slots one at a time with that column's color epsilon
+//     reproduces the C global sweeps entry for entry.
+// Everything is __host__ __device__ so tests/host_emu can run the identical code on the
+// CPU of the build container (which has no GPU); the shipped library has no CPU path.
+#pragma once
+#include "models.cuh"
+
+namespace econpdes {
+
+constexpr int kMaxDims = 3;
+constexpr double kSqrtEps = 1.4901161193847656e-8;
+
+// Tensor grid: per-dimension coordinate vectors, sizes and column-major strides.
+template <int N>
+struct GridView {
+  const double* x[N];
+  long long S[N];
+  long long stride[N];
+  long long l;  // number of grid points
+};
+
+// Stencil shapes: the full clipped +-1 box (coloring.jl:18-35) or, for models that never
+// read a cross derivative, its star subset (centre + 2N axial neighbours).
+template <int N, bool BOX>
+struct Stencil {
+  static constexpr int NK = BOX ? ipow3(N) : 1 + 2 * N;
+  EP_HD static constexpr int off(int k, int d) {
+    if (BOX) return (k / ipow3(d)) % 3 - 1;
+    if (k == 0) return 0;
+    return ((k - 1) / 2 == d) ? (((k - 1) % 2) ? 1 : -1) : 0;
+  }
+  EP_HD static constexpr int boxslot(int k) {
+    if (BOX) return k;
+    int s = (ipow3(N) - 1) / 2;
+    if (k == 0) return s;
+    return s + (((k - 1) % 2) ? 1 : -1) * ipow3((k - 1) / 2);
+  }
+};
+
+template <int N>
+EP_HD void unravel(long long pt, const GridView<N>& gv, long long* idx) {
+#pragma unroll
+  for (int d = 0; d < N; ++d) {
+    idx[d] = pt % gv.S[d];
+    pt /= gv.S[d];
+  }
+}
+
+template <int N>
+EP_HD void load_geom(const GridView<N>& gv, const long long* idx, PointGeom<N>& g, double* state) {
+#pragma unroll
+  for (int d = 0; d < N; ++d) {
+    spacing(gv.x[d], idx[d], gv.S[d], g.dm[d], g.dp[d], g.d[d]);
+    g.lo[d] = idx[d] == 0;
+    g.hi[d] = idx[d] == gv.S[d] - 1;
+    state[d] = gv.x[d][idx[d]];
+  }
+}
+
+// Gather the 3^N box of unknown f around point pt (slots outside the grid are never read
+// by `differentiate`; they are filled with the centre value).
+template <int N>
+EP_HD void load_box(const double* __restrict__ yf, long long pt, const GridView<N>& gv, const PointGeom<N>& g,
+                    double* w) {
+  constexpr int K = ipow3(N);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    long long q = pt;
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      const int o = (k / ipow3(d)) % 3 - 1;
+      if ((o < 0 && g.lo[d]) || (o > 0 && g.hi[d])) ok = false;
+      q += o * gv.stride[d];
+    }
+    w[k] = yf[ok ? q : pt];
+  }
+}
+
+// bc[i1.., (first|last) along d, ..iN, f] keeping the other indices (derivatives.jl:27-32).
+template <int N>
+EP_HD void load_bc(const double* __restrict__ bcf, long long pt, const long long* idx, const GridView<N>& gv,
+                   const PointGeom<N>& g, double* bc_lo, double* bc_hi) {
+#pragma unroll
+  for (int d = 0; d < N; ++d) {
+    bc_lo[d] = 0.0;
+    bc_hi[d] = 0.0;
+    if (bcf != nullptr) {
+      if (g.lo[d]) bc_lo[d] = bcf[pt];  // the point itself sits on the low face
+      if (g.hi[d]) bc_hi[d] = bcf[pt];
+    }
+  }
+  (void)idx;
+  (void)gv;
+}
+
+// The row-local description of the implicit-Euler / MCP wrapper around G
+// (finiteschemesolve.jl:158-162, 197-203).  `delta` already includes the signed relative
+// profile (stepper.Δ .* Δrel).
+struct RowTerms {
+  bool implicit;   // subtract (ypost - y)/delta on non-algebraic rows
+  bool has_bounds; // min(max(R, y-ub), y-lb)
+  double ypost, delta, lb, ub;
+  bool is_alg;
+};
+
+EP_HD double apply_row_terms(double g, double y, const RowTerms& t) {
+  double r = g;
+  // `.!is_algebraic .* (ypost .- y) ./ Δ`: Bool true is an exact 1, false a strong zero
+  if (t.implicit && !t.is_alg) r = r - (t.ypost - y) / t.delta;
+  if (t.has_bounds) {
+    const double a = y - t.ub, b = y - t.lb;
+    double m = r > a ? r : a;      // max(r, y-ub)   (NaN in r propagates like Julia's max)
+    if (r != r) m = r;
+    r = m < b ? m : b;             // min(., y-lb)
+    if (m != m) r = m;
+  }
+  return r;
+}
+
+// Residual of all F unknowns at one point from the boxes w[f][3^N].
+template <class M, bool SAVE>
+EP_HD void eval_point(const double* prm, const double* state, const PointGeom<M::N>& g,
+                      const double (*w)[ipow3(M::N)], const double (*bc_lo)[M::N], const double (*bc_hi)[M::N],
+                      double* out, double* sv) {
+  Deriv<M::N> u[M::F];
+#pragma unroll
+  for (int f = 0; f < M::F; ++f) differentiate<M::N>(w[f], g, bc_lo[f], bc_hi[f], u[f]);
+  M::template eval<SAVE>(prm, state, u, out, sv);
+}
+
+// FiniteDiff's step: sqrt(eps) * max(1, sqrt(||x .* mask_c||_2)); the kernel receives the
+// per-color table.  With eps_policy = per-column the step is sqrt(eps)*max(1,|x_j|).
+EP_HD double color_epsilon_from_sumsq(double sumsq) {
+  const double nrm = sqrt(sumsq);
+  const double e = kSqrtEps * fabs(sqrt(nrm));
+  return e > kSqrtEps ? e : kSqrtEps;
+}
+
+template <int N>
+EP_HD int point_color0(const long long* idx, const GridView<N>& gv) {  // 0-based grid color
+  int base = 0, stride = 1;
+#pragma unroll
+  for (int d = 0; d < N; ++d) {
+    base += static_cast<int>(idx[d] % 3) * stride;
+    stride *= gv.S[d] < 3 ? static_cast<int>(gv.S[d]) : 3;
+  }
+  return base;
+}
+
+template <int N>
+EP_HD int ncolors_grid(const GridView<N>& gv) {
+  int stride = 1;
+#pragma unroll
+  for (int d = 0; d < N; ++d) stride *= gv.S[d] < 3 ? static_cast<int>(gv.S[d]) : 3;
+  return stride;
+}
+
+// One block-row of the Jacobian of R = rowterms(G).  `emit(k, fin, fout, value)` receives
+// d R_fout(pt) / d y_fin(pt + off_k) for every stencil entry k of shape <N,BOX> (zero for
+// entries outside the grid).  r0 returns R(pt) itself (the unperturbed residual).
+template <class M, bool BOX, class Emit>
+EP_HD void jacobian_point(const double* prm, const double* state, const PointGeom<M::N>& g, const long long* idx,
+                          const GridView<M::N>& gv, double (*w)[ipow3(M::N)], const double (*bc_lo)[M::N],
+                          const double (*bc_hi)[M::N], const RowTerms* rt, const double* eps_table,
+                          int eps_per_column, double* r0, Emit emit) {
+  constexpr int N = M::N, F = M::F;
+  constexpr int C = (ipow3(N) - 1) / 2;
+  using St = Stencil<N, BOX>;
+  double g0[F];
+  eval_point<M, false>(prm, state, g, w, bc_lo, bc_hi, g0, nullptr);
+#pragma unroll
+  for (int f = 0; f < F; ++f) r0[f] = apply_row_terms(g0[f], w[f][C], rt[f]);
+  const int ncg = ncolors_grid<N>(gv);
+#pragma unroll
+  for (int fin = 0; fin < F; ++fin) {
+#pragma unroll
+    for (int k = 0; k < St::NK; ++k) {
+      bool ok = true;
+      int color = 0, stride = 1;
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        const int o = St::off(k, d);
+        if ((o < 0 && g.lo[d]) || (o > 0 && g.hi[d])) ok = false;
+        color += static_cast<int>((idx[d] + o + 3) % 3) * stride;
+        stride *= gv.S[d] < 3 ? static_cast<int>(gv.S[d]) : 3;
+      }
+      if (!ok) {
+#pragma unroll
+        for (int fout = 0; fout < F; ++fout) emit(k, fin, fout, 0.0);
+        continue;
+      }
+      const int slot = St::boxslot(k);
+      const double saved = w[fin][slot];
+      double eps;
+      if (eps_per_column) {
+        const double a = fabs(saved);
+        eps = kSqrtEps * (a > 1.0 ? a : 1.0);
+      } else {
+        eps = eps_table[color + fin * ncg];
+      }
+      w[fin][slot] = saved + eps;
+      double g1[F];
+      eval_point<M, false>(prm, state, g, w, bc_lo, bc_hi, g1, nullptr);
+#pragma unroll
+      for (int fout = 0; fout < F; ++fout) {
+        const double r1 = apply_row_terms(g1[fout], w[fout][C], rt[fout]);
+        emit(k, fin, fout, (r1 - r0[fout]) / eps);
+      }
+      w[fin][slot] = saved;
+    }
+  }
+}
+
+}  // namespace econpdes

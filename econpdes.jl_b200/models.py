@@ -1,0 +1,181 @@
+"""Registered models: the host-side mirror of the `__device__` functors in csrc/models.cuh.
+
+In the reference a model is any callable `pde(state, u)` (README.md:58-67); the examples
+use callable structs of Float64 fields (e.g. examples/asset_pricing/bansal_yaron.jl:22-32).
+A GPU backend cannot run an opaque host closure per grid point, so -- as BASELINE.json's
+north star prescribes -- each supported example model is a *registered* functor selected by
+the type of `pde`.  The dataclasses below carry exactly the reference structs' fields
+(same names transliterated to ASCII, same defaults) and know their parameter-vector
+layout, state names and unknown names.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, fields
+from typing import ClassVar, Tuple
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class RegisteredModel:
+    name: ClassVar[str] = ""
+    statenames: ClassVar[Tuple[str, ...]] = ()
+    solnames: ClassVar[Tuple[str, ...]] = ()
+    savednames: ClassVar[Tuple[str, ...]] = ()
+
+    def params(self) -> np.ndarray:
+        return np.array([float(getattr(self, f.name)) for f in fields(self)], dtype=np.float64)
+
+    @property
+    def ndims(self) -> int:
+        return len(self.statenames)
+
+    @property
+    def nfuncs(self) -> int:
+        return len(self.solnames)
+
+
+@dataclass(frozen=True)
+class ReadmeLinear(RegisteredModel):
+    """README.md:48-67."""
+    rho: float = 0.05
+    kappa: float = 0.2
+    name: ClassVar[str] = "readme_linear"
+    statenames: ClassVar = ("x",)
+    solnames: ClassVar = ("v",)
+
+
+@dataclass(frozen=True)
+class CampbellCochraneModel(RegisteredModel):
+    """examples/asset_pricing/campbell_cochrane.jl:28-35."""
+    mu: float = 0.0189
+    sigma: float = 0.015
+    gamma: float = 2.0
+    rho: float = 0.116
+    kappa_s: float = 0.138
+    b: float = 0.0
+    name: ClassVar[str] = "campbell_cochrane"
+    statenames: ClassVar = ("s",)
+    solnames: ClassVar = ("p",)
+
+
+@dataclass(frozen=True)
+class BansalYaronModel(RegisteredModel):
+    """examples/asset_pricing/bansal_yaron.jl:22-32."""
+    mubar: float = 0.018
+    vbar: float = 0.00073
+    kappa_mu: float = 0.252
+    nu_mu: float = 0.528
+    kappa_v: float = 0.156
+    nu_v: float = 0.00354
+    rho: float = 0.024
+    gamma: float = 7.5
+    psi: float = 1.5
+    name: ClassVar[str] = "bansal_yaron"
+    statenames: ClassVar = ("mu", "v")
+    solnames: ClassVar = ("p",)
+
+
+@dataclass(frozen=True)
+class AchdouHanLasryLionsMollModel_Diffusion(RegisteredModel):
+    """examples/consumption_saving/consumption_saving_diffusion_income.jl:25-34."""
+    kappa_y: float = 0.1
+    ybar: float = 1.0
+    sigma_y: float = 0.07
+    r: float = 0.03
+    rho: float = 0.05
+    gamma: float = 2.0
+    amin: float = 0.0
+    amax: float = 100.0
+    name: ClassVar[str] = "ahlm_diffusion"
+    statenames: ClassVar = ("y", "a")
+    solnames: ClassVar = ("v",)
+    savednames: ClassVar = ("mua", "c")
+
+
+@dataclass(frozen=True)
+class Hjb3dSynth(RegisteredModel):
+    """Synthetic 3-state HJB of config C5."""
+    kx: float = 0.2
+    ky: float = 0.3
+    kz: float = 0.4
+    sx: float = 0.1
+    sy: float = 0.1
+    sz: float = 0.1
+    corr: float = 0.5
+    rho: float = 0.05
+    theta: float = 1e-3
+    name: ClassVar[str] = "hjb3d_synth"
+    statenames: ClassVar = ("x", "y", "z")
+    solnames: ClassVar = ("v",)
+
+
+@dataclass(frozen=True)
+class NeoclassicalGrowthModel(RegisteredModel):
+    """examples/neoclassical_growth.jl:25-31."""
+    A: float = 0.5
+    alpha: float = 0.3
+    delta: float = 0.05
+    rho: float = 0.05
+    gamma: float = 2.0
+    name: ClassVar[str] = "neoclassical_growth"
+    statenames: ClassVar = ("k",)
+    solnames: ClassVar = ("v",)
+    savednames: ClassVar = ("c", "muk")
+
+
+@dataclass(frozen=True)
+class GrowthTest(RegisteredModel):
+    """test/runtests.jl:17-44."""
+    A: float = 0.5
+    alpha: float = 0.3
+    delta: float = 0.05
+    rho: float = 0.05
+    gamma: float = 2.0
+    name: ClassVar[str] = "growth_test"
+    statenames: ClassVar = ("k",)
+    solnames: ClassVar = ("v",)
+    savednames: ClassVar = ("c", "muk")
+
+
+@dataclass(frozen=True)
+class LinearSum1D(RegisteredModel):
+    name: ClassVar[str] = "linear_sum_1d"
+    statenames: ClassVar = ("x",)
+    solnames: ClassVar = ("v",)
+
+
+@dataclass(frozen=True)
+class LinearSum2D(RegisteredModel):
+    """test/runtests.jl:276-279."""
+    name: ClassVar[str] = "linear_sum_2d"
+    statenames: ClassVar = ("x", "z")
+    solnames: ClassVar = ("v",)
+
+
+@dataclass(frozen=True)
+class LinearSum3D(RegisteredModel):
+    name: ClassVar[str] = "linear_sum_3d"
+    statenames: ClassVar = ("x", "z", "q")
+    solnames: ClassVar = ("v",)
+
+
+@dataclass(frozen=True)
+class ForwardPrice(RegisteredModel):
+    """test/runtests.jl:379-384."""
+    name: ClassVar[str] = "forward_price"
+    statenames: ClassVar = ("x",)
+    solnames: ClassVar = ("v", "p")
+
+
+@dataclass(frozen=True)
+class VMinusTwo(RegisteredModel):
+    """test/runtests.jl:227."""
+    name: ClassVar[str] = "v_minus_two"
+    statenames: ClassVar = ("x",)
+    solnames: ClassVar = ("v",)
+
+
+ALL_MODELS = (ReadmeLinear, CampbellCochraneModel, BansalYaronModel, AchdouHanLasryLionsMollModel_Diffusion,
+              Hjb3dSynth, NeoclassicalGrowthModel, GrowthTest, LinearSum1D, LinearSum2D, LinearSum3D,
+              ForwardPrice, VMinusTwo)

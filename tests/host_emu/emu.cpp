@@ -1,0 +1,129 @@
+// TEST INFRASTRUCTURE: runs the product's __host__ __device__ per-point code
+// (csrc/stencil.cuh, models.cuh, pointops.cuh) in plain CPU loops so that the stencil,
+// functor and fused-Jacobian arithmetic can be checked against the oracle in the build
+// container, which has no GPU.  Not linked into libeconpdes_cuda.so; not a fallback.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "pointops.cuh"
+
+using namespace econpdes;
+
+namespace {
+
+template <class M>
+GridView<M::N> make_grid(const long long* S, const double* const* grids) {
+  GridView<M::N> gv;
+  long long st = 1;
+  for (int d = 0; d < M::N; ++d) {
+    gv.x[d] = grids[d];
+    gv.S[d] = S[d];
+    gv.stride[d] = st;
+    st *= S[d];
+  }
+  gv.l = st;
+  return gv;
+}
+
+template <class M>
+int residual(const long long* S, const double* const* grids, const double* prm, const double* y, const double* bc,
+             double* out, double* saved) {
+  constexpr int N = M::N, F = M::F, K = ipow3(N);
+  auto gv = make_grid<M>(S, grids);
+  for (long long pt = 0; pt < gv.l; ++pt) {
+    long long idx[N];
+    unravel<N>(pt, gv, idx);
+    PointGeom<N> g;
+    double st[N];
+    load_geom<N>(gv, idx, g, st);
+    double w[F][K], bl[F][N], bh[F][N];
+    for (int f = 0; f < F; ++f) {
+      load_box<N>(y + f * gv.l, pt, gv, g, w[f]);
+      load_bc<N>(bc ? bc + f * gv.l : nullptr, pt, idx, gv, g, bl[f], bh[f]);
+    }
+    double o[F], sv[M::NSAVED > 0 ? M::NSAVED : 1];
+    if (saved) eval_point<M, true>(prm, st, g, w, bl, bh, o, sv);
+    else eval_point<M, false>(prm, st, g, w, bl, bh, o, sv);
+    for (int f = 0; f < F; ++f) out[f * gv.l + pt] = o[f];
+    if (saved) for (int s = 0; s < M::NSAVED; ++s) saved[s * gv.l + pt] = sv[s];
+  }
+  return 0;
+}
+
+template <class M, bool BOX>
+int jacobian(const long long* S, const double* const* grids, const double* prm, const double* y, const double* bc,
+             const double* ypost, double delta, const double* eps_table, int eps_per_column, double* planes,
+             double* r0out) {
+  constexpr int N = M::N, F = M::F, K = ipow3(N);
+  auto gv = make_grid<M>(S, grids);
+  for (long long pt = 0; pt < gv.l; ++pt) {
+    long long idx[N];
+    unravel<N>(pt, gv, idx);
+    PointGeom<N> g;
+    double st[N];
+    load_geom<N>(gv, idx, g, st);
+    double w[F][K], bl[F][N], bh[F][N];
+    RowTerms rt[F];
+    for (int f = 0; f < F; ++f) {
+      load_box<N>(y + f * gv.l, pt, gv, g, w[f]);
+      load_bc<N>(bc ? bc + f * gv.l : nullptr, pt, idx, gv, g, bl[f], bh[f]);
+      rt[f].implicit = ypost != nullptr;
+      rt[f].has_bounds = false;
+      rt[f].ypost = ypost ? ypost[f * gv.l + pt] : 0.0;
+      rt[f].delta = delta;
+      rt[f].is_alg = false;
+      rt[f].lb = rt[f].ub = 0.0;
+    }
+    double r0[F];
+    const long long l = gv.l;
+    jacobian_point<M, BOX>(prm, st, g, idx, gv, w, bl, bh, rt, eps_table, eps_per_column, r0,
+                           [&](int k, int fin, int fout, double v) { planes[((long long)(k * F + fin) * F + fout) * l + pt] = v; });
+    for (int f = 0; f < F; ++f) r0out[f * l + pt] = r0[f];
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int emu_model_count() {
+  int n = 0;
+#define X(M) ++n;
+  ECONPDES_FOR_EACH_MODEL(X)
+#undef X
+  return n;
+}
+
+int emu_model_id(const char* name) {
+  int id = 0;
+#define X(M) if (std::strcmp(name, M::name()) == 0) return id; ++id;
+  ECONPDES_FOR_EACH_MODEL(X)
+#undef X
+  return -1;
+}
+
+int emu_residual(int model_id, const long long* S, const double* const* grids, const double* prm, const double* y,
+                 const double* bc, double* out, double* saved) {
+  int id = 0;
+#define X(M) if (id++ == model_id) return residual<M>(S, grids, prm, y, bc, out, saved);
+  ECONPDES_FOR_EACH_MODEL(X)
+#undef X
+  return -1;
+}
+
+// box != 0: full 3^N stencil planes; box == 0: star planes (1 + 2N)
+int emu_jacobian(int model_id, int box, const long long* S, const double* const* grids, const double* prm,
+                 const double* y, const double* bc, const double* ypost, double delta, const double* eps_table,
+                 int eps_per_column, double* planes, double* r0) {
+  int id = 0;
+#define X(M)                                                                                                  \
+  if (id++ == model_id)                                                                                       \
+    return box ? jacobian<M, true>(S, grids, prm, y, bc, ypost, delta, eps_table, eps_per_column, planes, r0) \
+               : jacobian<M, false>(S, grids, prm, y, bc, ypost, delta, eps_table, eps_per_column, planes, r0);
+  ECONPDES_FOR_EACH_MODEL(X)
+#undef X
+  return -1;
+}
+}

@@ -1,0 +1,121 @@
+"""No-GPU checks of the product's per-point device code (stencils, functors, fused
+row-wise colored-FD Jacobian), compiled for the host by tests/host_emu, against the oracle."""
+import math
+
+import numpy as np
+import pytest
+
+import econpdes_b200  # noqa: F401
+from econpdes_b200 import models as PM
+from oracle import econpdes_oracle as eo
+from oracle import models as OM
+from tests import emu_util as EU
+
+
+def _cases():
+    out = []
+    g, gu = OM.readme_linear_problem(50)
+    out.append(("readme", PM.ReadmeLinear(), OM.readme_linear(), g, gu))
+    g, gu, prm = OM.campbell_cochrane_problem(sn=200)
+    out.append(("cc", PM.CampbellCochraneModel(**prm), OM.campbell_cochrane(**prm), g, gu))
+    g, gu, prm = OM.bansal_yaron_problem(17, 13)
+    out.append(("by", PM.BansalYaronModel(**prm), OM.bansal_yaron(**prm), g, gu))
+    g, gu, prm = OM.ahlm_diffusion_problem(7, 40)
+    out.append(("ahlm", PM.AchdouHanLasryLionsMollModel_Diffusion(**prm), OM.ahlm_diffusion(**prm), g, gu))
+    g, gu, prm = OM.hjb3d_problem(6)
+    gu = {"v": 20.0 + np.zeros((6, 6, 6))}
+    out.append(("hjb3d", PM.Hjb3dSynth(**prm), OM.hjb3d_synth(**prm), g, gu))
+    g, gu, prm = OM.neoclassical_growth_problem(60)
+    out.append(("growth", PM.NeoclassicalGrowthModel(**prm), OM.neoclassical_growth(**prm), g, gu))
+    g, gu, _ = OM.growth_test_problem(40)
+    out.append(("growth_test", PM.GrowthTest(), OM.growth_test_hjb(), g, gu))
+    g = {"x": OM.julia_range(0, 1, 4), "z": OM.julia_range(0, 1, 5)}
+    out.append(("lin2d", PM.LinearSum2D(), OM.linear_sum(("x", "z")), g, {"v": np.zeros((4, 5))}))
+    g = {"x": OM.julia_range(0.1, 1, 5)}
+    out.append(("fwdprice", PM.ForwardPrice(), OM.forward_price(), g, {"v": np.ones(5), "p": np.ones(5) * 0.5}))
+    return out
+
+
+CASES = _cases()
+POW_MODELS = ("ahlm", "growth", "growth_test")
+
+
+def _perturbed(gu, seed=1):
+    rng = np.random.default_rng(seed)
+    return np.stack([v * (1 + 0.01 * rng.uniform(-1, 1, v.shape)) + 1e-3 * rng.uniform(-1, 1, v.shape)
+                     for v in gu.values()], axis=-1)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_residual_matches_oracle(case):
+    _, pm, om, g, gu = case
+    grids = list(g.values())
+    y = _perturbed(gu)
+    prob = eo.Problem(om, tuple(g), grids, tuple(gu))
+    want = prob.G(y.reshape(-1, order="F")).reshape(y.shape, order="F")
+    got = EU.residual(pm, grids, y)
+    if case[0] in POW_MODELS:
+        # numpy's vectorised pow and libm's pow differ by an ulp on a few inputs
+        np.testing.assert_allclose(got, want, rtol=0, atol=8 * np.finfo(float).eps * np.abs(want).max())
+    else:
+        # same operand order, IEEE +,-,*,/,sqrt only: bit-exact
+        np.testing.assert_array_equal(got, want)
+
+
+def test_residual_with_bc_matches_oracle():
+    pm, om = PM.Hjb3dSynth(), OM.hjb3d_synth(**OM.HJB3D_DEFAULT)
+    rng = np.random.default_rng(3)
+    grids = [np.cumsum(rng.uniform(0.05, 0.2, s)) for s in (5, 4, 6)]
+    y = rng.normal(size=(5, 4, 6, 1)) + 10
+    bc = rng.normal(size=(5, 4, 6, 1))
+    prob = eo.Problem(om, ("x", "y", "z"), grids, ("v",), bc)
+    want = prob.G(y.reshape(-1, order="F")).reshape(y.shape, order="F")
+    np.testing.assert_array_equal(EU.residual(pm, grids, y, bc=bc), want)
+
+
+def test_saved_outputs_match_oracle():
+    _, pm, om, g, gu = [c for c in CASES if c[0] == "ahlm"][0]
+    grids = list(g.values())
+    y = _perturbed(gu)
+    prob = eo.Problem(om, tuple(g), grids, tuple(gu))
+    sv = prob.saved(y.reshape(-1, order="F"))
+    _, got = EU.residual(pm, grids, y, saved=True)
+    np.testing.assert_allclose(got[..., 0], sv["mua"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(got[..., 1], sv["c"], rtol=1e-14)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("delta", [1.0, math.inf])
+def test_fused_jacobian_matches_colored_fd(case, delta):
+    """The fused row-wise Jacobian equals FiniteDiff's C global sweeps entry for entry
+    (up to the <=1 ulp x1 drift of the +eps/-eps restoration, SURVEY.md hard part 5)."""
+    name, pm, om, g, gu = case
+    grids = list(g.values())
+    S = tuple(len(x) for x in grids)
+    F = len(gu)
+    y = _perturbed(gu)
+    yvec = y.reshape(-1, order="F")
+    ypost = _perturbed(gu, seed=2)
+    ypvec = ypost.reshape(-1, order="F")
+    prob = eo.Problem(om, tuple(g), grids, tuple(gu))
+    cache = eo.JacobianCache(S, F)
+
+    def R(v):
+        with np.errstate(all="ignore"):
+            return prob.G(v) - (ypvec - v) / delta
+    nz_want, eps = eo.finite_difference_jacobian(R, yvec, cache)
+    box = name == "hjb3d"
+    planes, r0 = EU.jacobian_planes(pm, grids, y, ypost, delta, eps, box)
+    if name in POW_MODELS:
+        np.testing.assert_allclose(r0, R(yvec), rtol=0, atol=8 * np.finfo(float).eps * np.abs(r0).max())
+    else:
+        np.testing.assert_array_equal(r0, R(yvec))
+    nz_got = EU.planes_to_csc(planes, S, F, box, cache.colptr, cache.rowval)
+    scale = np.abs(nz_want).max()
+    # drift of x1 by 1 ulp changes (f(x1)-f(x))/eps by ~ulp(y)*|J|/eps ~ 1e-8 relative
+    np.testing.assert_allclose(nz_got, nz_want, rtol=0, atol=2e-6 * scale)
+    if not box and pm.ndims > 1:
+        # corners of the box are exact structural zeros for star models
+        full, _ = EU.jacobian_planes(pm, grids, y, ypost, delta, eps, True)
+        nz_full = EU.planes_to_csc(full, S, F, True, cache.colptr, cache.rowval)
+        np.testing.assert_array_equal(nz_full, nz_got)
