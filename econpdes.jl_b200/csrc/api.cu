@@ -1,0 +1,389 @@
+// extern "C" entry points of libeconpdes_cuda.so (include/econpdes_cuda.h).
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "batched1d.cuh"
+#include "engine.cuh"
+
+using namespace econpdes;
+
+namespace {
+
+template <class Fn>
+int guarded(Fn&& fn) {
+  try {
+    return fn();
+  } catch (const std::invalid_argument& e) {
+    set_error(e.what());
+    return ECONPDES_E_INVALID;
+  } catch (const CudaError& e) {
+    set_error(e.what());
+    const std::string m = e.what();
+    return m.find("no usable CUDA device") != std::string::npos ? ECONPDES_E_NO_DEVICE : ECONPDES_E_CUDA;
+  } catch (const std::exception& e) {
+    set_error(e.what());
+    return ECONPDES_E_UNSUPPORTED;
+  }
+}
+
+}  // namespace
+
+struct econpdes_handle {
+  std::unique_ptr<Solver> solver;
+  DevBuf<double> a, b, c;
+  bool have_jacobian = false;
+};
+
+struct econpdes_batch {
+  int model_id = -1;
+  long long B = 0;
+  int S = 0, nparams = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf<double> params, grids, guess, solution, residual_norm;
+  DevBuf<int> exit_reason, n_outer, n_newton, error, log_len;
+  DevBuf<econpdes_log_row> log;
+  int log_capacity = 0;
+  int64_t launches = 0;
+  ~econpdes_batch() {
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+extern "C" {
+
+int econpdes_model_count(void) { return model_count(); }
+
+int econpdes_model_id(const char* name) {
+  if (name == nullptr) return ECONPDES_E_INVALID;
+  for (int i = 0; i < model_count(); ++i)
+    if (std::strcmp(model_ops(i)->name(), name) == 0) return i;
+  set_error(std::string("unknown model `") + name + "`");
+  return ECONPDES_E_INVALID;
+}
+
+const char* econpdes_model_name(int model_id) {
+  const ModelOps* o = model_ops(model_id);
+  return o ? o->name() : nullptr;
+}
+
+int econpdes_model_info(int model_id, int32_t* ndims, int32_t* nfuncs, int32_t* nparams, int32_t* nsaved,
+                        int32_t* box_stencil) {
+  const ModelOps* o = model_ops(model_id);
+  if (!o) {
+    set_error("unknown model id");
+    return ECONPDES_E_INVALID;
+  }
+  if (ndims) *ndims = o->N();
+  if (nfuncs) *nfuncs = o->F();
+  if (nparams) *nparams = o->nparams();
+  if (nsaved) *nsaved = o->nsaved();
+  if (box_stencil) *box_stencil = o->box() ? 1 : 0;
+  return ECONPDES_OK;
+}
+
+void econpdes_default_options(econpdes_options* o) {
+  if (!o) return;
+  const double sqrt_eps = 1.4901161193847656e-8;
+  o->abstol = sqrt_eps;
+  o->inner_abstol = sqrt_eps;
+  o->delta = 1.0;
+  o->scale = 10.0;
+  o->min_delta = 1e-9;
+  o->max_delta = std::numeric_limits<double>::infinity();
+  o->max_residual_growth = 10.0;
+  o->maxiters = 100;
+  o->inner_maxiters = 10;
+  o->eps_policy = ECONPDES_EPS_FINITEDIFF_COLOR_NORM;
+  o->linear_solver = ECONPDES_LIN_AUTO;
+  o->lin_rtol = 1e-12;
+  o->lin_maxiters = 2000;
+  o->lin_restart = 40;
+}
+
+int econpdes_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int econpdes_set_device(int device) {
+  return guarded([&] {
+    ensure_device();
+    EP_CUDA(cudaSetDevice(device));
+    return ECONPDES_OK;
+  });
+}
+
+int64_t econpdes_total_kernel_launches(void) { return g_kernel_launches.load(); }
+
+int econpdes_create(const econpdes_problem* problem, econpdes_handle** out) {
+  return guarded([&] {
+    if (!out) throw std::invalid_argument("null handle pointer");
+    auto h = std::make_unique<econpdes_handle>();
+    h->solver = std::make_unique<Solver>(make_ctx(problem));
+    *out = h.release();
+    return ECONPDES_OK;
+  });
+}
+
+void econpdes_destroy(econpdes_handle* h) { delete h; }
+
+int econpdes_residual(econpdes_handle* h, const double* y, double* ydot) {
+  return guarded([&] {
+    if (!h || !y || !ydot) throw std::invalid_argument("null argument");
+    Ctx& c = h->solver->ctx();
+    h->a.upload(y, static_cast<size_t>(c.n), c.stream);
+    h->b.alloc(static_cast<size_t>(c.n));
+    h->solver->eval_G(h->a.p, h->b.p);
+    h->b.download(ydot, static_cast<size_t>(c.n), c.stream);
+    EP_CUDA(cudaStreamSynchronize(c.stream));
+    return ECONPDES_OK;
+  });
+}
+
+int econpdes_saved(econpdes_handle* h, const double* y, double* saved) {
+  return guarded([&] {
+    if (!h || !y || !saved) throw std::invalid_argument("null argument");
+    Ctx& c = h->solver->ctx();
+    if (c.nsaved == 0) return ECONPDES_OK;
+    h->a.upload(y, static_cast<size_t>(c.n), c.stream);
+    h->b.alloc(static_cast<size_t>(c.nsaved) * c.l);
+    model_ops(c.model_id)->saved(c, h->a.p, h->b.p);
+    h->b.download(saved, static_cast<size_t>(c.nsaved) * c.l, c.stream);
+    EP_CUDA(cudaStreamSynchronize(c.stream));
+    return ECONPDES_OK;
+  });
+}
+
+int econpdes_jacobian_csc(econpdes_handle* h, const double* y, const double* ypost, double delta, int32_t eps_policy,
+                          double* nzval, double* eps_out) {
+  return guarded([&] {
+    if (!h || !y || !nzval) throw std::invalid_argument("null argument");
+    Ctx& c = h->solver->ctx();
+    h->a.upload(y, static_cast<size_t>(c.n), c.stream);
+    if (ypost) h->b.upload(ypost, static_cast<size_t>(c.n), c.stream);
+    h->solver->jacobian(h->a.p, ypost ? h->b.p : nullptr, delta, eps_policy);
+    h->have_jacobian = true;
+    int64_t size[kMaxDims];
+    for (int d = 0; d < c.N; ++d) size[d] = c.S[d];
+    const int64_t nnz = econpdes_stencil_nnz(c.N, size, c.F);
+    h->c.alloc(static_cast<size_t>(nnz));
+    h->solver->csc_gather(h->c.p);
+    h->c.download(nzval, static_cast<size_t>(nnz), c.stream);
+    if (eps_out && eps_policy == ECONPDES_EPS_FINITEDIFF_COLOR_NORM)
+      c.color_eps.download(eps_out, static_cast<size_t>(c.ncolors), c.stream);
+    EP_CUDA(cudaStreamSynchronize(c.stream));
+    return ECONPDES_OK;
+  });
+}
+
+int econpdes_linear_solve(econpdes_handle* h, const econpdes_options* options, const double* b, double* x,
+                          int32_t* iters_out, double* relres_out) {
+  return guarded([&] {
+    if (!h || !b || !x || !options) throw std::invalid_argument("null argument");
+    if (!h->have_jacobian) throw std::invalid_argument("call econpdes_jacobian_csc before econpdes_linear_solve");
+    Ctx& c = h->solver->ctx();
+    h->a.upload(b, static_cast<size_t>(c.n), c.stream);
+    h->b.alloc(static_cast<size_t>(c.n));
+    int it = 0;
+    double rr = 0.0;
+    const int fail = h->solver->linear().solve(h->solver->planes(), h->a.p, h->b.p, *options, &it, &rr);
+    h->b.download(x, static_cast<size_t>(c.n), c.stream);
+    EP_CUDA(cudaStreamSynchronize(c.stream));
+    if (iters_out) *iters_out = it;
+    if (relres_out) *relres_out = rr;
+    return fail ? 1 : ECONPDES_OK;
+  });
+}
+
+int econpdes_implicit_timestep(econpdes_handle* h, const econpdes_options* options, const double* ypost, double delta,
+                               int32_t maxiters, double abstol, double* y_out, double* nl_residual,
+                               int32_t* newton_iters) {
+  return guarded([&] {
+    if (!h || !options || !ypost || !y_out) throw std::invalid_argument("null argument");
+    Ctx& c = h->solver->ctx();
+    h->a.upload(ypost, static_cast<size_t>(c.n), c.stream);
+    h->b.alloc(static_cast<size_t>(c.n));
+    NewtonOutcome o = h->solver->newton(h->a.p, delta, abstol, maxiters, *options, h->b.p);
+    h->b.download(y_out, static_cast<size_t>(c.n), c.stream);
+    EP_CUDA(cudaStreamSynchronize(c.stream));
+    if (nl_residual) *nl_residual = o.nl;
+    if (newton_iters) *newton_iters = o.iters;
+    return ECONPDES_OK;
+  });
+}
+
+int econpdes_solve(econpdes_handle* h, const econpdes_options* options, econpdes_result* result) {
+  return guarded([&] {
+    if (!h || !options || !result) throw std::invalid_argument("null argument");
+    return h->solver->solve(*options, result);
+  });
+}
+
+int econpdes_solve_stationary(const econpdes_problem* problem, const econpdes_options* options,
+                              econpdes_result* result) {
+  return guarded([&] {
+    if (!problem || !options || !result) throw std::invalid_argument("null argument");
+    Solver solver(make_ctx(problem));
+    return solver.solve(*options, result);
+  });
+}
+
+// ---- batched sweep ----
+int econpdes_batch_create(int model_id, int64_t nproblems, int64_t npoints, econpdes_batch** out) {
+  return guarded([&] {
+    const ModelOps* ops = model_ops(model_id);
+    if (!ops) throw std::invalid_argument("unknown model id");
+    if (ops->N() != 1 || ops->F() != 1)
+      throw std::invalid_argument("the batched engine takes 1-D single-unknown models");
+    if (nproblems < 1 || npoints < 2) throw std::invalid_argument("need >= 1 problem of >= 2 points");
+    if (npoints > 1024) throw std::runtime_error("batched engine: at most 1024 points per problem");
+    if (!out) throw std::invalid_argument("null batch pointer");
+    ensure_device();
+    auto b = std::make_unique<econpdes_batch>();
+    b->model_id = model_id;
+    b->B = nproblems;
+    b->S = static_cast<int>(npoints);
+    b->nparams = ops->nparams();
+    EP_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    const size_t B = static_cast<size_t>(nproblems), S = static_cast<size_t>(npoints);
+    b->params.alloc(B * (b->nparams > 0 ? b->nparams : 1));
+    b->grids.alloc(B * S);
+    b->guess.alloc(B * S);
+    b->solution.alloc(B * S);
+    b->residual_norm.alloc(B);
+    b->exit_reason.alloc(B);
+    b->n_outer.alloc(B);
+    b->n_newton.alloc(B);
+    b->error.alloc(B);
+    b->log_len.alloc(B);
+    *out = b.release();
+    return ECONPDES_OK;
+  });
+}
+
+void econpdes_batch_destroy(econpdes_batch* b) { delete b; }
+
+int econpdes_batch_upload(econpdes_batch* b, const double* params, const double* grids, const double* guess) {
+  return guarded([&] {
+    if (!b || !grids || !guess) throw std::invalid_argument("null argument");
+    const size_t B = static_cast<size_t>(b->B), S = static_cast<size_t>(b->S);
+    if (b->nparams > 0) {
+      if (!params) throw std::invalid_argument("null params");
+      b->params.upload(params, B * b->nparams, b->stream);
+    }
+    b->grids.upload(grids, B * S, b->stream);
+    b->guess.upload(guess, B * S, b->stream);
+    EP_CUDA(cudaStreamSynchronize(b->stream));
+    return ECONPDES_OK;
+  });
+}
+
+static int batch_launch(econpdes_batch* b, const econpdes_options* options, int log_capacity) {
+  if (std::isnan(options->delta) || options->delta == 0.0)
+    throw std::invalid_argument("`Δ` entries must be nonzero and not NaN (use `Inf` for no damping, a negative entry for forward relaxation)");
+  BatchArgs a;
+  a.nproblems = b->B;
+  a.S = b->S;
+  a.nparams = b->nparams;
+  a.params = b->params.p;
+  a.grids = b->grids.p;
+  a.guess = b->guess.p;
+  a.solution = b->solution.p;
+  a.residual_norm = b->residual_norm.p;
+  a.exit_reason = b->exit_reason.p;
+  a.n_outer = b->n_outer.p;
+  a.n_newton = b->n_newton.p;
+  a.error = b->error.p;
+  if (log_capacity > 0) {
+    b->log.alloc(static_cast<size_t>(b->B) * log_capacity);
+    b->log_capacity = log_capacity;
+  }
+  a.log = b->log_capacity > 0 ? b->log.p : nullptr;
+  a.log_capacity = b->log_capacity;
+  a.log_len = b->log_len.p;
+  a.opt = *options;
+  const int64_t l0 = g_kernel_launches.load();
+  if (!model_ops(b->model_id)->batched(a, b->stream)) throw std::runtime_error("model has no batched kernel");
+  b->launches += g_kernel_launches.load() - l0;
+  return ECONPDES_OK;
+}
+
+int econpdes_batch_solve(econpdes_batch* b, const econpdes_options* options, double* device_ms) {
+  return guarded([&] {
+    if (!b || !options) throw std::invalid_argument("null argument");
+    cudaEvent_t e0, e1;
+    EP_CUDA(cudaEventCreate(&e0));
+    EP_CUDA(cudaEventCreate(&e1));
+    EP_CUDA(cudaEventRecord(e0, b->stream));
+    batch_launch(b, options, b->log_capacity);
+    EP_CUDA(cudaEventRecord(e1, b->stream));
+    EP_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    EP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (device_ms) *device_ms = ms;
+    return ECONPDES_OK;
+  });
+}
+
+int econpdes_batch_set_log_capacity(econpdes_batch* b, int32_t log_capacity) {
+  return guarded([&] {
+    if (!b || log_capacity < 0) throw std::invalid_argument("bad log capacity");
+    b->log_capacity = log_capacity;
+    if (log_capacity > 0) b->log.alloc(static_cast<size_t>(b->B) * log_capacity);
+    return ECONPDES_OK;
+  });
+}
+
+int econpdes_batch_download(econpdes_batch* b, double* solution, double* residual_norm, int32_t* exit_reason,
+                            int32_t* n_outer, int32_t* n_newton, econpdes_log_row* log, int32_t log_capacity,
+                            int32_t* log_len) {
+  return guarded([&] {
+    if (!b) throw std::invalid_argument("null batch");
+    const size_t B = static_cast<size_t>(b->B), S = static_cast<size_t>(b->S);
+    std::vector<int> err(B);
+    b->error.download(err.data(), B, b->stream);
+    if (solution) b->solution.download(solution, B * S, b->stream);
+    if (residual_norm) b->residual_norm.download(residual_norm, B, b->stream);
+    if (exit_reason) b->exit_reason.download(exit_reason, B, b->stream);
+    if (n_outer) b->n_outer.download(n_outer, B, b->stream);
+    if (n_newton) b->n_newton.download(n_newton, B, b->stream);
+    if (log && log_len) {
+      if (log_capacity != b->log_capacity || b->log.p == nullptr)
+        throw std::invalid_argument("log capacity differs from the one the batch was solved with");
+      b->log.download(log, B * static_cast<size_t>(log_capacity), b->stream);
+      b->log_len.download(log_len, B, b->stream);
+    }
+    EP_CUDA(cudaStreamSynchronize(b->stream));
+    for (size_t i = 0; i < B; ++i)
+      if (err[i] != 0) {
+        set_error("G! returns NaN with the initial value (problem " + std::to_string(i) + ")");
+        return ECONPDES_E_NAN_GUESS;
+      }
+    return ECONPDES_OK;
+  });
+}
+
+int64_t econpdes_batch_kernel_launches(const econpdes_batch* b) { return b ? b->launches : 0; }
+
+int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, const double* params, const double* grids,
+                           const double* guess, const econpdes_options* options, double* solution,
+                           double* residual_norm, int32_t* exit_reason, int32_t* n_outer, int32_t* n_newton) {
+  econpdes_batch* b = nullptr;
+  int rc = econpdes_batch_create(model_id, nproblems, npoints, &b);
+  if (rc != ECONPDES_OK) return rc;
+  rc = econpdes_batch_upload(b, params, grids, guess);
+  if (rc == ECONPDES_OK) rc = econpdes_batch_solve(b, options, nullptr);
+  if (rc == ECONPDES_OK)
+    rc = econpdes_batch_download(b, solution, residual_norm, exit_reason, n_outer, n_newton, nullptr, 0, nullptr);
+  econpdes_batch_destroy(b);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,541 @@
+// Generic engine: per-model kernel dispatch, the Newton solve of one implicit step and
+// the pseudo-transient continuation driver -- the device-side counterpart of
+// `finiteschemesolve` (src/finiteschemesolve.jl:343-465), `implicit_timestep` (:153-230),
+// `_newtonstep` (:125-147) and NLsolve's `newton_` (restated in oracle/econpdes_oracle.py).
+// Scalars of the control loop (norms, the SER controller) live on the host; every field
+// stays in HBM for the whole solve.
+#include "engine.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <tuple>
+
+#include "batched1d.cuh"
+#include "tridiag.cuh"
+
+namespace econpdes {
+
+std::atomic<int64_t> g_kernel_launches{0};
+
+void ensure_device() {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    throw CudaError(std::string("no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "0 devices") +
+                    "); libeconpdes_cuda has no CPU fallback");
+  }
+}
+
+Ctx::~Ctx() {
+  if (h_norm) cudaFreeHost(h_norm);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+double Norms::norm2_over_n(long long n) const {
+  if (any_nan) return std::numeric_limits<double>::quiet_NaN();
+  return std::sqrt(sumsq) / static_cast<double>(n);
+}
+
+// ---------------------------------------------------------------------------------------
+// model registry
+// ---------------------------------------------------------------------------------------
+template <class M, bool ONE_D = (M::N == 1 && M::F == 1)>
+struct BatchedLaunch {
+  static bool run(const BatchArgs&, cudaStream_t) { return false; }
+};
+template <class M>
+struct BatchedLaunch<M, true> {
+  static bool run(const BatchArgs& a, cudaStream_t s) {
+    const int T = ((a.S + 31) / 32) * 32;
+    if (T > 1024) return false;
+    const size_t smem = batched_smem_bytes(T);
+    static bool configured = false;
+    if (!configured) {
+      EP_CUDA(cudaFuncSetAttribute(k_batched_pdesolve_1d<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(batched_smem_bytes(1024))));
+      configured = true;
+    }
+    EP_LAUNCH(k_batched_pdesolve_1d<M>, static_cast<unsigned>(a.nproblems), T, smem, s, a);
+    return true;
+  }
+};
+
+template <class M>
+struct ModelOpsT final : ModelOps {
+  const char* name() const override { return M::name(); }
+  int N() const override { return M::N; }
+  int F() const override { return M::F; }
+  int nparams() const override { return M::NPARAMS; }
+  int nsaved() const override { return M::NSAVED; }
+  bool box() const override { return M::USES_CROSS && M::N > 1; }
+  void residual(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm) const override {
+    EP_LAUNCH(k_residual<M>, blocks_for(c.l), kBlock, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p, rs, out,
+              c.nw(), want_norm ? 1 : 0);
+  }
+  void jacobian(const Ctx& c, const double* y, const RowSpec& rs, int eps_policy, double* planes,
+                double* r0) const override {
+    const int per_col = eps_policy == ECONPDES_EPS_PER_COLUMN;
+    if (!per_col) {
+      EP_LAUNCH(k_color_sumsq<M::N>, blocks_for(c.l), kBlock, 0, c.stream, c.grid_view<M::N>(), M::F, y, c.cw());
+    }
+    if constexpr (M::USES_CROSS && M::N > 1) {
+      EP_LAUNCH((k_jacobian<M, true>), blocks_for(c.l), kBlock, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p,
+                rs, c.color_eps.p, per_col, planes, r0);
+    } else {
+      EP_LAUNCH((k_jacobian<M, false>), blocks_for(c.l), kBlock, 0, c.stream, c.grid_view<M::N>(), c.prm, y,
+                c.bc.p, rs, c.color_eps.p, per_col, planes, r0);
+    }
+  }
+  void saved(const Ctx& c, const double* y, double* out) const override {
+    if (M::NSAVED == 0) return;
+    EP_LAUNCH(k_saved<M>, blocks_for(c.l), kBlock, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p, out);
+  }
+  bool batched(const BatchArgs& a, cudaStream_t s) const override { return BatchedLaunch<M>::run(a, s); }
+};
+
+namespace {
+template <class... Ms>
+struct Registry {
+  static const ModelOps* get(int id) {
+    static const std::tuple<ModelOpsT<Ms>...> ops;
+    return pick<0>(ops, id);
+  }
+  template <size_t I>
+  static const ModelOps* pick(const std::tuple<ModelOpsT<Ms>...>& ops, int id) {
+    if constexpr (I < sizeof...(Ms)) {
+      if (id == static_cast<int>(I)) return &std::get<I>(ops);
+      return pick<I + 1>(ops, id);
+    } else {
+      return nullptr;
+    }
+  }
+  static constexpr int count = sizeof...(Ms);
+};
+#define X(M) , M
+struct Dummy_ {};
+template <class D, class... Ms>
+using RegistryOf = Registry<Ms...>;
+using TheRegistry = RegistryOf<Dummy_ ECONPDES_FOR_EACH_MODEL(X)>;
+#undef X
+}  // namespace
+
+const ModelOps* model_ops(int model_id) { return TheRegistry::get(model_id); }
+int model_count() { return TheRegistry::count; }
+
+// ---------------------------------------------------------------------------------------
+// problem upload
+// ---------------------------------------------------------------------------------------
+std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p) {
+  if (p == nullptr) throw std::invalid_argument("null problem");
+  const ModelOps* ops = model_ops(p->model_id);
+  if (ops == nullptr) throw std::invalid_argument("unknown model id " + std::to_string(p->model_id));
+  if (p->ndims != ops->N() || p->nfuncs != ops->F())
+    throw std::invalid_argument(std::string("model `") + ops->name() + "` expects " + std::to_string(ops->N()) +
+                                " state variable(s) and " + std::to_string(ops->F()) + " unknown(s)");
+  if (p->nparams != ops->nparams())
+    throw std::invalid_argument(std::string("model `") + ops->name() + "` expects " +
+                                std::to_string(ops->nparams()) + " parameters");
+  if (p->guess == nullptr) throw std::invalid_argument("null guess");
+  ensure_device();
+  auto c = std::make_unique<Ctx>();
+  c->model_id = p->model_id;
+  c->N = ops->N();
+  c->F = ops->F();
+  c->nparams = ops->nparams();
+  c->nsaved = ops->nsaved();
+  c->box = ops->box();
+  c->nk = c->box ? ipow3(c->N) : 1 + 2 * c->N;
+  c->l = 1;
+  c->ncolors = c->F;
+  for (int d = 0; d < c->N; ++d) {
+    if (p->size[d] < 2) throw std::invalid_argument("state grid entries must have at least 2 points");  // stategrid.jl:16
+    if (p->grid[d] == nullptr) throw std::invalid_argument("null grid vector");
+    c->S[d] = p->size[d];
+    c->l *= p->size[d];
+    c->ncolors *= p->size[d] < 3 ? static_cast<int>(p->size[d]) : 3;
+  }
+  c->n = c->l * c->F;
+  for (int i = 0; i < c->nparams; ++i) c->prm.v[i] = p->params[i];
+  EP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  cudaStream_t s = c->stream;
+  for (int d = 0; d < c->N; ++d) c->grid[d].upload(p->grid[d], static_cast<size_t>(c->S[d]), s);
+  c->guess.upload(p->guess, static_cast<size_t>(c->n), s);
+  if (p->bc != nullptr) {
+    bool any = false;
+    for (long long j = 0; j < c->n && !any; ++j) any = p->bc[j] != 0.0;
+    if (any) c->bc.upload(p->bc, static_cast<size_t>(c->n), s);
+  }
+  if (p->is_algebraic != nullptr) {
+    bool any = false;
+    for (long long j = 0; j < c->n && !any; ++j) any = p->is_algebraic[j] != 0;
+    if (any) c->is_alg.upload(p->is_algebraic, static_cast<size_t>(c->n), s);
+  }
+  // Any non-default bound turns the solve into an MCP (finiteschemesolve.jl:156, 355)
+  bool lbany = false, ubany = false;
+  if (p->lower_bound != nullptr)
+    for (long long j = 0; j < c->n && !lbany; ++j) lbany = p->lower_bound[j] != -INFINITY;
+  if (p->upper_bound != nullptr)
+    for (long long j = 0; j < c->n && !ubany; ++j) ubany = p->upper_bound[j] != INFINITY;
+  c->has_bounds = lbany || ubany;
+  if (c->has_bounds) {
+    std::vector<double> tmp(static_cast<size_t>(c->n));
+    for (long long j = 0; j < c->n; ++j) tmp[j] = p->lower_bound ? p->lower_bound[j] : -INFINITY;
+    c->lb.upload(tmp.data(), tmp.size(), s);
+    EP_CUDA(cudaStreamSynchronize(s));
+    for (long long j = 0; j < c->n; ++j) tmp[j] = p->upper_bound ? p->upper_bound[j] : INFINITY;
+    c->ub.upload(tmp.data(), tmp.size(), s);
+    EP_CUDA(cudaStreamSynchronize(s));
+  }
+  if (p->delta_vec != nullptr) {  // finiteschemesolve.jl:349-353, 393-396
+    double base = INFINITY;
+    bool allinf = true;
+    for (long long j = 0; j < c->n; ++j) {
+      const double v = p->delta_vec[j];
+      if (std::isnan(v) || v == 0.0)
+        throw std::invalid_argument("`Δ` entries must be nonzero and not NaN (use `Inf` for no damping, a negative entry for forward relaxation)");
+      if (std::isfinite(v)) {
+        allinf = false;
+        base = std::fabs(v) < base ? std::fabs(v) : base;
+      }
+    }
+    c->has_delta_vec = true;
+    c->all_delta_inf = allinf;
+    if (!allinf) {
+      c->delta_base = base;
+      std::vector<double> rel(static_cast<size_t>(c->n));
+      for (long long j = 0; j < c->n; ++j) rel[j] = p->delta_vec[j] / base;
+      c->delta_rel.upload(rel.data(), rel.size(), s);
+      EP_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  c->max_blocks = blocks_for(c->n) + 1;
+  c->norm_part.alloc(3 * static_cast<size_t>(c->max_blocks));
+  c->norm_out.alloc(4);
+  c->color_part.alloc(static_cast<size_t>(blocks_for(c->l)) * c->ncolors);
+  c->color_eps.alloc(static_cast<size_t>(c->ncolors));
+  c->color_sumsq.alloc(static_cast<size_t>(c->ncolors));
+  c->counters.alloc(4);
+  c->counters.zero(s);
+  EP_CUDA(cudaMallocHost(&c->h_norm, 4 * sizeof(double)));
+  EP_CUDA(cudaStreamSynchronize(s));
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------
+// 1-D linear solver: (block-)tridiagonal PCR
+// ---------------------------------------------------------------------------------------
+namespace {
+
+template <int F>
+int pcr_solve(Ctx& c, const double* planes, const double* b, double* x, DevBuf<double>* work) {
+  const long long n = c.l;
+  const size_t per = static_cast<size_t>((3 * F * F + F) * n);
+  work[0].alloc(per);
+  work[1].alloc(per);
+  auto view = [&](double* base) { return PcrSystemOut{base, base + F * F * n, base + 2 * F * F * n, base + 3 * F * F * n}; };
+  PcrSystem in{planes + 1 * F * F * n, planes, planes + 2 * F * F * n, b};
+  int cur = 0;
+  for (long long s = 1; s < n; s <<= 1) {
+    PcrSystemOut out = view(work[cur].p);
+    EP_LAUNCH(k_pcr_step<F>, blocks_for(n), kBlock, 0, c.stream, n, s, in, out);
+    in = PcrSystem{out.A, out.B, out.C, out.d};
+    cur ^= 1;
+  }
+  EP_LAUNCH(k_pcr_final<F>, blocks_for(n), kBlock, 0, c.stream, n, in, x, c.nw());
+  EP_CUDA(cudaMemcpyAsync(c.h_norm, c.norm_out.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  EP_CUDA(cudaStreamSynchronize(c.stream));
+  return c.h_norm[2] != 0.0 ? 1 : 0;
+}
+
+struct TridiagSolver final : LinearSolver {
+  explicit TridiagSolver(Ctx& c) : c_(c) {}
+  int solve(const double* planes, const double* b, double* x, const econpdes_options&, int* iters,
+            double* relres) override {
+    if (iters) *iters = 0;
+    if (relres) *relres = 0.0;
+    switch (c_.F) {
+      case 1: return pcr_solve<1>(c_, planes, b, x, work_);
+      case 2: return pcr_solve<2>(c_, planes, b, x, work_);
+      case 3: return pcr_solve<3>(c_, planes, b, x, work_);
+      case 4: return pcr_solve<4>(c_, planes, b, x, work_);
+      default: throw std::invalid_argument("block-tridiagonal solver supports up to 4 unknowns");
+    }
+  }
+  Ctx& c_;
+  DevBuf<double> work_[2];
+};
+
+}  // namespace
+
+std::unique_ptr<LinearSolver> make_tridiag_solver(Ctx& c) { return std::make_unique<TridiagSolver>(c); }
+
+// ---------------------------------------------------------------------------------------
+// Solver
+// ---------------------------------------------------------------------------------------
+namespace {
+
+// ||ydot .* mask|| / sum(mask), mask = lb + eps <= y <= ub - eps  (finiteschemesolve.jl:410-413)
+__global__ void __launch_bounds__(kBlock) k_masked_norm(long long n, const double* __restrict__ ydot,
+                                                        const double* __restrict__ y, const double* __restrict__ lb,
+                                                        const double* __restrict__ ub, NormWork nw) {
+  __shared__ double scratch[96];
+  const long long j = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  double s = 0.0, cnt = 0.0;
+  int nanf = 0;
+  if (j < n) {
+    const double e = 2.220446049250313e-16;
+    const bool in = (lb[j] + e <= y[j]) && (y[j] <= ub[j] - e);
+    if (in) {
+      cnt = 1.0;
+      const double r = ydot[j];
+      if (r != r) nanf = 1; else s = r * r;
+    }
+  }
+  // reuse the (sum, max, flag) reduction: the count is summed in a second pass below
+  grid_norm_finish(s, cnt, nanf, nw, scratch);
+}
+
+__global__ void __launch_bounds__(kBlock) k_count_mask(long long n, const double* __restrict__ y,
+                                                       const double* __restrict__ lb, const double* __restrict__ ub,
+                                                       NormWork nw) {
+  __shared__ double scratch[96];
+  const long long j = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  double cnt = 0.0;
+  if (j < n) {
+    const double e = 2.220446049250313e-16;
+    if ((lb[j] + e <= y[j]) && (y[j] <= ub[j] - e)) cnt = 1.0;
+  }
+  grid_norm_finish(cnt, 0.0, 0, nw, scratch);
+}
+
+}  // namespace
+
+Solver::Solver(std::unique_ptr<Ctx> ctx) : c_(std::move(ctx)), ops_(model_ops(c_->model_id)) {
+  const size_t n = static_cast<size_t>(c_->n);
+  ypost_.alloc(n); y_.alloc(n); ynew_.alloc(n); R_.alloc(n); s_.alloc(n); G_.alloc(n);
+  planes_.alloc(static_cast<size_t>(c_->nk) * c_->F * c_->F * c_->l);
+  lin_ = c_->N == 1 ? make_tridiag_solver(*c_) : make_krylov_solver(*c_);
+}
+
+RowSpec Solver::row_spec(const double* ypost, double delta) const {
+  RowSpec rs;
+  rs.ypost = ypost;
+  rs.delta = delta;
+  rs.delta_rel = (ypost != nullptr && c_->has_delta_vec && !c_->all_delta_inf && std::isfinite(delta)) ? c_->delta_rel.p : nullptr;
+  rs.is_alg = c_->is_alg.p;
+  rs.lb = c_->lb.p;
+  rs.ub = c_->ub.p;
+  rs.has_bounds = (ypost != nullptr && c_->has_bounds) ? 1 : 0;
+  return rs;
+}
+
+Norms Solver::read_norms() {
+  EP_CUDA(cudaMemcpyAsync(c_->h_norm, c_->norm_out.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, c_->stream));
+  EP_CUDA(cudaStreamSynchronize(c_->stream));
+  return Norms{c_->h_norm[0], c_->h_norm[1], c_->h_norm[2] != 0.0};
+}
+
+Norms Solver::eval_G(const double* y, double* out) {
+  ops_->residual(*c_, y, row_spec(nullptr, INFINITY), out, true);
+  return read_norms();
+}
+
+Norms Solver::eval_R(const double* y, const double* ypost, double delta, double* out) {
+  ops_->residual(*c_, y, row_spec(ypost, delta), out, true);
+  return read_norms();
+}
+
+void Solver::jacobian(const double* y, const double* ypost, double delta, int eps_policy) {
+  ops_->jacobian(*c_, y, row_spec(ypost, delta), eps_policy, planes_.p, nullptr);
+}
+
+double Solver::masked_norm(const double* ydot, const double* y) {
+  EP_LAUNCH(k_masked_norm, blocks_for(c_->n), kBlock, 0, c_->stream, c_->n, ydot, y, c_->lb.p, c_->ub.p, c_->nw());
+  Norms a = read_norms();
+  EP_LAUNCH(k_count_mask, blocks_for(c_->n), kBlock, 0, c_->stream, c_->n, y, c_->lb.p, c_->ub.p, c_->nw());
+  Norms b = read_norms();
+  if (a.any_nan) return std::numeric_limits<double>::quiet_NaN();
+  return std::sqrt(a.sumsq) / b.sumsq;
+}
+
+// NLsolve newton_ with the Static line search, wrapped like _newtonstep (:125-147).
+NewtonOutcome Solver::newton(const double* ypost, double delta, double ftol, int maxit, const econpdes_options& opt,
+                             double* y_out) {
+  const long long n = c_->n;
+  NewtonOutcome out{0.0, 0, 0, false};
+  double* x = y_.p;
+  double* xn = ynew_.p;
+  EP_CUDA(cudaMemcpyAsync(x, ypost, n * sizeof(double), cudaMemcpyDeviceToDevice, c_->stream));
+  Norms nr = eval_R(x, ypost, delta, R_.p);
+  bool stopped = nr.any_nan;
+  bool fconv = !nr.any_nan && nr.maxabs <= ftol;
+  bool xconv = false;
+  while (!stopped && !fconv && !xconv && out.iters < maxit) {
+    ++out.iters;
+    jacobian(x, ypost, delta, opt.eps_policy);
+    int li = 0;
+    double rr = 0.0;
+    const int fail = lin_->solve(planes_.p, R_.p, s_.p, opt, &li, &rr);
+    out.lin_iters += li;
+    if (fail) {  // SingularException -> (y0, Inf)
+      out.singular = true;
+      out.nl = INFINITY;
+      EP_CUDA(cudaMemcpyAsync(y_out, ypost, n * sizeof(double), cudaMemcpyDeviceToDevice, c_->stream));
+      return out;
+    }
+    EP_LAUNCH(k_newton_update, blocks_for(n), kBlock, 0, c_->stream, n, x, s_.p, xn, c_->nw());
+    Norms nx = read_norms();
+    std::swap(x, xn);
+    nr = eval_R(x, ypost, delta, R_.p);
+    xconv = !nx.any_nan && nx.maxabs <= 0.0;
+    fconv = !nr.any_nan && nr.maxabs <= ftol;
+    stopped = nx.any_nan || nr.any_nan;
+  }
+  out.nl = nr.norm2_over_n(n);
+  if (x != y_out) EP_CUDA(cudaMemcpyAsync(y_out, x, n * sizeof(double), cudaMemcpyDeviceToDevice, c_->stream));
+  return out;
+}
+
+int Solver::solve(const econpdes_options& opt, econpdes_result* res) {
+  Ctx& c = *c_;
+  const long long n = c.n;
+  cudaStream_t s = c.stream;
+  const int64_t launches0 = g_kernel_launches.load();
+  cudaEvent_t e0, e1;
+  EP_CUDA(cudaEventCreate(&e0));
+  EP_CUDA(cudaEventCreate(&e1));
+  EP_CUDA(cudaEventRecord(e0, s));
+  res->log_len = 0;
+  res->n_outer = 0;
+  res->n_newton = 0;
+  res->n_linear_iters = 0;
+  res->exit_reason = ECONPDES_EXIT_CONVERGED;
+
+  if (!c.has_delta_vec && (std::isnan(opt.delta) || opt.delta == 0.0))
+    throw std::invalid_argument("`Δ` entries must be nonzero and not NaN (use `Inf` for no damping, a negative entry for forward relaxation)");
+
+  DevBuf<double> ytrial;
+  ytrial.alloc(static_cast<size_t>(n));
+  EP_CUDA(cudaMemcpyAsync(ypost_.p, c.guess.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  double r = eval_G(ypost_.p, G_.p).norm2_over_n(n);
+  int rc = ECONPDES_OK;
+  auto push_log = [&](int iter, int status, int nit, long long lit, double delta, double resid) {
+    if (res->log != nullptr && res->log_len < res->log_capacity) {
+      econpdes_log_row& row = res->log[res->log_len];
+      row.iter = iter; row.status = status; row.newton_iters = nit; row.linear_iters = static_cast<int32_t>(lit);
+      row.delta = delta; row.residual = resid;
+    }
+    ++res->log_len;
+  };
+  const bool delta_inf = c.has_delta_vec ? c.all_delta_inf : std::isinf(opt.delta);
+  if (std::isnan(r)) {
+    set_error("G! returns NaN with the initial value");   // finiteschemesolve.jl:372
+    rc = ECONPDES_E_NAN_GUESS;
+  } else if (r <= opt.abstol) {
+    res->exit_reason = ECONPDES_EXIT_ALREADY_ZERO;        // :373-376
+  } else if (delta_inf) {                                  // :377-389
+    NewtonOutcome o = newton(ypost_.p, INFINITY, opt.abstol, opt.maxiters, opt, ytrial.p);
+    res->n_newton = o.iters;
+    res->n_linear_iters = o.lin_iters;
+    EP_CUDA(cudaMemcpyAsync(ypost_.p, ytrial.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    r = o.nl;
+    res->exit_reason = r <= opt.abstol ? ECONPDES_EXIT_CONVERGED : ECONPDES_EXIT_INF_STEP_FAILED;
+  } else {
+    SerController ctl;
+    double drel = 1.0;
+    if (c.has_delta_vec) {
+      ctl.init(c.delta_base, opt.scale, opt.max_delta);
+    } else {
+      ctl.init(std::fabs(opt.delta), opt.scale, opt.max_delta);
+      drel = opt.delta < 0 ? -1.0 : 1.0;
+    }
+    int iter = 0;
+    while (iter < opt.maxiters && ctl.delta >= opt.min_delta && r > opt.abstol) {   // :406
+      ++iter;
+      NewtonOutcome o = newton(ypost_.p, ctl.delta * drel, opt.inner_abstol, opt.inner_maxiters, opt, ytrial.p);
+      res->n_newton += o.iters;
+      res->n_linear_iters += o.lin_iters;
+      const double old_r = r;
+      Norms ng = eval_G(ytrial.p, G_.p);
+      double rn = c.has_bounds ? masked_norm(G_.p, ytrial.p) : ng.norm2_over_n(n);
+      if (std::isnan(rn)) rn = INFINITY;                                              // :417
+      if (o.nl <= opt.inner_abstol && rn <= opt.max_residual_growth * old_r) {        // :418
+        push_log(iter, ECONPDES_STEP_ACCEPTED, o.iters, o.lin_iters, ctl.delta, rn);
+        ctl.accept(old_r, rn);
+        EP_CUDA(cudaMemcpyAsync(ypost_.p, ytrial.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        r = rn;
+      } else {
+        int status;
+        if (o.nl <= opt.inner_abstol) status = ECONPDES_STEP_REJECTED_GROWTH;         // :425
+        else if (std::isnan(o.nl)) status = ECONPDES_STEP_REJECTED_NAN;
+        else if (std::isinf(o.nl)) status = ECONPDES_STEP_REJECTED_SINGULAR;
+        else status = ECONPDES_STEP_REJECTED_INNER;                                   // :439
+        push_log(iter, status, o.iters, o.lin_iters, ctl.delta, std::numeric_limits<double>::quiet_NaN());
+        ctl.reject();
+      }
+    }
+    res->n_outer = iter;
+    if (r <= opt.abstol) res->exit_reason = ECONPDES_EXIT_CONVERGED;
+    else if (ctl.delta < opt.min_delta) res->exit_reason = ECONPDES_EXIT_BELOW_MIN_DELTA;
+    else res->exit_reason = ECONPDES_EXIT_MAXITERS;
+  }
+  DevBuf<double> saved;
+  if (rc == ECONPDES_OK && res->saved != nullptr && c.nsaved > 0) {
+    saved.alloc(static_cast<size_t>(c.nsaved) * c.l);
+    ops_->saved(c, ypost_.p, saved.p);
+  }
+  EP_CUDA(cudaEventRecord(e1, s));
+  EP_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  EP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  res->device_ms = ms;
+  res->residual_norm = r;
+  res->converged = (r <= opt.abstol) ? 1 : 0;
+  if (res->log_len > res->log_capacity) res->log_len = res->log_capacity;
+  if (res->solution != nullptr) ypost_.download(res->solution, static_cast<size_t>(n), s);
+  if (saved.p != nullptr) saved.download(res->saved, saved.n, s);
+  EP_CUDA(cudaStreamSynchronize(s));
+  res->kernel_launches = g_kernel_launches.load() - launches0;
+  return rc;
+}
+
+// Map from CSC nonzeros of local_stencil_jacobian to stencil planes (host, once).
+void Solver::csc_gather(double* nzval_dev) {
+  Ctx& c = *c_;
+  if (csc_map_.p == nullptr) {
+    int64_t size[kMaxDims];
+    for (int d = 0; d < c.N; ++d) size[d] = c.S[d];
+    nnz_ = econpdes_stencil_nnz(c.N, size, c.F);
+    std::vector<int64_t> colptr(static_cast<size_t>(c.n) + 1), rowval(static_cast<size_t>(nnz_));
+    econpdes_stencil_pattern(c.N, size, c.F, colptr.data(), rowval.data());
+    std::vector<long long> map(static_cast<size_t>(nnz_));
+    for (long long j = 0; j < c.n; ++j) {
+      const long long cpt = j % c.l, fin = j / c.l;
+      for (int64_t e = colptr[j] - 1; e < colptr[j + 1] - 1; ++e) {
+        const long long row = rowval[e] - 1, rpt = row % c.l, fout = row / c.l;
+        long long a = cpt, b = rpt;
+        int kbox = 0, nz = 0, kstar = 0, p3 = 1;
+        for (int d = 0; d < c.N; ++d) {
+          const int off = static_cast<int>(a % c.S[d] - b % c.S[d]);
+          a /= c.S[d];
+          b /= c.S[d];
+          kbox += (off + 1) * p3;
+          p3 *= 3;
+          if (off != 0) { ++nz; kstar = 1 + 2 * d + (off > 0 ? 1 : 0); }
+        }
+        long long k;
+        if (c.box) k = kbox; else k = nz == 0 ? 0 : (nz == 1 ? kstar : -1);
+        map[e] = k < 0 ? -1 : ((k * c.F + fin) * c.F + fout) * c.l + rpt;
+      }
+    }
+    csc_map_.upload(map.data(), map.size(), c.stream);
+    EP_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  EP_LAUNCH(k_gather_csc, blocks_for(nnz_), kBlock, 0, c.stream, nnz_, csc_map_.p, planes_.p, nzval_dev);
+}
+
+}  // namespace econpdes

@@ -1,0 +1,151 @@
+// Host-side structures of the generic engine: device-resident problem, the per-model
+// kernel dispatch table, the linear-solver interface and the pseudo-transient driver.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "../../include/econpdes_cuda.h"
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace econpdes {
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    if (count == n && p) return;
+    release();
+    if (count == 0) return;
+    EP_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+  }
+  void zero(cudaStream_t s) { if (p) EP_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+  void upload(const T* h, size_t count, cudaStream_t s) {
+    alloc(count);
+    EP_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void download(T* h, size_t count, cudaStream_t s) const {
+    EP_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+  }
+};
+
+// Problem resident on one device.
+struct Ctx {
+  int model_id = -1, N = 0, F = 0, nparams = 0, nsaved = 0;
+  bool box = false;        // stencil shape of the Jacobian planes
+  int nk = 0;              // planes per (fin, fout) pair
+  long long S[kMaxDims] = {1, 1, 1};
+  long long l = 0, n = 0;
+  int ncolors = 0;
+  ParamPack prm{};
+  DevBuf<double> grid[kMaxDims], guess, bc, lb, ub, delta_rel;
+  DevBuf<unsigned char> is_alg;
+  bool has_bounds = false, has_delta_vec = false, all_delta_inf = false;
+  double delta_base = 1.0;  // min finite |Δ_i| of a vector Δ (finiteschemesolve.jl:394)
+  cudaStream_t stream = nullptr;
+  // reductions
+  DevBuf<double> norm_part, norm_out, color_part, color_eps, color_sumsq;
+  DevBuf<unsigned> counters;
+  double* h_norm = nullptr;  // pinned [4]
+  int max_blocks = 0;
+  NormWork nw() const { return NormWork{norm_part.p, counters.p, norm_out.p, max_blocks}; }
+  ColorWork cw() const { return ColorWork{color_part.p, counters.p + 1, color_eps.p, color_sumsq.p}; }
+  template <int NN>
+  GridView<NN> grid_view() const {
+    GridView<NN> gv;
+    long long st = 1;
+    for (int d = 0; d < NN; ++d) {
+      gv.x[d] = grid[d].p;
+      gv.S[d] = S[d];
+      gv.stride[d] = st;
+      st *= S[d];
+    }
+    gv.l = st;
+    return gv;
+  }
+  ~Ctx();
+};
+
+struct Norms {
+  double sumsq, maxabs;
+  bool any_nan;
+  double norm2_over_n(long long n) const;  // NaN if any NaN, like norm(v)/length(v)
+};
+
+// Per-model kernel launchers (instantiated from the functor registry).
+struct ModelOps {
+  virtual ~ModelOps() = default;
+  virtual const char* name() const = 0;
+  virtual int N() const = 0;
+  virtual int F() const = 0;
+  virtual int nparams() const = 0;
+  virtual int nsaved() const = 0;
+  virtual bool box() const = 0;
+  virtual void residual(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm) const = 0;
+  virtual void jacobian(const Ctx& c, const double* y, const RowSpec& rs, int eps_policy, double* planes,
+                        double* r0) const = 0;
+  virtual void saved(const Ctx& c, const double* y, double* out) const = 0;
+  // fused batched engine; returns false if the model is not 1-D single-unknown
+  virtual bool batched(const struct BatchArgs& a, cudaStream_t s) const = 0;
+};
+const ModelOps* model_ops(int model_id);
+int model_count();
+
+// Linear solver behind each Newton iteration: J x = b with J in stencil planes.
+struct LinearSolver {
+  virtual ~LinearSolver() = default;
+  // returns 0 on success, 1 if the solve failed (singular / non-finite / not converged)
+  virtual int solve(const double* planes, const double* b, double* x, const econpdes_options& opt, int* iters,
+                    double* relres) = 0;
+};
+std::unique_ptr<LinearSolver> make_tridiag_solver(Ctx& c);
+std::unique_ptr<LinearSolver> make_krylov_solver(Ctx& c);  // krylov.cu
+
+struct NewtonOutcome {
+  double nl;        // ||R(zero)||_2/n, Inf if singular, NaN if NaN
+  int iters;
+  long long lin_iters;
+  bool singular;
+};
+
+class Solver {
+ public:
+  explicit Solver(std::unique_ptr<Ctx> ctx);
+  Ctx& ctx() { return *c_; }
+  Norms eval_G(const double* y, double* out);  // G!(ydot, y) + norms
+  Norms eval_R(const double* y, const double* ypost, double delta, double* out);
+  void jacobian(const double* y, const double* ypost, double delta, int eps_policy);
+  double* planes() { return planes_.p; }
+  LinearSolver& linear() { return *lin_; }
+  NewtonOutcome newton(const double* ypost, double delta, double ftol, int maxit, const econpdes_options& opt,
+                       double* y_out);
+  int solve(const econpdes_options& opt, econpdes_result* res);
+  void csc_gather(double* nzval_dev);
+  DevBuf<double> ypost_, y_, ynew_, R_, s_, G_, planes_;
+  long long nnz_ = 0;
+
+ private:
+  RowSpec row_spec(const double* ypost, double delta) const;
+  Norms read_norms();
+  double masked_norm(const double* ydot, const double* y);
+  std::unique_ptr<Ctx> c_;
+  const ModelOps* ops_;
+  std::unique_ptr<LinearSolver> lin_;
+  DevBuf<long long> csc_map_;
+};
+
+std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p);  // validates + uploads; throws
+void ensure_device();
+
+}  // namespace econpdes

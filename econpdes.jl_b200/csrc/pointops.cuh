@@ -166,7 +166,9 @@ EP_HD int ncolors_grid(const GridView<N>& gv) {
 // One block-row of the Jacobian of R = rowterms(G).  `emit(k, fin, fout, value)` receives
 // d R_fout(pt) / d y_fin(pt + off_k) for every stencil entry k of shape <N,BOX> (zero for
 // entries outside the grid).  r0 returns R(pt) itself (the unperturbed residual).
-template <class M, bool BOX, class Emit>
+// With HAVE_R0 the caller already holds R(pt) in r0 (FiniteDiff re-evaluates f(x); the
+// value is identical, so kernels that kept it skip that evaluation).
+template <class M, bool BOX, bool HAVE_R0 = false, class Emit>
 EP_HD void jacobian_point(const double* prm, const double* state, const PointGeom<M::N>& g, const long long* idx,
                           const GridView<M::N>& gv, double (*w)[ipow3(M::N)], const double (*bc_lo)[M::N],
                           const double (*bc_hi)[M::N], const RowTerms* rt, const double* eps_table,
@@ -174,10 +176,12 @@ EP_HD void jacobian_point(const double* prm, const double* state, const PointGeo
   constexpr int N = M::N, F = M::F;
   constexpr int C = (ipow3(N) - 1) / 2;
   using St = Stencil<N, BOX>;
-  double g0[F];
-  eval_point<M, false>(prm, state, g, w, bc_lo, bc_hi, g0, nullptr);
+  if (!HAVE_R0) {
+    double g0[F];
+    eval_point<M, false>(prm, state, g, w, bc_lo, bc_hi, g0, nullptr);
 #pragma unroll
-  for (int f = 0; f < F; ++f) r0[f] = apply_row_terms(g0[f], w[f][C], rt[f]);
+    for (int f = 0; f < F; ++f) r0[f] = apply_row_terms(g0[f], w[f][C], rt[f]);
+  }
   const int ncg = ncolors_grid<N>(gv);
 #pragma unroll
   for (int fin = 0; fin < F; ++fin) {

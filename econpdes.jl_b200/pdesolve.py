@@ -1,0 +1,506 @@
+"""Host side of the drop-in: `pdesolve(pde, grid, guess; ...) -> EconPDEResult`.
+
+Mirrors the reference's input normalisation (src/pdesolve.jl:96-133, 293-394) and result
+type (src/EconPDEs.jl:36-95), then makes ONE call into libeconpdes_cuda.so, which runs the
+whole pseudo-transient Newton loop on the GPU.  Nothing here computes a residual or a
+Jacobian: without the CUDA library the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import sys
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib as L
+from .models import RegisteredModel
+
+SQRT_EPS = math.sqrt(np.finfo(np.float64).eps)
+
+_REMOVED = {  # src/finiteschemesolve.jl:18-32
+    "maxdist": "`maxdist` was removed in EconPDEs 2.0; use `abstol` instead.",
+    "innerdist": "`innerdist` was removed in EconPDEs 2.0; use `inner_abstol` instead.",
+    "method": "`method` was removed in EconPDEs 2.0; use `alg = :newton`.",
+    "autodiff": "`autodiff` was removed in EconPDEs 2.0; EconPDEs configures its Jacobian internally.",
+    "algorithm": "`algorithm` was renamed in EconPDEs 2.0; use `alg` instead.",
+    "iterations": "`iterations` was renamed in EconPDEs 2.0; use `maxiters` instead.",
+    "inner_iterations": "`inner_iterations` was renamed in EconPDEs 2.0; use `inner_maxiters` instead.",
+    "J0": "`J0` was renamed in EconPDEs 2.0; use `jac_prototype` instead.",
+    "reformulation": "`reformulation` was removed in EconPDEs 2.0; bounded solves always use the minmax mixed-complementarity residual.",
+    "autoscale": "`autoscale` was removed in EconPDEs 2.0.",
+}
+_LOWER_LEVEL = {  # src/pdesolve.jl:1-8
+    "jac": "`jac` is only supported by `finiteschemesolve`; `pdesolve` constructs the discretized residual internally.",
+    "jac_prototype": "`jac_prototype` is only supported by `finiteschemesolve`; `pdesolve` builds the stencil sparsity pattern internally.",
+    "colorvec": "`colorvec` is only supported by `finiteschemesolve`; `pdesolve` computes the stencil coloring internally.",
+    "fdcache": "`fdcache` is internal and cannot be passed to `pdesolve`.",
+    "monotonicity_check": "`monotonicity_check` is internal; use `check_monotonicity` instead.",
+}
+
+
+@dataclass
+class EconPDEResult:
+    """src/EconPDEs.jl:36-48: solution, residual_norm, saved, tolerance; computed `converged`."""
+    solution: "OrderedDict[str, np.ndarray]"
+    residual_norm: float
+    saved: "OrderedDict[str, np.ndarray]"
+    tolerance: float
+    # extras the reference prints or warns with
+    exit_reason: int = 0
+    log: tuple = ()
+    n_outer: int = 0
+    n_newton: int = 0
+    n_linear_iters: int = 0
+    kernel_launches: int = 0
+    device_ms: float = 0.0
+
+    @property
+    def converged(self) -> bool:
+        return bool(self.residual_norm <= self.tolerance)
+
+    def __iter__(self):  # tuple destructuring: solution, residual_norm, saved = result
+        return iter((self.solution, self.residual_norm, self.saved))
+
+    def __repr__(self):  # compact show (src/EconPDEs.jl:60-95): names and sizes, not arrays
+        def fmt(d):
+            return ", ".join(f"{k} ({'×'.join(str(s) for s in v.shape)})" for k, v in d.items())
+        lines = ["EconPDEResult", f"  solution:      {fmt(self.solution)}"]
+        if self.saved:
+            lines.append(f"  saved:         {fmt(self.saved)}")
+        lines.append(f"  residual_norm: {self.residual_norm:.2e}")
+        lines.append(f"  converged:     {'true' if self.converged else 'false'} (tolerance {self.tolerance:.2e})")
+        return "\n".join(lines)
+
+
+def _as_ordered(x, what):
+    if isinstance(x, OrderedDict):
+        return x
+    if isinstance(x, dict):
+        # Python dicts keep insertion order (unlike Julia's Dict, src/pdesolve.jl:233-239)
+        return OrderedDict(x)
+    raise ValueError(f"pass {what} as a dict / OrderedDict of names to arrays")
+
+
+def _check_generated_names(statenames, ynames):
+    """src/pdesolve.jl:267-291."""
+    seen = {}
+
+    def reg(name, desc):
+        if name in seen:
+            raise ValueError(f"ambiguous names: the field `{name}` would mean both {seen[name]} and {desc}.")
+        seen[name] = desc
+    for s in ynames:
+        reg(s, f"the value of unknown `{s}`")
+        for x in statenames:
+            reg(f"{s}{x}_up", f"the forward derivative of `{s}` in `{x}`")
+            reg(f"{s}{x}_down", f"the backward derivative of `{s}` in `{x}`")
+            reg(f"{s}{x}{x}", f"the second derivative of `{s}` in `{x}`")
+        for i1, x1 in enumerate(statenames):
+            for x2 in statenames[i1 + 1:]:
+                reg(f"{s}{x1}{x2}", "the cross derivative")
+                reg(f"{s}{x1}{x2}_up", "the directional cross derivative")
+                reg(f"{s}{x1}{x2}_down", "the directional cross derivative")
+
+
+def _bc_array(bc, ynames, statenames, S):
+    """src/pdesolve.jl:312-335 (one slot per point; later dimensions overwrite earlier ones)."""
+    out = np.zeros(tuple(S) + (len(ynames),), order="F")
+    if bc is None:
+        return None
+    valid = [f"{y}{s}" for y in ynames for s in statenames]
+    for key in bc:
+        if key not in valid:
+            raise ValueError(f"unknown `bc` entry `{key}`: valid entries are {valid}, i.e. unknown+state")
+    for k, y in enumerate(ynames):
+        for d, s in enumerate(statenames):
+            key = f"{y}{s}"
+            if key not in bc:
+                continue
+            lo, hi = bc[key]
+            sl = [slice(None)] * len(S)
+            sl[d] = 0
+            out[tuple(sl) + (k,)] = lo
+            sl[d] = S[d] - 1
+            out[tuple(sl) + (k,)] = hi
+    return out
+
+
+def _per_unknown(val, ynames, S, default, dtype, keyword):
+    """_bound_array / _fill_is_algebraic / _delta_array, src/pdesolve.jl:293-394."""
+    F = len(ynames)
+    if val is None:
+        return None
+    out = np.full(tuple(S) + (F,), default, dtype=dtype, order="F")
+    if isinstance(val, dict):
+        extra = set(val) - set(ynames)
+        if extra:
+            raise ValueError(f"`{keyword}` contains names that are not in the initial guess: {sorted(extra)}")
+        if keyword != "Δ" and set(val) != set(ynames):
+            raise ValueError(f"`{keyword}` must have the same names as the initial guess")
+        for k, name in enumerate(ynames):
+            if name in val:
+                v = np.asarray(val[name])
+                if v.ndim != 0 and v.shape != tuple(S):
+                    raise ValueError(f"`{keyword}.{name}` has size {v.shape} but the state grid has size {tuple(S)}")
+                if dtype is bool and v.dtype != np.bool_:
+                    raise ValueError(f"`{keyword}.{name}` must be a Bool or an array of Bools")
+                out[..., k] = v
+        return out
+    v = np.asarray(val)
+    if v.ndim == 0:
+        out[...] = v
+    elif v.shape == tuple(S) + (F,):
+        out[...] = v
+    elif F == 1 and v.shape == tuple(S):
+        out[..., 0] = v
+    elif v.size == out.size:
+        out[...] = v.reshape(out.shape, order="F")
+    else:
+        raise ValueError(f"`{keyword}` has size {v.shape}")
+    return out
+
+
+def _options(abstol, maxiters, kw) -> L.Options:
+    lib = L.load()
+    o = L.Options()
+    lib.econpdes_default_options(C.byref(o))
+    o.abstol = abstol
+    o.maxiters = maxiters
+    names = {"scale": "scale", "minΔ": "min_delta", "min_delta": "min_delta", "maxΔ": "max_delta",
+             "max_delta": "max_delta", "max_residual_growth": "max_residual_growth",
+             "inner_maxiters": "inner_maxiters", "inner_abstol": "inner_abstol", "eps_policy": "eps_policy",
+             "lin_rtol": "lin_rtol", "lin_maxiters": "lin_maxiters", "lin_restart": "lin_restart",
+             "linear_solver": "linear_solver"}
+    for k in list(kw):
+        if k in names:
+            setattr(o, names[k], kw.pop(k))
+    return o
+
+
+def _print_log(res: EconPDEResult, description: str, file):
+    """The verbose table of src/finiteschemesolve.jl:403-404, 421, 435, 445, 453-455."""
+    print("Solving for " + description, file=file)
+    if res.n_outer > 0 or res.log:
+        print("Iter TimeStep Residual", file=file)
+        print("---- -------- --------", file=file)
+    for row in res.log:
+        if row["status"] == L.STEP_ACCEPTED:
+            print("%4d %8.2e %8.2e" % (row["iter"], row["delta"], row["residual"]), file=file)
+        elif row["status"] == L.STEP_REJECTED_GROWTH:
+            print("%4d %8.2e        ✗ (residual grew > max_residual_growth)" % (row["iter"], row["delta"]), file=file)
+        else:
+            reason = {L.STEP_REJECTED_NAN: " (model returned NaN)", L.STEP_REJECTED_SINGULAR: " (singular Jacobian)"}
+            print("%4d %8.2e        ✗%s" % (row["iter"], row["delta"], reason.get(row["status"], "")), file=file)
+    if res.converged and res.exit_reason == L.EXIT_CONVERGED:
+        ms = res.device_ms
+        t = "%.0fms" % ms if ms < 1000 else "%.1fs" % (ms / 1000)
+        print("Converged after %d time steps (%s)" % (res.n_outer, t), file=file)
+
+
+def _warn_text(res: EconPDEResult, min_delta: float) -> Optional[str]:
+    """@warn texts of src/finiteschemesolve.jl:387, 456-461."""
+    if res.converged:
+        return None
+    r, tol = "%.2e" % res.residual_norm, "%.2e" % res.tolerance
+    if res.exit_reason == L.EXIT_INF_STEP_FAILED:
+        return f"did not converge: residual {r} > tolerance {tol}. `Δ = Inf` disables pseudo-transient continuation"
+    if res.exit_reason == L.EXIT_BELOW_MIN_DELTA:
+        return (f"did not converge after {res.n_outer} time steps: the pseudo-transient time step fell below "
+                f"`minΔ` = {min_delta} (residual {r} > tolerance {tol}).")
+    return f"did not converge after {res.n_outer} time steps: residual {r} > tolerance {tol}."
+
+
+def pdesolve(pde, grid, guess, taus=None, *, is_algebraic=None, bc=None, lower_bound=None, upper_bound=None,
+             abstol=SQRT_EPS, verbose=True, warn=True, alg="newton", maxiters=100, check_monotonicity=False,
+             file=None, **kwargs) -> EconPDEResult:
+    """Stationary `pdesolve` on the GPU (src/pdesolve.jl:96-154).
+
+    `pde` must be a registered model (econpdes_b200.models): the device cannot call back into
+    a host closure per grid point.  `grid` / `guess` are dicts name -> array like the
+    reference's NamedTuples; `Δ` (or `delta`) may be a scalar or a dict per unknown.
+    """
+    import warnings
+    for k, msg in _REMOVED.items():
+        if k in kwargs:
+            raise ValueError(msg)
+    for k, msg in _LOWER_LEVEL.items():
+        if k in kwargs:
+            raise ValueError(msg)
+    if not isinstance(pde, RegisteredModel):
+        raise TypeError("the device path needs a registered model functor (econpdes_b200.models); arbitrary host "
+                        "closures `pde(state, u)` only run on the reference's CPU path")
+    if taus is not None:
+        raise NotImplementedError("time-dependent pdesolve(..., τs) is not on the device path yet (SURVEY.md 8f-2)")
+    if alg not in ("newton", ":newton"):
+        raise ValueError(f"NLsolve `alg` must be `:newton` on the device path; got `{alg!r}`")
+    grid = _as_ordered(grid, "the state grid")
+    guess = _as_ordered(guess, "the initial guess")
+    statenames, ynames = tuple(grid), tuple(guess)
+    _check_generated_names(list(statenames), list(ynames))
+    if statenames != tuple(pde.statenames) or ynames != tuple(pde.solnames):
+        raise ValueError(f"model `{pde.name}` expects states {pde.statenames} and unknowns {pde.solnames}; "
+                         f"got {statenames} and {ynames}")
+    grids = [np.ascontiguousarray(np.asarray(g, dtype=np.float64)) for g in grid.values()]
+    if any(g.ndim != 1 for g in grids):
+        raise ValueError("state grid entries must be vectors")
+    S = tuple(g.shape[0] for g in grids)
+    if any(s < 2 for s in S):
+        raise ValueError("state grid entries must have at least 2 points")
+    for name, v in guess.items():
+        if tuple(np.shape(v)) != S:
+            raise ValueError(f"the initial guess (e.g. terminal value) for `{name}` has size {np.shape(v)} "
+                             f"but the state grid has size {S}")
+    F = len(ynames)
+    guess_array = np.asfortranarray(np.stack([np.asarray(guess[k], dtype=np.float64) for k in ynames], axis=-1))
+    delta = kwargs.pop("Δ", kwargs.pop("delta", 1.0))
+    delta_arr = None
+    if isinstance(delta, dict):
+        delta_arr = _per_unknown(delta, ynames, S, 1.0, np.float64, "Δ")
+    bc_arr = _bc_array(bc, ynames, statenames, S)
+    alg_arr = _per_unknown(is_algebraic, ynames, S, False, bool, "is_algebraic")
+    lb_arr = _per_unknown(lower_bound, ynames, S, -np.inf, np.float64, "lower_bound")
+    ub_arr = _per_unknown(upper_bound, ynames, S, np.inf, np.float64, "upper_bound")
+    opts = _options(abstol, maxiters, kwargs)
+    if delta_arr is None:
+        opts.delta = float(delta)
+    if kwargs:
+        raise TypeError(f"unknown keyword arguments {sorted(kwargs)}")
+
+    lib = L.load()
+    mid = L.check(lib.econpdes_model_id(pde.name.encode()))
+    prm = pde.params()
+    p = L.Problem()
+    p.model_id, p.ndims, p.nfuncs, p.nparams = mid, len(S), F, prm.shape[0]
+    for d in range(len(S)):
+        p.size[d] = S[d]
+        p.grid[d] = L.dptr(grids[d])
+    keep = [prm, guess_array]
+    p.params = L.dptr(prm) if prm.shape[0] else None
+    p.guess = L.dptr(guess_array)
+
+    def fvec(a, dtype=np.float64):
+        if a is None:
+            return None
+        v = np.ascontiguousarray(a.reshape(-1, order="F"), dtype=dtype)
+        keep.append(v)
+        return v
+    v = fvec(bc_arr); p.bc = L.dptr(v)
+    v = fvec(alg_arr, np.uint8); p.is_algebraic = None if v is None else v.ctypes.data_as(L.c_uint8_p)
+    v = fvec(lb_arr); p.lower_bound = L.dptr(v)
+    v = fvec(ub_arr); p.upper_bound = L.dptr(v)
+    v = fvec(delta_arr); p.delta_vec = L.dptr(v)
+
+    n = int(np.prod(S)) * F
+    sol = np.empty(n)
+    nsaved = len(pde.savednames)
+    saved = np.empty(int(np.prod(S)) * nsaved) if nsaved else None
+    cap = max(int(maxiters), 1)
+    log = (L.LogRow * cap)()
+    r = L.Result()
+    r.solution = L.dptr(sol)
+    r.saved = L.dptr(saved)
+    r.log = log
+    r.log_capacity = cap
+    L.check(lib.econpdes_solve_stationary(C.byref(p), C.byref(opts), C.byref(r)))
+
+    ya = sol.reshape(S + (F,), order="F")
+    solution = OrderedDict((name, np.array(ya[..., k])) for k, name in enumerate(ynames))
+    sv = OrderedDict()
+    if nsaved:
+        sa = saved.reshape(S + (nsaved,), order="F")
+        sv = OrderedDict(solution)
+        for k, name in enumerate(pde.savednames):
+            sv[name] = np.array(sa[..., k])
+    rows = tuple(dict(iter=log[i].iter, status=log[i].status, newton_iters=log[i].newton_iters,
+                      linear_iters=log[i].linear_iters, delta=log[i].delta, residual=log[i].residual)
+                 for i in range(r.log_len))
+    res = EconPDEResult(solution, r.residual_norm, sv, abstol, r.exit_reason, rows, r.n_outer, r.n_newton,
+                        r.n_linear_iters, r.kernel_launches, r.device_ms)
+    if verbose:
+        desc = "%d %s (%s) on grid %s = %s" % (F, "unknown" if F == 1 else "unknowns", ", ".join(ynames),
+                                               "×".join(statenames), "×".join(str(s) for s in S))
+        _print_log(res, desc, file or sys.stdout)
+        if res.exit_reason == L.EXIT_ALREADY_ZERO:
+            warnings.warn("G! already returns zero with the initial value")
+    if warn:
+        txt = _warn_text(res, opts.min_delta)
+        if txt:
+            warnings.warn(txt)
+    return res
+
+
+@dataclass
+class BatchResult:
+    solution: np.ndarray       # [B, S]
+    residual_norm: np.ndarray  # [B]
+    converged: np.ndarray      # [B] bool
+    exit_reason: np.ndarray
+    n_outer: np.ndarray
+    n_newton: np.ndarray
+    device_ms: float
+    kernel_launches: int
+    log: Optional[list] = None
+
+
+def pdesolve_batched(model_cls, params: np.ndarray, grids: np.ndarray, guess: np.ndarray, *, abstol=SQRT_EPS,
+                     maxiters=100, log_capacity=0, **kwargs) -> BatchResult:
+    """B independent 1-D problems (a loop of `pdesolve` calls in the reference) in one launch.
+
+    params [B, nparams] (field order of `model_cls`), grids [B, S], guess [B, S].
+    """
+    lib = L.load()
+    delta = kwargs.pop("Δ", kwargs.pop("delta", 1.0))
+    opts = _options(abstol, maxiters, kwargs)
+    opts.delta = float(delta)
+    if kwargs:
+        raise TypeError(f"unknown keyword arguments {sorted(kwargs)}")
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    grids = np.ascontiguousarray(grids, dtype=np.float64)
+    guess = np.ascontiguousarray(guess, dtype=np.float64)
+    B, S = grids.shape
+    if guess.shape != (B, S):
+        raise ValueError(f"guess has shape {guess.shape}, expected {(B, S)}")
+    mid = L.check(lib.econpdes_model_id(model_cls.name.encode()))
+    h = C.c_void_p()
+    L.check(lib.econpdes_batch_create(mid, B, S, C.byref(h)))
+    try:
+        L.check(lib.econpdes_batch_upload(h, L.dptr(params) if params.size else None, L.dptr(grids), L.dptr(guess)))
+        if log_capacity:
+            L.check(lib.econpdes_batch_set_log_capacity(h, log_capacity))
+        ms = C.c_double()
+        L.check(lib.econpdes_batch_solve(h, C.byref(opts), C.byref(ms)))
+        sol = np.empty((B, S))
+        rn = np.empty(B)
+        er = np.empty(B, dtype=np.int32)
+        no = np.empty(B, dtype=np.int32)
+        nn = np.empty(B, dtype=np.int32)
+        logbuf = (L.LogRow * (B * log_capacity))() if log_capacity else None
+        loglen = np.zeros(B, dtype=np.int32)
+        L.check(lib.econpdes_batch_download(h, L.dptr(sol), L.dptr(rn), er.ctypes.data_as(L.c_int32_p),
+                                            no.ctypes.data_as(L.c_int32_p), nn.ctypes.data_as(L.c_int32_p),
+                                            logbuf, log_capacity, loglen.ctypes.data_as(L.c_int32_p) if log_capacity else None))
+        launches = lib.econpdes_batch_kernel_launches(h)
+        logs = None
+        if log_capacity:
+            logs = [[dict(iter=logbuf[b * log_capacity + i].iter, status=logbuf[b * log_capacity + i].status,
+                          newton_iters=logbuf[b * log_capacity + i].newton_iters,
+                          delta=logbuf[b * log_capacity + i].delta, residual=logbuf[b * log_capacity + i].residual)
+                     for i in range(loglen[b])] for b in range(B)]
+    finally:
+        lib.econpdes_batch_destroy(h)
+    return BatchResult(sol, rn, rn <= abstol, er, no, nn, ms.value, launches, logs)
+
+
+class Handle:
+    """Repeated residual / Jacobian / Newton-step evaluations on one device-resident problem
+    (the `G!`, `finite_difference_jacobian!` and `implicit_timestep` seams of
+    src/finiteschemesolve.jl:153-230)."""
+
+    def __init__(self, pde: RegisteredModel, grids, guess_array: np.ndarray, bc: Optional[np.ndarray] = None):
+        lib = L.load()
+        self.lib = lib
+        self.model = pde
+        self.grids = [np.ascontiguousarray(g, dtype=np.float64) for g in grids]
+        self.S = tuple(g.shape[0] for g in self.grids)
+        self.F = pde.nfuncs
+        self.n = int(np.prod(self.S)) * self.F
+        self._prm = pde.params()
+        self._guess = np.ascontiguousarray(np.asarray(guess_array, dtype=np.float64).reshape(-1, order="F"))
+        self._bc = None if bc is None else np.ascontiguousarray(np.asarray(bc, dtype=np.float64).reshape(-1, order="F"))
+        p = L.Problem()
+        p.model_id = L.check(lib.econpdes_model_id(pde.name.encode()))
+        p.ndims, p.nfuncs, p.nparams = len(self.S), self.F, self._prm.shape[0]
+        for d, g in enumerate(self.grids):
+            p.size[d] = self.S[d]
+            p.grid[d] = L.dptr(g)
+        p.params = L.dptr(self._prm) if self._prm.shape[0] else None
+        p.guess = L.dptr(self._guess)
+        p.bc = L.dptr(self._bc)
+        self.h = C.c_void_p()
+        L.check(lib.econpdes_create(C.byref(p), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.lib.econpdes_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _vec(self, a):
+        return np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1, order="F"))
+
+    def residual(self, y):
+        yv = self._vec(y)
+        out = np.empty(self.n)
+        L.check(self.lib.econpdes_residual(self.h, L.dptr(yv), L.dptr(out)))
+        return out
+
+    def saved(self, y):
+        ns = len(self.model.savednames)
+        yv = self._vec(y)
+        out = np.empty(int(np.prod(self.S)) * max(ns, 1))
+        L.check(self.lib.econpdes_saved(self.h, L.dptr(yv), L.dptr(out)))
+        return out.reshape(self.S + (max(ns, 1),), order="F")
+
+    def jacobian_csc(self, y, ypost=None, delta=math.inf, eps_policy=L.EPS_FINITEDIFF_COLOR_NORM):
+        yv = self._vec(y)
+        yp = None if ypost is None else self._vec(ypost)
+        size = (C.c_int64 * len(self.S))(*self.S)
+        nnz = self.lib.econpdes_stencil_nnz(len(self.S), size, self.F)
+        nz = np.empty(nnz)
+        ncol = self.F * int(np.prod([min(3, s) for s in self.S]))
+        eps = np.empty(ncol)
+        L.check(self.lib.econpdes_jacobian_csc(self.h, L.dptr(yv), L.dptr(yp), float(delta), eps_policy, L.dptr(nz),
+                                               L.dptr(eps)))
+        return nz, eps
+
+    def linear_solve(self, b, **kw):
+        opts = _options(SQRT_EPS, 100, kw)
+        bv = self._vec(b)
+        x = np.empty(self.n)
+        it = C.c_int32()
+        rr = C.c_double()
+        rc = L.check(self.lib.econpdes_linear_solve(self.h, C.byref(opts), L.dptr(bv), L.dptr(x), C.byref(it),
+                                                    C.byref(rr)))
+        return x, it.value, rr.value, rc
+
+    def implicit_timestep(self, ypost, delta, maxiters=10, abstol=SQRT_EPS, **kw):
+        opts = _options(SQRT_EPS, 100, kw)
+        yp = self._vec(ypost)
+        out = np.empty(self.n)
+        nl = C.c_double()
+        it = C.c_int32()
+        L.check(self.lib.econpdes_implicit_timestep(self.h, C.byref(opts), L.dptr(yp), float(delta), maxiters, abstol,
+                                                    L.dptr(out), C.byref(nl), C.byref(it)))
+        return out, nl.value, it.value
+
+
+def stencil_colors(S, F) -> np.ndarray:
+    """stencil_colors(S, F), src/utils/coloring.jl:52-70 (host-only entry point)."""
+    lib = L.load()
+    S = tuple(int(s) for s in S)
+    size = (C.c_int64 * len(S))(*S)
+    out = np.empty(int(np.prod(S)) * F, dtype=np.int64)
+    L.check(lib.econpdes_stencil_colors(len(S), size, F, out.ctypes.data_as(L.c_int64_p)))
+    return out
+
+
+def stencil_pattern(S, F):
+    """local_stencil_jacobian(S, F) as 1-based CSC (colptr, rowval), src/utils/coloring.jl:18-35."""
+    lib = L.load()
+    S = tuple(int(s) for s in S)
+    size = (C.c_int64 * len(S))(*S)
+    nnz = L.check(lib.econpdes_stencil_nnz(len(S), size, F))
+    colptr = np.empty(int(np.prod(S)) * F + 1, dtype=np.int64)
+    rowval = np.empty(nnz, dtype=np.int64)
+    L.check(lib.econpdes_stencil_pattern(len(S), size, F, colptr.ctypes.data_as(L.c_int64_p),
+                                         rowval.ctypes.data_as(L.c_int64_p)))
+    return colptr, rowval

@@ -1,0 +1,210 @@
+/* libeconpdes_cuda.so -- C ABI of the B200-native finite-scheme hot path of EconPDEs.jl.
+ *
+ * The reference (EconPDEs.jl v3.0.0) has no FFI: its seams are Julia functions.  This
+ * header declares the flat C entry points a Julia `ccall` shim (julia/EconPDEsCUDA.jl,
+ * INTEGRATION.md) or the Python ctypes host (econpdes.jl_b200/) binds.  Every entry point
+ * cites the reference interface it replaces (file:line relative to the reference root).
+ *
+ * Conventions
+ *  - All arrays are FP64, column-major, laid out (S_1..S_N, F) exactly like the reference's
+ *    `guess_array` (src/pdesolve.jl:111); `vec` of it is the unknown vector y.
+ *  - Pointers in `econpdes_problem`/`econpdes_result` are HOST pointers owned by the caller;
+ *    the library copies host->device at entry and device->host at exit and keeps every field
+ *    device-resident in between.  Functions suffixed `_device` take/return device pointers.
+ *  - Return value 0 = success, < 0 = error (ECONPDES_E_*); the message is available from
+ *    econpdes_last_error() (thread-local).  Non-convergence is NOT an error: it is
+ *    `converged = 0` plus an `exit_reason`, like the reference's @warn paths
+ *    (src/finiteschemesolve.jl:452-463).
+ *  - There is no CPU fallback: every compute entry point fails with ECONPDES_E_NO_DEVICE when
+ *    no CUDA device is usable.  econpdes_stencil_colors/pattern/nnz, econpdes_model_* and
+ *    econpdes_default_options are host-only and work without a GPU.
+ */
+#ifndef ECONPDES_CUDA_H
+#define ECONPDES_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECONPDES_ABI_VERSION 1
+#define ECONPDES_MAX_DIMS 3
+#define ECONPDES_MAX_FUNCS 4
+#define ECONPDES_MAX_PARAMS 16
+
+/* error codes */
+#define ECONPDES_OK 0
+#define ECONPDES_E_INVALID (-1)      /* bad argument (the reference's ArgumentError paths) */
+#define ECONPDES_E_NAN_GUESS (-2)    /* "G! returns NaN with the initial value", finiteschemesolve.jl:372 */
+#define ECONPDES_E_NO_DEVICE (-3)    /* no usable CUDA device: there is no CPU fallback */
+#define ECONPDES_E_CUDA (-4)         /* CUDA runtime error */
+#define ECONPDES_E_UNSUPPORTED (-5)  /* valid in the reference, not implemented on the device path yet */
+#define ECONPDES_E_NCCL (-6)
+
+/* exit_reason (src/finiteschemesolve.jl:373-389, 452-463) */
+#define ECONPDES_EXIT_CONVERGED 0
+#define ECONPDES_EXIT_ALREADY_ZERO 1      /* :373-375 */
+#define ECONPDES_EXIT_MAXITERS 2          /* :461 */
+#define ECONPDES_EXIT_BELOW_MIN_DELTA 3   /* :456-459 */
+#define ECONPDES_EXIT_INF_STEP_FAILED 4   /* :387 */
+
+/* per-step status (src/finiteschemesolve.jl:418-450) */
+#define ECONPDES_STEP_ACCEPTED 0
+#define ECONPDES_STEP_REJECTED_GROWTH 1   /* :425 */
+#define ECONPDES_STEP_REJECTED_INNER 2    /* :439 */
+#define ECONPDES_STEP_REJECTED_NAN 3      /* :443 "(model returned NaN)" */
+#define ECONPDES_STEP_REJECTED_SINGULAR 4 /* :444 "(singular Jacobian)" */
+
+/* eps_policy */
+#define ECONPDES_EPS_FINITEDIFF_COLOR_NORM 0 /* FiniteDiff.jl: one step per color, sqrt(eps)*max(1,sqrt(||x.*mask||)) */
+#define ECONPDES_EPS_PER_COLUMN 1            /* sqrt(eps)*max(1,|x_j|): robust option, not reference parity */
+
+/* linear_solver */
+#define ECONPDES_LIN_AUTO 0      /* 1-D: (block-)tridiagonal cyclic reduction; 2-D/3-D: Krylov + multigrid */
+#define ECONPDES_LIN_GMRES_MG 1
+#define ECONPDES_LIN_BICGSTAB_MG 2
+
+typedef struct econpdes_problem {
+  int32_t model_id;                 /* econpdes_model_id(name) */
+  int32_t ndims;                    /* N: number of state variables (StateGrid, src/utils/stategrid.jl:8-29) */
+  int32_t nfuncs;                   /* F: number of unknown functions */
+  int32_t nparams;
+  int64_t size[ECONPDES_MAX_DIMS];  /* S_d >= 2 (stategrid.jl:16) */
+  const double* grid[ECONPDES_MAX_DIMS]; /* coordinate vector per dimension, may be non-uniform */
+  const double* params;             /* model struct fields, order given by econpdes_model_info */
+  const double* guess;              /* (S.., F) column-major                         src/pdesolve.jl:111 */
+  const double* bc;                 /* (S.., F) or NULL = zeros (reflecting)         src/pdesolve.jl:312-335 */
+  const uint8_t* is_algebraic;      /* (S.., F) or NULL = all false                  src/pdesolve.jl:109,112 */
+  const double* lower_bound;        /* (S.., F) or NULL = -Inf                       src/pdesolve.jl:114 */
+  const double* upper_bound;        /* (S.., F) or NULL = +Inf                       src/pdesolve.jl:115 */
+  const double* delta_vec;          /* (S.., F) signed per-equation steps or NULL = scalar options.delta
+                                       src/pdesolve.jl:376-394, finiteschemesolve.jl:393-399 */
+} econpdes_problem;
+
+/* keyword arguments of finiteschemesolve (src/finiteschemesolve.jl:343; docs/src/solver.md:286-298) */
+typedef struct econpdes_options {
+  double abstol;               /* sqrt(eps) */
+  double inner_abstol;         /* sqrt(eps) */
+  double delta;                /* 1.0; +-Inf = one-shot solve without continuation */
+  double scale;                /* 10.0 */
+  double min_delta;            /* 1e-9 */
+  double max_delta;            /* Inf */
+  double max_residual_growth;  /* 10.0 */
+  int32_t maxiters;            /* 100 */
+  int32_t inner_maxiters;      /* 10 */
+  int32_t eps_policy;          /* ECONPDES_EPS_* */
+  int32_t linear_solver;       /* ECONPDES_LIN_* */
+  double lin_rtol;             /* relative residual target of the Krylov solve (1e-12) */
+  int32_t lin_maxiters;        /* Krylov iteration cap per solve (2000) */
+  int32_t lin_restart;         /* GMRES restart length (40) */
+} econpdes_options;
+
+typedef struct econpdes_log_row {
+  int32_t iter;
+  int32_t status;        /* ECONPDES_STEP_* */
+  int32_t newton_iters;
+  int32_t linear_iters;  /* Krylov iterations summed over the Newton iterations of this step */
+  double delta;          /* stepper.Δ printed in the TimeStep column (finiteschemesolve.jl:421) */
+  double residual;       /* ||G||_2/n at the accepted point; NaN on rejected steps */
+} econpdes_log_row;
+
+typedef struct econpdes_result {
+  double* solution;        /* out: (S.., F), caller-allocated */
+  double* saved;           /* out: (S.., NSAVED) or NULL     (_fill_saved!, src/pdesolve.jl:424-433) */
+  econpdes_log_row* log;   /* out: caller-allocated, log_capacity rows (or NULL) */
+  int32_t log_capacity;
+  int32_t log_len;
+  double residual_norm;    /* ||G(y)||_2 / n */
+  int32_t converged;       /* residual_norm <= abstol (src/EconPDEs.jl:44-48) */
+  int32_t exit_reason;     /* ECONPDES_EXIT_* */
+  int32_t n_outer;
+  int32_t n_newton;
+  int64_t n_linear_iters;
+  int64_t kernel_launches; /* kernels of this library launched during the call */
+  double device_ms;        /* CUDA-event time of the solve proper (between the H2D and D2H copies) */
+} econpdes_result;
+
+int econpdes_abi_version(void);
+const char* econpdes_last_error(void);
+
+/* --- model registry: replaces dispatch on typeof(pde) (callable structs, e.g.
+ *     examples/asset_pricing/bansal_yaron.jl:22-32) --- */
+int econpdes_model_count(void);
+int econpdes_model_id(const char* name);            /* < 0 if unknown */
+const char* econpdes_model_name(int model_id);
+int econpdes_model_info(int model_id, int32_t* ndims, int32_t* nfuncs, int32_t* nparams, int32_t* nsaved,
+                        int32_t* box_stencil);
+
+/* --- sparsity pattern + coloring, host-only, bit-exact with the reference --- */
+/* stencil_colors(S, F), src/utils/coloring.jl:52-70; colors_out[l*F], 1-based */
+int econpdes_stencil_colors(int ndims, const int64_t* size, int nfuncs, int64_t* colors_out);
+/* nnz of local_stencil_jacobian(S, F) = F^2 prod(3 S_d - 2), src/utils/coloring.jl:18-35 */
+int64_t econpdes_stencil_nnz(int ndims, const int64_t* size, int nfuncs);
+/* CSC pattern of local_stencil_jacobian: colptr[l*F+1], rowval[nnz], 1-based, rows sorted */
+int econpdes_stencil_pattern(int ndims, const int64_t* size, int nfuncs, int64_t* colptr, int64_t* rowval);
+
+void econpdes_default_options(econpdes_options* opts);
+
+/* --- one-shot stationary solve: replaces finiteschemesolve behind pdesolve
+ *     (src/pdesolve.jl:136-154 -> src/finiteschemesolve.jl:343-465) --- */
+int econpdes_solve_stationary(const econpdes_problem* problem, const econpdes_options* options,
+                              econpdes_result* result);
+
+/* --- handle API for repeated residual / Jacobian evaluations --- */
+typedef struct econpdes_handle econpdes_handle;
+int econpdes_create(const econpdes_problem* problem, econpdes_handle** out);
+void econpdes_destroy(econpdes_handle* h);
+/* G!(ydot, y): pde!, src/pdesolve.jl:436-462 */
+int econpdes_residual(econpdes_handle* h, const double* y, double* ydot);
+/* second NamedTuple of the model on the whole grid: _fill_saved!, src/pdesolve.jl:424-433 */
+int econpdes_saved(econpdes_handle* h, const double* y, double* saved);
+/* finite_difference_jacobian!(J, G_helper!, y, fdcache) as called at finiteschemesolve.jl:184:
+ * nzval of the CSC pattern above for R(y) = G(y) - (!alg)(ypost - y)/delta  (ypost NULL: R = G).
+ * eps_out (may be NULL) receives the per-color steps, length F*prod(min(3,S_d)). */
+int econpdes_jacobian_csc(econpdes_handle* h, const double* y, const double* ypost, double delta,
+                          int32_t eps_policy, double* nzval, double* eps_out);
+/* one linear solve J x = b with the solver the Newton loop uses (J from the last
+ * econpdes_jacobian_csc call); replaces Julia's `J \ b` (UMFPACK) reached through NLsolve */
+int econpdes_linear_solve(econpdes_handle* h, const econpdes_options* options, const double* b, double* x,
+                          int32_t* iters_out, double* relres_out);
+/* implicit_timestep(G!, ypost, delta; ...), src/finiteschemesolve.jl:153-230: one Newton solve of
+ * the implicit-Euler step.  y_out (n) receives the Newton result, nl_residual ||R||_2/n. */
+int econpdes_implicit_timestep(econpdes_handle* h, const econpdes_options* options, const double* ypost,
+                               double delta, int32_t maxiters, double abstol, double* y_out,
+                               double* nl_residual, int32_t* newton_iters);
+/* finiteschemesolve on the handle's problem starting from its guess */
+int econpdes_solve(econpdes_handle* h, const econpdes_options* options, econpdes_result* result);
+
+/* --- batched sweep of independent 1-D, single-unknown problems (config C4): every problem
+ *     is its own pdesolve call in the reference; here one thread block owns one problem and
+ *     runs its whole pseudo-transient loop on chip. --- */
+typedef struct econpdes_batch econpdes_batch;
+/* params[B][nparams], grids[B][S], guess[B][S] (host, row-major over the batch) */
+int econpdes_batch_create(int model_id, int64_t nproblems, int64_t npoints, econpdes_batch** out);
+void econpdes_batch_destroy(econpdes_batch* b);
+int econpdes_batch_upload(econpdes_batch* b, const double* params, const double* grids, const double* guess);
+/* keep up to log_capacity iteration-log rows per problem (0 = no log, the default) */
+int econpdes_batch_set_log_capacity(econpdes_batch* b, int32_t log_capacity);
+int econpdes_batch_solve(econpdes_batch* b, const econpdes_options* options, double* device_ms);
+/* solution[B][S], residual_norm[B], exit_reason[B], n_outer[B], n_newton[B]; any may be NULL.
+ * log rows (optional): log[B][log_capacity], log_len[B]. */
+int econpdes_batch_download(econpdes_batch* b, double* solution, double* residual_norm, int32_t* exit_reason,
+                            int32_t* n_outer, int32_t* n_newton, econpdes_log_row* log, int32_t log_capacity,
+                            int32_t* log_len);
+int64_t econpdes_batch_kernel_launches(const econpdes_batch* b);
+/* upload + solve + download in one call (the end-to-end path a pdesolve loop replaces) */
+int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, const double* params,
+                           const double* grids, const double* guess, const econpdes_options* options,
+                           double* solution, double* residual_norm, int32_t* exit_reason, int32_t* n_outer,
+                           int32_t* n_newton);
+
+/* --- device / multi-GPU plumbing --- */
+int econpdes_device_count(void);
+int econpdes_set_device(int device);
+int64_t econpdes_total_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECONPDES_CUDA_H */

@@ -1,0 +1,115 @@
+"""No-GPU checks of the drop-in boundary: the C-ABI library builds for sm_100a, loads, exports
+every symbol include/econpdes_cuda.h declares, its host-only entry points (pattern, coloring,
+model registry, default options) are bit-exact with the oracle, and compute entry points
+fail loudly without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import econpdes_b200 as E
+from econpdes_b200 import _lib as L
+from econpdes_b200 import models as PM
+from oracle import econpdes_oracle as eo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ep_build", os.path.join(ROOT, "econpdes.jl_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build()
+    return L.load()
+
+
+def test_header_symbols_all_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "econpdes_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(econpdes_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(L.SYMBOLS), declared ^ set(L.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.econpdes_abi_version() == 1
+
+
+def test_model_registry_matches_python_mirror(lib):
+    assert lib.econpdes_model_count() == len(PM.ALL_MODELS)
+    for cls in PM.ALL_MODELS:
+        mid = lib.econpdes_model_id(cls.name.encode())
+        assert mid >= 0, cls.name
+        nd, nf, npar, ns, box = (C.c_int32() for _ in range(5))
+        assert lib.econpdes_model_info(mid, nd, nf, npar, ns, box) == 0
+        m = cls()
+        assert (nd.value, nf.value, npar.value, ns.value) == (m.ndims, m.nfuncs, m.params().shape[0], len(m.savednames))
+        assert lib.econpdes_model_name(mid).decode() == cls.name
+    assert lib.econpdes_model_id(b"no_such_model") < 0
+    assert b"no_such_model" in lib.econpdes_last_error()
+
+
+def test_default_options_are_the_reference_keywords(lib):
+    # src/finiteschemesolve.jl:343, docs/src/solver.md:286-298
+    o = L.Options()
+    lib.econpdes_default_options(C.byref(o))
+    assert o.abstol == o.inner_abstol == eo.SQRT_EPS
+    assert (o.delta, o.scale, o.min_delta, o.max_residual_growth) == (1.0, 10.0, 1e-9, 10.0)
+    assert o.max_delta == float("inf") and o.maxiters == 100 and o.inner_maxiters == 10
+    assert o.eps_policy == L.EPS_FINITEDIFF_COLOR_NORM
+
+
+@pytest.mark.parametrize("S,F", [((5,), 1), ((2,), 2), ((4, 5), 2), ((2, 5), 1), ((3, 4, 5), 2), ((2, 2, 2, 2), 1),
+                                 ((64, 128), 1)])
+def test_pattern_and_colors_bit_exact(lib, S, F):
+    # test/runtests.jl:294-312, 491-502, 509-524
+    colors = E.stencil_colors(S, F)
+    np.testing.assert_array_equal(colors, eo.stencil_colors(S, F))
+    colptr, rowval = E.stencil_pattern(S, F)
+    cp, rv = eo.local_stencil_jacobian(S, F)
+    np.testing.assert_array_equal(colptr, cp)
+    np.testing.assert_array_equal(rowval, rv)
+    assert rowval.shape[0] == F * F * int(np.prod([3 * s - 2 for s in S]))
+    assert colors.max() == F * int(np.prod([min(3, s) for s in S]))
+
+
+def test_pattern_520_and_16_colors(lib):
+    colptr, rowval = E.stencil_pattern((4, 5), 2)
+    assert colptr.shape[0] - 1 == 40 and rowval.shape[0] == 520
+    assert E.stencil_colors((2, 2, 2, 2), 1).max() == 16
+    with pytest.raises(E.EconPDEsCudaError):
+        E.stencil_colors((1,), 1)          # at least 2 points per dimension (stategrid.jl:16)
+
+
+def test_compute_fails_loudly_without_device(lib):
+    if lib.econpdes_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(E.EconPDEsCudaError) as ei:
+        E.pdesolve(PM.ReadmeLinear(), {"x": np.linspace(0, 1, 50)}, {"v": np.zeros(50)}, verbose=False)
+    assert ei.value.code == L.E_NO_DEVICE and "no CPU fallback" in str(ei.value)
+    with pytest.raises(E.EconPDEsCudaError) as ei:
+        E.pdesolve_batched(PM.ReadmeLinear, np.array([[0.05, 0.2]]), np.linspace(0, 1, 50)[None], np.zeros((1, 50)))
+    assert ei.value.code == L.E_NO_DEVICE
+
+
+def test_host_side_normalisation_errors():
+    # src/pdesolve.jl:96-133 argument checks that need no device
+    g = {"k": np.linspace(1, 2, 10)}
+    with pytest.raises(TypeError):
+        E.pdesolve(lambda s, u: None, g, {"v": np.zeros(10)}, verbose=False)
+    with pytest.raises(ValueError, match="size"):
+        E.pdesolve(PM.GrowthTest(), g, {"v": np.zeros(3)}, verbose=False)
+    with pytest.raises(ValueError, match="at least 2 points"):
+        E.pdesolve(PM.GrowthTest(), {"k": np.array([1.0])}, {"v": np.zeros(1)}, verbose=False)
+    with pytest.raises(ValueError, match="unknown `bc` entry"):
+        E.pdesolve(PM.GrowthTest(), g, {"v": np.zeros(10)}, bc={"vx": (0, 0)}, verbose=False)
+    with pytest.raises(ValueError, match="removed"):
+        E.pdesolve(PM.GrowthTest(), g, {"v": np.zeros(10)}, maxdist=1e-6, verbose=False)
+    with pytest.raises(ValueError, match="only supported by `finiteschemesolve`"):
+        E.pdesolve(PM.GrowthTest(), g, {"v": np.zeros(10)}, colorvec=np.ones(10), verbose=False)
+    with pytest.raises(ValueError, match="ambiguous names"):
+        from econpdes_b200.pdesolve import _check_generated_names
+        _check_generated_names(["k", "a"], ["v", "vk"])

@@ -1,0 +1,347 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU
+oracle on the same seeded inputs and against the committed golden fixtures.
+
+Tolerances (BASELINE.json north_star): 1e-8 relative on every value function, 1e-10 on
+the final residual norm, same converged flag.  Residual sweeps are compared at the ulp
+level (CUDA's pow/log differ from glibc's by <= 2 ulp; +,-,*,/,sqrt are IEEE-exact and the
+kernels are built with -fmad=false).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import econpdes_b200 as E
+from econpdes_b200 import models as PM
+from oracle import econpdes_oracle as eo
+from oracle import models as OM
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+INF = math.inf
+
+
+def _cases():
+    out = []
+    g, gu = OM.readme_linear_problem(50)
+    out.append(("readme", PM.ReadmeLinear(), OM.readme_linear(), g, gu))
+    g, gu, prm = OM.campbell_cochrane_problem(sn=300)
+    out.append(("cc", PM.CampbellCochraneModel(**prm), OM.campbell_cochrane(**prm), g, gu))
+    g, gu, prm = OM.bansal_yaron_problem(37, 29)
+    out.append(("by", PM.BansalYaronModel(**prm), OM.bansal_yaron(**prm), g, gu))
+    g, gu, prm = OM.ahlm_diffusion_problem(9, 70)
+    out.append(("ahlm", PM.AchdouHanLasryLionsMollModel_Diffusion(**prm), OM.ahlm_diffusion(**prm), g, gu))
+    g, gu, prm = OM.hjb3d_problem(9)
+    gu = {"v": 20.0 + np.zeros((9, 9, 9))}
+    out.append(("hjb3d", PM.Hjb3dSynth(**prm), OM.hjb3d_synth(**prm), g, gu))
+    g, gu, prm = OM.neoclassical_growth_problem(90)
+    out.append(("growth", PM.NeoclassicalGrowthModel(**prm), OM.neoclassical_growth(**prm), g, gu))
+    g = {"x": OM.julia_range(0.1, 1, 5)}
+    out.append(("fwdprice", PM.ForwardPrice(), OM.forward_price(), g, {"v": np.ones(5), "p": np.ones(5) * 0.5}))
+    return out
+
+
+CASES = _cases()
+
+
+def _perturbed(gu, seed=1):
+    rng = np.random.default_rng(seed)
+    return np.stack([v * (1 + 0.01 * rng.uniform(-1, 1, v.shape)) + 1e-3 * rng.uniform(-1, 1, v.shape)
+                     for v in gu.values()], axis=-1)
+
+
+def _ulp_close(got, want, ulps):
+    scale = np.maximum(np.abs(want), np.abs(want).max() * 1e-3)
+    np.testing.assert_array_less(np.abs(got - want), ulps * np.finfo(float).eps * scale + 1e-300)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_residual_sweep(case):
+    name, pm, om, g, gu = case
+    grids = list(g.values())
+    y = _perturbed(gu)
+    prob = eo.Problem(om, tuple(g), grids, tuple(gu))
+    want = prob.G(y.reshape(-1, order="F"))
+    h = E.Handle(pm, grids, y)
+    got = h.residual(y)
+    h.close()
+    if name in ("readme", "by", "hjb3d", "fwdprice"):
+        np.testing.assert_array_equal(got, want)      # IEEE-exact operations only
+    else:
+        _ulp_close(got, want, 64)                     # log/pow: a few ulp, amplified by cancellation
+
+
+def test_residual_with_boundary_values():
+    pm, om = PM.Hjb3dSynth(), OM.hjb3d_synth(**OM.HJB3D_DEFAULT)
+    rng = np.random.default_rng(3)
+    grids = [np.cumsum(rng.uniform(0.05, 0.2, s)) for s in (7, 5, 6)]
+    y = rng.normal(size=(7, 5, 6, 1)) + 10
+    bc = rng.normal(size=(7, 5, 6, 1))
+    prob = eo.Problem(om, ("x", "y", "z"), grids, ("v",), bc)
+    want = prob.G(y.reshape(-1, order="F"))
+    h = E.Handle(pm, grids, y, bc=bc)
+    np.testing.assert_array_equal(h.residual(y), want)
+    h.close()
+
+
+def test_saved_outputs():
+    _, pm, om, g, gu = [c for c in CASES if c[0] == "ahlm"][0]
+    grids = list(g.values())
+    y = _perturbed(gu)
+    sv = eo.Problem(om, tuple(g), grids, tuple(gu)).saved(y.reshape(-1, order="F"))
+    h = E.Handle(pm, grids, y)
+    got = h.saved(y)
+    h.close()
+    np.testing.assert_allclose(got[..., 0], sv["mua"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(got[..., 1], sv["c"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("delta", [1.0, INF])
+def test_colored_fd_jacobian(case, delta):
+    name, pm, om, g, gu = case
+    grids = list(g.values())
+    S = tuple(len(x) for x in grids)
+    F = len(gu)
+    y, ypost = _perturbed(gu), _perturbed(gu, seed=2)
+    yv, ypv = y.reshape(-1, order="F"), ypost.reshape(-1, order="F")
+    prob = eo.Problem(om, tuple(g), grids, tuple(gu))
+    cache = eo.JacobianCache(S, F)
+
+    def R(v):
+        with np.errstate(all="ignore"):
+            return prob.G(v) - (ypv - v) / delta
+    nz_want, eps_want = eo.finite_difference_jacobian(R, yv, cache)
+    h = E.Handle(pm, grids, y)
+    nz, eps = h.jacobian_csc(y, ypost, delta)
+    h.close()
+    np.testing.assert_allclose(eps, eps_want, rtol=1e-14)
+    # finite-difference noise: ulp-level residual differences divided by eps ~ 1e-8
+    np.testing.assert_allclose(nz, nz_want, rtol=0, atol=2e-6 * np.abs(nz_want).max())
+
+
+def _check_against(res, ora, rtol=1e-8):
+    assert res.converged == ora.converged
+    for k in ora.solution:
+        np.testing.assert_allclose(res.solution[k], ora.solution[k], rtol=rtol, atol=rtol * 1e-3)
+    assert abs(res.residual_norm - ora.residual_norm) <= 1e-10
+    assert res.n_outer == ora.log.n_outer
+    assert [r["status"] for r in res.log] == [r[3] for r in ora.log.rows]
+    assert [r["newton_iters"] for r in res.log] == [r[4] for r in ora.log.rows]
+    for r, o in zip(res.log, ora.log.rows):
+        assert "%.2e" % r["delta"] == "%.2e" % o[1]
+
+
+def test_readme_quickstart_trace(capsys):
+    # README.md:72-82, through the generic engine
+    g, gu = OM.readme_linear_problem(50)
+    res = E.pdesolve(PM.ReadmeLinear(), g, gu)
+    out = capsys.readouterr().out
+    assert "Solving for 1 unknown (v) on grid x = 50" in out
+    for line in ("   1 1.00e+00 7.51e-02", "   2 1.09e+01 4.45e-02", "   3 1.85e+03 4.67e-04", "   4 1.76e+08"):
+        assert line in out
+    assert "Converged after 4 time steps" in out
+    assert res.converged and res.residual_norm < 1e-9
+    assert "EconPDEResult" in repr(res) and "v (50)" in repr(res) and "tolerance 1.49e-08" in repr(res)
+    _check_against(res, eo.pdesolve(OM.readme_linear(), g, gu))
+    assert res.kernel_launches > 0
+
+
+def test_campbell_cochrane_trace(capsys):
+    # docs/src/solver.md:66-73
+    g, gu, prm = OM.campbell_cochrane_problem()
+    res = E.pdesolve(PM.CampbellCochraneModel(**prm), g, gu)
+    out = capsys.readouterr().out
+    for line in ("   1 1.00e+00 2.51e-02", "   2 1.12e+01 1.21e-02", "   3 2.33e+03 8.01e-05", "   4 3.50e+08"):
+        assert line in out
+    _check_against(res, eo.pdesolve(OM.campbell_cochrane(**prm), g, gu))
+
+
+def test_growth_eleven_outer_iterations():
+    # examples/details.tex:173 -- exercises rejected steps and the epsilon rule
+    g, gu, prm = OM.neoclassical_growth_problem(1000)
+    res = E.pdesolve(PM.NeoclassicalGrowthModel(**prm), g, gu, verbose=False)
+    ora = eo.pdesolve(OM.neoclassical_growth(**prm), g, gu)
+    assert res.n_outer == 11
+    _check_against(res, ora)
+    np.testing.assert_allclose(res.saved["c"], ora.saved["c"], rtol=1e-8)
+    np.testing.assert_allclose(res.saved["muk"], ora.saved["muk"], rtol=0, atol=1e-8)
+
+
+def test_growth_testset_properties():
+    # test/runtests.jl:46-65
+    g, gu, kbar = OM.growth_test_problem(200)
+    res = E.pdesolve(PM.GrowthTest(), g, gu, verbose=False)
+    v, c, muk = res.solution["v"], res.saved["c"], res.saved["muk"]
+    assert res.residual_norm <= 1e-6
+    assert np.all(np.diff(v) > 0) and np.all(np.diff(np.diff(v)) < 1e-8) and np.all(np.diff(c) > 0)
+    assert abs(g["k"][int(np.argmax(muk < 0))] - kbar) < 0.05 * kbar
+    assert np.array_equal(res.saved["v"], v)
+    sol, rn, saved = res
+    assert sol is res.solution and rn == res.residual_norm and saved is res.saved
+
+
+def test_maxiters_one_warns_and_is_not_converged():
+    # test/runtests.jl:162-192
+    g, gu, _ = OM.growth_test_problem(50)
+    with pytest.warns(UserWarning, match="did not converge after 1 time steps"):
+        res = E.pdesolve(PM.GrowthTest(), g, gu, maxiters=1, verbose=False)
+    assert not res.converged
+
+
+def test_signed_per_function_delta_block_tridiagonal():
+    # test/runtests.jl:375-394: F = 2, vector Δ with a forward-relaxed equation
+    g = {"x": OM.julia_range(0.1, 1.0, 5)}
+    guess = {"v": np.zeros(5), "p": np.zeros(5)}
+    res = E.pdesolve(PM.ForwardPrice(), g, guess, Δ={"v": 1.0, "p": -1.0}, verbose=False)
+    assert res.converged
+    np.testing.assert_allclose(res.solution["v"], 2 * g["x"], atol=1e-6)
+    np.testing.assert_allclose(res.solution["p"], g["x"], atol=1e-6)
+    _check_against(res, eo.pdesolve(OM.forward_price(), g, guess, delta={"v": 1.0, "p": -1.0}))
+    res = E.pdesolve(PM.ForwardPrice(), g, guess, Δ={"v": INF, "p": -1.0}, verbose=False)
+    assert res.converged
+    np.testing.assert_allclose(res.solution["p"], g["x"], atol=1e-6)
+    with pytest.raises(E.EconPDEsCudaError):
+        E.pdesolve(PM.ForwardPrice(), g, guess, Δ={"v": 1.0, "p": 0.0}, verbose=False)
+    with pytest.raises(ValueError):
+        E.pdesolve(PM.ForwardPrice(), g, guess, Δ={"bogus": 1.0}, verbose=False)
+
+
+def test_mcp_lower_bound_known_answer():
+    # test/runtests.jl:225-232
+    g = {"x": OM.julia_range(0, 1, 5)}
+    res = E.pdesolve(PM.VMinusTwo(), g, {"v": np.zeros(5)}, Δ=INF, lower_bound={"v": np.full(5, 3.0)}, verbose=False)
+    np.testing.assert_allclose(res.solution["v"], 3.0)
+    res = E.pdesolve(PM.VMinusTwo(), g, {"v": np.zeros(5)}, Δ=INF, verbose=False)
+    np.testing.assert_allclose(res.solution["v"], 2.0)
+
+
+def test_linear_sum_1d_inf_step():
+    g = {"x": OM.julia_range(0, 1, 33)}
+    res = E.pdesolve(PM.LinearSum1D(), g, {"v": np.zeros(33)}, Δ=INF, verbose=False)
+    assert res.residual_norm <= 1e-8
+    np.testing.assert_allclose(res.solution["v"], g["x"], rtol=1e-12)
+
+
+def test_input_validation():
+    # test/runtests.jl:194-267 (the ArgumentError paths that exist for registered models)
+    g, gu, _ = OM.growth_test_problem(50)
+    with pytest.raises(ValueError):
+        E.pdesolve(PM.GrowthTest(), g, {"v": np.zeros(3)}, verbose=False)
+    with pytest.raises(ValueError):
+        E.pdesolve(PM.GrowthTest(), {"k": np.array([1.0])}, {"v": np.zeros(1)}, verbose=False)
+    with pytest.raises(ValueError):
+        E.pdesolve(PM.GrowthTest(), g, gu, bc={"vx": (0.0, 0.0)}, verbose=False)
+    with pytest.raises(ValueError):
+        E.pdesolve(PM.GrowthTest(), g, gu, method="trust_region", verbose=False)
+    with pytest.raises(ValueError):
+        E.pdesolve(PM.GrowthTest(), g, gu, is_algebraic={"w": True}, verbose=False)
+    with pytest.raises(ValueError):
+        E.pdesolve(PM.GrowthTest(), g, gu, jac=lambda J, y: J, verbose=False)
+    with pytest.raises(TypeError):
+        E.pdesolve(lambda s, u: None, g, gu, verbose=False)
+    assert E.pdesolve(PM.GrowthTest(), g, gu, is_algebraic={"v": np.zeros(50, dtype=bool)}, verbose=False).converged
+    assert E.pdesolve(PM.GrowthTest(), g, gu, bc={"vk": (0.0, 0.0)}, verbose=False).residual_norm <= 1e-6
+    nan_guess = {"v": np.full(50, np.nan)}
+    with pytest.raises(E.EconPDEsCudaError, match="NaN with the initial value"):
+        E.pdesolve(PM.GrowthTest(), g, nan_guess, verbose=False)
+
+
+# ------------------------------------------------------------------ batched engine (C4)
+def _sweep(nprob, sn=1000, start=0):
+    prms = [OM.campbell_cochrane_sweep_params(start + i) for i in range(nprob)]
+    grids = np.stack([OM.campbell_cochrane_grid(sn=sn, **p) for p in prms])
+    params = np.array([[p[k] for k in ("mu", "sigma", "gamma", "rho", "kappa_s", "b")] for p in prms])
+    return prms, params, grids, np.ones_like(grids)
+
+
+def test_batched_sweep_matches_oracle_per_problem():
+    prms, params, grids, guess = _sweep(6)
+    out = E.pdesolve_batched(PM.CampbellCochraneModel, params, grids, guess, log_capacity=16)
+    assert out.kernel_launches == 1
+    for b, prm in enumerate(prms):
+        ora = eo.pdesolve(OM.campbell_cochrane(**prm), {"s": grids[b]}, {"p": guess[b]})
+        assert bool(out.converged[b]) == ora.converged
+        np.testing.assert_allclose(out.solution[b], ora.solution["p"], rtol=1e-8)
+        assert abs(out.residual_norm[b] - ora.residual_norm) <= 1e-10
+        assert out.n_outer[b] == ora.log.n_outer == 4 and out.n_newton[b] == ora.log.n_newton == 8
+        for r, o in zip(out.log[b], ora.log.rows):
+            assert "%.2e" % r["delta"] == "%.2e" % o[1] and "%.2e" % r["residual"] == "%.2e" % o[2]
+
+
+def test_batched_matches_generic_engine_and_golden():
+    for idx in (0, 3, 16383):
+        gold = np.load(os.path.join(GOLD, f"c4_sweep_{idx}.npz"))
+        params = gold["params"][None, :]
+        out = E.pdesolve_batched(PM.CampbellCochraneModel, params, gold["grid_s"][None, :], gold["guess_p"][None, :])
+        np.testing.assert_allclose(out.solution[0], gold["sol_p"], rtol=1e-8)
+        assert abs(out.residual_norm[0] - float(gold["residual_norm"])) <= 1e-10
+        res = E.pdesolve(PM.CampbellCochraneModel(*gold["params"]), {"s": gold["grid_s"]}, {"p": gold["guess_p"]},
+                         verbose=False)
+        np.testing.assert_allclose(res.solution["p"], out.solution[0], rtol=1e-10)
+
+
+def test_batched_nonlinear_model_with_rejections():
+    # the growth model takes 11 outer iterations with 3 rejected steps: exercises every branch
+    g, gu, prm = OM.neoclassical_growth_problem(1000)
+    params = np.array([[prm[k] for k in ("A", "alpha", "delta", "rho", "gamma")]] * 3)
+    out = E.pdesolve_batched(PM.NeoclassicalGrowthModel, params, np.stack([g["k"]] * 3), np.stack([gu["v"]] * 3),
+                             log_capacity=32)
+    ora = eo.pdesolve(OM.neoclassical_growth(**prm), g, gu)
+    for b in range(3):
+        assert out.n_outer[b] == 11 and out.n_newton[b] == ora.log.n_newton
+        assert [r["status"] for r in out.log[b]] == [r[3] for r in ora.log.rows]
+        np.testing.assert_allclose(out.solution[b], ora.solution["v"], rtol=1e-8)
+        assert abs(out.residual_norm[b] - ora.residual_norm) <= 1e-10
+
+
+def test_batched_small_and_ragged_sizes():
+    # sizes that are not a multiple of the warp, and the 2-point minimum (stategrid.jl:16)
+    for S in (2, 3, 31, 33, 50, 1024):
+        x = OM.julia_range(0.0, 1.0, S)
+        out = E.pdesolve_batched(PM.ReadmeLinear, np.array([[0.05, 0.2]] * 2), np.stack([x, x]), np.zeros((2, S)))
+        ora = eo.pdesolve(OM.readme_linear(), {"x": x}, {"v": np.zeros(S)})
+        assert bool(out.converged[0]) == ora.converged
+        np.testing.assert_allclose(out.solution[0], ora.solution["v"], rtol=1e-8, atol=1e-12)
+        np.testing.assert_array_equal(out.solution[0], out.solution[1])
+    with pytest.raises(E.EconPDEsCudaError):
+        x = OM.julia_range(0.0, 1.0, 1025)
+        E.pdesolve_batched(PM.ReadmeLinear, np.array([[0.05, 0.2]]), x[None, :], np.zeros((1, 1025)))
+
+
+def test_batched_inf_delta_and_already_zero():
+    x = OM.julia_range(0.0, 1.0, 40)
+    out = E.pdesolve_batched(PM.LinearSum1D, np.zeros((1, 0)), x[None, :], np.zeros((1, 40)), Δ=INF)
+    np.testing.assert_allclose(out.solution[0], x, rtol=1e-12)
+    assert out.exit_reason[0] == 0 and out.n_outer[0] == 0
+    out = E.pdesolve_batched(PM.LinearSum1D, np.zeros((1, 0)), x[None, :], x[None, :].copy())
+    assert out.exit_reason[0] == 1     # already zero
+
+
+def test_batched_full_size_properties():
+    """Full C4 size on one GPU: 16 384 problems.  Size-independent checks: every problem
+    converges in 4 outer steps / 8 Newton iterations, identical problems give
+    identical bits, and a permutation of the batch permutes the output."""
+    B = 16384
+    prms, params, grids, guess = _sweep(64)
+    reps = B // 64
+    P, G, U = np.tile(params, (reps, 1)), np.tile(grids, (reps, 1)), np.tile(guess, (reps, 1))
+    out = E.pdesolve_batched(PM.CampbellCochraneModel, P, G, U)
+    assert out.converged.all() and (out.n_outer == 4).all() and (out.n_newton == 8).all()
+    np.testing.assert_array_equal(out.solution[:64], out.solution[-64:])
+    perm = np.random.default_rng(0).permutation(B)
+    out2 = E.pdesolve_batched(PM.CampbellCochraneModel, P[perm], G[perm], U[perm])
+    np.testing.assert_array_equal(out2.solution, out.solution[perm])
+
+
+def test_golden_1d_fixtures():
+    gold = np.load(os.path.join(GOLD, "c1_readme_50.npz"))
+    res = E.pdesolve(PM.ReadmeLinear(*gold["params"]), {"x": gold["grid_x"]}, {"v": gold["guess_v"]}, verbose=False)
+    np.testing.assert_allclose(res.solution["v"], gold["sol_v"], rtol=1e-8)
+    assert abs(res.residual_norm - float(gold["residual_norm"])) <= 1e-10 and res.converged == bool(gold["converged"])
+    gold = np.load(os.path.join(GOLD, "growth_1000.npz"))
+    res = E.pdesolve(PM.NeoclassicalGrowthModel(*gold["params"]), {"k": gold["grid_k"]}, {"v": gold["guess_v"]},
+                     verbose=False)
+    np.testing.assert_allclose(res.solution["v"], gold["sol_v"], rtol=1e-8)
+    assert res.n_outer == gold["log"].shape[0]
