@@ -52,8 +52,8 @@ def _perturbed(gu, seed=1):
 
 
 def _ulp_close(got, want, ulps):
-    scale = np.maximum(np.abs(want), np.abs(want).max() * 1e-3)
-    np.testing.assert_array_less(np.abs(got - want), ulps * np.finfo(float).eps * scale + 1e-300)
+    # residuals are differences of O(max|want|) terms: measure the error in ulps of that scale
+    np.testing.assert_allclose(got, want, rtol=0, atol=ulps * np.finfo(float).eps * np.abs(want).max())
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
@@ -69,7 +69,7 @@ def test_residual_sweep(case):
     if name in ("readme", "by", "hjb3d", "fwdprice"):
         np.testing.assert_array_equal(got, want)      # IEEE-exact operations only
     else:
-        _ulp_close(got, want, 64)                     # log/pow: a few ulp, amplified by cancellation
+        _ulp_close(got, want, 16)                     # CUDA log/pow differ from glibc by <= 2 ulp
 
 
 def test_residual_with_boundary_values():
@@ -267,7 +267,10 @@ def test_batched_sweep_matches_oracle_per_problem():
         assert abs(out.residual_norm[b] - ora.residual_norm) <= 1e-10
         assert out.n_outer[b] == ora.log.n_outer == 4 and out.n_newton[b] == ora.log.n_newton == 8
         for r, o in zip(out.log[b], ora.log.rows):
-            assert "%.2e" % r["delta"] == "%.2e" % o[1] and "%.2e" % r["residual"] == "%.2e" % o[2]
+            assert "%.2e" % r["delta"] == "%.2e" % o[1]
+            assert abs(r["residual"] - o[2]) <= 1e-10
+            if o[2] > 1e-8:   # rows above the round-off floor of the linear solve print identically
+                assert "%.2e" % r["residual"] == "%.2e" % o[2]
 
 
 def test_batched_matches_generic_engine_and_golden():
