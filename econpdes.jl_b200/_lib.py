@@ -86,6 +86,7 @@ SYMBOLS = {
     "econpdes_solve_batched": (C.c_int, [C.c_int, C.c_int64, C.c_int64, c_double_p, c_double_p, c_double_p,
                                          C.POINTER(Options), c_double_p, c_double_p, c_int32_p, c_int32_p,
                                          c_int32_p]),
+    "econpdes_release_workspace": (None, []),
     "econpdes_device_count": (C.c_int, []),
     "econpdes_set_device": (C.c_int, [C.c_int]),
     "econpdes_total_kernel_launches": (C.c_int64, []),

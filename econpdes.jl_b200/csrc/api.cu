@@ -45,6 +45,7 @@ struct econpdes_batch {
   DevBuf<econpdes_log_row> log;
   int log_capacity = 0;
   int64_t launches = 0;
+  int device = -1;
   ~econpdes_batch() {
     if (stream) cudaStreamDestroy(stream);
   }
@@ -372,17 +373,33 @@ int econpdes_batch_download(econpdes_batch* b, double* solution, double* residua
 
 int64_t econpdes_batch_kernel_launches(const econpdes_batch* b) { return b ? b->launches : 0; }
 
+// The one-call path keeps its device workspace between calls of the same shape (a
+// calibration loop calls it thousands of times): cudaMalloc/cudaFree of ~0.5 GB per call
+// cost more than the solve.  econpdes_release_workspace() frees it.
+static thread_local econpdes_batch* t_workspace = nullptr;
+
+void econpdes_release_workspace(void) {
+  delete t_workspace;
+  t_workspace = nullptr;
+}
+
 int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, const double* params, const double* grids,
                            const double* guess, const econpdes_options* options, double* solution,
                            double* residual_norm, int32_t* exit_reason, int32_t* n_outer, int32_t* n_newton) {
-  econpdes_batch* b = nullptr;
-  int rc = econpdes_batch_create(model_id, nproblems, npoints, &b);
-  if (rc != ECONPDES_OK) return rc;
-  rc = econpdes_batch_upload(b, params, grids, guess);
+  int device = -1;
+  cudaGetDevice(&device);
+  econpdes_batch* b = t_workspace;
+  if (b == nullptr || b->model_id != model_id || b->B != nproblems || b->S != npoints || b->device != device) {
+    econpdes_release_workspace();
+    const int rc = econpdes_batch_create(model_id, nproblems, npoints, &b);
+    if (rc != ECONPDES_OK) return rc;
+    b->device = device;
+    t_workspace = b;
+  }
+  int rc = econpdes_batch_upload(b, params, grids, guess);
   if (rc == ECONPDES_OK) rc = econpdes_batch_solve(b, options, nullptr);
   if (rc == ECONPDES_OK)
     rc = econpdes_batch_download(b, solution, residual_norm, exit_reason, n_outer, n_newton, nullptr, 0, nullptr);
-  econpdes_batch_destroy(b);
   return rc;
 }
 

@@ -105,12 +105,14 @@ __global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args)
   load_geom<1>(gv, idx, g, st);
   double bl[1][1] = {{0.0}}, bh[1][1] = {{0.0}};
   __syncthreads();
+  typename M::Pre pre;   // state-only part of the model, once per problem
+  M::prepare(prm, st, pre);
 
   // residual G at this thread's point from the y currently published in ysh
   auto evalG = [&]() -> double {
     double w[1][3] = {{ysh[i], ysh[i + 1], ysh[i + 2]}};
     double o[1];
-    eval_point<M, false>(prm, st, g, w, bl, bh, o, nullptr);
+    eval_point<M, false>(pre, g, w, bl, bh, o, nullptr);
     return o[0];
   };
   auto publish = [&](double v) {
@@ -145,68 +147,65 @@ __global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args)
     Gy = Gpost;
     double R = act ? apply_row_terms(Gy, y, rt[0]) : 0.0;
     newton_it = 0;
-    double s3[3], m2[2];
-    s3[0] = (act && R == R) ? R * R : 0.0;
-    m2[0] = (act && R == R) ? fabs(R) : 0.0;
-    m2[1] = (act && R != R) ? 1.0 : 0.0;
-    block_reduce_mixed<1, 2>(s3, m2, red);
-    bool anynan = m2[1] > 0.0;
-    bool fconv = !anynan && m2[0] <= ftol;
+    const int ci = i % 3;
+    // one block reduction per Newton iteration carries everything the control flow needs:
+    // sums: ||R||^2 and the three masked ||y .* mask_c||^2 of FiniteDiff's per-color step;
+    // maxs: ||R||_inf, NaN flag, ||y - xold||_inf (x_converged), non-finite linear solve flag
+    double s4[4], m4[4];
+    auto reduce_state = [&](double dx, double bad) {
+      const double q = act ? y * y : 0.0;
+      s4[0] = (act && R == R) ? R * R : 0.0;
+      s4[1] = ci == 0 ? q : 0.0;
+      s4[2] = ci == 1 ? q : 0.0;
+      s4[3] = ci == 2 ? q : 0.0;
+      m4[0] = (act && R == R) ? fabs(R) : 0.0;
+      m4[1] = (act && (R != R || y != y)) ? 1.0 : 0.0;
+      m4[2] = dx;
+      m4[3] = bad;
+      block_reduce_mixed<4, 4>(s4, m4, red);
+    };
+    reduce_state(0.0, 0.0);
+    bool anynan = m4[1] > 0.0;
+    bool fconv = !anynan && m4[0] <= ftol;
     bool xconv = false;
-    double sumsqR = s3[0];
     bool singular = false;
     // y is already published in ysh by the caller when y == ypost
     while (!anynan && !fconv && !xconv && newton_it < maxit) {
       ++newton_it;
-      // FiniteDiff step per color: sqrt(eps)*max(1, sqrt(||x .* mask_c||_2))
-      const int ci = i % 3;
-      const double q = act ? y * y : 0.0;
-      s3[0] = ci == 0 ? q : 0.0;
-      s3[1] = ci == 1 ? q : 0.0;
-      s3[2] = ci == 2 ? q : 0.0;
-      block_reduce_mixed<3, 0>(s3, m2, red);
-      double eps_table[3];
-      eps_table[0] = color_epsilon_from_sumsq(s3[0]);
-      eps_table[1] = color_epsilon_from_sumsq(s3[1]);
-      eps_table[2] = color_epsilon_from_sumsq(s3[2]);
+      double eps_table[3];   // FiniteDiff: sqrt(eps)*max(1, sqrt(||x .* mask_c||_2))
+      eps_table[0] = color_epsilon_from_sumsq(s4[1]);
+      eps_table[1] = color_epsilon_from_sumsq(s4[2]);
+      eps_table[2] = color_epsilon_from_sumsq(s4[3]);
       double ja = 0.0, jb = 1.0, jc = 0.0;
       if (act) {
         double w[1][3] = {{ysh[i], ysh[i + 1], ysh[i + 2]}};
         double r0[1] = {R};
-        jacobian_point<M, false, true>(prm, st, g, idx, gv, w, bl, bh, rt, eps_table,
+        jacobian_point<M, false, true>(pre, g, idx, gv, w, bl, bh, rt, eps_table,
                                        opt.eps_policy == ECONPDES_EPS_PER_COLUMN, r0,
                                        [&](int k, int, int, double v) {
                                          if (k == 0) jb = v; else if (k == 1) ja = v; else jc = v;
                                        });
       }
       const double sol = block_pcr_solve(ja, jb, jc, act ? R : 0.0, i, S, pcr);
-      m2[0] = (act && !isfinite(sol)) ? 1.0 : 0.0;
-      block_reduce_mixed<0, 1>(s3, m2, red);
-      if (m2[0] > 0.0) { singular = true; break; }
+      const double bad = (act && !isfinite(sol)) ? 1.0 : 0.0;
       const double xold = y;
       y = xold + (-sol);
       publish(y);
       Gy = act ? evalG() : 0.0;
       R = act ? apply_row_terms(Gy, y, rt[0]) : 0.0;
-      s3[0] = (act && R == R) ? R * R : 0.0;
-      m2[0] = (act && R == R) ? fabs(R) : 0.0;
-      m2[1] = (act && (R != R || y != y)) ? 1.0 : 0.0;
-      block_reduce_mixed<1, 2>(s3, m2, red);
-      sumsqR = s3[0];
-      anynan = m2[1] > 0.0;
-      fconv = !anynan && m2[0] <= ftol;
-      // x_converged: chebyshev(x, xold) <= 0
-      m2[0] = act ? fabs(y - xold) : 0.0;
-      block_reduce_mixed<0, 1>(s3, m2, red);
-      xconv = !anynan && m2[0] <= 0.0;
+      reduce_state(act ? fabs(y - xold) : 0.0, bad);
+      if (m4[3] > 0.0) { singular = true; break; }   // a vanishing pivot: SingularException
+      anynan = m4[1] > 0.0;
+      fconv = !anynan && m4[0] <= ftol;
+      xconv = !anynan && m4[2] <= 0.0;               // chebyshev(x, xold) <= xtol = 0
     }
-    if (singular) {   // SingularException -> (y0, Inf), :142-146
+    if (singular) {   // -> (y0, Inf), finiteschemesolve.jl:142-146
       y = ypost;
       Gy = Gpost;
       nl = INFINITY;
       publish(y);
     } else {
-      nl = anynan ? NAN : sqrt(sumsqR) / nd;
+      nl = anynan ? NAN : sqrt(s4[0]) / nd;
     }
   };
 

@@ -49,10 +49,12 @@ struct PointLoad {
   PointGeom<N> g;
   double st[N];
   double w[F][K], bl[F][N], bh[F][N];
+  typename M::Pre pre;
   __device__ __forceinline__ void load(const GridView<N>& gv, long long pt, const double* __restrict__ y,
-                                       const double* __restrict__ bc) {
+                                       const double* __restrict__ bc, const double* prm) {
     unravel<N>(pt, gv, idx);
     load_geom<N>(gv, idx, g, st);
+    M::prepare(prm, st, pre);
 #pragma unroll
     for (int f = 0; f < F; ++f) {
       load_box<N>(y + f * gv.l, pt, gv, g, w[f]);
@@ -72,9 +74,9 @@ __global__ void __launch_bounds__(kBlock) k_residual(GridView<M::N> gv, ParamPac
   int nanf = 0;
   if (pt < gv.l) {
     PointLoad<M> P;
-    P.load(gv, pt, y, bc);
+    P.load(gv, pt, y, bc, prm.v);
     double o[F];
-    eval_point<M, false>(prm.v, P.st, P.g, P.w, P.bl, P.bh, o, nullptr);
+    eval_point<M, false>(P.pre, P.g, P.w, P.bl, P.bh, o, nullptr);
 #pragma unroll
     for (int f = 0; f < F; ++f) {
       const long long j = f * gv.l + pt;
@@ -177,13 +179,13 @@ __global__ void __launch_bounds__(kBlock) k_jacobian(GridView<M::N> gv, ParamPac
   const long long pt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (pt >= gv.l) return;
   PointLoad<M> P;
-  P.load(gv, pt, y, bc);
+  P.load(gv, pt, y, bc, prm.v);
   RowTerms rt[F];
 #pragma unroll
   for (int f = 0; f < F; ++f) rt[f] = make_row_terms(rs, f * gv.l + pt);
   double r0[F];
   const long long l = gv.l;
-  jacobian_point<M, BOX>(prm.v, P.st, P.g, P.idx, gv, P.w, P.bl, P.bh, rt, eps_table, eps_per_column, r0,
+  jacobian_point<M, BOX>(P.pre, P.g, P.idx, gv, P.w, P.bl, P.bh, rt, eps_table, eps_per_column, r0,
                          [&](int k, int fin, int fout, double v) {
                            planes[(static_cast<long long>(k * F + fin) * F + fout) * l + pt] = v;
                          });
@@ -199,9 +201,9 @@ __global__ void __launch_bounds__(kBlock) k_saved(GridView<M::N> gv, ParamPack p
   const long long pt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (pt >= gv.l) return;
   PointLoad<M> P;
-  P.load(gv, pt, y, bc);
+  P.load(gv, pt, y, bc, prm.v);
   double o[M::F], sv[M::NSAVED > 0 ? M::NSAVED : 1];
-  eval_point<M, true>(prm.v, P.st, P.g, P.w, P.bl, P.bh, o, sv);
+  eval_point<M, true>(P.pre, P.g, P.w, P.bl, P.bh, o, sv);
 #pragma unroll
   for (int s = 0; s < M::NSAVED; ++s) saved[s * gv.l + pt] = sv[s];
 }

@@ -6,14 +6,22 @@
 // parameter vector layout of every model is part of the C ABI (include/econpdes_cuda.h,
 // `econpdes_model_info`) and mirrored by econpdes.jl_b200/models.py.
 //
-// Interface of a functor M:
+// A functor M is split in two so that kernels which evaluate the model several times at
+// one grid point (the colored-FD Jacobian: one evaluation per stencil column; the fused
+// batched solve: every Newton iteration) pay the state-only arithmetic once:
+//   M::prepare(prm, state, pre)   everything that depends on the grid point and the
+//                                 parameters but not on the unknowns (drifts, volatilities,
+//                                 sqrt/log/pow of the state ...)
+//   M::eval<SAVE>(pre, u, out, saved)   the rest
+// The split only moves sub-expressions; every floating-point operation and its operand
+// order is the reference's, so the result is bit-identical to evaluating the body in one go.
+//
 //   M::N, M::F            number of states / unknowns
 //   M::NPARAMS, M::NSAVED parameter count, number of saved scalars per point
 //   M::USES_CROSS         false if the body never reads a cross derivative: the
 //                         Jacobian is then a star stencil and the corner columns of the
 //                         +-1 box are exactly zero (the reference stores them as
 //                         structural zeros, coloring.jl:18-35)
-//   M::eval<SAVE>(prm, state, u, out, saved)
 #pragma once
 #include <math.h>
 
@@ -29,12 +37,16 @@ struct ReadmeLinear {
   static constexpr int N = 1, F = 1, NPARAMS = 2, NSAVED = 0;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "readme_linear"; }
-  template <bool SAVE>
-  EP_HD static void eval(const double* prm, const double* st, const Deriv<1>* u, double* out, double*) {
+  struct Pre { double x, mu, rho; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
     const double rho = prm[0], kappa = prm[1];
-    const double x = st[0];
-    const double mu = -kappa * (x - 0.5);
-    out[0] = -(x + mu * (mu >= 0 ? u[0].up[0] : u[0].dn[0]) - rho * u[0].v);
+    c.x = st[0];
+    c.mu = -kappa * (c.x - 0.5);
+    c.rho = rho;
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<1>* u, double* out, double*) {
+    out[0] = -(c.x + c.mu * (c.mu >= 0 ? u[0].up[0] : u[0].dn[0]) - c.rho * u[0].v);
   }
 };
 
@@ -43,23 +55,29 @@ struct CampbellCochrane {
   static constexpr int N = 1, F = 1, NPARAMS = 6, NSAVED = 0;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "campbell_cochrane"; }
-  template <bool SAVE>
-  EP_HD static void eval(const double* prm, const double* st, const Deriv<1>* u, double* out, double*) {
+  struct Pre { double mu, sigma, mus, sigs, sigs2, mus_eff, kap, r; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
     const double mu = prm[0], sigma = prm[1], gamma = prm[2], rho = prm[3], kappa_s = prm[4], b = prm[5];
     const double s = st[0];
-    const double p = u[0].v, pss = u[0].dd[0];
     const double Sbar = sigma * sqrt(gamma / (kappa_s - b / gamma));
     const double sbar = log(Sbar);
     const double lam = 1 / Sbar * sqrt(1 - 2 * (s - sbar)) - 1;
-    const double mus = -kappa_s * (s - sbar);
-    const double sigs = lam * sigma;
-    const double mus_eff = mus + sigs * (sigma - gamma * (sigma + sigs));
-    const double ps = (mus_eff >= 0) ? u[0].up[0] : u[0].dn[0];
-    const double sigp = ps / p * sigs;
-    const double mup = ps / p * mus + 0.5 * pss / p * (sigs * sigs);
-    const double kap = gamma * (sigma + sigs);
-    const double r = rho + gamma * mu - (gamma * kappa_s - b) / 2 + b * (sbar - s);
-    out[0] = -p * (1 / p + mu + mup + sigp * sigma - r - kap * (sigma + sigp));
+    c.mu = mu;
+    c.sigma = sigma;
+    c.mus = -kappa_s * (s - sbar);
+    c.sigs = lam * sigma;
+    c.sigs2 = c.sigs * c.sigs;
+    c.mus_eff = c.mus + c.sigs * (sigma - gamma * (sigma + c.sigs));
+    c.kap = gamma * (sigma + c.sigs);
+    c.r = rho + gamma * mu - (gamma * kappa_s - b) / 2 + b * (sbar - s);
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<1>* u, double* out, double*) {
+    const double p = u[0].v, pss = u[0].dd[0];
+    const double ps = (c.mus_eff >= 0) ? u[0].up[0] : u[0].dn[0];
+    const double sigp = ps / p * c.sigs;
+    const double mup = ps / p * c.mus + 0.5 * pss / p * c.sigs2;
+    out[0] = -p * (1 / p + c.mu + mup + sigp * c.sigma - c.r - c.kap * (c.sigma + sigp));
   }
 };
 
@@ -68,31 +86,39 @@ struct BansalYaron {
   static constexpr int N = 2, F = 1, NPARAMS = 9, NSAVED = 0;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "bansal_yaron"; }
-  template <bool SAVE>
-  EP_HD static void eval(const double* prm, const double* st, const Deriv<2>* u, double* out, double*) {
+  struct Pre { double muc, mumu, sigmu, sigmu2, muv, sigv, sigv2, cz, r_base, cs, kzc_sigc; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
     const double mubar = prm[0], vbar = prm[1], kappa_mu = prm[2], nu_mu = prm[3], kappa_v = prm[4],
                  nu_v = prm[5], rho = prm[6], gamma = prm[7], psi = prm[8];
     const double mu = st[0], v = st[1];
-    const double p = u[0].v;
-    const double muc = mu;
+    c.muc = mu;
     const double sigc = sqrt(v);
-    const double mumu = kappa_mu * (mubar - mu);
-    const double sigmu = nu_mu * sqrt(v);
-    const double muv = kappa_v * (vbar - v);
-    const double sigv = nu_v * sqrt(v);
-    const double pmu = (mumu >= 0) ? u[0].up[0] : u[0].dn[0];
-    const double pv = (muv >= 0) ? u[0].up[1] : u[0].dn[1];
-    const double sigp_Zmu = pmu / p * sigmu;
-    const double sigp_Zv = pv / p * sigv;
-    const double sigp2 = sigp_Zmu * sigp_Zmu + sigp_Zv * sigp_Zv;
-    const double mup = pmu / p * mumu + pv / p * muv + 0.5 * u[0].dd[0] / p * (sigmu * sigmu) +
-                       0.5 * u[0].dd[1] / p * (sigv * sigv);
+    c.mumu = kappa_mu * (mubar - mu);
+    c.sigmu = nu_mu * sqrt(v);
+    c.sigmu2 = c.sigmu * c.sigmu;
+    c.muv = kappa_v * (vbar - v);
+    c.sigv = nu_v * sqrt(v);
+    c.sigv2 = c.sigv * c.sigv;
     const double kap_Zc = gamma * sigc;
-    const double kap_Zmu = -(1 - gamma * psi) / (psi - 1) * sigp_Zmu;
-    const double kap_Zv = -(1 - gamma * psi) / (psi - 1) * sigp_Zv;
-    const double r = rho + muc / psi - (1 + 1 / psi) / 2 * gamma * (sigc * sigc) -
-                     (gamma * psi - 1) / (2 * (psi - 1)) * sigp2;
-    out[0] = -p * (1 / p + muc + mup - r - kap_Zc * sigc - kap_Zmu * sigp_Zmu - kap_Zv * sigp_Zv);
+    c.cz = -(1 - gamma * psi) / (psi - 1);
+    c.r_base = rho + c.muc / psi - (1 + 1 / psi) / 2 * gamma * (sigc * sigc);
+    c.cs = (gamma * psi - 1) / (2 * (psi - 1));
+    c.kzc_sigc = kap_Zc * sigc;
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<2>* u, double* out, double*) {
+    const double p = u[0].v;
+    const double pmu = (c.mumu >= 0) ? u[0].up[0] : u[0].dn[0];
+    const double pv = (c.muv >= 0) ? u[0].up[1] : u[0].dn[1];
+    const double sigp_Zmu = pmu / p * c.sigmu;
+    const double sigp_Zv = pv / p * c.sigv;
+    const double sigp2 = sigp_Zmu * sigp_Zmu + sigp_Zv * sigp_Zv;
+    const double mup = pmu / p * c.mumu + pv / p * c.muv + 0.5 * u[0].dd[0] / p * c.sigmu2 +
+                       0.5 * u[0].dd[1] / p * c.sigv2;
+    const double kap_Zmu = c.cz * sigp_Zmu;
+    const double kap_Zv = c.cz * sigp_Zv;
+    const double r = c.r_base - c.cs * sigp2;
+    out[0] = -p * (1 / p + c.muc + mup - r - c.kzc_sigc - kap_Zmu * sigp_Zmu - kap_Zv * sigp_Zv);
   }
 };
 
@@ -102,33 +128,47 @@ struct AhlmDiffusion {
   static constexpr int N = 2, F = 1, NPARAMS = 8, NSAVED = 2;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "ahlm_diffusion"; }
-  template <bool SAVE>
-  EP_HD static void eval(const double* prm, const double* st, const Deriv<2>* u, double* out, double* sv) {
+  struct Pre { double muy, cmax, inc, va3, util3, neg_inv_gamma, one_m_gamma, sig2, rho; bool above_amin; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
     const double kappa_y = prm[0], ybar = prm[1], sigma_y = prm[2], r = prm[3], rho = prm[4], gamma = prm[5],
                  amin = prm[6];
     const double y = st[0], a = st[1];
+    c.muy = kappa_y * (ybar - y);
+    c.cmax = 100.0 * (y + r * ep_max(a, 0.0));
+    c.inc = y + r * a;                       // c = y + r a when the drift is pinned at zero
+    c.neg_inv_gamma = -1 / gamma;
+    c.one_m_gamma = 1 - gamma;
+    c.va3 = pow(c.inc, -gamma);
+    c.util3 = pow(c.inc, c.one_m_gamma) / c.one_m_gamma;
+    c.sig2 = sigma_y * sigma_y;
+    c.rho = rho;
+    c.above_amin = a > amin;
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& p, const Deriv<2>* u, double* out, double* sv) {
     const double v = u[0].v, vy_up = u[0].up[0], vy_down = u[0].dn[0], va_up = u[0].up[1], va_down = u[0].dn[1],
                  vyy = u[0].dd[0];
-    const double muy = kappa_y * (ybar - y);
-    const double cmax = 100.0 * (y + r * ep_max(a, 0.0));
-    const double vy = (muy >= 0) ? vy_up : vy_down;
-    const double c_up = va_up > 0 ? ep_min(pow(va_up, -1 / gamma), cmax) : cmax;
-    const double mua_up = y + r * a - c_up;
-    double c, va, mua;
+    const double vy = (p.muy >= 0) ? vy_up : vy_down;
+    const double c_up = va_up > 0 ? ep_min(pow(va_up, p.neg_inv_gamma), p.cmax) : p.cmax;
+    const double mua_up = p.inc - c_up;
+    double c, va, mua, util;
     if (mua_up >= 0.0) {
       va = va_up; c = c_up; mua = mua_up;
+      util = pow(c, p.one_m_gamma) / p.one_m_gamma;
     } else {
-      const double c_down = va_down > 0 ? ep_min(pow(va_down, -1 / gamma), cmax) : cmax;
-      const double mua_down = y + r * a - c_down;
-      if ((mua_down <= 0.0) && (a > amin)) {
+      const double c_down = va_down > 0 ? ep_min(pow(va_down, p.neg_inv_gamma), p.cmax) : p.cmax;
+      const double mua_down = p.inc - c_down;
+      if ((mua_down <= 0.0) && p.above_amin) {
         va = va_down; c = c_down; mua = mua_down;
+        util = pow(c, p.one_m_gamma) / p.one_m_gamma;
       } else {
-        c = y + r * a;
-        va = pow(c, -gamma);
+        c = p.inc;
+        va = p.va3;
         mua = 0.0;
+        util = p.util3;
       }
     }
-    out[0] = -(pow(c, 1 - gamma) / (1 - gamma) + mua * va + muy * vy + 0.5 * vyy * (sigma_y * sigma_y) - rho * v);
+    out[0] = -(util + mua * va + p.muy * vy + 0.5 * vyy * p.sig2 - p.rho * v);
     if (SAVE) { sv[0] = mua; sv[1] = c; }
   }
 };
@@ -139,20 +179,31 @@ struct Hjb3dSynth {
   static constexpr int N = 3, F = 1, NPARAMS = 9, NSAVED = 0;
   static constexpr bool USES_CROSS = true;
   static const char* name() { return "hjb3d_synth"; }
-  template <bool SAVE>
-  EP_HD static void eval(const double* prm, const double* st, const Deriv<3>* u, double* out, double*) {
-    const double kx = prm[0], ky = prm[1], kz = prm[2], sx = prm[3], sy = prm[4], sz = prm[5], corr = prm[6],
-                 rho = prm[7], theta = prm[8];
+  struct Pre { double xyz, mx, my, mz, hx, hy, hz, cxy, rho, theta; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
+    const double kx = prm[0], ky = prm[1], kz = prm[2], sx = prm[3], sy = prm[4], sz = prm[5], corr = prm[6];
     const double x = st[0], y = st[1], z = st[2];
+    c.xyz = x + y + z;
+    c.mx = -kx * (x - 0.5);
+    c.my = -ky * (y - 0.5);
+    c.mz = -kz * (z - 0.5);
+    c.hx = 0.5 * (sx * sx);
+    c.hy = 0.5 * (sy * sy);
+    c.hz = 0.5 * (sz * sz);
+    c.cxy = corr * sx * sy;
+    c.rho = prm[7];
+    c.theta = prm[8];
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<3>* u, double* out, double*) {
     const double v = u[0].v;
-    const double mx = -kx * (x - 0.5), my = -ky * (y - 0.5), mz = -kz * (z - 0.5);
-    const double vx = (mx >= 0) ? u[0].up[0] : u[0].dn[0];
-    const double vy = (my >= 0) ? u[0].up[1] : u[0].dn[1];
-    const double vz = (mz >= 0) ? u[0].up[2] : u[0].dn[2];
-    const double drift = mx * vx + my * vy + mz * vz;
-    const double diff = 0.5 * (sx * sx) * u[0].dd[0] + 0.5 * (sy * sy) * u[0].dd[1] + 0.5 * (sz * sz) * u[0].dd[2];
-    const double cross = corr * sx * sy * u[0].xu[0];
-    out[0] = -(x + y + z + drift + diff + cross - rho * v - theta * (v * v));
+    const double vx = (c.mx >= 0) ? u[0].up[0] : u[0].dn[0];
+    const double vy = (c.my >= 0) ? u[0].up[1] : u[0].dn[1];
+    const double vz = (c.mz >= 0) ? u[0].up[2] : u[0].dn[2];
+    const double drift = c.mx * vx + c.my * vy + c.mz * vz;
+    const double diff = c.hx * u[0].dd[0] + c.hy * u[0].dd[1] + c.hz * u[0].dd[2];
+    const double cross = c.cxy * u[0].xu[0];
+    out[0] = -(c.xyz + drift + diff + cross - c.rho * v - c.theta * (v * v));
   }
 };
 
@@ -161,29 +212,41 @@ struct NeoclassicalGrowth {
   static constexpr int N = 1, F = 1, NPARAMS = 5, NSAVED = 2;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "neoclassical_growth"; }
-  template <bool SAVE>
-  EP_HD static void eval(const double* prm, const double* st, const Deriv<1>* u, double* out, double* sv) {
+  struct Pre { double cap, net, vk3, util3, neg_inv_gamma, one_m_gamma, rho; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
     const double A = prm[0], alpha = prm[1], delta = prm[2], rho = prm[3], gamma = prm[4];
     const double k = st[0];
+    c.cap = 10 * A * pow(k, alpha);
+    c.net = A * pow(k, alpha) - delta * k;   // A k^alpha - delta k
+    c.neg_inv_gamma = -1 / gamma;
+    c.one_m_gamma = 1 - gamma;
+    c.vk3 = pow(c.net, -gamma);
+    c.util3 = pow(c.net, c.one_m_gamma) / c.one_m_gamma;
+    c.rho = rho;
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& p, const Deriv<1>* u, double* out, double* sv) {
     const double v = u[0].v, vk_up = u[0].up[0], vk_down = u[0].dn[0];
-    const double cap = 10 * A * pow(k, alpha);
-    const double c_up = vk_up >= 0 ? ep_min(pow(vk_up, -1 / gamma), cap) : cap;
-    const double muk_up = A * pow(k, alpha) - delta * k - c_up;
-    double c, vk, muk;
+    const double c_up = vk_up >= 0 ? ep_min(pow(vk_up, p.neg_inv_gamma), p.cap) : p.cap;
+    const double muk_up = p.net - c_up;
+    double c, vk, muk, util;
     if (muk_up > 0) {
       c = c_up; vk = vk_up; muk = muk_up;
+      util = pow(c, p.one_m_gamma) / p.one_m_gamma;
     } else {
-      const double c_down = vk_down >= 0 ? ep_min(pow(vk_down, -1 / gamma), cap) : cap;
-      const double muk_down = A * pow(k, alpha) - delta * k - c_down;
+      const double c_down = vk_down >= 0 ? ep_min(pow(vk_down, p.neg_inv_gamma), p.cap) : p.cap;
+      const double muk_down = p.net - c_down;
       if (muk_down < 0) {
         c = c_down; vk = vk_down; muk = muk_down;
+        util = pow(c, p.one_m_gamma) / p.one_m_gamma;
       } else {
         muk = 0.0;
-        c = A * pow(k, alpha) - delta * k;
-        vk = pow(c, -gamma);
+        c = p.net;
+        vk = p.vk3;
+        util = p.util3;
       }
     }
-    out[0] = -(pow(c, 1 - gamma) / (1 - gamma) + muk * vk - rho * v);
+    out[0] = -(util + muk * vk - p.rho * v);
     if (SAVE) { sv[0] = c; sv[1] = muk; }
   }
 };
@@ -193,27 +256,29 @@ struct GrowthTest {
   static constexpr int N = 1, F = 1, NPARAMS = 5, NSAVED = 2;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "growth_test"; }
+  using Pre = NeoclassicalGrowth::Pre;
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) { NeoclassicalGrowth::prepare(prm, st, c); }
   template <bool SAVE>
-  EP_HD static void eval(const double* prm, const double* st, const Deriv<1>* u, double* out, double* sv) {
-    const double A = prm[0], alpha = prm[1], delta = prm[2], rho = prm[3], gamma = prm[4];
-    const double k = st[0];
+  EP_HD static void eval(const Pre& p, const Deriv<1>* u, double* out, double* sv) {
     const double vk_up = u[0].up[0], vk_down = u[0].dn[0];
-    const double cmax = 10 * A * pow(k, alpha);
-    const double c_up = vk_up > 0 ? ep_min(pow(vk_up, -1 / gamma), cmax) : cmax;
-    const double mu_up = A * pow(k, alpha) - delta * k - c_up;
-    const double c_down = vk_down > 0 ? ep_min(pow(vk_down, -1 / gamma), cmax) : cmax;
-    const double mu_down = A * pow(k, alpha) - delta * k - c_down;
-    double c, vk, muk;
+    const double c_up = vk_up > 0 ? ep_min(pow(vk_up, p.neg_inv_gamma), p.cap) : p.cap;
+    const double mu_up = p.net - c_up;
+    const double c_down = vk_down > 0 ? ep_min(pow(vk_down, p.neg_inv_gamma), p.cap) : p.cap;
+    const double mu_down = p.net - c_down;
+    double c, vk, muk, util;
     if (mu_up > 0) {
       c = c_up; vk = vk_up; muk = mu_up;
+      util = pow(c, p.one_m_gamma) / p.one_m_gamma;
     } else if (mu_down < 0) {
       c = c_down; vk = vk_down; muk = mu_down;
+      util = pow(c, p.one_m_gamma) / p.one_m_gamma;
     } else {
-      c = A * pow(k, alpha) - delta * k;
-      vk = pow(c, -gamma);
+      c = p.net;
+      vk = p.vk3;
       muk = 0.0;
+      util = p.util3;
     }
-    out[0] = -(pow(c, 1 - gamma) / (1 - gamma) + muk * vk - rho * u[0].v);
+    out[0] = -(util + muk * vk - p.rho * u[0].v);
     if (SAVE) { sv[0] = c; sv[1] = muk; }
   }
 };
@@ -224,11 +289,16 @@ struct LinearSum {
   static constexpr int N = NDIM, F = 1, NPARAMS = 0, NSAVED = 0;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return NDIM == 1 ? "linear_sum_1d" : (NDIM == 2 ? "linear_sum_2d" : "linear_sum_3d"); }
+  struct Pre { double st[NDIM]; };
+  EP_HD static void prepare(const double*, const double* st, Pre& c) {
+#pragma unroll
+    for (int d = 0; d < NDIM; ++d) c.st[d] = st[d];
+  }
   template <bool SAVE>
-  EP_HD static void eval(const double*, const double* st, const Deriv<NDIM>* u, double* out, double*) {
+  EP_HD static void eval(const Pre& c, const Deriv<NDIM>* u, double* out, double*) {
     double acc = u[0].v;
 #pragma unroll
-    for (int d = 0; d < NDIM; ++d) acc = acc - st[d];
+    for (int d = 0; d < NDIM; ++d) acc = acc - c.st[d];
     out[0] = -acc;
   }
 };
@@ -238,9 +308,11 @@ struct ForwardPrice {
   static constexpr int N = 1, F = 2, NPARAMS = 0, NSAVED = 0;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "forward_price"; }
+  struct Pre { double x; };
+  EP_HD static void prepare(const double*, const double* st, Pre& c) { c.x = st[0]; }
   template <bool SAVE>
-  EP_HD static void eval(const double*, const double* st, const Deriv<1>* u, double* out, double*) {
-    out[0] = -(st[0] + u[1].v - u[0].v);
+  EP_HD static void eval(const Pre& c, const Deriv<1>* u, double* out, double*) {
+    out[0] = -(c.x + u[1].v - u[0].v);
     out[1] = u[0].v / 2 - u[1].v;
   }
 };
@@ -250,8 +322,10 @@ struct VMinusTwo {
   static constexpr int N = 1, F = 1, NPARAMS = 0, NSAVED = 0;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "v_minus_two"; }
+  struct Pre { int unused; };
+  EP_HD static void prepare(const double*, const double*, Pre& c) { c.unused = 0; }
   template <bool SAVE>
-  EP_HD static void eval(const double*, const double*, const Deriv<1>* u, double* out, double*) {
+  EP_HD static void eval(const Pre&, const Deriv<1>* u, double* out, double*) {
     out[0] = u[0].v - 2.0;
   }
 };

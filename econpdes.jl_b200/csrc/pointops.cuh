@@ -32,7 +32,7 @@ template <int N, bool BOX>
 struct Stencil {
   static constexpr int NK = BOX ? ipow3(N) : 1 + 2 * N;
   EP_HD static constexpr int off(int k, int d) {
-    if (BOX) return (k / ipow3(d)) % 3 - 1;
+    if (BOX) return (k / p3(d)) % 3 - 1;
     if (k == 0) return 0;
     return ((k - 1) / 2 == d) ? (((k - 1) % 2) ? 1 : -1) : 0;
   }
@@ -40,7 +40,7 @@ struct Stencil {
     if (BOX) return k;
     int s = (ipow3(N) - 1) / 2;
     if (k == 0) return s;
-    return s + (((k - 1) % 2) ? 1 : -1) * ipow3((k - 1) / 2);
+    return s + (((k - 1) % 2) ? 1 : -1) * p3((k - 1) / 2);
   }
 };
 
@@ -62,6 +62,7 @@ EP_HD void load_geom(const GridView<N>& gv, const long long* idx, PointGeom<N>& 
     g.hi[d] = idx[d] == gv.S[d] - 1;
     state[d] = gv.x[d][idx[d]];
   }
+  finish_geom<N>(g);
 }
 
 // Gather the 3^N box of unknown f around point pt (slots outside the grid are never read
@@ -76,7 +77,7 @@ EP_HD void load_box(const double* __restrict__ yf, long long pt, const GridView<
     bool ok = true;
 #pragma unroll
     for (int d = 0; d < N; ++d) {
-      const int o = (k / ipow3(d)) % 3 - 1;
+      const int o = (k / p3(d)) % 3 - 1;
       if ((o < 0 && g.lo[d]) || (o > 0 && g.hi[d])) ok = false;
       q += o * gv.stride[d];
     }
@@ -127,13 +128,13 @@ EP_HD double apply_row_terms(double g, double y, const RowTerms& t) {
 
 // Residual of all F unknowns at one point from the boxes w[f][3^N].
 template <class M, bool SAVE>
-EP_HD void eval_point(const double* prm, const double* state, const PointGeom<M::N>& g,
+EP_HD void eval_point(const typename M::Pre& pre, const PointGeom<M::N>& g,
                       const double (*w)[ipow3(M::N)], const double (*bc_lo)[M::N], const double (*bc_hi)[M::N],
                       double* out, double* sv) {
   Deriv<M::N> u[M::F];
 #pragma unroll
   for (int f = 0; f < M::F; ++f) differentiate<M::N>(w[f], g, bc_lo[f], bc_hi[f], u[f]);
-  M::template eval<SAVE>(prm, state, u, out, sv);
+  M::template eval<SAVE>(pre, u, out, sv);
 }
 
 // FiniteDiff's step: sqrt(eps) * max(1, sqrt(||x .* mask_c||_2)); the kernel receives the
@@ -169,7 +170,7 @@ EP_HD int ncolors_grid(const GridView<N>& gv) {
 // With HAVE_R0 the caller already holds R(pt) in r0 (FiniteDiff re-evaluates f(x); the
 // value is identical, so kernels that kept it skip that evaluation).
 template <class M, bool BOX, bool HAVE_R0 = false, class Emit>
-EP_HD void jacobian_point(const double* prm, const double* state, const PointGeom<M::N>& g, const long long* idx,
+EP_HD void jacobian_point(const typename M::Pre& pre, const PointGeom<M::N>& g, const long long* idx,
                           const GridView<M::N>& gv, double (*w)[ipow3(M::N)], const double (*bc_lo)[M::N],
                           const double (*bc_hi)[M::N], const RowTerms* rt, const double* eps_table,
                           int eps_per_column, double* r0, Emit emit) {
@@ -178,7 +179,7 @@ EP_HD void jacobian_point(const double* prm, const double* state, const PointGeo
   using St = Stencil<N, BOX>;
   if (!HAVE_R0) {
     double g0[F];
-    eval_point<M, false>(prm, state, g, w, bc_lo, bc_hi, g0, nullptr);
+    eval_point<M, false>(pre, g, w, bc_lo, bc_hi, g0, nullptr);
 #pragma unroll
     for (int f = 0; f < F; ++f) r0[f] = apply_row_terms(g0[f], w[f][C], rt[f]);
   }
@@ -212,7 +213,7 @@ EP_HD void jacobian_point(const double* prm, const double* state, const PointGeo
       }
       w[fin][slot] = saved + eps;
       double g1[F];
-      eval_point<M, false>(prm, state, g, w, bc_lo, bc_hi, g1, nullptr);
+      eval_point<M, false>(pre, g, w, bc_lo, bc_hi, g1, nullptr);
 #pragma unroll
       for (int fout = 0; fout < F; ++fout) {
         const double r1 = apply_row_terms(g1[fout], w[fout][C], rt[fout]);

@@ -180,29 +180,25 @@ __global__ void __launch_bounds__(kBlock) k_pcr_final(long long n, PcrSystem in,
 // rows.  Returns x_i.  All threads of the block must call it.
 __device__ __forceinline__ double block_pcr_solve(double a, double b, double c, double d, int i, int n, double* sh) {
   const int T = blockDim.x;
-  double* sa = sh;
-  double* sb = sh + T;
-  double* sc = sh + 2 * T;
-  double* sd = sh + 3 * T;
   int buf = 0;
   if (i >= n) { a = 0.0; b = 1.0; c = 0.0; d = 0.0; }
   for (int s = 1; s < n; s <<= 1) {
-    double* wa = sa + buf * 4 * T;
-    double* wb = sb + buf * 4 * T;
-    double* wc = sc + buf * 4 * T;
-    double* wd = sd + buf * 4 * T;
-    wa[i] = a; wb[i] = b; wc[i] = c; wd[i] = d;
+    double* wa = sh + buf * 4 * T;   // a, 1/b, c, d of every row for this step
+    double* wi = wa + T;
+    double* wc = wi + T;
+    double* wd = wc + T;
+    wa[i] = a; wi[i] = 1.0 / b; wc[i] = c; wd[i] = d;   // each pivot is inverted once, by its owner
     __syncthreads();
     const int im = i - s, ip = i + s;
     double na = 0.0, nc = 0.0;
     if (im >= 0 && i < n) {
-      const double alpha = -a / wb[im];
+      const double alpha = -a * wi[im];
       na = alpha * wa[im];
       b += alpha * wc[im];
       d += alpha * wd[im];
     }
     if (ip < n && i < n) {
-      const double gamma = -c / wb[ip];
+      const double gamma = -c * wi[ip];
       nc = gamma * wc[ip];
       b += gamma * wa[ip];
       d += gamma * wd[ip];

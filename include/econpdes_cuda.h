@@ -199,6 +199,10 @@ int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, con
                            double* solution, double* residual_norm, int32_t* exit_reason, int32_t* n_outer,
                            int32_t* n_newton);
 
+/* econpdes_solve_batched keeps its device workspace (per host thread) between calls of the same
+ * shape; this frees it. */
+void econpdes_release_workspace(void);
+
 /* --- device / multi-GPU plumbing --- */
 int econpdes_device_count(void);
 int econpdes_set_device(int device);

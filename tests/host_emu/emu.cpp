@@ -43,8 +43,10 @@ int residual(const long long* S, const double* const* grids, const double* prm, 
       load_bc<N>(bc ? bc + f * gv.l : nullptr, pt, idx, gv, g, bl[f], bh[f]);
     }
     double o[F], sv[M::NSAVED > 0 ? M::NSAVED : 1];
-    if (saved) eval_point<M, true>(prm, st, g, w, bl, bh, o, sv);
-    else eval_point<M, false>(prm, st, g, w, bl, bh, o, sv);
+    typename M::Pre pre;
+    M::prepare(prm, st, pre);
+    if (saved) eval_point<M, true>(pre, g, w, bl, bh, o, sv);
+    else eval_point<M, false>(pre, g, w, bl, bh, o, sv);
     for (int f = 0; f < F; ++f) out[f * gv.l + pt] = o[f];
     if (saved) for (int s = 0; s < M::NSAVED; ++s) saved[s * gv.l + pt] = sv[s];
   }
@@ -77,7 +79,9 @@ int jacobian(const long long* S, const double* const* grids, const double* prm, 
     }
     double r0[F];
     const long long l = gv.l;
-    jacobian_point<M, BOX>(prm, st, g, idx, gv, w, bl, bh, rt, eps_table, eps_per_column, r0,
+    typename M::Pre pre;
+    M::prepare(prm, st, pre);
+    jacobian_point<M, BOX>(pre, g, idx, gv, w, bl, bh, rt, eps_table, eps_per_column, r0,
                            [&](int k, int fin, int fout, double v) { planes[((long long)(k * F + fin) * F + fout) * l + pt] = v; });
     for (int f = 0; f < F; ++f) r0out[f * l + pt] = r0[f];
   }
