@@ -348,3 +348,76 @@ def test_golden_1d_fixtures():
                      verbose=False)
     np.testing.assert_allclose(res.solution["v"], gold["sol_v"], rtol=1e-8)
     assert res.n_outer == gold["log"].shape[0]
+
+
+# ------------------------------------------------------------ 2-D / 3-D: Krylov + multigrid
+def _csc(nz, S, F):
+    import scipy.sparse as sp
+    colptr, rowval = eo.local_stencil_jacobian(S, F)
+    n = int(np.prod(S)) * F
+    return sp.csc_matrix((nz, rowval - 1, colptr - 1), shape=(n, n))
+
+
+@pytest.mark.parametrize("name", ["by", "ahlm", "hjb3d"])
+@pytest.mark.parametrize("delta", [1.0, 1e3, INF])
+def test_linear_solve_matches_sparse_lu(name, delta):
+    """J x = b by FGMRES + multigrid equals the sparse LU solve the reference performs."""
+    import scipy.sparse.linalg as spla
+    _, pm, om, g, gu = [c for c in CASES if c[0] == name][0]
+    grids = list(g.values())
+    S = tuple(len(x) for x in grids)
+    y, ypost = _perturbed(gu), _perturbed(gu, seed=2)
+    h = E.Handle(pm, grids, y)
+    nz, _ = h.jacobian_csc(y, ypost, delta)
+    rng = np.random.default_rng(5)
+    b = rng.normal(size=int(np.prod(S)))
+    x, iters, relres, rc = h.linear_solve(b)
+    h.close()
+    assert rc == 0 and relres <= 1e-11 and 0 < iters <= 60
+    want = spla.splu(_csc(nz, S, 1)).solve(b)
+    np.testing.assert_allclose(x, want, rtol=0, atol=1e-9 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("fixture,model,gk,sk", [
+    ("c3_bansal_yaron_30", PM.BansalYaronModel, ("mu", "v"), "p"),
+    ("c3_bansal_yaron_64", PM.BansalYaronModel, ("mu", "v"), "p"),
+    ("c2_ahlm_10x100", PM.AchdouHanLasryLionsMollModel_Diffusion, ("y", "a"), "v"),
+    ("c2_ahlm_16x256", PM.AchdouHanLasryLionsMollModel_Diffusion, ("y", "a"), "v"),
+    ("c5_hjb3d_12", PM.Hjb3dSynth, ("x", "y", "z"), "v"),
+])
+def test_pdesolve_nd_against_golden(fixture, model, gk, sk):
+    gold = np.load(os.path.join(GOLD, fixture + ".npz"))
+    grid = {k: gold["grid_" + k] for k in gk}
+    res = E.pdesolve(model(*gold["params"]), grid, {sk: gold["guess_" + sk]}, verbose=False)
+    assert res.converged == bool(gold["converged"])
+    np.testing.assert_allclose(res.solution[sk], gold["sol_" + sk], rtol=1e-8)
+    assert abs(res.residual_norm - float(gold["residual_norm"])) <= 1e-10
+    log = gold["log"]
+    assert res.n_outer == log.shape[0]
+    assert [r["status"] for r in res.log] == [int(s) for s in log[:, 3]]
+    assert [r["newton_iters"] for r in res.log] == [int(s) for s in log[:, 4]]
+    for r, o in zip(res.log, log):
+        assert "%.2e" % r["delta"] == "%.2e" % o[1]
+    for name in [k[6:] for k in gold.files if k.startswith("saved_")]:
+        np.testing.assert_allclose(res.saved[name], gold["saved_" + name], rtol=1e-7, atol=1e-9)
+
+
+def test_pdesolve_2d_known_answer_and_inf_step():
+    # test/runtests.jl:269-281: v = x + z at Δ = Inf
+    grid = {"x": OM.julia_range(0, 1, 4), "z": OM.julia_range(0, 1, 5)}
+    res = E.pdesolve(PM.LinearSum2D(), grid, {"v": np.zeros((4, 5))}, Δ=INF, verbose=False)
+    assert res.residual_norm <= 1e-8
+    np.testing.assert_allclose(res.solution["v"], grid["x"][:, None] + grid["z"][None, :], rtol=1e-10, atol=1e-12)
+    g3 = {k: OM.julia_range(0, 1, n) for k, n in (("x", 3), ("z", 4), ("q", 5))}
+    res = E.pdesolve(PM.LinearSum3D(), g3, {"v": np.zeros((3, 4, 5))}, Δ=INF, verbose=False)
+    want = g3["x"][:, None, None] + g3["z"][None, :, None] + g3["q"][None, None, :]
+    np.testing.assert_allclose(res.solution["v"], want, rtol=1e-10, atol=1e-12)
+
+
+def test_pdesolve_ahlm_live_oracle_with_saved():
+    g, gu, prm = OM.ahlm_diffusion_problem(12, 150)
+    res = E.pdesolve(PM.AchdouHanLasryLionsMollModel_Diffusion(**prm), g, gu, verbose=False)
+    ora = eo.pdesolve(OM.ahlm_diffusion(**prm), g, gu)
+    _check_against(res, ora)
+    np.testing.assert_allclose(res.saved["c"], ora.saved["c"], rtol=1e-7)
+    np.testing.assert_allclose(res.saved["mua"], ora.saved["mua"], rtol=0, atol=1e-7)
