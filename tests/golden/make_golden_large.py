@@ -1,0 +1,34 @@
+"""Larger oracle fixtures (minutes of CPU each): C2 at its full 64x4096 size, C3 at 256^2,
+C5 at 24^3.  Stored as float64 .npz; see make_golden.py for provenance."""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import econpdes_oracle as eo  # noqa: E402
+from oracle import models as M  # noqa: E402
+from tests.golden.make_golden import pack  # noqa: E402
+
+which = sys.argv[1:] or ["c2", "c3", "c5"]
+if "c2" in which:
+    t = time.time()
+    g, gu, prm = M.ahlm_diffusion_problem(64, 4096)
+    res = eo.pdesolve(M.ahlm_diffusion(**prm), g, gu)
+    d = {k: v for k, v in pack(res, g, gu, prm).items() if not (k.startswith("guess_") or k.startswith("saved_"))}
+    np.savez_compressed(os.path.join(HERE, "c2_ahlm_64x4096.npz"), **d)   # guess is a formula: keep the file small
+    print("c2", res.converged, res.residual_norm, res.log.n_outer, res.log.n_newton, time.time() - t, flush=True)
+if "c3" in which:
+    t = time.time()
+    g, gu, prm = M.bansal_yaron_problem(256, 256)
+    res = eo.pdesolve(M.bansal_yaron(**prm), g, gu)
+    np.savez_compressed(os.path.join(HERE, "c3_bansal_yaron_256.npz"), **pack(res, g, gu, prm))
+    print("c3", res.converged, res.residual_norm, res.log.n_outer, res.log.n_newton, time.time() - t, flush=True)
+if "c5" in which:
+    t = time.time()
+    g, gu, prm = M.hjb3d_problem(24)
+    res = eo.pdesolve(M.hjb3d_synth(**prm), g, gu)
+    np.savez_compressed(os.path.join(HERE, "c5_hjb3d_24.npz"), **pack(res, g, gu, prm))
+    print("c5", res.converged, res.residual_norm, res.log.n_outer, res.log.n_newton, time.time() - t, flush=True)

@@ -421,3 +421,40 @@ def test_pdesolve_ahlm_live_oracle_with_saved():
     _check_against(res, ora)
     np.testing.assert_allclose(res.saved["c"], ora.saved["c"], rtol=1e-7)
     np.testing.assert_allclose(res.saved["mua"], ora.saved["mua"], rtol=0, atol=1e-7)
+
+
+def test_c2_full_size_against_oracle_fixture():
+    """Config C2 at its full 64x4096 size (the oracle needs ~2 min of SuperLU for this)."""
+    gold = np.load(os.path.join(GOLD, "c2_ahlm_64x4096.npz"))
+    m = PM.AchdouHanLasryLionsMollModel_Diffusion(*gold["params"])
+    ys, as_ = gold["grid_y"], gold["grid_a"]
+    Y, A = np.meshgrid(ys, as_, indexing="ij")
+    guess = (m.rho / m.gamma + (1 - 1 / m.gamma) * m.r) ** (-m.gamma) * (A + Y / m.r) ** (1 - m.gamma) / (1 - m.gamma)
+    res = E.pdesolve(m, {"y": ys, "a": as_}, {"v": guess}, verbose=False)
+    assert res.converged == bool(gold["converged"]) and res.n_outer == gold["log"].shape[0]
+    assert [r["newton_iters"] for r in res.log] == [int(s) for s in gold["log"][:, 4]]
+    np.testing.assert_allclose(res.solution["v"], gold["sol_v"], rtol=1e-8)
+    assert abs(res.residual_norm - float(gold["residual_norm"])) <= 1e-10
+
+
+@pytest.mark.parametrize("fixture,model,gk,sk", [
+    ("c3_bansal_yaron_256", PM.BansalYaronModel, ("mu", "v"), "p"),
+    ("c5_hjb3d_24", PM.Hjb3dSynth, ("x", "y", "z"), "v"),
+])
+def test_pdesolve_nd_against_larger_golden(fixture, model, gk, sk):
+    test_pdesolve_nd_against_golden(fixture, model, gk, sk)
+
+
+def test_c3_reference_semantics_reject_pattern_1024():
+    """SURVEY.md hard part 3: at 1024^2 FiniteDiff's per-color step degrades the Jacobian; under
+    exact reference semantics step 1 takes all 10 Newton iterations and step 2 (dt = 10.2) is
+    rejected.  The device path must reproduce that, not paper over it."""
+    from econpdes_b200 import examples as EX
+    g, gu = EX.bansal_yaron_grid(1024, 1024)
+    res = E.pdesolve(PM.BansalYaronModel(), g, gu, verbose=False, maxiters=3, warn=False)
+    assert [r["status"] for r in res.log] == [0, 2, 0]
+    assert res.log[0]["newton_iters"] == 10 and "%.2e" % res.log[1]["delta"] == "1.02e+01"
+    assert "%.2e" % res.log[2]["delta"] == "1.02e+00"
+    # the robust per-column step (not reference parity) solves the same steps in a few iterations
+    res2 = E.pdesolve(PM.BansalYaronModel(), g, gu, verbose=False, maxiters=3, warn=False, eps_policy=1)
+    assert [r["status"] for r in res2.log] == [0, 0, 0] and res2.log[0]["newton_iters"] <= 5
