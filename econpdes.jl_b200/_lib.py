@@ -74,6 +74,7 @@ SYMBOLS = {
                                         c_double_p]),
     "econpdes_implicit_timestep": (C.c_int, [C.c_void_p, C.POINTER(Options), c_double_p, C.c_double, C.c_int32,
                                              C.c_double, c_double_p, c_double_p, c_int32_p]),
+    "econpdes_bench_kernels": (C.c_int, [C.c_void_p, c_double_p, C.c_int, c_double_p]),
     "econpdes_solve": (C.c_int, [C.c_void_p, C.POINTER(Options), C.POINTER(Result)]),
     "econpdes_batch_create": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]),
     "econpdes_batch_destroy": (None, [C.c_void_p]),

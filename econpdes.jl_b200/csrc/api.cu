@@ -218,6 +218,56 @@ int econpdes_implicit_timestep(econpdes_handle* h, const econpdes_options* optio
   });
 }
 
+int econpdes_bench_kernels(econpdes_handle* h, const double* y, int reps, double* ms_out) {
+  return guarded([&] {
+    if (!h || !y || !ms_out || reps < 1) throw std::invalid_argument("bad argument");
+    Solver& sv = *h->solver;
+    Ctx& c = sv.ctx();
+    cudaStream_t s = c.stream;
+    h->a.upload(y, static_cast<size_t>(c.n), s);
+    h->b.alloc(static_cast<size_t>(c.n));
+    DevBuf<double> flush;
+    const size_t flush_bytes = 512ull << 20;
+    flush.alloc(flush_bytes / sizeof(double));
+    cudaEvent_t e0, e1;
+    EP_CUDA(cudaEventCreate(&e0));
+    EP_CUDA(cudaEventCreate(&e1));
+    auto timed = [&](auto&& fn) {
+      double tot = 0.0;
+      for (int r = 0; r < reps + 1; ++r) {
+        EP_CUDA(cudaMemsetAsync(flush.p, 0, flush_bytes, s));   // evict L2 between timed launches
+        EP_CUDA(cudaEventRecord(e0, s));
+        fn();
+        EP_CUDA(cudaEventRecord(e1, s));
+        EP_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        EP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (r > 0) tot += ms;
+      }
+      return tot / reps;
+    };
+    const ModelOps* ops = model_ops(c.model_id);
+    RowSpec g{};   // R = G
+    g.ypost = nullptr; g.delta = INFINITY; g.delta_rel = nullptr; g.is_alg = nullptr; g.lb = nullptr; g.ub = nullptr;
+    g.has_bounds = 0;
+    RowSpec r = g;
+    r.ypost = c.guess.p;
+    r.delta = 1.0;
+    ms_out[0] = timed([&] { ops->residual(c, h->a.p, g, h->b.p, false); });
+    ms_out[1] = timed([&] { ops->residual(c, h->a.p, r, h->b.p, true); });
+    ms_out[2] = timed([&] { ops->jacobian(c, h->a.p, r, ECONPDES_EPS_FINITEDIFF_COLOR_NORM, sv.planes(), nullptr); });
+    h->have_jacobian = true;
+    double lin[3] = {0, 0, 0};
+    if (c.N >= 2) sv.linear().bench(sv.planes(), h->a.p, reps, flush.p, flush_bytes, lin);
+    ms_out[3] = lin[0];
+    ms_out[4] = lin[1];
+    ms_out[5] = lin[2];
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ECONPDES_OK;
+  });
+}
+
 int econpdes_solve(econpdes_handle* h, const econpdes_options* options, econpdes_result* result) {
   return guarded([&] {
     if (!h || !options || !result) throw std::invalid_argument("null argument");

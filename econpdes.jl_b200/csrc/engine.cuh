@@ -108,6 +108,13 @@ struct LinearSolver {
   // returns 0 on success, 1 if the solve failed (singular / non-finite / not converged)
   virtual int solve(const double* planes, const double* b, double* x, const econpdes_options& opt, int* iters,
                     double* relres) = 0;
+  // device ms per launch of the solver's building blocks (bench.py): [0] stencil SpMV,
+  // [1] one preconditioner application (multigrid V-cycle), [2] hierarchy set-up
+  virtual void bench(const double* planes, const double* v, int reps, double* flush, size_t flush_bytes,
+                     double* ms_out) {
+    (void)planes; (void)v; (void)reps; (void)flush; (void)flush_bytes;
+    ms_out[0] = ms_out[1] = ms_out[2] = 0.0;
+  }
 };
 std::unique_ptr<LinearSolver> make_tridiag_solver(Ctx& c);
 std::unique_ptr<LinearSolver> make_krylov_solver(Ctx& c);  // krylov.cu

@@ -29,7 +29,8 @@ namespace econpdes {
 namespace {
 
 constexpr int kMaxLevels = 16;
-constexpr int kCoarseMax = 8;      // stop coarsening when every dimension has <= this many points
+constexpr int kCoarseMax2D = 8;    // stop coarsening when every dimension has <= this many points
+constexpr int kCoarseMax3D = 4;    // (the coarsest operator is factorised densely by one thread block)
 constexpr double kLinearThreshold = 0.3;
 
 template <int N>
@@ -323,58 +324,65 @@ __global__ void __launch_bounds__(kBlock) k_prolong_add(Transfer t, LevelGeom<N>
   xf[pf] += acc;
 }
 
-// Galerkin coarse operator: one thread per (coarse row I, coarse offset O) sums
-// w(i,I) A[i, j] w(j, I+O) over the fine rows i under I and their stencil columns j.
-template <int N, bool BOXF>
-__global__ void __launch_bounds__(kBlock) k_rap(Transfer t, LevelGeom<N> gf, LevelGeom<N> gc,
-                                                const double* __restrict__ Af, double* __restrict__ Ac) {
-  using Sf = Stencil<N, BOXF>;
+// Separable Galerkin product: coarsen ONE dimension d of the operator (the full P^T A P with
+// tensor-product transfers is the composition of these passes, each O(9) work per entry).
+// Input planes live on grid gin (shape BOXIN), output box planes on gout (= gin with
+// dimension d coarsened).  One thread per (output row, output offset).
+template <int N, bool BOX>
+__device__ __forceinline__ int plane_of(const int* o) {
+  if (BOX) {
+    int k = 0;
+#pragma unroll
+    for (int d = 0; d < N; ++d) k += (o[d] + 1) * p3(d);
+    return k;
+  }
+  int nz = 0, k = 0;
+#pragma unroll
+  for (int d = 0; d < N; ++d)
+    if (o[d] != 0) { ++nz; k = 1 + 2 * d + (o[d] > 0 ? 1 : 0); }
+  return nz == 0 ? 0 : (nz == 1 ? k : -1);
+}
+
+template <int N, bool BOXIN>
+__global__ void __launch_bounds__(kBlock) k_rap_1d(int d, int type, LevelGeom<N> gin, LevelGeom<N> gout,
+                                                   const double* __restrict__ Ain, double* __restrict__ Aout) {
   constexpr int KC = ipow3(N);
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (tid >= gc.l * KC) return;
-  const long long pc = tid % gc.l;
-  const int kO = static_cast<int>(tid / gc.l);
-  long long I[N], J[N], lo[N], hi[N];
-  unravel_l<N>(pc, gc, I);
-  bool inside = true;
+  if (tid >= gout.l * KC) return;
+  const long long pout = tid % gout.l;
+  const int kout = static_cast<int>(tid / gout.l);
+  long long idx[N];
+  unravel_l<N>(pout, gout, idx);
+  int O[N];
 #pragma unroll
-  for (int d = 0; d < N; ++d) {
-    J[d] = I[d] + (kO / p3(d)) % 3 - 1;
-    if (J[d] < 0 || J[d] >= gc.S[d]) inside = false;
-    fine_range(t.type[d], I[d], gf.S[d], lo[d], hi[d]);
-  }
+  for (int e = 0; e < N; ++e) O[e] = (kout / p3(e)) % 3 - 1;
+  const long long I = idx[d], J = I + O[d];
   double acc = 0.0;
-  if (inside) {
-    long long cnt[N];
-    long long total = 1;
+  if (J >= 0 && J < gout.S[d]) {
+    long long lo, hi, pbase = 0;
+    fine_range(type, I, gin.S[d], lo, hi);
 #pragma unroll
-    for (int d = 0; d < N; ++d) { cnt[d] = hi[d] - lo[d] + 1; total *= cnt[d]; }
-    for (long long r = 0; r < total; ++r) {
-      long long i[N], rr = r, pf = 0;
-      double wi = 1.0;
-#pragma unroll
-      for (int d = 0; d < N; ++d) {
-        i[d] = lo[d] + rr % cnt[d];
-        rr /= cnt[d];
-        wi *= tw(t.type[d], i[d], I[d], gc.S[d]);
-        pf += i[d] * gf.stride[d];
-      }
+    for (int e = 0; e < N; ++e)
+      if (e != d) pbase += idx[e] * gin.stride[e];
+    for (long long i = lo; i <= hi; ++i) {
+      const double wi = tw(type, i, I, gout.S[d]);
       if (wi == 0.0) continue;
+      const long long pin = pbase + i * gin.stride[d];
 #pragma unroll
-      for (int k = 0; k < Sf::NK; ++k) {
-        double wj = 1.0;
-        bool ok = true;
+      for (int od = -1; od <= 1; ++od) {
+        const long long j = i + od;
+        if (j < 0 || j >= gin.S[d]) continue;
+        const double wj = tw(type, j, J, gout.S[d]);
+        if (wj == 0.0) continue;
+        int o[N];
 #pragma unroll
-        for (int d = 0; d < N; ++d) {
-          const long long j = i[d] + Sf::off(k, d);
-          if (j < 0 || j >= gf.S[d]) ok = false;
-          else wj *= tw(t.type[d], j, J[d], gc.S[d]);
-        }
-        if (ok && wj != 0.0) acc += wi * Af[k * gf.l + pf] * wj;
+        for (int e = 0; e < N; ++e) o[e] = e == d ? od : O[e];
+        const int kin = plane_of<N, BOXIN>(o);
+        if (kin >= 0) acc += wi * Ain[kin * gin.l + pin] * wj;
       }
     }
   }
-  Ac[kO * gc.l + pc] = acc;
+  Aout[kout * gout.l + pout] = acc;
 }
 
 // sum over the grid of min(|a+|,|a-|) and max(|a+|,|a-|) of the two couplings across each
@@ -584,10 +592,41 @@ class KrylovSolver final : public LinearSolver {
     return fgmres(b, x, opt, iters, relres);
   }
 
+  void bench(const double* planes, const double* v, int reps, double* flush, size_t flush_bytes,
+             double* ms_out) override {
+    cudaStream_t s = c_.stream;
+    cudaEvent_t e0, e1;
+    EP_CUDA(cudaEventCreate(&e0));
+    EP_CUDA(cudaEventCreate(&e1));
+    auto timed = [&](auto&& fn) {
+      double tot = 0.0;
+      for (int r = 0; r < reps + 1; ++r) {
+        EP_CUDA(cudaMemsetAsync(flush, 0, flush_bytes, s));   // evict L2 between timed launches
+        EP_CUDA(cudaEventRecord(e0, s));
+        fn();
+        EP_CUDA(cudaEventRecord(e1, s));
+        EP_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        EP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (r > 0) tot += ms;   // first one is warm-up
+      }
+      return tot / reps;
+    };
+    ms_out[2] = timed([&] { setup(planes); });
+    Level<N>& L0 = *lev_[0];
+    w_.alloc(static_cast<size_t>(L0.l));
+    DevBuf<double> z;
+    z.alloc(static_cast<size_t>(L0.l));
+    ms_out[0] = timed([&] { spmv(L0, v, nullptr, w_.p, 0); });
+    ms_out[1] = timed([&] { vcycle(0, v, z.p); });
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+
  private:
   Ctx& c_;
   std::vector<std::unique_ptr<Level<N>>> lev_;
-  DevBuf<double> dense_, sym_, V_, Z_, w_, dots_, part_, hdev_;
+  DevBuf<double> dense_, sym_, V_, Z_, w_, dots_, part_, hdev_, rap_tmp_[2];
   DevBuf<int> piv_;
   double* h_ = nullptr;
   int dense_n_ = 0;
@@ -619,7 +658,7 @@ class KrylovSolver final : public LinearSolver {
       prepare_level(L);
       bool coarsest = true;
       for (int d = 0; d < N; ++d)
-        if (L.S[d] > kCoarseMax) coarsest = false;
+        if (L.S[d] > (N == 3 ? kCoarseMax3D : kCoarseMax2D)) coarsest = false;
       if (coarsest || li + 1 >= kMaxLevels) break;
       // transfer type per dimension from the symmetry of the couplings
       sym_.zero(s);
@@ -650,9 +689,35 @@ class KrylovSolver final : public LinearSolver {
       Lc.nk = ipow3(N);
       Lc.Aown.alloc(static_cast<size_t>(Lc.nk) * Lc.l);
       Lc.A = Lc.Aown.p;
-      const long long nthreads = Lc.l * ipow3(N);
-      if (L.box) EP_LAUNCH((k_rap<N, true>), blocks_for(nthreads), kBlock, 0, s, t, make_geom<N>(L.S), make_geom<N>(Lc.S), L.A, Lc.Aown.p);
-      else EP_LAUNCH((k_rap<N, false>), blocks_for(nthreads), kBlock, 0, s, t, make_geom<N>(L.S), make_geom<N>(Lc.S), L.A, Lc.Aown.p);
+      // separable Galerkin product, one coarsened dimension per pass
+      {
+        long long Sin[N];
+        for (int d = 0; d < N; ++d) Sin[d] = L.S[d];
+        const double* in = L.A;
+        bool inbox = L.box;
+        int npass = 0, pass = 0;
+        for (int d = 0; d < N; ++d) npass += t.type[d] >= 0 ? 1 : 0;
+        for (int d = 0; d < N; ++d) {
+          if (t.type[d] < 0) continue;
+          long long Sout[N];
+          for (int e = 0; e < N; ++e) Sout[e] = Sin[e];
+          Sout[d] = t.Sc[d];
+          const LevelGeom<N> gin = make_geom<N>(Sin), gout = make_geom<N>(Sout);
+          double* out;
+          if (++pass == npass) {
+            out = Lc.Aown.p;
+          } else {
+            rap_tmp_[pass & 1].alloc(static_cast<size_t>(ipow3(N)) * gout.l);
+            out = rap_tmp_[pass & 1].p;
+          }
+          const long long nthreads = gout.l * ipow3(N);
+          if (inbox) EP_LAUNCH((k_rap_1d<N, true>), blocks_for(nthreads), kBlock, 0, s, d, t.type[d], gin, gout, in, out);
+          else EP_LAUNCH((k_rap_1d<N, false>), blocks_for(nthreads), kBlock, 0, s, d, t.type[d], gin, gout, in, out);
+          in = out;
+          inbox = true;
+          for (int e = 0; e < N; ++e) Sin[e] = Sout[e];
+        }
+      }
       ++li;
     }
     nlev_ = static_cast<int>(li) + 1;

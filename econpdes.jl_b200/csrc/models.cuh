@@ -29,11 +29,19 @@
 
 namespace econpdes {
 
+// Defaults shared by the functors.  slot_used(k) says whether the residual can depend on box
+// slot k = (o1+1) + 3(o2+1) + 9(o3+1) at all; the Jacobian kernel skips the perturbed evaluation
+// for slots a model never reads (their entries are exact zeros in the reference too, because
+// (f(x1)-f(x))/eps = 0/eps).
+struct ModelDefaults {
+  EP_HD static constexpr bool slot_used(int) { return true; }
+};
+
 EP_HD double ep_min(double a, double b) { return a < b ? a : b; }   // operands are never NaN where used
 EP_HD double ep_max(double a, double b) { return a > b ? a : b; }
 
 // README.md:58-67  rho*v = x + mu(x) v_x
-struct ReadmeLinear {
+struct ReadmeLinear : ModelDefaults {
   static constexpr int N = 1, F = 1, NPARAMS = 2, NSAVED = 0;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "readme_linear"; }
@@ -51,7 +59,7 @@ struct ReadmeLinear {
 };
 
 // examples/asset_pricing/campbell_cochrane.jl:66-84
-struct CampbellCochrane {
+struct CampbellCochrane : ModelDefaults {
   static constexpr int N = 1, F = 1, NPARAMS = 6, NSAVED = 0;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "campbell_cochrane"; }
@@ -82,7 +90,7 @@ struct CampbellCochrane {
 };
 
 // examples/asset_pricing/bansal_yaron.jl:65-95   states (mu, v)
-struct BansalYaron {
+struct BansalYaron : ModelDefaults {
   static constexpr int N = 2, F = 1, NPARAMS = 9, NSAVED = 0;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "bansal_yaron"; }
@@ -124,7 +132,7 @@ struct BansalYaron {
 
 // examples/consumption_saving/consumption_saving_diffusion_income.jl:71-106  states (y, a)
 // saved = (mua, c)
-struct AhlmDiffusion {
+struct AhlmDiffusion : ModelDefaults {
   static constexpr int N = 2, F = 1, NPARAMS = 8, NSAVED = 2;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "ahlm_diffusion"; }
@@ -175,10 +183,15 @@ struct AhlmDiffusion {
 
 // Synthetic 3-state HJB of config C5; definition shared verbatim with
 // oracle/models.py:hjb3d_synth.
-struct Hjb3dSynth {
+struct Hjb3dSynth : ModelDefaults {
   static constexpr int N = 3, F = 1, NPARAMS = 9, NSAVED = 0;
   static constexpr bool USES_CROSS = true;
   static const char* name() { return "hjb3d_synth"; }
+  // the body reads the axial neighbours and, through vxy_up only, the (+1,+1,0) / (-1,-1,0) corners
+  EP_HD static constexpr bool slot_used(int k) {
+    const int o0 = k % 3 - 1, o1 = (k / 3) % 3 - 1, o2 = k / 9 - 1;
+    return (o2 == 0 && (o0 == 0 || o1 == 0 || o0 == o1)) || (o0 == 0 && o1 == 0);
+  }
   struct Pre { double xyz, mx, my, mz, hx, hy, hz, cxy, rho, theta; };
   EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
     const double kx = prm[0], ky = prm[1], kz = prm[2], sx = prm[3], sy = prm[4], sz = prm[5], corr = prm[6];
@@ -208,7 +221,7 @@ struct Hjb3dSynth {
 };
 
 // examples/neoclassical_growth.jl:61-84   saved = (c, muk)
-struct NeoclassicalGrowth {
+struct NeoclassicalGrowth : ModelDefaults {
   static constexpr int N = 1, F = 1, NPARAMS = 5, NSAVED = 2;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "neoclassical_growth"; }
@@ -252,7 +265,7 @@ struct NeoclassicalGrowth {
 };
 
 // test/runtests.jl:28-44 (branch structure differs from the example above)
-struct GrowthTest {
+struct GrowthTest : ModelDefaults {
   static constexpr int N = 1, F = 1, NPARAMS = 5, NSAVED = 2;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "growth_test"; }
@@ -285,7 +298,7 @@ struct GrowthTest {
 
 // test/runtests.jl:276-279, 314-317:  vt = -(v - x - z - ...)
 template <int NDIM>
-struct LinearSum {
+struct LinearSum : ModelDefaults {
   static constexpr int N = NDIM, F = 1, NPARAMS = 0, NSAVED = 0;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return NDIM == 1 ? "linear_sum_1d" : (NDIM == 2 ? "linear_sum_2d" : "linear_sum_3d"); }
@@ -304,7 +317,7 @@ struct LinearSum {
 };
 
 // test/runtests.jl:379-384: two unknowns (v, p): v = x + p, p = v/2 written forward
-struct ForwardPrice {
+struct ForwardPrice : ModelDefaults {
   static constexpr int N = 1, F = 2, NPARAMS = 0, NSAVED = 0;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "forward_price"; }
@@ -318,7 +331,7 @@ struct ForwardPrice {
 };
 
 // test/runtests.jl:227: vt = v - 2 (used with lower_bound for the MCP known answer)
-struct VMinusTwo {
+struct VMinusTwo : ModelDefaults {
   static constexpr int N = 1, F = 1, NPARAMS = 0, NSAVED = 0;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "v_minus_two"; }

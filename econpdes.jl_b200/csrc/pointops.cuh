@@ -197,12 +197,12 @@ EP_HD void jacobian_point(const typename M::Pre& pre, const PointGeom<M::N>& g, 
         color += static_cast<int>((idx[d] + o + 3) % 3) * stride;
         stride *= gv.S[d] < 3 ? static_cast<int>(gv.S[d]) : 3;
       }
-      if (!ok) {
+      const int slot = St::boxslot(k);
+      if (!ok || !M::slot_used(slot)) {
 #pragma unroll
         for (int fout = 0; fout < F; ++fout) emit(k, fin, fout, 0.0);
         continue;
       }
-      const int slot = St::boxslot(k);
       const double saved = w[fin][slot];
       double eps;
       if (eps_per_column) {

@@ -462,6 +462,13 @@ class Handle:
                                                L.dptr(eps)))
         return nz, eps
 
+    def bench_kernels(self, y, reps=5):
+        """ms per launch: residual, implicit residual+norms, Jacobian, SpMV, V-cycle, MG set-up"""
+        yv = self._vec(y)
+        out = np.zeros(6)
+        L.check(self.lib.econpdes_bench_kernels(self.h, L.dptr(yv), reps, L.dptr(out)))
+        return dict(zip(("residual", "implicit_residual_norms", "jacobian", "spmv", "vcycle", "mg_setup"), out))
+
     def linear_solve(self, b, **kw):
         opts = _options(SQRT_EPS, 100, kw)
         bv = self._vec(b)

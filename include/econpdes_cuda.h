@@ -173,6 +173,12 @@ int econpdes_linear_solve(econpdes_handle* h, const econpdes_options* options, c
 int econpdes_implicit_timestep(econpdes_handle* h, const econpdes_options* options, const double* ypost,
                                double delta, int32_t maxiters, double abstol, double* y_out,
                                double* nl_residual, int32_t* newton_iters);
+/* Measurement hook for bench.py: average device time (ms per launch, CUDA events on the launching
+ * stream, L2 flushed between launches) of the grid-wide kernels at y on the handle's problem:
+ * ms_out[0] residual sweep G(y), [1] implicit residual R(y) + norms, [2] colored-FD Jacobian
+ * (color norms + stencil planes), [3] stencil SpMV, [4] one multigrid V-cycle, [5] multigrid set-up
+ * ([3..5] are 0 for 1-D problems). */
+int econpdes_bench_kernels(econpdes_handle* h, const double* y, int reps, double* ms_out);
 /* finiteschemesolve on the handle's problem starting from its guess */
 int econpdes_solve(econpdes_handle* h, const econpdes_options* options, econpdes_result* result);
 
