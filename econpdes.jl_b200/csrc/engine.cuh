@@ -13,7 +13,8 @@ namespace econpdes {
 template <class T>
 struct DevBuf {
   T* p = nullptr;
-  size_t n = 0;
+  size_t n = 0;    // logical element count
+  size_t cap = 0;  // allocated element count (grow-only: work buffers are re-used across solves)
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
@@ -22,13 +23,18 @@ struct DevBuf {
     if (p) cudaFree(p);
     p = nullptr;
     n = 0;
+    cap = 0;
   }
   void alloc(size_t count) {
-    if (count == n && p) return;
+    if (count <= cap && p) {
+      n = count;
+      return;
+    }
     release();
     if (count == 0) return;
     EP_CUDA(cudaMalloc(&p, count * sizeof(T)));
     n = count;
+    cap = count;
   }
   void zero(cudaStream_t s) { if (p) EP_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
   void upload(const T* h, size_t count, cudaStream_t s) {

@@ -21,6 +21,7 @@
 // its operator per line direction so that every line solve streams contiguous memory, and
 // vectors are transposed in and out around those sweeps.
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "engine.cuh"
@@ -269,8 +270,10 @@ __device__ __forceinline__ void fine_range(int type, long long I, long long Sf, 
 }
 
 template <int N>
-__global__ void __launch_bounds__(kBlock) k_restrict(Transfer t, LevelGeom<N> gf, LevelGeom<N> gc,
-                                                     const double* __restrict__ rf, double* __restrict__ rc) {
+__global__ void __launch_bounds__(kBlock) k_restrict(const Transfer* __restrict__ tp, LevelGeom<N> gf,
+                                                     LevelGeom<N> gc, const double* __restrict__ rf,
+                                                     double* __restrict__ rc) {
+  const Transfer t = *tp;   // lives in device memory so a captured CUDA graph sees every set-up's choice
   const long long pc = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (pc >= gc.l) return;
   long long I[N], lo[N], hi[N];
@@ -298,8 +301,10 @@ __global__ void __launch_bounds__(kBlock) k_restrict(Transfer t, LevelGeom<N> gf
 
 // x_f += P e_c
 template <int N>
-__global__ void __launch_bounds__(kBlock) k_prolong_add(Transfer t, LevelGeom<N> gf, LevelGeom<N> gc,
-                                                        const double* __restrict__ ec, double* __restrict__ xf) {
+__global__ void __launch_bounds__(kBlock) k_prolong_add(const Transfer* __restrict__ tp, LevelGeom<N> gf,
+                                                        LevelGeom<N> gc, const double* __restrict__ ec,
+                                                        double* __restrict__ xf) {
+  const Transfer t = *tp;
   const long long pf = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (pf >= gf.l) return;
   long long i[N];
@@ -581,9 +586,12 @@ class KrylovSolver final : public LinearSolver {
   explicit KrylovSolver(Ctx& c) : c_(c) {
     EP_CUDA(cudaMallocHost(&h_, 256 * sizeof(double)));
     sym_.alloc(2 * kMaxDims);
+    const char* e = std::getenv("ECONPDES_NO_GRAPH");
+    use_graph_ = !(e && e[0] == '1');
   }
   ~KrylovSolver() override {
     if (h_) cudaFreeHost(h_);
+    if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
   }
 
   int solve(const double* planes, const double* b, double* x, const econpdes_options& opt, int* iters,
@@ -618,7 +626,7 @@ class KrylovSolver final : public LinearSolver {
     DevBuf<double> z;
     z.alloc(static_cast<size_t>(L0.l));
     ms_out[0] = timed([&] { spmv(L0, v, nullptr, w_.p, 0); });
-    ms_out[1] = timed([&] { vcycle(0, v, z.p); });
+    ms_out[1] = timed([&] { precondition(v, z.p); });
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
   }
@@ -628,6 +636,12 @@ class KrylovSolver final : public LinearSolver {
   std::vector<std::unique_ptr<Level<N>>> lev_;
   DevBuf<double> dense_, sym_, V_, Z_, w_, dots_, part_, hdev_, rap_tmp_[2];
   DevBuf<int> piv_;
+  DevBuf<Transfer> transfers_dev_;
+  cudaGraphExec_t graph_exec_ = nullptr;
+  const double* graph_A_ = nullptr;
+  int graph_nlev_ = 0;
+  int64_t graph_kernels_ = 0;
+  bool use_graph_ = true;
   double* h_ = nullptr;
   int dense_n_ = 0;
   int restart_alloc_ = 0;
@@ -721,6 +735,13 @@ class KrylovSolver final : public LinearSolver {
       ++li;
     }
     nlev_ = static_cast<int>(li) + 1;
+    {
+      Transfer host[kMaxLevels] = {};
+      for (int q = 0; q + 1 < nlev_; ++q) host[q] = lev_[q]->to_coarse;
+      transfers_dev_.alloc(kMaxLevels);
+      EP_CUDA(cudaMemcpyAsync(transfers_dev_.p, host, sizeof(host), cudaMemcpyHostToDevice, s));
+      EP_CUDA(cudaStreamSynchronize(s));
+    }
     // dense LU of the coarsest operator
     Level<N>& Lc = *lev_[nlev_ - 1];
     dense_n_ = static_cast<int>(Lc.l);
@@ -829,12 +850,50 @@ class KrylovSolver final : public LinearSolver {
     smooth(L, b, x, false);
     spmv(L, x, b, L.r.p, 1);
     Level<N>& Lc = *lev_[li + 1];
-    EP_LAUNCH((k_restrict<N>), blocks_for(Lc.l), kBlock, 0, s, L.to_coarse, make_geom<N>(L.S), make_geom<N>(Lc.S),
-              L.r.p, Lc.b.p);
+    EP_LAUNCH((k_restrict<N>), blocks_for(Lc.l), kBlock, 0, s, transfers_dev_.p + li, make_geom<N>(L.S),
+              make_geom<N>(Lc.S), L.r.p, Lc.b.p);
     vcycle(li + 1, Lc.b.p, Lc.x.p);
-    EP_LAUNCH((k_prolong_add<N>), blocks_for(L.l), kBlock, 0, s, L.to_coarse, make_geom<N>(L.S), make_geom<N>(Lc.S),
-              Lc.x.p, x);
+    EP_LAUNCH((k_prolong_add<N>), blocks_for(L.l), kBlock, 0, s, transfers_dev_.p + li, make_geom<N>(L.S),
+              make_geom<N>(Lc.S), Lc.x.p, x);
     smooth(L, b, x, true);
+  }
+
+  // z = V-cycle(v).  The cycle is ~25 small launches per level, launch-latency bound on all but
+  // the finest levels, so it is captured once into a CUDA graph (buffers, grids and shared-memory
+  // sizes depend only on the grid shape; per-set-up choices live in device memory) and replayed.
+  void precondition(const double* v, double* z) {
+    cudaStream_t s = c_.stream;
+    Level<N>& L0 = *lev_[0];
+    if (!use_graph_) {
+      vcycle(0, v, z);
+      return;
+    }
+    if (graph_exec_ == nullptr || graph_A_ != L0.A || graph_nlev_ != nlev_) {
+      if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
+      vcycle(0, L0.b.p, L0.x.p);   // uncaptured once: function attributes, allocations
+      EP_CUDA(cudaStreamSynchronize(s));
+      const int64_t k0 = g_kernel_launches.load();
+      cudaGraph_t graph = nullptr;
+      EP_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      try {
+        vcycle(0, L0.b.p, L0.x.p);
+      } catch (...) {
+        cudaStreamEndCapture(s, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      EP_CUDA(cudaStreamEndCapture(s, &graph));
+      graph_kernels_ = g_kernel_launches.load() - k0;
+      g_kernel_launches.fetch_sub(graph_kernels_);   // captured, not launched
+      EP_CUDA(cudaGraphInstantiate(&graph_exec_, graph, 0));
+      cudaGraphDestroy(graph);
+      graph_A_ = L0.A;
+      graph_nlev_ = nlev_;
+    }
+    EP_CUDA(cudaMemcpyAsync(L0.b.p, v, L0.l * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    EP_CUDA(cudaGraphLaunch(graph_exec_, s));
+    g_kernel_launches.fetch_add(graph_kernels_);
+    EP_CUDA(cudaMemcpyAsync(z, L0.x.p, L0.l * sizeof(double), cudaMemcpyDeviceToDevice, s));
   }
 
   void dots(long long n, int j, const double* V, const double* w, double* host_out) {
@@ -894,7 +953,7 @@ class KrylovSolver final : public LinearSolver {
       int j = 0;
       for (; j < m && total < opt.lin_maxiters; ++j, ++total) {
         double* zj = Z_.p + static_cast<size_t>(j) * n;
-        vcycle(0, V_.p + static_cast<size_t>(j) * n, zj);
+        precondition(V_.p + static_cast<size_t>(j) * n, zj);
         spmv(L0, zj, nullptr, w_.p, 0);
         // classical Gram-Schmidt, twice
         std::fill(hcol.begin(), hcol.end(), 0.0);
