@@ -139,6 +139,24 @@ __global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args)
   // On return y/Gy hold the Newton result and G there; nl = ||R||_2/n (Inf: singular).
   double y = ypost, Gy = Gpost, nl = 0.0;
   int newton_it = 0;
+  // Block-wide OR of a small bit mask in one barrier: warps fold their lanes with REDUX and
+  // post the result with one shared atomic.  Three slots rotate: call k uses slot k%3 and,
+  // after its barrier, clears slot (k+2)%3 -- last read before this barrier, next written
+  // after the following call's barrier -- so no extra synchronisation is needed.
+  unsigned* flagw = reinterpret_cast<unsigned*>(red + 7 * 32);
+  int flag_phase = 0;
+  if (i < 3) flagw[i] = 0u;
+  __syncthreads();
+  auto block_or_bits = [&](unsigned bits) -> unsigned {
+    const unsigned w = __reduce_or_sync(0xffffffffu, bits);
+    if ((i & 31) == 0 && w != 0u) atomicOr(&flagw[flag_phase], w);
+    __syncthreads();
+    const unsigned all = flagw[flag_phase];
+    if (i == 0) flagw[(flag_phase + 2) % 3] = 0u;
+    flag_phase = (flag_phase + 1) % 3;
+    return all;
+  };
+
   auto newton = [&](double delta, double ftol, int maxit) {
     RowTerms rt[1];
     rt[0].implicit = true; rt[0].has_bounds = false; rt[0].ypost = ypost; rt[0].delta = delta;
@@ -148,34 +166,38 @@ __global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args)
     double R = act ? apply_row_terms(Gy, y, rt[0]) : 0.0;
     newton_it = 0;
     const int ci = i % 3;
-    // one block reduction per Newton iteration carries everything the control flow needs:
-    // sums: ||R||^2 and the three masked ||y .* mask_c||^2 of FiniteDiff's per-color step;
-    // maxs: ||R||_inf, NaN flag, ||y - xold||_inf (x_converged), non-finite linear solve flag
-    double s4[4], m4[4];
-    auto reduce_state = [&](double dx, double bad) {
-      const double q = act ? y * y : 0.0;
-      s4[0] = (act && R == R) ? R * R : 0.0;
-      s4[1] = ci == 0 ? q : 0.0;
-      s4[2] = ci == 1 ? q : 0.0;
-      s4[3] = ci == 2 ? q : 0.0;
-      m4[0] = (act && R == R) ? fabs(R) : 0.0;
-      m4[1] = (act && (R != R || y != y)) ? 1.0 : 0.0;
-      m4[2] = dx;
-      m4[3] = bad;
-      block_reduce_mixed<4, 4>(s4, m4, red);
+    // NLsolve's loop only tests predicates of the residual (||R||_inf <= ftol, any NaN,
+    // x == xold) -- folded block-wide as bits -- plus, for the Jacobian, FiniteDiff's three
+    // masked sums of squares of the current iterate.  ||R||_2 is only needed once, at the end.
+    enum : unsigned { kNaN = 1u, kBig = 2u, kMoved = 4u, kBad = 8u };
+    auto state_bits = [&](bool moved, bool bad) -> unsigned {
+      unsigned b = 0u;
+      if (act) {
+        if (R != R || y != y) b |= kNaN;
+        if (!(fabs(R) <= ftol)) b |= kBig;
+        if (moved) b |= kMoved;
+        if (bad) b |= kBad;
+      }
+      return block_or_bits(b);
     };
-    reduce_state(0.0, 0.0);
-    bool anynan = m4[1] > 0.0;
-    bool fconv = !anynan && m4[0] <= ftol;
+    unsigned bits = state_bits(true, false);
+    bool anynan = (bits & kNaN) != 0u;
+    bool fconv = !anynan && (bits & kBig) == 0u;
     bool xconv = false;
     bool singular = false;
     // y is already published in ysh by the caller when y == ypost
     while (!anynan && !fconv && !xconv && newton_it < maxit) {
       ++newton_it;
+      double s3[3], m0[1];
+      const double q = act ? y * y : 0.0;
+      s3[0] = ci == 0 ? q : 0.0;
+      s3[1] = ci == 1 ? q : 0.0;
+      s3[2] = ci == 2 ? q : 0.0;
+      block_reduce_mixed<3, 0>(s3, m0, red);
       double eps_table[3];   // FiniteDiff: sqrt(eps)*max(1, sqrt(||x .* mask_c||_2))
-      eps_table[0] = color_epsilon_from_sumsq(s4[1]);
-      eps_table[1] = color_epsilon_from_sumsq(s4[2]);
-      eps_table[2] = color_epsilon_from_sumsq(s4[3]);
+      eps_table[0] = color_epsilon_from_sumsq(s3[0]);
+      eps_table[1] = color_epsilon_from_sumsq(s3[1]);
+      eps_table[2] = color_epsilon_from_sumsq(s3[2]);
       double ja = 0.0, jb = 1.0, jc = 0.0;
       if (act) {
         double w[1][3] = {{ysh[i], ysh[i + 1], ysh[i + 2]}};
@@ -187,25 +209,30 @@ __global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args)
                                        });
       }
       const double sol = block_pcr_solve(ja, jb, jc, act ? R : 0.0, i, S, pcr);
-      const double bad = (act && !isfinite(sol)) ? 1.0 : 0.0;
+      const bool bad = act && !isfinite(sol);
       const double xold = y;
       y = xold + (-sol);
       publish(y);
       Gy = act ? evalG() : 0.0;
       R = act ? apply_row_terms(Gy, y, rt[0]) : 0.0;
-      reduce_state(act ? fabs(y - xold) : 0.0, bad);
-      if (m4[3] > 0.0) { singular = true; break; }   // a vanishing pivot: SingularException
-      anynan = m4[1] > 0.0;
-      fconv = !anynan && m4[0] <= ftol;
-      xconv = !anynan && m4[2] <= 0.0;               // chebyshev(x, xold) <= xtol = 0
+      bits = state_bits(y != xold, bad);
+      if (bits & kBad) { singular = true; break; }   // a vanishing pivot: SingularException
+      anynan = (bits & kNaN) != 0u;
+      fconv = !anynan && (bits & kBig) == 0u;
+      xconv = !anynan && (bits & kMoved) == 0u;      // chebyshev(x, xold) <= xtol = 0
     }
     if (singular) {   // -> (y0, Inf), finiteschemesolve.jl:142-146
       y = ypost;
       Gy = Gpost;
       nl = INFINITY;
       publish(y);
+    } else if (anynan) {
+      nl = NAN;
     } else {
-      nl = anynan ? NAN : sqrt(s4[0]) / nd;
+      double s1[1], m1[1];
+      s1[0] = act ? R * R : 0.0;
+      block_reduce_mixed<1, 0>(s1, m1, red);
+      nl = sqrt(s1[0]) / nd;
     }
   };
 
