@@ -13,7 +13,7 @@ semantics).  metric = Newton solves per second, whole job.
   value     inputs already resident in HBM, device time (CUDA events on the launching stream)
   e2e       same metric through the C-ABI call with pinned HOST buffers (H2D + solve + D2H)
   roofline  fused batched kernel: algorithmic bytes / launch time vs measured HBM peak
-  cpu_baseline  the CPU oracle (port of the reference algorithm) on a bounded sample, 1 core
+  cpu_baseline  the plain-C CPU oracle (port of the reference algorithm) on a bounded sample, 1 core
 """
 import argparse
 import ctypes as C
@@ -233,6 +233,11 @@ def run_ours(args):
                      "note": "fused on-chip solve: algorithmic bytes never reach HBM; DRAM traffic is grid+guess in, solution out"},
         "pdesolves_per_sec": B * world / (ms_per_step * 1e-3),
     }
+    if world == 1 and not args.no_kernels:
+        # residual / Jacobian / SpMV / V-cycle of the generic engine on the C3 and C5 shapes
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_kernels
+        line["kernels"] = bench_kernels.measure(reps=3)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_sample, 1)
     print(json.dumps(line), flush=True)
@@ -240,63 +245,42 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def _oracle_solve_range(rng):
-    from oracle import econpdes_oracle as eo
-    from oracle import models as OM
-    first, count = rng
-    newton = 0
-    for i in range(first, first + count):
-        prm = OM.campbell_cochrane_sweep_params(i)
-        g, gu, _ = OM.campbell_cochrane_problem(prm)
-        res = eo.pdesolve(OM.campbell_cochrane(**prm), g, gu)
-        newton += res.log.n_newton
-    return newton
+def _c_oracle_time(first, count, threads):
+    """Times the plain-C oracle (oracle/oracle1d.c: the reference's serial algorithm, restated)
+    on `count` problems of the sweep; grids are built before the clock starts, like the GPU leg."""
+    from econpdes_b200 import examples as EX
+    from oracle import c_oracle
+    params, grids, guess = EX.campbell_cochrane_sweep(first, count)
+    c_oracle.solve_batch("campbell_cochrane", params[:8], grids[:8], guess[:8], threads=1)   # warm
+    t0 = time.perf_counter()
+    _, rn, no, nn = c_oracle.solve_batch("campbell_cochrane", params, grids, guess, threads=threads)
+    dt = time.perf_counter() - t0
+    return float(nn.sum()), dt, bool((rn <= math.sqrt(np.finfo(float).eps)).all())
 
 
-def _oracle_prepare_and_time(first, count, procs):
-    """Times only the solves (grids are built before the clock starts, like the GPU leg)."""
-    from oracle import econpdes_oracle as eo
-    from oracle import models as OM
-    if procs <= 1:
-        probs = []
-        for i in range(first, first + count):
-            prm = OM.campbell_cochrane_sweep_params(i)
-            g, gu, _ = OM.campbell_cochrane_problem(prm)
-            probs.append((OM.campbell_cochrane(**prm), g, gu))
-        t0 = time.perf_counter()
-        newton = sum(eo.pdesolve(p, g, gu).log.n_newton for p, g, gu in probs)
-        return newton, time.perf_counter() - t0
-    import multiprocessing as mp
-    per = max(1, count // procs)
-    ranges = [(first + k * per, per) for k in range(procs)]
-    with mp.get_context("fork").Pool(procs) as pool:
-        pool.map(_oracle_solve_range, [(0, 1)] * procs)  # warm the workers
-        t0 = time.perf_counter()
-        newton = sum(pool.map(_oracle_solve_range, ranges))
-        return newton, time.perf_counter() - t0
-
-
-def cpu_baseline(sample, procs):
-    newton, dt = _oracle_prepare_and_time(0, sample, procs)
-    return {"value": newton / dt, "unit": "Newton solves/s", "cores": procs, "kind": "port",
+def cpu_baseline(sample, threads):
+    newton, dt, ok = _c_oracle_time(0, sample, threads)
+    return {"value": newton / dt, "unit": "Newton solves/s", "cores": threads, "kind": "port",
             "sample": f"{sample} of the {PROBLEMS_PER_GPU} sweep problems (998 points each), full pdesolve by the "
-                      f"numpy/scipy oracle (oracle/econpdes_oracle.py), {dt:.1f} s",
-            "pdesolves_per_sec": sample / dt}
+                      f"plain-C oracle (oracle/oracle1d.c), {dt:.1f} s, all converged: {ok}",
+            "pdesolves_per_sec": sample / dt, "ms_per_pdesolve": dt / sample * 1e3,
+            "reference_published_ms_per_pdesolve": 2.575}
 
 
 def run_reference(args):
-    """The reference algorithm on the box's host cores (CPU oracle port: Julia is not
-    installable here), all cores, bounded sample per step."""
+    """The reference algorithm on the box's host cores.  Julia is not installable here (DESIGN.md
+    section 8), so this is the CPU oracle port (oracle/oracle1d.c) with one thread per core on a
+    bounded sample of the same sweep."""
     rank, world, _ = _dist()
     if rank != 0:
         return
-    procs = os.cpu_count() or 1
-    sample = max(procs, args.ref_sample // procs * procs)
+    threads = os.cpu_count() or 1
+    sample = max(threads, args.ref_sample)
     for _ in range(min(args.warmup, 1)):
-        _oracle_prepare_and_time(0, procs, procs)
-    tot_newton, tot_t = 0, 0.0
+        _c_oracle_time(0, threads * 4, threads)
+    tot_newton, tot_t = 0.0, 0.0
     for _ in range(args.steps):
-        nwt, dt = _oracle_prepare_and_time(0, sample, procs)
+        nwt, dt, _ = _c_oracle_time(0, sample, threads)
         tot_newton += nwt
         tot_t += dt
     value = tot_newton / tot_t
@@ -306,8 +290,8 @@ def run_reference(args):
             "config": {"workload": "C4 batched calibration sweep: independent Campbell-Cochrane habit 1-D problems, "
                                    "full pdesolve per problem", "points_per_problem": POINTS,
                        "sample_problems_per_step": sample},
-            "cpu_baseline": {"value": value, "unit": "Newton solves/s", "cores": procs, "kind": "port",
-                             "sample": f"{sample} sweep problems per step over {procs} processes"},
+            "cpu_baseline": {"value": value, "unit": "Newton solves/s", "cores": threads, "kind": "port",
+                             "sample": f"{sample} sweep problems per step, {threads} threads, plain-C oracle"},
             "e2e": {"value": value, "unit": "Newton solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -320,9 +304,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--problems", type=int, default=PROBLEMS_PER_GPU, help="problems per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=256)
-    ap.add_argument("--ref-sample", type=int, default=512)
+    ap.add_argument("--cpu-sample", type=int, default=4096)
+    ap.add_argument("--ref-sample", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the grid-kernel roofline leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

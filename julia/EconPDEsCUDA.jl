@@ -1,0 +1,99 @@
+# EconPDEsCUDA.jl -- the binding a maintainer of EconPDEs.jl would add to route registered models
+# to libeconpdes_cuda.so.  NOT exercised in this repository's CI: the build image has no Julia
+# (see DESIGN.md section 2); the same C ABI is driven from Python ctypes in econpdes.jl_b200/.
+#
+# Usage:   using EconPDEs, EconPDEsCUDA
+#          result = pdesolve(CUDAModel(BansalYaronModel()), stategrid, guess)   # -> EconPDEResult
+module EconPDEsCUDA
+
+using EconPDEs
+using EconPDEs: EconPDEResult, StateGrid, _asnamedtuple, _check_generated_names, _fill_is_algebraic,
+                _bc_array, _bound_array, _delta_array
+
+const lib = get(ENV, "ECONPDES_CUDA_LIB", "libeconpdes_cuda")
+
+# mirrors `econpdes_problem`, `econpdes_options`, `econpdes_log_row`, `econpdes_result`
+# (include/econpdes_cuda.h); field order and types must match exactly.
+struct CProblem
+    model_id::Int32; ndims::Int32; nfuncs::Int32; nparams::Int32
+    size::NTuple{3, Int64}
+    grid::NTuple{3, Ptr{Float64}}
+    params::Ptr{Float64}; guess::Ptr{Float64}; bc::Ptr{Float64}; is_algebraic::Ptr{UInt8}
+    lower_bound::Ptr{Float64}; upper_bound::Ptr{Float64}; delta_vec::Ptr{Float64}
+end
+mutable struct COptions
+    abstol::Float64; inner_abstol::Float64; delta::Float64; scale::Float64; min_delta::Float64
+    max_delta::Float64; max_residual_growth::Float64
+    maxiters::Int32; inner_maxiters::Int32; eps_policy::Int32; linear_solver::Int32
+    lin_rtol::Float64; lin_maxiters::Int32; lin_restart::Int32
+    COptions() = new()
+end
+struct CLogRow
+    iter::Int32; status::Int32; newton_iters::Int32; linear_iters::Int32; delta::Float64; residual::Float64
+end
+mutable struct CResult
+    solution::Ptr{Float64}; saved::Ptr{Float64}; log::Ptr{CLogRow}
+    log_capacity::Int32; log_len::Int32
+    residual_norm::Float64
+    converged::Int32; exit_reason::Int32; n_outer::Int32; n_newton::Int32
+    n_linear_iters::Int64; kernel_launches::Int64; device_ms::Float64
+    CResult() = new()
+end
+
+"Wraps one of the example model structs; `name` selects the registered device functor."
+struct CUDAModel{M}
+    model::M
+    name::String
+    params::Vector{Float64}
+    saved::Tuple{Vararg{Symbol}}
+end
+# e.g. CUDAModel(m::BansalYaronModel) = CUDAModel(m, "bansal_yaron",
+#          Float64[m.μbar, m.vbar, m.κμ, m.νμ, m.κv, m.νv, m.ρ, m.γ, m.ψ], ())
+
+last_error() = unsafe_string(ccall((:econpdes_last_error, lib), Cstring, ()))
+
+function EconPDEs.pdesolve(m::CUDAModel, grid, guess; is_algebraic = nothing, bc = nothing,
+                           lower_bound = nothing, upper_bound = nothing, abstol = sqrt(eps()),
+                           verbose = true, maxiters = 100, Δ = 1.0, kwargs...)
+    # identical normalisation to src/pdesolve.jl:97-123
+    grid = _asnamedtuple(grid); guess = _asnamedtuple(guess)
+    _check_generated_names(collect(keys(grid)), collect(keys(guess)))
+    stategrid = StateGrid(grid); S = size(stategrid); F = length(guess)
+    guess_array = cat(values(guess)...; dims = length(S) + 1)
+    alg = UInt8.(cat(values(_fill_is_algebraic(is_algebraic, guess, S))...; dims = length(S) + 1))
+    bcs = _bc_array(bc, guess, grid)
+    lb = _bound_array(lower_bound, guess, -Inf, :lower_bound)
+    ub = _bound_array(upper_bound, guess, Inf, :upper_bound)
+    Δvec = Δ isa Union{NamedTuple, AbstractDict} ? vec(_delta_array(Δ, guess, S)) : nothing
+    grids = [collect(Float64, g) for g in values(grid)]
+    opts = COptions(); ccall((:econpdes_default_options, lib), Cvoid, (Ref{COptions},), opts)
+    opts.abstol = abstol; opts.maxiters = maxiters
+    Δvec === nothing && (opts.delta = Δ)
+    for (k, v) in kwargs   # scale, minΔ, maxΔ, max_residual_growth, inner_maxiters, inner_abstol
+        k === :minΔ ? (opts.min_delta = v) : k === :maxΔ ? (opts.max_delta = v) : setfield!(opts, k, convert(fieldtype(COptions, k), v))
+    end
+    mid = ccall((:econpdes_model_id, lib), Cint, (Cstring,), m.name)
+    mid < 0 && throw(ArgumentError(last_error()))
+    sol = similar(guess_array); saved = Array{Float64}(undef, S..., length(m.saved)); log = Vector{CLogRow}(undef, maxiters)
+    res = CResult(); res.solution = pointer(sol); res.saved = isempty(m.saved) ? C_NULL : pointer(saved)
+    res.log = pointer(log); res.log_capacity = maxiters
+    GC.@preserve grids guess_array alg bcs lb ub Δvec sol saved log m begin
+        gp = ntuple(d -> d <= length(S) ? pointer(grids[d]) : Ptr{Float64}(C_NULL), 3)
+        prob = CProblem(mid, length(S), F, length(m.params), ntuple(d -> d <= length(S) ? S[d] : 1, 3), gp,
+                        pointer(m.params), pointer(guess_array), pointer(bcs), pointer(alg), pointer(lb), pointer(ub),
+                        Δvec === nothing ? C_NULL : pointer(Δvec))
+        rc = ccall((:econpdes_solve_stationary, lib), Cint, (Ref{CProblem}, Ref{COptions}, Ref{CResult}), prob, opts, res)
+    end
+    rc < 0 && throw(ArgumentError(last_error()))    # e.g. "G! returns NaN with the initial value"
+    ynames = tuple(keys(guess)...)
+    solution = NamedTuple{ynames}(ntuple(k -> collect(selectdim(sol, ndims(sol), k)), F))
+    savednt = isempty(m.saved) ? NamedTuple() :
+        merge(solution, NamedTuple{m.saved}(ntuple(k -> collect(selectdim(saved, ndims(saved), k)), length(m.saved))))
+    verbose && for r in log[1:res.log_len]   # same table as src/finiteschemesolve.jl:421,435,445
+        r.status == 0 ? Printf.@printf("%4d %8.2e %8.2e\n", r.iter, r.delta, r.residual) :
+                        Printf.@printf("%4d %8.2e        ✗\n", r.iter, r.delta)
+    end
+    return EconPDEResult(solution, res.residual_norm, savednt, abstol)
+end
+
+end # module
