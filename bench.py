@@ -113,8 +113,11 @@ def run_ours(args):
         torch.cuda.set_device(local)
     lib = L.load()
     L.check(lib.econpdes_set_device(local))
+    from econpdes_b200.sharding import Reducer, weak_slice
     B, S = args.problems, POINTS
-    params, grids, guess = EX.campbell_cochrane_sweep(rank * B, B)
+    first, _ = weak_slice(B, rank)
+    params, grids, guess = EX.campbell_cochrane_sweep(first, B)
+    red = Reducer(dist, "cuda")
     opts = _options(math.sqrt(np.finfo(float).eps), 100, {})
     mid = L.check(lib.econpdes_model_id(CampbellCochraneModel.name.encode()))
 
@@ -124,19 +127,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def allmax(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    allmax, allsum = red.max, red.sum
 
     # ---- device-resident leg (value) ----
     h = C.c_void_p()
@@ -300,7 +291,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--problems", type=int, default=PROBLEMS_PER_GPU, help="problems per GPU")
