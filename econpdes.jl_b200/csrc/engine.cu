@@ -78,7 +78,8 @@ struct ModelOpsT final : ModelOps {
                 double* r0) const override {
     const int per_col = eps_policy == ECONPDES_EPS_PER_COLUMN;
     if (!per_col) {
-      EP_LAUNCH(k_color_sumsq<M::N>, blocks_for(c.l), kBlock, 0, c.stream, c.grid_view<M::N>(), M::F, y, c.cw());
+      const int cblocks = blocks_for(c.l) < 148 * 4 ? blocks_for(c.l) : 148 * 4;   // persistent: 4 blocks per SM
+      EP_LAUNCH(k_color_sumsq<M::N>, cblocks, kBlock, 0, c.stream, c.grid_view<M::N>(), M::F, y, c.cw());
     }
     if constexpr (M::USES_CROSS && M::N > 1) {
       EP_LAUNCH((k_jacobian<M, true>), blocks_for(c.l), kBlock, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p,

@@ -115,31 +115,38 @@ template <int N>
 __global__ void __launch_bounds__(kBlock) k_color_sumsq(GridView<N> gv, int F, const double* __restrict__ y,
                                                         ColorWork cw) {
   __shared__ double bins[kBlock / 32][kMaxColors];
+  __shared__ double fin[kBlock / 32];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int ncg = ncolors_grid<N>(gv);
   const int nc = ncg * F;
   for (int c = lane; c < nc; c += 32) bins[warp][c] = 0.0;
   __syncwarp();
-  const long long pt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const bool active = pt < gv.l;
-  int color0 = -1;
-  if (active) {
-    long long idx[N];
-    unravel<N>(pt, gv, idx);
-    color0 = point_color0<N>(idx, gv);
-  }
-  for (int f = 0; f < F; ++f) {
-    const double v = active ? y[f * gv.l + pt] : 0.0;
-    const double q = v * v;
-    unsigned remaining = __ballot_sync(0xffffffffu, active);
-    while (remaining) {
-      const int leader = __ffs(remaining) - 1;
-      const int c = __shfl_sync(0xffffffffu, color0, leader);
-      const bool mine = active && color0 == c;
-      const double sum = warp_sum(mine ? q : 0.0);
-      if (lane == leader) bins[warp][c + f * ncg] += sum;
-      remaining &= ~__ballot_sync(0xffffffffu, mine);
+  // persistent grid: a bounded number of blocks stride over the points, so the final fold
+  // reads a few hundred partials per color instead of one per 256 points
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long npass = (gv.l + stride - 1) / stride;
+  for (long long pass = 0; pass < npass; ++pass) {
+    const long long pt = pass * stride + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool active = pt < gv.l;
+    int color0 = -1;
+    if (active) {
+      long long idx[N];
+      unravel<N>(pt, gv, idx);
+      color0 = point_color0<N>(idx, gv);
+    }
+    for (int f = 0; f < F; ++f) {
+      const double v = active ? y[f * gv.l + pt] : 0.0;
+      const double q = v * v;
+      unsigned remaining = __ballot_sync(0xffffffffu, active);
+      while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const int c = __shfl_sync(0xffffffffu, color0, leader);
+        const bool mine = active && color0 == c;
+        const double sum = warp_sum(mine ? q : 0.0);
+        if (lane == leader) bins[warp][c + f * ncg] += sum;
+        remaining &= ~__ballot_sync(0xffffffffu, mine);
+      }
     }
   }
   __syncthreads();
@@ -158,11 +165,21 @@ __global__ void __launch_bounds__(kBlock) k_color_sumsq(GridView<N> gv, int F, c
   __syncthreads();
   if (is_last) {
     __threadfence();
-    for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+    // fixed-order fold: every color is summed by the whole block (strided partials, then
+    // warp butterflies, then warps in order), so the result does not depend on scheduling
+    for (int c = 0; c < nc; ++c) {
       double t = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) t += cw.part[static_cast<long long>(b) * nc + c];
-      cw.sumsq[c] = t;
-      cw.eps[c] = color_epsilon_from_sumsq(t);
+      for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) t += cw.part[static_cast<long long>(b) * nc + c];
+      t = warp_sum(t);
+      if (lane == 0) fin[warp] = t;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < nwarps; ++w) tot += fin[w];
+        cw.sumsq[c] = tot;
+        cw.eps[c] = color_epsilon_from_sumsq(tot);
+      }
+      __syncthreads();
     }
     if (threadIdx.x == 0) *cw.counter = 0u;
   }

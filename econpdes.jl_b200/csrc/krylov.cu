@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(kBlock) k_spmv(LevelGeom<N> g, const double* _
       if ((o < 0 && idx[d] == 0) || (o > 0 && idx[d] == g.S[d] - 1)) ok = false;
       q += o * g.stride[d];
     }
-    if (ok) acc += A[k * g.l + pt] * x[q];
+    // entries that point outside the grid hold 0: load unconditionally (clamped address) so all
+    // loads of a point are in flight together instead of one round trip per guarded entry
+    acc += A[k * g.l + pt] * x[ok ? q : pt];
   }
   y[pt] = mode ? b[pt] - acc : acc;
 }
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(1024) k_line_zebra(LevelGeom<N> g, const doubl
           if ((o < 0 && ie == 0) || (o > 0 && ie == g.S[e] - 1)) ok = false;
           q += o * g.stride[e];
         }
-        if (!inl && ok) rhs -= A[k * g.l + pt] * x[q];
+        if (!inl) rhs -= A[k * g.l + pt] * x[ok ? q : pt];   // zero coefficient outside the grid
       }
       ra[m] = i > 0 ? A[km * g.l + pt] : 0.0;
       rb[m] = A[kc * g.l + pt];
@@ -496,6 +498,40 @@ __global__ void __launch_bounds__(256) k_dense_lu(int n, double* __restrict__ M,
   }
 }
 
+// Column j of the inverse from the LU factors (one thread per column, run once per set-up);
+// the V-cycle then applies the coarsest solve as one dense mat-vec instead of 2n dependent steps.
+__global__ void __launch_bounds__(64) k_dense_invert(int n, const double* __restrict__ M, const int* __restrict__ piv,
+                                                     double* __restrict__ Minv, double* __restrict__ work) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double* y = work + static_cast<long long>(j) * n;
+  for (int i = 0; i < n; ++i) y[i] = i == j ? 1.0 : 0.0;
+  for (int c = 0; c < n; ++c) {
+    const int p = piv[c];
+    if (p != c) { const double t = y[c]; y[c] = y[p]; y[p] = t; }
+    const double yc = y[c];
+    if (yc != 0.0)
+      for (int r = c + 1; r < n; ++r) y[r] -= M[c * n + r] * yc;
+  }
+  for (int c = n - 1; c >= 0; --c) {
+    y[c] /= M[c * n + c];
+    const double yc = y[c];
+    for (int r = 0; r < c; ++r) y[r] -= M[c * n + r] * yc;
+  }
+  for (int i = 0; i < n; ++i) Minv[static_cast<long long>(j) * n + i] = y[i];   // column-major
+}
+
+// x = Minv b, one warp per row
+__global__ void __launch_bounds__(256) k_dense_apply(int n, const double* __restrict__ Minv,
+                                                     const double* __restrict__ b, double* __restrict__ x) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  double t = 0.0;
+  for (int c = threadIdx.x & 31; c < n; c += 32) t += Minv[static_cast<long long>(c) * n + r] * b[c];
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) x[r] = t;
+}
+
 __global__ void __launch_bounds__(256) k_dense_solve(int n, const double* __restrict__ M, const int* __restrict__ piv,
                                                      const double* __restrict__ b, double* __restrict__ x) {
   extern __shared__ double y[];
@@ -543,11 +579,13 @@ __global__ void __launch_bounds__(kBlock) k_multi_dot(long long n, int j, const 
   }
 }
 __global__ void k_finish_dots(int nq, int nblocks, const double* __restrict__ part, double* __restrict__ out) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per dot product; fixed summation order (strided partials, then butterfly)
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= nq) return;
   double t = 0.0;
-  for (int b = 0; b < nblocks; ++b) t += part[static_cast<long long>(q) * nblocks + b];
-  out[q] = t;
+  for (int b = threadIdx.x & 31; b < nblocks; b += 32) t += part[static_cast<long long>(q) * nblocks + b];
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) out[q] = t;
 }
 // w -= sum_q h[q] V_q
 __global__ void __launch_bounds__(kBlock) k_multi_axpy(long long n, int j, const double* __restrict__ V,
@@ -634,7 +672,7 @@ class KrylovSolver final : public LinearSolver {
  private:
   Ctx& c_;
   std::vector<std::unique_ptr<Level<N>>> lev_;
-  DevBuf<double> dense_, sym_, V_, Z_, w_, dots_, part_, hdev_, rap_tmp_[2];
+  DevBuf<double> dense_, sym_, V_, Z_, w_, dots_, part_, hdev_, rap_tmp_[2], dense_inv_, dense_work_;
   DevBuf<int> piv_;
   DevBuf<Transfer> transfers_dev_;
   cudaGraphExec_t graph_exec_ = nullptr;
@@ -751,6 +789,9 @@ class KrylovSolver final : public LinearSolver {
     if (Lc.box) EP_LAUNCH((k_dense_build<N, true>), blocks_for(Lc.l), kBlock, 0, s, make_geom<N>(Lc.S), Lc.A, dense_.p);
     else EP_LAUNCH((k_dense_build<N, false>), blocks_for(Lc.l), kBlock, 0, s, make_geom<N>(Lc.S), Lc.A, dense_.p);
     EP_LAUNCH(k_dense_lu, 1, 256, 0, s, dense_n_, dense_.p, piv_.p);
+    dense_inv_.alloc(static_cast<size_t>(dense_n_) * dense_n_);
+    dense_work_.alloc(static_cast<size_t>(dense_n_) * dense_n_);
+    EP_LAUNCH(k_dense_invert, (dense_n_ + 63) / 64, 64, 0, s, dense_n_, dense_.p, piv_.p, dense_inv_.p, dense_work_.p);
   }
   int nlev_ = 0;
 
@@ -843,7 +884,7 @@ class KrylovSolver final : public LinearSolver {
     cudaStream_t s = c_.stream;
     Level<N>& L = *lev_[li];
     if (li == nlev_ - 1) {
-      EP_LAUNCH(k_dense_solve, 1, 256, dense_n_ * sizeof(double), s, dense_n_, dense_.p, piv_.p, b, x);
+      EP_LAUNCH(k_dense_apply, (dense_n_ + 7) / 8, 256, 0, s, dense_n_, dense_inv_.p, b, x);
       return;
     }
     EP_CUDA(cudaMemsetAsync(x, 0, L.l * sizeof(double), s));
@@ -903,7 +944,7 @@ class KrylovSolver final : public LinearSolver {
     part_.alloc(static_cast<size_t>(nb) * (restart_alloc_ + 2));
     dots_.alloc(static_cast<size_t>(restart_alloc_ + 2));
     EP_LAUNCH(k_multi_dot, dim3(nb, j + 1), kBlock, 0, s, n, j, V, w, part_.p);
-    EP_LAUNCH(k_finish_dots, 1, 64, 0, s, j + 1, nb, part_.p, dots_.p);
+    EP_LAUNCH(k_finish_dots, (j + 1 + 7) / 8, 256, 0, s, j + 1, nb, part_.p, dots_.p);
     EP_CUDA(cudaMemcpyAsync(host_out, dots_.p, (j + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
     EP_CUDA(cudaStreamSynchronize(s));
   }
