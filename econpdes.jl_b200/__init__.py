@@ -11,3 +11,4 @@ from . import models  # noqa: F401
 from ._lib import EconPDEsCudaError, LIB_PATH  # noqa: F401
 from .pdesolve import (BatchResult, EconPDEResult, Handle, pdesolve, pdesolve_batched, stencil_colors,  # noqa: F401
                        stencil_pattern)
+from .slab import SlabGroup, pdesolve_slab, slab_range  # noqa: F401

@@ -25,6 +25,7 @@ UNITS = {
     "engine.cu": ["-fmad=false"],
     "api.cu": ["-fmad=false"],
     "krylov.cu": [],
+    "dist.cu": [],
     "pattern.cpp": [],
     "errors.cpp": [],
 }
@@ -56,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed")
     if procs or not os.path.exists(OUT):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-lcudart"]
+        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-lcudart", "-ldl"]
         subprocess.check_call(cmd)
     return OUT
 

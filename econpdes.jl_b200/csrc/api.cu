@@ -17,6 +17,9 @@ int guarded(Fn&& fn) {
   } catch (const std::invalid_argument& e) {
     set_error(e.what());
     return ECONPDES_E_INVALID;
+  } catch (const NcclError& e) {
+    set_error(e.what());
+    return ECONPDES_E_NCCL;
   } catch (const CudaError& e) {
     set_error(e.what());
     const std::string m = e.what();
@@ -33,6 +36,10 @@ struct econpdes_handle {
   std::unique_ptr<Solver> solver;
   DevBuf<double> a, b, c;
   bool have_jacobian = false;
+};
+
+struct econpdes_dist {
+  std::unique_ptr<Dist> dist;
 };
 
 struct econpdes_batch {
@@ -280,6 +287,53 @@ int econpdes_solve_stationary(const econpdes_problem* problem, const econpdes_op
   return guarded([&] {
     if (!problem || !options || !result) throw std::invalid_argument("null argument");
     Solver solver(make_ctx(problem));
+    return solver.solve(*options, result);
+  });
+}
+
+// ---- slab-decomposed solve ----
+int econpdes_dist_unique_id(uint8_t* id) {
+  return guarded([&] {
+    if (!id) throw std::invalid_argument("null id");
+    Dist::unique_id(id);
+    return ECONPDES_OK;
+  });
+}
+
+int econpdes_dist_create(int rank, int world, const uint8_t* id, econpdes_dist** out) {
+  return guarded([&] {
+    if (!id || !out) throw std::invalid_argument("null argument");
+    ensure_device();
+    auto d = std::make_unique<econpdes_dist>();
+    d->dist = std::make_unique<Dist>(rank, world, id);
+    *out = d.release();
+    return ECONPDES_OK;
+  });
+}
+
+void econpdes_dist_destroy(econpdes_dist* d) { delete d; }
+
+int64_t econpdes_dist_collectives(const econpdes_dist* d) { return d && d->dist ? d->dist->collectives() : 0; }
+
+int econpdes_slab_range(int64_t size_last, int rank, int world, int64_t* first, int64_t* count) {
+  return guarded([&] {
+    if (!first || !count || world < 1 || rank < 0 || rank >= world) throw std::invalid_argument("bad rank/world");
+    const int64_t units = size_last / 2;   // pairs of planes
+    if (units < world) throw std::invalid_argument("every rank needs at least 2 planes of the slowest dimension");
+    const int64_t base = units / world, rem = units % world;
+    const int64_t ufirst = rank * base + (rank < rem ? rank : rem);
+    const int64_t ucount = base + (rank < rem ? 1 : 0);
+    *first = 2 * ufirst;
+    *count = 2 * ucount + ((rank == world - 1) ? size_last % 2 : 0);
+    return ECONPDES_OK;
+  });
+}
+
+int econpdes_solve_stationary_slab(econpdes_dist* d, const econpdes_problem* problem, int64_t slab_first,
+                                   int64_t slab_count, const econpdes_options* options, econpdes_result* result) {
+  return guarded([&] {
+    if (!d || !d->dist || !problem || !options || !result) throw std::invalid_argument("null argument");
+    Solver solver(make_ctx(problem, d->dist.get(), slab_first, slab_count));
     return solver.solve(*options, result);
   });
 }

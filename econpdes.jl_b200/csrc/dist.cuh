@@ -1,0 +1,57 @@
+// Multi-GPU plumbing of the slab-decomposed single-grid solve (config C5):
+// one process per GPU, the slowest grid dimension cut into contiguous slabs.  What crosses
+// ranks on the hot path is
+//   * one ghost plane per side of every field a stencil reads  (ncclSend/ncclRecv pairs over
+//     NVLink, grouped so both directions are in flight together),
+//   * a handful of doubles per reduction (norms, Krylov dot products, the per-color sums of
+//     squares behind FiniteDiff's step): ncclAllGather of the per-rank partials, folded in
+//     rank order so every rank computes bit-identical scalars and takes identical branches.
+// NCCL is bound at run time (dlopen of libnccl.so.2 -- the copy torch already loaded when the
+// host is the Python package) so the single-GPU library has no link-time NCCL dependency.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+
+namespace econpdes {
+
+constexpr int kUniqueIdBytes = 128;  // NCCL_UNIQUE_ID_BYTES
+
+struct NcclError : std::runtime_error {
+  explicit NcclError(const std::string& m) : std::runtime_error(m) {}
+};
+
+class Dist {
+ public:
+  static void unique_id(uint8_t* id128);  // rank 0 creates, the host broadcasts (torch.distributed, MPI, a pipe)
+  Dist(int rank, int world, const uint8_t* id128);  // collective: ncclCommInitRank on the current device
+  ~Dist();
+  Dist(const Dist&) = delete;
+  Dist& operator=(const Dist&) = delete;
+
+  int rank() const { return rank_; }
+  int world() const { return world_; }
+  bool has_lo() const { return rank_ > 0; }
+  bool has_hi() const { return rank_ + 1 < world_; }
+
+  // v points at the first OWNED plane of a field stored with one ghost plane on either side:
+  // [ghost | plane_0 .. plane_{nplanes-1} | ghost], each `plane` doubles.  Fills both ghosts
+  // from the neighbours' edge planes (nothing is written at the ends of the global grid).
+  void exchange_halo(double* v, long long plane, long long nplanes, cudaStream_t s);
+  // one-sided variants used by the multigrid transfers
+  void send_lo_recv_hi(const double* send_first, double* recv_hi_ghost, long long count, cudaStream_t s);
+  void send_hi_recv_lo(const double* send_last, double* recv_lo_ghost, long long count, cudaStream_t s);
+  // recv[r*count .. (r+1)*count) = rank r's send[0..count)   (device pointers)
+  void all_gather(const double* send, double* recv, long long count, cudaStream_t s);
+
+  int64_t collectives() const { return ncoll_; }
+
+ private:
+  int rank_, world_;
+  void* comm_ = nullptr;
+  int64_t ncoll_ = 0;
+};
+
+}  // namespace econpdes

@@ -28,7 +28,22 @@ void ensure_device() {
   }
 }
 
+const double* Ctx::gather_to_host(const double* partial_dev, int count) {
+  if (count > kGatherMax) throw std::invalid_argument("gather_to_host: too many values");
+  const int world = dist != nullptr ? dist->world() : 1;
+  const double* src = partial_dev;
+  if (dist != nullptr) {
+    dist->all_gather(partial_dev, gather.p, count, stream);
+    src = gather.p;
+  }
+  EP_CUDA(cudaMemcpyAsync(h_gather, src, static_cast<size_t>(world) * count * sizeof(double), cudaMemcpyDeviceToHost,
+                          stream));
+  EP_CUDA(cudaStreamSynchronize(stream));
+  return h_gather;
+}
+
 Ctx::~Ctx() {
+  if (h_gather) cudaFreeHost(h_gather);
   if (h_norm) cudaFreeHost(h_norm);
   if (stream) cudaStreamDestroy(stream);
 }
@@ -62,6 +77,18 @@ struct BatchedLaunch<M, true> {
   }
 };
 
+// Slab path: every rank holds every rank's per-color sums of squares (rank-major); fold them in
+// rank order and turn the totals into FiniteDiff's steps.
+static __global__ void k_color_eps_fold(int world, int nc, const double* __restrict__ all, double* __restrict__ sumsq,
+                                        double* __restrict__ eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  double t = 0.0;
+  for (int r = 0; r < world; ++r) t += all[r * nc + c];
+  sumsq[c] = t;
+  eps[c] = color_epsilon_from_sumsq(t);
+}
+
 template <class M>
 struct ModelOpsT final : ModelOps {
   const char* name() const override { return M::name(); }
@@ -80,6 +107,11 @@ struct ModelOpsT final : ModelOps {
     if (!per_col) {
       const int cblocks = blocks_for(c.l) < 148 * 4 ? blocks_for(c.l) : 148 * 4;   // persistent: 4 blocks per SM
       EP_LAUNCH(k_color_sumsq<M::N>, cblocks, kBlock, 0, c.stream, c.grid_view<M::N>(), M::F, y, c.cw());
+      if (c.dist != nullptr) {   // one all-gather of the C masked norms per Jacobian
+        c.dist->all_gather(c.color_sumsq.p, c.gather.p, c.ncolors, c.stream);
+        EP_LAUNCH(k_color_eps_fold, 1, 128, 0, c.stream, c.dist->world(), c.ncolors, c.gather.p, c.color_sumsq.p,
+                  c.color_eps.p);
+      }
     }
     if constexpr (M::USES_CROSS && M::N > 1) {
       EP_LAUNCH((k_jacobian<M, true>), blocks_for(c.l), kBlock, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p,
@@ -128,7 +160,7 @@ int model_count() { return TheRegistry::count; }
 // ---------------------------------------------------------------------------------------
 // problem upload
 // ---------------------------------------------------------------------------------------
-std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p) {
+std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p, Dist* dist, long long slab_first, long long slab_count) {
   if (p == nullptr) throw std::invalid_argument("null problem");
   const ModelOps* ops = model_ops(p->model_id);
   if (ops == nullptr) throw std::invalid_argument("unknown model id " + std::to_string(p->model_id));
@@ -156,6 +188,21 @@ std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p) {
     c->S[d] = p->size[d];
     c->l *= p->size[d];
     c->ncolors *= p->size[d] < 3 ? static_cast<int>(p->size[d]) : 3;
+  }
+  c->n_glob = c->l * c->F;
+  c->slab_count = c->S[c->N - 1];
+  if (dist != nullptr) {
+    if (c->N < 2 || c->F != 1)
+      throw std::invalid_argument("the slab-decomposed solve takes 2-D/3-D grids with one unknown");
+    if (p->delta_vec != nullptr) throw std::invalid_argument("the slab-decomposed solve takes a scalar Δ");
+    if (slab_first < 0 || slab_count < 2 || slab_first + slab_count > c->S[c->N - 1])
+      throw std::invalid_argument("slab range out of bounds (each rank needs >= 2 planes)");
+    if (c->ncolors > kGatherMax) throw std::invalid_argument("too many colors for the slab path");
+    c->dist = dist;
+    c->slab_first = slab_first;
+    c->slab_count = slab_count;
+    c->halo = c->l / c->S[c->N - 1];
+    c->l = c->halo * slab_count;
   }
   c->n = c->l * c->F;
   for (int i = 0; i < c->nparams; ++i) c->prm.v[i] = p->params[i];
@@ -220,6 +267,9 @@ std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p) {
   c->counters.alloc(4);
   c->counters.zero(s);
   EP_CUDA(cudaMallocHost(&c->h_norm, 4 * sizeof(double)));
+  const size_t world = dist != nullptr ? static_cast<size_t>(dist->world()) : 1;
+  c->gather.alloc(world * kGatherMax);
+  EP_CUDA(cudaMallocHost(&c->h_gather, world * kGatherMax * sizeof(double)));
   EP_CUDA(cudaStreamSynchronize(s));
   return c;
 }
@@ -315,6 +365,7 @@ __global__ void __launch_bounds__(kBlock) k_count_mask(long long n, const double
 
 Solver::Solver(std::unique_ptr<Ctx> ctx) : c_(std::move(ctx)), ops_(model_ops(c_->model_id)) {
   const size_t n = static_cast<size_t>(c_->n);
+  ypost_.pad = y_.pad = ynew_.pad = static_cast<size_t>(c_->halo);   // fields a stencil reads carry ghost planes
   ypost_.alloc(n); y_.alloc(n); ynew_.alloc(n); R_.alloc(n); s_.alloc(n); G_.alloc(n);
   planes_.alloc(static_cast<size_t>(c_->nk) * c_->F * c_->F * c_->l);
   lin_ = c_->N == 1 ? make_tridiag_solver(*c_) : make_krylov_solver(*c_);
@@ -333,22 +384,32 @@ RowSpec Solver::row_spec(const double* ypost, double delta) const {
 }
 
 Norms Solver::read_norms() {
-  EP_CUDA(cudaMemcpyAsync(c_->h_norm, c_->norm_out.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, c_->stream));
-  EP_CUDA(cudaStreamSynchronize(c_->stream));
-  return Norms{c_->h_norm[0], c_->h_norm[1], c_->h_norm[2] != 0.0};
+  // (sum of squares, max, NaN flag) of every rank, folded in rank order (one rank: itself)
+  const double* g = c_->gather_to_host(c_->norm_out.p, 3);
+  const int world = c_->dist != nullptr ? c_->dist->world() : 1;
+  Norms out{0.0, 0.0, false};
+  for (int r = 0; r < world; ++r) {
+    out.sumsq += g[3 * r];
+    out.maxabs = g[3 * r + 1] > out.maxabs ? g[3 * r + 1] : out.maxabs;
+    out.any_nan = out.any_nan || g[3 * r + 2] != 0.0;
+  }
+  return out;
 }
 
 Norms Solver::eval_G(const double* y, double* out) {
+  c_->exchange_halo(y);
   ops_->residual(*c_, y, row_spec(nullptr, INFINITY), out, true);
   return read_norms();
 }
 
 Norms Solver::eval_R(const double* y, const double* ypost, double delta, double* out) {
+  c_->exchange_halo(y);
   ops_->residual(*c_, y, row_spec(ypost, delta), out, true);
   return read_norms();
 }
 
 void Solver::jacobian(const double* y, const double* ypost, double delta, int eps_policy) {
+  c_->exchange_halo(y);
   ops_->jacobian(*c_, y, row_spec(ypost, delta), eps_policy, planes_.p, nullptr);
 }
 
@@ -394,7 +455,7 @@ NewtonOutcome Solver::newton(const double* ypost, double delta, double ftol, int
     fconv = !nr.any_nan && nr.maxabs <= ftol;
     stopped = nx.any_nan || nr.any_nan;
   }
-  out.nl = nr.norm2_over_n(n);
+  out.nl = nr.norm2_over_n(c_->n_glob);
   if (x != y_out) EP_CUDA(cudaMemcpyAsync(y_out, x, n * sizeof(double), cudaMemcpyDeviceToDevice, c_->stream));
   return out;
 }
@@ -417,10 +478,12 @@ int Solver::solve(const econpdes_options& opt, econpdes_result* res) {
   if (!c.has_delta_vec && (std::isnan(opt.delta) || opt.delta == 0.0))
     throw std::invalid_argument("`Δ` entries must be nonzero and not NaN (use `Inf` for no damping, a negative entry for forward relaxation)");
 
+  const long long ng = c.n_glob;   // norms are over the whole grid; copies move this device's part
   DevBuf<double> ytrial;
+  ytrial.pad = static_cast<size_t>(c.halo);
   ytrial.alloc(static_cast<size_t>(n));
   EP_CUDA(cudaMemcpyAsync(ypost_.p, c.guess.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
-  double r = eval_G(ypost_.p, G_.p).norm2_over_n(n);
+  double r = eval_G(ypost_.p, G_.p).norm2_over_n(ng);
   int rc = ECONPDES_OK;
   auto push_log = [&](int iter, int status, int nit, long long lit, double delta, double resid) {
     if (res->log != nullptr && res->log_len < res->log_capacity) {
@@ -459,8 +522,8 @@ int Solver::solve(const econpdes_options& opt, econpdes_result* res) {
       res->n_newton += o.iters;
       res->n_linear_iters += o.lin_iters;
       const double old_r = r;
-      Norms ng = eval_G(ytrial.p, G_.p);
-      double rn = c.has_bounds ? masked_norm(G_.p, ytrial.p) : ng.norm2_over_n(n);
+      Norms ngn = eval_G(ytrial.p, G_.p);
+      double rn = c.has_bounds ? masked_norm(G_.p, ytrial.p) : ngn.norm2_over_n(ng);
       if (std::isnan(rn)) rn = INFINITY;                                              // :417
       if (o.nl <= opt.inner_abstol && rn <= opt.max_residual_growth * old_r) {        // :418
         push_log(iter, ECONPDES_STEP_ACCEPTED, o.iters, o.lin_iters, ctl.delta, rn);

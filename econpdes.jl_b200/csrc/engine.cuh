@@ -6,33 +6,39 @@
 
 #include "../../include/econpdes_cuda.h"
 #include "common.cuh"
+#include "dist.cuh"
 #include "kernels.cuh"
 
 namespace econpdes {
 
 template <class T>
 struct DevBuf {
-  T* p = nullptr;
+  T* p = nullptr;  // first logical element (pad elements of ghost storage precede and follow it)
   size_t n = 0;    // logical element count
-  size_t cap = 0;  // allocated element count (grow-only: work buffers are re-used across solves)
+  size_t cap = 0;  // allocated logical element count (grow-only: work buffers are re-used across solves)
+  size_t pad = 0;  // ghost elements on either side (slab-decomposed fields: one plane); set before alloc
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFree(p - pad_alloc_);
     p = nullptr;
     n = 0;
     cap = 0;
   }
   void alloc(size_t count) {
-    if (count <= cap && p) {
+    if (count <= cap && p && pad == pad_alloc_) {
       n = count;
       return;
     }
     release();
     if (count == 0) return;
-    EP_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    T* base = nullptr;
+    EP_CUDA(cudaMalloc(&base, (count + 2 * pad) * sizeof(T)));
+    if (pad) EP_CUDA(cudaMemset(base, 0, (count + 2 * pad) * sizeof(T)));   // ghosts at the global ends stay 0
+    p = base + pad;
+    pad_alloc_ = pad;
     n = count;
     cap = count;
   }
@@ -44,6 +50,9 @@ struct DevBuf {
   void download(T* h, size_t count, cudaStream_t s) const {
     EP_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
   }
+
+ private:
+  size_t pad_alloc_ = 0;
 };
 
 // Problem resident on one device.
@@ -51,9 +60,16 @@ struct Ctx {
   int model_id = -1, N = 0, F = 0, nparams = 0, nsaved = 0;
   bool box = false;        // stencil shape of the Jacobian planes
   int nk = 0;              // planes per (fin, fout) pair
-  long long S[kMaxDims] = {1, 1, 1};
-  long long l = 0, n = 0;
+  long long S[kMaxDims] = {1, 1, 1};  // GLOBAL grid sizes
+  long long l = 0, n = 0;             // points / unknowns owned by this device
+  long long n_glob = 0;               // unknowns of the whole grid (norms divide by it)
   int ncolors = 0;
+  // slab decomposition along dimension N-1 (dist == nullptr: the whole grid lives here)
+  Dist* dist = nullptr;
+  long long slab_first = 0, slab_count = 0;   // owned range of dimension N-1
+  long long halo = 0;                          // ghost plane size (prod S_0..S_{N-2}) when dist != nullptr
+  DevBuf<double> gather;                       // [world][kGatherMax] landing area of small all-gathers
+  double* h_gather = nullptr;                  // pinned copy
   ParamPack prm{};
   DevBuf<double> grid[kMaxDims], guess, bc, lb, ub, delta_rel;
   DevBuf<unsigned char> is_alg;
@@ -77,9 +93,16 @@ struct Ctx {
       gv.stride[d] = st;
       st *= S[d];
     }
-    gv.l = st;
+    gv.l = l;
+    gv.off = slab_first;
     return gv;
   }
+  void exchange_halo(const double* field) const {
+    if (dist != nullptr) dist->exchange_halo(const_cast<double*>(field), halo, slab_count, stream);
+  }
+  // Per-rank partials (device, `count` doubles) -> every rank's copy on the host, rank-major.
+  // Returns the pinned landing area; valid until the next call.
+  const double* gather_to_host(const double* partial_dev, int count);
   ~Ctx();
 };
 
@@ -158,7 +181,12 @@ class Solver {
   DevBuf<long long> csc_map_;
 };
 
-std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p);  // validates + uploads; throws
+constexpr int kGatherMax = 128;  // doubles per rank in one small all-gather
+
+// validates + uploads; throws.  With `dist`, the problem arrays are this rank's slab
+// (S_0..S_{N-2}, slab_count) while problem->size and problem->grid describe the GLOBAL grid.
+std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p, Dist* dist = nullptr, long long slab_first = 0,
+                              long long slab_count = 0);
 void ensure_device();
 
 }  // namespace econpdes

@@ -39,6 +39,9 @@ struct LevelGeom {
   long long S[N];
   long long stride[N];
   long long l;
+  // slab of a distributed level: the first / last plane of dimension N-1 has a neighbour plane
+  // in the ghost storage around the vector (filled by a halo exchange), not a grid boundary
+  bool open_lo = false, open_hi = false;
 };
 
 template <int N>
@@ -81,7 +84,9 @@ __global__ void __launch_bounds__(kBlock) k_spmv(LevelGeom<N> g, const double* _
 #pragma unroll
     for (int d = 0; d < N; ++d) {
       const int o = St::off(k, d);
-      if ((o < 0 && idx[d] == 0) || (o > 0 && idx[d] == g.S[d] - 1)) ok = false;
+      const bool lo_edge = idx[d] == 0 && !(d == N - 1 && g.open_lo);
+      const bool hi_edge = idx[d] == g.S[d] - 1 && !(d == N - 1 && g.open_hi);
+      if ((o < 0 && lo_edge) || (o > 0 && hi_edge)) ok = false;
       q += o * g.stride[d];
     }
     // entries that point outside the grid hold 0: load unconditionally (clamped address) so all
@@ -663,7 +668,7 @@ class KrylovSolver final : public LinearSolver {
     w_.alloc(static_cast<size_t>(L0.l));
     DevBuf<double> z;
     z.alloc(static_cast<size_t>(L0.l));
-    ms_out[0] = timed([&] { spmv(L0, v, nullptr, w_.p, 0); });
+    ms_out[0] = timed([&] { spmv_top(v, nullptr, w_.p, 0); });
     ms_out[1] = timed([&] { precondition(v, z.p); });
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
@@ -675,6 +680,9 @@ class KrylovSolver final : public LinearSolver {
   DevBuf<double> dense_, sym_, V_, Z_, w_, dots_, part_, hdev_, rap_tmp_[2], dense_inv_, dense_work_;
   DevBuf<int> piv_;
   DevBuf<Transfer> transfers_dev_;
+  // slab path: ghosted copy of the SpMV operand, block-local copy of the operator for the
+  // preconditioner (couplings that leave the slab dropped), all-gather landing area
+  DevBuf<double> xh_, Ablock_;
   cudaGraphExec_t graph_exec_ = nullptr;
   const double* graph_A_ = nullptr;
   int graph_nlev_ = 0;
@@ -691,6 +699,42 @@ class KrylovSolver final : public LinearSolver {
   void spmv(const Level<N>& L, const double* x, const double* b, double* y, int mode) {
     if (L.box) spmv<true>(L, x, b, y, mode); else spmv<false>(L, x, b, y, mode);
   }
+  // The operator of the Krylov iteration: on a slab, A couples to the neighbour ranks' edge
+  // planes, so the operand is copied into ghosted storage and its halos are exchanged first.
+  void spmv_top(const double* x, const double* b, double* y, int mode) {
+    Level<N>& L0 = *lev_[0];
+    if (c_.dist == nullptr) {
+      spmv(L0, x, b, y, mode);
+      return;
+    }
+    cudaStream_t s = c_.stream;
+    xh_.pad = static_cast<size_t>(c_.halo);
+    xh_.alloc(static_cast<size_t>(L0.l));
+    EP_CUDA(cudaMemcpyAsync(xh_.p, x, L0.l * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    c_.exchange_halo(xh_.p);
+    LevelGeom<N> g = make_geom<N>(L0.S);
+    g.open_lo = c_.dist->has_lo();
+    g.open_hi = c_.dist->has_hi();
+    if (c_.box) EP_LAUNCH((k_spmv<N, true>), blocks_for(L0.l), kBlock, 0, s, g, top_A_, xh_.p, b, y, mode);
+    else EP_LAUNCH((k_spmv<N, false>), blocks_for(L0.l), kBlock, 0, s, g, top_A_, xh_.p, b, y, mode);
+  }
+  const double* top_A_ = nullptr;
+
+  // Block-Jacobi view of the operator for the slab-local preconditioner: plane k keeps its
+  // values except on the slab's edge planes where offset o_{N-1} points to another rank.
+  const double* block_local_operator(const double* planes) {
+    cudaStream_t s = c_.stream;
+    const size_t l = static_cast<size_t>(c_.l), plane = static_cast<size_t>(c_.halo);
+    Ablock_.alloc(static_cast<size_t>(c_.nk) * l);
+    EP_CUDA(cudaMemcpyAsync(Ablock_.p, planes, static_cast<size_t>(c_.nk) * l * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    for (int k = 0; k < c_.nk; ++k) {
+      const int o = c_.box ? Stencil<N, true>::off(k, N - 1) : Stencil<N, false>::off(k, N - 1);
+      if (o < 0 && c_.dist->has_lo()) EP_CUDA(cudaMemsetAsync(Ablock_.p + k * l, 0, plane * sizeof(double), s));
+      if (o > 0 && c_.dist->has_hi())
+        EP_CUDA(cudaMemsetAsync(Ablock_.p + k * l + (l - plane), 0, plane * sizeof(double), s));
+    }
+    return Ablock_.p;
+  }
 
   // Build the hierarchy for the operator in `planes` (called once per Jacobian).
   void setup(const double* planes) {
@@ -698,12 +742,14 @@ class KrylovSolver final : public LinearSolver {
     if (lev_.empty()) {
       auto L0 = std::make_unique<Level<N>>();
       for (int d = 0; d < N; ++d) L0->S[d] = c_.S[d];
+      L0->S[N - 1] = c_.slab_count;   // == S[N-1] on a single device
       L0->l = c_.l;
       L0->box = c_.box;
       L0->nk = c_.nk;
       lev_.push_back(std::move(L0));
     }
-    lev_[0]->A = planes;
+    top_A_ = planes;
+    lev_[0]->A = c_.dist != nullptr ? block_local_operator(planes) : planes;
     size_t li = 0;
     while (true) {
       Level<N>& L = *lev_[li];
@@ -945,6 +991,16 @@ class KrylovSolver final : public LinearSolver {
     dots_.alloc(static_cast<size_t>(restart_alloc_ + 2));
     EP_LAUNCH(k_multi_dot, dim3(nb, j + 1), kBlock, 0, s, n, j, V, w, part_.p);
     EP_LAUNCH(k_finish_dots, (j + 1 + 7) / 8, 256, 0, s, j + 1, nb, part_.p, dots_.p);
+    if (c_.dist != nullptr) {   // per-rank partial dot products, folded in rank order on every rank
+      const double* g = c_.gather_to_host(dots_.p, j + 1);
+      const int world = c_.dist->world();
+      for (int q = 0; q <= j; ++q) {
+        double t = 0.0;
+        for (int r = 0; r < world; ++r) t += g[r * (j + 1) + q];
+        host_out[q] = t;
+      }
+      return;
+    }
     EP_CUDA(cudaMemcpyAsync(host_out, dots_.p, (j + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
     EP_CUDA(cudaStreamSynchronize(s));
   }
@@ -979,7 +1035,7 @@ class KrylovSolver final : public LinearSolver {
     int status = 1;
     for (int cycle = 0; cycle < 50 && total < opt.lin_maxiters; ++cycle) {
       // r = b - A x
-      spmv(L0, x, b, w_.p, 1);
+      spmv_top(x, b, w_.p, 1);
       dots(n, 0, V_.p, w_.p, hh);
       const double beta = std::sqrt(hh[0]);
       relres = beta / bnorm;
@@ -995,7 +1051,7 @@ class KrylovSolver final : public LinearSolver {
       for (; j < m && total < opt.lin_maxiters; ++j, ++total) {
         double* zj = Z_.p + static_cast<size_t>(j) * n;
         precondition(V_.p + static_cast<size_t>(j) * n, zj);
-        spmv(L0, zj, nullptr, w_.p, 0);
+        spmv_top(zj, nullptr, w_.p, 0);
         // classical Gram-Schmidt, twice
         std::fill(hcol.begin(), hcol.end(), 0.0);
         for (int pass = 0; pass < 2; ++pass) {
@@ -1041,7 +1097,7 @@ class KrylovSolver final : public LinearSolver {
     }
     if (status != 0) {
       // final check of the true residual (the loop may have ended on the iteration cap)
-      spmv(L0, x, b, w_.p, 1);
+      spmv_top(x, b, w_.p, 1);
       dots(n, 0, V_.p, w_.p, hh);
       relres = std::sqrt(hh[0]) / bnorm;
       status = (std::isfinite(relres) && relres <= 1e-8) ? 0 : 1;

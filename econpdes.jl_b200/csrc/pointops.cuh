@@ -18,12 +18,17 @@ constexpr int kMaxDims = 3;
 constexpr double kSqrtEps = 1.4901161193847656e-8;
 
 // Tensor grid: per-dimension coordinate vectors, sizes and column-major strides.
+// A slab-decomposed grid (one rank of a multi-GPU solve) keeps the GLOBAL sizes in S -- they
+// decide boundaries, spacings and colors -- and owns `l` points: all of dimensions 0..N-2 and
+// a contiguous range of the slowest dimension starting at global index `off`.  Fields of a
+// slab carry one ghost plane on either side, so neighbour addresses pt +- stride stay valid.
 template <int N>
 struct GridView {
   const double* x[N];
   long long S[N];
   long long stride[N];
-  long long l;  // number of grid points
+  long long l;        // number of grid points owned (= prod S on a single device)
+  long long off = 0;  // global index of the first owned entry of dimension N-1
 };
 
 // Stencil shapes: the full clipped +-1 box (coloring.jl:18-35) or, for models that never
@@ -47,10 +52,11 @@ struct Stencil {
 template <int N>
 EP_HD void unravel(long long pt, const GridView<N>& gv, long long* idx) {
 #pragma unroll
-  for (int d = 0; d < N; ++d) {
+  for (int d = 0; d + 1 < N; ++d) {
     idx[d] = pt % gv.S[d];
     pt /= gv.S[d];
   }
+  idx[N - 1] = pt + gv.off;   // global index along the slab dimension
 }
 
 template <int N>

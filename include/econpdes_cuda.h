@@ -214,6 +214,32 @@ int econpdes_device_count(void);
 int econpdes_set_device(int device);
 int64_t econpdes_total_kernel_launches(void);
 
+/* --- slab-decomposed solve of ONE large grid across the GPUs of a node (config C5).
+ *     One process per GPU.  The slowest dimension (N-1; slabs are contiguous in the column-major
+ *     layout of src/pdesolve.jl:111) is cut into contiguous ranges; each rank owns the planes
+ *     [slab_first, slab_first + slab_count) and exchanges one ghost plane per side over
+ *     NVLink (NCCL send/recv) before every residual / Jacobian / SpMV sweep; norms, Krylov dot
+ *     products and FiniteDiff's per-color sums are all-gathered and folded in rank order, so every
+ *     rank takes the same accept/reject decisions as the single-device solve.
+ *     The reference has no counterpart (it is single-threaded): this replaces the same
+ *     finiteschemesolve call as econpdes_solve_stationary. --- */
+#define ECONPDES_UNIQUE_ID_BYTES 128
+typedef struct econpdes_dist econpdes_dist;
+/* rank 0 creates the id; the host broadcasts it to the other ranks (torch.distributed, MPI, a pipe) */
+int econpdes_dist_unique_id(uint8_t* id /* [ECONPDES_UNIQUE_ID_BYTES] */);
+/* collective over all ranks; binds to the calling thread's current CUDA device */
+int econpdes_dist_create(int rank, int world, const uint8_t* id, econpdes_dist** out);
+void econpdes_dist_destroy(econpdes_dist* d);
+int64_t econpdes_dist_collectives(const econpdes_dist* d); /* NCCL calls issued so far */
+/* balanced partition of dimension N-1 in units of two planes (slabs start on even indices so the
+ * multigrid hierarchy coarsens inside a slab); host-only */
+int econpdes_slab_range(int64_t size_last, int rank, int world, int64_t* first, int64_t* count);
+/* problem->size / problem->grid describe the GLOBAL grid; guess, bc, is_algebraic and the bounds are
+ * this rank's slab (S_1..S_{N-1}, slab_count), and so is result->solution.  Scalars of the result
+ * (residual_norm, converged, log, counts) are identical on every rank. */
+int econpdes_solve_stationary_slab(econpdes_dist* d, const econpdes_problem* problem, int64_t slab_first,
+                                   int64_t slab_count, const econpdes_options* options, econpdes_result* result);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,3 +82,50 @@ def test_two_rank_sweep_matches_single_process():
     # rank 0 holds 6 problems, rank 1 holds 5 (+1 row of padding)
     np.testing.assert_array_equal(all_sol[:6], sol[:6])
     np.testing.assert_array_equal(all_sol[6:11], sol[6:11])
+
+
+def _slab_worker(rank, world, port, S_last, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import econpdes_b200 as E
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    # the byte channel SlabGroup.from_torch uses for the NCCL unique id (the id itself needs a GPU)
+    box = [bytes(range(128)) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    first, count = E.slab_range(S_last, rank, world)
+    spans = [None] * world
+    dist.all_gather_object(spans, (first, count))
+    if rank == 0:
+        q.put((box[0], spans))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_partition_and_id_broadcast_two_ranks():
+    """Host side of the slab-decomposed solve (config C5): every rank derives its plane range from
+    the C ABI's econpdes_slab_range and receives rank 0's 128-byte communicator id."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_worker, args=(r, 2, port, 257, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    uid, spans = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert uid == bytes(range(128))
+    assert spans == [(0, 128), (128, 129)]
+
+
+def test_slab_ranges_even_aligned_cover():
+    sys.path.insert(0, ROOT)
+    import econpdes_b200 as E
+    for S, world in ((256, 8), (256, 2), (33, 3), (64, 4), (17, 8)):
+        spans = [E.slab_range(S, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == S
+        for (f, c), (f2, _) in zip(spans, spans[1:]):
+            assert f + c == f2 and f % 2 == 0 and c >= 2 and c % 2 == 0
+    with pytest.raises(E.EconPDEsCudaError):
+        E.slab_range(6, 0, 4)
