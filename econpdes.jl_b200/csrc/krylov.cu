@@ -202,7 +202,9 @@ __global__ void __launch_bounds__(1024) k_line_zebra(LevelGeom<N> g, const doubl
           const int o = St::off(k, e);
           if (e > 0 && o != 0) inl = false;
           const long long ie = e == 0 ? i : other[e - 1];
-          if ((o < 0 && ie == 0) || (o > 0 && ie == g.S[e] - 1)) ok = false;
+          const bool lo_edge = ie == 0 && !(e == N - 1 && g.open_lo);
+          const bool hi_edge = ie == g.S[e] - 1 && !(e == N - 1 && g.open_hi);
+          if ((o < 0 && lo_edge) || (o > 0 && hi_edge)) ok = false;
           q += o * g.stride[e];
         }
         if (!inl) rhs -= A[k * g.l + pt] * x[ok ? q : pt];   // zero coefficient outside the grid
@@ -260,6 +262,10 @@ struct Transfer {
   int type[kMaxDims];      // 1 linear, 0 aggregation, -1 identity
   long long Sf[kMaxDims], Sc[kMaxDims];
 };
+// On a slab the indices of dimension N-1 are local; slabs start on even global indices, so
+// coarse local I still sits at fine local 2I.  A neighbour rank shows up as fine index -1 /
+// coarse index Sc (one past the owned range): `open_lo` admits the former, and the weights are
+// evaluated with the virtual coarse extent Sc + 1 when `open_hi`.
 __device__ __forceinline__ double tw(int type, long long i, long long I, long long Sc) {
   if (type < 0) return i == I ? 1.0 : 0.0;
   if (type == 0) return (i >> 1) == I ? 1.0 : 0.0;
@@ -269,10 +275,12 @@ __device__ __forceinline__ double tw(int type, long long i, long long I, long lo
   return (I == l || I == r) ? 0.5 : 0.0;
 }
 // range of fine indices with non-zero weight for coarse I
-__device__ __forceinline__ void fine_range(int type, long long I, long long Sf, long long& lo, long long& hi) {
+__device__ __forceinline__ void fine_range(int type, long long I, long long Sf, long long& lo, long long& hi,
+                                           bool open_lo = false) {
   if (type < 0) { lo = hi = I; return; }
   if (type == 0) { lo = 2 * I; hi = 2 * I + 1 < Sf ? 2 * I + 1 : Sf - 1; return; }
-  lo = 2 * I - 1 > 0 ? 2 * I - 1 : 0;
+  const long long first = open_lo ? -1 : 0;
+  lo = 2 * I - 1 > first ? 2 * I - 1 : first;
   hi = 2 * I + 1 < Sf ? 2 * I + 1 : Sf - 1;
 }
 
@@ -286,7 +294,7 @@ __global__ void __launch_bounds__(kBlock) k_restrict(const Transfer* __restrict_
   long long I[N], lo[N], hi[N];
   unravel_l<N>(pc, gc, I);
 #pragma unroll
-  for (int d = 0; d < N; ++d) fine_range(t.type[d], I[d], gf.S[d], lo[d], hi[d]);
+  for (int d = 0; d < N; ++d) fine_range(t.type[d], I[d], gf.S[d], lo[d], hi[d], d == N - 1 && gf.open_lo);
   double acc = 0.0;
   long long cnt[N], total = 1;
 #pragma unroll
@@ -298,8 +306,8 @@ __global__ void __launch_bounds__(kBlock) k_restrict(const Transfer* __restrict_
     for (int d = 0; d < N; ++d) {
       const long long i = lo[d] + rr % cnt[d];
       rr /= cnt[d];
-      w *= tw(t.type[d], i, I[d], gc.S[d]);
-      q += i * gf.stride[d];
+      w *= tw(t.type[d], i, I[d], gc.S[d] + ((d == N - 1 && gf.open_hi) ? 1 : 0));
+      q += i * gf.stride[d];   // i == -1 on a slab: the lower ghost plane of rf
     }
     if (w != 0.0) acc += w * rf[q];
   }
@@ -328,8 +336,9 @@ __global__ void __launch_bounds__(kBlock) k_prolong_add(const Transfer* __restri
       long long I;
       if (t.type[d] < 0) I = i[d]; else I = (i[d] >> 1) + bit;
       if (bit && (t.type[d] != 1 || (i[d] & 1) == 0)) skip = true;   // second candidate only for odd linear points
-      if (I >= gc.S[d]) skip = true;
-      if (!skip) { w *= tw(t.type[d], i[d], I, gc.S[d]); q += I * gc.stride[d]; }
+      const long long Sce = gc.S[d] + ((d == N - 1 && gf.open_hi) ? 1 : 0);   // slab: I == Sc is the upper ghost of ec
+      if (I >= Sce) skip = true;
+      if (!skip) { w *= tw(t.type[d], i[d], I, Sce); q += I * gc.stride[d]; }
     }
     if (!skip && w != 0.0) acc += w * ec[q];
   }
@@ -355,9 +364,13 @@ __device__ __forceinline__ int plane_of(const int* o) {
   return nz == 0 ? 0 : (nz == 1 ? k : -1);
 }
 
+// On a slab, coarsening dimension N-1 needs the operator rows of the lower neighbour's last plane
+// (`Aghost[k][plane]`, fine index -1), and keeps the couplings to the neighbours' coarse planes
+// (J == -1 / J == Sc).
 template <int N, bool BOXIN>
 __global__ void __launch_bounds__(kBlock) k_rap_1d(int d, int type, LevelGeom<N> gin, LevelGeom<N> gout,
-                                                   const double* __restrict__ Ain, double* __restrict__ Aout) {
+                                                   const double* __restrict__ Ain, double* __restrict__ Aout,
+                                                   const double* __restrict__ Aghost) {
   constexpr int KC = ipow3(N);
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (tid >= gout.l * KC) return;
@@ -369,28 +382,35 @@ __global__ void __launch_bounds__(kBlock) k_rap_1d(int d, int type, LevelGeom<N>
 #pragma unroll
   for (int e = 0; e < N; ++e) O[e] = (kout / p3(e)) % 3 - 1;
   const long long I = idx[d], J = I + O[d];
+  const bool slab = d == N - 1;
+  const bool olo = slab && gin.open_lo, ohi = slab && gin.open_hi;
+  const long long Sce = gout.S[d] + (ohi ? 1 : 0);          // virtual coarse extent for the weights
+  const long long jlo = olo ? -2 : 0, jhi = gin.S[d] - 1 + (ohi ? 1 : 0);   // admissible fine columns [jlo, jhi]
   double acc = 0.0;
-  if (J >= 0 && J < gout.S[d]) {
+  if (J >= (olo ? -1 : 0) && J < Sce) {
     long long lo, hi, pbase = 0;
-    fine_range(type, I, gin.S[d], lo, hi);
+    fine_range(type, I, gin.S[d], lo, hi, olo);
 #pragma unroll
     for (int e = 0; e < N; ++e)
       if (e != d) pbase += idx[e] * gin.stride[e];
     for (long long i = lo; i <= hi; ++i) {
-      const double wi = tw(type, i, I, gout.S[d]);
+      const double wi = tw(type, i, I, Sce);
       if (wi == 0.0) continue;
       const long long pin = pbase + i * gin.stride[d];
 #pragma unroll
       for (int od = -1; od <= 1; ++od) {
         const long long j = i + od;
-        if (j < 0 || j >= gin.S[d]) continue;
-        const double wj = tw(type, j, J, gout.S[d]);
+        if (j < jlo || j > jhi) continue;
+        const double wj = tw(type, j, J, Sce);
         if (wj == 0.0) continue;
         int o[N];
 #pragma unroll
         for (int e = 0; e < N; ++e) o[e] = e == d ? od : O[e];
         const int kin = plane_of<N, BOXIN>(o);
-        if (kin >= 0) acc += wi * Ain[kin * gin.l + pin] * wj;
+        if (kin >= 0) {
+          const double a = i < 0 ? Aghost[kin * gin.stride[d] + pbase] : Ain[kin * gin.l + pin];
+          acc += wi * a * wj;
+        }
       }
     }
   }
@@ -608,13 +628,54 @@ __global__ void __launch_bounds__(kBlock) k_scale_copy(long long n, double a, co
   if (i < n) dst[i] = a * src[i];
 }
 
+// ---- slab plumbing of the distributed levels -----------------------------------------------
+constexpr int kMaxRanks = 16;
+struct SlabMap {           // every rank's owned range of dimension N-1 at one level
+  int world;
+  long long first[kMaxRanks], count[kMaxRanks];
+};
+// last owned plane of every operator plane, packed [k][plane] for the neighbour above
+static __global__ void __launch_bounds__(kBlock) k_pack_last_plane(int nk, long long l, long long plane,
+                                                                   const double* __restrict__ A,
+                                                                   double* __restrict__ out) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= nk * plane) return;
+  const long long k = t / plane, p = t % plane;
+  out[t] = A[k * l + (l - plane) + p];
+}
+// local [nk][l_loc] -> send buffer [nk][maxl]
+static __global__ void __launch_bounds__(kBlock) k_pack_slab(int nk, long long lloc, long long maxl,
+                                                             const double* __restrict__ src, double* __restrict__ dst) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= nk * lloc) return;
+  const long long k = t / lloc, p = t % lloc;
+  dst[k * maxl + p] = src[k * lloc + p];
+}
+// all-gathered [rank][nk][maxl] -> full [nk][l_glob] (slabs are contiguous along dimension N-1)
+static __global__ void __launch_bounds__(kBlock) k_unpack_slabs(SlabMap m, int nk, long long plane, long long maxl,
+                                                                long long lglob, const double* __restrict__ all,
+                                                                double* __restrict__ full) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(nk) * lglob) return;
+  const long long k = t / lglob, pt = t % lglob;
+  const long long i = pt / plane;
+  int r = 0;
+  while (r + 1 < m.world && i >= m.first[r + 1]) ++r;
+  full[t] = all[(static_cast<long long>(r) * nk + k) * maxl + (pt - m.first[r] * plane)];
+}
+
 // ---- the solver ---------------------------------------------------------------------------
 template <int N>
 struct Level {
-  long long S[N];
+  long long S[N];                       // sizes held on this device (slab: local count of dimension N-1)
   long long l = 0;
   bool box = true;
   int nk = 0;
+  // distributed (slab) level: vectors x, b, r, tx carry one ghost plane per side
+  bool dist = false, open_lo = false, open_hi = false;
+  long long plane = 0;                  // prod S[0..N-2]
+  long long Sg_last = 0;                // global size of dimension N-1
+  SlabMap map{};                        // owned ranges of all ranks at this level
   const double* A = nullptr;           // layout 0
   DevBuf<double> Aown;                  // owned storage for coarse levels
   DevBuf<double> Aperm[N];              // operator in layout d (d >= 1)
@@ -631,6 +692,8 @@ class KrylovSolver final : public LinearSolver {
     sym_.alloc(2 * kMaxDims);
     const char* e = std::getenv("ECONPDES_NO_GRAPH");
     use_graph_ = !(e && e[0] == '1');
+    if (c.dist != nullptr) use_graph_ = false;   // the slab cycle interleaves NCCL calls with its kernels
+    if (const char* rb = std::getenv("ECONPDES_REPLICATE_BELOW")) replicate_below_ = std::atoll(rb);
   }
   ~KrylovSolver() override {
     if (h_) cudaFreeHost(h_);
@@ -682,7 +745,8 @@ class KrylovSolver final : public LinearSolver {
   DevBuf<Transfer> transfers_dev_;
   // slab path: ghosted copy of the SpMV operand, block-local copy of the operator for the
   // preconditioner (couplings that leave the slab dropped), all-gather landing area
-  DevBuf<double> xh_, Ablock_;
+  DevBuf<double> xh_, gsend_, grecv_, rap_send_, rap_ghost_, bloc_;
+  long long replicate_below_ = 48LL * 48 * 48;   // levels with at most this many points run replicated
   cudaGraphExec_t graph_exec_ = nullptr;
   const double* graph_A_ = nullptr;
   int graph_nlev_ = 0;
@@ -720,25 +784,44 @@ class KrylovSolver final : public LinearSolver {
   }
   const double* top_A_ = nullptr;
 
-  // Block-Jacobi view of the operator for the slab-local preconditioner: plane k keeps its
-  // values except on the slab's edge planes where offset o_{N-1} points to another rank.
-  const double* block_local_operator(const double* planes) {
+  // geometry of a level (layout 0, or layout d with dimension d fastest); on a slab the last
+  // layout dimension is still N-1 for every line direction d < N-1
+  LevelGeom<N> geom(const Level<N>& L) const {
+    LevelGeom<N> g = make_geom<N>(L.S);
+    g.open_lo = L.dist && L.open_lo;
+    g.open_hi = L.dist && L.open_hi;
+    return g;
+  }
+  LevelGeom<N> geom_layout(const Level<N>& L, int d) const {
+    LevelGeom<N> g = make_geom<N>(L.Sd[d]);
+    g.open_lo = L.dist && L.open_lo;
+    g.open_hi = L.dist && L.open_hi;
+    return g;
+  }
+  void halo(const Level<N>& L, double* v) { c_.dist->exchange_halo(v, L.plane, L.S[N - 1], c_.stream); }
+
+  // [nk][l_loc] slabs of every rank -> [nk][l_glob] on every rank
+  void gather_slabs(const SlabMap& m, int nk, long long plane, const double* local, double* full) {
     cudaStream_t s = c_.stream;
-    const size_t l = static_cast<size_t>(c_.l), plane = static_cast<size_t>(c_.halo);
-    Ablock_.alloc(static_cast<size_t>(c_.nk) * l);
-    EP_CUDA(cudaMemcpyAsync(Ablock_.p, planes, static_cast<size_t>(c_.nk) * l * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    for (int k = 0; k < c_.nk; ++k) {
-      const int o = c_.box ? Stencil<N, true>::off(k, N - 1) : Stencil<N, false>::off(k, N - 1);
-      if (o < 0 && c_.dist->has_lo()) EP_CUDA(cudaMemsetAsync(Ablock_.p + k * l, 0, plane * sizeof(double), s));
-      if (o > 0 && c_.dist->has_hi())
-        EP_CUDA(cudaMemsetAsync(Ablock_.p + k * l + (l - plane), 0, plane * sizeof(double), s));
-    }
-    return Ablock_.p;
+    const int me = c_.dist->rank();
+    long long maxcount = 0, total = 0;
+    for (int r = 0; r < m.world; ++r) { maxcount = m.count[r] > maxcount ? m.count[r] : maxcount; total += m.count[r]; }
+    const long long maxl = maxcount * plane, lloc = m.count[me] * plane, lglob = total * plane;
+    gsend_.alloc(static_cast<size_t>(nk) * maxl);
+    grecv_.alloc(static_cast<size_t>(m.world) * nk * maxl);
+    EP_LAUNCH(k_pack_slab, blocks_for(nk * lloc), kBlock, 0, s, nk, lloc, maxl, local, gsend_.p);
+    c_.dist->all_gather(gsend_.p, grecv_.p, nk * maxl, s);
+    EP_LAUNCH(k_unpack_slabs, blocks_for(nk * lglob), kBlock, 0, s, m, nk, plane, maxl, lglob, grecv_.p, full);
   }
 
   // Build the hierarchy for the operator in `planes` (called once per Jacobian).
+  // Slab path: the fine levels stay distributed like the grid (ghost planes + halo exchanges);
+  // once a level is small (<= replicate_below_ points) its operator is all-gathered and every
+  // rank runs the rest of the cycle redundantly -- those levels are launch-latency bound, so
+  // replicating them costs less than their halo exchanges would.
   void setup(const double* planes) {
     cudaStream_t s = c_.stream;
+    Dist* dd = c_.dist;
     if (lev_.empty()) {
       auto L0 = std::make_unique<Level<N>>();
       for (int d = 0; d < N; ++d) L0->S[d] = c_.S[d];
@@ -746,15 +829,33 @@ class KrylovSolver final : public LinearSolver {
       L0->l = c_.l;
       L0->box = c_.box;
       L0->nk = c_.nk;
+      L0->Sg_last = c_.S[N - 1];
+      if (dd != nullptr) {
+        if (dd->world() > kMaxRanks) throw std::invalid_argument("slab path: at most 16 ranks");
+        L0->dist = true;
+        L0->open_lo = dd->has_lo();
+        L0->open_hi = dd->has_hi();
+        L0->plane = c_.halo;
+        L0->map.world = dd->world();
+        // every rank derives every rank's range (econpdes_slab_range arithmetic)
+        const long long units = c_.S[N - 1] / 2, base = units / dd->world(), rem = units % dd->world();
+        for (int r = 0; r < dd->world(); ++r) {
+          const long long uf = r * base + (r < rem ? r : rem), uc = base + (r < rem ? 1 : 0);
+          L0->map.first[r] = 2 * uf;
+          L0->map.count[r] = 2 * uc + (r == dd->world() - 1 ? c_.S[N - 1] % 2 : 0);
+        }
+        if (L0->map.first[dd->rank()] != c_.slab_first || L0->map.count[dd->rank()] != c_.slab_count)
+          throw std::invalid_argument("slab path: ranges must come from econpdes_slab_range");
+      }
       lev_.push_back(std::move(L0));
     }
     top_A_ = planes;
-    lev_[0]->A = c_.dist != nullptr ? block_local_operator(planes) : planes;
+    lev_[0]->A = planes;
     size_t li = 0;
     while (true) {
       Level<N>& L = *lev_[li];
       prepare_level(L);
-      bool coarsest = true;
+      bool coarsest = !L.dist;
       for (int d = 0; d < N; ++d)
         if (L.S[d] > (N == 3 ? kCoarseMax3D : kCoarseMax2D)) coarsest = false;
       if (coarsest || li + 1 >= kMaxLevels) break;
@@ -762,27 +863,63 @@ class KrylovSolver final : public LinearSolver {
       sym_.zero(s);
       if (L.box) EP_LAUNCH((k_edge_symmetry<N, true>), blocks_for(L.l), kBlock, 0, s, make_geom<N>(L.S), L.A, sym_.p);
       else EP_LAUNCH((k_edge_symmetry<N, false>), blocks_for(L.l), kBlock, 0, s, make_geom<N>(L.S), L.A, sym_.p);
-      EP_CUDA(cudaMemcpyAsync(h_, sym_.p, 2 * N * sizeof(double), cudaMemcpyDeviceToHost, s));
-      EP_CUDA(cudaStreamSynchronize(s));
+      double symh[2 * kMaxDims] = {};
+      if (L.dist) {   // every rank must take the same decision: fold all ranks' sums in rank order
+        const double* g = c_.gather_to_host(sym_.p, 2 * N);
+        for (int r = 0; r < dd->world(); ++r)
+          for (int q = 0; q < 2 * N; ++q) symh[q] += g[r * 2 * N + q];
+      } else {
+        EP_CUDA(cudaMemcpyAsync(h_, sym_.p, 2 * N * sizeof(double), cudaMemcpyDeviceToHost, s));
+        EP_CUDA(cudaStreamSynchronize(s));
+        for (int q = 0; q < 2 * N; ++q) symh[q] = h_[q];
+      }
       Transfer t{};
-      long long Sc[N];
+      long long Sc[N];   // sizes of the coarse level as held on this device if it stays distributed
       for (int d = 0; d < N; ++d) {
+        const long long Sfull = (L.dist && d == N - 1) ? L.Sg_last : L.S[d];
         t.Sf[d] = L.S[d];
-        if (L.S[d] <= 2) {
+        if (Sfull <= 2) {
           t.type[d] = -1;
           Sc[d] = L.S[d];
         } else {
-          const double ratio = h_[2 * d + 1] > 0 ? h_[2 * d] / h_[2 * d + 1] : 1.0;
+          const double ratio = symh[2 * d + 1] > 0 ? symh[2 * d] / symh[2 * d + 1] : 1.0;
           t.type[d] = ratio > kLinearThreshold ? 1 : 0;
           Sc[d] = (L.S[d] + 1) / 2;
         }
         t.Sc[d] = Sc[d];
       }
+      // does the coarse level stay distributed?
+      SlabMap cmap{};
+      bool coarse_dist = false;
+      long long Scg_last = Sc[N - 1], coarse_glob = 1;
+      if (L.dist) {
+        if (t.type[N - 1] < 0) throw std::runtime_error("slab path: slab dimension too short to coarsen");
+        Scg_last = (L.Sg_last + 1) / 2;
+        cmap.world = L.map.world;
+        coarse_dist = true;
+        for (int r = 0; r < cmap.world; ++r) {
+          cmap.first[r] = L.map.first[r] / 2;
+          cmap.count[r] = (L.map.count[r] + 1) / 2;
+          const bool last = r == cmap.world - 1;
+          if (cmap.first[r] % 2 != 0 || cmap.count[r] < 2 || (!last && cmap.count[r] % 2 != 0)) coarse_dist = false;
+        }
+        coarse_glob = Scg_last;
+        for (int d = 0; d + 1 < N; ++d) coarse_glob *= Sc[d];
+        if (coarse_glob <= replicate_below_) coarse_dist = false;
+      }
       L.to_coarse = t;
       if (lev_.size() <= li + 1) lev_.push_back(std::make_unique<Level<N>>());
       Level<N>& Lc = *lev_[li + 1];
+      Lc.dist = coarse_dist;
+      Lc.map = cmap;
+      Lc.Sg_last = Scg_last;
+      Lc.open_lo = coarse_dist && L.open_lo;
+      Lc.open_hi = coarse_dist && L.open_hi;
       Lc.l = 1;
-      for (int d = 0; d < N; ++d) { Lc.S[d] = Sc[d]; Lc.l *= Sc[d]; }
+      for (int d = 0; d < N; ++d) Lc.S[d] = Sc[d];
+      if (L.dist && !coarse_dist) Lc.S[N - 1] = Scg_last;   // replicated: the whole coarse grid
+      for (int d = 0; d < N; ++d) Lc.l *= Lc.S[d];
+      Lc.plane = Lc.l / Lc.S[N - 1];
       Lc.box = true;
       Lc.nk = ipow3(N);
       Lc.Aown.alloc(static_cast<size_t>(Lc.nk) * Lc.l);
@@ -795,26 +932,42 @@ class KrylovSolver final : public LinearSolver {
         bool inbox = L.box;
         int npass = 0, pass = 0;
         for (int d = 0; d < N; ++d) npass += t.type[d] >= 0 ? 1 : 0;
+        const bool regather = L.dist && !coarse_dist;   // local coarse slab first, then all-gather
         for (int d = 0; d < N; ++d) {
           if (t.type[d] < 0) continue;
           long long Sout[N];
           for (int e = 0; e < N; ++e) Sout[e] = Sin[e];
           Sout[d] = t.Sc[d];
-          const LevelGeom<N> gin = make_geom<N>(Sin), gout = make_geom<N>(Sout);
+          LevelGeom<N> gin = make_geom<N>(Sin), gout = make_geom<N>(Sout);
           double* out;
-          if (++pass == npass) {
+          if (++pass == npass && !regather) {
             out = Lc.Aown.p;
           } else {
             rap_tmp_[pass & 1].alloc(static_cast<size_t>(ipow3(N)) * gout.l);
             out = rap_tmp_[pass & 1].p;
           }
+          const double* ghost = nullptr;
+          if (L.dist && d == N - 1) {
+            gin.open_lo = L.open_lo;
+            gin.open_hi = L.open_hi;
+            if (t.type[d] == 1) {   // rows of the lower neighbour's last plane, all operator planes
+              const int nkin = inbox ? ipow3(N) : 1 + 2 * N;
+              const long long pl = gin.stride[N - 1];
+              rap_send_.alloc(static_cast<size_t>(nkin) * pl);
+              rap_ghost_.alloc(static_cast<size_t>(nkin) * pl);
+              EP_LAUNCH(k_pack_last_plane, blocks_for(nkin * pl), kBlock, 0, s, nkin, gin.l, pl, in, rap_send_.p);
+              dd->send_hi_recv_lo(rap_send_.p, rap_ghost_.p, nkin * pl, s);
+              ghost = rap_ghost_.p;
+            }
+          }
           const long long nthreads = gout.l * ipow3(N);
-          if (inbox) EP_LAUNCH((k_rap_1d<N, true>), blocks_for(nthreads), kBlock, 0, s, d, t.type[d], gin, gout, in, out);
-          else EP_LAUNCH((k_rap_1d<N, false>), blocks_for(nthreads), kBlock, 0, s, d, t.type[d], gin, gout, in, out);
+          if (inbox) EP_LAUNCH((k_rap_1d<N, true>), blocks_for(nthreads), kBlock, 0, s, d, t.type[d], gin, gout, in, out, ghost);
+          else EP_LAUNCH((k_rap_1d<N, false>), blocks_for(nthreads), kBlock, 0, s, d, t.type[d], gin, gout, in, out, ghost);
           in = out;
           inbox = true;
           for (int e = 0; e < N; ++e) Sin[e] = Sout[e];
         }
+        if (regather) gather_slabs(cmap, ipow3(N), Lc.plane, in, Lc.Aown.p);
       }
       ++li;
     }
@@ -844,8 +997,11 @@ class KrylovSolver final : public LinearSolver {
   void prepare_level(Level<N>& L) {
     cudaStream_t s = c_.stream;
     const size_t l = static_cast<size_t>(L.l);
+    const size_t pad = L.dist ? static_cast<size_t>(L.plane) : 0;
+    L.x.pad = L.b.pad = L.r.pad = L.tx.pad = L.tb.pad = pad;
     L.x.alloc(l); L.b.alloc(l); L.r.alloc(l); L.tx.alloc(l); L.tb.alloc(l);
-    for (int d = 1; d < N; ++d) {
+    const int ndirs = L.dist ? N - 1 : N;   // lines along the slab dimension would cross ranks
+    for (int d = 1; d < ndirs; ++d) {
       int perm[N];
       layout_dims<N>(L.S, d, L.Sd[d], perm);
       L.Aperm[d].alloc(static_cast<size_t>(L.nk) * l);
@@ -871,10 +1027,10 @@ class KrylovSolver final : public LinearSolver {
   }
 
   template <bool BOX>
-  void line_sweep_layout(const Level<N>& L, int d, const double* A, const double* b, double* x) {
+  void line_sweep_layout(Level<N>& L, int d, const double* A, const double* b, double* x) {
     const long long* Sd = L.Sd[d];
     const int n = static_cast<int>(Sd[0]);
-    const LevelGeom<N> g = make_geom<N>(Sd);
+    const LevelGeom<N> g = geom_layout(L, d);
     const int ncolors = 1 << (N - 1);
     int T = ((n + 31) / 32) * 32;
     int rpt = 1;
@@ -887,7 +1043,7 @@ class KrylovSolver final : public LinearSolver {
         const int ce = (color >> (e - 1)) & 1;
         nlines *= (Sd[e] - ce + 1) / 2;
       }
-      if (nlines <= 0) continue;
+      if (nlines > 0) {
 #define EP_LINE(R)                                                                                          \
   do {                                                                                                      \
     static bool cfg = false;                                                                                \
@@ -898,29 +1054,38 @@ class KrylovSolver final : public LinearSolver {
     }                                                                                                       \
     EP_LAUNCH((k_line_zebra<N, BOX, R>), static_cast<unsigned>(nlines), T, smem, c_.stream, g, A, b, x, color); \
   } while (0)
-      if (rpt == 1) EP_LINE(1);
-      else if (rpt == 2) EP_LINE(2);
-      else if (rpt <= 4) EP_LINE(4);
-      else EP_LINE(8);
+        if (rpt == 1) EP_LINE(1);
+        else if (rpt == 2) EP_LINE(2);
+        else if (rpt <= 4) EP_LINE(4);
+        else EP_LINE(8);
 #undef EP_LINE
+      }
+      // Slab: the top color bit is the parity of the plane index along dimension N-1 (slabs start
+      // on even planes, so local parity = global parity).  A rank's edge planes need the
+      // neighbour's edge plane of the OTHER parity, which changed in the other half of the sweep:
+      // one halo exchange after each half reproduces the single-device sweep exactly.
+      if (L.dist && (color == ncolors / 2 - 1 || color == ncolors - 1)) halo(L, x);
     }
   }
 
   // one alternating-direction zebra line smoothing pass (dims ascending or descending)
   void smooth(Level<N>& L, const double* b, double* x, bool reverse) {
     cudaStream_t s = c_.stream;
-    for (int q = 0; q < N; ++q) {
-      const int d = reverse ? N - 1 - q : q;
+    const int ndirs = L.dist ? N - 1 : N;
+    for (int q = 0; q < ndirs; ++q) {
+      const int d = reverse ? ndirs - 1 - q : q;
       if (L.S[d] < 2) continue;
       if (d == 0) {
         if (L.box) line_sweep_layout<true>(L, 0, L.A, b, x); else line_sweep_layout<false>(L, 0, L.A, b, x);
       } else {
-        const TransposeShape ts = transpose_shape<N>(L.S, d);
-        launch_transpose(s, x, L.tx.p, ts, false);
+        TransposeShape ts = transpose_shape<N>(L.S, d), tsx = ts;
+        const long long g = L.dist ? L.plane : 0;   // ghost planes travel with x (N == 3, d == 1: per-plane batches)
+        if (L.dist) tsx.batches += 2;
+        launch_transpose(s, x - g, L.tx.p - g, tsx, false);
         launch_transpose(s, b, L.tb.p, ts, false);
         if (L.box) line_sweep_layout<true>(L, d, L.Aperm[d].p, L.tb.p, L.tx.p);
         else line_sweep_layout<false>(L, d, L.Aperm[d].p, L.tb.p, L.tx.p);
-        launch_transpose(s, L.tx.p, x, ts, true);
+        launch_transpose(s, L.tx.p - g, x - g, tsx, true);
       }
     }
   }
@@ -933,15 +1098,55 @@ class KrylovSolver final : public LinearSolver {
       EP_LAUNCH(k_dense_apply, (dense_n_ + 7) / 8, 256, 0, s, dense_n_, dense_inv_.p, b, x);
       return;
     }
-    EP_CUDA(cudaMemsetAsync(x, 0, L.l * sizeof(double), s));
-    smooth(L, b, x, false);
-    spmv(L, x, b, L.r.p, 1);
     Level<N>& Lc = *lev_[li + 1];
-    EP_LAUNCH((k_restrict<N>), blocks_for(Lc.l), kBlock, 0, s, transfers_dev_.p + li, make_geom<N>(L.S),
-              make_geom<N>(Lc.S), L.r.p, Lc.b.p);
-    vcycle(li + 1, Lc.b.p, Lc.x.p);
-    EP_LAUNCH((k_prolong_add<N>), blocks_for(L.l), kBlock, 0, s, transfers_dev_.p + li, make_geom<N>(L.S),
-              make_geom<N>(Lc.S), Lc.x.p, x);
+    const LevelGeom<N> gf = geom(L);
+    if (!L.dist) {
+      EP_CUDA(cudaMemsetAsync(x, 0, L.l * sizeof(double), s));
+      smooth(L, b, x, false);
+      spmv(L, x, b, L.r.p, 1);
+      EP_LAUNCH((k_restrict<N>), blocks_for(Lc.l), kBlock, 0, s, transfers_dev_.p + li, gf, make_geom<N>(Lc.S), L.r.p,
+                Lc.b.p);
+      vcycle(li + 1, Lc.b.p, Lc.x.p);
+      EP_LAUNCH((k_prolong_add<N>), blocks_for(L.l), kBlock, 0, s, transfers_dev_.p + li, gf, make_geom<N>(Lc.S),
+                Lc.x.p, x);
+      smooth(L, b, x, true);
+      return;
+    }
+    // ---- distributed level: x, r (and the coarse x) carry ghost planes ----
+    Dist& dd = *c_.dist;
+    const bool linear = L.to_coarse.type[N - 1] == 1;
+    EP_CUDA(cudaMemsetAsync(x - L.plane, 0, (L.l + 2 * L.plane) * sizeof(double), s));
+    smooth(L, b, x, false);   // leaves the ghosts of x current
+    if (L.box) EP_LAUNCH((k_spmv<N, true>), blocks_for(L.l), kBlock, 0, s, gf, L.A, x, b, L.r.p, 1);
+    else EP_LAUNCH((k_spmv<N, false>), blocks_for(L.l), kBlock, 0, s, gf, L.A, x, b, L.r.p, 1);
+    // full weighting reaches one fine plane below the slab
+    if (linear) dd.send_hi_recv_lo(L.r.p + (L.S[N - 1] - 1) * L.plane, L.r.p - L.plane, L.plane, s);
+    // this rank's part of the coarse grid
+    long long Scl[N];
+    for (int d = 0; d < N; ++d) Scl[d] = Lc.S[d];
+    const long long cfirst = L.map.first[dd.rank()] / 2;
+    Scl[N - 1] = (L.S[N - 1] + 1) / 2;
+    const LevelGeom<N> gcl = make_geom<N>(Scl);
+    const double* ec;
+    if (Lc.dist) {
+      EP_LAUNCH((k_restrict<N>), blocks_for(gcl.l), kBlock, 0, s, transfers_dev_.p + li, gf, gcl, L.r.p, Lc.b.p);
+      vcycle(li + 1, Lc.b.p, Lc.x.p);
+      // interpolation reaches one coarse plane above the slab
+      if (linear) dd.send_lo_recv_hi(Lc.x.p, Lc.x.p + Lc.l, Lc.plane, s);
+      ec = Lc.x.p;
+    } else {
+      // replicated coarse level: all-gather the restricted residual, every rank runs the rest
+      bloc_.alloc(static_cast<size_t>(gcl.l));
+      EP_LAUNCH((k_restrict<N>), blocks_for(gcl.l), kBlock, 0, s, transfers_dev_.p + li, gf, gcl, L.r.p, bloc_.p);
+      SlabMap cm{};
+      cm.world = L.map.world;
+      for (int r = 0; r < cm.world; ++r) { cm.first[r] = L.map.first[r] / 2; cm.count[r] = (L.map.count[r] + 1) / 2; }
+      gather_slabs(cm, 1, Lc.plane, bloc_.p, Lc.b.p);
+      vcycle(li + 1, Lc.b.p, Lc.x.p);
+      ec = Lc.x.p + cfirst * Lc.plane;   // the plane above the slab is simply the next one
+    }
+    EP_LAUNCH((k_prolong_add<N>), blocks_for(L.l), kBlock, 0, s, transfers_dev_.p + li, gf, gcl, ec, x);
+    halo(L, x);
     smooth(L, b, x, true);
   }
 
@@ -951,6 +1156,11 @@ class KrylovSolver final : public LinearSolver {
   void precondition(const double* v, double* z) {
     cudaStream_t s = c_.stream;
     Level<N>& L0 = *lev_[0];
+    if (L0.dist) {   // the cycle's x carries ghost planes: run it in the level's own buffer
+      vcycle(0, v, L0.x.p);
+      EP_CUDA(cudaMemcpyAsync(z, L0.x.p, L0.l * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      return;
+    }
     if (!use_graph_) {
       vcycle(0, v, z);
       return;

@@ -32,8 +32,10 @@ def _problem(name):
     return PM.BansalYaronModel(), g, gu
 
 
-def _worker(rank, world, idq, outq, name):
+def _worker(rank, world, idq, outq, name, replicate_below):
     sys.path.insert(0, ROOT)
+    if replicate_below:
+        os.environ["ECONPDES_REPLICATE_BELOW"] = str(replicate_below)
     import econpdes_b200 as E2
     from econpdes_b200 import _lib as L2
     L2.check(L2.load().econpdes_set_device(rank))
@@ -47,8 +49,12 @@ def _worker(rank, world, idq, outq, name):
     grp.close()
 
 
-@pytest.mark.parametrize("name", ["hjb3d", "hjb3d_odd", "bansal_yaron"])
-def test_two_gpu_slab_matches_single_gpu(name):
+# replicate_below: multigrid levels with at most that many points run replicated on every rank;
+# 0 keeps the default (the test grids then have ONE distributed level), 1500 forces several
+# distributed levels so the distributed transfers and Galerkin passes are exercised too
+@pytest.mark.parametrize("name,replicate_below", [("hjb3d", 0), ("hjb3d", 1500), ("hjb3d_odd", 0),
+                                                  ("hjb3d_odd", 1500), ("bansal_yaron", 0), ("bansal_yaron", 200)])
+def test_two_gpu_slab_matches_single_gpu(name, replicate_below):
     if L.load().econpdes_device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import multiprocessing as mp
@@ -56,7 +62,7 @@ def test_two_gpu_slab_matches_single_gpu(name):
     world = 2
     idqs = [ctx.Queue() for _ in range(world)]
     outq = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, idqs[r], outq, name)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, idqs[r], outq, name, replicate_below)) for r in range(world)]
     for p in procs:
         p.start()
     uid = E.slab.new_unique_id()
