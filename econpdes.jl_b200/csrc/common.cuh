@@ -34,6 +34,22 @@ extern std::atomic<int64_t> g_kernel_launches;
     EP_CUDA(cudaGetLastError());                                 \
   } while (0)
 
+// Phase breakdown of a solve (ECONPDES_PROFILE=1): wall time between stream synchronisations,
+// accumulated per phase name and printed to stderr at the end of Solver::solve.  Off by default
+// (the synchronisations serialise host and device).
+struct Prof {
+  static bool enabled();
+  static void add(const char* name, double ms);
+  static void report(int rank);
+};
+struct ProfScope {
+  const char* name;
+  cudaStream_t s;
+  double t0 = 0.0;
+  ProfScope(const char* n, cudaStream_t st);
+  ~ProfScope();
+};
+
 constexpr int kBlock = 256;
 inline int blocks_for(long long n, int block = kBlock) { return static_cast<int>((n + block - 1) / block); }
 

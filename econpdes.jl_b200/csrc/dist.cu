@@ -1,10 +1,16 @@
 // NCCL binding (run-time, see dist.cuh) and the three communication patterns of the slab path.
 #include "dist.cuh"
 
+#include "common.cuh"
+
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <stdexcept>
 
@@ -134,4 +140,43 @@ void Dist::all_gather(const double* send, double* recv, long long count, cudaStr
   ++ncoll_;
 }
 
+}  // namespace econpdes
+
+// ---- phase profile (common.cuh) ----
+namespace econpdes {
+namespace {
+std::map<std::string, std::pair<double, long>>& prof_table() {
+  static std::map<std::string, std::pair<double, long>> t;
+  return t;
+}
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+bool Prof::enabled() {
+  static const bool on = [] { const char* e = std::getenv("ECONPDES_PROFILE"); return e && e[0] == '1'; }();
+  return on;
+}
+void Prof::add(const char* name, double ms) {
+  auto& e = prof_table()[name];
+  e.first += ms;
+  e.second += 1;
+}
+void Prof::report(int rank) {
+  if (!enabled()) return;
+  for (const auto& kv : prof_table())
+    std::fprintf(stderr, "[econpdes profile rank %d] %-22s %10.3f ms %8ld calls\n", rank, kv.first.c_str(),
+                 kv.second.first, kv.second.second);
+  prof_table().clear();
+}
+ProfScope::ProfScope(const char* n, cudaStream_t st) : name(n), s(st) {
+  if (!Prof::enabled() || name[0] == 0) return;
+  cudaStreamSynchronize(s);
+  t0 = now_ms();
+}
+ProfScope::~ProfScope() {
+  if (!Prof::enabled() || name[0] == 0) return;
+  cudaStreamSynchronize(s);
+  Prof::add(name, now_ms() - t0);
+}
 }  // namespace econpdes

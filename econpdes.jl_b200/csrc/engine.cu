@@ -397,18 +397,21 @@ Norms Solver::read_norms() {
 }
 
 Norms Solver::eval_G(const double* y, double* out) {
+  ProfScope ps("residual G", c_->stream);
   c_->exchange_halo(y);
   ops_->residual(*c_, y, row_spec(nullptr, INFINITY), out, true);
   return read_norms();
 }
 
 Norms Solver::eval_R(const double* y, const double* ypost, double delta, double* out) {
+  ProfScope ps("residual R", c_->stream);
   c_->exchange_halo(y);
   ops_->residual(*c_, y, row_spec(ypost, delta), out, true);
   return read_norms();
 }
 
 void Solver::jacobian(const double* y, const double* ypost, double delta, int eps_policy) {
+  ProfScope ps("jacobian", c_->stream);
   c_->exchange_halo(y);
   ops_->jacobian(*c_, y, row_spec(ypost, delta), eps_policy, planes_.p, nullptr);
 }
@@ -564,6 +567,7 @@ int Solver::solve(const econpdes_options& opt, econpdes_result* res) {
   if (saved.p != nullptr) saved.download(res->saved, saved.n, s);
   EP_CUDA(cudaStreamSynchronize(s));
   res->kernel_launches = g_kernel_launches.load() - launches0;
+  Prof::report(c.dist != nullptr ? c.dist->rank() : 0);
   return rc;
 }
 

@@ -692,7 +692,12 @@ class KrylovSolver final : public LinearSolver {
     sym_.alloc(2 * kMaxDims);
     const char* e = std::getenv("ECONPDES_NO_GRAPH");
     use_graph_ = !(e && e[0] == '1');
-    if (c.dist != nullptr) use_graph_ = false;   // the slab cycle interleaves NCCL calls with its kernels
+    // the slab cycle interleaves NCCL calls with its kernels: NCCL operations are capturable, every
+    // rank captures the same sequence (ECONPDES_DIST_GRAPH=0 replays eagerly instead)
+    if (c.dist != nullptr) {
+      const char* dg = std::getenv("ECONPDES_DIST_GRAPH");
+      if (dg && dg[0] == '0') use_graph_ = false;
+    }
     if (const char* rb = std::getenv("ECONPDES_REPLICATE_BELOW")) replicate_below_ = std::atoll(rb);
   }
   ~KrylovSolver() override {
@@ -703,6 +708,7 @@ class KrylovSolver final : public LinearSolver {
   int solve(const double* planes, const double* b, double* x, const econpdes_options& opt, int* iters,
             double* relres) override {
     setup(planes);
+    ProfScope ps("lin fgmres total", c_.stream);
     return fgmres(b, x, opt, iters, relres);
   }
 
@@ -750,6 +756,7 @@ class KrylovSolver final : public LinearSolver {
   cudaGraphExec_t graph_exec_ = nullptr;
   const double* graph_A_ = nullptr;
   int graph_nlev_ = 0;
+  unsigned long long graph_sig_ = 0;
   int64_t graph_kernels_ = 0;
   bool use_graph_ = true;
   double* h_ = nullptr;
@@ -766,6 +773,7 @@ class KrylovSolver final : public LinearSolver {
   // The operator of the Krylov iteration: on a slab, A couples to the neighbour ranks' edge
   // planes, so the operand is copied into ghosted storage and its halos are exchanged first.
   void spmv_top(const double* x, const double* b, double* y, int mode) {
+    ProfScope ps("lin spmv", c_.stream);
     Level<N>& L0 = *lev_[0];
     if (c_.dist == nullptr) {
       spmv(L0, x, b, y, mode);
@@ -821,6 +829,7 @@ class KrylovSolver final : public LinearSolver {
   // replicating them costs less than their halo exchanges would.
   void setup(const double* planes) {
     cudaStream_t s = c_.stream;
+    ProfScope ps("lin setup", s);
     Dist* dd = c_.dist;
     if (lev_.empty()) {
       auto L0 = std::make_unique<Level<N>>();
@@ -1115,8 +1124,16 @@ class KrylovSolver final : public LinearSolver {
     // ---- distributed level: x, r (and the coarse x) carry ghost planes ----
     Dist& dd = *c_.dist;
     const bool linear = L.to_coarse.type[N - 1] == 1;
+    static const char* kSm[4] = {"vc L0 smooth", "vc L1 smooth", "vc L2 smooth", "vc L3+ smooth"};
+    static const char* kTr[4] = {"vc L0 transfer", "vc L1 transfer", "vc L2 transfer", "vc L3+ transfer"};
+    const bool prof = Prof::enabled() && !use_graph_;
+    const int pl = li < 3 ? li : 3;
     EP_CUDA(cudaMemsetAsync(x - L.plane, 0, (L.l + 2 * L.plane) * sizeof(double), s));
-    smooth(L, b, x, false);   // leaves the ghosts of x current
+    {
+      ProfScope ps(prof ? kSm[pl] : "", prof ? s : nullptr);
+      smooth(L, b, x, false);   // leaves the ghosts of x current
+    }
+    ProfScope* pt = prof ? new ProfScope(kTr[pl], s) : nullptr;
     if (L.box) EP_LAUNCH((k_spmv<N, true>), blocks_for(L.l), kBlock, 0, s, gf, L.A, x, b, L.r.p, 1);
     else EP_LAUNCH((k_spmv<N, false>), blocks_for(L.l), kBlock, 0, s, gf, L.A, x, b, L.r.p, 1);
     // full weighting reaches one fine plane below the slab
@@ -1130,7 +1147,9 @@ class KrylovSolver final : public LinearSolver {
     const double* ec;
     if (Lc.dist) {
       EP_LAUNCH((k_restrict<N>), blocks_for(gcl.l), kBlock, 0, s, transfers_dev_.p + li, gf, gcl, L.r.p, Lc.b.p);
+      delete pt;
       vcycle(li + 1, Lc.b.p, Lc.x.p);
+      pt = prof ? new ProfScope(kTr[pl], s) : nullptr;
       // interpolation reaches one coarse plane above the slab
       if (linear) dd.send_lo_recv_hi(Lc.x.p, Lc.x.p + Lc.l, Lc.plane, s);
       ec = Lc.x.p;
@@ -1142,12 +1161,21 @@ class KrylovSolver final : public LinearSolver {
       cm.world = L.map.world;
       for (int r = 0; r < cm.world; ++r) { cm.first[r] = L.map.first[r] / 2; cm.count[r] = (L.map.count[r] + 1) / 2; }
       gather_slabs(cm, 1, Lc.plane, bloc_.p, Lc.b.p);
-      vcycle(li + 1, Lc.b.p, Lc.x.p);
+      delete pt;
+      {
+        ProfScope ps(prof ? "vc replicated levels" : "", prof ? s : nullptr);
+        vcycle(li + 1, Lc.b.p, Lc.x.p);
+      }
+      pt = prof ? new ProfScope(kTr[pl], s) : nullptr;
       ec = Lc.x.p + cfirst * Lc.plane;   // the plane above the slab is simply the next one
     }
     EP_LAUNCH((k_prolong_add<N>), blocks_for(L.l), kBlock, 0, s, transfers_dev_.p + li, gf, gcl, ec, x);
     halo(L, x);
-    smooth(L, b, x, true);
+    delete pt;
+    {
+      ProfScope ps(prof ? kSm[pl] : "", prof ? s : nullptr);
+      smooth(L, b, x, true);
+    }
   }
 
   // z = V-cycle(v).  The cycle is ~25 small launches per level, launch-latency bound on all but
@@ -1155,17 +1183,23 @@ class KrylovSolver final : public LinearSolver {
   // sizes depend only on the grid shape; per-set-up choices live in device memory) and replayed.
   void precondition(const double* v, double* z) {
     cudaStream_t s = c_.stream;
+    ProfScope ps("lin vcycle", s);
     Level<N>& L0 = *lev_[0];
-    if (L0.dist) {   // the cycle's x carries ghost planes: run it in the level's own buffer
-      vcycle(0, v, L0.x.p);
-      EP_CUDA(cudaMemcpyAsync(z, L0.x.p, L0.l * sizeof(double), cudaMemcpyDeviceToDevice, s));
-      return;
-    }
     if (!use_graph_) {
-      vcycle(0, v, z);
+      if (L0.dist) {   // the cycle's x carries ghost planes: run it in the level's own buffer
+        vcycle(0, v, L0.x.p);
+        EP_CUDA(cudaMemcpyAsync(z, L0.x.p, L0.l * sizeof(double), cudaMemcpyDeviceToDevice, s));
+      } else {
+        vcycle(0, v, z);
+      }
       return;
     }
-    if (graph_exec_ == nullptr || graph_A_ != L0.A || graph_nlev_ != nlev_) {
+    // host-side choices baked into a captured cycle: which levels are distributed and whether
+    // their slab-dimension transfer needs ghost exchanges
+    unsigned long long sig = 0;
+    for (int q = 0; q < nlev_; ++q)
+      sig = sig * 7 + (lev_[q]->dist ? 1 + (lev_[q]->to_coarse.type[N - 1] == 1 ? 1 : 0) : 0);
+    if (graph_exec_ == nullptr || graph_A_ != L0.A || graph_nlev_ != nlev_ || graph_sig_ != sig) {
       if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
       vcycle(0, L0.b.p, L0.x.p);   // uncaptured once: function attributes, allocations
       EP_CUDA(cudaStreamSynchronize(s));
@@ -1186,6 +1220,7 @@ class KrylovSolver final : public LinearSolver {
       cudaGraphDestroy(graph);
       graph_A_ = L0.A;
       graph_nlev_ = nlev_;
+      graph_sig_ = sig;
     }
     EP_CUDA(cudaMemcpyAsync(L0.b.p, v, L0.l * sizeof(double), cudaMemcpyDeviceToDevice, s));
     EP_CUDA(cudaGraphLaunch(graph_exec_, s));
@@ -1196,6 +1231,7 @@ class KrylovSolver final : public LinearSolver {
   void dots(long long n, int j, const double* V, const double* w, double* host_out) {
     // host_out[0..j-1] = <V_q, w>, host_out[j] = <w, w>
     cudaStream_t s = c_.stream;
+    ProfScope ps("lin dots", s);
     const int nb = 148 * 2;
     part_.alloc(static_cast<size_t>(nb) * (restart_alloc_ + 2));
     dots_.alloc(static_cast<size_t>(restart_alloc_ + 2));
