@@ -95,6 +95,7 @@ SYMBOLS = {
     "econpdes_dist_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_void_p)]),
     "econpdes_dist_destroy": (None, [C.c_void_p]),
     "econpdes_dist_collectives": (C.c_int64, [C.c_void_p]),
+    "econpdes_dist_p2p_exchanges": (C.c_int64, [C.c_void_p]),
     "econpdes_slab_range": (C.c_int, [C.c_int64, C.c_int, C.c_int, c_int64_p, c_int64_p]),
     "econpdes_solve_stationary_slab": (C.c_int, [C.c_void_p, C.POINTER(Problem), C.c_int64, C.c_int64,
                                                  C.POINTER(Options), C.POINTER(Result)]),

@@ -315,6 +315,8 @@ void econpdes_dist_destroy(econpdes_dist* d) { delete d; }
 
 int64_t econpdes_dist_collectives(const econpdes_dist* d) { return d && d->dist ? d->dist->collectives() : 0; }
 
+int64_t econpdes_dist_p2p_exchanges(const econpdes_dist* d) { return d && d->dist ? d->dist->p2p_exchanges() : 0; }
+
 int econpdes_slab_range(int64_t size_last, int rank, int world, int64_t* first, int64_t* count) {
   return guarded([&] {
     if (!first || !count || world < 1 || rank < 0 || rank >= world) throw std::invalid_argument("bad rank/world");

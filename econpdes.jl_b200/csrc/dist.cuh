@@ -46,12 +46,30 @@ class Dist {
   // recv[r*count .. (r+1)*count) = rank r's send[0..count)   (device pointers)
   void all_gather(const double* send, double* recv, long long count, cudaStream_t s);
 
-  int64_t collectives() const { return ncoll_; }
+  int64_t collectives() const { return ncoll_; }       // NCCL calls
+  int64_t p2p_exchanges() const { return np2p_; }       // halo exchanges done by k_halo_p2p
+  bool p2p_enabled() const { return box_ != nullptr; }
+
+  // Direct NVLink halo path: every rank exposes a small mailbox (flags + one plane-sized slot per
+  // neighbour) through CUDA IPC; ONE kernel per exchange stores this rank's edge planes into the
+  // neighbours' slots, publishes them with a system-scope flag, waits for the neighbours' flags
+  // and moves the received planes into the ghost storage (dist.cu: k_halo_p2p).  Collective;
+  // `slot_doubles` = largest plane that will be exchanged.  Falls back to NCCL send/recv when
+  // IPC is unavailable or ECONPDES_P2P_HALO=0.
+  void enable_p2p(long long slot_doubles, cudaStream_t s);
+  void check_p2p_error(cudaStream_t s);   // throws if a mailbox wait timed out
 
  private:
+  struct PeerBox;
+  void halo_any(const double* send_lo, const double* send_hi, double* recv_lo, double* recv_hi, long long count,
+                cudaStream_t s);
   int rank_, world_;
   void* comm_ = nullptr;
-  int64_t ncoll_ = 0;
+  int64_t ncoll_ = 0, np2p_ = 0;
+  PeerBox* box_ = nullptr;      // this rank's mailbox (device memory, IPC-exported)
+  PeerBox* box_lo_ = nullptr;   // neighbours' mailboxes mapped into this process
+  PeerBox* box_hi_ = nullptr;
+  long long slot_ = 0;
 };
 
 }  // namespace econpdes

@@ -270,6 +270,7 @@ std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p, Dist* dist, long long s
   const size_t world = dist != nullptr ? static_cast<size_t>(dist->world()) : 1;
   c->gather.alloc(world * kGatherMax);
   EP_CUDA(cudaMallocHost(&c->h_gather, world * kGatherMax * sizeof(double)));
+  if (dist != nullptr) dist->enable_p2p(c->halo, s);   // collective: every rank builds its Ctx at the same point
   EP_CUDA(cudaStreamSynchronize(s));
   return c;
 }
@@ -567,6 +568,7 @@ int Solver::solve(const econpdes_options& opt, econpdes_result* res) {
   if (saved.p != nullptr) saved.download(res->saved, saved.n, s);
   EP_CUDA(cudaStreamSynchronize(s));
   res->kernel_launches = g_kernel_launches.load() - launches0;
+  if (c.dist != nullptr) c.dist->check_p2p_error(s);
   Prof::report(c.dist != nullptr ? c.dist->rank() : 0);
   return rc;
 }

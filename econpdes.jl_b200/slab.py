@@ -66,6 +66,10 @@ class SlabGroup:
     def collectives(self) -> int:
         return int(L.load().econpdes_dist_collectives(self._h))
 
+    @property
+    def p2p_exchanges(self) -> int:
+        return int(L.load().econpdes_dist_p2p_exchanges(self._h))
+
     def close(self):
         if self._h:
             L.load().econpdes_dist_destroy(self._h)

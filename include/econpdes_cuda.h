@@ -231,6 +231,10 @@ int econpdes_dist_unique_id(uint8_t* id /* [ECONPDES_UNIQUE_ID_BYTES] */);
 int econpdes_dist_create(int rank, int world, const uint8_t* id, econpdes_dist** out);
 void econpdes_dist_destroy(econpdes_dist* d);
 int64_t econpdes_dist_collectives(const econpdes_dist* d); /* NCCL calls issued so far */
+/* halo exchanges done by the library's own NVLink kernel (k_halo_p2p: peer-memory stores + system-scope
+ * flags through CUDA IPC mailboxes) instead of NCCL send/recv; 0 if IPC is unavailable or
+ * ECONPDES_P2P_HALO=0 */
+int64_t econpdes_dist_p2p_exchanges(const econpdes_dist* d);
 /* balanced partition of dimension N-1 in units of two planes (slabs start on even indices so the
  * multigrid hierarchy coarsens inside a slab); host-only */
 int econpdes_slab_range(int64_t size_last, int rank, int world, int64_t* first, int64_t* count);

@@ -52,6 +52,7 @@ def main():
                           "n_linear_iters": res.n_linear_iters, "device_ms_max": dev_ms, "wall_ms_max": wall_ms,
                           "newton_solves_per_sec": res.n_newton / (dev_ms * 1e-3),
                           "kernel_launches_rank0": res.kernel_launches, "nccl_calls_rank0": grp.collectives,
+                          "p2p_halo_exchanges_rank0": grp.p2p_exchanges,
                           "log": [(r["iter"], "%.2e" % r["delta"], "%.2e" % r["residual"], r["status"],
                                    r["newton_iters"], r["linear_iters"]) for r in res.log],
                           "v_range": [lo.item(), hi.item()]}), flush=True)
