@@ -189,6 +189,11 @@ def run_ours(args):
     h2d = int(params.nbytes + grids.nbytes + guess.nbytes)
     d2h = int(tsol.numpy().nbytes + trn.numpy().nbytes + ex.nbytes + no.nbytes + nn.nbytes)
 
+    # ---- config C5: ONE 256^3 grid, slab-decomposed over the same ranks (strong scaling) ----
+    c5 = None
+    if not args.no_c5:
+        c5 = c5_slab(args, dist, rank, world, local, allmax)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -224,6 +229,8 @@ def run_ours(args):
                      "note": "fused on-chip solve: algorithmic bytes never reach HBM; DRAM traffic is grid+guess in, solution out"},
         "pdesolves_per_sec": B * world / (ms_per_step * 1e-3),
     }
+    if c5 is not None:
+        line["c5_slab"] = c5
     if world == 1 and not args.no_kernels:
         # residual / Jacobian / SpMV / V-cycle of the generic engine on the C3 and C5 shapes
         sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -234,6 +241,35 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def c5_slab(args, dist, rank, world, local, allmax):
+    """BASELINE.json configs[4]: 3-state HJB on a 256^3 grid, slab-decomposed across the ranks
+    (halo planes over NVLink, all-gathered Krylov dot products / norms).  Fixed total work:
+    "scaling": "strong".  One warm-up solve (graph capture, NCCL connections), one timed."""
+    import econpdes_b200 as E
+    from econpdes_b200 import examples as EX
+    from econpdes_b200 import models as PM
+    n = args.c5_n
+    if world > 1:
+        grp = E.SlabGroup.from_torch(dist, local)
+    else:
+        grp = E.SlabGroup(0, 1, E.slab.new_unique_id())
+    g, _ = EX.hjb3d_grid(n)
+    first, count = E.slab_range(n, rank, world)
+    guess = {"v": np.zeros((n, n, count))}
+    res = None
+    for _ in range(2):
+        res = E.pdesolve_slab(PM.Hjb3dSynth(), g, guess, grp)
+    ms = allmax(res.device_ms)
+    out = {"workload": f"C5 synthetic 3-state HJB, {n}^3 grid, one pdesolve", "n_gpus": world, "scaling": "strong",
+           "ms_per_pdesolve": ms, "newton_solves": res.n_newton, "newton_solves_per_sec": res.n_newton / (ms * 1e-3),
+           "outer_steps": res.n_outer, "krylov_iterations": res.n_linear_iters, "converged": bool(res.converged),
+           "residual_norm": res.residual_norm, "kernel_launches_rank0": res.kernel_launches,
+           "nccl_calls_rank0": grp.collectives, "p2p_halo_exchanges_rank0": grp.p2p_exchanges,
+           "decomposition": f"{world} slab(s) of {count} planes along the slowest dimension"}
+    grp.close()
+    return out
 
 
 def _c_oracle_time(first, count, threads):
@@ -299,6 +335,8 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernels", action="store_true", help="skip the grid-kernel roofline leg")
+    ap.add_argument("--no-c5", action="store_true", help="skip the slab-decomposed 3-D solve")
+    ap.add_argument("--c5-n", type=int, default=256, help="points per axis of the C5 grid")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

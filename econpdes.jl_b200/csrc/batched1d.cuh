@@ -100,9 +100,9 @@ __global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args)
   GridView<1> gv;
   gv.x[0] = xg; gv.S[0] = S; gv.stride[0] = 1; gv.l = S;
   long long idx[1] = {act ? i : 0};
-  PointGeom<1> g;
+  PointGeom<1, 1> g;   // reciprocals of the spacings once per problem, reused by every stencil evaluation
   double st[1];
-  load_geom<1>(gv, idx, g, st);
+  load_geom(gv, idx, g, st);
   double bl[1][1] = {{0.0}}, bh[1][1] = {{0.0}};
   __syncthreads();
   typename M::Pre pre;   // state-only part of the model, once per problem

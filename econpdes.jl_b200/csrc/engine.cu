@@ -10,6 +10,7 @@
 #include <cstring>
 #include <limits>
 #include <tuple>
+#include <vector>
 
 #include "batched1d.cuh"
 #include "tridiag.cuh"
@@ -208,7 +209,13 @@ std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p, Dist* dist, long long s
   for (int i = 0; i < c->nparams; ++i) c->prm.v[i] = p->params[i];
   EP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   cudaStream_t s = c->stream;
-  for (int d = 0; d < c->N; ++d) c->grid[d].upload(p->grid[d], static_cast<size_t>(c->S[d]), s);
+  for (int d = 0; d < c->N; ++d) {
+    c->grid[d].upload(p->grid[d], static_cast<size_t>(c->S[d]), s);
+    std::vector<double> tab(static_cast<size_t>(kGeomRows) * c->S[d]);
+    make_geom_table(p->grid[d], c->S[d], tab.data());
+    c->geomtab[d].upload(tab.data(), tab.size(), s);
+    EP_CUDA(cudaStreamSynchronize(s));
+  }
   c->guess.upload(p->guess, static_cast<size_t>(c->n), s);
   if (p->bc != nullptr) {
     bool any = false;

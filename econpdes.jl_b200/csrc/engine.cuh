@@ -71,7 +71,7 @@ struct Ctx {
   DevBuf<double> gather;                       // [world][kGatherMax] landing area of small all-gathers
   double* h_gather = nullptr;                  // pinned copy
   ParamPack prm{};
-  DevBuf<double> grid[kMaxDims], guess, bc, lb, ub, delta_rel;
+  DevBuf<double> grid[kMaxDims], geomtab[kMaxDims], guess, bc, lb, ub, delta_rel;
   DevBuf<unsigned char> is_alg;
   bool has_bounds = false, has_delta_vec = false, all_delta_inf = false;
   double delta_base = 1.0;  // min finite |Δ_i| of a vector Δ (finiteschemesolve.jl:394)
@@ -89,6 +89,7 @@ struct Ctx {
     long long st = 1;
     for (int d = 0; d < NN; ++d) {
       gv.x[d] = grid[d].p;
+      gv.tab[d] = geomtab[d].p;
       gv.S[d] = S[d];
       gv.stride[d] = st;
       st *= S[d];

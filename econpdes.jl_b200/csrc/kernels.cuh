@@ -42,18 +42,24 @@ __device__ __forceinline__ RowTerms make_row_terms(const RowSpec& rs, long long 
   return t;
 }
 
-template <class M>
+// RECIP: see PointGeom (stencil.cuh)
+// single-evaluation sweeps: tabulated reciprocals pay off from three dimensions on (15+ stencil
+// quotients per point); below that the extra registers cost more than the divisions (measured)
+template <int N>
+constexpr int kSweepRecip = N >= 3 ? 1 : 0;
+
+template <class M, int RECIP>
 struct PointLoad {
   static constexpr int N = M::N, F = M::F, K = ipow3(M::N);
   long long idx[N];
-  PointGeom<N> g;
+  PointGeom<N, RECIP> g;
   double st[N];
   double w[F][K], bl[F][N], bh[F][N];
   typename M::Pre pre;
   __device__ __forceinline__ void load(const GridView<N>& gv, long long pt, const double* __restrict__ y,
                                        const double* __restrict__ bc, const double* prm) {
     unravel<N>(pt, gv, idx);
-    load_geom<N>(gv, idx, g, st);
+    load_geom(gv, idx, g, st);
     M::prepare(prm, st, pre);
 #pragma unroll
     for (int f = 0; f < F; ++f) {
@@ -73,7 +79,7 @@ __global__ void __launch_bounds__(kBlock) k_residual(GridView<M::N> gv, ParamPac
   double s = 0.0, m = 0.0;
   int nanf = 0;
   if (pt < gv.l) {
-    PointLoad<M> P;
+    PointLoad<M, kSweepRecip<M::N>> P;
     P.load(gv, pt, y, bc, prm.v);
     double o[F];
     eval_point<M, false>(P.pre, P.g, P.w, P.bl, P.bh, o, nullptr);
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(kBlock) k_jacobian(GridView<M::N> gv, ParamPac
   constexpr int F = M::F;
   const long long pt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (pt >= gv.l) return;
-  PointLoad<M> P;
+  PointLoad<M, M::N >= 3 ? (M::USES_CROSS ? 2 : 1) : 0> P;   // see kSweepRecip: 2-D kernels are register-bound
   P.load(gv, pt, y, bc, prm.v);
   RowTerms rt[F];
 #pragma unroll
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(kBlock) k_saved(GridView<M::N> gv, ParamPack p
                                                   const double* __restrict__ bc, double* __restrict__ saved) {
   const long long pt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (pt >= gv.l) return;
-  PointLoad<M> P;
+  PointLoad<M, kSweepRecip<M::N>> P;
   P.load(gv, pt, y, bc, prm.v);
   double o[M::F], sv[M::NSAVED > 0 ? M::NSAVED : 1];
   eval_point<M, true>(P.pre, P.g, P.w, P.bl, P.bh, o, sv);

@@ -29,7 +29,12 @@ struct GridView {
   long long stride[N];
   long long l;        // number of grid points owned (= prod S on a single device)
   long long off = 0;  // global index of the first owned entry of dimension N-1
+  // optional per-dimension geometry table [kGeomRows][S_d]: dm, dp, d, 1/dp, 1/dm, 1/(dp d),
+  // 1/(dm d), 1/(dp dm) -- built once per grid (make_geom_table), so a sweep reads eight
+  // L1-resident values per dimension instead of re-deriving them with five divisions
+  const double* tab[N] = {};
 };
+constexpr int kGeomRows = 8;
 
 // Stencil shapes: the full clipped +-1 box (coloring.jl:18-35) or, for models that never
 // read a cross derivative, its star subset (centre + 2N axial neighbours).
@@ -59,23 +64,45 @@ EP_HD void unravel(long long pt, const GridView<N>& gv, long long* idx) {
   idx[N - 1] = pt + gv.off;   // global index along the slab dimension
 }
 
-template <int N>
-EP_HD void load_geom(const GridView<N>& gv, const long long* idx, PointGeom<N>& g, double* state) {
+template <int N, int RECIP>
+EP_HD void load_geom(const GridView<N>& gv, const long long* idx, PointGeom<N, RECIP>& g, double* state) {
 #pragma unroll
   for (int d = 0; d < N; ++d) {
-    spacing(gv.x[d], idx[d], gv.S[d], g.dm[d], g.dp[d], g.d[d]);
     g.lo[d] = idx[d] == 0;
     g.hi[d] = idx[d] == gv.S[d] - 1;
     state[d] = gv.x[d][idx[d]];
+    if (RECIP >= 1 && gv.tab[d] != nullptr) {
+      const double* t = gv.tab[d] + idx[d];
+      const long long S = gv.S[d];
+      g.dm[d] = t[0]; g.dp[d] = t[S]; g.d[d] = t[2 * S];
+      g.rdp[d] = t[3 * S]; g.rdm[d] = t[4 * S]; g.rdpd[d] = t[5 * S]; g.rdmd[d] = t[6 * S]; g.rdpm[d] = t[7 * S];
+      g.dpd[d] = g.dp[d] * g.d[d];
+      g.dmd[d] = g.dm[d] * g.d[d];
+      g.dpm[d] = g.dp[d] * g.dm[d];
+    } else {
+      spacing(gv.x[d], idx[d], gv.S[d], g.dm[d], g.dp[d], g.d[d]);
+      finish_axis(g, d);
+    }
   }
-  finish_geom<N>(g);
+  finish_geom(g);
+}
+
+// Host side of the table (plain IEEE arithmetic, identical to the device's).
+inline void make_geom_table(const double* x, long long S, double* tab /* [kGeomRows][S] */) {
+  for (long long i = 0; i < S; ++i) {
+    PointGeom<1, 1> g;
+    spacing(x, i, S, g.dm[0], g.dp[0], g.d[0]);
+    finish_axis(g, 0);
+    tab[i] = g.dm[0]; tab[S + i] = g.dp[0]; tab[2 * S + i] = g.d[0];
+    tab[3 * S + i] = g.rdp[0]; tab[4 * S + i] = g.rdm[0]; tab[5 * S + i] = g.rdpd[0];
+    tab[6 * S + i] = g.rdmd[0]; tab[7 * S + i] = g.rdpm[0];
+  }
 }
 
 // Gather the 3^N box of unknown f around point pt (slots outside the grid are never read
 // by `differentiate`; they are filled with the centre value).
-template <int N>
-EP_HD void load_box(const double* __restrict__ yf, long long pt, const GridView<N>& gv, const PointGeom<N>& g,
-                    double* w) {
+template <int N, class G>
+EP_HD void load_box(const double* __restrict__ yf, long long pt, const GridView<N>& gv, const G& g, double* w) {
   constexpr int K = ipow3(N);
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -92,9 +119,9 @@ EP_HD void load_box(const double* __restrict__ yf, long long pt, const GridView<
 }
 
 // bc[i1.., (first|last) along d, ..iN, f] keeping the other indices (derivatives.jl:27-32).
-template <int N>
+template <int N, class G>
 EP_HD void load_bc(const double* __restrict__ bcf, long long pt, const long long* idx, const GridView<N>& gv,
-                   const PointGeom<N>& g, double* bc_lo, double* bc_hi) {
+                   const G& g, double* bc_lo, double* bc_hi) {
 #pragma unroll
   for (int d = 0; d < N; ++d) {
     bc_lo[d] = 0.0;
@@ -133,13 +160,13 @@ EP_HD double apply_row_terms(double g, double y, const RowTerms& t) {
 }
 
 // Residual of all F unknowns at one point from the boxes w[f][3^N].
-template <class M, bool SAVE>
-EP_HD void eval_point(const typename M::Pre& pre, const PointGeom<M::N>& g,
+template <class M, bool SAVE, class G>
+EP_HD void eval_point(const typename M::Pre& pre, const G& g,
                       const double (*w)[ipow3(M::N)], const double (*bc_lo)[M::N], const double (*bc_hi)[M::N],
                       double* out, double* sv) {
   Deriv<M::N> u[M::F];
 #pragma unroll
-  for (int f = 0; f < M::F; ++f) differentiate<M::N>(w[f], g, bc_lo[f], bc_hi[f], u[f]);
+  for (int f = 0; f < M::F; ++f) differentiate(w[f], g, bc_lo[f], bc_hi[f], u[f]);
   M::template eval<SAVE>(pre, u, out, sv);
 }
 
@@ -175,8 +202,8 @@ EP_HD int ncolors_grid(const GridView<N>& gv) {
 // entries outside the grid).  r0 returns R(pt) itself (the unperturbed residual).
 // With HAVE_R0 the caller already holds R(pt) in r0 (FiniteDiff re-evaluates f(x); the
 // value is identical, so kernels that kept it skip that evaluation).
-template <class M, bool BOX, bool HAVE_R0 = false, class Emit>
-EP_HD void jacobian_point(const typename M::Pre& pre, const PointGeom<M::N>& g, const long long* idx,
+template <class M, bool BOX, bool HAVE_R0 = false, class G, class Emit>
+EP_HD void jacobian_point(const typename M::Pre& pre, const G& g, const long long* idx,
                           const GridView<M::N>& gv, double (*w)[ipow3(M::N)], const double (*bc_lo)[M::N],
                           const double (*bc_hi)[M::N], const RowTerms* rt, const double* eps_table,
                           int eps_per_column, double* r0, Emit emit) {

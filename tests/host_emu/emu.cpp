@@ -26,7 +26,9 @@ GridView<M::N> make_grid(const long long* S, const double* const* grids) {
   return gv;
 }
 
-template <class M>
+int g_recip = 0;   // PointGeom RECIP mode under test (all modes must give the same bits)
+
+template <class M, int RECIP>
 int residual(const long long* S, const double* const* grids, const double* prm, const double* y, const double* bc,
              double* out, double* saved) {
   constexpr int N = M::N, F = M::F, K = ipow3(N);
@@ -34,9 +36,9 @@ int residual(const long long* S, const double* const* grids, const double* prm, 
   for (long long pt = 0; pt < gv.l; ++pt) {
     long long idx[N];
     unravel<N>(pt, gv, idx);
-    PointGeom<N> g;
+    PointGeom<N, RECIP> g;
     double st[N];
-    load_geom<N>(gv, idx, g, st);
+    load_geom(gv, idx, g, st);
     double w[F][K], bl[F][N], bh[F][N];
     for (int f = 0; f < F; ++f) {
       load_box<N>(y + f * gv.l, pt, gv, g, w[f]);
@@ -53,7 +55,7 @@ int residual(const long long* S, const double* const* grids, const double* prm, 
   return 0;
 }
 
-template <class M, bool BOX>
+template <class M, bool BOX, int RECIP>
 int jacobian(const long long* S, const double* const* grids, const double* prm, const double* y, const double* bc,
              const double* ypost, double delta, const double* eps_table, int eps_per_column, double* planes,
              double* r0out) {
@@ -62,9 +64,9 @@ int jacobian(const long long* S, const double* const* grids, const double* prm, 
   for (long long pt = 0; pt < gv.l; ++pt) {
     long long idx[N];
     unravel<N>(pt, gv, idx);
-    PointGeom<N> g;
+    PointGeom<N, RECIP> g;
     double st[N];
-    load_geom<N>(gv, idx, g, st);
+    load_geom(gv, idx, g, st);
     double w[F][K], bl[F][N], bh[F][N];
     RowTerms rt[F];
     for (int f = 0; f < F; ++f) {
@@ -92,6 +94,8 @@ int jacobian(const long long* S, const double* const* grids, const double* prm, 
 
 extern "C" {
 
+void emu_set_recip(int mode) { g_recip = mode; }
+
 int emu_model_count() {
   int n = 0;
 #define X(M) ++n;
@@ -111,7 +115,11 @@ int emu_model_id(const char* name) {
 int emu_residual(int model_id, const long long* S, const double* const* grids, const double* prm, const double* y,
                  const double* bc, double* out, double* saved) {
   int id = 0;
-#define X(M) if (id++ == model_id) return residual<M>(S, grids, prm, y, bc, out, saved);
+#define X(M)                                                                        \
+  if (id++ == model_id)                                                             \
+    return g_recip == 0 ? residual<M, 0>(S, grids, prm, y, bc, out, saved)          \
+         : g_recip == 1 ? residual<M, 1>(S, grids, prm, y, bc, out, saved)          \
+                        : residual<M, 2>(S, grids, prm, y, bc, out, saved);
   ECONPDES_FOR_EACH_MODEL(X)
 #undef X
   return -1;
@@ -124,8 +132,10 @@ int emu_jacobian(int model_id, int box, const long long* S, const double* const*
   int id = 0;
 #define X(M)                                                                                                  \
   if (id++ == model_id)                                                                                       \
-    return box ? jacobian<M, true>(S, grids, prm, y, bc, ypost, delta, eps_table, eps_per_column, planes, r0) \
-               : jacobian<M, false>(S, grids, prm, y, bc, ypost, delta, eps_table, eps_per_column, planes, r0);
+    return box ? (g_recip == 0 ? jacobian<M, true, 0>(S, grids, prm, y, bc, ypost, delta, eps_table, eps_per_column, planes, r0) \
+                               : jacobian<M, true, 2>(S, grids, prm, y, bc, ypost, delta, eps_table, eps_per_column, planes, r0)) \
+               : (g_recip == 0 ? jacobian<M, false, 0>(S, grids, prm, y, bc, ypost, delta, eps_table, eps_per_column, planes, r0) \
+                               : jacobian<M, false, 2>(S, grids, prm, y, bc, ypost, delta, eps_table, eps_per_column, planes, r0));
   ECONPDES_FOR_EACH_MODEL(X)
 #undef X
   return -1;

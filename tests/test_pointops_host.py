@@ -119,3 +119,44 @@ def test_fused_jacobian_matches_colored_fd(case, delta):
         full, _ = EU.jacobian_planes(pm, grids, y, ypost, delta, eps, True)
         nz_full = EU.planes_to_csc(full, S, F, True, cache.colptr, cache.rowval)
         np.testing.assert_array_equal(nz_full, nz_got)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_reciprocal_quotients_give_the_same_bits(case):
+    """stencil.cuh forms the stencils' quotients either by IEEE division (RECIP 0) or from
+    reciprocals of the grid-only divisors with Markstein's correction step (RECIP 1: per-axis,
+    RECIP 2: also the cross-derivative divisors).  All modes must agree to the last bit, on
+    uniform and non-uniform grids and with non-zero boundary derivatives."""
+    _, pm, om, g, gu = case
+    grids = list(g.values())
+    # non-uniform variant of the grid: monotone warp of each axis
+    warped = [x[0] + (x[-1] - x[0]) * ((x - x[0]) / (x[-1] - x[0])) ** 1.7 for x in grids]
+    lib = EU.lib()
+    for gs in (grids, warped):
+        for seed in (1, 2, 3):
+            y = _perturbed(gu, seed)
+            bc = 0.3 * np.random.default_rng(seed).uniform(-1, 1, y.shape)
+            outs = []
+            for mode in (0, 1, 2):
+                lib.emu_set_recip(mode)
+                outs.append(EU.residual(pm, gs, y, bc=bc))
+            lib.emu_set_recip(0)
+            np.testing.assert_array_equal(outs[0], outs[1])
+            np.testing.assert_array_equal(outs[0], outs[2])
+
+
+def test_reciprocal_jacobian_planes_give_the_same_bits():
+    g, gu, prm = OM.hjb3d_problem(7)
+    pm = PM.Hjb3dSynth(**prm)
+    grids = list(g.values())
+    y = _perturbed({"v": 20.0 + np.zeros((7, 7, 7))})
+    ypost = _perturbed({"v": 20.0 + np.zeros((7, 7, 7))}, seed=5)
+    eps = np.full(27, 3e-8)
+    lib = EU.lib()
+    outs = []
+    for mode in (0, 2):
+        lib.emu_set_recip(mode)
+        outs.append(EU.jacobian_planes(pm, grids, y, ypost, 1.7, eps, True))
+    lib.emu_set_recip(0)
+    for a, b in zip(outs[0], outs[1]):
+        np.testing.assert_array_equal(a, b)
