@@ -255,11 +255,12 @@ int econpdes_bench_kernels(econpdes_handle* h, const double* y, int reps, double
     };
     const ModelOps* ops = model_ops(c.model_id);
     RowSpec g{};   // R = G
-    g.ypost = nullptr; g.delta = INFINITY; g.delta_rel = nullptr; g.is_alg = nullptr; g.lb = nullptr; g.ub = nullptr;
+    g.ypost = nullptr; g.delta = INFINITY; g.rdelta = 0.0; g.delta_rel = nullptr; g.is_alg = nullptr; g.lb = nullptr; g.ub = nullptr;
     g.has_bounds = 0;
     RowSpec r = g;
     r.ypost = c.guess.p;
     r.delta = 1.0;
+    r.rdelta = 1.0;
     ms_out[0] = timed([&] { ops->residual(c, h->a.p, g, h->b.p, false); });
     ms_out[1] = timed([&] { ops->residual(c, h->a.p, r, h->b.p, true); });
     ms_out[2] = timed([&] { ops->jacobian(c, h->a.p, r, ECONPDES_EPS_FINITEDIFF_COLOR_NORM, sv.planes(), nullptr); });

@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args)
     RowTerms rt[1];
     rt[0].implicit = true; rt[0].has_bounds = false; rt[0].ypost = ypost; rt[0].delta = delta;
     rt[0].is_alg = false; rt[0].lb = 0.0; rt[0].ub = 0.0;
+    rt[0].rdelta = isfinite(delta) ? 1.0 / delta : 0.0;   // once per Newton solve
     y = ypost;
     Gy = Gpost;
     double R = act ? apply_row_terms(Gy, y, rt[0]) : 0.0;
@@ -194,10 +195,21 @@ __global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args)
       s3[1] = ci == 1 ? q : 0.0;
       s3[2] = ci == 2 ? q : 0.0;
       block_reduce_mixed<3, 0>(s3, m0, red);
-      double eps_table[3];   // FiniteDiff: sqrt(eps)*max(1, sqrt(||x .* mask_c||_2))
-      eps_table[0] = color_epsilon_from_sumsq(s3[0]);
-      eps_table[1] = color_epsilon_from_sumsq(s3[1]);
-      eps_table[2] = color_epsilon_from_sumsq(s3[2]);
+      // FiniteDiff: sqrt(eps)*max(1, sqrt(||x .* mask_c||_2)).  Lanes 0..2 of every warp turn one
+      // color each into its step and the step's reciprocal (two square roots and a division,
+      // executed once per warp instead of three times), then broadcast.
+      double eps_table[3], reps_table[3];
+      {
+        const int lane = i & 31;
+        const double mine = lane == 0 ? s3[0] : (lane == 1 ? s3[1] : s3[2]);
+        const double e = color_epsilon_from_sumsq(mine);
+        const double re = 1.0 / e;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          eps_table[c] = __shfl_sync(0xffffffffu, e, c);
+          reps_table[c] = __shfl_sync(0xffffffffu, re, c);
+        }
+      }
       double ja = 0.0, jb = 1.0, jc = 0.0;
       if (act) {
         double w[1][3] = {{ysh[i], ysh[i + 1], ysh[i + 2]}};
@@ -206,7 +218,7 @@ __global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args)
                                        opt.eps_policy == ECONPDES_EPS_PER_COLUMN, r0,
                                        [&](int k, int, int, double v) {
                                          if (k == 0) jb = v; else if (k == 1) ja = v; else jc = v;
-                                       });
+                                       }, reps_table);
       }
       const double sol = block_pcr_solve(ja, jb, jc, act ? R : 0.0, i, S, pcr);
       const bool bad = act && !isfinite(sol);

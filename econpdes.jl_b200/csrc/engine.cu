@@ -383,6 +383,7 @@ RowSpec Solver::row_spec(const double* ypost, double delta) const {
   RowSpec rs;
   rs.ypost = ypost;
   rs.delta = delta;
+  rs.rdelta = (ypost != nullptr && std::isfinite(delta)) ? 1.0 / delta : 0.0;
   rs.delta_rel = (ypost != nullptr && c_->has_delta_vec && !c_->all_delta_inf && std::isfinite(delta)) ? c_->delta_rel.p : nullptr;
   rs.is_alg = c_->is_alg.p;
   rs.lb = c_->lb.p;

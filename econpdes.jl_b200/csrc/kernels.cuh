@@ -23,6 +23,7 @@ struct ParamPack {
 struct RowSpec {
   const double* ypost;      // nullptr: R = G
   double delta;             // stepper.Δ (already signed when delta_rel == nullptr)
+  double rdelta;            // RN(1/delta) for a finite scalar delta (set by the host), else 0
   const double* delta_rel;  // nullptr or per-row signed profile Δrel (finiteschemesolve.jl:393-399)
   const unsigned char* is_alg;
   const double* lb;
@@ -36,6 +37,7 @@ __device__ __forceinline__ RowTerms make_row_terms(const RowSpec& rs, long long 
   t.has_bounds = rs.has_bounds != 0;
   t.ypost = t.implicit ? rs.ypost[j] : 0.0;
   t.delta = rs.delta_rel != nullptr ? rs.delta * rs.delta_rel[j] : rs.delta;
+  t.rdelta = rs.delta_rel != nullptr ? 0.0 : rs.rdelta;
   t.is_alg = rs.is_alg != nullptr ? rs.is_alg[j] != 0 : false;
   t.lb = (t.has_bounds && rs.lb != nullptr) ? rs.lb[j] : -INFINITY;
   t.ub = (t.has_bounds && rs.ub != nullptr) ? rs.ub[j] : INFINITY;

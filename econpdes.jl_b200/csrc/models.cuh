@@ -83,9 +83,12 @@ struct CampbellCochrane : ModelDefaults {
   EP_HD static void eval(const Pre& c, const Deriv<1>* u, double* out, double*) {
     const double p = u[0].v, pss = u[0].dd[0];
     const double ps = (c.mus_eff >= 0) ? u[0].up[0] : u[0].dn[0];
-    const double sigp = ps / p * c.sigs;
-    const double mup = ps / p * c.mus + 0.5 * pss / p * c.sigs2;
-    out[0] = -p * (1 / p + c.mu + mup + sigp * c.sigma - c.r - c.kap * (c.sigma + sigp));
+    // one IEEE reciprocal of p; the other quotients by p reuse it (mdiv: same bits as `/`)
+    const double rp = 1 / p;
+    const double ps_p = mdiv(ps, p, rp);
+    const double sigp = ps_p * c.sigs;
+    const double mup = ps_p * c.mus + mdiv(0.5 * pss, p, rp) * c.sigs2;
+    out[0] = -p * (rp + c.mu + mup + sigp * c.sigma - c.r - c.kap * (c.sigma + sigp));
   }
 };
 
@@ -118,15 +121,17 @@ struct BansalYaron : ModelDefaults {
     const double p = u[0].v;
     const double pmu = (c.mumu >= 0) ? u[0].up[0] : u[0].dn[0];
     const double pv = (c.muv >= 0) ? u[0].up[1] : u[0].dn[1];
-    const double sigp_Zmu = pmu / p * c.sigmu;
-    const double sigp_Zv = pv / p * c.sigv;
+    const double rp = 1 / p;   // the other quotients by p reuse it (mdiv: same bits as `/`)
+    const double pmu_p = mdiv(pmu, p, rp), pv_p = mdiv(pv, p, rp);
+    const double sigp_Zmu = pmu_p * c.sigmu;
+    const double sigp_Zv = pv_p * c.sigv;
     const double sigp2 = sigp_Zmu * sigp_Zmu + sigp_Zv * sigp_Zv;
-    const double mup = pmu / p * c.mumu + pv / p * c.muv + 0.5 * u[0].dd[0] / p * c.sigmu2 +
-                       0.5 * u[0].dd[1] / p * c.sigv2;
+    const double mup = pmu_p * c.mumu + pv_p * c.muv + mdiv(0.5 * u[0].dd[0], p, rp) * c.sigmu2 +
+                       mdiv(0.5 * u[0].dd[1], p, rp) * c.sigv2;
     const double kap_Zmu = c.cz * sigp_Zmu;
     const double kap_Zv = c.cz * sigp_Zv;
     const double r = c.r_base - c.cs * sigp2;
-    out[0] = -p * (1 / p + c.muc + mup - r - c.kzc_sigc - kap_Zmu * sigp_Zmu - kap_Zv * sigp_Zv);
+    out[0] = -p * (rp + c.muc + mup - r - c.kzc_sigc - kap_Zmu * sigp_Zmu - kap_Zv * sigp_Zv);
   }
 };
 

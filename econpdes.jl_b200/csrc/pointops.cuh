@@ -143,12 +143,14 @@ struct RowTerms {
   bool has_bounds; // min(max(R, y-ub), y-lb)
   double ypost, delta, lb, ub;
   bool is_alg;
+  double rdelta = 0.0;  // RN(1/delta) when the caller formed it once for many rows (finite delta only), else 0
 };
 
 EP_HD double apply_row_terms(double g, double y, const RowTerms& t) {
   double r = g;
   // `.!is_algebraic .* (ypost .- y) ./ Δ`: Bool true is an exact 1, false a strong zero
-  if (t.implicit && !t.is_alg) r = r - (t.ypost - y) / t.delta;
+  if (t.implicit && !t.is_alg)
+    r = r - (t.rdelta != 0.0 ? mdiv(t.ypost - y, t.delta, t.rdelta) : (t.ypost - y) / t.delta);
   if (t.has_bounds) {
     const double a = y - t.ub, b = y - t.lb;
     double m = r > a ? r : a;      // max(r, y-ub)   (NaN in r propagates like Julia's max)
@@ -206,7 +208,7 @@ template <class M, bool BOX, bool HAVE_R0 = false, class G, class Emit>
 EP_HD void jacobian_point(const typename M::Pre& pre, const G& g, const long long* idx,
                           const GridView<M::N>& gv, double (*w)[ipow3(M::N)], const double (*bc_lo)[M::N],
                           const double (*bc_hi)[M::N], const RowTerms* rt, const double* eps_table,
-                          int eps_per_column, double* r0, Emit emit) {
+                          int eps_per_column, double* r0, Emit emit, const double* reps_table = nullptr) {
   constexpr int N = M::N, F = M::F;
   constexpr int C = (ipow3(N) - 1) / 2;
   using St = Stencil<N, BOX>;
@@ -237,12 +239,13 @@ EP_HD void jacobian_point(const typename M::Pre& pre, const G& g, const long lon
         continue;
       }
       const double saved = w[fin][slot];
-      double eps;
+      double eps, reps = 0.0;   // reps: RN(1/eps) when the caller tabulated it with the color steps
       if (eps_per_column) {
         const double a = fabs(saved);
         eps = kSqrtEps * (a > 1.0 ? a : 1.0);
       } else {
         eps = eps_table[color + fin * ncg];
+        if (reps_table != nullptr) reps = reps_table[color + fin * ncg];
       }
       w[fin][slot] = saved + eps;
       double g1[F];
@@ -250,7 +253,7 @@ EP_HD void jacobian_point(const typename M::Pre& pre, const G& g, const long lon
 #pragma unroll
       for (int fout = 0; fout < F; ++fout) {
         const double r1 = apply_row_terms(g1[fout], w[fout][C], rt[fout]);
-        emit(k, fin, fout, (r1 - r0[fout]) / eps);
+        emit(k, fin, fout, reps != 0.0 ? mdiv(r1 - r0[fout], eps, reps) : (r1 - r0[fout]) / eps);
       }
       w[fin][slot] = saved;
     }

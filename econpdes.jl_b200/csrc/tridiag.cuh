@@ -178,6 +178,19 @@ __global__ void __launch_bounds__(kBlock) k_pcr_final(long long n, PcrSystem in,
 // Used by the fused batched kernel; a, b, c, d are this thread's row, sh is shared scratch
 // of 8 * blockDim.x doubles (double-buffered a, b, c, d).  Rows >= n behave as identity
 // rows.  Returns x_i.  All threads of the block must call it.
+// 1/b to ~1 ulp without the special-case handling of an IEEE division: hardware seed (>= 20
+// bits) + two Newton steps.  b = 0 or non-finite gives a non-finite result, which the caller
+// reports as a singular Jacobian either way.  (The tridiagonal solve replaces the reference's
+// sparse LU; its rounding is not on the parity path.)
+__device__ __forceinline__ double fast_rcp(double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  return fma(r, e, r);
+}
+
 __device__ __forceinline__ double block_pcr_solve(double a, double b, double c, double d, int i, int n, double* sh) {
   const int T = blockDim.x;
   int buf = 0;
@@ -187,7 +200,7 @@ __device__ __forceinline__ double block_pcr_solve(double a, double b, double c, 
     double* wi = wa + T;
     double* wc = wi + T;
     double* wd = wc + T;
-    wa[i] = a; wi[i] = 1.0 / b; wc[i] = c; wd[i] = d;   // each pivot is inverted once, by its owner
+    wa[i] = a; wi[i] = fast_rcp(b); wc[i] = c; wd[i] = d;   // each pivot is inverted once, by its owner
     __syncthreads();
     const int im = i - s, ip = i + s;
     double na = 0.0, nc = 0.0;
