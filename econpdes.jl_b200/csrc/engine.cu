@@ -206,6 +206,8 @@ std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p, Dist* dist, long long s
     c->l = c->halo * slab_count;
   }
   c->n = c->l * c->F;
+  if (c->n + 2 * c->halo >= (1LL << 31))
+    throw std::invalid_argument("grids of 2^31 unknowns or more per device are not supported (32-bit point indexing)");
   for (int i = 0; i < c->nparams; ++i) c->prm.v[i] = p->params[i];
   EP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   cudaStream_t s = c->stream;

@@ -56,12 +56,15 @@ struct Stencil {
 
 template <int N>
 EP_HD void unravel(long long pt, const GridView<N>& gv, long long* idx) {
+  // a device holds fewer than 2^31 points (checked when the problem is created): 32-bit division
+  unsigned p = static_cast<unsigned>(pt);
 #pragma unroll
   for (int d = 0; d + 1 < N; ++d) {
-    idx[d] = pt % gv.S[d];
-    pt /= gv.S[d];
+    const unsigned s = static_cast<unsigned>(gv.S[d]);
+    idx[d] = p % s;
+    p /= s;
   }
-  idx[N - 1] = pt + gv.off;   // global index along the slab dimension
+  idx[N - 1] = p + gv.off;   // global index along the slab dimension
 }
 
 template <int N, int RECIP>
@@ -104,17 +107,21 @@ inline void make_geom_table(const double* x, long long S, double* tab /* [kGeomR
 template <int N, class G>
 EP_HD void load_box(const double* __restrict__ yf, long long pt, const GridView<N>& gv, const G& g, double* w) {
   constexpr int K = ipow3(N);
+  int str[N];   // 32-bit offsets (see unravel)
+#pragma unroll
+  for (int d = 0; d < N; ++d) str[d] = static_cast<int>(gv.stride[d]);
+  const double* __restrict__ yc = yf + pt;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    long long q = pt;
+    int q = 0;
     bool ok = true;
 #pragma unroll
     for (int d = 0; d < N; ++d) {
       const int o = (k / p3(d)) % 3 - 1;
       if ((o < 0 && g.lo[d]) || (o > 0 && g.hi[d])) ok = false;
-      q += o * gv.stride[d];
+      q += o * str[d];
     }
-    w[k] = yf[ok ? q : pt];
+    w[k] = yc[ok ? q : 0];
   }
 }
 
@@ -219,6 +226,9 @@ EP_HD void jacobian_point(const typename M::Pre& pre, const G& g, const long lon
     for (int f = 0; f < F; ++f) r0[f] = apply_row_terms(g0[f], w[f][C], rt[f]);
   }
   const int ncg = ncolors_grid<N>(gv);
+  int i3[N];
+#pragma unroll
+  for (int d = 0; d < N; ++d) i3[d] = static_cast<int>(idx[d] % 3);
 #pragma unroll
   for (int fin = 0; fin < F; ++fin) {
 #pragma unroll
@@ -229,7 +239,7 @@ EP_HD void jacobian_point(const typename M::Pre& pre, const G& g, const long lon
       for (int d = 0; d < N; ++d) {
         const int o = St::off(k, d);
         if ((o < 0 && g.lo[d]) || (o > 0 && g.hi[d])) ok = false;
-        color += static_cast<int>((idx[d] + o + 3) % 3) * stride;
+        color += ((i3[d] + o + 3) % 3) * stride;
         stride *= gv.S[d] < 3 ? static_cast<int>(gv.S[d]) : 3;
       }
       const int slot = St::boxslot(k);
