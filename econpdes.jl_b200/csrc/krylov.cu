@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "engine.cuh"
+#include "tridiag.cuh"
 
 namespace econpdes {
 namespace {
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(1024) k_line_zebra(LevelGeom<N> g, const doubl
 #pragma unroll
     for (int m = 0; m < RPT; ++m) {
       const int i = threadIdx.x + m * blockDim.x;
-      if (i < n) { sa[i] = ra[m]; si[i] = 1.0 / rb[m]; sc[i] = rc[m]; sd[i] = rd[m]; }
+      if (i < n) { sa[i] = ra[m]; si[i] = fast_rcp(rb[m]); sc[i] = rc[m]; sd[i] = rd[m]; }
     }
     __syncthreads();
 #pragma unroll
@@ -250,6 +251,187 @@ __global__ void __launch_bounds__(1024) k_line_zebra(LevelGeom<N> g, const doubl
   for (int m = 0; m < RPT; ++m) {
     const int i = threadIdx.x + m * blockDim.x;
     if (i < n) x[base + i] = rd[m] / rb[m];
+  }
+}
+
+// ---- zebra line smoother, lines of up to 256 points: one WARP per line -------------------
+// The block-wide PCR above spends ~80 shared-memory operations and log2(n) barriers per point.
+// Here a warp owns a line:
+//   1. coalesced assembly (lane l handles points l, l+32, ..): right-hand side b - (off-line
+//      couplings) x and the three in-line coefficients, parked in shared memory;
+//   2. lane l takes the PPT consecutive rows l*PPT .. l*PPT+PPT-1 into registers and eliminates
+//      its interior rows (Thomas with three right-hand sides), which expresses them through the
+//      last unknown of the previous lane and its own last unknown;
+//   3. the 32 "last unknowns" form a tridiagonal system across the lanes, solved by PCR with
+//      warp shuffles (5 steps, no barrier);
+//   4. interior unknowns follow by substitution; the line is written back coalesced.
+// ~10 shared-memory operations per point instead of ~80 and no __syncthreads.
+template <int PPT>
+__device__ __forceinline__ int line_pos(int i) { return PPT > 1 ? i + i / PPT : i; }   // padded: conflict-free strided reads
+
+template <int N, bool BOX, int PPT>
+__global__ void __launch_bounds__(256) k_line_zebra_warp(LevelGeom<N> g, const double* __restrict__ A,
+                                                         const double* __restrict__ b, double* __restrict__ x,
+                                                         int color, long long nlines) {
+  using St = Stencil<N, BOX>;
+  constexpr int NP = 32 * PPT;            // line capacity
+  constexpr int PITCH = NP + 32;          // padded array length
+  extern __shared__ double sh[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long line = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+  if (line >= nlines) return;             // warp-uniform; no block-level barrier below
+  double* sa = sh + warp * 4 * PITCH;
+  double* sb = sa + PITCH;
+  double* sc = sb + PITCH;
+  double* sd = sc + PITCH;
+  const int n = static_cast<int>(g.S[0]);
+  long long other[N > 1 ? N - 1 : 1];
+  {
+    long long q = line;
+#pragma unroll
+    for (int e = 1; e < N; ++e) {
+      const int ce = (color >> (e - 1)) & 1;
+      const long long cnt = (g.S[e] - ce + 1) / 2;
+      other[e - 1] = ce + 2 * (q % cnt);
+      q /= cnt;
+    }
+  }
+  long long base = 0;
+#pragma unroll
+  for (int e = 1; e < N; ++e) base += other[e - 1] * g.stride[e];
+  int kc = -1, km = -1, kp = -1;
+#pragma unroll
+  for (int k = 0; k < St::NK; ++k) {
+    bool inl = true;
+#pragma unroll
+    for (int e = 1; e < N; ++e)
+      if (St::off(k, e) != 0) inl = false;
+    if (inl) {
+      if (St::off(k, 0) == 0) kc = k;
+      if (St::off(k, 0) < 0) km = k;
+      if (St::off(k, 0) > 0) kp = k;
+    }
+  }
+  // ---- 1. coalesced assembly ----
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int i = lane + 32 * j;
+    double va = 0.0, vb = 1.0, vc = 0.0, vd = 0.0;   // rows beyond the line are identity rows
+    if (i < n) {
+      const long long pt = base + i;
+      double rhs = b[pt];
+#pragma unroll
+      for (int k = 0; k < St::NK; ++k) {
+        bool inl = true, ok = true;
+        long long q = pt;
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          const int o = St::off(k, e);
+          if (e > 0 && o != 0) inl = false;
+          const long long ie = e == 0 ? i : other[e - 1];
+          const bool lo_edge = ie == 0 && !(e == N - 1 && g.open_lo);
+          const bool hi_edge = ie == g.S[e] - 1 && !(e == N - 1 && g.open_hi);
+          if ((o < 0 && lo_edge) || (o > 0 && hi_edge)) ok = false;
+          q += o * g.stride[e];
+        }
+        if (!inl) rhs -= A[k * g.l + pt] * x[ok ? q : pt];   // zero coefficient outside the grid
+      }
+      va = i > 0 ? A[km * g.l + pt] : 0.0;
+      vb = A[kc * g.l + pt];
+      vc = i < n - 1 ? A[kp * g.l + pt] : 0.0;
+      vd = rhs;
+    }
+    const int p = line_pos<PPT>(i);
+    sa[p] = va; sb[p] = vb; sc[p] = vc; sd[p] = vd;
+  }
+  __syncwarp();
+  // ---- 2. interior rows of this lane: x_j = u_j - v_j x_prev - w_j x_last ----
+  constexpr int M1 = PPT > 1 ? PPT - 1 : 1;
+  double cp[M1], u[M1], v[M1];
+  const int r0 = lane * PPT;
+  if (PPT > 1) {
+    {
+      const int p = line_pos<PPT>(r0);
+      const double inv = fast_rcp(sb[p]);
+      cp[0] = sc[p] * inv;
+      u[0] = sd[p] * inv;
+      v[0] = sa[p] * inv;
+    }
+#pragma unroll
+    for (int j = 1; j < PPT - 1; ++j) {
+      const int p = line_pos<PPT>(r0 + j);
+      const double aj = sa[p];
+      const double inv = fast_rcp(sb[p] - aj * cp[j - 1]);
+      cp[j] = sc[p] * inv;
+      u[j] = (sd[p] - aj * u[j - 1]) * inv;
+      v[j] = (-aj * v[j - 1]) * inv;
+    }
+  }
+  double w[M1];
+  if (PPT > 1) {
+    w[PPT - 2] = cp[PPT - 2];
+#pragma unroll
+    for (int j = PPT - 3; j >= 0; --j) {
+      u[j] -= cp[j] * u[j + 1];
+      v[j] -= cp[j] * v[j + 1];
+      w[j] = -cp[j] * w[j + 1];
+    }
+  }
+  // ---- 3. reduced system in the lanes' last unknowns ----
+  double ra, rb, rc, rd;
+  {
+    const int p = line_pos<PPT>(r0 + PPT - 1);
+    const double al = sa[p], bl = sb[p], cl = sc[p], dl = sd[p];
+    if (PPT > 1) {
+      // first interior unknown of the next lane: u'_0 - v'_0 x_last(me) - w'_0 x_last(next)
+      const double un = __shfl_down_sync(0xffffffffu, u[0], 1);
+      const double vn = __shfl_down_sync(0xffffffffu, v[0], 1);
+      const double wn = __shfl_down_sync(0xffffffffu, w[0], 1);
+      ra = -al * v[PPT - 2];
+      rb = bl - al * w[PPT - 2] - cl * vn;
+      rc = -cl * wn;
+      rd = dl - al * u[PPT - 2] - cl * un;
+    } else {
+      ra = al; rb = bl; rc = cl; rd = dl;
+    }
+  }
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const double inv = fast_rcp(rb);
+    const double am = __shfl_up_sync(0xffffffffu, ra, s), im = __shfl_up_sync(0xffffffffu, inv, s);
+    const double cm = __shfl_up_sync(0xffffffffu, rc, s), dm = __shfl_up_sync(0xffffffffu, rd, s);
+    const double ap = __shfl_down_sync(0xffffffffu, ra, s), ip = __shfl_down_sync(0xffffffffu, inv, s);
+    const double cq = __shfl_down_sync(0xffffffffu, rc, s), dq = __shfl_down_sync(0xffffffffu, rd, s);
+    double na = 0.0, nc = 0.0;
+    if (lane >= s) {
+      const double alpha = -ra * im;
+      na = alpha * am;
+      rb += alpha * cm;
+      rd += alpha * dm;
+    }
+    if (lane + s < 32) {
+      const double gamma = -rc * ip;
+      nc = gamma * cq;
+      rb += gamma * ap;
+      rd += gamma * dq;
+    }
+    ra = na;
+    rc = nc;
+  }
+  const double xl = rd / rb;
+  const double xprev = __shfl_up_sync(0xffffffffu, xl, 1);   // lane 0: multiplied by v = 0
+  // ---- 4. substitution, coalesced write-back ----
+  __syncwarp();
+  sd[line_pos<PPT>(r0 + PPT - 1)] = xl;
+  if (PPT > 1) {
+#pragma unroll
+    for (int j = 0; j < PPT - 1; ++j) sd[line_pos<PPT>(r0 + j)] = u[j] - v[j] * xprev - w[j] * xl;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int i = lane + 32 * j;
+    if (i < n) x[base + i] = sd[line_pos<PPT>(i)];
   }
 }
 
@@ -371,50 +553,65 @@ template <int N, bool BOXIN>
 __global__ void __launch_bounds__(kBlock) k_rap_1d(int d, int type, LevelGeom<N> gin, LevelGeom<N> gout,
                                                    const double* __restrict__ Ain, double* __restrict__ Aout,
                                                    const double* __restrict__ Aghost) {
-  constexpr int KC = ipow3(N);
+  // one thread per (output row, offsets in the other dimensions): it reads the <= 3 x 3 fine
+  // entries (fine row i, in-dimension offset od) once and scatters them into the three output
+  // offsets O[d] = -1, 0, +1
+  constexpr int KO = ipow3(N) / 3;   // offset combinations of the other dimensions
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (tid >= gout.l * KC) return;
+  if (tid >= gout.l * KO) return;
   const long long pout = tid % gout.l;
-  const int kout = static_cast<int>(tid / gout.l);
+  const int ko = static_cast<int>(tid / gout.l);
   long long idx[N];
   unravel_l<N>(pout, gout, idx);
   int O[N];
+  {
+    int q = ko;
 #pragma unroll
-  for (int e = 0; e < N; ++e) O[e] = (kout / p3(e)) % 3 - 1;
-  const long long I = idx[d], J = I + O[d];
+    for (int e = 0; e < N; ++e) {
+      if (e == d) { O[e] = 0; continue; }
+      O[e] = q % 3 - 1;
+      q /= 3;
+    }
+  }
+  const long long I = idx[d];
   const bool slab = d == N - 1;
   const bool olo = slab && gin.open_lo, ohi = slab && gin.open_hi;
   const long long Sce = gout.S[d] + (ohi ? 1 : 0);          // virtual coarse extent for the weights
   const long long jlo = olo ? -2 : 0, jhi = gin.S[d] - 1 + (ohi ? 1 : 0);   // admissible fine columns [jlo, jhi]
-  double acc = 0.0;
-  if (J >= (olo ? -1 : 0) && J < Sce) {
-    long long lo, hi, pbase = 0;
-    fine_range(type, I, gin.S[d], lo, hi, olo);
+  const long long Jlo = olo ? -1 : 0;
+  double acc[3] = {0.0, 0.0, 0.0};
+  long long lo, hi, pbase = 0;
+  fine_range(type, I, gin.S[d], lo, hi, olo);
 #pragma unroll
-    for (int e = 0; e < N; ++e)
-      if (e != d) pbase += idx[e] * gin.stride[e];
-    for (long long i = lo; i <= hi; ++i) {
-      const double wi = tw(type, i, I, Sce);
-      if (wi == 0.0) continue;
-      const long long pin = pbase + i * gin.stride[d];
+  for (int e = 0; e < N; ++e)
+    if (e != d) pbase += idx[e] * gin.stride[e];
+  for (long long i = lo; i <= hi; ++i) {
+    const double wi = tw(type, i, I, Sce);
+    if (wi == 0.0) continue;
+    const long long pin = pbase + i * gin.stride[d];
 #pragma unroll
-      for (int od = -1; od <= 1; ++od) {
-        const long long j = i + od;
-        if (j < jlo || j > jhi) continue;
-        const double wj = tw(type, j, J, Sce);
-        if (wj == 0.0) continue;
-        int o[N];
+    for (int od = -1; od <= 1; ++od) {
+      const long long j = i + od;
+      if (j < jlo || j > jhi) continue;
+      int o[N];
 #pragma unroll
-        for (int e = 0; e < N; ++e) o[e] = e == d ? od : O[e];
-        const int kin = plane_of<N, BOXIN>(o);
-        if (kin >= 0) {
-          const double a = i < 0 ? Aghost[kin * gin.stride[d] + pbase] : Ain[kin * gin.l + pin];
-          acc += wi * a * wj;
-        }
+      for (int e = 0; e < N; ++e) o[e] = e == d ? od : O[e];
+      const int kin = plane_of<N, BOXIN>(o);
+      if (kin < 0) continue;
+      const double a = wi * (i < 0 ? Aghost[kin * gin.stride[d] + pbase] : Ain[kin * gin.l + pin]);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const long long J = I + q - 1;
+        if (J < Jlo || J >= Sce) continue;
+        acc[q] += a * tw(type, j, J, Sce);
       }
     }
   }
-  Aout[kout * gout.l + pout] = acc;
+  int kout0 = 0;   // plane of (O with O[d] = -1); the three outputs are p3(d) apart
+#pragma unroll
+  for (int e = 0; e < N; ++e) kout0 += (e == d ? 0 : O[e] + 1) * p3(e);
+#pragma unroll
+  for (int q = 0; q < 3; ++q) Aout[(kout0 + q * p3(d)) * gout.l + pout] = acc[q];
 }
 
 // sum over the grid of min(|a+|,|a-|) and max(|a+|,|a-|) of the two couplings across each
@@ -690,6 +887,10 @@ class KrylovSolver final : public LinearSolver {
   explicit KrylovSolver(Ctx& c) : c_(c) {
     EP_CUDA(cudaMallocHost(&h_, 256 * sizeof(double)));
     sym_.alloc(2 * kMaxDims);
+    if (const char* wl = std::getenv("ECONPDES_WARP_LINES_MAX")) {
+      warp_lines_max_ = std::atoi(wl);
+      if (warp_lines_max_ > 256) warp_lines_max_ = 256;
+    }
     const char* e = std::getenv("ECONPDES_NO_GRAPH");
     use_graph_ = !(e && e[0] == '1');
     // the slab cycle interleaves NCCL calls with its kernels: NCCL operations are capturable, every
@@ -759,6 +960,11 @@ class KrylovSolver final : public LinearSolver {
   unsigned long long graph_sig_ = 0;
   int64_t graph_kernels_ = 0;
   bool use_graph_ = true;
+  // lines of up to this many points take the warp-per-line kernel (max 256).  Default 0: on B200 the
+  // block-wide PCR hides the global-load latency of the 27 operator planes better (256^3: 260 us
+  // vs 302 us per color sweep, both ~55-60 % of HBM peak; coarse levels tie), so the warp kernel
+  // stays an option (ECONPDES_WARP_LINES_MAX) rather than the default.
+  int warp_lines_max_ = 0;
   double* h_ = nullptr;
   int dense_n_ = 0;
   int restart_alloc_ = 0;
@@ -969,7 +1175,7 @@ class KrylovSolver final : public LinearSolver {
               ghost = rap_ghost_.p;
             }
           }
-          const long long nthreads = gout.l * ipow3(N);
+          const long long nthreads = gout.l * (ipow3(N) / 3);
           if (inbox) EP_LAUNCH((k_rap_1d<N, true>), blocks_for(nthreads), kBlock, 0, s, d, t.type[d], gin, gout, in, out, ghost);
           else EP_LAUNCH((k_rap_1d<N, false>), blocks_for(nthreads), kBlock, 0, s, d, t.type[d], gin, gout, in, out, ghost);
           in = out;
@@ -1052,7 +1258,27 @@ class KrylovSolver final : public LinearSolver {
         const int ce = (color >> (e - 1)) & 1;
         nlines *= (Sd[e] - ce + 1) / 2;
       }
-      if (nlines > 0) {
+      if (nlines > 0 && n <= warp_lines_max_) {
+        // one warp per line, 8 lines per block
+        const int ppt = n <= 32 ? 1 : (n <= 64 ? 2 : (n <= 128 ? 4 : 8));
+        const unsigned blocks = static_cast<unsigned>((nlines + 7) / 8);
+        const size_t wsmem = 8 * 4 * static_cast<size_t>(32 * ppt + 32) * sizeof(double);
+#define EP_WLINE(P)                                                                                          \
+  do {                                                                                                       \
+    static bool cfg = false;                                                                                 \
+    if (!cfg) {                                                                                              \
+      EP_CUDA(cudaFuncSetAttribute(k_line_zebra_warp<N, BOX, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   100 * 1024));                                                             \
+      cfg = true;                                                                                            \
+    }                                                                                                        \
+    EP_LAUNCH((k_line_zebra_warp<N, BOX, P>), blocks, 256, wsmem, c_.stream, g, A, b, x, color, nlines);     \
+  } while (0)
+        if (ppt == 1) EP_WLINE(1);
+        else if (ppt == 2) EP_WLINE(2);
+        else if (ppt == 4) EP_WLINE(4);
+        else EP_WLINE(8);
+#undef EP_WLINE
+      } else if (nlines > 0) {
 #define EP_LINE(R)                                                                                          \
   do {                                                                                                      \
     static bool cfg = false;                                                                                \
