@@ -338,6 +338,26 @@ void Dist::send_hi_recv_lo(const double* send_last, double* recv_lo_ghost, long 
   halo_any(nullptr, send_last, recv_lo_ghost, nullptr, count, s);
 }
 
+void Dist::all_gather_raw(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s) {
+  if (world_ == 1) {
+    if (send != recv) cudaMemcpyAsync(recv, send, bytes_per_rank, cudaMemcpyDeviceToDevice, s);
+    return;
+  }
+  EP_NCCL(api().AllGather(send, recv, bytes_per_rank, ncclChar, static_cast<ncclComm_t>(comm_), s));
+  ++ncoll_;
+}
+
+void Dist::send_hi_recv_lo_raw(const void* send_last, void* recv_lo_ghost, size_t bytes, cudaStream_t s) {
+  if (world_ == 1) return;
+  const NcclApi& n = api();
+  ncclComm_t comm = static_cast<ncclComm_t>(comm_);
+  EP_NCCL(n.GroupStart());
+  if (has_hi()) EP_NCCL(n.Send(send_last, bytes, ncclChar, rank_ + 1, comm, s));
+  if (has_lo()) EP_NCCL(n.Recv(recv_lo_ghost, bytes, ncclChar, rank_ - 1, comm, s));
+  EP_NCCL(n.GroupEnd());
+  ++ncoll_;
+}
+
 void Dist::all_gather(const double* send, double* recv, long long count, cudaStream_t s) {
   if (world_ == 1) {
     if (send != recv)

@@ -45,6 +45,9 @@ class Dist {
   void send_hi_recv_lo(const double* send_last, double* recv_lo_ghost, long long count, cudaStream_t s);
   // recv[r*count .. (r+1)*count) = rank r's send[0..count)   (device pointers)
   void all_gather(const double* send, double* recv, long long count, cudaStream_t s);
+  // untyped variants for the multigrid set-up (operator planes in the hierarchy's storage type)
+  void all_gather_raw(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s);
+  void send_hi_recv_lo_raw(const void* send_last, void* recv_lo_ghost, size_t bytes, cudaStream_t s);
 
   int64_t collectives() const { return ncoll_; }       // NCCL calls
   int64_t p2p_exchanges() const { return np2p_; }       // halo exchanges done by k_halo_p2p

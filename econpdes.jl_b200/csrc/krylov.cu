@@ -35,6 +35,17 @@ constexpr int kCoarseMax2D = 8;    // stop coarsening when every dimension has <
 constexpr int kCoarseMax3D = 4;    // (the coarsest operator is factorised densely by one thread block)
 constexpr double kLinearThreshold = 0.3;
 
+// Storage type of the multigrid hierarchy's operators.  The V-cycle is a preconditioner inside
+// flexible GMRES, whose own operator (the Jacobian planes) and vectors stay FP64, so the hierarchy
+// can hold its stencil coefficients in FP32: the line smoother streams 27 planes per point and
+// runs at ~60 % of HBM bandwidth on a 256^3 grid, so halving those bytes is what shortens the
+// cycle.  All arithmetic (sweeps, Galerkin products, residuals) is still FP64.
+#ifdef ECONPDES_MG_DOUBLE
+using mgreal = double;
+#else
+using mgreal = float;
+#endif
+
 template <int N>
 struct LevelGeom {
   long long S[N];
@@ -68,8 +79,8 @@ __device__ __forceinline__ void unravel_l(long long pt, const LevelGeom<N>& g, l
 }
 
 // y = A x (mode 0) or y = b - A x (mode 1); entries pointing outside the grid hold 0.
-template <int N, bool BOX>
-__global__ void __launch_bounds__(kBlock) k_spmv(LevelGeom<N> g, const double* __restrict__ A,
+template <int N, bool BOX, class TA>
+__global__ void __launch_bounds__(kBlock) k_spmv(LevelGeom<N> g, const TA* __restrict__ A,
                                                  const double* __restrict__ x, const double* __restrict__ b,
                                                  double* __restrict__ y, int mode) {
   using St = Stencil<N, BOX>;
@@ -99,9 +110,10 @@ __global__ void __launch_bounds__(kBlock) k_spmv(LevelGeom<N> g, const double* _
 
 // ---- transposes: layout d puts dimension d fastest, the others keep their order --------
 // All of them are (batched) 2-D transposes of an R x C matrix (R fastest) into C x R.
-__global__ void k_transpose(const double* __restrict__ src, double* __restrict__ dst, long long R, long long C,
+template <class T>
+__global__ void k_transpose(const T* __restrict__ src, T* __restrict__ dst, long long R, long long C,
                             long long batch_stride) {
-  __shared__ double tile[32][33];
+  __shared__ T tile[32][33];
   const long long base = static_cast<long long>(blockIdx.z) * batch_stride;
   long long r = static_cast<long long>(blockIdx.x) * 32 + threadIdx.x;
   long long c = static_cast<long long>(blockIdx.y) * 32 + threadIdx.y;
@@ -127,11 +139,12 @@ TransposeShape transpose_shape(const long long* S, int d) {
   if (d == 1) return {S[0], S[1], S[2], S[0] * S[1]};
   return {S[0] * S[1], S[2], 1, 0};
 }
-void launch_transpose(cudaStream_t s, const double* src, double* dst, TransposeShape t, bool inverse) {
+template <class T>
+void launch_transpose(cudaStream_t s, const T* src, T* dst, TransposeShape t, bool inverse) {
   const long long R = inverse ? t.C : t.R, C = inverse ? t.R : t.C;
   dim3 grid(static_cast<unsigned>((R + 31) / 32), static_cast<unsigned>((C + 31) / 32),
             static_cast<unsigned>(t.batches));
-  EP_LAUNCH(k_transpose, grid, dim3(32, 8), 0, s, src, dst, R, C, t.batch_stride);
+  EP_LAUNCH(k_transpose<T>, grid, dim3(32, 8), 0, s, src, dst, R, C, t.batch_stride);
 }
 // sizes of layout d, and where each original dimension lands
 template <int N>
@@ -147,7 +160,7 @@ void layout_dims(const long long* S, int d, long long* Sd, int* perm /* perm[e] 
 // Solves, for every line of the given color, the tridiagonal system made of the in-line
 // couplings with right-hand side b - (off-line couplings) x, by PCR in shared memory.
 template <int N, bool BOX, int RPT>
-__global__ void __launch_bounds__(1024) k_line_zebra(LevelGeom<N> g, const double* __restrict__ A,
+__global__ void __launch_bounds__(1024) k_line_zebra(LevelGeom<N> g, const mgreal* __restrict__ A,
                                                      const double* __restrict__ b, double* __restrict__ x,
                                                      int color) {
   using St = Stencil<N, BOX>;
@@ -270,7 +283,7 @@ template <int PPT>
 __device__ __forceinline__ int line_pos(int i) { return PPT > 1 ? i + i / PPT : i; }   // padded: conflict-free strided reads
 
 template <int N, bool BOX, int PPT>
-__global__ void __launch_bounds__(256) k_line_zebra_warp(LevelGeom<N> g, const double* __restrict__ A,
+__global__ void __launch_bounds__(256) k_line_zebra_warp(LevelGeom<N> g, const mgreal* __restrict__ A,
                                                          const double* __restrict__ b, double* __restrict__ x,
                                                          int color, long long nlines) {
   using St = Stencil<N, BOX>;
@@ -551,8 +564,8 @@ __device__ __forceinline__ int plane_of(const int* o) {
 // (J == -1 / J == Sc).
 template <int N, bool BOXIN>
 __global__ void __launch_bounds__(kBlock) k_rap_1d(int d, int type, LevelGeom<N> gin, LevelGeom<N> gout,
-                                                   const double* __restrict__ Ain, double* __restrict__ Aout,
-                                                   const double* __restrict__ Aghost) {
+                                                   const mgreal* __restrict__ Ain, mgreal* __restrict__ Aout,
+                                                   const mgreal* __restrict__ Aghost) {
   // one thread per (output row, offsets in the other dimensions): it reads the <= 3 x 3 fine
   // entries (fine row i, in-dimension offset od) once and scatters them into the three output
   // offsets O[d] = -1, 0, +1
@@ -611,13 +624,13 @@ __global__ void __launch_bounds__(kBlock) k_rap_1d(int d, int type, LevelGeom<N>
 #pragma unroll
   for (int e = 0; e < N; ++e) kout0 += (e == d ? 0 : O[e] + 1) * p3(e);
 #pragma unroll
-  for (int q = 0; q < 3; ++q) Aout[(kout0 + q * p3(d)) * gout.l + pout] = acc[q];
+  for (int q = 0; q < 3; ++q) Aout[(kout0 + q * p3(d)) * gout.l + pout] = static_cast<mgreal>(acc[q]);
 }
 
 // sum over the grid of min(|a+|,|a-|) and max(|a+|,|a-|) of the two couplings across each
 // edge along every dimension: out[2d], out[2d+1].  Symmetric (diffusion-like) -> ratio near 1.
 template <int N, bool BOX>
-__global__ void __launch_bounds__(kBlock) k_edge_symmetry(LevelGeom<N> g, const double* __restrict__ A,
+__global__ void __launch_bounds__(kBlock) k_edge_symmetry(LevelGeom<N> g, const mgreal* __restrict__ A,
                                                           double* __restrict__ out) {
   using St = Stencil<N, BOX>;
   __shared__ double sm[2 * kMaxDims][kBlock / 32];
@@ -664,7 +677,7 @@ __global__ void __launch_bounds__(kBlock) k_edge_symmetry(LevelGeom<N> g, const 
 
 // ---- coarsest level: dense LU with partial pivoting by one thread block ----------------
 template <int N, bool BOX>
-__global__ void __launch_bounds__(kBlock) k_dense_build(LevelGeom<N> g, const double* __restrict__ A,
+__global__ void __launch_bounds__(kBlock) k_dense_build(LevelGeom<N> g, const mgreal* __restrict__ A,
                                                         double* __restrict__ M) {
   using St = Stencil<N, BOX>;
   const long long pt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -833,25 +846,27 @@ struct SlabMap {           // every rank's owned range of dimension N-1 at one l
 };
 // last owned plane of every operator plane, packed [k][plane] for the neighbour above
 static __global__ void __launch_bounds__(kBlock) k_pack_last_plane(int nk, long long l, long long plane,
-                                                                   const double* __restrict__ A,
-                                                                   double* __restrict__ out) {
+                                                                   const mgreal* __restrict__ A,
+                                                                   mgreal* __restrict__ out) {
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= nk * plane) return;
   const long long k = t / plane, p = t % plane;
   out[t] = A[k * l + (l - plane) + p];
 }
 // local [nk][l_loc] -> send buffer [nk][maxl]
-static __global__ void __launch_bounds__(kBlock) k_pack_slab(int nk, long long lloc, long long maxl,
-                                                             const double* __restrict__ src, double* __restrict__ dst) {
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_pack_slab(int nk, long long lloc, long long maxl,
+                                                      const T* __restrict__ src, T* __restrict__ dst) {
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= nk * lloc) return;
   const long long k = t / lloc, p = t % lloc;
   dst[k * maxl + p] = src[k * lloc + p];
 }
 // all-gathered [rank][nk][maxl] -> full [nk][l_glob] (slabs are contiguous along dimension N-1)
-static __global__ void __launch_bounds__(kBlock) k_unpack_slabs(SlabMap m, int nk, long long plane, long long maxl,
-                                                                long long lglob, const double* __restrict__ all,
-                                                                double* __restrict__ full) {
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_unpack_slabs(SlabMap m, int nk, long long plane, long long maxl,
+                                                         long long lglob, const T* __restrict__ all,
+                                                         T* __restrict__ full) {
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<long long>(nk) * lglob) return;
   const long long k = t / lglob, pt = t % lglob;
@@ -859,6 +874,14 @@ static __global__ void __launch_bounds__(kBlock) k_unpack_slabs(SlabMap m, int n
   int r = 0;
   while (r + 1 < m.world && i >= m.first[r + 1]) ++r;
   full[t] = all[(static_cast<long long>(r) * nk + k) * maxl + (pt - m.first[r] * plane)];
+}
+
+// FP64 Jacobian planes -> storage type of the hierarchy (level 0 of the preconditioner)
+static __global__ void __launch_bounds__(kBlock) k_to_mgreal(long long n, const double* __restrict__ src,
+                                                             mgreal* __restrict__ dst) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = static_cast<mgreal>(src[i]);
 }
 
 // ---- the solver ---------------------------------------------------------------------------
@@ -873,9 +896,9 @@ struct Level {
   long long plane = 0;                  // prod S[0..N-2]
   long long Sg_last = 0;                // global size of dimension N-1
   SlabMap map{};                        // owned ranges of all ranks at this level
-  const double* A = nullptr;           // layout 0
-  DevBuf<double> Aown;                  // owned storage for coarse levels
-  DevBuf<double> Aperm[N];              // operator in layout d (d >= 1)
+  const mgreal* A = nullptr;           // layout 0
+  DevBuf<mgreal> Aown;                  // owned storage for coarse levels
+  DevBuf<mgreal> Aperm[N];              // operator in layout d (d >= 1)
   long long Sd[N][N];                   // sizes of layout d
   Transfer to_coarse;                   // valid if not the coarsest level
   DevBuf<double> x, b, r, tx, tb;       // work vectors (tx/tb: transposed copies)
@@ -947,15 +970,17 @@ class KrylovSolver final : public LinearSolver {
  private:
   Ctx& c_;
   std::vector<std::unique_ptr<Level<N>>> lev_;
-  DevBuf<double> dense_, sym_, V_, Z_, w_, dots_, part_, hdev_, rap_tmp_[2], dense_inv_, dense_work_;
+  DevBuf<double> dense_, sym_, V_, Z_, w_, dots_, part_, hdev_, dense_inv_, dense_work_;
+  DevBuf<mgreal> A0_, rap_tmp_[2], rap_send_, rap_ghost_;   // level-0 copy of the Jacobian planes; Galerkin scratch
   DevBuf<int> piv_;
   DevBuf<Transfer> transfers_dev_;
   // slab path: ghosted copy of the SpMV operand, block-local copy of the operator for the
   // preconditioner (couplings that leave the slab dropped), all-gather landing area
-  DevBuf<double> xh_, gsend_, grecv_, rap_send_, rap_ghost_, bloc_;
+  DevBuf<double> xh_, bloc_;
+  DevBuf<unsigned char> gsend_, grecv_;   // all-gather staging (operator planes or vectors)
   long long replicate_below_ = 48LL * 48 * 48;   // levels with at most this many points run replicated
   cudaGraphExec_t graph_exec_ = nullptr;
-  const double* graph_A_ = nullptr;
+  const mgreal* graph_A_ = nullptr;
   int graph_nlev_ = 0;
   unsigned long long graph_sig_ = 0;
   int64_t graph_kernels_ = 0;
@@ -971,7 +996,7 @@ class KrylovSolver final : public LinearSolver {
 
   template <bool BOX>
   void spmv(const Level<N>& L, const double* x, const double* b, double* y, int mode) {
-    EP_LAUNCH((k_spmv<N, BOX>), blocks_for(L.l), kBlock, 0, c_.stream, make_geom<N>(L.S), L.A, x, b, y, mode);
+    EP_LAUNCH((k_spmv<N, BOX, mgreal>), blocks_for(L.l), kBlock, 0, c_.stream, make_geom<N>(L.S), L.A, x, b, y, mode);
   }
   void spmv(const Level<N>& L, const double* x, const double* b, double* y, int mode) {
     if (L.box) spmv<true>(L, x, b, y, mode); else spmv<false>(L, x, b, y, mode);
@@ -981,8 +1006,10 @@ class KrylovSolver final : public LinearSolver {
   void spmv_top(const double* x, const double* b, double* y, int mode) {
     ProfScope ps("lin spmv", c_.stream);
     Level<N>& L0 = *lev_[0];
-    if (c_.dist == nullptr) {
-      spmv(L0, x, b, y, mode);
+    if (c_.dist == nullptr) {   // the Krylov operator is the FP64 Jacobian, not the hierarchy's copy
+      const LevelGeom<N> g0 = make_geom<N>(L0.S);
+      if (c_.box) EP_LAUNCH((k_spmv<N, true, double>), blocks_for(L0.l), kBlock, 0, c_.stream, g0, top_A_, x, b, y, mode);
+      else EP_LAUNCH((k_spmv<N, false, double>), blocks_for(L0.l), kBlock, 0, c_.stream, g0, top_A_, x, b, y, mode);
       return;
     }
     cudaStream_t s = c_.stream;
@@ -993,8 +1020,8 @@ class KrylovSolver final : public LinearSolver {
     LevelGeom<N> g = make_geom<N>(L0.S);
     g.open_lo = c_.dist->has_lo();
     g.open_hi = c_.dist->has_hi();
-    if (c_.box) EP_LAUNCH((k_spmv<N, true>), blocks_for(L0.l), kBlock, 0, s, g, top_A_, xh_.p, b, y, mode);
-    else EP_LAUNCH((k_spmv<N, false>), blocks_for(L0.l), kBlock, 0, s, g, top_A_, xh_.p, b, y, mode);
+    if (c_.box) EP_LAUNCH((k_spmv<N, true, double>), blocks_for(L0.l), kBlock, 0, s, g, top_A_, xh_.p, b, y, mode);
+    else EP_LAUNCH((k_spmv<N, false, double>), blocks_for(L0.l), kBlock, 0, s, g, top_A_, xh_.p, b, y, mode);
   }
   const double* top_A_ = nullptr;
 
@@ -1015,17 +1042,21 @@ class KrylovSolver final : public LinearSolver {
   void halo(const Level<N>& L, double* v) { c_.dist->exchange_halo(v, L.plane, L.S[N - 1], c_.stream); }
 
   // [nk][l_loc] slabs of every rank -> [nk][l_glob] on every rank
-  void gather_slabs(const SlabMap& m, int nk, long long plane, const double* local, double* full) {
+  template <class T>
+  void gather_slabs(const SlabMap& m, int nk, long long plane, const T* local, T* full) {
     cudaStream_t s = c_.stream;
     const int me = c_.dist->rank();
     long long maxcount = 0, total = 0;
     for (int r = 0; r < m.world; ++r) { maxcount = m.count[r] > maxcount ? m.count[r] : maxcount; total += m.count[r]; }
     const long long maxl = maxcount * plane, lloc = m.count[me] * plane, lglob = total * plane;
-    gsend_.alloc(static_cast<size_t>(nk) * maxl);
-    grecv_.alloc(static_cast<size_t>(m.world) * nk * maxl);
-    EP_LAUNCH(k_pack_slab, blocks_for(nk * lloc), kBlock, 0, s, nk, lloc, maxl, local, gsend_.p);
-    c_.dist->all_gather(gsend_.p, grecv_.p, nk * maxl, s);
-    EP_LAUNCH(k_unpack_slabs, blocks_for(nk * lglob), kBlock, 0, s, m, nk, plane, maxl, lglob, grecv_.p, full);
+    const size_t per_rank = static_cast<size_t>(nk) * maxl * sizeof(T);
+    gsend_.alloc(per_rank);
+    grecv_.alloc(static_cast<size_t>(m.world) * per_rank);
+    T* snd = reinterpret_cast<T*>(gsend_.p);
+    T* rcv = reinterpret_cast<T*>(grecv_.p);
+    EP_LAUNCH(k_pack_slab<T>, blocks_for(nk * lloc), kBlock, 0, s, nk, lloc, maxl, local, snd);
+    c_.dist->all_gather_raw(snd, rcv, per_rank, s);
+    EP_LAUNCH(k_unpack_slabs<T>, blocks_for(nk * lglob), kBlock, 0, s, m, nk, plane, maxl, lglob, rcv, full);
   }
 
   // Build the hierarchy for the operator in `planes` (called once per Jacobian).
@@ -1065,7 +1096,12 @@ class KrylovSolver final : public LinearSolver {
       lev_.push_back(std::move(L0));
     }
     top_A_ = planes;
-    lev_[0]->A = planes;
+    {   // level 0 of the preconditioner: the Jacobian planes in the hierarchy's storage type
+      const long long cnt = static_cast<long long>(c_.nk) * c_.l;
+      A0_.alloc(static_cast<size_t>(cnt));
+      EP_LAUNCH(k_to_mgreal, 148 * 8, kBlock, 0, s, cnt, planes, A0_.p);
+      lev_[0]->A = A0_.p;
+    }
     size_t li = 0;
     while (true) {
       Level<N>& L = *lev_[li];
@@ -1143,7 +1179,7 @@ class KrylovSolver final : public LinearSolver {
       {
         long long Sin[N];
         for (int d = 0; d < N; ++d) Sin[d] = L.S[d];
-        const double* in = L.A;
+        const mgreal* in = L.A;
         bool inbox = L.box;
         int npass = 0, pass = 0;
         for (int d = 0; d < N; ++d) npass += t.type[d] >= 0 ? 1 : 0;
@@ -1154,14 +1190,14 @@ class KrylovSolver final : public LinearSolver {
           for (int e = 0; e < N; ++e) Sout[e] = Sin[e];
           Sout[d] = t.Sc[d];
           LevelGeom<N> gin = make_geom<N>(Sin), gout = make_geom<N>(Sout);
-          double* out;
+          mgreal* out;
           if (++pass == npass && !regather) {
             out = Lc.Aown.p;
           } else {
             rap_tmp_[pass & 1].alloc(static_cast<size_t>(ipow3(N)) * gout.l);
             out = rap_tmp_[pass & 1].p;
           }
-          const double* ghost = nullptr;
+          const mgreal* ghost = nullptr;
           if (L.dist && d == N - 1) {
             gin.open_lo = L.open_lo;
             gin.open_hi = L.open_hi;
@@ -1171,7 +1207,7 @@ class KrylovSolver final : public LinearSolver {
               rap_send_.alloc(static_cast<size_t>(nkin) * pl);
               rap_ghost_.alloc(static_cast<size_t>(nkin) * pl);
               EP_LAUNCH(k_pack_last_plane, blocks_for(nkin * pl), kBlock, 0, s, nkin, gin.l, pl, in, rap_send_.p);
-              dd->send_hi_recv_lo(rap_send_.p, rap_ghost_.p, nkin * pl, s);
+              dd->send_hi_recv_lo_raw(rap_send_.p, rap_ghost_.p, static_cast<size_t>(nkin) * pl * sizeof(mgreal), s);
               ghost = rap_ghost_.p;
             }
           }
@@ -1242,7 +1278,7 @@ class KrylovSolver final : public LinearSolver {
   }
 
   template <bool BOX>
-  void line_sweep_layout(Level<N>& L, int d, const double* A, const double* b, double* x) {
+  void line_sweep_layout(Level<N>& L, int d, const mgreal* A, const double* b, double* x) {
     const long long* Sd = L.Sd[d];
     const int n = static_cast<int>(Sd[0]);
     const LevelGeom<N> g = geom_layout(L, d);
@@ -1360,8 +1396,8 @@ class KrylovSolver final : public LinearSolver {
       smooth(L, b, x, false);   // leaves the ghosts of x current
     }
     ProfScope* pt = prof ? new ProfScope(kTr[pl], s) : nullptr;
-    if (L.box) EP_LAUNCH((k_spmv<N, true>), blocks_for(L.l), kBlock, 0, s, gf, L.A, x, b, L.r.p, 1);
-    else EP_LAUNCH((k_spmv<N, false>), blocks_for(L.l), kBlock, 0, s, gf, L.A, x, b, L.r.p, 1);
+    if (L.box) EP_LAUNCH((k_spmv<N, true, mgreal>), blocks_for(L.l), kBlock, 0, s, gf, L.A, x, b, L.r.p, 1);
+    else EP_LAUNCH((k_spmv<N, false, mgreal>), blocks_for(L.l), kBlock, 0, s, gf, L.A, x, b, L.r.p, 1);
     // full weighting reaches one fine plane below the slab
     if (linear) dd.send_hi_recv_lo(L.r.p + (L.S[N - 1] - 1) * L.plane, L.r.p - L.plane, L.plane, s);
     // this rank's part of the coarse grid
