@@ -22,6 +22,7 @@
 // vectors are transposed in and out around those sweeps.
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "engine.cuh"
@@ -40,10 +41,12 @@ constexpr double kLinearThreshold = 0.3;
 // can hold its stencil coefficients in FP32: the line smoother streams 27 planes per point and
 // runs at ~60 % of HBM bandwidth on a 256^3 grid, so halving those bytes is what shortens the
 // cycle.  All arithmetic (sweeps, Galerkin products, residuals) is still FP64.
+// Only the 3-D hierarchies do so: with the 5-plane star stencils of the 2-D models the sweeps are
+// not bandwidth-bound and the conversions cost more than the bytes save (measured).
 #ifdef ECONPDES_MG_DOUBLE
-using mgreal = double;
+template <int N> using mgreal_t = double;
 #else
-using mgreal = float;
+template <int N> using mgreal_t = std::conditional_t<(N >= 3), float, double>;
 #endif
 
 template <int N>
@@ -160,7 +163,7 @@ void layout_dims(const long long* S, int d, long long* Sd, int* perm /* perm[e] 
 // Solves, for every line of the given color, the tridiagonal system made of the in-line
 // couplings with right-hand side b - (off-line couplings) x, by PCR in shared memory.
 template <int N, bool BOX, int RPT>
-__global__ void __launch_bounds__(1024) k_line_zebra(LevelGeom<N> g, const mgreal* __restrict__ A,
+__global__ void __launch_bounds__(1024) k_line_zebra(LevelGeom<N> g, const mgreal_t<N>* __restrict__ A,
                                                      const double* __restrict__ b, double* __restrict__ x,
                                                      int color) {
   using St = Stencil<N, BOX>;
@@ -283,7 +286,7 @@ template <int PPT>
 __device__ __forceinline__ int line_pos(int i) { return PPT > 1 ? i + i / PPT : i; }   // padded: conflict-free strided reads
 
 template <int N, bool BOX, int PPT>
-__global__ void __launch_bounds__(256) k_line_zebra_warp(LevelGeom<N> g, const mgreal* __restrict__ A,
+__global__ void __launch_bounds__(256) k_line_zebra_warp(LevelGeom<N> g, const mgreal_t<N>* __restrict__ A,
                                                          const double* __restrict__ b, double* __restrict__ x,
                                                          int color, long long nlines) {
   using St = Stencil<N, BOX>;
@@ -564,8 +567,9 @@ __device__ __forceinline__ int plane_of(const int* o) {
 // (J == -1 / J == Sc).
 template <int N, bool BOXIN>
 __global__ void __launch_bounds__(kBlock) k_rap_1d(int d, int type, LevelGeom<N> gin, LevelGeom<N> gout,
-                                                   const mgreal* __restrict__ Ain, mgreal* __restrict__ Aout,
-                                                   const mgreal* __restrict__ Aghost) {
+                                                   const mgreal_t<N>* __restrict__ Ain,
+                                                   mgreal_t<N>* __restrict__ Aout,
+                                                   const mgreal_t<N>* __restrict__ Aghost) {
   // one thread per (output row, offsets in the other dimensions): it reads the <= 3 x 3 fine
   // entries (fine row i, in-dimension offset od) once and scatters them into the three output
   // offsets O[d] = -1, 0, +1
@@ -624,13 +628,13 @@ __global__ void __launch_bounds__(kBlock) k_rap_1d(int d, int type, LevelGeom<N>
 #pragma unroll
   for (int e = 0; e < N; ++e) kout0 += (e == d ? 0 : O[e] + 1) * p3(e);
 #pragma unroll
-  for (int q = 0; q < 3; ++q) Aout[(kout0 + q * p3(d)) * gout.l + pout] = static_cast<mgreal>(acc[q]);
+  for (int q = 0; q < 3; ++q) Aout[(kout0 + q * p3(d)) * gout.l + pout] = static_cast<mgreal_t<N>>(acc[q]);
 }
 
 // sum over the grid of min(|a+|,|a-|) and max(|a+|,|a-|) of the two couplings across each
 // edge along every dimension: out[2d], out[2d+1].  Symmetric (diffusion-like) -> ratio near 1.
 template <int N, bool BOX>
-__global__ void __launch_bounds__(kBlock) k_edge_symmetry(LevelGeom<N> g, const mgreal* __restrict__ A,
+__global__ void __launch_bounds__(kBlock) k_edge_symmetry(LevelGeom<N> g, const mgreal_t<N>* __restrict__ A,
                                                           double* __restrict__ out) {
   using St = Stencil<N, BOX>;
   __shared__ double sm[2 * kMaxDims][kBlock / 32];
@@ -677,7 +681,7 @@ __global__ void __launch_bounds__(kBlock) k_edge_symmetry(LevelGeom<N> g, const 
 
 // ---- coarsest level: dense LU with partial pivoting by one thread block ----------------
 template <int N, bool BOX>
-__global__ void __launch_bounds__(kBlock) k_dense_build(LevelGeom<N> g, const mgreal* __restrict__ A,
+__global__ void __launch_bounds__(kBlock) k_dense_build(LevelGeom<N> g, const mgreal_t<N>* __restrict__ A,
                                                         double* __restrict__ M) {
   using St = Stencil<N, BOX>;
   const long long pt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -845,9 +849,9 @@ struct SlabMap {           // every rank's owned range of dimension N-1 at one l
   long long first[kMaxRanks], count[kMaxRanks];
 };
 // last owned plane of every operator plane, packed [k][plane] for the neighbour above
-static __global__ void __launch_bounds__(kBlock) k_pack_last_plane(int nk, long long l, long long plane,
-                                                                   const mgreal* __restrict__ A,
-                                                                   mgreal* __restrict__ out) {
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_pack_last_plane(int nk, long long l, long long plane,
+                                                            const T* __restrict__ A, T* __restrict__ out) {
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= nk * plane) return;
   const long long k = t / plane, p = t % plane;
@@ -877,11 +881,12 @@ __global__ void __launch_bounds__(kBlock) k_unpack_slabs(SlabMap m, int nk, long
 }
 
 // FP64 Jacobian planes -> storage type of the hierarchy (level 0 of the preconditioner)
-static __global__ void __launch_bounds__(kBlock) k_to_mgreal(long long n, const double* __restrict__ src,
-                                                             mgreal* __restrict__ dst) {
+template <class T>
+__global__ void __launch_bounds__(kBlock) k_to_mgreal(long long n, const double* __restrict__ src,
+                                                      T* __restrict__ dst) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
-    dst[i] = static_cast<mgreal>(src[i]);
+    dst[i] = static_cast<T>(src[i]);
 }
 
 // ---- the solver ---------------------------------------------------------------------------
@@ -896,6 +901,7 @@ struct Level {
   long long plane = 0;                  // prod S[0..N-2]
   long long Sg_last = 0;                // global size of dimension N-1
   SlabMap map{};                        // owned ranges of all ranks at this level
+  using mgreal = mgreal_t<N>;
   const mgreal* A = nullptr;           // layout 0
   DevBuf<mgreal> Aown;                  // owned storage for coarse levels
   DevBuf<mgreal> Aperm[N];              // operator in layout d (d >= 1)
@@ -907,6 +913,7 @@ struct Level {
 template <int N>
 class KrylovSolver final : public LinearSolver {
  public:
+  using mgreal = mgreal_t<N>;
   explicit KrylovSolver(Ctx& c) : c_(c) {
     EP_CUDA(cudaMallocHost(&h_, 256 * sizeof(double)));
     sym_.alloc(2 * kMaxDims);
@@ -1096,10 +1103,12 @@ class KrylovSolver final : public LinearSolver {
       lev_.push_back(std::move(L0));
     }
     top_A_ = planes;
-    {   // level 0 of the preconditioner: the Jacobian planes in the hierarchy's storage type
+    if constexpr (std::is_same_v<mgreal, double>) {
+      lev_[0]->A = planes;
+    } else {   // level 0 of the preconditioner: the Jacobian planes in the hierarchy's storage type
       const long long cnt = static_cast<long long>(c_.nk) * c_.l;
       A0_.alloc(static_cast<size_t>(cnt));
-      EP_LAUNCH(k_to_mgreal, 148 * 8, kBlock, 0, s, cnt, planes, A0_.p);
+      EP_LAUNCH(k_to_mgreal<mgreal>, 148 * 8, kBlock, 0, s, cnt, planes, A0_.p);
       lev_[0]->A = A0_.p;
     }
     size_t li = 0;
@@ -1206,7 +1215,7 @@ class KrylovSolver final : public LinearSolver {
               const long long pl = gin.stride[N - 1];
               rap_send_.alloc(static_cast<size_t>(nkin) * pl);
               rap_ghost_.alloc(static_cast<size_t>(nkin) * pl);
-              EP_LAUNCH(k_pack_last_plane, blocks_for(nkin * pl), kBlock, 0, s, nkin, gin.l, pl, in, rap_send_.p);
+              EP_LAUNCH(k_pack_last_plane<mgreal>, blocks_for(nkin * pl), kBlock, 0, s, nkin, gin.l, pl, in, rap_send_.p);
               dd->send_hi_recv_lo_raw(rap_send_.p, rap_ghost_.p, static_cast<size_t>(nkin) * pl * sizeof(mgreal), s);
               ghost = rap_ghost_.p;
             }
