@@ -238,7 +238,7 @@ def run_ours(args):
         line["kernels"] = bench_kernels.measure(reps=3)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_sample, 1)
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -254,7 +254,7 @@ def c5_slab(args, dist, rank, world, local, allmax):
     if world > 1:
         grp = E.SlabGroup.from_torch(dist, local)
     else:
-        grp = E.SlabGroup(0, 1, E.slab.new_unique_id())
+        grp = E.SlabGroup(0, 1)
     g, _ = EX.hjb3d_grid(n)
     first, count = E.slab_range(n, rank, world)
     guess = {"v": np.zeros((n, n, count))}
@@ -321,10 +321,43 @@ def run_reference(args):
                              "sample": f"{sample} sweep problems per step, {threads} threads, plain-C oracle"},
             "e2e": {"value": value, "unit": "Newton solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+class _OneJsonLine:
+    """The driver parses stdout as ONE JSON line, but libraries (NCCL's version banner, torch
+    warnings) also write to fd 1.  Everything goes to stderr while the benchmark runs; only the
+    final line is written to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+_OUT = None
+
+
+def _emit(line):
+    text = json.dumps(line)
+    if _OUT is not None:
+        _OUT.emit(text)
+    else:
+        print(text, flush=True)
 
 
 def main():
+    global _OUT
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
@@ -338,10 +371,13 @@ def main():
     ap.add_argument("--no-c5", action="store_true", help="skip the slab-decomposed 3-D solve")
     ap.add_argument("--c5-n", type=int, default=256, help="points per axis of the C5 grid")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with _OneJsonLine() as out:
+        _OUT = out
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    _OUT = None
 
 
 if __name__ == "__main__":

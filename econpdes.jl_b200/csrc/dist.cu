@@ -80,6 +80,7 @@ void Dist::unique_id(uint8_t* id128) {
 
 Dist::Dist(int rank, int world, const uint8_t* id128) : rank_(rank), world_(world) {
   if (world < 1 || rank < 0 || rank >= world) throw std::invalid_argument("rank/world out of range");
+  if (world == 1) return;   // a single slab needs no communicator (every collective is a local copy)
   ncclUniqueId id;
   std::memcpy(id.internal, id128, kUniqueIdBytes);
   ncclComm_t comm = nullptr;

@@ -40,7 +40,9 @@ def new_unique_id() -> bytes:
 class SlabGroup:
     """The ranks that share one grid: wraps the library's NCCL communicator (`econpdes_dist`)."""
 
-    def __init__(self, rank: int, world: int, unique_id: bytes):
+    def __init__(self, rank: int, world: int, unique_id: bytes = b""):
+        if world == 1 and not unique_id:
+            unique_id = bytes(UNIQUE_ID_BYTES)   # one slab: no NCCL communicator is created
         if len(unique_id) != UNIQUE_ID_BYTES:
             raise ValueError("unique id must be %d bytes" % UNIQUE_ID_BYTES)
         self.rank, self.world = rank, world

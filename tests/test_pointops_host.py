@@ -160,3 +160,51 @@ def test_reciprocal_jacobian_planes_give_the_same_bits():
     lib.emu_set_recip(0)
     for a, b in zip(outs[0], outs[1]):
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("bad", [np.inf, -np.inf, np.nan, 1e200, -3e305])
+def test_reciprocal_quotients_with_non_finite_and_huge_values(bad):
+    """Inf / NaN / near-overflow iterates (a diverging Newton step) must come out of the
+    reciprocal path exactly as IEEE division returns them: same Infs, same NaN positions."""
+    g, gu, prm = OM.hjb3d_problem(6)
+    pm = PM.Hjb3dSynth(**prm)
+    grids = list(g.values())
+    y = _perturbed({"v": 20.0 + np.zeros((6, 6, 6))})
+    y[2, 3, 1, 0] = bad
+    y[0, 0, 5, 0] = bad
+    lib = EU.lib()
+    outs = []
+    for mode in (0, 1, 2):
+        lib.emu_set_recip(mode)
+        with np.errstate(all="ignore"):
+            outs.append(EU.residual(pm, grids, y))
+    lib.emu_set_recip(0)
+    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_array_equal(outs[0], outs[2])
+    g1, gu1, prm1 = OM.campbell_cochrane_problem(sn=60)
+    pm1 = PM.CampbellCochraneModel(**prm1)
+    y1 = _perturbed(gu1)
+    y1[17, 0] = bad
+    outs = []
+    for mode in (0, 1):
+        lib.emu_set_recip(mode)
+        with np.errstate(all="ignore"):
+            outs.append(EU.residual(pm1, list(g1.values()), y1))
+    lib.emu_set_recip(0)
+    np.testing.assert_array_equal(outs[0], outs[1])
+
+
+def test_shared_reciprocal_in_functors_matches_ieee_for_degenerate_values():
+    """The asset-pricing functors divide by the unknown p through one reciprocal (mdiv); p = 0,
+    Inf or NaN must give what the reference's IEEE divisions give (oracle: numpy `/`)."""
+    g, gu, prm = OM.campbell_cochrane_problem(sn=40)
+    pm, om = PM.CampbellCochraneModel(**prm), OM.campbell_cochrane(**prm)
+    grids = list(g.values())
+    for bad in (0.0, np.inf, -np.inf, np.nan, 1e308):
+        y = _perturbed(gu)
+        y[11, 0] = bad
+        prob = eo.Problem(om, tuple(g), grids, tuple(gu))
+        with np.errstate(all="ignore"):
+            want = prob.G(y.reshape(-1, order="F")).reshape(y.shape, order="F")
+            got = EU.residual(pm, grids, y)
+        np.testing.assert_array_equal(got, want)
