@@ -47,6 +47,22 @@ def _peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_traffic_bytes(summary, kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of one kernel from the committed
+    `ncu --set full` summary under profiles/ (tools/ncu_summary.py); None if absent."""
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        with open(os.path.join(ROOT, "profiles", summary)) as f:
+            ks = [k for k in json.load(f)["kernels"] if kernel_substr in k["kernel"]]
+        tot = 0.0
+        for key in ("dram_read", "dram_write"):
+            v, u = ks[0][key].split()
+            tot += float(v) * unit[u]
+        return tot
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples SM clocks and throttle reasons with nvidia-smi during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -202,12 +218,7 @@ def run_ours(args):
     alg_bytes = float(S) * (BYTES_PER_NEWTON_POINT * newton_rank + BYTES_PER_SWEEP_POINT * float(no.sum() + B))
     kernel_ms = dev_ms / args.steps
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_batched_kernel_ncu.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    traffic = _ncu_traffic_bytes("r01_batched_kernel_ncu_full.json", "k_batched_pdesolve_1d")
     line = {
         "metric": "newton_solves_per_sec", "value": value, "unit": "Newton solves/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

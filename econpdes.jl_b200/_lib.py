@@ -64,6 +64,8 @@ SYMBOLS = {
     "econpdes_stencil_pattern": (C.c_int, [C.c_int, c_int64_p, C.c_int, c_int64_p, c_int64_p]),
     "econpdes_default_options": (None, [C.POINTER(Options)]),
     "econpdes_solve_stationary": (C.c_int, [C.POINTER(Problem), C.POINTER(Options), C.POINTER(Result)]),
+    "econpdes_solve_backward": (C.c_int, [C.POINTER(Problem), C.POINTER(Options), c_double_p, C.c_int32, c_double_p,
+                                          c_double_p, c_double_p, c_int32_p, c_double_p, c_int64_p]),
     "econpdes_create": (C.c_int, [C.POINTER(Problem), C.POINTER(C.c_void_p)]),
     "econpdes_destroy": (None, [C.c_void_p]),
     "econpdes_residual": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),

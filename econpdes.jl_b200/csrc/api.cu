@@ -292,6 +292,17 @@ int econpdes_solve_stationary(const econpdes_problem* problem, const econpdes_op
   });
 }
 
+int econpdes_solve_backward(const econpdes_problem* problem, const econpdes_options* options, const double* taus,
+                            int32_t ntaus, double* solution, double* saved, double* residual_norms,
+                            int32_t* newton_iters, double* device_ms, int64_t* kernel_launches) {
+  return guarded([&] {
+    if (!problem || !options) throw std::invalid_argument("null argument");
+    Solver solver(make_ctx(problem));
+    return solver.solve_backward(*options, taus, ntaus, solution, saved, residual_norms, newton_iters, device_ms,
+                                 kernel_launches);
+  });
+}
+
 // ---- slab-decomposed solve ----
 int econpdes_dist_unique_id(uint8_t* id) {
   return guarded([&] {

@@ -583,6 +583,57 @@ int Solver::solve(const econpdes_options& opt, econpdes_result* res) {
   return rc;
 }
 
+// Backward induction over a time grid (src/pdesolve.jl:191-211): the state stays on the device, each
+// time slice is copied out as it is produced.
+int Solver::solve_backward(const econpdes_options& opt, const double* taus, int ntaus, double* solution,
+                           double* saved_out, double* residual_norms, int32_t* newton_iters, double* device_ms,
+                           int64_t* launches) {
+  Ctx& c = *c_;
+  if (c.dist != nullptr) throw std::invalid_argument("the time-dependent solve is single-device");
+  if (taus == nullptr || ntaus < 1) throw std::invalid_argument("the time grid `τs` must contain at least one time");
+  for (int i = 0; i < ntaus; ++i) {
+    if (!std::isfinite(taus[i])) throw std::invalid_argument("the time grid `τs` must contain finite real numbers");
+    if (i > 0 && !(taus[i] > taus[i - 1])) throw std::invalid_argument("the time grid `τs` must be strictly increasing");
+  }
+  if (solution == nullptr || residual_norms == nullptr) throw std::invalid_argument("null output");
+  const long long n = c.n;
+  cudaStream_t s = c.stream;
+  const int64_t launches0 = g_kernel_launches.load();
+  cudaEvent_t e0, e1;
+  EP_CUDA(cudaEventCreate(&e0));
+  EP_CUDA(cudaEventCreate(&e1));
+  EP_CUDA(cudaEventRecord(e0, s));
+  DevBuf<double> ynext, saved;
+  ynext.alloc(static_cast<size_t>(n));
+  if (saved_out != nullptr && c.nsaved > 0) saved.alloc(static_cast<size_t>(c.nsaved) * c.l);
+  EP_CUDA(cudaMemcpyAsync(ypost_.p, c.guess.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  for (int i = 0; i < ntaus; ++i) residual_norms[i] = 0.0;
+  for (int it = ntaus - 1; it >= 0; --it) {
+    ypost_.download(solution + static_cast<size_t>(it) * n, static_cast<size_t>(n), s);
+    if (saved.p != nullptr) {
+      ops_->saved(c, ypost_.p, saved.p);
+      saved.download(saved_out + static_cast<size_t>(it) * saved.n, saved.n, s);
+    }
+    if (it > 0) {
+      NewtonOutcome o = newton(ypost_.p, taus[it] - taus[it - 1], opt.inner_abstol, opt.inner_maxiters, opt, ynext.p);
+      residual_norms[it] = o.nl;
+      if (newton_iters != nullptr) newton_iters[it] = o.iters;
+      EP_CUDA(cudaMemcpyAsync(ypost_.p, ynext.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    } else if (newton_iters != nullptr) {
+      newton_iters[0] = 0;
+    }
+  }
+  EP_CUDA(cudaEventRecord(e1, s));
+  EP_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  EP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (device_ms != nullptr) *device_ms = ms;
+  if (launches != nullptr) *launches = g_kernel_launches.load() - launches0;
+  return ECONPDES_OK;
+}
+
 // Map from CSC nonzeros of local_stencil_jacobian to stencil planes (host, once).
 void Solver::csc_gather(double* nzval_dev) {
   Ctx& c = *c_;

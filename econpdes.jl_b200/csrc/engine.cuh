@@ -168,6 +168,9 @@ class Solver {
   NewtonOutcome newton(const double* ypost, double delta, double ftol, int maxit, const econpdes_options& opt,
                        double* y_out);
   int solve(const econpdes_options& opt, econpdes_result* res);
+  // _solve_backward (src/pdesolve.jl:158-224); host output arrays as in econpdes_solve_backward
+  int solve_backward(const econpdes_options& opt, const double* taus, int ntaus, double* solution, double* saved,
+                     double* residual_norms, int32_t* newton_iters, double* device_ms, int64_t* launches);
   void csc_gather(double* nzval_dev);
   DevBuf<double> ypost_, y_, ynew_, R_, s_, G_, planes_;
   long long nnz_ = 0;

@@ -60,7 +60,9 @@ class EconPDEResult:
 
     @property
     def converged(self) -> bool:
-        return bool(self.residual_norm <= self.tolerance)
+        # time-dependent results store one residual per time; convergence uses the worst one
+        # (src/EconPDEs.jl:44-48); a NaN residual is not converged
+        return bool(np.all(np.asarray(self.residual_norm) <= self.tolerance))
 
     def __iter__(self):  # tuple destructuring: solution, residual_norm, saved = result
         return iter((self.solution, self.residual_norm, self.saved))
@@ -71,7 +73,11 @@ class EconPDEResult:
         lines = ["EconPDEResult", f"  solution:      {fmt(self.solution)}"]
         if self.saved:
             lines.append(f"  saved:         {fmt(self.saved)}")
-        lines.append(f"  residual_norm: {self.residual_norm:.2e}")
+        rn = self.residual_norm
+        if np.ndim(rn) == 0:
+            lines.append(f"  residual_norm: {rn:.2e}")
+        else:
+            lines.append(f"  residual_norm: max {np.max(rn):.2e} over {len(rn)} times")
         lines.append(f"  converged:     {'true' if self.converged else 'false'} (tolerance {self.tolerance:.2e})")
         return "\n".join(lines)
 
@@ -233,8 +239,21 @@ def pdesolve(pde, grid, guess, taus=None, *, is_algebraic=None, bc=None, lower_b
     if not isinstance(pde, RegisteredModel):
         raise TypeError("the device path needs a registered model functor (econpdes_b200.models); arbitrary host "
                         "closures `pde(state, u)` only run on the reference's CPU path")
-    if taus is not None:
-        raise NotImplementedError("time-dependent pdesolve(..., τs) is not on the device path yet (SURVEY.md 8f-2)")
+    if taus is not None:   # _reject_time_dependent_stationary_keywords + _check_time_grid, src/pdesolve.jl:10-15, 241-251
+        for k in ("Δ", "delta", "scale", "minΔ", "min_delta", "maxΔ", "max_delta", "max_residual_growth"):
+            if k in kwargs:
+                raise ValueError(f"`{k}` only applies to stationary pseudo-transient continuation; time-dependent "
+                                 "`pdesolve(..., τs)` uses the spacing of `τs` as the time step.")
+        taus = np.ascontiguousarray(np.asarray(taus, dtype=np.float64))
+        if taus.ndim != 1 or taus.size == 0:
+            raise ValueError("the time grid `τs` must contain at least one time")
+        if not np.all(np.isfinite(taus)):
+            raise ValueError("the time grid `τs` must contain finite real numbers")
+        if np.any(np.diff(taus) <= 0):
+            raise ValueError("the time grid `τs` must be strictly increasing")
+        # src/pdesolve.jl:158: inner_maxiters = maxiters, inner_abstol = abstol unless given
+        kwargs.setdefault("inner_maxiters", maxiters)
+        kwargs.setdefault("inner_abstol", abstol)
     if alg not in ("newton", ":newton"):
         raise ValueError(f"NLsolve `alg` must be `:newton` on the device path; got `{alg!r}`")
     grid = _as_ordered(grid, "the state grid")
@@ -294,6 +313,9 @@ def pdesolve(pde, grid, guess, taus=None, *, is_algebraic=None, bc=None, lower_b
     v = fvec(ub_arr); p.upper_bound = L.dptr(v)
     v = fvec(delta_arr); p.delta_vec = L.dptr(v)
 
+    if taus is not None:
+        return _solve_backward(lib, p, opts, taus, pde, S, F, ynames, statenames, abstol, verbose, warn,
+                               file or sys.stdout, keep)
     n = int(np.prod(S)) * F
     sol = np.empty(n)
     nsaved = len(pde.savednames)
@@ -330,6 +352,53 @@ def pdesolve(pde, grid, guess, taus=None, *, is_algebraic=None, bc=None, lower_b
         txt = _warn_text(res, opts.min_delta)
         if txt:
             warnings.warn(txt)
+    return res
+
+
+def _solve_backward(lib, p, opts, taus, pde, S, F, ynames, statenames, abstol, verbose, warn, file, keep):
+    """Time-dependent `pdesolve(pde, grid, guess, τs)` (src/pdesolve.jl:158-224): every unknown gains a
+    trailing time dimension, `residual_norm` is one value per time."""
+    import warnings
+    nt = taus.shape[0]
+    l = int(np.prod(S))
+    nsaved = len(pde.savednames)
+    sol = np.empty(l * F * nt)
+    saved = np.empty(l * nsaved * nt) if nsaved else None
+    rn = np.zeros(nt)
+    nit = np.zeros(nt, dtype=np.int32)
+    ms, launches = C.c_double(), C.c_int64()
+    L.check(lib.econpdes_solve_backward(C.byref(p), C.byref(opts), L.dptr(taus), nt, L.dptr(sol), L.dptr(saved),
+                                        L.dptr(rn), nit.ctypes.data_as(L.c_int32_p), C.byref(ms), C.byref(launches)))
+    ya = sol.reshape(S + (F, nt), order="F")
+    solution = OrderedDict((name, np.array(ya[..., k, :])) for k, name in enumerate(ynames))
+    sv = OrderedDict()
+    if nsaved:
+        sa = saved.reshape(S + (nsaved, nt), order="F")
+        sv = OrderedDict(solution)
+        for k, name in enumerate(pde.savednames):
+            sv[name] = np.array(sa[..., k, :])
+    res = EconPDEResult(solution, rn, sv, abstol, L.EXIT_CONVERGED, (), nt - 1, int(nit.sum()), 0,
+                        launches.value, ms.value)
+    if verbose:
+        desc = "%d %s (%s) on grid %s = %s" % (F, "unknown" if F == 1 else "unknowns", ", ".join(ynames),
+                                               "×".join(statenames), "×".join(str(s) for s in S))
+        print("Solving for %s, backward from τ = %g to %g (%d steps)" % (desc, taus[-1], taus[0], nt - 1), file=file)
+        print("    Time Residual", file=file)
+        print("-------- --------", file=file)
+        for i in range(nt - 1, 0, -1):
+            print("%8g %8.2e" % (taus[i - 1], rn[i]), file=file)
+        nfailed = int(np.sum(~(rn[1:] <= abstol)))
+        t = "%.0fms" % ms.value if ms.value < 1000 else "%.1fs" % (ms.value / 1000)
+        if nfailed == 0:
+            print("Completed %d time steps (%s)" % (nt - 1, t), file=file)
+        else:
+            print("Completed %d time steps (%s): %d steps did not converge" % (nt - 1, t, nfailed), file=file)
+    if warn:
+        for i in range(nt - 1, 0, -1):
+            if not (rn[i] <= abstol):
+                warnings.warn("the implicit time step at τ = %g did not converge (residual norm: %.2e); the solution "
+                              "at this and earlier times may be inaccurate — try a finer time grid or more "
+                              "`inner_maxiters`" % (taus[i - 1], rn[i]))
     return res
 
 

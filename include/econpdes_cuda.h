@@ -151,6 +151,20 @@ void econpdes_default_options(econpdes_options* opts);
 int econpdes_solve_stationary(const econpdes_problem* problem, const econpdes_options* options,
                               econpdes_result* result);
 
+/* --- time-dependent solve: replaces _solve_backward behind pdesolve(pde, grid, guess, taus)
+ *     (src/pdesolve.jl:158-224).  The guess is the terminal value at taus[ntaus-1]; going backward,
+ *     every earlier time is one implicit_timestep (Newton solve, no step controller) with
+ *     delta = taus[i] - taus[i-1], options->inner_maxiters Newton iterations at most and
+ *     options->inner_abstol as its ||R||_inf tolerance.  taus must be finite and strictly increasing
+ *     (_check_time_grid, :241-251).  Outputs, caller-allocated: solution (S.., F, ntaus) and, if not
+ *     NULL, saved (S.., NSAVED, ntaus), column-major with time slowest; residual_norms[ntaus]
+ *     (entry 0 stays 0, entry i is the Newton residual of the step that produced time i-1, as in the
+ *     reference); newton_iters[ntaus] (may be NULL).  The model functors take no time argument
+ *     (the reference's 3-argument pde(state, u, t) form is not on the device path). --- */
+int econpdes_solve_backward(const econpdes_problem* problem, const econpdes_options* options, const double* taus,
+                            int32_t ntaus, double* solution, double* saved, double* residual_norms,
+                            int32_t* newton_iters, double* device_ms, int64_t* kernel_launches);
+
 /* --- handle API for repeated residual / Jacobian evaluations --- */
 typedef struct econpdes_handle econpdes_handle;
 int econpdes_create(const econpdes_problem* problem, econpdes_handle** out);

@@ -679,8 +679,8 @@ class EconPDEResult:
     log: SolveLog = None
 
     @property
-    def converged(self) -> bool:
-        return bool(self.residual_norm <= self.tolerance)
+    def converged(self) -> bool:   # src/EconPDEs.jl:44-48: the worst residual of a time-dependent result
+        return bool(np.all(np.asarray(self.residual_norm) <= self.tolerance))
 
 
 def _expand(val, solnames, S, default, dtype):
@@ -729,3 +729,38 @@ def pdesolve(pde, grid: Dict[str, np.ndarray], guess: Dict[str, np.ndarray], *, 
     if saved:
         saved = {**solution, **saved}
     return EconPDEResult(solution, r, saved, abstol, log)
+
+
+def pdesolve_backward(pde, grid: Dict[str, np.ndarray], guess: Dict[str, np.ndarray], taus, *, abstol=SQRT_EPS,
+                      maxiters=100, inner_maxiters=None, inner_abstol=None, bc=None) -> EconPDEResult:
+    """Time-dependent ``pdesolve(pde, grid, guess, τs)``: ``_solve_backward`` (src/pdesolve.jl:158-224).
+    The guess is the terminal value at τs[end]; every earlier time is one ``implicit_timestep`` with
+    Δ = τs[i] − τs[i−1] (:203), ``inner_maxiters = maxiters`` and ``inner_abstol = abstol`` by
+    default (:158).  solution[name][..., i] is the value at τs[i]; residual_norm[i] is the Newton
+    residual of the step that produced time i−1 (entry 0 stays 0)."""
+    taus = np.asarray(taus, dtype=np.float64)
+    inner_maxiters = maxiters if inner_maxiters is None else inner_maxiters
+    inner_abstol = abstol if inner_abstol is None else inner_abstol
+    statenames, solnames = tuple(grid.keys()), tuple(guess.keys())
+    grids = tuple(np.asarray(g, dtype=np.float64) for g in grid.values())
+    S = tuple(g.shape[0] for g in grids)
+    F, nt = len(solnames), taus.shape[0]
+    prob = Problem(pde, statenames, grids, solnames, bc_array(bc, solnames, statenames, S))
+    cache = JacobianCache(S, F)
+    y = np.stack([np.asarray(guess[k], dtype=np.float64) for k in solnames], axis=-1).reshape(-1, order="F")
+    solution = {name: np.empty(S + (nt,)) for name in solnames}
+    saved: Dict[str, np.ndarray] = {}
+    rn = np.zeros(nt)
+    for it in range(nt - 1, -1, -1):                                   # :191
+        ya = y.reshape(S + (F,), order="F")
+        for k, name in enumerate(solnames):                            # :192-194
+            solution[name][..., it] = ya[..., k]
+        sv = prob.saved(y)                                             # :196-201
+        for name, v in (sv or {}).items():
+            saved.setdefault(name, np.empty(S + (nt,)))[..., it] = v
+        if it > 0:                                                     # :202-204
+            y, rn[it] = implicit_timestep(prob.G, y, taus[it] - taus[it - 1], cache, abstol=inner_abstol,
+                                          maxiters=inner_maxiters)
+    if saved:
+        saved = {**solution, **saved}
+    return EconPDEResult(solution, rn, saved, abstol, None)

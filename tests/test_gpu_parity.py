@@ -458,3 +458,39 @@ def test_c3_reference_semantics_reject_pattern_1024():
     # the robust per-column step (not reference parity) solves the same steps in a few iterations
     res2 = E.pdesolve(PM.BansalYaronModel(), g, gu, verbose=False, maxiters=3, warn=False, eps_policy=1)
     assert [r["status"] for r in res2.log] == [0, 0, 0] and res2.log[0]["newton_iters"] <= 5
+
+
+def test_time_dependent_solve_matches_oracle():
+    """pdesolve(pde, grid, guess, taus) (src/pdesolve.jl:158-224; reference test
+    test/runtests.jl:100-148): every time slice within 1e-8 relative of the oracle's backward
+    induction, per-step Newton residuals within 1e-10, saved outputs per time, same `converged`."""
+    g, gu, _ = OM.growth_test_problem(100)
+    taus = OM.julia_range(0, 100, 10)
+    ora = eo.pdesolve_backward(OM.growth_test_hjb(), g, gu, taus)
+    res = E.pdesolve(PM.GrowthTest(), g, gu, taus, verbose=False)
+    assert res.solution["v"].shape == (100, 10)
+    np.testing.assert_array_equal(res.solution["v"][:, -1], gu["v"])     # terminal condition, bit for bit
+    np.testing.assert_allclose(res.solution["v"], ora.solution["v"], rtol=1e-8)
+    np.testing.assert_allclose(res.residual_norm, ora.residual_norm, rtol=0, atol=1e-10)
+    assert res.residual_norm[0] == 0.0 and res.residual_norm[1:].max() <= 1e-6
+    assert res.converged == ora.converged and res.converged
+    for name in ("c",):
+        np.testing.assert_allclose(res.saved[name], ora.saved[name], rtol=1e-8)
+    assert res.kernel_launches > 0
+    # inner-solve keywords are accepted; stationary step controls are rejected
+    res2 = E.pdesolve(PM.GrowthTest(), g, gu, taus, inner_maxiters=20, inner_abstol=1e-8, verbose=False)
+    assert res2.residual_norm[1:].max() <= 1e-6
+    for kw in ({"Δ": 1.0}, {"scale": 2.0}, {"minΔ": 1e-6}, {"maxΔ": 10.0}):
+        with pytest.raises(ValueError):
+            E.pdesolve(PM.GrowthTest(), g, gu, taus, verbose=False, **kw)
+    with pytest.raises(ValueError):
+        E.pdesolve(PM.GrowthTest(), g, gu, taus[::-1], verbose=False)
+
+
+def test_time_dependent_two_dimensional_model():
+    g, gu, prm = OM.bansal_yaron_problem(21, 17)
+    taus = np.array([0.0, 0.5, 1.5, 4.0])
+    ora = eo.pdesolve_backward(OM.bansal_yaron(**prm), g, gu, taus)
+    res = E.pdesolve(PM.BansalYaronModel(**prm), g, gu, taus, verbose=False)
+    np.testing.assert_allclose(res.solution["p"], ora.solution["p"], rtol=1e-8)
+    np.testing.assert_allclose(res.residual_norm, ora.residual_norm, rtol=0, atol=1e-10)

@@ -255,3 +255,24 @@ def test_sweep_problems_converge_like_the_default():
         g, gu, _ = M.campbell_cochrane_problem(prm)
         res = eo.pdesolve(M.campbell_cochrane(**prm), g, gu)
         assert res.converged and res.log.n_outer == 4 and res.log.n_newton == 8
+
+
+def test_time_dependent_solve_reproduces_reference_test():
+    """test/runtests.jl:100-148 ("Time-dependent solve"): growth model, 100 points, 10 times on
+    [0, 100]; trailing time dimension, terminal condition kept bit for bit, every step converged,
+    saved outputs per time."""
+    from oracle import econpdes_oracle as eo2
+    from oracle import models as OM2
+    g, gu, _ = OM2.growth_test_problem(100)
+    taus = OM2.julia_range(0, 100, 10)
+    res = eo2.pdesolve_backward(OM2.growth_test_hjb(), g, gu, taus)
+    assert res.solution["v"].shape == (100, 10)                              # :108
+    np.testing.assert_array_equal(res.solution["v"][:, -1], gu["v"])         # :109
+    assert res.residual_norm[1:].max() <= 1e-6                               # :110
+    assert res.converged                                                     # :111
+    assert res.saved["c"].shape == (100, 10)                                 # :112
+    res2 = eo2.pdesolve_backward(OM2.growth_test_hjb(), g, gu, taus, inner_maxiters=20, inner_abstol=1e-8)
+    assert res2.residual_norm[1:].max() <= 1e-6                              # :136-137
+    # going far enough back in time the value approaches the stationary solution
+    stat = eo2.pdesolve(OM2.growth_test_hjb(), g, gu)
+    assert np.abs(res.solution["v"][:, 0] - stat.solution["v"]).max() < 0.05 * np.abs(stat.solution["v"]).max()
