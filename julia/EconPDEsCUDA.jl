@@ -96,4 +96,35 @@ function EconPDEs.pdesolve(m::CUDAModel, grid, guess; is_algebraic = nothing, bc
     return EconPDEResult(solution, res.residual_norm, savednt, abstol)
 end
 
+# Time-dependent problems: pdesolve(m, grid, guess, τs) -> _solve_backward (src/pdesolve.jl:158-224).
+# The guess is the terminal value; every unknown gains a trailing time dimension.
+function EconPDEs.pdesolve(m::CUDAModel, grid, guess, τs::AbstractVector; bc = nothing, abstol = sqrt(eps()),
+                           maxiters = 100, inner_maxiters = maxiters, inner_abstol = abstol, kwargs...)
+    EconPDEs._reject_time_dependent_stationary_keywords(kwargs); EconPDEs._check_time_grid(τs)
+    grid = _asnamedtuple(grid); guess = _asnamedtuple(guess)
+    stategrid = StateGrid(grid); S = size(stategrid); F = length(guess); nt = length(τs)
+    guess_array = cat(values(guess)...; dims = length(S) + 1)
+    bcs = _bc_array(bc, guess, grid); grids = [collect(Float64, g) for g in values(grid)]; ts = collect(Float64, τs)
+    opts = COptions(); ccall((:econpdes_default_options, lib), Cvoid, (Ref{COptions},), opts)
+    opts.abstol = abstol; opts.maxiters = maxiters; opts.inner_maxiters = inner_maxiters; opts.inner_abstol = inner_abstol
+    mid = ccall((:econpdes_model_id, lib), Cint, (Cstring,), m.name)
+    sol = Array{Float64}(undef, S..., F, nt); saved = Array{Float64}(undef, S..., length(m.saved), nt)
+    rn = zeros(nt); nit = zeros(Int32, nt); ms = Ref(0.0); nl = Ref(Int64(0))
+    GC.@preserve grids guess_array bcs sol saved rn nit ts m begin
+        gp = ntuple(d -> d <= length(S) ? pointer(grids[d]) : Ptr{Float64}(C_NULL), 3)
+        prob = CProblem(mid, length(S), F, length(m.params), ntuple(d -> d <= length(S) ? S[d] : 1, 3), gp,
+                        pointer(m.params), pointer(guess_array), pointer(bcs), C_NULL, C_NULL, C_NULL, C_NULL)
+        rc = ccall((:econpdes_solve_backward, lib), Cint,
+                   (Ref{CProblem}, Ref{COptions}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                    Ptr{Int32}, Ref{Float64}, Ref{Int64}),
+                   prob, opts, ts, nt, sol, isempty(m.saved) ? C_NULL : pointer(saved), rn, nit, ms, nl)
+    end
+    rc < 0 && throw(ArgumentError(last_error()))
+    ynames = tuple(keys(guess)...)
+    solution = NamedTuple{ynames}(ntuple(k -> collect(selectdim(sol, length(S) + 1, k)), F))
+    savednt = isempty(m.saved) ? NamedTuple() :
+        merge(solution, NamedTuple{m.saved}(ntuple(k -> collect(selectdim(saved, length(S) + 1, k)), length(m.saved))))
+    return EconPDEResult(solution, rn, savednt, abstol)
+end
+
 end # module
