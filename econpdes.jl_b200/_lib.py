@@ -90,6 +90,7 @@ SYMBOLS = {
                                          C.POINTER(Options), c_double_p, c_double_p, c_int32_p, c_int32_p,
                                          c_int32_p]),
     "econpdes_release_workspace": (None, []),
+    "econpdes_set_batch_points_per_thread": (C.c_int, [C.c_int]),
     "econpdes_device_count": (C.c_int, []),
     "econpdes_set_device": (C.c_int, [C.c_int]),
     "econpdes_total_kernel_launches": (C.c_int64, []),

@@ -47,6 +47,9 @@ struct econpdes_batch {
   long long B = 0;
   int S = 0, nparams = 0;
   cudaStream_t stream = nullptr;
+  static constexpr int kPipe = 3;
+  cudaStream_t pipe[kPipe] = {};   // copy/compute pipeline of the one-call path (econpdes_solve_batched)
+  int* err_host = nullptr;         // pinned [B]: a pageable target would make every slice's read-back blocking
   DevBuf<double> params, grids, guess, solution, residual_norm;
   DevBuf<int> exit_reason, n_outer, n_newton, error, log_len;
   DevBuf<econpdes_log_row> log;
@@ -55,6 +58,9 @@ struct econpdes_batch {
   int device = -1;
   ~econpdes_batch() {
     if (stream) cudaStreamDestroy(stream);
+    for (cudaStream_t p : pipe)
+      if (p) cudaStreamDestroy(p);
+    if (err_host) cudaFreeHost(err_host);
   }
 };
 
@@ -402,11 +408,14 @@ int econpdes_batch_upload(econpdes_batch* b, const double* params, const double*
   });
 }
 
-static int batch_launch(econpdes_batch* b, const econpdes_options* options, int log_capacity) {
+// launches the problems [first, last) on stream s (the whole batch on the batch's own stream by default)
+static int batch_launch(econpdes_batch* b, const econpdes_options* options, int log_capacity, long long first = 0,
+                        long long last = -1, cudaStream_t s = nullptr) {
   if (std::isnan(options->delta) || options->delta == 0.0)
     throw std::invalid_argument("`Δ` entries must be nonzero and not NaN (use `Inf` for no damping, a negative entry for forward relaxation)");
   BatchArgs a;
-  a.nproblems = b->B;
+  a.problem0 = first;
+  a.nproblems = last < 0 ? b->B : last;
   a.S = b->S;
   a.nparams = b->nparams;
   a.params = b->params.p;
@@ -427,7 +436,7 @@ static int batch_launch(econpdes_batch* b, const econpdes_options* options, int 
   a.log_len = b->log_len.p;
   a.opt = *options;
   const int64_t l0 = g_kernel_launches.load();
-  if (!model_ops(b->model_id)->batched(a, b->stream)) throw std::runtime_error("model has no batched kernel");
+  if (!model_ops(b->model_id)->batched(a, s ? s : b->stream)) throw std::runtime_error("model has no batched kernel");
   b->launches += g_kernel_launches.load() - l0;
   return ECONPDES_OK;
 }
@@ -496,6 +505,14 @@ int64_t econpdes_batch_kernel_launches(const econpdes_batch* b) { return b ? b->
 // cost more than the solve.  econpdes_release_workspace() frees it.
 static thread_local econpdes_batch* t_workspace = nullptr;
 
+int econpdes_set_batch_points_per_thread(int points) {
+  if (points < 0 || points > 4) {
+    set_error("points per thread must be 0 (automatic), 1, 2, 3 or 4");
+    return ECONPDES_E_INVALID;
+  }
+  return g_batch_points_per_thread.exchange(points);
+}
+
 void econpdes_release_workspace(void) {
   delete t_workspace;
   t_workspace = nullptr;
@@ -514,11 +531,55 @@ int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, con
     b->device = device;
     t_workspace = b;
   }
-  int rc = econpdes_batch_upload(b, params, grids, guess);
-  if (rc == ECONPDES_OK) rc = econpdes_batch_solve(b, options, nullptr);
-  if (rc == ECONPDES_OK)
-    rc = econpdes_batch_download(b, solution, residual_norm, exit_reason, n_outer, n_newton, nullptr, 0, nullptr);
-  return rc;
+  // Copy/compute pipeline: the batch is cut into slices; slice c's upload, solve and download are queued in
+  // order on stream c % 3, so the host->device copy of one slice, the kernel of another and the device->host
+  // copy of a third run at the same time (separate copy engines), and kernels of neighbouring slices fill each
+  // other's tail waves.  Problems are independent, so the result does not depend on the slicing.
+  return guarded([&] {
+    if (!grids || !guess || !options) throw std::invalid_argument("null argument");
+    if (b->nparams > 0 && !params) throw std::invalid_argument("null params");
+    const long long B = b->B;
+    const size_t S = static_cast<size_t>(b->S), P = static_cast<size_t>(b->nparams);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    long long nslices = B / (4LL * sms);           // at least four waves per slice
+    nslices = nslices < 1 ? 1 : (nslices > 8 ? 8 : nslices);
+    long long per = (B + nslices - 1) / nslices;
+    per = (per + sms - 1) / sms * sms;             // whole waves
+    for (cudaStream_t& p : b->pipe)
+      if (!p) EP_CUDA(cudaStreamCreateWithFlags(&p, cudaStreamNonBlocking));
+    if (!b->err_host) EP_CUDA(cudaMallocHost(&b->err_host, static_cast<size_t>(B) * sizeof(int)));
+    b->log_capacity = 0;
+    int* err = b->err_host;
+    int c = 0;
+    for (long long first = 0; first < B; first += per, ++c) {
+      const long long last = first + per < B ? first + per : B;
+      const size_t n = static_cast<size_t>(last - first), o = static_cast<size_t>(first);
+      cudaStream_t s = b->pipe[c % econpdes_batch::kPipe];
+      if (P > 0)
+        EP_CUDA(cudaMemcpyAsync(b->params.p + o * P, params + o * P, n * P * sizeof(double), cudaMemcpyHostToDevice, s));
+      EP_CUDA(cudaMemcpyAsync(b->grids.p + o * S, grids + o * S, n * S * sizeof(double), cudaMemcpyHostToDevice, s));
+      EP_CUDA(cudaMemcpyAsync(b->guess.p + o * S, guess + o * S, n * S * sizeof(double), cudaMemcpyHostToDevice, s));
+      batch_launch(b, options, 0, first, last, s);
+      EP_CUDA(cudaMemcpyAsync(err + o, b->error.p + o, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+      if (solution)
+        EP_CUDA(cudaMemcpyAsync(solution + o * S, b->solution.p + o * S, n * S * sizeof(double), cudaMemcpyDeviceToHost, s));
+      if (residual_norm)
+        EP_CUDA(cudaMemcpyAsync(residual_norm + o, b->residual_norm.p + o, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+      if (exit_reason)
+        EP_CUDA(cudaMemcpyAsync(exit_reason + o, b->exit_reason.p + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      if (n_outer) EP_CUDA(cudaMemcpyAsync(n_outer + o, b->n_outer.p + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      if (n_newton)
+        EP_CUDA(cudaMemcpyAsync(n_newton + o, b->n_newton.p + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    }
+    for (cudaStream_t p : b->pipe) EP_CUDA(cudaStreamSynchronize(p));
+    for (size_t i = 0; i < static_cast<size_t>(B); ++i)
+      if (err[i] != 0) {
+        set_error("G! returns NaN with the initial value (problem " + std::to_string(i) + ")");
+        return static_cast<int>(ECONPDES_E_NAN_GUESS);
+      }
+    return static_cast<int>(ECONPDES_OK);
+  });
 }
 
 }  // extern "C"

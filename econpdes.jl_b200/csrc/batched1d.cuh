@@ -18,7 +18,8 @@
 namespace econpdes {
 
 struct BatchArgs {
-  long long nproblems;
+  long long nproblems;     // one past the last problem of this launch
+  long long problem0 = 0;  // first problem of this launch (block b solves problem problem0 + b)
   int S;
   int nparams;
   const double* params;  // [B][nparams]
@@ -79,65 +80,103 @@ struct SerController {
   }
 };
 
-template <class M>
-__global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args) {
+// threads of a block that covers the engine's maximum of 1024 points with P points each (whole warps)
+constexpr int batched_max_threads(int P) { return ((1024 + P - 1) / P + 31) / 32 * 32; }
+
+// P = grid points per thread (consecutive).  With P > 1 the per-thread bookkeeping (block
+// reductions, barriers, controller, color steps) is shared by P points, the P evaluations are
+// independent instruction streams, and the tridiagonal solve only runs PCR on the T interface rows
+// (block_chunk_solve, tridiag.cuh).
+template <class M, int P>
+__global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_1d(BatchArgs args) {
   static_assert(M::N == 1 && M::F == 1, "the fused batched engine handles 1-D single-unknown models");
   extern __shared__ double smem[];
   const int T = blockDim.x;
-  double* ysh = smem;                 // [T + 2]: y with one halo slot each side
-  double* red = ysh + (T + 2);        // [8 * 32] reduction scratch
+  const int NP = T * P;
+  double* ysh = smem;                 // [NP + 2]: y with one halo slot each side
+  double* red = ysh + (NP + 2);       // [8 * 32] reduction scratch
   double* prm = red + 8 * 32;         // [16]
-  double* pcr = prm + 16;             // [8 * T]
-  const long long b = blockIdx.x;
-  const int i = threadIdx.x;
+  double* pcr = prm + 16;             // [8 * T] PCR buffers; holds the grid coordinates during set-up
+  double* xch = pcr + 8 * T;          // [4 * T] chunk interface exchange
+  const long long b = args.problem0 + blockIdx.x;
+  const int t = threadIdx.x;
   const int S = args.S;
-  const bool act = i < S;
+  const int i0 = t * P;               // first point of this thread
   const econpdes_options& opt = args.opt;
 
-  if (i < args.nparams) prm[i] = args.params[b * args.nparams + i];
-  if (i == 0) { ysh[0] = 0.0; ysh[T + 1] = 0.0; }
-  const double* xg = args.grids + b * S;
-  GridView<1> gv;
-  gv.x[0] = xg; gv.S[0] = S; gv.stride[0] = 1; gv.l = S;
-  long long idx[1] = {act ? i : 0};
-  PointGeom<1, 1> g;   // reciprocals of the spacings once per problem, reused by every stencil evaluation
-  double st[1];
-  load_geom(gv, idx, g, st);
-  double bl[1][1] = {{0.0}}, bh[1][1] = {{0.0}};
+  if (t < args.nparams) prm[t] = args.params[b * args.nparams + t];
+  if (t == 0) { ysh[0] = 0.0; ysh[NP + 1] = 0.0; }
+  // coalesced loads of the grid (staged in the PCR area, NP <= 8 T) and the guess
+  double* xs = pcr;
+  for (int k = t; k < NP; k += T) {
+    xs[k] = k < S ? args.grids[b * S + k] : 0.0;
+    ysh[k + 1] = k < S ? args.guess[b * S + k] : 0.0;
+  }
   __syncthreads();
-  typename M::Pre pre;   // state-only part of the model, once per problem
-  M::prepare(prm, st, pre);
+  GridView<1> gv;
+  gv.x[0] = xs; gv.S[0] = S; gv.stride[0] = 1; gv.l = S;
+  bool act[P];
+  long long idx[P][1];
+  PointGeom<1, 1> g[P];   // reciprocals of the spacings once per problem, reused by every stencil evaluation
+  typename M::Pre pre[P]; // state-only part of the model, once per problem
+  double ypost[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    act[j] = i0 + j < S;
+    idx[j][0] = act[j] ? i0 + j : 0;
+    double st[1];
+    load_geom(gv, idx[j], g[j], st);
+    M::prepare(prm, st, pre[j]);
+    ypost[j] = ysh[i0 + j + 1];
+  }
+  const double bl[1][1] = {{0.0}}, bh[1][1] = {{0.0}};
+  __syncthreads();   // the grid staging area is free again
 
-  // residual G at this thread's point from the y currently published in ysh
-  auto evalG = [&]() -> double {
-    double w[1][3] = {{ysh[i], ysh[i + 1], ysh[i + 2]}};
-    double o[1];
-    eval_point<M, false>(pre, g, w, bl, bh, o, nullptr);
-    return o[0];
+  // residual G at this thread's points from the y currently published in ysh
+  auto evalG = [&](double* G) {
+    double yv[P + 2];
+#pragma unroll
+    for (int k = 0; k < P + 2; ++k) yv[k] = ysh[i0 + k];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const double w[1][3] = {{yv[j], yv[j + 1], yv[j + 2]}};
+      double o[1];
+      eval_point<M, false>(pre[j], g[j], w, bl, bh, o, nullptr);
+      G[j] = act[j] ? o[0] : 0.0;
+    }
   };
-  auto publish = [&](double v) {
+  auto publish = [&](const double* v) {
     __syncthreads();  // everyone finished reading the previous y
-    ysh[i + 1] = v;
+#pragma unroll
+    for (int j = 0; j < P; ++j) ysh[i0 + j + 1] = v[j];
     __syncthreads();
   };
 
-  double ypost = act ? args.guess[b * S + i] : 0.0;
-  publish(ypost);
-  double Gpost = act ? evalG() : 0.0;
+  double Gpost[P];
+  evalG(Gpost);
   const double nd = static_cast<double>(S);
 
-  double sums[3], maxs[2];
-  sums[0] = (act && Gpost == Gpost) ? Gpost * Gpost : 0.0;
-  maxs[0] = (act && Gpost != Gpost) ? 1.0 : 0.0;
-  block_reduce_mixed<1, 1>(sums, maxs, red);
-  double r = maxs[0] > 0.0 ? NAN : sqrt(sums[0]) / nd;  // norm(ydot)/length(ydot), :371
+  // ||G||_2 / n with NaN -> NaN, as norm(ydot) / length(ydot) (:371, :415)
+  auto normG = [&](const double* Gv) -> double {
+    double s1[1] = {0.0}, m1[1] = {0.0};
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      if (act[j] && Gv[j] == Gv[j]) s1[0] += Gv[j] * Gv[j];
+      if (act[j] && Gv[j] != Gv[j]) m1[0] = 1.0;
+    }
+    block_reduce_mixed<1, 1>(s1, m1, red);
+    return m1[0] > 0.0 ? NAN : sqrt(s1[0]) / nd;
+  };
+  double r = normG(Gpost);
 
   int exit_reason = ECONPDES_EXIT_CONVERGED, n_outer = 0, n_newton = 0, log_len = 0, error = 0;
 
   // One Newton solve of the implicit step from ypost with time step `delta`
   // (implicit_timestep + _newtonstep + NLsolve newton_, finiteschemesolve.jl:125-230).
   // On return y/Gy hold the Newton result and G there; nl = ||R||_2/n (Inf: singular).
-  double y = ypost, Gy = Gpost, nl = 0.0;
+  double y[P], Gy[P], nl = 0.0;
+#pragma unroll
+  for (int j = 0; j < P; ++j) { y[j] = ypost[j]; Gy[j] = Gpost[j]; }
   int newton_it = 0;
   // Block-wide OR of a small bit mask in one barrier: warps fold their lanes with REDUX and
   // post the result with one shared atomic.  Three slots rotate: call k uses slot k%3 and,
@@ -145,62 +184,71 @@ __global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args)
   // after the following call's barrier -- so no extra synchronisation is needed.
   unsigned* flagw = reinterpret_cast<unsigned*>(red + 7 * 32);
   int flag_phase = 0;
-  if (i < 3) flagw[i] = 0u;
+  if (t < 3) flagw[t] = 0u;
   __syncthreads();
   auto block_or_bits = [&](unsigned bits) -> unsigned {
     const unsigned w = __reduce_or_sync(0xffffffffu, bits);
-    if ((i & 31) == 0 && w != 0u) atomicOr(&flagw[flag_phase], w);
+    if ((t & 31) == 0 && w != 0u) atomicOr(&flagw[flag_phase], w);
     __syncthreads();
     const unsigned all = flagw[flag_phase];
-    if (i == 0) flagw[(flag_phase + 2) % 3] = 0u;
+    if (t == 0) flagw[(flag_phase + 2) % 3] = 0u;
     flag_phase = (flag_phase + 1) % 3;
     return all;
   };
 
   auto newton = [&](double delta, double ftol, int maxit) {
-    RowTerms rt[1];
-    rt[0].implicit = true; rt[0].has_bounds = false; rt[0].ypost = ypost; rt[0].delta = delta;
-    rt[0].is_alg = false; rt[0].lb = 0.0; rt[0].ub = 0.0;
-    rt[0].rdelta = isfinite(delta) ? 1.0 / delta : 0.0;   // once per Newton solve
-    y = ypost;
-    Gy = Gpost;
-    double R = act ? apply_row_terms(Gy, y, rt[0]) : 0.0;
+    RowTerms rt[P];
+    const double rdelta = isfinite(delta) ? 1.0 / delta : 0.0;   // once per Newton solve
+    double R[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      rt[j].implicit = true; rt[j].has_bounds = false; rt[j].ypost = ypost[j]; rt[j].delta = delta;
+      rt[j].is_alg = false; rt[j].lb = 0.0; rt[j].ub = 0.0; rt[j].rdelta = rdelta;
+      y[j] = ypost[j];
+      Gy[j] = Gpost[j];
+      R[j] = act[j] ? apply_row_terms(Gy[j], y[j], rt[j]) : 0.0;
+    }
     newton_it = 0;
-    const int ci = i % 3;
     // NLsolve's loop only tests predicates of the residual (||R||_inf <= ftol, any NaN,
     // x == xold) -- folded block-wide as bits -- plus, for the Jacobian, FiniteDiff's three
     // masked sums of squares of the current iterate.  ||R||_2 is only needed once, at the end.
     enum : unsigned { kNaN = 1u, kBig = 2u, kMoved = 4u, kBad = 8u };
-    auto state_bits = [&](bool moved, bool bad) -> unsigned {
-      unsigned b = 0u;
-      if (act) {
-        if (R != R || y != y) b |= kNaN;
-        if (!(fabs(R) <= ftol)) b |= kBig;
-        if (moved) b |= kMoved;
-        if (bad) b |= kBad;
+    auto state_bits = [&](unsigned extra) -> unsigned {
+      unsigned bb = extra;
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        if (act[j]) {
+          if (R[j] != R[j] || y[j] != y[j]) bb |= kNaN;
+          if (!(fabs(R[j]) <= ftol)) bb |= kBig;
+        }
       }
-      return block_or_bits(b);
+      return block_or_bits(bb);
     };
-    unsigned bits = state_bits(true, false);
+    unsigned bits = state_bits(kMoved);
     bool anynan = (bits & kNaN) != 0u;
     bool fconv = !anynan && (bits & kBig) == 0u;
     bool xconv = false;
     bool singular = false;
+    const int c0 = i0 % 3;   // color of point j is (c0 + j) % 3
     // y is already published in ysh by the caller when y == ypost
     while (!anynan && !fconv && !xconv && newton_it < maxit) {
       ++newton_it;
-      double s3[3], m0[1];
-      const double q = act ? y * y : 0.0;
-      s3[0] = ci == 0 ? q : 0.0;
-      s3[1] = ci == 1 ? q : 0.0;
-      s3[2] = ci == 2 ? q : 0.0;
+      double s3[3] = {0.0, 0.0, 0.0}, m0[1];
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        const double q = act[j] ? y[j] * y[j] : 0.0;
+        const int cj = (c0 + j) % 3;
+        s3[0] += cj == 0 ? q : 0.0;
+        s3[1] += cj == 1 ? q : 0.0;
+        s3[2] += cj == 2 ? q : 0.0;
+      }
       block_reduce_mixed<3, 0>(s3, m0, red);
       // FiniteDiff: sqrt(eps)*max(1, sqrt(||x .* mask_c||_2)).  Lanes 0..2 of every warp turn one
       // color each into its step and the step's reciprocal (two square roots and a division,
       // executed once per warp instead of three times), then broadcast.
       double eps_table[3], reps_table[3];
       {
-        const int lane = i & 31;
+        const int lane = t & 31;
         const double mine = lane == 0 ? s3[0] : (lane == 1 ? s3[1] : s3[2]);
         const double e = color_epsilon_from_sumsq(mine);
         const double re = 1.0 / e;
@@ -210,50 +258,61 @@ __global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args)
           reps_table[c] = __shfl_sync(0xffffffffu, re, c);
         }
       }
-      double ja = 0.0, jb = 1.0, jc = 0.0;
-      if (act) {
-        double w[1][3] = {{ysh[i], ysh[i + 1], ysh[i + 2]}};
-        double r0[1] = {R};
-        jacobian_point<M, false, true>(pre, g, idx, gv, w, bl, bh, rt, eps_table,
-                                       opt.eps_policy == ECONPDES_EPS_PER_COLUMN, r0,
-                                       [&](int k, int, int, double v) {
-                                         if (k == 0) jb = v; else if (k == 1) ja = v; else jc = v;
-                                       }, reps_table);
+      double ja[P], jb[P], jc[P], rhs[P];
+      {
+        double yv[P + 2];
+#pragma unroll
+        for (int k = 0; k < P + 2; ++k) yv[k] = ysh[i0 + k];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+          ja[j] = 0.0; jb[j] = 1.0; jc[j] = 0.0; rhs[j] = 0.0;
+          if (act[j]) {
+            double w[1][3] = {{yv[j], yv[j + 1], yv[j + 2]}};
+            double r0[1] = {R[j]};
+            double va = 0.0, vb = 1.0, vc = 0.0;
+            jacobian_point<M, false, true>(pre[j], g[j], idx[j], gv, w, bl, bh, &rt[j], eps_table,
+                                           opt.eps_policy == ECONPDES_EPS_PER_COLUMN, r0,
+                                           [&](int k, int, int, double v) {
+                                             if (k == 0) vb = v; else if (k == 1) va = v; else vc = v;
+                                           }, reps_table);
+            ja[j] = va; jb[j] = vb; jc[j] = vc; rhs[j] = R[j];
+          }
+        }
       }
-      const double sol = block_pcr_solve(ja, jb, jc, act ? R : 0.0, i, S, pcr);
-      const bool bad = act && !isfinite(sol);
-      const double xold = y;
-      y = xold + (-sol);
+      double sol[P];
+      block_chunk_solve<P>(ja, jb, jc, rhs, t, (S + P - 1) / P, pcr, xch, sol);
+      unsigned extra = 0u;
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        if (act[j] && !isfinite(sol[j])) extra |= kBad;
+        const double xold = y[j];
+        y[j] = xold + (-sol[j]);
+        if (act[j] && y[j] != xold) extra |= kMoved;
+      }
       publish(y);
-      Gy = act ? evalG() : 0.0;
-      R = act ? apply_row_terms(Gy, y, rt[0]) : 0.0;
-      bits = state_bits(y != xold, bad);
+      evalG(Gy);
+#pragma unroll
+      for (int j = 0; j < P; ++j) R[j] = act[j] ? apply_row_terms(Gy[j], y[j], rt[j]) : 0.0;
+      bits = state_bits(extra);
       if (bits & kBad) { singular = true; break; }   // a vanishing pivot: SingularException
       anynan = (bits & kNaN) != 0u;
       fconv = !anynan && (bits & kBig) == 0u;
       xconv = !anynan && (bits & kMoved) == 0u;      // chebyshev(x, xold) <= xtol = 0
     }
     if (singular) {   // -> (y0, Inf), finiteschemesolve.jl:142-146
-      y = ypost;
-      Gy = Gpost;
+#pragma unroll
+      for (int j = 0; j < P; ++j) { y[j] = ypost[j]; Gy[j] = Gpost[j]; }
       nl = INFINITY;
       publish(y);
     } else if (anynan) {
       nl = NAN;
     } else {
-      double s1[1], m1[1];
-      s1[0] = act ? R * R : 0.0;
+      double s1[1] = {0.0}, m1[1];
+#pragma unroll
+      for (int j = 0; j < P; ++j) s1[0] += act[j] ? R[j] * R[j] : 0.0;
       block_reduce_mixed<1, 0>(s1, m1, red);
       nl = sqrt(s1[0]) / nd;
     }
-  };
-
-  auto normG = [&](double Gv) -> double {
-    double s1[1], m1[1];
-    s1[0] = (act && Gv == Gv) ? Gv * Gv : 0.0;
-    m1[0] = (act && Gv != Gv) ? 1.0 : 0.0;
-    block_reduce_mixed<1, 1>(s1, m1, red);
-    return m1[0] > 0.0 ? NAN : sqrt(s1[0]) / nd;
   };
 
   if (r != r) {
@@ -263,7 +322,8 @@ __global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args)
   } else if (isinf(opt.delta)) {                     // :377-389
     newton(INFINITY, opt.abstol, opt.maxiters);
     n_newton = newton_it;
-    ypost = y;
+#pragma unroll
+    for (int j = 0; j < P; ++j) ypost[j] = y[j];
     r = nl;
     exit_reason = r <= opt.abstol ? ECONPDES_EXIT_CONVERGED : ECONPDES_EXIT_INF_STEP_FAILED;
   } else {
@@ -281,21 +341,21 @@ __global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args)
       int status;
       if (nl <= opt.inner_abstol && rn <= opt.max_residual_growth * old_r) {   // :418
         status = ECONPDES_STEP_ACCEPTED;
-        if (i == 0 && args.log != nullptr && log_len < args.log_capacity) {
+        if (t == 0 && args.log != nullptr && log_len < args.log_capacity) {
           econpdes_log_row& row = args.log[b * args.log_capacity + log_len];
           row.iter = iter; row.status = status; row.newton_iters = newton_it; row.linear_iters = 0;
           row.delta = ctl.delta; row.residual = rn;
         }
         ctl.accept(old_r, rn);
-        ypost = y;
-        Gpost = Gy;
+#pragma unroll
+        for (int j = 0; j < P; ++j) { ypost[j] = y[j]; Gpost[j] = Gy[j]; }
         r = rn;
       } else {
         if (nl <= opt.inner_abstol) status = ECONPDES_STEP_REJECTED_GROWTH;          // :425
         else if (nl != nl) status = ECONPDES_STEP_REJECTED_NAN;                       // :443
         else if (isinf(nl)) status = ECONPDES_STEP_REJECTED_SINGULAR;                 // :444
         else status = ECONPDES_STEP_REJECTED_INNER;                                   // :439
-        if (i == 0 && args.log != nullptr && log_len < args.log_capacity) {
+        if (t == 0 && args.log != nullptr && log_len < args.log_capacity) {
           econpdes_log_row& row = args.log[b * args.log_capacity + log_len];
           row.iter = iter; row.status = status; row.newton_iters = newton_it; row.linear_iters = 0;
           row.delta = ctl.delta; row.residual = NAN;
@@ -311,8 +371,9 @@ __global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args)
     else exit_reason = ECONPDES_EXIT_MAXITERS;
   }
 
-  if (act) args.solution[b * S + i] = ypost;
-  if (i == 0) {
+  publish(ypost);   // coalesced store of the solution through shared memory
+  for (int k = t; k < S; k += T) args.solution[b * S + k] = ysh[k + 1];
+  if (t == 0) {
     args.residual_norm[b] = r;
     args.exit_reason[b] = exit_reason;
     args.n_outer[b] = n_outer;
@@ -322,6 +383,7 @@ __global__ void __launch_bounds__(1024, 1) k_batched_pdesolve_1d(BatchArgs args)
   }
 }
 
-inline size_t batched_smem_bytes(int T) { return sizeof(double) * ((T + 2) + 8 * 32 + 16 + 8 * T); }
+// T threads of P points each
+inline size_t batched_smem_bytes(int T, int P) { return sizeof(double) * ((T * P + 2) + 8 * 32 + 16 + 8 * T + 4 * T); }
 
 }  // namespace econpdes

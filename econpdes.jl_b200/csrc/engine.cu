@@ -12,6 +12,8 @@
 #include <tuple>
 #include <vector>
 
+#include <cstdlib>
+
 #include "batched1d.cuh"
 #include "tridiag.cuh"
 
@@ -57,23 +59,42 @@ double Norms::norm2_over_n(long long n) const {
 // ---------------------------------------------------------------------------------------
 // model registry
 // ---------------------------------------------------------------------------------------
+std::atomic<int> g_batch_points_per_thread{0};
+
 template <class M, bool ONE_D = (M::N == 1 && M::F == 1)>
 struct BatchedLaunch {
   static bool run(const BatchArgs&, cudaStream_t) { return false; }
 };
 template <class M>
 struct BatchedLaunch<M, true> {
-  static bool run(const BatchArgs& a, cudaStream_t s) {
-    const int T = ((a.S + 31) / 32) * 32;
-    if (T > 1024) return false;
-    const size_t smem = batched_smem_bytes(T);
+  template <int P>
+  static void launch(const BatchArgs& a, cudaStream_t s) {
+    const int T = (((a.S + P - 1) / P + 31) / 32) * 32;
+    const size_t smem = batched_smem_bytes(T, P);
     static bool configured = false;
     if (!configured) {
-      EP_CUDA(cudaFuncSetAttribute(k_batched_pdesolve_1d<M>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(batched_smem_bytes(1024))));
+      EP_CUDA(cudaFuncSetAttribute((k_batched_pdesolve_1d<M, P>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(batched_smem_bytes(batched_max_threads(P), P))));
       configured = true;
     }
-    EP_LAUNCH(k_batched_pdesolve_1d<M>, static_cast<unsigned>(a.nproblems), T, smem, s, a);
+    EP_LAUNCH((k_batched_pdesolve_1d<M, P>), static_cast<unsigned>(a.nproblems - a.problem0), T, smem, s, a);
+  }
+  static bool run(const BatchArgs& a, cudaStream_t s) {
+    if (a.S > 1024) return false;
+    // grid points per thread (batched1d.cuh): econpdes_set_batch_points_per_thread, else the
+    // ECONPDES_BATCH_P environment variable, else by problem size
+    static const int env = [] {
+      const char* e = std::getenv("ECONPDES_BATCH_P");
+      return e ? std::atoi(e) : 0;
+    }();
+    const int knob = g_batch_points_per_thread.load();
+    const int forced = knob ? knob : env;
+    int P = forced ? forced : (a.S > 256 ? 4 : (a.S > 64 ? 2 : 1));
+    while (P > 1 && (a.S + P - 1) / P > batched_max_threads(P)) --P;
+    if (P >= 4) launch<4>(a, s);
+    else if (P == 3) launch<3>(a, s);
+    else if (P >= 2) launch<2>(a, s);
+    else launch<1>(a, s);
     return true;
   }
 };

@@ -55,6 +55,8 @@ struct DevBuf {
   size_t pad_alloc_ = 0;
 };
 
+extern std::atomic<int> g_batch_points_per_thread;   // 0 = automatic (api: econpdes_set_batch_points_per_thread)
+
 // Problem resident on one device.
 struct Ctx {
   int model_id = -1, N = 0, F = 0, nparams = 0, nsaved = 0;

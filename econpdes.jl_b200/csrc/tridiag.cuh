@@ -223,4 +223,64 @@ __device__ __forceinline__ double block_pcr_solve(double a, double b, double c, 
   return d / b;
 }
 
+// ---- P consecutive rows per thread: Schur complement onto one interface row per thread ----
+// Thread t owns rows P t .. P t + P - 1.  Its first P - 1 rows (the chunk interior, a small
+// tridiagonal block T_t) are eliminated in registers by the Thomas algorithm with three right-hand
+// sides, which expresses them through the interface unknowns u_{t-1}, u_t (u_t = x_{P t + P - 1}):
+//      x_int = p - q u_{t-1} - r u_t,   p = T_t^{-1} d_int,  q = T_t^{-1} (a_0 e_0),  r = T_t^{-1} (c_{P-2} e_{P-2})
+// Substituting the last interior row of chunk t and the first of chunk t+1 into interface row t
+// leaves a tridiagonal system in u with one row per thread, solved by block_pcr_solve; the
+// interiors follow by back-substitution.  For P = 2 this is one odd-even reduction step.  Work per
+// row falls from ~log2(n) PCR updates to ~log2(n/P)/P + a few Thomas updates.
+// a, b, c, d: the thread's rows (rows beyond the system must be identity rows: a = c = d = 0, b = 1);
+// nred = number of interface rows that matter (ceil(n / P)); sh: 8 * blockDim.x doubles;
+// xch: 4 * blockDim.x doubles.  All threads of the block must call it.
+template <int P>
+__device__ __forceinline__ void block_chunk_solve(const double* a, const double* b, const double* c, const double* d,
+                                                  int t, int nred, double* sh, double* xch, double* x) {
+  if constexpr (P == 1) {
+    x[0] = block_pcr_solve(a[0], b[0], c[0], d[0], t, nred, sh);
+  } else {
+    constexpr int m = P - 1;
+    const int T = blockDim.x;
+    double cp[m], p[m], q[m], r[m];
+    {
+      double w = fast_rcp(b[0]);
+      cp[0] = c[0] * w; p[0] = d[0] * w; q[0] = a[0] * w;
+#pragma unroll
+      for (int j = 1; j < m; ++j) {
+        w = fast_rcp(b[j] - a[j] * cp[j - 1]);
+        cp[j] = c[j] * w;
+        p[j] = (d[j] - a[j] * p[j - 1]) * w;
+        q[j] = -(a[j] * q[j - 1]) * w;
+      }
+      r[m - 1] = cp[m - 1];
+#pragma unroll
+      for (int j = m - 2; j >= 0; --j) {
+        p[j] -= cp[j] * p[j + 1];
+        q[j] -= cp[j] * q[j + 1];
+        r[j] = -cp[j] * r[j + 1];
+      }
+    }
+    // first interior row of every chunk, for the interface row of the chunk before it
+    xch[t] = p[0]; xch[T + t] = q[0]; xch[2 * T + t] = r[0];
+    __syncthreads();
+    const bool has_next = t + 1 < T;
+    const double pn = has_next ? xch[t + 1] : 0.0, qn = has_next ? xch[T + t + 1] : 0.0,
+                 rn = has_next ? xch[2 * T + t + 1] : 0.0;
+    const double aI = a[m], cI = c[m];
+    const double A = -aI * q[m - 1];
+    const double B = b[m] - aI * r[m - 1] - cI * qn;
+    const double C = -cI * rn;
+    const double D = d[m] - aI * p[m - 1] - cI * pn;
+    const double u = block_pcr_solve(A, B, C, D, t, nred, sh);
+    xch[3 * T + t] = u;
+    __syncthreads();
+    const double um = t > 0 ? xch[3 * T + t - 1] : 0.0;
+#pragma unroll
+    for (int j = 0; j < m; ++j) x[j] = p[j] - q[j] * um - r[j] * u;
+    x[m] = u;
+  }
+}
+
 }  // namespace econpdes

@@ -464,6 +464,41 @@ def pdesolve_batched(model_cls, params: np.ndarray, grids: np.ndarray, guess: np
     return BatchResult(sol, rn, rn <= abstol, er, no, nn, ms.value, launches, logs)
 
 
+def set_batch_points_per_thread(points: int) -> int:
+    """Tuning knob of the batched engine (grid points owned by one thread; 0 = automatic).
+    Returns the previous setting."""
+    return L.check(L.load().econpdes_set_batch_points_per_thread(int(points)))
+
+
+def solve_batched_one_call(model_cls, params, grids, guess, *, abstol=SQRT_EPS, maxiters=100, **kwargs):
+    """`econpdes_solve_batched`: upload, solve and download in one C call that pipelines slices of
+    the batch over three streams (use pinned host arrays to get the overlap).  Returns
+    (solution, residual_norm, exit_reason, n_outer, n_newton)."""
+    lib = L.load()
+    delta = kwargs.pop("Δ", kwargs.pop("delta", 1.0))
+    opts = _options(abstol, maxiters, kwargs)
+    opts.delta = float(delta)
+    if kwargs:
+        raise TypeError(f"unknown keyword arguments {sorted(kwargs)}")
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    grids = np.ascontiguousarray(grids, dtype=np.float64)
+    guess = np.ascontiguousarray(guess, dtype=np.float64)
+    B, S = grids.shape
+    if guess.shape != (B, S):
+        raise ValueError(f"guess has shape {guess.shape}, expected {(B, S)}")
+    mid = L.check(lib.econpdes_model_id(model_cls.name.encode()))
+    sol = np.empty((B, S))
+    rn = np.empty(B)
+    er = np.empty(B, dtype=np.int32)
+    no = np.empty(B, dtype=np.int32)
+    nn = np.empty(B, dtype=np.int32)
+    L.check(lib.econpdes_solve_batched(mid, B, S, L.dptr(params) if params.size else None, L.dptr(grids),
+                                       L.dptr(guess), C.byref(opts), L.dptr(sol), L.dptr(rn),
+                                       er.ctypes.data_as(L.c_int32_p), no.ctypes.data_as(L.c_int32_p),
+                                       nn.ctypes.data_as(L.c_int32_p)))
+    return sol, rn, er, no, nn
+
+
 class Handle:
     """Repeated residual / Jacobian / Newton-step evaluations on one device-resident problem
     (the `G!`, `finite_difference_jacobian!` and `implicit_timestep` seams of

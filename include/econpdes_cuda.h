@@ -223,6 +223,12 @@ int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, con
  * shape; this frees it. */
 void econpdes_release_workspace(void);
 
+/* Tuning knob of the batched engine: grid points owned by one thread (1, 2, 3 or 4; 0 = choose from
+ * the problem size, the default).  Results agree to round-off of the tridiagonal solve for every
+ * setting (the reference's sparse LU is replaced either way); exposed so tests can cover each variant.
+ * Returns the previous setting. */
+int econpdes_set_batch_points_per_thread(int points);
+
 /* --- device / multi-GPU plumbing --- */
 int econpdes_device_count(void);
 int econpdes_set_device(int device);

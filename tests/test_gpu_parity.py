@@ -313,6 +313,70 @@ def test_batched_small_and_ragged_sizes():
         E.pdesolve_batched(PM.ReadmeLinear, np.array([[0.05, 0.2]]), x[None, :], np.zeros((1, 1025)))
 
 
+@pytest.fixture
+def points_per_thread():
+    """restores the automatic choice of the batched engine's points-per-thread knob"""
+    yield E.set_batch_points_per_thread
+    E.set_batch_points_per_thread(0)
+
+
+def test_batched_points_per_thread_variants(points_per_thread):
+    """Every thread-blocking of the fused kernel (1-4 consecutive points per thread; the chunked
+    tridiagonal solve differs per variant) against the oracle and against each other."""
+    prms, params, grids, guess = _sweep(3)
+    oras = [eo.pdesolve(OM.campbell_cochrane(**prm), {"s": grids[b]}, {"p": guess[b]}) for b, prm in enumerate(prms)]
+    g, gu, prm = OM.neoclassical_growth_problem(1000)
+    gparams = np.array([[prm[k] for k in ("A", "alpha", "delta", "rho", "gamma")]])
+    gora = eo.pdesolve(OM.neoclassical_growth(**prm), g, gu)
+    sols = []
+    for P in (1, 2, 3, 4):
+        points_per_thread(P)
+        out = E.pdesolve_batched(PM.CampbellCochraneModel, params, grids, guess, log_capacity=16)
+        sols.append(out.solution)
+        for b, ora in enumerate(oras):
+            np.testing.assert_allclose(out.solution[b], ora.solution["p"], rtol=1e-8)
+            assert abs(out.residual_norm[b] - ora.residual_norm) <= 1e-10
+            assert out.n_outer[b] == ora.log.n_outer and out.n_newton[b] == ora.log.n_newton
+            assert ["%.2e" % r["delta"] for r in out.log[b]] == ["%.2e" % o[1] for o in ora.log.rows]
+        # rejected steps, 11 outer iterations
+        out = E.pdesolve_batched(PM.NeoclassicalGrowthModel, gparams, g["k"][None, :], gu["v"][None, :], log_capacity=32)
+        assert out.n_outer[0] == 11 and out.n_newton[0] == gora.log.n_newton
+        assert [r["status"] for r in out.log[0]] == [r[3] for r in gora.log.rows]
+        np.testing.assert_allclose(out.solution[0], gora.solution["v"], rtol=1e-8)
+        # ragged sizes: fewer points than one chunk, a partly filled last chunk, the maximum
+        for S in (2, 3, 5, 31, 33, 50, 257, 1021, 1024):
+            x = OM.julia_range(0.0, 1.0, S)
+            o = E.pdesolve_batched(PM.ReadmeLinear, np.array([[0.05, 0.2]]), x[None, :], np.zeros((1, S)))
+            ora = eo.pdesolve(OM.readme_linear(), {"x": x}, {"v": np.zeros(S)})
+            # (on this linear problem round-off of the linear solve decides whether a step takes one more
+            # Newton iteration, so iteration counts are only compared on the models above)
+            assert bool(o.converged[0]) == ora.converged and o.n_outer[0] == ora.log.n_outer
+            np.testing.assert_allclose(o.solution[0], ora.solution["v"], rtol=1e-8, atol=1e-12)
+    for s in sols[1:]:
+        np.testing.assert_allclose(s, sols[0], rtol=1e-10)
+
+
+def test_one_call_pipelined_path_matches_handle_path():
+    """econpdes_solve_batched slices the batch over three copy/compute streams; the result must be
+    the handle path's, bit for bit (also with a ragged last slice and from pageable memory)."""
+    prms, params, grids, guess = _sweep(4)
+    for B in (3, 2 * 8 * 148 + 37):
+        reps = (B + 3) // 4
+        Pm, G, U = np.tile(params, (reps, 1))[:B], np.tile(grids, (reps, 1))[:B], np.tile(guess, (reps, 1))[:B]
+        ref = E.pdesolve_batched(PM.CampbellCochraneModel, Pm, G, U)
+        sol, rn, er, no, nn = E.solve_batched_one_call(PM.CampbellCochraneModel, Pm, G, U)
+        np.testing.assert_array_equal(sol, ref.solution)
+        np.testing.assert_array_equal(rn, ref.residual_norm)
+        np.testing.assert_array_equal(er, ref.exit_reason)
+        np.testing.assert_array_equal(no, ref.n_outer)
+        np.testing.assert_array_equal(nn, ref.n_newton)
+    # a NaN guess in a late slice is reported like the reference's ArgumentError
+    U = U.copy()
+    U[B - 5, 10] = np.nan
+    with pytest.raises(E.EconPDEsCudaError, match="NaN with the initial value"):
+        E.solve_batched_one_call(PM.CampbellCochraneModel, Pm, G, U)
+
+
 def test_batched_inf_delta_and_already_zero():
     x = OM.julia_range(0.0, 1.0, 40)
     out = E.pdesolve_batched(PM.LinearSum1D, np.zeros((1, 0)), x[None, :], np.zeros((1, 40)), Δ=INF)
