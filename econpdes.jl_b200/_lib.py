@@ -91,6 +91,7 @@ SYMBOLS = {
                                          c_int32_p]),
     "econpdes_release_workspace": (None, []),
     "econpdes_set_batch_points_per_thread": (C.c_int, [C.c_int]),
+    "econpdes_selftest_reciprocal": (C.c_int, [C.c_uint64, C.c_int64, C.POINTER(C.c_int64)]),
     "econpdes_device_count": (C.c_int, []),
     "econpdes_set_device": (C.c_int, [C.c_int]),
     "econpdes_total_kernel_launches": (C.c_int64, []),

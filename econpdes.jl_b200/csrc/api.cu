@@ -32,6 +32,47 @@ int guarded(Fn&& fn) {
 
 }  // namespace
 
+namespace {
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long& st) {
+  unsigned long long z = (st += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ bool same_bits(double x, double y) {
+  return (x != x && y != y) || __double_as_longlong(x) == __double_as_longlong(y);
+}
+__global__ void k_selftest_reciprocal(unsigned long long seed, long long n, unsigned long long* mismatch) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  unsigned long long m0 = 0, m1 = 0, m2 = 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    unsigned long long st = seed + 0x632BE59BD9B4E019ull * static_cast<unsigned long long>(i);
+    unsigned long long bb = splitmix64(st);
+    const unsigned long long ab = splitmix64(st);
+    // every 8th draw: a mantissa of all ones / all zeros / one bit (the hard cases of the correction step)
+    if ((i & 7) == 7) bb = (bb & 0xFFF0000000000000ull) | ((i & 8) ? 0x000FFFFFFFFFFFFFull : ((i & 16) ? 1ull : 0ull));
+    const double b = __longlong_as_double(static_cast<long long>(bb));
+    const double a = __longlong_as_double(static_cast<long long>(ab));
+    const double want = 1.0 / b, got = ep_rcp(b);
+    const double fb = fabs(b);
+    if (fb >= 0x1p1022 && fb < INFINITY) {
+      const long long d = __double_as_longlong(got) - __double_as_longlong(want);
+      if (d > 1 || d < -1) ++m2;
+    } else if (!same_bits(got, want)) {
+      ++m0;
+    }
+    // quotients: a = 0 / Inf / NaN, or a and a / b at least 2^-900 (the correction step a - q0 b must not
+    // underflow; below that the subnormal result may be rounded twice)
+    const double fa = fabs(a), q = a / b;
+    const bool a_ok = !(fa > 0.0) || !(fa < INFINITY) || (fa >= 0x1p-900 && fabs(q) >= 0x1p-900);
+    if (fb >= 0x1p-1000 && fb <= 0x1p1000 && a_ok && !same_bits(mdiv(a, b, got), q)) ++m1;
+  }
+  if (m0) atomicAdd(&mismatch[0], m0);
+  if (m1) atomicAdd(&mismatch[1], m1);
+  if (m2) atomicAdd(&mismatch[2], m2);
+}
+}  // namespace
+
 struct econpdes_handle {
   std::unique_ptr<Solver> solver;
   DevBuf<double> a, b, c;
@@ -504,6 +545,21 @@ int64_t econpdes_batch_kernel_launches(const econpdes_batch* b) { return b ? b->
 // calibration loop calls it thousands of times): cudaMalloc/cudaFree of ~0.5 GB per call
 // cost more than the solve.  econpdes_release_workspace() frees it.
 static thread_local econpdes_batch* t_workspace = nullptr;
+
+int econpdes_selftest_reciprocal(uint64_t seed, int64_t n, int64_t mismatch[3]) {
+  return guarded([&] {
+    if (!mismatch || n < 0) throw std::invalid_argument("bad argument");
+    ensure_device();
+    DevBuf<unsigned long long> d;
+    d.alloc(3);
+    EP_CUDA(cudaMemset(d.p, 0, 3 * sizeof(unsigned long long)));
+    EP_LAUNCH(k_selftest_reciprocal, 148 * 8, 256, 0, nullptr, seed, n, d.p);
+    unsigned long long h[3];
+    EP_CUDA(cudaMemcpy(h, d.p, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 3; ++i) mismatch[i] = static_cast<int64_t>(h[i]);
+    return static_cast<int>(ECONPDES_OK);
+  });
+}
 
 int econpdes_set_batch_points_per_thread(int points) {
   if (points < 0 || points > 4) {

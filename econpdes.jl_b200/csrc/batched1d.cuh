@@ -87,7 +87,10 @@ constexpr int batched_max_threads(int P) { return ((1024 + P - 1) / P + 31) / 32
 // reductions, barriers, controller, color steps) is shared by P points, the P evaluations are
 // independent instruction streams, and the tridiagonal solve only runs PCR on the T interface rows
 // (block_chunk_solve, tridiag.cuh).
-template <class M, int P>
+// PER_COL: eps_policy == ECONPDES_EPS_PER_COLUMN, fixed at compile time so that the Newton iteration has no
+// data-independent branches: together with the branch-free reciprocals (ep_rcp, mdiv) the evaluations of a
+// thread's P points form one basic block the scheduler can interleave.
+template <class M, int P, bool PER_COL>
 __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_1d(BatchArgs args) {
   static_assert(M::N == 1 && M::F == 1, "the fused batched engine handles 1-D single-unknown models");
   extern __shared__ double smem[];
@@ -198,12 +201,12 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
 
   auto newton = [&](double delta, double ftol, int maxit) {
     RowTerms rt[P];
-    const double rdelta = isfinite(delta) ? 1.0 / delta : 0.0;   // once per Newton solve
+    const double rdelta = 1.0 / delta;   // once per Newton solve; 1/Inf = 0 makes mdiv return the IEEE quotient 0
     double R[P];
 #pragma unroll
     for (int j = 0; j < P; ++j) {
       rt[j].implicit = true; rt[j].has_bounds = false; rt[j].ypost = ypost[j]; rt[j].delta = delta;
-      rt[j].is_alg = false; rt[j].lb = 0.0; rt[j].ub = 0.0; rt[j].rdelta = rdelta;
+      rt[j].is_alg = false; rt[j].lb = 0.0; rt[j].ub = 0.0; rt[j].rdelta = rdelta; rt[j].rdelta_always = true;
       y[j] = ypost[j];
       Gy[j] = Gpost[j];
       R[j] = act[j] ? apply_row_terms(Gy[j], y[j], rt[j]) : 0.0;
@@ -265,18 +268,16 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
         for (int k = 0; k < P + 2; ++k) yv[k] = ysh[i0 + k];
 #pragma unroll
         for (int j = 0; j < P; ++j) {
-          ja[j] = 0.0; jb[j] = 1.0; jc[j] = 0.0; rhs[j] = 0.0;
-          if (act[j]) {
-            double w[1][3] = {{yv[j], yv[j + 1], yv[j + 2]}};
-            double r0[1] = {R[j]};
-            double va = 0.0, vb = 1.0, vc = 0.0;
-            jacobian_point<M, false, true>(pre[j], g[j], idx[j], gv, w, bl, bh, &rt[j], eps_table,
-                                           opt.eps_policy == ECONPDES_EPS_PER_COLUMN, r0,
-                                           [&](int k, int, int, double v) {
-                                             if (k == 0) vb = v; else if (k == 1) va = v; else vc = v;
-                                           }, reps_table);
-            ja[j] = va; jb[j] = vb; jc[j] = vc; rhs[j] = R[j];
-          }
+          // inactive points (beyond the grid, last thread only) are evaluated too and replaced by
+          // identity rows: a select instead of a branch keeps the P evaluations in one basic block
+          double w[1][3] = {{yv[j], yv[j + 1], yv[j + 2]}};
+          double r0[1] = {R[j]};
+          double va = 0.0, vb = 1.0, vc = 0.0;
+          jacobian_point<M, false, true, PER_COL ? 1 : 0>(pre[j], g[j], idx[j], gv, w, bl, bh, &rt[j], eps_table, PER_COL,
+                                                          r0, [&](int k, int, int, double v) {
+                                                            if (k == 0) vb = v; else if (k == 1) va = v; else vc = v;
+                                                          }, reps_table);
+          ja[j] = act[j] ? va : 0.0; jb[j] = act[j] ? vb : 1.0; jc[j] = act[j] ? vc : 0.0; rhs[j] = R[j];
         }
       }
       double sol[P];

@@ -67,17 +67,22 @@ struct BatchedLaunch {
 };
 template <class M>
 struct BatchedLaunch<M, true> {
-  template <int P>
+  template <int P, bool PER_COL>
   static void launch(const BatchArgs& a, cudaStream_t s) {
     const int T = (((a.S + P - 1) / P + 31) / 32) * 32;
     const size_t smem = batched_smem_bytes(T, P);
     static bool configured = false;
     if (!configured) {
-      EP_CUDA(cudaFuncSetAttribute((k_batched_pdesolve_1d<M, P>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+      EP_CUDA(cudaFuncSetAttribute((k_batched_pdesolve_1d<M, P, PER_COL>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(batched_smem_bytes(batched_max_threads(P), P))));
       configured = true;
     }
-    EP_LAUNCH((k_batched_pdesolve_1d<M, P>), static_cast<unsigned>(a.nproblems - a.problem0), T, smem, s, a);
+    EP_LAUNCH((k_batched_pdesolve_1d<M, P, PER_COL>), static_cast<unsigned>(a.nproblems - a.problem0), T, smem, s, a);
+  }
+  template <int P>
+  static void launch(const BatchArgs& a, cudaStream_t s) {
+    if (a.opt.eps_policy == ECONPDES_EPS_PER_COLUMN) launch<P, true>(a, s);
+    else launch<P, false>(a, s);
   }
   static bool run(const BatchArgs& a, cudaStream_t s) {
     if (a.S > 1024) return false;

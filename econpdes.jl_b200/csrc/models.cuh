@@ -84,7 +84,7 @@ struct CampbellCochrane : ModelDefaults {
     const double p = u[0].v, pss = u[0].dd[0];
     const double ps = (c.mus_eff >= 0) ? u[0].up[0] : u[0].dn[0];
     // one IEEE reciprocal of p; the other quotients by p reuse it (mdiv: same bits as `/`)
-    const double rp = 1 / p;
+    const double rp = ep_rcp(p);   // RN(1/p), branch-free
     const double ps_p = mdiv(ps, p, rp);
     const double sigp = ps_p * c.sigs;
     const double mup = ps_p * c.mus + mdiv(0.5 * pss, p, rp) * c.sigs2;
@@ -121,7 +121,7 @@ struct BansalYaron : ModelDefaults {
     const double p = u[0].v;
     const double pmu = (c.mumu >= 0) ? u[0].up[0] : u[0].dn[0];
     const double pv = (c.muv >= 0) ? u[0].up[1] : u[0].dn[1];
-    const double rp = 1 / p;   // the other quotients by p reuse it (mdiv: same bits as `/`)
+    const double rp = ep_rcp(p);   // RN(1/p); the other quotients by p reuse it (mdiv: same bits as `/`)
     const double pmu_p = mdiv(pmu, p, rp), pv_p = mdiv(pv, p, rp);
     const double sigp_Zmu = pmu_p * c.sigmu;
     const double sigp_Zv = pv_p * c.sigv;

@@ -151,13 +151,17 @@ struct RowTerms {
   double ypost, delta, lb, ub;
   bool is_alg;
   double rdelta = 0.0;  // RN(1/delta) when the caller formed it once for many rows (finite delta only), else 0
+  // the caller guarantees rdelta = RN(1/delta) for EVERY delta (1/Inf = 0 included: mdiv then returns
+  // the IEEE quotient +-0), so the quotient never needs the division -- a compile-time constant in the
+  // batched kernel, which removes the branch
+  bool rdelta_always = false;
 };
 
 EP_HD double apply_row_terms(double g, double y, const RowTerms& t) {
   double r = g;
   // `.!is_algebraic .* (ypost .- y) ./ Δ`: Bool true is an exact 1, false a strong zero
   if (t.implicit && !t.is_alg)
-    r = r - (t.rdelta != 0.0 ? mdiv(t.ypost - y, t.delta, t.rdelta) : (t.ypost - y) / t.delta);
+    r = r - ((t.rdelta_always || t.rdelta != 0.0) ? mdiv(t.ypost - y, t.delta, t.rdelta) : (t.ypost - y) / t.delta);
   if (t.has_bounds) {
     const double a = y - t.ub, b = y - t.lb;
     double m = r > a ? r : a;      // max(r, y-ub)   (NaN in r propagates like Julia's max)
@@ -211,7 +215,9 @@ EP_HD int ncolors_grid(const GridView<N>& gv) {
 // entries outside the grid).  r0 returns R(pt) itself (the unperturbed residual).
 // With HAVE_R0 the caller already holds R(pt) in r0 (FiniteDiff re-evaluates f(x); the
 // value is identical, so kernels that kept it skip that evaluation).
-template <class M, bool BOX, bool HAVE_R0 = false, class G, class Emit>
+// POLICY: -1 = `eps_per_column` decides at run time; 0 = per-color steps from eps_table, with their
+// reciprocals in reps_table (required); 1 = per-column steps.  The compile-time forms are branch-free.
+template <class M, bool BOX, bool HAVE_R0 = false, int POLICY = -1, class G, class Emit>
 EP_HD void jacobian_point(const typename M::Pre& pre, const G& g, const long long* idx,
                           const GridView<M::N>& gv, double (*w)[ipow3(M::N)], const double (*bc_lo)[M::N],
                           const double (*bc_hi)[M::N], const RowTerms* rt, const double* eps_table,
@@ -243,19 +249,21 @@ EP_HD void jacobian_point(const typename M::Pre& pre, const G& g, const long lon
         stride *= gv.S[d] < 3 ? static_cast<int>(gv.S[d]) : 3;
       }
       const int slot = St::boxslot(k);
-      if (!ok || !M::slot_used(slot)) {
+      // entries outside the grid: skipped, or (branch-free forms) evaluated anyway and zeroed below
+      if ((POLICY < 0 && !ok) || !M::slot_used(slot)) {
 #pragma unroll
         for (int fout = 0; fout < F; ++fout) emit(k, fin, fout, 0.0);
         continue;
       }
       const double saved = w[fin][slot];
       double eps, reps = 0.0;   // reps: RN(1/eps) when the caller tabulated it with the color steps
-      if (eps_per_column) {
+      if (POLICY == 1 || (POLICY < 0 && eps_per_column)) {
         const double a = fabs(saved);
         eps = kSqrtEps * (a > 1.0 ? a : 1.0);
+        if (POLICY == 1) reps = ep_rcp(eps);
       } else {
         eps = eps_table[color + fin * ncg];
-        if (reps_table != nullptr) reps = reps_table[color + fin * ncg];
+        if (POLICY == 0 || reps_table != nullptr) reps = reps_table[color + fin * ncg];
       }
       w[fin][slot] = saved + eps;
       double g1[F];
@@ -263,7 +271,8 @@ EP_HD void jacobian_point(const typename M::Pre& pre, const G& g, const long lon
 #pragma unroll
       for (int fout = 0; fout < F; ++fout) {
         const double r1 = apply_row_terms(g1[fout], w[fout][C], rt[fout]);
-        emit(k, fin, fout, reps != 0.0 ? mdiv(r1 - r0[fout], eps, reps) : (r1 - r0[fout]) / eps);
+        const double q = (POLICY >= 0 || reps != 0.0) ? mdiv(r1 - r0[fout], eps, reps) : (r1 - r0[fout]) / eps;
+        emit(k, fin, fout, ok ? q : 0.0);
       }
       w[fin][slot] = saved;
     }

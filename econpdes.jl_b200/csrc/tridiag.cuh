@@ -220,7 +220,7 @@ __device__ __forceinline__ double block_pcr_solve(double a, double b, double c, 
     c = nc;
     buf ^= 1;  // the next step writes the other buffer, so one barrier per step suffices
   }
-  return d / b;
+  return d * fast_rcp(b);
 }
 
 // ---- P consecutive rows per thread: Schur complement onto one interface row per thread ----

@@ -229,6 +229,16 @@ void econpdes_release_workspace(void);
  * Returns the previous setting. */
 int econpdes_set_batch_points_per_thread(int points);
 
+/* Device self-test of the branch-free reciprocal and quotient the kernels use in place of IEEE division
+ * (stencil.cuh: ep_rcp, mdiv).  Draws `n` operand pairs (a, b) as uniformly random 64-bit patterns (every
+ * exponent, subnormals, Inf and NaN, extreme mantissas) from `seed` and counts results whose bits differ
+ * from the compiler's 1.0 / b and a / b.  All three counts must be 0:
+ *   mismatch[0]  reciprocals, for |b| < 2^1022 and b = 0, Inf, NaN
+ *   mismatch[1]  quotients a / b through RN(1/b), for |b| in [2^-1000, 2^1000] and a = 0, Inf, NaN or |a| and
+ *                |a / b| at least 2^-900 (nearer the underflow threshold a subnormal result may round twice)
+ *   mismatch[2]  reciprocals with |b| >= 2^1022 (subnormal results) off by more than one unit in the last place */
+int econpdes_selftest_reciprocal(uint64_t seed, int64_t n, int64_t mismatch[3]);
+
 /* --- device / multi-GPU plumbing --- */
 int econpdes_device_count(void);
 int econpdes_set_device(int device);
