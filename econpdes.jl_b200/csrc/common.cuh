@@ -52,6 +52,11 @@ struct ProfScope {
 
 constexpr int kBlock = 256;
 inline int blocks_for(long long n, int block = kBlock) { return static_cast<int>((n + block - 1) / block); }
+// grid of a grid-stride sweep that ends in a grid-wide reduction: at most 16 blocks per SM of a B200
+inline int sweep_blocks(long long n, int block = kBlock) {
+  const int b = blocks_for(n, block);
+  return b < 148 * 16 ? b : 148 * 16;
+}
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ double warp_sum(double v) {

@@ -125,7 +125,7 @@ struct ModelOpsT final : ModelOps {
   int nsaved() const override { return M::NSAVED; }
   bool box() const override { return M::USES_CROSS && M::N > 1; }
   void residual(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm) const override {
-    EP_LAUNCH(k_residual<M>, blocks_for(c.l), kBlock, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p, rs, out,
+    EP_LAUNCH(k_residual<M>, sweep_blocks(c.l), kBlock, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p, rs, out,
               c.nw(), want_norm ? 1 : 0);
   }
   void jacobian(const Ctx& c, const double* y, const RowSpec& rs, int eps_policy, double* planes,
@@ -487,7 +487,7 @@ NewtonOutcome Solver::newton(const double* ypost, double delta, double ftol, int
       EP_CUDA(cudaMemcpyAsync(y_out, ypost, n * sizeof(double), cudaMemcpyDeviceToDevice, c_->stream));
       return out;
     }
-    EP_LAUNCH(k_newton_update, blocks_for(n), kBlock, 0, c_->stream, n, x, s_.p, xn, c_->nw());
+    EP_LAUNCH(k_newton_update, sweep_blocks(n), kBlock, 0, c_->stream, n, x, s_.p, xn, c_->nw());
     Norms nx = read_norms();
     std::swap(x, xn);
     nr = eval_R(x, ypost, delta, R_.p);
