@@ -48,7 +48,7 @@ __device__ __forceinline__ RowTerms make_row_terms(const RowSpec& rs, long long 
 // single-evaluation sweeps: tabulated reciprocals pay off from three dimensions on (15+ stencil
 // quotients per point); below that the extra registers cost more than the divisions (measured)
 template <int N>
-constexpr int kSweepRecip = N >= 3 ? 1 : 0;
+constexpr int kSweepRecip = N >= 2 ? 1 : 0;
 
 template <class M, int RECIP>
 struct PointLoad {
@@ -119,7 +119,7 @@ constexpr int kMaxColors = 27 * 4;
 struct ColorWork {
   double* part;       // [max_blocks][ncolors]
   unsigned* counter;
-  double* eps;        // [ncolors] out: sqrt(eps)*max(1, sqrt(||x.*mask_c||_2))
+  double* eps;        // [2 * ncolors] out: sqrt(eps)*max(1, sqrt(||x.*mask_c||_2)), then the reciprocals
   double* sumsq;      // [ncolors] out
 };
 
@@ -189,7 +189,9 @@ __global__ void __launch_bounds__(kBlock) k_color_sumsq(GridView<N> gv, int F, c
         double tot = 0.0;
         for (int w = 0; w < nwarps; ++w) tot += fin[w];
         cw.sumsq[c] = tot;
-        cw.eps[c] = color_epsilon_from_sumsq(tot);
+        const double e = color_epsilon_from_sumsq(tot);
+        cw.eps[c] = e;
+        cw.eps[nc + c] = 1.0 / e;   // RN(1/eps): the Jacobian kernel divides through it (mdiv)
       }
       __syncthreads();
     }
@@ -199,25 +201,28 @@ __global__ void __launch_bounds__(kBlock) k_color_sumsq(GridView<N> gv, int F, c
 
 // Fused colored FD Jacobian: planes[((k*F + fin)*F + fout)*l + pt] = dR_fout(pt)/dy_fin(pt+off_k)
 // for the stencil shape <N,BOX>.  r0 (may be nullptr) receives R(y).
-template <class M, bool BOX>
-__global__ void __launch_bounds__(kBlock) k_jacobian(GridView<M::N> gv, ParamPack prm, const double* __restrict__ y,
-                                                     const double* __restrict__ bc, RowSpec rs,
-                                                     const double* __restrict__ eps_table, int eps_per_column,
-                                                     double* __restrict__ planes, double* __restrict__ r0out) {
+// POLICY: 0 = per-color steps (eps_table holds the steps, then their reciprocals), 1 = per-column steps
+// (see jacobian_point); MINB = resident blocks per SM asked of the register allocator.
+template <class M, bool BOX, int POLICY, int MINB = 2>
+__global__ void __launch_bounds__(kBlock, MINB) k_jacobian(GridView<M::N> gv, ParamPack prm, const double* __restrict__ y,
+                                                           const double* __restrict__ bc, RowSpec rs,
+                                                           const double* __restrict__ eps_table, int eps_per_column,
+                                                           double* __restrict__ planes, double* __restrict__ r0out) {
   constexpr int F = M::F;
   const long long pt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (pt >= gv.l) return;
-  PointLoad<M, M::N >= 3 ? (M::USES_CROSS ? 2 : 1) : 0> P;   // see kSweepRecip: 2-D kernels are register-bound
+  PointLoad<M, M::N >= 2 ? (M::USES_CROSS ? 2 : 1) : 0> P;
   P.load(gv, pt, y, bc, prm.v);
   RowTerms rt[F];
 #pragma unroll
   for (int f = 0; f < F; ++f) rt[f] = make_row_terms(rs, f * gv.l + pt);
   double r0[F];
   const long long l = gv.l;
-  jacobian_point<M, BOX>(P.pre, P.g, P.idx, gv, P.w, P.bl, P.bh, rt, eps_table, eps_per_column, r0,
-                         [&](int k, int fin, int fout, double v) {
-                           planes[(static_cast<long long>(k * F + fin) * F + fout) * l + pt] = v;
-                         });
+  const double* reps_table = POLICY == 0 ? eps_table + ncolors_grid<M::N>(gv) * F : nullptr;
+  jacobian_point<M, BOX, false, POLICY>(P.pre, P.g, P.idx, gv, P.w, P.bl, P.bh, rt, eps_table, eps_per_column, r0,
+                                        [&](int k, int fin, int fout, double v) {
+                                          planes[(static_cast<long long>(k * F + fin) * F + fout) * l + pt] = v;
+                                        }, reps_table);
   if (r0out != nullptr) {
 #pragma unroll
     for (int f = 0; f < F; ++f) r0out[f * l + pt] = r0[f];

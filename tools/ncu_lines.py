@@ -1,15 +1,16 @@
 """Aggregate an .ncu-rep's source page (needs -lineinfo and --import-source on) into executed
 warp instructions and stall samples per source line.
 
-    python tools/ncu_lines.py gpurun_out/prof.ncu-rep [top=50]
+    python tools/ncu_lines.py gpurun_out/prof.ncu-rep [top=50] [index of the launch in the report]
 """
 import csv
 import subprocess
 import sys
 
 
-def main(rep, top=50):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"],
+def main(rep, top=50, skip=None):
+    sel = [] if skip is None else ["--launch-skip", str(skip), "--launch-count", "1"]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"] + sel,
                          capture_output=True, text=True).stdout
     cur, hdr, agg = None, None, []
     for r in csv.reader(raw.splitlines()):
@@ -41,4 +42,4 @@ def main(rep, top=50):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 50)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 50, int(sys.argv[3]) if len(sys.argv) > 3 else None)
