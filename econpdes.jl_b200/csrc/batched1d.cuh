@@ -116,6 +116,10 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
     ysh[k + 1] = k < S ? args.guess[b * S + k] : 0.0;
   }
   __syncthreads();
+  if (M::NDERIVED > 0) {   // parameter-only constants of the model, once per problem
+    if (t == 0) M::derive(prm);
+    __syncthreads();
+  }
   GridView<1> gv;
   gv.x[0] = xs; gv.S[0] = S; gv.stride[0] = 1; gv.l = S;
   bool act[P];

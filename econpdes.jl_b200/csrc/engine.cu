@@ -124,6 +124,10 @@ struct ModelOpsT final : ModelOps {
   int N() const override { return M::N; }
   int F() const override { return M::F; }
   int nparams() const override { return M::NPARAMS; }
+  void derive(double* prm) const override {
+    static_assert(M::NPARAMS + M::NDERIVED <= kMaxParams, "parameter pack too small");
+    M::derive(prm);
+  }
   int nsaved() const override { return M::NSAVED; }
   bool box() const override { return M::USES_CROSS && M::N > 1; }
   void residual(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm) const override {
@@ -239,6 +243,7 @@ std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p, Dist* dist, long long s
   if (c->n + 2 * c->halo >= (1LL << 31))
     throw std::invalid_argument("grids of 2^31 unknowns or more per device are not supported (32-bit point indexing)");
   for (int i = 0; i < c->nparams; ++i) c->prm.v[i] = p->params[i];
+  ops->derive(c->prm.v);
   EP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   cudaStream_t s = c->stream;
   for (int d = 0; d < c->N; ++d) {

@@ -88,13 +88,10 @@ struct Ctx {
   template <int NN>
   GridView<NN> grid_view() const {
     GridView<NN> gv;
-    long long st = 1;
+    gv.set_sizes(S);
     for (int d = 0; d < NN; ++d) {
       gv.x[d] = grid[d].p;
       gv.tab[d] = geomtab[d].p;
-      gv.S[d] = S[d];
-      gv.stride[d] = st;
-      st *= S[d];
     }
     gv.l = l;
     gv.off = slab_first;
@@ -122,6 +119,7 @@ struct ModelOps {
   virtual int N() const = 0;
   virtual int F() const = 0;
   virtual int nparams() const = 0;
+  virtual void derive(double* prm) const = 0;   // appends the model's parameter-only constants (models.cuh)
   virtual int nsaved() const = 0;
   virtual bool box() const = 0;
   virtual void residual(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm) const = 0;

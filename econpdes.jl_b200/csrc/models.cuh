@@ -35,7 +35,14 @@ namespace econpdes {
 // (f(x1)-f(x))/eps = 0/eps).
 struct ModelDefaults {
   EP_HD static constexpr bool slot_used(int) { return true; }
+  // Parameter-only sub-expressions (quotients of parameters, reciprocals for mdiv) are evaluated once
+  // per problem -- on the host when the problem is created, by one thread in the batched kernel -- and
+  // appended to the parameter vector at prm[NPARAMS .. NPARAMS + NDERIVED): the same IEEE operations
+  // the reference performs at every grid point, so the bits are the same.
+  static constexpr int NDERIVED = 0;
+  EP_HD static void derive(double*) {}
 };
+constexpr int kMaxParams = 16;   // ParamPack: NPARAMS + NDERIVED
 
 EP_HD double ep_min(double a, double b) { return a < b ? a : b; }   // operands are never NaN where used
 EP_HD double ep_max(double a, double b) { return a > b ? a : b; }
@@ -94,9 +101,16 @@ struct CampbellCochrane : ModelDefaults {
 
 // examples/asset_pricing/bansal_yaron.jl:65-95   states (mu, v)
 struct BansalYaron : ModelDefaults {
-  static constexpr int N = 2, F = 1, NPARAMS = 9, NSAVED = 0;
+  static constexpr int N = 2, F = 1, NPARAMS = 9, NSAVED = 0, NDERIVED = 4;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "bansal_yaron"; }
+  EP_HD static void derive(double* prm) {
+    const double gamma = prm[7], psi = prm[8];
+    prm[9] = -(1 - gamma * psi) / (psi - 1);            // cz
+    prm[10] = (gamma * psi - 1) / (2 * (psi - 1));      // cs
+    prm[11] = 1 / psi;                                  // RN(1/psi) for muc / psi
+    prm[12] = (1 + 1 / psi) / 2 * gamma;                // leading factor of the precautionary term
+  }
   struct Pre { double muc, mumu, sigmu, sigmu2, muv, sigv, sigv2, cz, r_base, cs, kzc_sigc; };
   EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
     const double mubar = prm[0], vbar = prm[1], kappa_mu = prm[2], nu_mu = prm[3], kappa_v = prm[4],
@@ -111,9 +125,9 @@ struct BansalYaron : ModelDefaults {
     c.sigv = nu_v * sqrt(v);
     c.sigv2 = c.sigv * c.sigv;
     const double kap_Zc = gamma * sigc;
-    c.cz = -(1 - gamma * psi) / (psi - 1);
-    c.r_base = rho + c.muc / psi - (1 + 1 / psi) / 2 * gamma * (sigc * sigc);
-    c.cs = (gamma * psi - 1) / (2 * (psi - 1));
+    c.cz = prm[9];
+    c.r_base = rho + mdiv(c.muc, psi, prm[11]) - prm[12] * (sigc * sigc);
+    c.cs = prm[10];
     c.kzc_sigc = kap_Zc * sigc;
   }
   template <bool SAVE>
@@ -138,10 +152,15 @@ struct BansalYaron : ModelDefaults {
 // examples/consumption_saving/consumption_saving_diffusion_income.jl:71-106  states (y, a)
 // saved = (mua, c)
 struct AhlmDiffusion : ModelDefaults {
-  static constexpr int N = 2, F = 1, NPARAMS = 8, NSAVED = 2;
+  static constexpr int N = 2, F = 1, NPARAMS = 8, NSAVED = 2, NDERIVED = 2;
   static constexpr bool USES_CROSS = false;
   static const char* name() { return "ahlm_diffusion"; }
-  struct Pre { double muy, cmax, inc, va3, util3, neg_inv_gamma, one_m_gamma, sig2, rho; bool above_amin; };
+  EP_HD static void derive(double* prm) {
+    const double gamma = prm[5];
+    prm[8] = -1 / gamma;
+    prm[9] = 1 / (1 - gamma);   // RN(1/(1 - gamma)) for the quotients by 1 - gamma
+  }
+  struct Pre { double muy, cmax, inc, va3, util3, neg_inv_gamma, one_m_gamma, r_one_m_gamma, sig2, rho; bool above_amin; };
   EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
     const double kappa_y = prm[0], ybar = prm[1], sigma_y = prm[2], r = prm[3], rho = prm[4], gamma = prm[5],
                  amin = prm[6];
@@ -149,10 +168,11 @@ struct AhlmDiffusion : ModelDefaults {
     c.muy = kappa_y * (ybar - y);
     c.cmax = 100.0 * (y + r * ep_max(a, 0.0));
     c.inc = y + r * a;                       // c = y + r a when the drift is pinned at zero
-    c.neg_inv_gamma = -1 / gamma;
+    c.neg_inv_gamma = prm[8];
     c.one_m_gamma = 1 - gamma;
+    c.r_one_m_gamma = prm[9];
     c.va3 = pow(c.inc, -gamma);
-    c.util3 = pow(c.inc, c.one_m_gamma) / c.one_m_gamma;
+    c.util3 = mdiv(pow(c.inc, c.one_m_gamma), c.one_m_gamma, c.r_one_m_gamma);
     c.sig2 = sigma_y * sigma_y;
     c.rho = rho;
     c.above_amin = a > amin;
@@ -167,13 +187,13 @@ struct AhlmDiffusion : ModelDefaults {
     double c, va, mua, util;
     if (mua_up >= 0.0) {
       va = va_up; c = c_up; mua = mua_up;
-      util = pow(c, p.one_m_gamma) / p.one_m_gamma;
+      util = mdiv(pow(c, p.one_m_gamma), p.one_m_gamma, p.r_one_m_gamma);
     } else {
       const double c_down = va_down > 0 ? ep_min(pow(va_down, p.neg_inv_gamma), p.cmax) : p.cmax;
       const double mua_down = p.inc - c_down;
       if ((mua_down <= 0.0) && p.above_amin) {
         va = va_down; c = c_down; mua = mua_down;
-        util = pow(c, p.one_m_gamma) / p.one_m_gamma;
+        util = mdiv(pow(c, p.one_m_gamma), p.one_m_gamma, p.r_one_m_gamma);
       } else {
         c = p.inc;
         va = p.va3;

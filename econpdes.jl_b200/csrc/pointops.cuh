@@ -22,6 +22,28 @@ constexpr double kSqrtEps = 1.4901161193847656e-8;
 // decide boundaries, spacings and colors -- and owns `l` points: all of dimensions 0..N-2 and
 // a contiguous range of the slowest dimension starting at global index `off`.  Fields of a
 // slab carry one ghost plane on either side, so neighbour addresses pt +- stride stay valid.
+// Unsigned 32-bit division by a run-time invariant (Granlund-Montgomery, round-up multiplier):
+// q = (t + ((n - t) >> s1)) >> s2 with t = umulhi(m, n); exact for every n < 2^32 and d >= 1.
+struct FastDiv {
+  unsigned m = 0, s1 = 0, s2 = 0, d = 1;
+  EP_HD void set(unsigned dd) {
+    d = dd;
+    unsigned l = 0;
+    while ((1ull << l) < dd) ++l;                                    // ceil(log2 d)
+    m = static_cast<unsigned>(((1ull << 32) * ((1ull << l) - dd)) / dd + 1);
+    s1 = l < 1 ? l : 1;
+    s2 = l > 0 ? l - 1 : 0;
+  }
+  EP_HD unsigned div(unsigned n) const {
+#if defined(__CUDA_ARCH__)
+    const unsigned t = __umulhi(m, n);
+#else
+    const unsigned t = static_cast<unsigned>((static_cast<unsigned long long>(m) * n) >> 32);
+#endif
+    return (t + ((n - t) >> s1)) >> s2;
+  }
+};
+
 template <int N>
 struct GridView {
   const double* x[N];
@@ -29,12 +51,25 @@ struct GridView {
   long long stride[N];
   long long l;        // number of grid points owned (= prod S on a single device)
   long long off = 0;  // global index of the first owned entry of dimension N-1
-  // optional per-dimension geometry table [kGeomRows][S_d]: dm, dp, d, 1/dp, 1/dm, 1/(dp d),
-  // 1/(dm d), 1/(dp dm) -- built once per grid (make_geom_table), so a sweep reads eight
-  // L1-resident values per dimension instead of re-deriving them with five divisions
+  // optional per-dimension geometry table [S_d][kGeomRows]: dm, dp, d, 1/dp, 1/dm, 1/(dp d),
+  // 1/(dm d), 1/(dp dm) -- built once per grid (make_geom_table), so a sweep reads one 64-byte
+  // record per dimension (four 16-byte loads) instead of re-deriving it with five divisions
   const double* tab[N] = {};
+  FastDiv div[N];     // division by S[d] (set_sizes)
+  // sizes, column-major strides and the divisors unravel uses
+  EP_HD void set_sizes(const long long* sizes) {
+    long long st = 1;
+    for (int d = 0; d < N; ++d) {
+      S[d] = sizes[d];
+      stride[d] = st;
+      st *= sizes[d];
+      div[d].set(static_cast<unsigned>(sizes[d]));
+    }
+    l = st;
+  }
 };
 constexpr int kGeomRows = 8;
+struct alignas(16) Pair { double a, b; };
 
 // Stencil shapes: the full clipped +-1 box (coloring.jl:18-35) or, for models that never
 // read a cross derivative, its star subset (centre + 2N axial neighbours).
@@ -60,9 +95,9 @@ EP_HD void unravel(long long pt, const GridView<N>& gv, long long* idx) {
   unsigned p = static_cast<unsigned>(pt);
 #pragma unroll
   for (int d = 0; d + 1 < N; ++d) {
-    const unsigned s = static_cast<unsigned>(gv.S[d]);
-    idx[d] = p % s;
-    p /= s;
+    const unsigned q = gv.div[d].div(p);
+    idx[d] = p - q * static_cast<unsigned>(gv.S[d]);
+    p = q;
   }
   idx[N - 1] = p + gv.off;   // global index along the slab dimension
 }
@@ -75,10 +110,11 @@ EP_HD void load_geom(const GridView<N>& gv, const long long* idx, PointGeom<N, R
     g.hi[d] = idx[d] == gv.S[d] - 1;
     state[d] = gv.x[d][idx[d]];
     if (RECIP >= 1 && gv.tab[d] != nullptr) {
-      const double* t = gv.tab[d] + idx[d];
-      const long long S = gv.S[d];
-      g.dm[d] = t[0]; g.dp[d] = t[S]; g.d[d] = t[2 * S];
-      g.rdp[d] = t[3 * S]; g.rdm[d] = t[4 * S]; g.rdpd[d] = t[5 * S]; g.rdmd[d] = t[6 * S]; g.rdpm[d] = t[7 * S];
+      // one 64-byte record per grid index, 16-byte aligned: four vector loads
+      const Pair* t = reinterpret_cast<const Pair*>(gv.tab[d] + idx[d] * kGeomRows);
+      const Pair t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3];
+      g.dm[d] = t0.a; g.dp[d] = t0.b; g.d[d] = t1.a;
+      g.rdp[d] = t1.b; g.rdm[d] = t2.a; g.rdpd[d] = t2.b; g.rdmd[d] = t3.a; g.rdpm[d] = t3.b;
       g.dpd[d] = g.dp[d] * g.d[d];
       g.dmd[d] = g.dm[d] * g.d[d];
       g.dpm[d] = g.dp[d] * g.dm[d];
@@ -91,14 +127,15 @@ EP_HD void load_geom(const GridView<N>& gv, const long long* idx, PointGeom<N, R
 }
 
 // Host side of the table (plain IEEE arithmetic, identical to the device's).
-inline void make_geom_table(const double* x, long long S, double* tab /* [kGeomRows][S] */) {
+inline void make_geom_table(const double* x, long long S, double* tab /* [S][kGeomRows] */) {
   for (long long i = 0; i < S; ++i) {
     PointGeom<1, 1> g;
     spacing(x, i, S, g.dm[0], g.dp[0], g.d[0]);
     finish_axis(g, 0);
-    tab[i] = g.dm[0]; tab[S + i] = g.dp[0]; tab[2 * S + i] = g.d[0];
-    tab[3 * S + i] = g.rdp[0]; tab[4 * S + i] = g.rdm[0]; tab[5 * S + i] = g.rdpd[0];
-    tab[6 * S + i] = g.rdmd[0]; tab[7 * S + i] = g.rdpm[0];
+    double* t = tab + i * kGeomRows;
+    t[0] = g.dm[0]; t[1] = g.dp[0]; t[2] = g.d[0];
+    t[3] = g.rdp[0]; t[4] = g.rdm[0]; t[5] = g.rdpd[0];
+    t[6] = g.rdmd[0]; t[7] = g.rdpm[0];
   }
 }
 

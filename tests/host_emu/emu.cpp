@@ -15,16 +15,20 @@ namespace {
 template <class M>
 GridView<M::N> make_grid(const long long* S, const double* const* grids) {
   GridView<M::N> gv;
-  long long st = 1;
-  for (int d = 0; d < M::N; ++d) {
-    gv.x[d] = grids[d];
-    gv.S[d] = S[d];
-    gv.stride[d] = st;
-    st *= S[d];
-  }
-  gv.l = st;
+  gv.set_sizes(S);
+  for (int d = 0; d < M::N; ++d) gv.x[d] = grids[d];
   return gv;
 }
+
+// the caller's parameters followed by the model's derived constants (as the engine builds them)
+template <class M>
+struct full_params {
+  double v[kMaxParams] = {};
+  explicit full_params(const double* prm) {
+    for (int i = 0; i < M::NPARAMS; ++i) v[i] = prm[i];
+    M::derive(v);
+  }
+};
 
 int g_recip = 0;   // PointGeom RECIP mode under test (all modes must give the same bits)
 
@@ -46,7 +50,7 @@ int residual(const long long* S, const double* const* grids, const double* prm, 
     }
     double o[F], sv[M::NSAVED > 0 ? M::NSAVED : 1];
     typename M::Pre pre;
-    M::prepare(prm, st, pre);
+    M::prepare(full_params<M>(prm).v, st, pre);
     if (saved) eval_point<M, true>(pre, g, w, bl, bh, o, sv);
     else eval_point<M, false>(pre, g, w, bl, bh, o, sv);
     for (int f = 0; f < F; ++f) out[f * gv.l + pt] = o[f];
@@ -82,7 +86,7 @@ int jacobian(const long long* S, const double* const* grids, const double* prm, 
     double r0[F];
     const long long l = gv.l;
     typename M::Pre pre;
-    M::prepare(prm, st, pre);
+    M::prepare(full_params<M>(prm).v, st, pre);
     jacobian_point<M, BOX>(pre, g, idx, gv, w, bl, bh, rt, eps_table, eps_per_column, r0,
                            [&](int k, int fin, int fout, double v) { planes[((long long)(k * F + fin) * F + fout) * l + pt] = v; });
     for (int f = 0; f < F; ++f) r0out[f * l + pt] = r0[f];
@@ -95,6 +99,19 @@ int jacobian(const long long* S, const double* const* grids, const double* prm, 
 extern "C" {
 
 void emu_set_recip(int mode) { g_recip = mode; }
+
+// FastDiv (division by a grid size in unravel) against `/` for n = 0..count-1 and near 2^31 / 2^32
+long long emu_fastdiv_mismatches(unsigned d, unsigned count) {
+  FastDiv f;
+  f.set(d);
+  long long bad = 0;
+  for (unsigned n = 0; n < count; ++n) bad += f.div(n) != n / d;
+  for (unsigned k = 0; k < 4096; ++k) {
+    const unsigned a = 0x7fffffffu - k, b = 0xffffffffu - k, c = 0x80000000u + k;
+    bad += (f.div(a) != a / d) + (f.div(b) != b / d) + (f.div(c) != c / d);
+  }
+  return bad;
+}
 
 int emu_model_count() {
   int n = 0;

@@ -2,6 +2,8 @@
 row-wise colored-FD Jacobian), compiled for the host by tests/host_emu, against the oracle."""
 import math
 
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -208,3 +210,12 @@ def test_shared_reciprocal_in_functors_matches_ieee_for_degenerate_values():
             want = prob.G(y.reshape(-1, order="F")).reshape(y.shape, order="F")
             got = EU.residual(pm, grids, y)
         np.testing.assert_array_equal(got, want)
+
+
+def test_fast_division_by_grid_sizes():
+    """unravel divides the flat point index by the grid sizes through a multiply-high (FastDiv)."""
+    lib = EU.lib()
+    lib.emu_fastdiv_mismatches.restype = ctypes.c_longlong
+    lib.emu_fastdiv_mismatches.argtypes = [ctypes.c_uint, ctypes.c_uint]
+    for d in (1, 2, 3, 5, 7, 9, 50, 64, 255, 256, 257, 998, 1000, 2048, 4096, 65535, 65537, 1 << 20, (1 << 31) - 1):
+        assert lib.emu_fastdiv_mismatches(d, 200000) == 0, d
