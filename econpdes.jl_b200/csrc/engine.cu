@@ -149,12 +149,14 @@ struct ModelOpsT final : ModelOps {
     constexpr bool BOX = M::USES_CROSS && M::N > 1;
     // step policy fixed at compile time (branch-free row evaluation), two resident blocks per SM:
     // measured 0.53 -> 0.35 ms at 2048^2 and 2.94 -> 2.47 ms at 256^3 against the run-time-policy kernel
+    // 3-D rows (10+ evaluations of a 27-point box) get 170 registers: 128-thread blocks, three per SM
+    constexpr int JB = M::N >= 3 ? 128 : kBlock, JMINB = M::N >= 3 ? 3 : 2;
     auto go = [&](auto kernel) {
-      EP_LAUNCH(kernel, blocks_for(c.l), kBlock, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p, rs, c.color_eps.p,
+      EP_LAUNCH(kernel, blocks_for(c.l, JB), JB, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p, rs, c.color_eps.p,
                 per_col, planes, r0);
     };
-    if (per_col) go(k_jacobian<M, BOX, 1, 2>);
-    else go(k_jacobian<M, BOX, 0, 2>);
+    if (per_col) go(k_jacobian<M, BOX, 1, JB, JMINB>);
+    else go(k_jacobian<M, BOX, 0, JB, JMINB>);
   }
   void saved(const Ctx& c, const double* y, double* out) const override {
     if (M::NSAVED == 0) return;

@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(kBlock) k_color_sumsq(GridView<N> gv, int F, c
 // for the stencil shape <N,BOX>.  r0 (may be nullptr) receives R(y).
 // POLICY: 0 = per-color steps (eps_table holds the steps, then their reciprocals), 1 = per-column steps
 // (see jacobian_point); MINB = resident blocks per SM asked of the register allocator.
-template <class M, bool BOX, int POLICY, int MINB = 2>
-__global__ void __launch_bounds__(kBlock, MINB) k_jacobian(GridView<M::N> gv, ParamPack prm, const double* __restrict__ y,
+template <class M, bool BOX, int POLICY, int BLOCK = kBlock, int MINB = 2>
+__global__ void __launch_bounds__(BLOCK, MINB) k_jacobian(GridView<M::N> gv, ParamPack prm, const double* __restrict__ y,
                                                            const double* __restrict__ bc, RowSpec rs,
                                                            const double* __restrict__ eps_table, int eps_per_column,
                                                            double* __restrict__ planes, double* __restrict__ r0out) {
