@@ -90,7 +90,10 @@ struct econpdes_batch {
   cudaStream_t stream = nullptr;
   static constexpr int kPipe = 3;
   cudaStream_t pipe[kPipe] = {};   // copy/compute pipeline of the one-call path (econpdes_solve_batched)
-  int* err_host = nullptr;         // pinned [B]: a pageable target would make every slice's read-back blocking
+  // pinned staging for the per-problem scalars (error, exit reason, counts, residual norm): a pageable
+  // target would make every slice's read-back block the host and serialise the pipeline
+  int* err_host = nullptr;         // [4][B]: error, exit_reason, n_outer, n_newton
+  double* rn_host = nullptr;       // [B]
   DevBuf<double> params, grids, guess, solution, residual_norm;
   DevBuf<int> exit_reason, n_outer, n_newton, error, log_len;
   DevBuf<econpdes_log_row> log;
@@ -102,6 +105,7 @@ struct econpdes_batch {
     for (cudaStream_t p : pipe)
       if (p) cudaStreamDestroy(p);
     if (err_host) cudaFreeHost(err_host);
+    if (rn_host) cudaFreeHost(rn_host);
   }
 };
 
@@ -604,7 +608,9 @@ int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, con
     per = (per + sms - 1) / sms * sms;             // whole waves
     for (cudaStream_t& p : b->pipe)
       if (!p) EP_CUDA(cudaStreamCreateWithFlags(&p, cudaStreamNonBlocking));
-    if (!b->err_host) EP_CUDA(cudaMallocHost(&b->err_host, static_cast<size_t>(B) * sizeof(int)));
+    if (!b->err_host) EP_CUDA(cudaMallocHost(&b->err_host, 4 * static_cast<size_t>(B) * sizeof(int)));
+    if (!b->rn_host) EP_CUDA(cudaMallocHost(&b->rn_host, static_cast<size_t>(B) * sizeof(double)));
+    const size_t nB = static_cast<size_t>(B);
     b->log_capacity = 0;
     int* err = b->err_host;
     int c = 0;
@@ -621,14 +627,19 @@ int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, con
       if (solution)
         EP_CUDA(cudaMemcpyAsync(solution + o * S, b->solution.p + o * S, n * S * sizeof(double), cudaMemcpyDeviceToHost, s));
       if (residual_norm)
-        EP_CUDA(cudaMemcpyAsync(residual_norm + o, b->residual_norm.p + o, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        EP_CUDA(cudaMemcpyAsync(b->rn_host + o, b->residual_norm.p + o, n * sizeof(double), cudaMemcpyDeviceToHost, s));
       if (exit_reason)
-        EP_CUDA(cudaMemcpyAsync(exit_reason + o, b->exit_reason.p + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-      if (n_outer) EP_CUDA(cudaMemcpyAsync(n_outer + o, b->n_outer.p + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        EP_CUDA(cudaMemcpyAsync(err + nB + o, b->exit_reason.p + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+      if (n_outer)
+        EP_CUDA(cudaMemcpyAsync(err + 2 * nB + o, b->n_outer.p + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
       if (n_newton)
-        EP_CUDA(cudaMemcpyAsync(n_newton + o, b->n_newton.p + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        EP_CUDA(cudaMemcpyAsync(err + 3 * nB + o, b->n_newton.p + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     }
     for (cudaStream_t p : b->pipe) EP_CUDA(cudaStreamSynchronize(p));
+    if (residual_norm) std::memcpy(residual_norm, b->rn_host, nB * sizeof(double));
+    if (exit_reason) std::memcpy(exit_reason, err + nB, nB * sizeof(int32_t));
+    if (n_outer) std::memcpy(n_outer, err + 2 * nB, nB * sizeof(int32_t));
+    if (n_newton) std::memcpy(n_newton, err + 3 * nB, nB * sizeof(int32_t));
     for (size_t i = 0; i < static_cast<size_t>(B); ++i)
       if (err[i] != 0) {
         set_error("G! returns NaN with the initial value (problem " + std::to_string(i) + ")");

@@ -213,7 +213,11 @@ int econpdes_batch_download(econpdes_batch* b, double* solution, double* residua
                             int32_t* n_outer, int32_t* n_newton, econpdes_log_row* log, int32_t log_capacity,
                             int32_t* log_len);
 int64_t econpdes_batch_kernel_launches(const econpdes_batch* b);
-/* upload + solve + download in one call (the end-to-end path a pdesolve loop replaces) */
+/* upload + solve + download in one call (the end-to-end path a pdesolve loop replaces).  The batch is cut
+ * into up to 8 slices whose host->device copies, solves and device->host copies are pipelined over three
+ * streams.  The copies of `grids`, `guess` and `solution` overlap only when those buffers are page-locked
+ * (cudaHostAlloc / cudaHostRegister / torch pin_memory); pageable buffers give the same results, serially.
+ * The per-problem scalars are staged through the library's own page-locked memory. */
 int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, const double* params,
                            const double* grids, const double* guess, const econpdes_options* options,
                            double* solution, double* residual_norm, int32_t* exit_reason, int32_t* n_outer,
