@@ -218,7 +218,7 @@ def run_ours(args):
     alg_bytes = float(S) * (BYTES_PER_NEWTON_POINT * newton_rank + BYTES_PER_SWEEP_POINT * float(no.sum() + B))
     kernel_ms = dev_ms / args.steps
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = _ncu_traffic_bytes("r01_batched_kernel_ncu_full.json", "k_batched_pdesolve_1d")
+    traffic = _ncu_traffic_bytes("r01_batched_kernel_P4_ncu_full.json", "k_batched_pdesolve_1d")
     line = {
         "metric": "newton_solves_per_sec", "value": value, "unit": "Newton solves/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -234,7 +234,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": d2h, "api": "econpdes_solve_batched (C ABI, pinned host buffers)"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "kernel": "k_batched_pdesolve_1d<CampbellCochrane>", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "k_batched_pdesolve_1d<CampbellCochrane, P=4>", "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "fused on-chip solve: algorithmic bytes never reach HBM; DRAM traffic is grid+guess in, solution out"},
