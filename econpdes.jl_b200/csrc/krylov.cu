@@ -842,6 +842,119 @@ __global__ void __launch_bounds__(kBlock) k_scale_copy(long long n, double a, co
   if (i < n) dst[i] = a * src[i];
 }
 
+// Flexible GMRES(m), right-preconditioned: apply(x, b, y, mode) is y = A x (mode 0) or y = b - A x
+// (mode 1), precond(v, z) is z ~ A^{-1} v, dots(n, j, V, w, out) returns <V_q, w> (q < j) and <w, w>
+// on the host.  Shared by the multigrid solver and the block line-relaxation solver.
+struct GmresWork {
+  DevBuf<double> V, Z, w, hdev;
+  double* h = nullptr;   // pinned host scratch, >= restart + 2 doubles
+  int restart_alloc = 0;
+};
+template <class Apply, class Precond, class Dots>
+int fgmres_run(cudaStream_t s, long long n, GmresWork& gw, const double* b, double* x, const econpdes_options& opt,
+               Apply&& spmv_top, Precond&& precondition, Dots&& dots, int* iters_out, double* relres_out) {
+  {
+    DevBuf<double>&V_ = gw.V, &Z_ = gw.Z, &w_ = gw.w, &hdev_ = gw.hdev;
+    int& restart_alloc_ = gw.restart_alloc;
+    double* h_ = gw.h;
+    const int m = opt.lin_restart > 0 && opt.lin_restart <= 60 ? opt.lin_restart : 40;
+    if (m != restart_alloc_) {
+      restart_alloc_ = m;
+      V_.alloc(static_cast<size_t>(m + 1) * n);
+      Z_.alloc(static_cast<size_t>(m) * n);
+      w_.alloc(static_cast<size_t>(n));
+      hdev_.alloc(static_cast<size_t>(m + 2));
+    }
+    std::vector<double> H((m + 1) * m, 0.0), cs(m), sn(m), gvec(m + 1), hcol(m + 2), yv(m);
+    double* hh = h_;  // pinned scratch (>= m + 2 doubles)
+    EP_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), s));
+    // ||b||
+    dots(n, 0, V_.p, b, hh);
+    const double bnorm = std::sqrt(hh[0]);
+    int total = 0;
+    double relres = 0.0;
+    if (!(bnorm > 0.0) || !std::isfinite(bnorm)) {
+      if (iters_out) *iters_out = 0;
+      if (relres_out) *relres_out = 0.0;
+      return std::isfinite(bnorm) ? 0 : 1;
+    }
+    double prev_true = INFINITY;
+    int status = 1;
+    for (int cycle = 0; cycle < 50 && total < opt.lin_maxiters; ++cycle) {
+      // r = b - A x
+      spmv_top(x, b, w_.p, 1);
+      dots(n, 0, V_.p, w_.p, hh);
+      const double beta = std::sqrt(hh[0]);
+      relres = beta / bnorm;
+      if (!std::isfinite(beta)) { status = 1; break; }
+      if (relres <= opt.lin_rtol || (cycle > 0 && relres <= 10 * opt.lin_rtol)) { status = 0; break; }
+      // stagnation at the attainable accuracy of the system: accept what LU would also deliver
+      if (cycle > 0 && beta > 0.5 * prev_true) { status = relres <= 1e-8 ? 0 : 1; break; }
+      prev_true = beta;
+      EP_LAUNCH(k_scale_copy, blocks_for(n), kBlock, 0, s, n, 1.0 / beta, w_.p, V_.p);
+      std::fill(gvec.begin(), gvec.end(), 0.0);
+      gvec[0] = beta;
+      int j = 0;
+      for (; j < m && total < opt.lin_maxiters; ++j, ++total) {
+        double* zj = Z_.p + static_cast<size_t>(j) * n;
+        precondition(V_.p + static_cast<size_t>(j) * n, zj);
+        spmv_top(zj, nullptr, w_.p, 0);
+        // classical Gram-Schmidt, twice
+        std::fill(hcol.begin(), hcol.end(), 0.0);
+        for (int pass = 0; pass < 2; ++pass) {
+          dots(n, j + 1, V_.p, w_.p, hh);
+          EP_CUDA(cudaMemcpyAsync(hdev_.p, hh, (j + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
+          EP_LAUNCH(k_multi_axpy, blocks_for(n), kBlock, 0, s, n, j + 1, V_.p, hdev_.p, w_.p, -1.0);
+          for (int q = 0; q <= j; ++q) hcol[q] += hh[q];
+          EP_CUDA(cudaStreamSynchronize(s));  // hh is reused by the next dots()
+        }
+        dots(n, 0, V_.p, w_.p, hh);
+        const double hnext = std::sqrt(hh[0]);
+        hcol[j + 1] = hnext;
+        if (!std::isfinite(hnext)) { status = 1; j = -1; break; }
+        if (hnext > 0.0)
+          EP_LAUNCH(k_scale_copy, blocks_for(n), kBlock, 0, s, n, 1.0 / hnext, w_.p, V_.p + static_cast<size_t>(j + 1) * n);
+        // Givens rotations
+        for (int q = 0; q < j; ++q) {
+          const double t = cs[q] * hcol[q] + sn[q] * hcol[q + 1];
+          hcol[q + 1] = -sn[q] * hcol[q] + cs[q] * hcol[q + 1];
+          hcol[q] = t;
+        }
+        const double denom = std::hypot(hcol[j], hcol[j + 1]);
+        cs[j] = denom > 0 ? hcol[j] / denom : 1.0;
+        sn[j] = denom > 0 ? hcol[j + 1] / denom : 0.0;
+        hcol[j] = denom;
+        gvec[j + 1] = -sn[j] * gvec[j];
+        gvec[j] = cs[j] * gvec[j];
+        for (int q = 0; q <= j; ++q) H[q * m + j] = hcol[q];
+        relres = std::fabs(gvec[j + 1]) / bnorm;
+        if (relres <= opt.lin_rtol || hnext == 0.0) { ++j; ++total; break; }
+      }
+      if (j < 0) break;
+      // x += Z y with H y = g
+      for (int q = j - 1; q >= 0; --q) {
+        double t = gvec[q];
+        for (int r2 = q + 1; r2 < j; ++r2) t -= H[q * m + r2] * yv[r2];
+        yv[q] = t / H[q * m + q];
+      }
+      for (int q = 0; q < j; ++q) hh[q] = yv[q];
+      EP_CUDA(cudaMemcpyAsync(hdev_.p, hh, j * sizeof(double), cudaMemcpyHostToDevice, s));
+      EP_LAUNCH(k_multi_axpy, blocks_for(n), kBlock, 0, s, n, j, Z_.p, hdev_.p, x, 1.0);
+      EP_CUDA(cudaStreamSynchronize(s));
+    }
+    if (status != 0) {
+      // final check of the true residual (the loop may have ended on the iteration cap)
+      spmv_top(x, b, w_.p, 1);
+      dots(n, 0, V_.p, w_.p, hh);
+      relres = std::sqrt(hh[0]) / bnorm;
+      status = (std::isfinite(relres) && relres <= 1e-8) ? 0 : 1;
+    }
+    if (iters_out) *iters_out = total;
+    if (relres_out) *relres_out = relres;
+    return status;
+  }
+}
+
 // ---- slab plumbing of the distributed levels -----------------------------------------------
 constexpr int kMaxRanks = 16;
 struct SlabMap {           // every rank's owned range of dimension N-1 at one level
@@ -916,6 +1029,7 @@ class KrylovSolver final : public LinearSolver {
   using mgreal = mgreal_t<N>;
   explicit KrylovSolver(Ctx& c) : c_(c) {
     EP_CUDA(cudaMallocHost(&h_, 256 * sizeof(double)));
+    gw_.h = h_;
     sym_.alloc(2 * kMaxDims);
     if (const char* wl = std::getenv("ECONPDES_WARP_LINES_MAX")) {
       warp_lines_max_ = std::atoi(wl);
@@ -977,7 +1091,8 @@ class KrylovSolver final : public LinearSolver {
  private:
   Ctx& c_;
   std::vector<std::unique_ptr<Level<N>>> lev_;
-  DevBuf<double> dense_, sym_, V_, Z_, w_, dots_, part_, hdev_, dense_inv_, dense_work_;
+  DevBuf<double> dense_, sym_, w_, dots_, part_, dense_inv_, dense_work_;
+  GmresWork gw_;
   DevBuf<mgreal> A0_, rap_tmp_[2], rap_send_, rap_ghost_;   // level-0 copy of the Jacobian planes; Galerkin scratch
   DevBuf<int> piv_;
   DevBuf<Transfer> transfers_dev_;
@@ -999,7 +1114,6 @@ class KrylovSolver final : public LinearSolver {
   int warp_lines_max_ = 0;
   double* h_ = nullptr;
   int dense_n_ = 0;
-  int restart_alloc_ = 0;
 
   template <bool BOX>
   void spmv(const Level<N>& L, const double* x, const double* b, double* y, int mode) {
@@ -1504,8 +1618,8 @@ class KrylovSolver final : public LinearSolver {
     cudaStream_t s = c_.stream;
     ProfScope ps("lin dots", s);
     const int nb = 148 * 2;
-    part_.alloc(static_cast<size_t>(nb) * (restart_alloc_ + 2));
-    dots_.alloc(static_cast<size_t>(restart_alloc_ + 2));
+    part_.alloc(static_cast<size_t>(nb) * (gw_.restart_alloc + 2));
+    dots_.alloc(static_cast<size_t>(gw_.restart_alloc + 2));
     EP_LAUNCH(k_multi_dot, dim3(nb, j + 1), kBlock, 0, s, n, j, V, w, part_.p);
     EP_LAUNCH(k_finish_dots, (j + 1 + 7) / 8, 256, 0, s, j + 1, nb, part_.p, dots_.p);
     if (c_.dist != nullptr) {   // per-rank partial dot products, folded in rank order on every rank
@@ -1524,117 +1638,260 @@ class KrylovSolver final : public LinearSolver {
 
   // Flexible GMRES(m), right-preconditioned by the V-cycle.
   int fgmres(const double* b, double* x, const econpdes_options& opt, int* iters_out, double* relres_out) {
-    cudaStream_t s = c_.stream;
-    Level<N>& L0 = *lev_[0];
-    const long long n = L0.l;
-    const int m = opt.lin_restart > 0 && opt.lin_restart <= 60 ? opt.lin_restart : 40;
-    if (m != restart_alloc_) {
-      restart_alloc_ = m;
-      V_.alloc(static_cast<size_t>(m + 1) * n);
-      Z_.alloc(static_cast<size_t>(m) * n);
-      w_.alloc(static_cast<size_t>(n));
-      hdev_.alloc(static_cast<size_t>(m + 2));
-    }
-    std::vector<double> H((m + 1) * m, 0.0), cs(m), sn(m), gvec(m + 1), hcol(m + 2), yv(m);
-    double* hh = h_;  // pinned scratch (>= m + 2 doubles)
-    EP_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), s));
-    // ||b||
-    dots(n, 0, V_.p, b, hh);
-    const double bnorm = std::sqrt(hh[0]);
-    int total = 0;
-    double relres = 0.0;
-    if (!(bnorm > 0.0) || !std::isfinite(bnorm)) {
-      if (iters_out) *iters_out = 0;
-      if (relres_out) *relres_out = 0.0;
-      return std::isfinite(bnorm) ? 0 : 1;
-    }
-    double prev_true = INFINITY;
-    int status = 1;
-    for (int cycle = 0; cycle < 50 && total < opt.lin_maxiters; ++cycle) {
-      // r = b - A x
-      spmv_top(x, b, w_.p, 1);
-      dots(n, 0, V_.p, w_.p, hh);
-      const double beta = std::sqrt(hh[0]);
-      relres = beta / bnorm;
-      if (!std::isfinite(beta)) { status = 1; break; }
-      if (relres <= opt.lin_rtol || (cycle > 0 && relres <= 10 * opt.lin_rtol)) { status = 0; break; }
-      // stagnation at the attainable accuracy of the system: accept what LU would also deliver
-      if (cycle > 0 && beta > 0.5 * prev_true) { status = relres <= 1e-8 ? 0 : 1; break; }
-      prev_true = beta;
-      EP_LAUNCH(k_scale_copy, blocks_for(n), kBlock, 0, s, n, 1.0 / beta, w_.p, V_.p);
-      std::fill(gvec.begin(), gvec.end(), 0.0);
-      gvec[0] = beta;
-      int j = 0;
-      for (; j < m && total < opt.lin_maxiters; ++j, ++total) {
-        double* zj = Z_.p + static_cast<size_t>(j) * n;
-        precondition(V_.p + static_cast<size_t>(j) * n, zj);
-        spmv_top(zj, nullptr, w_.p, 0);
-        // classical Gram-Schmidt, twice
-        std::fill(hcol.begin(), hcol.end(), 0.0);
-        for (int pass = 0; pass < 2; ++pass) {
-          dots(n, j + 1, V_.p, w_.p, hh);
-          EP_CUDA(cudaMemcpyAsync(hdev_.p, hh, (j + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
-          EP_LAUNCH(k_multi_axpy, blocks_for(n), kBlock, 0, s, n, j + 1, V_.p, hdev_.p, w_.p, -1.0);
-          for (int q = 0; q <= j; ++q) hcol[q] += hh[q];
-          EP_CUDA(cudaStreamSynchronize(s));  // hh is reused by the next dots()
-        }
-        dots(n, 0, V_.p, w_.p, hh);
-        const double hnext = std::sqrt(hh[0]);
-        hcol[j + 1] = hnext;
-        if (!std::isfinite(hnext)) { status = 1; j = -1; break; }
-        if (hnext > 0.0)
-          EP_LAUNCH(k_scale_copy, blocks_for(n), kBlock, 0, s, n, 1.0 / hnext, w_.p, V_.p + static_cast<size_t>(j + 1) * n);
-        // Givens rotations
-        for (int q = 0; q < j; ++q) {
-          const double t = cs[q] * hcol[q] + sn[q] * hcol[q + 1];
-          hcol[q + 1] = -sn[q] * hcol[q] + cs[q] * hcol[q + 1];
-          hcol[q] = t;
-        }
-        const double denom = std::hypot(hcol[j], hcol[j + 1]);
-        cs[j] = denom > 0 ? hcol[j] / denom : 1.0;
-        sn[j] = denom > 0 ? hcol[j + 1] / denom : 0.0;
-        hcol[j] = denom;
-        gvec[j + 1] = -sn[j] * gvec[j];
-        gvec[j] = cs[j] * gvec[j];
-        for (int q = 0; q <= j; ++q) H[q * m + j] = hcol[q];
-        relres = std::fabs(gvec[j + 1]) / bnorm;
-        if (relres <= opt.lin_rtol || hnext == 0.0) { ++j; ++total; break; }
-      }
-      if (j < 0) break;
-      // x += Z y with H y = g
-      for (int q = j - 1; q >= 0; --q) {
-        double t = gvec[q];
-        for (int r2 = q + 1; r2 < j; ++r2) t -= H[q * m + r2] * yv[r2];
-        yv[q] = t / H[q * m + q];
-      }
-      for (int q = 0; q < j; ++q) hh[q] = yv[q];
-      EP_CUDA(cudaMemcpyAsync(hdev_.p, hh, j * sizeof(double), cudaMemcpyHostToDevice, s));
-      EP_LAUNCH(k_multi_axpy, blocks_for(n), kBlock, 0, s, n, j, Z_.p, hdev_.p, x, 1.0);
-      EP_CUDA(cudaStreamSynchronize(s));
-    }
-    if (status != 0) {
-      // final check of the true residual (the loop may have ended on the iteration cap)
-      spmv_top(x, b, w_.p, 1);
-      dots(n, 0, V_.p, w_.p, hh);
-      relres = std::sqrt(hh[0]) / bnorm;
-      status = (std::isfinite(relres) && relres <= 1e-8) ? 0 : 1;
-    }
-    if (iters_out) *iters_out = total;
-    if (relres_out) *relres_out = relres;
-    return status;
+    return fgmres_run(c_.stream, lev_[0]->l, gw_, b, x, opt,
+                      [&](const double* xx, const double* bb, double* yy, int mode) { spmv_top(xx, bb, yy, mode); },
+                      [&](const double* v, double* z) { precondition(v, z); },
+                      [&](long long n, int j, const double* V, const double* w, double* out) { dots(n, j, V, w, out); },
+                      iters_out, relres_out);
   }
 };
+
+// ---------------------------------------------------------------------------------------
+// Several unknowns per grid point (F > 1) on 2-D / 3-D grids
+// ---------------------------------------------------------------------------------------
+// The Jacobian couples the F unknowns of a point and of its stencil neighbours: planes hold F x F
+// blocks, planes[((k F + fin) F + fout) l + pt] = dR_fout(pt) / dy_fin(pt + off_k).  The reference
+// factorises it with sparse LU; here it is solved matrix-free by flexible GMRES preconditioned with
+// alternating-direction BLOCK line relaxation (the "line-tridiagonal, ADI-style" preconditioner of
+// BASELINE.json's north star): for every grid dimension in turn, the residual is updated and the
+// block-tridiagonal systems along all lines of that dimension (centre blocks plus the +-1 couplings
+// in that dimension, every other coupling dropped) are solved exactly by parallel cyclic reduction
+// with F x F pivots (tridiag.cuh), the corrections accumulating multiplicatively.  One-level: the
+// iteration count grows with the grid, which is adequate for the multi-unknown examples (grids of
+// 10^3..10^5 points); the single-unknown configurations use the multigrid solver above.
+
+// y = A x (mode 0) or y = b - A x (mode 1) with F x F blocks
+template <int N, bool BOX, int F>
+__global__ void __launch_bounds__(kBlock) k_spmv_block(LevelGeom<N> g, const double* __restrict__ A,
+                                                       const double* __restrict__ x, const double* __restrict__ b,
+                                                       double* __restrict__ y, int mode) {
+  using St = Stencil<N, BOX>;
+  const long long pt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pt >= g.l) return;
+  long long idx[N];
+  unravel_l<N>(pt, g, idx);
+  double acc[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) acc[f] = 0.0;
+#pragma unroll
+  for (int k = 0; k < St::NK; ++k) {
+    long long q = pt;
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      const int o = St::off(k, d);
+      if ((o < 0 && idx[d] == 0) || (o > 0 && idx[d] == g.S[d] - 1)) ok = false;
+      q += o * g.stride[d];
+    }
+    const long long src = ok ? q : pt;   // entries pointing outside the grid hold 0
+#pragma unroll
+    for (int fin = 0; fin < F; ++fin) {
+      const double xv = x[fin * g.l + src];
+#pragma unroll
+      for (int fout = 0; fout < F; ++fout) acc[fout] += A[(static_cast<long long>(k * F + fin) * F + fout) * g.l + pt] * xv;
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < F; ++f) y[f * g.l + pt] = mode ? b[f * g.l + pt] - acc[f] : acc[f];
+}
+
+// One PCR step with stride s along the lines of one grid dimension (`stride` = distance in memory
+// between neighbours of that dimension, Sd = its size): k_pcr_step (tridiag.cuh) with the row
+// neighbours i -+ s*stride and the line ends as system boundaries.
+template <int F>
+__global__ void __launch_bounds__(kBlock) k_pcr_step_lines(long long l, long long s, long long stride, long long Sd,
+                                                           PcrSystem in, PcrSystemOut out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= l) return;
+  const long long id = (i / stride) % Sd;
+  SmallMat<F> B = load_mat<F>(in.B, l, i);
+  double d[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) d[f] = in.d[f * l + i];
+  SmallMat<F> An, Cn;
+#pragma unroll
+  for (int e = 0; e < F * F; ++e) An.a[e] = Cn.a[e] = 0.0;
+  if (id - s >= 0) {
+    const long long im = i - s * stride;
+    const SmallMat<F> A = load_mat<F>(in.A, l, i);
+    const SmallMat<F> alpha = mat_mul<F>(A, mat_inv<F>(load_mat<F>(in.B, l, im)));
+    const SmallMat<F> t1 = mat_mul<F>(alpha, load_mat<F>(in.A, l, im));
+    const SmallMat<F> t2 = mat_mul<F>(alpha, load_mat<F>(in.C, l, im));
+#pragma unroll
+    for (int e = 0; e < F * F; ++e) { An.a[e] = -t1.a[e]; B.a[e] -= t2.a[e]; }
+#pragma unroll
+    for (int r = 0; r < F; ++r) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < F; ++k) t += alpha(r, k) * in.d[k * l + im];
+      d[r] -= t;
+    }
+  }
+  if (id + s < Sd) {
+    const long long ip = i + s * stride;
+    const SmallMat<F> C = load_mat<F>(in.C, l, i);
+    const SmallMat<F> gamma = mat_mul<F>(C, mat_inv<F>(load_mat<F>(in.B, l, ip)));
+    const SmallMat<F> t1 = mat_mul<F>(gamma, load_mat<F>(in.C, l, ip));
+    const SmallMat<F> t2 = mat_mul<F>(gamma, load_mat<F>(in.A, l, ip));
+#pragma unroll
+    for (int e = 0; e < F * F; ++e) { Cn.a[e] = -t1.a[e]; B.a[e] -= t2.a[e]; }
+#pragma unroll
+    for (int r = 0; r < F; ++r) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < F; ++k) t += gamma(r, k) * in.d[k * l + ip];
+      d[r] -= t;
+    }
+  }
+  store_mat<F>(out.A, l, i, An);
+  store_mat<F>(out.B, l, i, B);
+  store_mat<F>(out.C, l, i, Cn);
+#pragma unroll
+  for (int f = 0; f < F; ++f) out.d[f * l + i] = d[f];
+}
+
+// z (+)= B^{-1} d
+template <int F>
+__global__ void __launch_bounds__(kBlock) k_pcr_final_lines(long long l, PcrSystem in, double* __restrict__ z,
+                                                            int accumulate) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= l) return;
+  const SmallMat<F> Binv = mat_inv<F>(load_mat<F>(in.B, l, i));
+#pragma unroll
+  for (int r = 0; r < F; ++r) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < F; ++k) t += Binv(r, k) * in.d[k * l + i];
+    z[r * l + i] = accumulate ? z[r * l + i] + t : t;
+  }
+}
+
+template <int N, int F>
+class BlockLineSolver final : public LinearSolver {
+ public:
+  explicit BlockLineSolver(Ctx& c) : c_(c) {
+    if (c.dist != nullptr) throw std::runtime_error("slab-decomposed solves take single-unknown models");
+    EP_CUDA(cudaMallocHost(&gw_.h, 256 * sizeof(double)));
+    g_ = make_geom<N>(c.S);
+  }
+  ~BlockLineSolver() override {
+    if (gw_.h) cudaFreeHost(gw_.h);
+  }
+
+  int solve(const double* planes, const double* b, double* x, const econpdes_options& opt, int* iters,
+            double* relres) override {
+    planes_ = planes;
+    const long long n = g_.l * F;
+    return fgmres_run(c_.stream, n, gw_, b, x, opt,
+                      [&](const double* xx, const double* bb, double* yy, int mode) { spmv(xx, bb, yy, mode); },
+                      [&](const double* v, double* z) { precondition(v, z); },
+                      [&](long long nn, int j, const double* V, const double* w, double* out) { dots(nn, j, V, w, out); },
+                      iters, relres);
+  }
+
+  void bench(const double* planes, const double* v, int reps, double* flush, size_t flush_bytes,
+             double* ms_out) override {
+    (void)flush; (void)flush_bytes;
+    planes_ = planes;
+    cudaStream_t s = c_.stream;
+    const long long n = g_.l * F;
+    DevBuf<double> y, z;
+    y.alloc(static_cast<size_t>(n));
+    z.alloc(static_cast<size_t>(n));
+    cudaEvent_t e0, e1;
+    EP_CUDA(cudaEventCreate(&e0));
+    EP_CUDA(cudaEventCreate(&e1));
+    auto timed = [&](auto&& fn) {
+      fn();
+      EP_CUDA(cudaEventRecord(e0, s));
+      for (int r = 0; r < reps; ++r) fn();
+      EP_CUDA(cudaEventRecord(e1, s));
+      EP_CUDA(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      EP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      return static_cast<double>(ms) / reps;
+    };
+    ms_out[0] = timed([&] { spmv(v, nullptr, y.p, 0); });
+    ms_out[1] = timed([&] { precondition(v, z.p); });
+    ms_out[2] = 0.0;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  }
+
+ private:
+  Ctx& c_;
+  LevelGeom<N> g_;
+  const double* planes_ = nullptr;
+  GmresWork gw_;
+  DevBuf<double> r_, work_[2], dots_, part_;
+
+  void spmv(const double* x, const double* b, double* y, int mode) {
+    if (c_.box) EP_LAUNCH((k_spmv_block<N, true, F>), blocks_for(g_.l), kBlock, 0, c_.stream, g_, planes_, x, b, y, mode);
+    else EP_LAUNCH((k_spmv_block<N, false, F>), blocks_for(g_.l), kBlock, 0, c_.stream, g_, planes_, x, b, y, mode);
+  }
+
+  void dots(long long n, int j, const double* V, const double* w, double* host_out) {
+    cudaStream_t s = c_.stream;
+    const int nb = 148 * 2;
+    part_.alloc(static_cast<size_t>(nb) * (gw_.restart_alloc + 2));
+    dots_.alloc(static_cast<size_t>(gw_.restart_alloc + 2));
+    EP_LAUNCH(k_multi_dot, dim3(nb, j + 1), kBlock, 0, s, n, j, V, w, part_.p);
+    EP_LAUNCH(k_finish_dots, (j + 1 + 7) / 8, 256, 0, s, j + 1, nb, part_.p, dots_.p);
+    EP_CUDA(cudaMemcpyAsync(host_out, dots_.p, (j + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    EP_CUDA(cudaStreamSynchronize(s));
+  }
+
+  // plane index of the centre and of the -1 / +1 neighbour along dimension d
+  int k_of(int d, int o) const {
+    if (c_.box) return (ipow3(N) - 1) / 2 + o * p3(d);
+    return o == 0 ? 0 : (o < 0 ? 1 + 2 * d : 2 + 2 * d);
+  }
+
+  // z ~ A^{-1} v: one multiplicative sweep of exact block line solves over the grid dimensions
+  void precondition(const double* v, double* z) {
+    cudaStream_t s = c_.stream;
+    const long long l = g_.l;
+    const size_t blk = static_cast<size_t>(F) * F * l, sys = 3 * blk + static_cast<size_t>(F) * l;
+    r_.alloc(static_cast<size_t>(F) * l);
+    work_[0].alloc(sys);
+    work_[1].alloc(sys);
+    for (int d = 0; d < N; ++d) {
+      const double* rhs = v;
+      if (d > 0) {   // residual of the correction so far
+        spmv(z, v, r_.p, 1);
+        rhs = r_.p;
+      }
+      PcrSystem in{planes_ + static_cast<size_t>(k_of(d, -1)) * blk, planes_ + static_cast<size_t>(k_of(d, 0)) * blk,
+                   planes_ + static_cast<size_t>(k_of(d, +1)) * blk, rhs};
+      int cur = 0;
+      for (long long st = 1; st < g_.S[d]; st <<= 1) {
+        PcrSystemOut out{work_[cur].p, work_[cur].p + blk, work_[cur].p + 2 * blk, work_[cur].p + 3 * blk};
+        EP_LAUNCH(k_pcr_step_lines<F>, blocks_for(l), kBlock, 0, s, l, st, g_.stride[d], g_.S[d], in, out);
+        in = PcrSystem{out.A, out.B, out.C, out.d};
+        cur ^= 1;
+      }
+      EP_LAUNCH(k_pcr_final_lines<F>, blocks_for(l), kBlock, 0, s, l, in, z, d > 0 ? 1 : 0);
+    }
+  }
+};
+
+template <int N>
+std::unique_ptr<LinearSolver> make_block_solver(Ctx& c) {
+  switch (c.F) {
+    case 2: return std::make_unique<BlockLineSolver<N, 2>>(c);
+    case 3: return std::make_unique<BlockLineSolver<N, 3>>(c);
+    case 4: return std::make_unique<BlockLineSolver<N, 4>>(c);
+    default: throw std::invalid_argument("2-D/3-D systems take at most 4 unknowns per grid point");
+  }
+}
 
 }  // namespace
 
 std::unique_ptr<LinearSolver> make_krylov_solver(Ctx& c) {
   if (c.F != 1) {
-    struct Unsupported final : LinearSolver {
-      int solve(const double*, const double*, double*, const econpdes_options&, int*, double*) override {
-        throw std::runtime_error("2-D/3-D systems with several unknowns are not on the device path yet");
-      }
-    };
-    return std::make_unique<Unsupported>();
+    if (c.N == 2) return make_block_solver<2>(c);
+    if (c.N == 3) return make_block_solver<3>(c);
+    throw std::invalid_argument("Krylov solver handles 2-D and 3-D grids");
   }
   if (c.N == 2) return std::make_unique<KrylovSolver<2>>(c);
   if (c.N == 3) return std::make_unique<KrylovSolver<3>>(c);

@@ -368,6 +368,45 @@ struct VMinusTwo : ModelDefaults {
   }
 };
 
+// Two coupled HJB equations on a 2-D grid (regime switching between two drift/payoff regimes with
+// intensities lam12, lam21, correlated diffusions, quadratic damping): the synthetic stand-in for
+// the reference's multi-unknown 2-D examples (di_tella.jl: 3 unknowns on (x, nu)); exercises F x F
+// blocks on the full +-1 box.  Definition shared verbatim with oracle/models.py:hjb2d_regimes.
+struct Hjb2dRegimes : ModelDefaults {
+  static constexpr int N = 2, F = 2, NPARAMS = 10, NSAVED = 0;
+  static constexpr bool USES_CROSS = true;
+  static const char* name() { return "hjb2d_regimes"; }
+  struct Pre { double pay1, pay2, mx1, mx2, my, hx, hy, cxy, rho, lam12, lam21, theta; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
+    const double kx1 = prm[0], kx2 = prm[1], ky = prm[2], sx = prm[3], sy = prm[4], corr = prm[5];
+    const double x = st[0], y = st[1];
+    c.pay1 = x + y;
+    c.pay2 = 2 * x - y + 1;
+    c.mx1 = -kx1 * (x - 0.5);
+    c.mx2 = -kx2 * (x - 0.3);
+    c.my = -ky * (y - 0.5);
+    c.hx = 0.5 * (sx * sx);
+    c.hy = 0.5 * (sy * sy);
+    c.cxy = corr * sx * sy;
+    c.rho = prm[6];
+    c.lam12 = prm[7];
+    c.lam21 = prm[8];
+    c.theta = prm[9];
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<2>* u, double* out, double*) {
+    const double v = u[0].v, w = u[1].v;
+    const double vx = (c.mx1 >= 0) ? u[0].up[0] : u[0].dn[0];
+    const double vy = (c.my >= 0) ? u[0].up[1] : u[0].dn[1];
+    const double wx = (c.mx2 >= 0) ? u[1].up[0] : u[1].dn[0];
+    const double wy = (c.my >= 0) ? u[1].up[1] : u[1].dn[1];
+    out[0] = -(c.pay1 + c.mx1 * vx + c.my * vy + c.hx * u[0].dd[0] + c.hy * u[0].dd[1] + c.cxy * u[0].x[0] -
+               c.rho * v + c.lam12 * (w - v) - c.theta * (v * v));
+    out[1] = -(c.pay2 + c.mx2 * wx + c.my * wy + c.hx * u[1].dd[0] + c.hy * u[1].dd[1] + c.cxy * u[1].x[0] -
+               c.rho * w + c.lam21 * (v - w) - c.theta * (w * w));
+  }
+};
+
 // X-macro: the registry order defines the model ids of the C ABI.
 #define ECONPDES_FOR_EACH_MODEL(X) \
   X(ReadmeLinear)                  \
@@ -381,6 +420,7 @@ struct VMinusTwo : ModelDefaults {
   X(LinearSum<2>)                  \
   X(LinearSum<3>)                  \
   X(ForwardPrice)                  \
-  X(VMinusTwo)
+  X(VMinusTwo)                     \
+  X(Hjb2dRegimes)
 
 }  // namespace econpdes

@@ -111,6 +111,24 @@ class Hjb3dSynth(RegisteredModel):
 
 
 @dataclass(frozen=True)
+class Hjb2dRegimes(RegisteredModel):
+    """Two coupled HJB equations on a 2-D grid (csrc/models.cuh: Hjb2dRegimes)."""
+    kx1: float = 0.2
+    kx2: float = 0.35
+    ky: float = 0.3
+    sx: float = 0.1
+    sy: float = 0.12
+    corr: float = 0.3
+    rho: float = 0.05
+    lam12: float = 0.4
+    lam21: float = 0.25
+    theta: float = 1e-3
+    name: ClassVar[str] = "hjb2d_regimes"
+    statenames: ClassVar = ("x", "y")
+    solnames: ClassVar = ("v", "w")
+
+
+@dataclass(frozen=True)
 class NeoclassicalGrowthModel(RegisteredModel):
     """examples/neoclassical_growth.jl:25-31."""
     A: float = 0.5
@@ -178,4 +196,4 @@ class VMinusTwo(RegisteredModel):
 
 ALL_MODELS = (ReadmeLinear, CampbellCochraneModel, BansalYaronModel, AchdouHanLasryLionsMollModel_Diffusion,
               Hjb3dSynth, NeoclassicalGrowthModel, GrowthTest, LinearSum1D, LinearSum2D, LinearSum3D,
-              ForwardPrice, VMinusTwo)
+              ForwardPrice, VMinusTwo, Hjb2dRegimes)

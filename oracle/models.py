@@ -320,6 +320,38 @@ def forward_price():
     return pde
 
 
+HJB2D_REGIMES_DEFAULT = dict(kx1=0.2, kx2=0.35, ky=0.3, sx=0.1, sy=0.12, corr=0.3, rho=0.05, lam12=0.4, lam21=0.25,
+                             theta=1e-3)
+
+
+def hjb2d_regimes(kx1, kx2, ky, sx, sy, corr, rho, lam12, lam21, theta):
+    """Two coupled HJB equations on (x, y) (regime switching); same definition as the device
+    functor Hjb2dRegimes (csrc/models.cuh).  Unknowns v, w."""
+    def pde(state, u):
+        x, y = state["x"], state["y"]
+        v, w = u["v"], u["w"]
+        mx1 = -kx1 * (x - 0.5)
+        mx2 = -kx2 * (x - 0.3)
+        my = -ky * (y - 0.5)
+        vx = np.where(mx1 >= 0, u["vx_up"], u["vx_down"])
+        vy = np.where(my >= 0, u["vy_up"], u["vy_down"])
+        wx = np.where(mx2 >= 0, u["wx_up"], u["wx_down"])
+        wy = np.where(my >= 0, u["wy_up"], u["wy_down"])
+        hx, hy, cxy = 0.5 * (sx * sx), 0.5 * (sy * sy), corr * sx * sy
+        vt = -(x + y + mx1 * vx + my * vy + hx * u["vxx"] + hy * u["vyy"] + cxy * u["vxy"] - rho * v
+               + lam12 * (w - v) - theta * (v * v))
+        wt = -(2 * x - y + 1 + mx2 * wx + my * wy + hx * u["wxx"] + hy * u["wyy"] + cxy * u["wxy"] - rho * w
+               + lam21 * (v - w) - theta * (w * w))
+        return {"vt": vt, "wt": wt}
+    return pde
+
+
+def hjb2d_regimes_problem(nx=24, ny=20, params=None):
+    prm = dict(HJB2D_REGIMES_DEFAULT if params is None else params)
+    return ({"x": julia_range(0.0, 1.0, nx), "y": julia_range(0.0, 1.0, ny)},
+            {"v": np.zeros((nx, ny)), "w": np.zeros((nx, ny))}, prm)
+
+
 def v_minus_two():
     """test/runtests.jl:227: vt = v - 2."""
     def pde(state, u):

@@ -39,6 +39,9 @@ def _cases():
     out.append(("growth", PM.NeoclassicalGrowthModel(**prm), OM.neoclassical_growth(**prm), g, gu))
     g = {"x": OM.julia_range(0.1, 1, 5)}
     out.append(("fwdprice", PM.ForwardPrice(), OM.forward_price(), g, {"v": np.ones(5), "p": np.ones(5) * 0.5}))
+    g, gu, prm = OM.hjb2d_regimes_problem(11, 9)
+    gu = {"v": 15.0 + np.zeros((11, 9)), "w": 16.0 + np.zeros((11, 9))}
+    out.append(("regimes2d", PM.Hjb2dRegimes(**prm), OM.hjb2d_regimes(**prm), g, gu))
     return out
 
 
@@ -452,6 +455,41 @@ def test_linear_solve_matches_sparse_lu(name, delta):
     assert rc == 0 and relres <= 1e-11 and 0 < iters <= 60
     want = spla.splu(_csc(nz, S, 1)).solve(b)
     np.testing.assert_allclose(x, want, rtol=0, atol=1e-9 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("delta", [1.0, 1e3, INF])
+def test_block_linear_solve_matches_sparse_lu(delta):
+    """Two unknowns per point on a 2-D grid: J x = b by FGMRES + block line relaxation equals the
+    sparse LU solve the reference performs (F x F blocks on the full +-1 box)."""
+    import scipy.sparse.linalg as spla
+    _, pm, om, g, gu = [c for c in CASES if c[0] == "regimes2d"][0]
+    grids = list(g.values())
+    S = tuple(len(x) for x in grids)
+    y, ypost = _perturbed(gu), _perturbed(gu, seed=2)
+    h = E.Handle(pm, grids, y)
+    nz, _ = h.jacobian_csc(y, ypost, delta)
+    rng = np.random.default_rng(5)
+    b = rng.normal(size=int(np.prod(S)) * 2)
+    x, iters, relres, rc = h.linear_solve(b)
+    h.close()
+    assert rc == 0 and relres <= 1e-11 and iters > 0
+    want = spla.splu(_csc(nz, S, 2)).solve(b)
+    np.testing.assert_allclose(x, want, rtol=0, atol=1e-9 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("nx,ny", [(24, 20), (64, 48)])
+def test_pdesolve_two_unknowns_on_a_2d_grid(nx, ny):
+    """pdesolve of a coupled 2-D system (F = 2, N = 2) against the oracle: same accept/reject and
+    Newton sequence, value functions to 1e-8, residual norm to 1e-10."""
+    g, gu, prm = OM.hjb2d_regimes_problem(nx, ny)
+    ora = eo.pdesolve(OM.hjb2d_regimes(**prm), g, gu)
+    res = E.pdesolve(PM.Hjb2dRegimes(**prm), g, gu, verbose=False)
+    assert res.converged == ora.converged
+    assert res.n_outer == ora.log.n_outer
+    assert [r["newton_iters"] for r in res.log] == [r[4] for r in ora.log.rows]
+    for k in ("v", "w"):
+        np.testing.assert_allclose(res.solution[k], ora.solution[k], rtol=1e-8)
+    assert abs(res.residual_norm - ora.residual_norm) <= 1e-10
 
 
 @pytest.mark.parametrize("fixture,model,gk,sk", [

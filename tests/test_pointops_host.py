@@ -35,6 +35,9 @@ def _cases():
     out.append(("lin2d", PM.LinearSum2D(), OM.linear_sum(("x", "z")), g, {"v": np.zeros((4, 5))}))
     g = {"x": OM.julia_range(0.1, 1, 5)}
     out.append(("fwdprice", PM.ForwardPrice(), OM.forward_price(), g, {"v": np.ones(5), "p": np.ones(5) * 0.5}))
+    g, gu, prm = OM.hjb2d_regimes_problem(9, 7)
+    gu = {"v": 15.0 + np.zeros((9, 7)), "w": 16.0 + np.zeros((9, 7))}
+    out.append(("regimes2d", PM.Hjb2dRegimes(**prm), OM.hjb2d_regimes(**prm), g, gu))
     return out
 
 
@@ -106,7 +109,7 @@ def test_fused_jacobian_matches_colored_fd(case, delta):
         with np.errstate(all="ignore"):
             return prob.G(v) - (ypvec - v) / delta
     nz_want, eps = eo.finite_difference_jacobian(R, yvec, cache)
-    box = name == "hjb3d"
+    box = name in ("hjb3d", "regimes2d")
     planes, r0 = EU.jacobian_planes(pm, grids, y, ypost, delta, eps, box)
     if name in POW_MODELS:
         np.testing.assert_allclose(r0, R(yvec), rtol=0, atol=8 * np.finfo(float).eps * np.abs(r0).max())
