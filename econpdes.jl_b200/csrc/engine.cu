@@ -125,9 +125,10 @@ struct ModelOpsT final : ModelOps {
   int F() const override { return M::F; }
   int nparams() const override { return M::NPARAMS; }
   void derive(double* prm) const override {
-    static_assert(M::NPARAMS + M::NDERIVED <= kMaxParams, "parameter pack too small");
+    static_assert(M::NPARAMS + M::NDERIVED + (M::TIME_SLOT >= 0 ? 1 : 0) <= kMaxParams, "parameter pack too small");
     M::derive(prm);
   }
+  int time_slot() const override { return M::TIME_SLOT; }
   int nsaved() const override { return M::NSAVED; }
   bool box() const override { return M::USES_CROSS && M::N > 1; }
   void residual(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm) const override {
@@ -513,6 +514,8 @@ NewtonOutcome Solver::newton(const double* ypost, double delta, double ftol, int
 
 int Solver::solve(const econpdes_options& opt, econpdes_result* res) {
   Ctx& c = *c_;
+  if (ops_->time_slot() >= 0)
+    throw std::invalid_argument("the PDE function takes a time argument `(state, u, t)`: pass a time grid `τs`");
   const long long n = c.n;
   cudaStream_t s = c.stream;
   const int64_t launches0 = g_kernel_launches.load();
@@ -645,7 +648,11 @@ int Solver::solve_backward(const econpdes_options& opt, const double* taus, int 
   if (saved_out != nullptr && c.nsaved > 0) saved.alloc(static_cast<size_t>(c.nsaved) * c.l);
   EP_CUDA(cudaMemcpyAsync(ypost_.p, c.guess.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
   for (int i = 0; i < ntaus; ++i) residual_norms[i] = 0.0;
+  const int tslot = ops_->time_slot();
   for (int it = ntaus - 1; it >= 0; --it) {
+    // pde_onestep = (state, u) -> pde(state, u, τs[iτ]) (src/pdesolve.jl:195): the saved outputs of this
+    // time and the step towards the previous one are both evaluated at τs[iτ]
+    if (tslot >= 0) c.prm.v[tslot] = taus[it];
     ypost_.download(solution + static_cast<size_t>(it) * n, static_cast<size_t>(n), s);
     if (saved.p != nullptr) {
       ops_->saved(c, ypost_.p, saved.p);

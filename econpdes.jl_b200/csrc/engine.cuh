@@ -119,7 +119,8 @@ struct ModelOps {
   virtual int N() const = 0;
   virtual int F() const = 0;
   virtual int nparams() const = 0;
-  virtual void derive(double* prm) const = 0;   // appends the model's parameter-only constants (models.cuh)
+  virtual void derive(double* prm) const = 0;
+  virtual int time_slot() const = 0;            // parameter slot holding the time of pde(state, u, t), or -1   // appends the model's parameter-only constants (models.cuh)
   virtual int nsaved() const = 0;
   virtual bool box() const = 0;
   virtual void residual(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm) const = 0;

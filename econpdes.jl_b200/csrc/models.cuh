@@ -41,6 +41,10 @@ struct ModelDefaults {
   // the reference performs at every grid point, so the bits are the same.
   static constexpr int NDERIVED = 0;
   EP_HD static void derive(double*) {}
+  // Bodies of the three-argument form pde(state, u, t) (src/pdesolve.jl:253-260) read the time from
+  // prm[TIME_SLOT]; the backward-induction driver stores the current time there before every step.
+  // -1: the body takes no time argument.
+  static constexpr int TIME_SLOT = -1;
 };
 constexpr int kMaxParams = 16;   // ParamPack: NPARAMS + NDERIVED
 
@@ -407,6 +411,47 @@ struct Hjb2dRegimes : ModelDefaults {
   }
 };
 
+// examples/asset_pricing/tuckman_vila.jl:67-86  state z, time tau (three-argument form)
+struct TuckmanVila : ModelDefaults {
+  static constexpr int N = 1, F = 1, NPARAMS = 6, NSAVED = 0;
+  static constexpr int TIME_SLOT = NPARAMS;
+  static constexpr bool USES_CROSS = false;
+  static const char* name() { return "tuckman_vila"; }
+  struct Pre { double z, muL, muS, muL_s2, muS_s2, inv_a, a, s2, hs2, rho_z; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& p) {
+    const double c = prm[0], r = prm[1], rho = prm[2], sigma = prm[3], a = prm[4], T = prm[5], tau = prm[TIME_SLOT];
+    const double z = st[0];
+    const double q = 1 + z * z;
+    const double phi = z * pow(q, -1 / 2.0);
+    const double phiz = pow(q, -3 / 2.0);
+    const double phizz = -3 * z * pow(q, -5 / 2.0);
+    const double stau = c / r * (1 - exp(-r * (T - tau)));
+    const double s2 = sigma * sigma;
+    p.muL = rho * z - 0.5 * s2 * phizz / phiz + c / stau * (phi - 1) / phiz;
+    p.muS = rho * z - 0.5 * s2 * phizz / phiz + c / stau * (phi + 1) / phiz;
+    p.muL_s2 = p.muL / s2;
+    p.muS_s2 = p.muS / s2;
+    p.inv_a = 1 / a;
+    p.a = a;
+    p.s2 = s2;
+    p.hs2 = 0.5 * s2;
+    p.rho_z = rho * z;
+    p.z = z;
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& p, const Deriv<1>* u, double* out, double*) {
+    const double Fzz = u[0].dd[0];
+    const double Fz = (p.z >= 0) ? u[0].up[0] : u[0].dn[0];
+    const double iL = p.inv_a * (p.muL_s2 + Fz);
+    const double iS = p.inv_a * (p.muS_s2 + Fz);
+    double mu = 0.0, i = 0.0;
+    if (iL > 0) { i = iL; mu = p.muL; }
+    else if (iS < 0) { i = iS; mu = p.muS; }
+    const double ai = p.a * i;
+    out[0] = -((mu + p.s2 * Fz) * p.a * i - p.hs2 * (ai * ai) - p.rho_z * Fz + p.hs2 * (Fzz - Fz * Fz));
+  }
+};
+
 // X-macro: the registry order defines the model ids of the C ABI.
 #define ECONPDES_FOR_EACH_MODEL(X) \
   X(ReadmeLinear)                  \
@@ -421,6 +466,7 @@ struct Hjb2dRegimes : ModelDefaults {
   X(LinearSum<3>)                  \
   X(ForwardPrice)                  \
   X(VMinusTwo)                     \
-  X(Hjb2dRegimes)
+  X(Hjb2dRegimes)                  \
+  X(TuckmanVila)
 
 }  // namespace econpdes

@@ -129,6 +129,21 @@ class Hjb2dRegimes(RegisteredModel):
 
 
 @dataclass(frozen=True)
+class TuckmanVilaModel(RegisteredModel):
+    """examples/asset_pricing/tuckman_vila.jl:20-27; the body takes the time as a third argument, so the
+    model is solved with a time grid: pdesolve(m, grid, guess, τs)."""
+    c: float = 0.06
+    r: float = 0.09
+    rho: float = 5.42
+    sigma: float = 26.72
+    a: float = 26.72
+    T: float = 100.0
+    name: ClassVar[str] = "tuckman_vila"
+    statenames: ClassVar = ("z",)
+    solnames: ClassVar = ("F",)
+
+
+@dataclass(frozen=True)
 class NeoclassicalGrowthModel(RegisteredModel):
     """examples/neoclassical_growth.jl:25-31."""
     A: float = 0.5
@@ -196,4 +211,4 @@ class VMinusTwo(RegisteredModel):
 
 ALL_MODELS = (ReadmeLinear, CampbellCochraneModel, BansalYaronModel, AchdouHanLasryLionsMollModel_Diffusion,
               Hjb3dSynth, NeoclassicalGrowthModel, GrowthTest, LinearSum1D, LinearSum2D, LinearSum3D,
-              ForwardPrice, VMinusTwo, Hjb2dRegimes)
+              ForwardPrice, VMinusTwo, Hjb2dRegimes, TuckmanVilaModel)

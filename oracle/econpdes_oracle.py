@@ -732,12 +732,15 @@ def pdesolve(pde, grid: Dict[str, np.ndarray], guess: Dict[str, np.ndarray], *, 
 
 
 def pdesolve_backward(pde, grid: Dict[str, np.ndarray], guess: Dict[str, np.ndarray], taus, *, abstol=SQRT_EPS,
-                      maxiters=100, inner_maxiters=None, inner_abstol=None, bc=None) -> EconPDEResult:
+                      maxiters=100, inner_maxiters=None, inner_abstol=None, bc=None,
+                      has_time=False) -> EconPDEResult:
     """Time-dependent ``pdesolve(pde, grid, guess, τs)``: ``_solve_backward`` (src/pdesolve.jl:158-224).
     The guess is the terminal value at τs[end]; every earlier time is one ``implicit_timestep`` with
     Δ = τs[i] − τs[i−1] (:203), ``inner_maxiters = maxiters`` and ``inner_abstol = abstol`` by
     default (:158).  solution[name][..., i] is the value at τs[i]; residual_norm[i] is the Newton
-    residual of the step that produced time i−1 (entry 0 stays 0)."""
+    residual of the step that produced time i−1 (entry 0 stays 0).  ``has_time``: the PDE function has
+    the three-argument form ``pde(state, u, t)`` (:166, :253-260) and is evaluated at t = τs[i] for the
+    saved outputs of time i and for the step from τs[i] to τs[i−1] (:195)."""
     taus = np.asarray(taus, dtype=np.float64)
     inner_maxiters = maxiters if inner_maxiters is None else inner_maxiters
     inner_abstol = abstol if inner_abstol is None else inner_abstol
@@ -745,13 +748,16 @@ def pdesolve_backward(pde, grid: Dict[str, np.ndarray], guess: Dict[str, np.ndar
     grids = tuple(np.asarray(g, dtype=np.float64) for g in grid.values())
     S = tuple(g.shape[0] for g in grids)
     F, nt = len(solnames), taus.shape[0]
-    prob = Problem(pde, statenames, grids, solnames, bc_array(bc, solnames, statenames, S))
+    clock = {"t": float(taus[-1])}
+    pde_now = (lambda state, u: pde(state, u, clock["t"])) if has_time else pde
+    prob = Problem(pde_now, statenames, grids, solnames, bc_array(bc, solnames, statenames, S))
     cache = JacobianCache(S, F)
     y = np.stack([np.asarray(guess[k], dtype=np.float64) for k in solnames], axis=-1).reshape(-1, order="F")
     solution = {name: np.empty(S + (nt,)) for name in solnames}
     saved: Dict[str, np.ndarray] = {}
     rn = np.zeros(nt)
     for it in range(nt - 1, -1, -1):                                   # :191
+        clock["t"] = float(taus[it])                                   # :195
         ya = y.reshape(S + (F,), order="F")
         for k, name in enumerate(solnames):                            # :192-194
             solution[name][..., it] = ya[..., k]

@@ -352,6 +352,39 @@ def hjb2d_regimes_problem(nx=24, ny=20, params=None):
             {"v": np.zeros((nx, ny)), "w": np.zeros((nx, ny))}, prm)
 
 
+def tuckman_vila(c=0.06, r=0.09, rho=5.42, sigma=26.72, a=26.72, T=100.0):
+    """examples/asset_pricing/tuckman_vila.jl:67-86: three-argument form pde(state, u, tau)."""
+    def pde(state, u, tau):
+        z = state["z"]
+        F, Fz_up, Fz_down, Fzz = u["F"], u["Fz_up"], u["Fz_down"], u["Fzz"]
+        Fz = np.where(z >= 0, Fz_up, Fz_down)
+        with np.errstate(all="ignore"):
+            phi = z * (1 + z ** 2) ** (-1 / 2)
+            phiz = (1 + z ** 2) ** (-3 / 2)
+            phizz = -3 * z * (1 + z ** 2) ** (-5 / 2)
+            stau = c / r * (1 - np.exp(-r * (T - tau)))
+            muL = rho * z - 0.5 * sigma ** 2 * phizz / phiz + np.float64(c) / stau * (phi - 1) / phiz
+            iL = 1 / a * (muL / sigma ** 2 + Fz)
+            muS = rho * z - 0.5 * sigma ** 2 * phizz / phiz + np.float64(c) / stau * (phi + 1) / phiz
+            iS = 1 / a * (muS / sigma ** 2 + Fz)
+            i = np.where(iL > 0, iL, np.where(iS < 0, iS, 0.0))
+            mu = np.where(iL > 0, muL, np.where(iS < 0, muS, 0.0))
+            Ft = -((mu + sigma ** 2 * Fz) * a * i - 0.5 * sigma ** 2 * (a * i) ** 2 - rho * z * Fz
+                   + 0.5 * sigma ** 2 * (Fzz - Fz ** 2))
+        return {"Ft": Ft}
+    return pde
+
+
+def tuckman_vila_problem(zn=200, nt=10, **prm):
+    """Grid, terminal value and time grid of the example (tuckman_vila.jl:39-58)."""
+    from scipy.stats import norm
+    p = dict(c=0.06, r=0.09, rho=5.42, sigma=26.72, a=26.72, T=100.0)
+    p.update(prm)
+    sd = np.sqrt(p["sigma"] ** 2 / (2 * p["rho"]))
+    z = julia_range(norm.ppf(0.00001, 0, sd), norm.ppf(0.99999, 0, sd), zn)
+    return {"z": z}, {"F": np.zeros(zn)}, julia_range(0.0, p["T"], nt), p
+
+
 def v_minus_two():
     """test/runtests.jl:227: vt = v - 2."""
     def pde(state, u):

@@ -601,6 +601,22 @@ def test_time_dependent_solve_matches_oracle():
         E.pdesolve(PM.GrowthTest(), g, gu, taus[::-1], verbose=False)
 
 
+def test_time_dependent_model_with_time_argument():
+    """Three-argument form pde(state, u, t) (src/pdesolve.jl:166, 195, 253-260): the Tuckman-Vila example
+    (examples/asset_pricing/tuckman_vila.jl) at its default grid and time grid, against the oracle."""
+    g, gu, taus, prm = OM.tuckman_vila_problem()
+    ora = eo.pdesolve_backward(OM.tuckman_vila(**prm), g, gu, taus, has_time=True)
+    res = E.pdesolve(PM.TuckmanVilaModel(**prm), g, gu, taus, verbose=False)
+    assert res.solution["F"].shape == (200, 10)
+    scale = np.abs(ora.solution["F"]).max()
+    np.testing.assert_allclose(res.solution["F"], ora.solution["F"], rtol=1e-8, atol=1e-10 * scale)
+    np.testing.assert_allclose(res.residual_norm, ora.residual_norm, rtol=0, atol=1e-10)
+    assert res.converged == ora.converged and res.converged
+    # without a time grid the body cannot be evaluated (the reference: no applicable method)
+    with pytest.raises(E.EconPDEsCudaError, match="time argument"):
+        E.pdesolve(PM.TuckmanVilaModel(**prm), g, gu, verbose=False)
+
+
 def test_time_dependent_two_dimensional_model():
     g, gu, prm = OM.bansal_yaron_problem(21, 17)
     taus = np.array([0.0, 0.5, 1.5, 4.0])

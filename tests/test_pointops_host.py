@@ -38,11 +38,16 @@ def _cases():
     g, gu, prm = OM.hjb2d_regimes_problem(9, 7)
     gu = {"v": 15.0 + np.zeros((9, 7)), "w": 16.0 + np.zeros((9, 7))}
     out.append(("regimes2d", PM.Hjb2dRegimes(**prm), OM.hjb2d_regimes(**prm), g, gu))
+    # three-argument body: the host emulation leaves the time slot at 0
+    g, gu, _, prm = OM.tuckman_vila_problem(zn=50)
+    tv = OM.tuckman_vila(**prm)
+    out.append(("tuckman", PM.TuckmanVilaModel(**prm), lambda state, u: tv(state, u, 0.0), g,
+                {"F": 100.0 * np.cos(np.linspace(0, 3, 50))}))
     return out
 
 
 CASES = _cases()
-POW_MODELS = ("ahlm", "growth", "growth_test")
+POW_MODELS = ("ahlm", "growth", "growth_test", "tuckman")
 
 
 def _perturbed(gu, seed=1):
