@@ -49,6 +49,8 @@ struct CUDAModel{M}
 end
 # e.g. CUDAModel(m::BansalYaronModel) = CUDAModel(m, "bansal_yaron",
 #          Float64[m.μbar, m.vbar, m.κμ, m.νμ, m.κv, m.νv, m.ρ, m.γ, m.ψ], ())
+#      CUDAModel(m::TuckmanVilaModel) = CUDAModel(m, "tuckman_vila", Float64[m.c, m.r, m.ρ, m.σ, m.a, m.T], ())
+#          (a three-argument body pde(state, u, τ): only the method with a time grid applies, as in the reference)
 
 last_error() = unsafe_string(ccall((:econpdes_last_error, lib), Cstring, ()))
 
@@ -125,6 +127,26 @@ function EconPDEs.pdesolve(m::CUDAModel, grid, guess, τs::AbstractVector; bc = 
     savednt = isempty(m.saved) ? NamedTuple() :
         merge(solution, NamedTuple{m.saved}(ntuple(k -> collect(selectdim(saved, length(S) + 1, k)), length(m.saved))))
     return EconPDEResult(solution, rn, savednt, abstol)
+end
+
+# A loop of `pdesolve` calls over parameter draws (calibration / estimation sweeps of a 1-D model) in one
+# call: params is nparams x B, grids and guess are S x B (one column per problem, column-major = the
+# [B][S] row-major layout of the C ABI).  The library pipelines slices of the batch over three
+# copy/compute streams; returns (solution S x B, residual_norm, exit_reason, n_outer, n_newton).
+function pdesolve_batched(name::String, params::Matrix{Float64}, grids::Matrix{Float64}, guess::Matrix{Float64};
+                          abstol = sqrt(eps()), maxiters = 100, Δ = 1.0)
+    S, B = size(grids); size(guess) == (S, B) || throw(ArgumentError("guess must be S x B like grids"))
+    opts = COptions(); ccall((:econpdes_default_options, lib), Cvoid, (Ref{COptions},), opts)
+    opts.abstol = abstol; opts.maxiters = maxiters; opts.delta = Δ
+    mid = ccall((:econpdes_model_id, lib), Cint, (Cstring,), name)
+    sol = Matrix{Float64}(undef, S, B); rn = Vector{Float64}(undef, B)
+    er = Vector{Int32}(undef, B); no = Vector{Int32}(undef, B); nn = Vector{Int32}(undef, B)
+    rc = ccall((:econpdes_solve_batched, lib), Cint,
+               (Cint, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{COptions}, Ptr{Float64}, Ptr{Float64},
+                Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
+               mid, B, S, params, grids, guess, opts, sol, rn, er, no, nn)
+    rc < 0 && throw(ArgumentError(last_error()))
+    return sol, rn, er, no, nn
 end
 
 end # module
