@@ -36,7 +36,7 @@ class Options(C.Structure):
                 ("min_delta", C.c_double), ("max_delta", C.c_double), ("max_residual_growth", C.c_double),
                 ("maxiters", C.c_int32), ("inner_maxiters", C.c_int32), ("eps_policy", C.c_int32),
                 ("linear_solver", C.c_int32), ("lin_rtol", C.c_double), ("lin_maxiters", C.c_int32),
-                ("lin_restart", C.c_int32)]
+                ("lin_restart", C.c_int32), ("check_monotonicity", C.c_int32), ("monotonicity_tol", C.c_double)]
 
 
 class LogRow(C.Structure):
@@ -48,7 +48,11 @@ class Result(C.Structure):
     _fields_ = [("solution", c_double_p), ("saved", c_double_p), ("log", C.POINTER(LogRow)),
                 ("log_capacity", C.c_int32), ("log_len", C.c_int32), ("residual_norm", C.c_double),
                 ("converged", C.c_int32), ("exit_reason", C.c_int32), ("n_outer", C.c_int32), ("n_newton", C.c_int32),
-                ("n_linear_iters", C.c_int64), ("kernel_launches", C.c_int64), ("device_ms", C.c_double)]
+                ("n_linear_iters", C.c_int64), ("kernel_launches", C.c_int64), ("device_ms", C.c_double),
+                ("sign_flags", C.c_int32), ("nonmonotone_entries", C.c_int32), ("nonmonotone_max", C.c_double)]
+
+
+SIGN_WHOLE_SYSTEM = 1 << 30
 
 
 # every symbol include/econpdes_cuda.h declares: name -> (restype, argtypes)
@@ -127,7 +131,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.econpdes_abi_version() != 1:
+    if lib.econpdes_abi_version() != 2:
         raise ImportError("libeconpdes_cuda ABI version mismatch")
     _lib = lib
     return lib

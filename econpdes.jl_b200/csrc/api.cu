@@ -158,6 +158,8 @@ void econpdes_default_options(econpdes_options* o) {
   o->lin_rtol = 1e-12;
   o->lin_maxiters = 2000;
   o->lin_restart = 40;
+  o->check_monotonicity = 0;
+  o->monotonicity_tol = 1e-6;
 }
 
 int econpdes_device_count(void) {

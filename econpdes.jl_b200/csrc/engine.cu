@@ -474,6 +474,77 @@ double Solver::masked_norm(const double* ydot, const double* y) {
   return std::sqrt(a.sumsq) / b.sumsq;
 }
 
+// Diagnostics of src/monotonicity.jl as reductions over the stencil-format Jacobian.
+// counts: [0..F) rows checked per unknown, [F..2F) rows whose residual diagonal J_ii - 1/Δ_i is opposite
+// in sign to Δ_i (_check_sign_convention!, :57-98), [2F] same-unknown spatial off-diagonal entries above
+// tol (_check_monotonicity!, :100-133), maxbits: the largest such entry (positive doubles order like their
+// bit patterns).  Integer atomics: the result does not depend on scheduling.
+static __global__ void __launch_bounds__(kBlock) k_jacobian_diagnostics(long long l, int F, int nk, int kcenter,
+                                                                  const double* __restrict__ planes, double delta,
+                                                                  const double* __restrict__ delta_rel,
+                                                                  const unsigned char* __restrict__ is_alg, double tol,
+                                                                  int stencils, int* __restrict__ counts,
+                                                                  unsigned long long* __restrict__ maxbits) {
+  const long long pt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pt >= l) return;
+  for (int k = 0; k < F; ++k) {
+    const long long row = k * l + pt;
+    const bool alg = is_alg != nullptr && is_alg[row] != 0;
+    const double di = delta_rel != nullptr ? delta * delta_rel[row] : delta;
+    if (!alg && isfinite(di)) {
+      const double d = planes[(static_cast<long long>(kcenter * F + k) * F + k) * l + pt] - 1 / di;
+      if (fabs(d) > tol) {
+        atomicAdd(&counts[k], 1);
+        const bool same = (d > 0 && di > 0) || (d < 0 && di < 0);
+        if (!same) atomicAdd(&counts[F + k], 1);
+      }
+    }
+    if (stencils) {
+      for (int ks = 0; ks < nk; ++ks) {
+        if (ks == kcenter) continue;
+        const double v = planes[(static_cast<long long>(ks * F + k) * F + k) * l + pt];
+        if (v > tol) {
+          atomicAdd(&counts[2 * F], 1);
+          atomicMax(maxbits, static_cast<unsigned long long>(__double_as_longlong(v)));
+        }
+      }
+    }
+  }
+}
+
+void Solver::jacobian_diagnostics(double delta, const econpdes_options& opt) {
+  Ctx& c = *c_;
+  // checked once, on the first assembled Jacobian; a one-shot solve (infinite Δ) is sign-agnostic (:70-71)
+  if (sign_checked_ || !std::isfinite(delta) || c.dist != nullptr) return;
+  sign_checked_ = true;
+  DevBuf<int> counts;
+  DevBuf<unsigned long long> mx;
+  counts.alloc(static_cast<size_t>(2 * c.F + 1));
+  mx.alloc(1);
+  counts.zero(c.stream);
+  mx.zero(c.stream);
+  const double* drel = (c.has_delta_vec && !c.all_delta_inf) ? c.delta_rel.p : nullptr;
+  const int kcenter = c.box ? (ipow3(c.N) - 1) / 2 : 0;
+  EP_LAUNCH(k_jacobian_diagnostics, blocks_for(c.l), kBlock, 0, c.stream, c.l, c.F, c.nk, kcenter, planes_.p, delta, drel,
+            c.is_alg.p, opt.monotonicity_tol, opt.check_monotonicity, counts.p, mx.p);
+  std::vector<int> h(static_cast<size_t>(2 * c.F + 1));
+  unsigned long long hm = 0;
+  counts.download(h.data(), h.size(), c.stream);
+  mx.download(&hm, 1, c.stream);
+  EP_CUDA(cudaStreamSynchronize(c.stream));
+  int flagged = 0, total_checked = 0;
+  for (int k = 0; k < c.F; ++k) {
+    total_checked += h[k];
+    if (h[k] > 0 && h[c.F + k] == h[k]) { sign_flags_ |= 1 << k; ++flagged; }
+  }
+  bool all_wrong = total_checked > 0;
+  for (int k = 0; k < c.F; ++k) all_wrong = all_wrong && h[c.F + k] == h[k];
+  if (drel == nullptr && delta > 0 && all_wrong) sign_flags_ |= ECONPDES_SIGN_WHOLE_SYSTEM;
+  (void)flagged;
+  nonmonotone_entries_ = h[2 * c.F];
+  std::memcpy(&nonmonotone_max_, &hm, sizeof(double));
+}
+
 // NLsolve newton_ with the Static line search, wrapped like _newtonstep (:125-147).
 NewtonOutcome Solver::newton(const double* ypost, double delta, double ftol, int maxit, const econpdes_options& opt,
                              double* y_out) {
@@ -489,6 +560,7 @@ NewtonOutcome Solver::newton(const double* ypost, double delta, double ftol, int
   while (!stopped && !fconv && !xconv && out.iters < maxit) {
     ++out.iters;
     jacobian(x, ypost, delta, opt.eps_policy);
+    jacobian_diagnostics(delta, opt);
     int li = 0;
     double rr = 0.0;
     const int fail = lin_->solve(planes_.p, R_.p, s_.p, opt, &li, &rr);
@@ -611,6 +683,9 @@ int Solver::solve(const econpdes_options& opt, econpdes_result* res) {
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   res->device_ms = ms;
+  res->sign_flags = sign_flags_;
+  res->nonmonotone_entries = nonmonotone_entries_;
+  res->nonmonotone_max = nonmonotone_max_;
   res->residual_norm = r;
   res->converged = (r <= opt.abstol) ? 1 : 0;
   if (res->log_len > res->log_capacity) res->log_len = res->log_capacity;

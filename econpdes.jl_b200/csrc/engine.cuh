@@ -175,11 +175,16 @@ class Solver {
   void csc_gather(double* nzval_dev);
   DevBuf<double> ypost_, y_, ynew_, R_, s_, G_, planes_;
   long long nnz_ = 0;
+  // src/monotonicity.jl diagnostics of the first assembled Jacobian (see econpdes_result)
+  int sign_flags_ = 0, nonmonotone_entries_ = 0;
+  double nonmonotone_max_ = 0.0;
+  bool sign_checked_ = false;
 
  private:
   RowSpec row_spec(const double* ypost, double delta) const;
   Norms read_norms();
   double masked_norm(const double* ydot, const double* y);
+  void jacobian_diagnostics(double delta, const econpdes_options& opt);
   std::unique_ptr<Ctx> c_;
   const ModelOps* ops_;
   std::unique_ptr<LinearSolver> lin_;

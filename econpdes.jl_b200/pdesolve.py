@@ -57,6 +57,10 @@ class EconPDEResult:
     n_linear_iters: int = 0
     kernel_launches: int = 0
     device_ms: float = 0.0
+    # src/monotonicity.jl diagnostics of the first assembled Jacobian (see econpdes_result)
+    sign_flags: int = 0
+    nonmonotone_entries: int = 0
+    nonmonotone_max: float = 0.0
 
     @property
     def converged(self) -> bool:
@@ -180,7 +184,7 @@ def _options(abstol, maxiters, kw) -> L.Options:
              "max_delta": "max_delta", "max_residual_growth": "max_residual_growth",
              "inner_maxiters": "inner_maxiters", "inner_abstol": "inner_abstol", "eps_policy": "eps_policy",
              "lin_rtol": "lin_rtol", "lin_maxiters": "lin_maxiters", "lin_restart": "lin_restart",
-             "linear_solver": "linear_solver"}
+             "linear_solver": "linear_solver", "monotonicity_tol": "monotonicity_tol"}
     for k in list(kw):
         if k in names:
             setattr(o, names[k], kw.pop(k))
@@ -205,6 +209,30 @@ def _print_log(res: EconPDEResult, description: str, file):
         ms = res.device_ms
         t = "%.0fms" % ms if ms < 1000 else "%.1fs" % (ms / 1000)
         print("Converged after %d time steps (%s)" % (res.n_outer, t), file=file)
+
+
+def _diagnostic_warnings(res: EconPDEResult, ynames) -> list:
+    """@warn texts of src/monotonicity.jl:84-96 (sign convention, checked by default) and a summary of
+    the opt-in stencil check (:100-133; the reference prints one warning per offending entry)."""
+    out = []
+    if res.sign_flags & L.SIGN_WHOLE_SYSTEM:
+        out.append("The residual Jacobian has a negative diagonal at every grid point: the PDE function most likely "
+                   "returns `RHS - ρv` instead of `-(RHS - ρv)`, which makes the false transient unstable (the solve "
+                   "typically diverges from iteration 1). Flip the sign of the returned time derivative.")
+    else:
+        for k, name in enumerate(ynames):
+            if res.sign_flags & (1 << k):
+                out.append(f"The equation for `{name}` has a residual-Jacobian diagonal opposite in sign to its "
+                           "pseudo-time step at every grid point, which makes its false transient unstable (the solve "
+                           f"typically diverges from iteration 1). Flip the sign of `Δ.{name}` — positive Δ marches an "
+                           "equation backward like a value function and needs a positive diagonal; negative Δ marches "
+                           "it forward like a tâtonnement price update and needs a negative one — or flip the sign of "
+                           "the returned time derivative.")
+    if res.nonmonotone_entries > 0:
+        out.append(f"The residual Jacobian has {res.nonmonotone_entries} same-variable spatial off-diagonal entries "
+                   f"with the wrong monotonicity sign (largest {res.nonmonotone_max:.3g}): the finite-difference "
+                   "scheme is not monotone there.")
+    return out
 
 
 def _warn_text(res: EconPDEResult, min_delta: float) -> Optional[str]:
@@ -313,6 +341,7 @@ def pdesolve(pde, grid, guess, taus=None, *, is_algebraic=None, bc=None, lower_b
     v = fvec(ub_arr); p.upper_bound = L.dptr(v)
     v = fvec(delta_arr); p.delta_vec = L.dptr(v)
 
+    opts.check_monotonicity = 1 if check_monotonicity else 0
     if taus is not None:
         return _solve_backward(lib, p, opts, taus, pde, S, F, ynames, statenames, abstol, verbose, warn,
                                file or sys.stdout, keep)
@@ -341,7 +370,10 @@ def pdesolve(pde, grid, guess, taus=None, *, is_algebraic=None, bc=None, lower_b
                       linear_iters=log[i].linear_iters, delta=log[i].delta, residual=log[i].residual)
                  for i in range(r.log_len))
     res = EconPDEResult(solution, r.residual_norm, sv, abstol, r.exit_reason, rows, r.n_outer, r.n_newton,
-                        r.n_linear_iters, r.kernel_launches, r.device_ms)
+                        r.n_linear_iters, r.kernel_launches, r.device_ms, r.sign_flags, r.nonmonotone_entries,
+                        r.nonmonotone_max)
+    for txt in _diagnostic_warnings(res, ynames):   # src/monotonicity.jl (emitted regardless of `warn`, like @warn there)
+        warnings.warn(txt)
     if verbose:
         desc = "%d %s (%s) on grid %s = %s" % (F, "unknown" if F == 1 else "unknowns", ", ".join(ynames),
                                                "×".join(statenames), "×".join(str(s) for s in S))

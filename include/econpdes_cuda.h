@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ECONPDES_ABI_VERSION 1
+#define ECONPDES_ABI_VERSION 2
 #define ECONPDES_MAX_DIMS 3
 #define ECONPDES_MAX_FUNCS 4
 #define ECONPDES_MAX_PARAMS 16
@@ -98,6 +98,9 @@ typedef struct econpdes_options {
   double lin_rtol;             /* relative residual target of the Krylov solve (1e-12) */
   int32_t lin_maxiters;        /* Krylov iteration cap per solve (2000) */
   int32_t lin_restart;         /* GMRES restart length (40) */
+  int32_t check_monotonicity;  /* 0; `check_monotonicity` of pdesolve (src/pdesolve.jl:82-89): also count the
+                                  same-unknown spatial off-diagonal entries of the first Jacobian above the tolerance */
+  double monotonicity_tol;     /* 1e-6 (`monotonicity_tol`) */
 } econpdes_options;
 
 typedef struct econpdes_log_row {
@@ -123,7 +126,18 @@ typedef struct econpdes_result {
   int64_t n_linear_iters;
   int64_t kernel_launches; /* kernels of this library launched during the call */
   double device_ms;        /* CUDA-event time of the solve proper (between the H2D and D2H copies) */
+  /* Jacobian diagnostics of src/monotonicity.jl, reductions over the first assembled stencil-format Jacobian:
+   * sign_flags bit k (k < F): the residual-Jacobian diagonal of unknown k is opposite in sign to its
+   * pseudo-time step at EVERY checked grid point (_check_sign_convention!, :57-98; runs by default);
+   * bit ECONPDES_SIGN_WHOLE_SYSTEM: uniform positive step and every unknown flagged (the single
+   * "returns RHS - rho v" diagnosis).  nonmonotone_entries / nonmonotone_max: number and largest value of
+   * same-unknown spatial off-diagonal entries above monotonicity_tol (_check_monotonicity!, :100-133; only
+   * with options.check_monotonicity). */
+  int32_t sign_flags;
+  int32_t nonmonotone_entries;
+  double nonmonotone_max;
 } econpdes_result;
+#define ECONPDES_SIGN_WHOLE_SYSTEM (1 << 30)
 
 int econpdes_abi_version(void);
 const char* econpdes_last_error(void);

@@ -26,6 +26,7 @@ mutable struct COptions
     max_delta::Float64; max_residual_growth::Float64
     maxiters::Int32; inner_maxiters::Int32; eps_policy::Int32; linear_solver::Int32
     lin_rtol::Float64; lin_maxiters::Int32; lin_restart::Int32
+    check_monotonicity::Int32; monotonicity_tol::Float64
     COptions() = new()
 end
 struct CLogRow
@@ -37,6 +38,7 @@ mutable struct CResult
     residual_norm::Float64
     converged::Int32; exit_reason::Int32; n_outer::Int32; n_newton::Int32
     n_linear_iters::Int64; kernel_launches::Int64; device_ms::Float64
+    sign_flags::Int32; nonmonotone_entries::Int32; nonmonotone_max::Float64   # src/monotonicity.jl diagnostics
     CResult() = new()
 end
 

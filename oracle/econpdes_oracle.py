@@ -731,6 +731,39 @@ def pdesolve(pde, grid: Dict[str, np.ndarray], guess: Dict[str, np.ndarray], *, 
     return EconPDEResult(solution, r, saved, abstol, log)
 
 
+def jacobian_diagnostics(J, delta, is_algebraic, S, F, tol=1e-6):
+    """src/monotonicity.jl on an assembled sparse Jacobian J (scipy CSC) of the implicit step with scalar
+    or per-row Δ: returns (nchecked[F], nwrong[F]) of _check_sign_convention! (:57-98) and the number and
+    largest value of same-unknown spatial off-diagonal entries above tol (_check_monotonicity!, :100-133)."""
+    n = J.shape[0]
+    l = n // F
+    dvec = np.full(n, float(delta)) if np.ndim(delta) == 0 else np.asarray(delta, dtype=np.float64)
+    alg = np.zeros(n, dtype=bool) if is_algebraic is None else np.asarray(is_algebraic, dtype=bool).reshape(-1, order="F")
+    diag = J.diagonal()
+    nchecked, nwrong = np.zeros(F, dtype=int), np.zeros(F, dtype=int)
+    for i in range(n):
+        if alg[i] or not np.isfinite(dvec[i]):
+            continue
+        d = diag[i] - 1 / dvec[i]
+        if not abs(d) > tol:
+            continue
+        k = i // l
+        nchecked[k] += 1
+        if np.sign(d) != np.sign(dvec[i]):
+            nwrong[k] += 1
+    coo = J.tocoo()
+    cnt, mx = 0, 0.0
+    for r, c, v in zip(coo.row, coo.col, coo.data):
+        if not v > tol or r == c or r // l != c // l:
+            continue
+        ri = np.unravel_index(r % l, S, order="F")
+        ci = np.unravel_index(c % l, S, order="F")
+        if max(abs(a - b) for a, b in zip(ri, ci)) <= 1:
+            cnt += 1
+            mx = max(mx, v)
+    return nchecked, nwrong, cnt, mx
+
+
 def pdesolve_backward(pde, grid: Dict[str, np.ndarray], guess: Dict[str, np.ndarray], taus, *, abstol=SQRT_EPS,
                       maxiters=100, inner_maxiters=None, inner_abstol=None, bc=None,
                       has_time=False) -> EconPDEResult:

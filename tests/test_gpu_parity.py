@@ -601,6 +601,39 @@ def test_time_dependent_solve_matches_oracle():
         E.pdesolve(PM.GrowthTest(), g, gu, taus[::-1], verbose=False)
 
 
+def test_jacobian_diagnostics_match_the_reference_checks():
+    """src/monotonicity.jl as device reductions over the first assembled Jacobian: the sign-convention
+    check (default on) and the opt-in stencil monotonicity count, against the oracle's restatement on the
+    CSC Jacobian."""
+    import warnings as W
+    # a correctly signed model raises nothing
+    g, gu = OM.readme_linear_problem(50)
+    with W.catch_warnings():
+        W.simplefilter("error")
+        res = E.pdesolve(PM.ReadmeLinear(), g, gu, verbose=False)
+    assert res.sign_flags == 0 and res.nonmonotone_entries == 0
+    # forward relaxation (negative Δ) of a value function: diagonal opposite in sign to Δ everywhere
+    with pytest.warns(UserWarning, match="equation for `v` has a residual-Jacobian diagonal opposite in sign"):
+        res = E.pdesolve(PM.ReadmeLinear(), g, gu, verbose=False, warn=False, maxiters=2, Δ=-1.0)
+    assert res.sign_flags == 1
+    # two unknowns, central cross-derivative: some corner couplings have the non-monotone sign
+    g, gu, prm = OM.hjb2d_regimes_problem(16, 12)
+    grids = list(g.values())
+    S = tuple(len(x) for x in grids)
+    y = np.stack([gu["v"], gu["w"]], axis=-1)
+    h = E.Handle(PM.Hjb2dRegimes(**prm), grids, y)
+    nz, _ = h.jacobian_csc(y, y, 1.0)
+    h.close()
+    nchk, nwrong, cnt, mx = eo.jacobian_diagnostics(_csc(nz, S, 2), 1.0, None, S, 2)
+    assert cnt > 0 and not nwrong.any()
+    with pytest.warns(UserWarning, match="wrong monotonicity sign"):
+        res = E.pdesolve(PM.Hjb2dRegimes(**prm), g, gu, verbose=False, check_monotonicity=True)
+    assert res.sign_flags == 0
+    assert res.nonmonotone_entries == cnt and res.nonmonotone_max == mx
+    res = E.pdesolve(PM.Hjb2dRegimes(**prm), g, gu, verbose=False)     # opt-in: silent by default
+    assert res.nonmonotone_entries == 0
+
+
 def test_time_dependent_model_with_time_argument():
     """Three-argument form pde(state, u, t) (src/pdesolve.jl:166, 195, 253-260): the Tuckman-Vila example
     (examples/asset_pricing/tuckman_vila.jl) at its default grid and time grid, against the oracle."""
