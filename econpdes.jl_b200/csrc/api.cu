@@ -604,10 +604,33 @@ int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, con
     const size_t S = static_cast<size_t>(b->S), P = static_cast<size_t>(b->nparams);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    long long nslices = B / (4LL * sms);           // at least four waves per slice
-    nslices = nslices < 1 ? 1 : (nslices > 8 ? 8 : nslices);
-    long long per = (B + nslices - 1) / nslices;
-    per = (per + sms - 1) / sms * sms;             // whole waves
+    // Slice sizes in whole waves (one block per SM): short slices at both ends so the pipeline fills and
+    // drains quickly (the first kernel waits for one small upload, the last download is small), long ones
+    // in the middle (at most a sixth of the batch) where copies hide behind the kernels.
+    std::vector<long long> bounds{0};
+    {
+      const long long waves = (B + sms - 1) / sms;
+      const long long cap = waves / 6 > 2 ? waves / 6 : 2;
+      std::vector<long long> sizes, back;
+      long long left = waves, w = 2;
+      while (left > 0) {                 // 2, 4, 8, ... waves from both ends towards the middle, capped
+        long long take = w < left ? w : left;
+        sizes.push_back(take);
+        left -= take;
+        if (left <= 0) break;
+        take = w < left ? w : left;
+        back.push_back(take);
+        left -= take;
+        w = 2 * w < cap ? 2 * w : cap;
+      }
+      sizes.insert(sizes.end(), back.rbegin(), back.rend());
+      for (long long wv : sizes) {
+        const long long nxt = bounds.back() + wv * sms;
+        bounds.push_back(nxt < B ? nxt : B);
+        if (bounds.back() == B) break;
+      }
+      if (bounds.back() != B) bounds.push_back(B);
+    }
     for (cudaStream_t& p : b->pipe)
       if (!p) EP_CUDA(cudaStreamCreateWithFlags(&p, cudaStreamNonBlocking));
     if (!b->err_host) EP_CUDA(cudaMallocHost(&b->err_host, 4 * static_cast<size_t>(B) * sizeof(int)));
@@ -615,9 +638,8 @@ int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, con
     const size_t nB = static_cast<size_t>(B);
     b->log_capacity = 0;
     int* err = b->err_host;
-    int c = 0;
-    for (long long first = 0; first < B; first += per, ++c) {
-      const long long last = first + per < B ? first + per : B;
+    for (size_t c = 0; c + 1 < bounds.size(); ++c) {
+      const long long first = bounds[c], last = bounds[c + 1];
       const size_t n = static_cast<size_t>(last - first), o = static_cast<size_t>(first);
       cudaStream_t s = b->pipe[c % econpdes_batch::kPipe];
       if (P > 0)
