@@ -66,6 +66,15 @@ __global__ void k_selftest_reciprocal(unsigned long long seed, long long n, unsi
     const double fa = fabs(a), q = a / b;
     const bool a_ok = !(fa > 0.0) || !(fa < INFINITY) || (fa >= 0x1p-900 && fabs(q) >= 0x1p-900);
     if (fb >= 0x1p-1000 && fb <= 0x1p1000 && a_ok && !same_bits(mdiv(a, b, got), q)) ++m1;
+    // degenerate divisors (0, +-Inf, NaN) with every kind of dividend
+    {
+      const int sel = static_cast<int>((ab >> 7) & 3);
+      const double sgn = (ab >> 9) & 1 ? -1.0 : 1.0;
+      const double bs = sel == 0 ? sgn * 0.0 : (sel == 1 ? sgn * INFINITY : (sel == 2 ? NAN : b));
+      const int asel = static_cast<int>((ab >> 10) & 7);
+      const double as = asel == 0 ? 0.0 : (asel == 1 ? -0.0 : (asel == 2 ? INFINITY : (asel == 3 ? -INFINITY : (asel == 4 ? NAN : a))));
+      if (sel != 3 && !same_bits(mdiv(as, bs, ep_rcp(bs)), as / bs)) ++m1;
+    }
   }
   if (m0) atomicAdd(&mismatch[0], m0);
   if (m1) atomicAdd(&mismatch[1], m1);
