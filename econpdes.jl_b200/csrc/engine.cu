@@ -132,8 +132,11 @@ struct ModelOpsT final : ModelOps {
   int nsaved() const override { return M::NSAVED; }
   bool box() const override { return M::USES_CROSS && M::N > 1; }
   void residual(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm) const override {
-    EP_LAUNCH(k_residual<M>, sweep_blocks(c.l), kBlock, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p, rs, out,
-              c.nw(), want_norm ? 1 : 0);
+    // 128-thread blocks, four per SM (128 registers): finer scheduling granularity than 256 x 2 at the
+    // same occupancy (measured 3-8 % faster on the 2048^2 and 256^3 sweeps)
+    constexpr int RB = 128;
+    EP_LAUNCH((k_residual<M, RB, 4>), sweep_blocks(c.l, RB), RB, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p, rs,
+              out, c.nw(), want_norm ? 1 : 0);
   }
   void jacobian(const Ctx& c, const double* y, const RowSpec& rs, int eps_policy, double* planes,
                 double* r0) const override {
@@ -305,7 +308,7 @@ std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p, Dist* dist, long long s
       EP_CUDA(cudaStreamSynchronize(s));
     }
   }
-  c->max_blocks = blocks_for(c->n) + 1;
+  c->max_blocks = blocks_for(c->n, 128) + 1;   // the smallest block size any norm-producing sweep uses
   c->norm_part.alloc(3 * static_cast<size_t>(c->max_blocks));
   c->norm_out.alloc(4);
   c->color_part.alloc(static_cast<size_t>(blocks_for(c->l)) * c->ncolors);

@@ -71,8 +71,8 @@ struct PointLoad {
   }
 };
 
-template <class M>
-__global__ void __launch_bounds__(kBlock, 2) k_residual(GridView<M::N> gv, ParamPack prm, const double* __restrict__ y,
+template <class M, int BLOCK = kBlock, int MINB = 2>
+__global__ void __launch_bounds__(BLOCK, MINB) k_residual(GridView<M::N> gv, ParamPack prm, const double* __restrict__ y,
                                                      const double* __restrict__ bc, RowSpec rs,
                                                      double* __restrict__ out, NormWork nw, int want_norm) {
   constexpr int F = M::F;
