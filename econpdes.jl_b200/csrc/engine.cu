@@ -556,6 +556,7 @@ NewtonOutcome Solver::newton(const double* ypost, double delta, double ftol, int
   double* x = y_.p;
   double* xn = ynew_.p;
   EP_CUDA(cudaMemcpyAsync(x, ypost, n * sizeof(double), cudaMemcpyDeviceToDevice, c_->stream));
+  lin_->new_step();
   Norms nr = eval_R(x, ypost, delta, R_.p);
   bool stopped = nr.any_nan;
   bool fconv = !nr.any_nan && nr.maxabs <= ftol;

@@ -139,6 +139,9 @@ struct LinearSolver {
   // returns 0 on success, 1 if the solve failed (singular / non-finite / not converged)
   virtual int solve(const double* planes, const double* b, double* x, const econpdes_options& opt, int* iters,
                     double* relres) = 0;
+  // a new Newton solve starts (new time step, new ypost): solvers that keep state across calls (the
+  // multigrid hierarchy) refresh it at the next solve
+  virtual void new_step() {}
   // device ms per launch of the solver's building blocks (bench.py): [0] stencil SpMV,
   // [1] one preconditioner application (multigrid V-cycle), [2] hierarchy set-up
   virtual void bench(const double* planes, const double* v, int reps, double* flush, size_t flush_bytes,

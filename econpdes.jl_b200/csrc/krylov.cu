@@ -1048,13 +1048,86 @@ class KrylovSolver final : public LinearSolver {
   ~KrylovSolver() override {
     if (h_) cudaFreeHost(h_);
     if (graph_exec_) cudaGraphExecDestroy(graph_exec_);
+    for (cudaEvent_t e : ev_)
+      if (e) cudaEventDestroy(e);
   }
 
+  void new_step() override { need_setup_ = true; }
+
+  // The hierarchy is a preconditioner inside FLEXIBLE GMRES, whose operator is always the current
+  // Jacobian: within one Newton solve (same time step, same ypost) the Jacobian often moves little
+  // between iterations, so the hierarchy of the first iteration is kept while that pays: once the lagged
+  // solves need, on average, more extra Krylov iterations than a set-up costs (both timed on the device),
+  // lagging is switched off for the rest of this problem (upwind switching in the consumption-saving
+  // model changes the Jacobian too much; Bansal-Yaron at 1024^2 saves 10 %).  Newton iterates are
+  // unchanged: every solve is driven to the same relative residual.  ECONPDES_LAG_PRECOND=0 rebuilds
+  // every time.
   int solve(const double* planes, const double* b, double* x, const econpdes_options& opt, int* iters,
             double* relres) override {
-    setup(planes);
-    ProfScope ps("lin fgmres total", c_.stream);
-    return fgmres(b, x, opt, iters, relres);
+    static const bool lag_env = [] { const char* e = std::getenv("ECONPDES_LAG_PRECOND"); return !(e && e[0] == '0'); }();
+    cudaStream_t s = c_.stream;
+    if (ev_[0] == nullptr)
+      for (cudaEvent_t& e : ev_) EP_CUDA(cudaEventCreate(&e));
+    bool rebuild = !lag_env || lag_off_ || need_setup_ || lev_.empty();
+    // lagging pays while the extra Krylov iterations of a lagged solve cost less than the set-up it
+    // saves, on average over the lagged solves of this problem (single solves are noisy: their
+    // right-hand sides differ)
+    // (slab-decomposed solves must take the same decision on every rank -- the set-up exchanges operator
+    // planes -- so there the rule uses iteration counts only, which are identical everywhere)
+    if (!rebuild && n_stale_ >= 3) {
+      const double avg_extra = extra_sum_ / n_stale_;
+      const bool costly = c_.dist != nullptr ? avg_extra > 0.5 * base_iters_ + 1.0
+                                             : (setup_ms_ > 0.0 && iter_ms_ > 0.0 && avg_extra * iter_ms_ > setup_ms_);
+      if (costly) {
+        rebuild = true;
+        lag_off_ = true;
+      }
+    }
+    need_setup_ = false;
+    auto run = [&](bool with_setup, int* it) {
+      if (with_setup) {
+        EP_CUDA(cudaEventRecord(ev_[0], s));
+        setup(planes);
+        EP_CUDA(cudaEventRecord(ev_[1], s));
+      } else {
+        top_A_ = planes;
+      }
+      int rc;
+      {
+        ProfScope ps("lin fgmres total", s);
+        EP_CUDA(cudaEventRecord(ev_[2], s));
+        rc = fgmres(b, x, opt, it, relres);
+        EP_CUDA(cudaEventRecord(ev_[3], s));
+      }
+      EP_CUDA(cudaEventSynchronize(ev_[3]));
+      float ms = 0.f;
+      if (with_setup) {
+        EP_CUDA(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
+        setup_ms_ = ms;
+      }
+      EP_CUDA(cudaEventElapsedTime(&ms, ev_[2], ev_[3]));
+      if (*it > 0) iter_ms_ = ms / *it;
+      return rc;
+    };
+    int it = 0;
+    int rc = run(rebuild, &it);
+    int total = it;
+    if (rebuild) {
+      base_iters_ = it;
+      stale_iters_ = 0;
+    } else if (rc != 0) {   // do not let a stale preconditioner turn into a rejected time step
+      rc = run(true, &it);
+      total += it;
+      base_iters_ = it;
+      stale_iters_ = 0;
+      lag_off_ = true;
+    } else {
+      stale_iters_ = it;
+      extra_sum_ += it - base_iters_;
+      ++n_stale_;
+    }
+    if (iters) *iters = total;
+    return rc;
   }
 
   void bench(const double* planes, const double* v, int reps, double* flush, size_t flush_bytes,
@@ -1107,6 +1180,13 @@ class KrylovSolver final : public LinearSolver {
   unsigned long long graph_sig_ = 0;
   int64_t graph_kernels_ = 0;
   bool use_graph_ = true;
+  bool need_setup_ = true;
+  int base_iters_ = 0, stale_iters_ = 0;   // Krylov iterations right after a set-up / with the lagged hierarchy
+  bool lag_off_ = false;
+  double extra_sum_ = 0.0;   // sum over the lagged solves of (their iterations - the fresh solve's)
+  int n_stale_ = 0;
+  double setup_ms_ = 0.0, iter_ms_ = 0.0;   // device time of the last set-up / per Krylov iteration
+  cudaEvent_t ev_[4] = {};
   // lines of up to this many points take the warp-per-line kernel (max 256).  Default 0: on B200 the
   // block-wide PCR hides the global-load latency of the 27 operator planes better (256^3: 260 us
   // vs 302 us per color sweep, both ~55-60 % of HBM peak; coarse levels tie), so the warp kernel
