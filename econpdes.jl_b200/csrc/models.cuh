@@ -452,6 +452,86 @@ struct TuckmanVila : ModelDefaults {
   }
 };
 
+// examples/asset_pricing/di_tella.jl:92-146   states (x, nu), unknowns (pA, pB, p); p is an algebraic
+// (constraint) variable: is_algebraic = (pA = false, pB = false, p = true).
+// saved = (sigmax, Q, r, kappa, sigmap, growth, investment)
+struct DiTella : ModelDefaults {
+  static constexpr int N = 2, F = 3, NPARAMS = 12, NSAVED = 7;
+  static constexpr bool USES_CROSS = true;
+  static const char* name() { return "di_tella"; }
+  struct Pre {
+    double gamma, psi, rho, tau, A, delta, B, sigma, phi;
+    double x, nu, munu, signu;
+  };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
+    c.gamma = prm[0]; c.psi = prm[1]; c.rho = prm[2]; c.tau = prm[3]; c.A = prm[4]; c.delta = prm[5];
+    c.B = prm[6]; c.sigma = prm[7]; c.phi = prm[8];
+    const double nubar = prm[9], kappanu = prm[10], signubar = prm[11];
+    c.x = st[0];
+    c.nu = st[1];
+    c.munu = kappanu * (nubar - c.nu);
+    c.signu = signubar * sqrt(c.nu);
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<2>* u, double* out, double* sv) {
+    const double gamma = c.gamma, psi = c.psi, rho = c.rho, tau = c.tau, A = c.A, delta = c.delta, B = c.B,
+                 sigma = c.sigma, phi = c.phi, x = c.x, nu = c.nu, munu = c.munu, signu = c.signu;
+    const double pA = u[0].v, pB = u[1].v, p = u[2].v;
+    const double q = (p - B) / (2 * A);
+    const double g = q - delta;
+    const double i = A * (q * q) + B * q;
+    const double pAnu = (munu >= 0) ? u[0].up[1] : u[0].dn[1];
+    const double pBnu = (munu >= 0) ? u[1].up[1] : u[1].dn[1];
+    const double pnu = (munu >= 0) ? u[2].up[1] : u[2].dn[1];
+    const double w = x * (1 - x) * (1 - gamma) / (gamma * (psi - 1));   // x (1-x) (1-γ) / (γ (ψ-1))
+    const double cg = (1 - gamma) / (gamma * (psi - 1));
+    double pAx = u[0].up[0], pBx = u[1].up[0], px = u[2].up[0];
+    double sigX, sigpA, sigpB, sigp, kappa, kidio, sigA, nuA, sigB, muX;
+    // the two-pass upwinding of the reference (`@goto start`): evaluate with the _up derivatives in x,
+    // redo once with the _down ones when the drift of x is not positive
+    for (int pass = 0;; ++pass) {
+      sigX = w * (pAnu / pA - pBnu / pB) * signu / (1 - w * (pAx / pA - pBx / pB));
+      sigpA = pAx / pA * sigX + pAnu / pA * signu;
+      sigpB = pBx / pB * sigX + pBnu / pB * signu;
+      sigp = px / p * sigX + pnu / p * signu;
+      kappa = (sigp + sigma - cg * (x * sigpA + (1 - x) * sigpB)) / (1 / gamma);
+      kidio = gamma * phi * nu / x;
+      sigA = kappa / gamma + cg * sigpA;
+      nuA = kidio / gamma;
+      sigB = kappa / gamma + cg * sigpB;
+      muX = x * (1 - x) * ((sigA * kappa + nuA * kidio - 1 / pA - tau) - (sigB * kappa - 1 / pB + tau * x / (1 - x)) -
+                           (sigA - sigB) * (sigma + sigp));
+      if (pass == 0 && muX <= 0) {
+        pAx = u[0].dn[0]; pBx = u[1].dn[0]; px = u[2].dn[0];
+        continue;
+      }
+      break;
+    }
+    const bool cup = sigX * signu >= 0;
+    const double pAxnu = cup ? u[0].xu[0] : u[0].xd[0];
+    const double pBxnu = cup ? u[1].xu[0] : u[1].xd[0];
+    const double pxnu = cup ? u[2].xu[0] : u[2].xd[0];
+    const double sX2 = sigX * sigX, sn2 = signu * signu;
+    const double mupA = pAx / pA * muX + pAnu / pA * munu + 0.5 * u[0].dd[0] / pA * sX2 + 0.5 * u[0].dd[1] / pA * sn2 +
+                        pAxnu / pA * sigX * signu;
+    const double mupB = pBx / pB * muX + pBnu / pB * munu + 0.5 * u[1].dd[0] / pB * sX2 + 0.5 * u[1].dd[1] / pB * sn2 +
+                        pBxnu / pB * sigX * signu;
+    const double mup = px / p * muX + pnu / p * munu + 0.5 * u[2].dd[0] / p * sX2 + 0.5 * u[2].dd[1] / p * sn2 +
+                       pxnu / p * sigX * signu;
+    const double pn = phi * nu;
+    const double r = (1 - i) / p + g + mup + sigma * sigp - kappa * (sigma + sigp) - gamma / x * (pn * pn);
+    out[0] = -pA * (1 / pA + (psi - 1) * tau / (1 - gamma) * (pow(pA / pB, (1 - gamma) / (1 - psi)) - 1) - psi * rho +
+                    (psi - 1) * (r + kappa * sigA + kidio * nuA) + mupA - (psi - 1) * gamma / 2 * (sigA * sigA + nuA * nuA) +
+                    (2 - psi - gamma) / (2 * (psi - 1)) * (sigpA * sigpA) + (1 - gamma) * sigpA * sigA);
+    out[1] = -pB * (1 / pB - psi * rho + (psi - 1) * (r + kappa * sigB) + mupB - (psi - 1) * gamma / 2 * (sigB * sigB) +
+                    (2 - psi - gamma) / (2 * (psi - 1)) * (sigpB * sigpB) + (1 - gamma) * sigpB * sigB);
+    out[2] = -p * ((1 - i) / p - x / pA - (1 - x) / pB);
+    if (SAVE) {
+      sv[0] = sigX; sv[1] = pow(pA / pB, 1 / (psi - 1)); sv[2] = r; sv[3] = kappa; sv[4] = sigp; sv[5] = g; sv[6] = i;
+    }
+  }
+};
+
 // X-macro: the registry order defines the model ids of the C ABI.
 #define ECONPDES_FOR_EACH_MODEL(X) \
   X(ReadmeLinear)                  \
@@ -467,6 +547,7 @@ struct TuckmanVila : ModelDefaults {
   X(ForwardPrice)                  \
   X(VMinusTwo)                     \
   X(Hjb2dRegimes)                  \
-  X(TuckmanVila)
+  X(TuckmanVila)                   \
+  X(DiTella)
 
 }  // namespace econpdes

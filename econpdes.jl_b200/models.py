@@ -144,6 +144,27 @@ class TuckmanVilaModel(RegisteredModel):
 
 
 @dataclass(frozen=True)
+class DiTellaModel(RegisteredModel):
+    """examples/asset_pricing/di_tella.jl:16-38; solve with is_algebraic = {"pA": False, "pB": False, "p": True}."""
+    gamma: float = 5.0
+    psi: float = 2.0
+    rho: float = 0.0665
+    tau: float = 1.15
+    A: float = 54.0
+    delta: float = 0.05
+    B: float = (0.20 - 54.0 * (0.02 + 0.05) ** 2) / (0.02 + 0.05)
+    sigma: float = 0.0125
+    phi: float = 0.2
+    nubar: float = 0.25
+    kappanu: float = 1.38
+    signubar: float = -0.17
+    name: ClassVar[str] = "di_tella"
+    statenames: ClassVar = ("x", "nu")
+    solnames: ClassVar = ("pA", "pB", "p")
+    savednames: ClassVar = ("sigmax", "Q", "r", "kappa", "sigmap", "growth", "investment")
+
+
+@dataclass(frozen=True)
 class NeoclassicalGrowthModel(RegisteredModel):
     """examples/neoclassical_growth.jl:25-31."""
     A: float = 0.5
@@ -211,4 +232,4 @@ class VMinusTwo(RegisteredModel):
 
 ALL_MODELS = (ReadmeLinear, CampbellCochraneModel, BansalYaronModel, AchdouHanLasryLionsMollModel_Diffusion,
               Hjb3dSynth, NeoclassicalGrowthModel, GrowthTest, LinearSum1D, LinearSum2D, LinearSum3D,
-              ForwardPrice, VMinusTwo, Hjb2dRegimes, TuckmanVilaModel)
+              ForwardPrice, VMinusTwo, Hjb2dRegimes, TuckmanVilaModel, DiTellaModel)

@@ -51,6 +51,8 @@ struct CUDAModel{M}
 end
 # e.g. CUDAModel(m::BansalYaronModel) = CUDAModel(m, "bansal_yaron",
 #          Float64[m.μbar, m.vbar, m.κμ, m.νμ, m.κv, m.νv, m.ρ, m.γ, m.ψ], ())
+#      CUDAModel(m::DiTellaModel) = CUDAModel(m, "di_tella", Float64[m.γ, m.ψ, m.ρ, m.τ, m.A, m.δ, m.B, m.σ, m.ϕ, m.νbar, m.κν, m.σνbar],
+#          (:σx, :Q, :r, :κ, :σp, :growth, :investment))
 #      CUDAModel(m::TuckmanVilaModel) = CUDAModel(m, "tuckman_vila", Float64[m.c, m.r, m.ρ, m.σ, m.a, m.T], ())
 #          (a three-argument body pde(state, u, τ): only the method with a time grid applies, as in the reference)
 

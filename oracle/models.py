@@ -385,6 +385,82 @@ def tuckman_vila_problem(zn=200, nt=10, **prm):
     return {"z": z}, {"F": np.zeros(zn)}, julia_range(0.0, p["T"], nt), p
 
 
+DI_TELLA_DEFAULT = dict(gamma=5.0, psi=2.0, rho=0.0665, tau=1.15, A=54.0, delta=0.05,
+                        B=(0.20 - 54.0 * (0.02 + 0.05) ** 2) / (0.02 + 0.05), sigma=0.0125, phi=0.2, nubar=0.25,
+                        kappanu=1.38, signubar=-0.17)
+
+
+def di_tella(gamma, psi, rho, tau, A, delta, B, sigma, phi, nubar, kappanu, signubar):
+    """examples/asset_pricing/di_tella.jl:92-146 (states x, nu; unknowns pA, pB, p; p algebraic).
+    The two-pass upwinding in x (`@goto start`) is evaluated for both passes and selected pointwise."""
+    def pde(state, u):
+        x, nu = state["x"], state["nu"]
+        pA, pB, p = u["pA"], u["pB"], u["p"]
+        with np.errstate(all="ignore"):
+            q = (p - B) / (2 * A)
+            g = q - delta
+            i = A * q ** 2 + B * q
+            munu = kappanu * (nubar - nu)
+            signu = signubar * np.sqrt(nu)
+            up = munu >= 0
+            pAnu = np.where(up, u["pAnu_up"], u["pAnu_down"])
+            pBnu = np.where(up, u["pBnu_up"], u["pBnu_down"])
+            pnu = np.where(up, u["pnu_up"], u["pnu_down"])
+
+            def block(pAx, pBx, px):
+                sigX = x * (1 - x) * (1 - gamma) / (gamma * (psi - 1)) * (pAnu / pA - pBnu / pB) * signu / (
+                    1 - x * (1 - x) * (1 - gamma) / (gamma * (psi - 1)) * (pAx / pA - pBx / pB))
+                sigpA = pAx / pA * sigX + pAnu / pA * signu
+                sigpB = pBx / pB * sigX + pBnu / pB * signu
+                sigp = px / p * sigX + pnu / p * signu
+                kappa = (sigp + sigma - (1 - gamma) / (gamma * (psi - 1)) * (x * sigpA + (1 - x) * sigpB)) / (1 / gamma)
+                kidio = gamma * phi * nu / x
+                sigA = kappa / gamma + (1 - gamma) / (gamma * (psi - 1)) * sigpA
+                nuA = kidio / gamma
+                sigB = kappa / gamma + (1 - gamma) / (gamma * (psi - 1)) * sigpB
+                muX = x * (1 - x) * ((sigA * kappa + nuA * kidio - 1 / pA - tau)
+                                     - (sigB * kappa - 1 / pB + tau * x / (1 - x)) - (sigA - sigB) * (sigma + sigp))
+                return sigX, sigpA, sigpB, sigp, kappa, kidio, sigA, nuA, sigB, muX
+            first = block(u["pAx_up"], u["pBx_up"], u["px_up"])
+            second = block(u["pAx_down"], u["pBx_down"], u["px_down"])
+            redo = first[-1] <= 0
+            sigX, sigpA, sigpB, sigp, kappa, kidio, sigA, nuA, sigB, muX = (np.where(redo, b2, b1)
+                                                                              for b1, b2 in zip(first, second))
+            pAx = np.where(redo, u["pAx_down"], u["pAx_up"])
+            pBx = np.where(redo, u["pBx_down"], u["pBx_up"])
+            px = np.where(redo, u["px_down"], u["px_up"])
+            cup = sigX * signu >= 0
+            pAxnu = np.where(cup, u["pAxnu_up"], u["pAxnu_down"])
+            pBxnu = np.where(cup, u["pBxnu_up"], u["pBxnu_down"])
+            pxnu = np.where(cup, u["pxnu_up"], u["pxnu_down"])
+            mupA = (pAx / pA * muX + pAnu / pA * munu + 0.5 * u["pAxx"] / pA * sigX ** 2 + 0.5 * u["pAnunu"] / pA * signu ** 2
+                    + pAxnu / pA * sigX * signu)
+            mupB = (pBx / pB * muX + pBnu / pB * munu + 0.5 * u["pBxx"] / pB * sigX ** 2 + 0.5 * u["pBnunu"] / pB * signu ** 2
+                    + pBxnu / pB * sigX * signu)
+            mup = (px / p * muX + pnu / p * munu + 0.5 * u["pxx"] / p * sigX ** 2 + 0.5 * u["pnunu"] / p * signu ** 2
+                   + pxnu / p * sigX * signu)
+            r = (1 - i) / p + g + mup + sigma * sigp - kappa * (sigma + sigp) - gamma / x * (phi * nu) ** 2
+            pAt = -pA * (1 / pA + (psi - 1) * tau / (1 - gamma) * ((pA / pB) ** ((1 - gamma) / (1 - psi)) - 1) - psi * rho
+                         + (psi - 1) * (r + kappa * sigA + kidio * nuA) + mupA - (psi - 1) * gamma / 2 * (sigA ** 2 + nuA ** 2)
+                         + (2 - psi - gamma) / (2 * (psi - 1)) * sigpA ** 2 + (1 - gamma) * sigpA * sigA)
+            pBt = -pB * (1 / pB - psi * rho + (psi - 1) * (r + kappa * sigB) + mupB - (psi - 1) * gamma / 2 * sigB ** 2
+                         + (2 - psi - gamma) / (2 * (psi - 1)) * sigpB ** 2 + (1 - gamma) * sigpB * sigB)
+            pt = -p * ((1 - i) / p - x / pA - (1 - x) / pB)
+            Q = (pA / pB) ** (1 / (psi - 1))
+        return ({"pAt": pAt, "pBt": pBt, "pt": pt},
+                {"sigmax": sigX, "Q": Q, "r": r, "kappa": kappa, "sigmap": sigp, "growth": g, "investment": i})
+    return pde
+
+
+def di_tella_problem(xn=30, nun=30, params=None):
+    """Grid and guess of the example (di_tella.jl:52-76)."""
+    prm = dict(DI_TELLA_DEFAULT if params is None else params)
+    xs = np.array(sorted(set(julia_range(0.01, 0.99, xn).tolist() + [0.05, 0.10, 0.20])))
+    nus = np.array(sorted(set(julia_range(0.01, 1.00, nun).tolist() + [0.10, 0.25, 0.60])))
+    shape = (len(xs), len(nus))
+    return {"x": xs, "nu": nus}, {"pA": np.ones(shape), "pB": np.ones(shape), "p": np.ones(shape)}, prm
+
+
 def v_minus_two():
     """test/runtests.jl:227: vt = v - 2."""
     def pde(state, u):

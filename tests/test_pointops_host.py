@@ -38,6 +38,8 @@ def _cases():
     g, gu, prm = OM.hjb2d_regimes_problem(9, 7)
     gu = {"v": 15.0 + np.zeros((9, 7)), "w": 16.0 + np.zeros((9, 7))}
     out.append(("regimes2d", PM.Hjb2dRegimes(**prm), OM.hjb2d_regimes(**prm), g, gu))
+    g, gu, prm = OM.di_tella_problem(7, 6)
+    out.append(("ditella", PM.DiTellaModel(**prm), OM.di_tella(**prm), g, gu))
     # three-argument body: the host emulation leaves the time slot at 0
     g, gu, _, prm = OM.tuckman_vila_problem(zn=50)
     tv = OM.tuckman_vila(**prm)
@@ -47,7 +49,7 @@ def _cases():
 
 
 CASES = _cases()
-POW_MODELS = ("ahlm", "growth", "growth_test", "tuckman")
+POW_MODELS = ("ahlm", "growth", "growth_test", "tuckman", "ditella")
 
 
 def _perturbed(gu, seed=1):
@@ -114,7 +116,7 @@ def test_fused_jacobian_matches_colored_fd(case, delta):
         with np.errstate(all="ignore"):
             return prob.G(v) - (ypvec - v) / delta
     nz_want, eps = eo.finite_difference_jacobian(R, yvec, cache)
-    box = name in ("hjb3d", "regimes2d")
+    box = name in ("hjb3d", "regimes2d", "ditella")
     planes, r0 = EU.jacobian_planes(pm, grids, y, ypost, delta, eps, box)
     if name in POW_MODELS:
         np.testing.assert_allclose(r0, R(yvec), rtol=0, atol=8 * np.finfo(float).eps * np.abs(r0).max())
