@@ -532,6 +532,113 @@ struct DiTella : ModelDefaults {
   }
 };
 
+// examples/consumption_saving/consumption_saving_two_income.jl:68-112   state a, unknowns (vl, vh)
+// saved = (cl, ch, mula, muha)
+struct AhlmTwoStates : ModelDefaults {
+  static constexpr int N = 1, F = 2, NPARAMS = 9, NSAVED = 4;
+  static constexpr bool USES_CROSS = false;
+  static const char* name() { return "ahlm_two_states"; }
+  struct Pre { double yl, yh, llh, lhl, r, rho, gamma, amin, a, clmax, chmax, incl, inch, nig, omg; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
+    c.nig = -1 / prm[6];
+    c.omg = 1 - prm[6];
+    c.yl = prm[0]; c.yh = prm[1]; c.llh = prm[2]; c.lhl = prm[3]; c.r = prm[4]; c.rho = prm[5]; c.gamma = prm[6];
+    c.amin = prm[7];   // prm[8] = amax is only used to build the grid
+    c.a = st[0];
+    c.clmax = 100.0 * (c.yl + c.r * ep_max(c.a, 0.0));
+    c.chmax = 100.0 * (c.yh + c.r * ep_max(c.a, 0.0));
+    c.incl = c.yl + c.r * c.a;
+    c.inch = c.yh + c.r * c.a;
+  }
+  // one income state: upwind the asset drift, cap consumption, pin the drift at the borrowing limit
+  EP_HD static void branch(const Pre& p, double va_up, double va_down, double cmax, double inc, double& va, double& c,
+                           double& mua) {
+    const double c_up = va_up > 0 ? ep_min(pow(va_up, p.nig), cmax) : cmax;
+    const double mua_up = inc - c_up;
+    if (mua_up >= 0.0) {
+      va = va_up; c = c_up; mua = mua_up;
+    } else {
+      const double c_down = va_down > 0 ? ep_min(pow(va_down, p.nig), cmax) : cmax;
+      const double mua_down = inc - c_down;
+      if (mua_down <= 0.0 && p.a > p.amin) {
+        va = va_down; c = c_down; mua = mua_down;
+      } else {
+        c = inc;
+        mua = 0.0;
+        va = pow(c, -p.gamma);
+      }
+    }
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& p, const Deriv<1>* u, double* out, double* sv) {
+    const double vl = u[0].v, vh = u[1].v;
+    double vla, cl, mula, vha, ch, muha;
+    branch(p, u[0].up[0], u[0].dn[0], p.clmax, p.incl, vla, cl, mula);
+    out[0] = -(pow(cl, p.omg) / p.omg + mula * vla + p.llh * (vh - vl) - p.rho * vl);
+    branch(p, u[1].up[0], u[1].dn[0], p.chmax, p.inch, vha, ch, muha);
+    out[1] = -(pow(ch, p.omg) / p.omg + muha * vha + p.lhl * (vl - vh) - p.rho * vh);
+    if (SAVE) { sv[0] = cl; sv[1] = ch; sv[2] = mula; sv[3] = muha; }
+  }
+};
+
+// examples/asset_pricing/garleanu_panageas.jl:74-117   state x, unknowns (pA, pB, phi1, phi2)
+// saved = (r, kappa).  B1, B2 arrive normalised as the struct's constructor stores them (:35-39).
+struct GarleanuPanageas : ModelDefaults {
+  static constexpr int N = 1, F = 4, NPARAMS = 14, NSAVED = 2;
+  static constexpr bool USES_CROSS = false;
+  static const char* name() { return "garleanu_panageas"; }
+  struct Pre { double gA, psA, gB, psB, rho, delta, nuA, mu, sigma, B1, d1, B2, d2, omega, x; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
+    c.gA = prm[0]; c.psA = prm[1]; c.gB = prm[2]; c.psB = prm[3]; c.rho = prm[4]; c.delta = prm[5]; c.nuA = prm[6];
+    c.mu = prm[7]; c.sigma = prm[8]; c.B1 = prm[9]; c.d1 = prm[10]; c.B2 = prm[11]; c.d2 = prm[12]; c.omega = prm[13];
+    c.x = st[0];
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<1>* u, double* out, double* sv) {
+    const double gA = c.gA, psA = c.psA, gB = c.gB, psB = c.psB, rho = c.rho, delta = c.delta, nuA = c.nuA, mu = c.mu,
+                 sigma = c.sigma, B1 = c.B1, d1 = c.d1, B2 = c.B2, d2 = c.d2, omega = c.omega, x = c.x;
+    const double pA = u[0].v, pB = u[1].v, f1 = u[2].v, f2 = u[3].v;
+    double pAx = u[0].up[0], pBx = u[1].up[0], f1x = u[2].up[0], f2x = u[3].up[0];
+    double G, sigx, spA, spB, sf1, sf2, kappa, sCA, sCB, mcA, mcB, r, muCA, muCB, mux;
+    for (int pass = 0;; ++pass) {   // `@goto start`: redo once with the _down derivatives when the drift is not positive
+      G = 1 / (x / gA + (1 - x) / gB);
+      sigx = sigma * x * (G / gA - 1) /
+             (1 + G * x * (1 - x) / (gA * gB) * ((1 - gB * psB) / (psB - 1) * (pBx / pB) - (1 - gA * psA) / (psA - 1) * (pAx / pA)));
+      spA = pAx / pA * sigx;
+      spB = pBx / pB * sigx;
+      sf1 = f1x / f1 * sigx;
+      sf2 = f2x / f2 * sigx;
+      kappa = G * (sigma - x * (1 - gA * psA) / (gA * (psA - 1)) * spA - (1 - x) * (1 - gB * psB) / (gB * (psB - 1)) * spB);
+      sCA = kappa / gA + (1 - gA * psA) / (gA * (psA - 1)) * spA;
+      sCB = kappa / gB + (1 - gB * psB) / (gB * (psB - 1)) * spB;
+      mcA = kappa * kappa * (1 + psA) / (2 * gA) + (1 - psA * gA) / (gA * (psA - 1)) * kappa * spA -
+            (1 - gA * psA) / (2 * gA * (psA - 1)) * (spA * spA);
+      mcB = kappa * kappa * (1 + psB) / (2 * gB) + (1 - psB * gB) / (gB * (psB - 1)) * kappa * spB -
+            (1 - gB * psB) / (2 * gB * (psB - 1)) * (spB * spB);
+      r = rho + 1 / (psA * x + psB * (1 - x)) *
+                    (mu - x * mcA - (1 - x) * mcB - delta * ((nuA / pA + (1 - nuA) / pB) * omega * (B1 * f1 + B2 * f2) - 1));
+      muCA = psA * (r - rho) + mcA;
+      muCB = psB * (r - rho) + mcB;
+      mux = x * (muCA - mu) + delta * (nuA / pA * omega * (B1 * f1 + B2 * f2) - x) - sigma * sigx;
+      if (pass == 0 && mux <= 0) {
+        pAx = u[0].dn[0]; pBx = u[1].dn[0]; f1x = u[2].dn[0]; f2x = u[3].dn[0];
+        continue;
+      }
+      break;
+    }
+    const double sx2 = sigx * sigx;
+    const double mupA = pAx / pA * mux + 0.5 * u[0].dd[0] / pA * sx2;
+    const double mupB = pBx / pB * mux + 0.5 * u[1].dd[0] / pB * sx2;
+    const double muf1 = f1x / f1 * mux + 0.5 * u[2].dd[0] / f1 * sx2;
+    const double muf2 = f2x / f2 * mux + 0.5 * u[3].dd[0] / f2 * sx2;
+    out[0] = -pA * (1 / pA + muCA + mupA + sCA * spA - r - delta - kappa * (spA + sCA));
+    out[1] = -pB * (1 / pB + muCB + mupB + sCB * spB - r - delta - kappa * (spB + sCB));
+    out[2] = -f1 * (1 / f1 + mu - delta - d1 + muf1 + sigma * sf1 - r - kappa * (sf1 + sigma));
+    out[3] = -f2 * (1 / f2 + mu - delta - d2 + muf2 + sigma * sf2 - r - kappa * (sf2 + sigma));
+    if (SAVE) { sv[0] = r; sv[1] = kappa; }
+  }
+};
+
 // X-macro: the registry order defines the model ids of the C ABI.
 #define ECONPDES_FOR_EACH_MODEL(X) \
   X(ReadmeLinear)                  \
@@ -548,6 +655,8 @@ struct DiTella : ModelDefaults {
   X(VMinusTwo)                     \
   X(Hjb2dRegimes)                  \
   X(TuckmanVila)                   \
-  X(DiTella)
+  X(DiTella)                       \
+  X(AhlmTwoStates)                 \
+  X(GarleanuPanageas)
 
 }  // namespace econpdes

@@ -165,6 +165,49 @@ class DiTellaModel(RegisteredModel):
 
 
 @dataclass(frozen=True)
+class AchdouHanLasryLionsMollModel_TwoStates(RegisteredModel):
+    """examples/consumption_saving/consumption_saving_two_income.jl:22-32 (amin already nudged inside the
+    natural borrowing limit, :44)."""
+    yl: float = 0.5
+    yh: float = 1.5
+    llh: float = 0.2
+    lhl: float = 0.2
+    r: float = 0.03
+    rho: float = 0.04
+    gamma: float = 2.0
+    amin: float = -0.5 / 0.03 + 0.001
+    amax: float = 50.0
+    name: ClassVar[str] = "ahlm_two_states"
+    statenames: ClassVar = ("a",)
+    solnames: ClassVar = ("vl", "vh")
+    savednames: ClassVar = ("cl", "ch", "mula", "muha")
+
+
+@dataclass(frozen=True)
+class GarleanuPanageasModel(RegisteredModel):
+    """examples/asset_pricing/garleanu_panageas.jl:20-40.  B1, B2 are the NORMALISED loadings the reference
+    struct stores (its constructor divides by δ/(δ+δ1) B1 + δ/(δ+δ2) B2); `default()` builds them."""
+    gA: float = 1.5
+    psA: float = 0.7
+    gB: float = 10.0
+    psB: float = 0.05
+    rho: float = 0.001
+    delta: float = 0.02
+    nuA: float = 0.01
+    mu: float = 0.02
+    sigma: float = 0.041
+    B1: float = 30.72 / (0.02 / (0.02 + 0.0525) * 30.72 + 0.02 / (0.02 + 0.0611) * -30.29)
+    d1: float = 0.0525
+    B2: float = -30.29 / (0.02 / (0.02 + 0.0525) * 30.72 + 0.02 / (0.02 + 0.0611) * -30.29)
+    d2: float = 0.0611
+    omega: float = 0.92
+    name: ClassVar[str] = "garleanu_panageas"
+    statenames: ClassVar = ("x",)
+    solnames: ClassVar = ("pA", "pB", "phi1", "phi2")
+    savednames: ClassVar = ("r", "kappa")
+
+
+@dataclass(frozen=True)
 class NeoclassicalGrowthModel(RegisteredModel):
     """examples/neoclassical_growth.jl:25-31."""
     A: float = 0.5
@@ -232,4 +275,5 @@ class VMinusTwo(RegisteredModel):
 
 ALL_MODELS = (ReadmeLinear, CampbellCochraneModel, BansalYaronModel, AchdouHanLasryLionsMollModel_Diffusion,
               Hjb3dSynth, NeoclassicalGrowthModel, GrowthTest, LinearSum1D, LinearSum2D, LinearSum3D,
-              ForwardPrice, VMinusTwo, Hjb2dRegimes, TuckmanVilaModel, DiTellaModel)
+              ForwardPrice, VMinusTwo, Hjb2dRegimes, TuckmanVilaModel, DiTellaModel,
+              AchdouHanLasryLionsMollModel_TwoStates, GarleanuPanageasModel)

@@ -53,6 +53,10 @@ end
 #          Float64[m.μbar, m.vbar, m.κμ, m.νμ, m.κv, m.νv, m.ρ, m.γ, m.ψ], ())
 #      CUDAModel(m::DiTellaModel) = CUDAModel(m, "di_tella", Float64[m.γ, m.ψ, m.ρ, m.τ, m.A, m.δ, m.B, m.σ, m.ϕ, m.νbar, m.κν, m.σνbar],
 #          (:σx, :Q, :r, :κ, :σp, :growth, :investment))
+#      CUDAModel(m::GarleanuPanageasModel) = CUDAModel(m, "garleanu_panageas",
+#          Float64[m.γA, m.ψA, m.γB, m.ψB, m.ρ, m.δ, m.νA, m.μ, m.σ, m.B1, m.δ1, m.B2, m.δ2, m.ω], (:r, :κ))
+#      CUDAModel(m::AchdouHanLasryLionsMollModel_TwoStates) = CUDAModel(m, "ahlm_two_states",
+#          Float64[m.yl, m.yh, m.λlh, m.λhl, m.r, m.ρ, m.γ, m.amin, m.amax], (:cl, :ch, :μla, :μha))
 #      CUDAModel(m::TuckmanVilaModel) = CUDAModel(m, "tuckman_vila", Float64[m.c, m.r, m.ρ, m.σ, m.a, m.T], ())
 #          (a three-argument body pde(state, u, τ): only the method with a time grid applies, as in the reference)
 

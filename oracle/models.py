@@ -461,6 +461,113 @@ def di_tella_problem(xn=30, nun=30, params=None):
     return {"x": xs, "nu": nus}, {"pA": np.ones(shape), "pB": np.ones(shape), "p": np.ones(shape)}, prm
 
 
+def ahlm_two_states(yl=0.5, yh=1.5, llh=0.2, lhl=0.2, r=0.03, rho=0.04, gamma=2.0, amin=None, amax=50.0):
+    """examples/consumption_saving/consumption_saving_two_income.jl:68-112 (unknowns vl, vh on the asset grid)."""
+    if amin is None:
+        amin = -yl / r + 0.001
+
+    def one(a, va_up, va_down, y):
+        cmax = 100.0 * (y + r * np.maximum(a, 0.0))
+        with np.errstate(all="ignore"):
+            c_up = np.where(va_up > 0, np.minimum(np.abs(va_up) ** (-1 / gamma), cmax), cmax)
+            mu_up = y + r * a - c_up
+            c_down = np.where(va_down > 0, np.minimum(np.abs(va_down) ** (-1 / gamma), cmax), cmax)
+            mu_down = y + r * a - c_down
+            use_up = mu_up >= 0.0
+            use_down = (~use_up) & (mu_down <= 0.0) & (a > amin)
+            c3 = y + r * a
+            c = np.where(use_up, c_up, np.where(use_down, c_down, c3))
+            mu = np.where(use_up, mu_up, np.where(use_down, mu_down, 0.0))
+            va = np.where(use_up, va_up, np.where(use_down, va_down, np.abs(c3) ** (-gamma)))
+        return va, c, mu
+
+    def pde(state, u):
+        a = state["a"]
+        vl, vh = u["vl"], u["vh"]
+        vla, cl, mula = one(a, u["vla_up"], u["vla_down"], yl)
+        vha, ch, muha = one(a, u["vha_up"], u["vha_down"], yh)
+        with np.errstate(all="ignore"):
+            vlt = -(cl ** (1 - gamma) / (1 - gamma) + mula * vla + llh * (vh - vl) - rho * vl)
+            vht = -(ch ** (1 - gamma) / (1 - gamma) + muha * vha + lhl * (vl - vh) - rho * vh)
+        return {"vlt": vlt, "vht": vht}, {"cl": cl, "ch": ch, "mula": mula, "muha": muha}
+    return pde
+
+
+def ahlm_two_states_problem(n=200, **over):
+    """Grid and guess of the example (consumption_saving_two_income.jl:41-54)."""
+    prm = dict(yl=0.5, yh=1.5, llh=0.2, lhl=0.2, r=0.03, rho=0.04, gamma=2.0, amax=50.0)
+    prm.update(over)
+    prm.setdefault("amin", -prm["yl"] / prm["r"] + 0.001)
+    yl, yh, r, rho, gamma, amin, amax = (prm[k] for k in ("yl", "yh", "r", "rho", "gamma", "amin", "amax"))
+    a = amin + julia_range(0.0, (amax - amin) ** (1 / 2), n) ** 2
+    vl = (rho / gamma + (1 - 1 / gamma) * r) ** (-gamma) * (a + yl / r) ** (1 - gamma) / (1 - gamma)
+    vh = (rho / gamma + (1 - gamma) * r) ** (-gamma) * (a + yh / r) ** (1 - gamma) / (1 - gamma)
+    return {"a": a}, {"vl": vl, "vh": vh}, prm
+
+
+def garleanu_panageas_params(gA=1.5, psA=0.7, gB=10.0, psB=0.05, rho=0.001, delta=0.02, nuA=0.01, mu=0.02, sigma=0.041,
+                             B1=30.72, d1=0.0525, B2=-30.29, d2=0.0611, omega=0.92):
+    """Struct of examples/asset_pricing/garleanu_panageas.jl:20-40; the constructor normalises B1, B2."""
+    scale = delta / (delta + d1) * B1 + delta / (delta + d2) * B2
+    return dict(gA=gA, psA=psA, gB=gB, psB=psB, rho=rho, delta=delta, nuA=nuA, mu=mu, sigma=sigma, B1=B1 / scale, d1=d1,
+                B2=B2 / scale, d2=d2, omega=omega)
+
+
+def garleanu_panageas(gA, psA, gB, psB, rho, delta, nuA, mu, sigma, B1, d1, B2, d2, omega):
+    """examples/asset_pricing/garleanu_panageas.jl:74-117 (unknowns pA, pB, phi1, phi2 on x in [0, 1])."""
+    def pde(state, u):
+        x = state["x"]
+        pA, pB, f1, f2 = u["pA"], u["pB"], u["phi1"], u["phi2"]
+
+        def block(pAx, pBx, f1x, f2x):
+            G = 1 / (x / gA + (1 - x) / gB)
+            sigx = sigma * x * (G / gA - 1) / (1 + G * x * (1 - x) / (gA * gB) * (
+                (1 - gB * psB) / (psB - 1) * (pBx / pB) - (1 - gA * psA) / (psA - 1) * (pAx / pA)))
+            spA = pAx / pA * sigx
+            spB = pBx / pB * sigx
+            sf1 = f1x / f1 * sigx
+            sf2 = f2x / f2 * sigx
+            kappa = G * (sigma - x * (1 - gA * psA) / (gA * (psA - 1)) * spA - (1 - x) * (1 - gB * psB) / (gB * (psB - 1)) * spB)
+            sCA = kappa / gA + (1 - gA * psA) / (gA * (psA - 1)) * spA
+            sCB = kappa / gB + (1 - gB * psB) / (gB * (psB - 1)) * spB
+            mcA = kappa ** 2 * (1 + psA) / (2 * gA) + (1 - psA * gA) / (gA * (psA - 1)) * kappa * spA - (1 - gA * psA) / (
+                2 * gA * (psA - 1)) * spA ** 2
+            mcB = kappa ** 2 * (1 + psB) / (2 * gB) + (1 - psB * gB) / (gB * (psB - 1)) * kappa * spB - (1 - gB * psB) / (
+                2 * gB * (psB - 1)) * spB ** 2
+            r = rho + 1 / (psA * x + psB * (1 - x)) * (mu - x * mcA - (1 - x) * mcB - delta * (
+                (nuA / pA + (1 - nuA) / pB) * omega * (B1 * f1 + B2 * f2) - 1))
+            muCA = psA * (r - rho) + mcA
+            muCB = psB * (r - rho) + mcB
+            mux = x * (muCA - mu) + delta * (nuA / pA * omega * (B1 * f1 + B2 * f2) - x) - sigma * sigx
+            return sigx, spA, spB, sf1, sf2, kappa, sCA, sCB, r, muCA, muCB, mux
+        with np.errstate(all="ignore"):
+            first = block(u["pAx_up"], u["pBx_up"], u["phi1x_up"], u["phi2x_up"])
+            second = block(u["pAx_down"], u["pBx_down"], u["phi1x_down"], u["phi2x_down"])
+            redo = first[-1] <= 0
+            sigx, spA, spB, sf1, sf2, kappa, sCA, sCB, r, muCA, muCB, mux = (np.where(redo, b2, b1)
+                                                                              for b1, b2 in zip(first, second))
+            pAx = np.where(redo, u["pAx_down"], u["pAx_up"])
+            pBx = np.where(redo, u["pBx_down"], u["pBx_up"])
+            f1x = np.where(redo, u["phi1x_down"], u["phi1x_up"])
+            f2x = np.where(redo, u["phi2x_down"], u["phi2x_up"])
+            mupA = pAx / pA * mux + 0.5 * u["pAxx"] / pA * sigx ** 2
+            mupB = pBx / pB * mux + 0.5 * u["pBxx"] / pB * sigx ** 2
+            muf1 = f1x / f1 * mux + 0.5 * u["phi1xx"] / f1 * sigx ** 2
+            muf2 = f2x / f2 * mux + 0.5 * u["phi2xx"] / f2 * sigx ** 2
+            pAt = -pA * (1 / pA + muCA + mupA + sCA * spA - r - delta - kappa * (spA + sCA))
+            pBt = -pB * (1 / pB + muCB + mupB + sCB * spB - r - delta - kappa * (spB + sCB))
+            f1t = -f1 * (1 / f1 + mu - delta - d1 + muf1 + sigma * sf1 - r - kappa * (sf1 + sigma))
+            f2t = -f2 * (1 / f2 + mu - delta - d2 + muf2 + sigma * sf2 - r - kappa * (sf2 + sigma))
+        return {"pAt": pAt, "pBt": pBt, "phi1t": f1t, "phi2t": f2t}, {"r": r, "kappa": kappa}
+    return pde
+
+
+def garleanu_panageas_problem(n=100, **over):
+    prm = garleanu_panageas_params(**over)
+    x = julia_range(0.0, 1.0, n)
+    return {"x": x}, {k: np.ones(n) for k in ("pA", "pB", "phi1", "phi2")}, prm
+
+
 def v_minus_two():
     """test/runtests.jl:227: vt = v - 2."""
     def pde(state, u):

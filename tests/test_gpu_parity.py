@@ -477,6 +477,42 @@ def test_block_linear_solve_matches_sparse_lu(delta):
     np.testing.assert_allclose(x, want, rtol=0, atol=1e-9 * np.abs(want).max())
 
 
+def test_two_income_example_block_tridiagonal():
+    """examples/consumption_saving/consumption_saving_two_income.jl at its default grid (200 points): two
+    value functions coupled by the income switching intensities -> 2 x 2 block-tridiagonal Newton systems
+    (block PCR), saved policies."""
+    g, gu, prm = OM.ahlm_two_states_problem()
+    ora = eo.pdesolve(OM.ahlm_two_states(**prm), g, gu)
+    res = E.pdesolve(PM.AchdouHanLasryLionsMollModel_TwoStates(**prm), g, gu, verbose=False)
+    assert res.converged == ora.converged and res.converged
+    assert [r["status"] for r in res.log] == [r[3] for r in ora.log.rows]
+    assert [r["newton_iters"] for r in res.log] == [r[4] for r in ora.log.rows]
+    for k in ("vl", "vh"):
+        np.testing.assert_allclose(res.solution[k], ora.solution[k], rtol=1e-8)
+    assert abs(res.residual_norm - ora.residual_norm) <= 1e-10
+    for k in ("cl", "ch", "mula", "muha"):
+        np.testing.assert_allclose(res.saved[k], ora.saved[k], rtol=1e-7, atol=1e-10)
+    assert res.saved["mula"][0] == 0.0          # the low-income household is constrained at the borrowing limit
+
+
+def test_garleanu_panageas_example_four_unknowns():
+    """examples/asset_pricing/garleanu_panageas.jl at its default grid (100 points): four coupled unknowns ->
+    4 x 4 block-tridiagonal Newton systems, two-pass upwinding, saved interest rate and price of risk."""
+    g, gu, prm = OM.garleanu_panageas_problem()
+    ora = eo.pdesolve(OM.garleanu_panageas(**prm), g, gu)
+    res = E.pdesolve(PM.GarleanuPanageasModel(**prm), g, gu, verbose=False)
+    assert res.converged == ora.converged and res.converged
+    assert [r["status"] for r in res.log] == [r[3] for r in ora.log.rows]
+    assert [r["newton_iters"] for r in res.log] == [r[4] for r in ora.log.rows]
+    for k in ("pA", "pB", "phi1", "phi2"):
+        np.testing.assert_allclose(res.solution[k], ora.solution[k], rtol=1e-8)
+    assert abs(res.residual_norm - ora.residual_norm) <= 1e-10
+    for k in ("r", "kappa"):
+        np.testing.assert_allclose(res.saved[k], ora.saved[k], rtol=1e-7, atol=1e-12)
+    # price of risk = gamma * sigma of whoever holds all the wealth at the ends of the grid
+    np.testing.assert_allclose(res.saved["kappa"][[0, -1]], [prm["gB"] * prm["sigma"], prm["gA"] * prm["sigma"]], rtol=1e-9)
+
+
 def test_di_tella_example_three_unknowns_one_algebraic():
     """examples/asset_pricing/di_tella.jl at its default grid (33 x 33) and guess: three unknowns on a 2-D
     grid, `p` algebraic, upwinded cross derivatives, saved outputs.  The pseudo-transient path has rejected

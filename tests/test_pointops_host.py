@@ -40,6 +40,11 @@ def _cases():
     out.append(("regimes2d", PM.Hjb2dRegimes(**prm), OM.hjb2d_regimes(**prm), g, gu))
     g, gu, prm = OM.di_tella_problem(7, 6)
     out.append(("ditella", PM.DiTellaModel(**prm), OM.di_tella(**prm), g, gu))
+    g, gu, prm = OM.ahlm_two_states_problem(60)
+    out.append(("twoincome", PM.AchdouHanLasryLionsMollModel_TwoStates(**prm), OM.ahlm_two_states(**prm), g, gu))
+    g, gu, prm = OM.garleanu_panageas_problem(40)
+    gu = {k: v * (1.0 + 0.2 * np.linspace(0, 1, 40)) for k, v in gu.items()}
+    out.append(("gp", PM.GarleanuPanageasModel(**prm), OM.garleanu_panageas(**prm), g, gu))
     # three-argument body: the host emulation leaves the time slot at 0
     g, gu, _, prm = OM.tuckman_vila_problem(zn=50)
     tv = OM.tuckman_vila(**prm)
@@ -49,7 +54,7 @@ def _cases():
 
 
 CASES = _cases()
-POW_MODELS = ("ahlm", "growth", "growth_test", "tuckman", "ditella")
+POW_MODELS = ("ahlm", "growth", "growth_test", "tuckman", "ditella", "twoincome")
 
 
 def _perturbed(gu, seed=1):
