@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeconpdes_cuda.so")
 
 MAX_DIMS = 3
+ABI_VERSION = 2   # ECONPDES_ABI_VERSION of include/econpdes_cuda.h these mirrors were written against
 
 OK, E_INVALID, E_NAN_GUESS, E_NO_DEVICE, E_CUDA, E_UNSUPPORTED, E_NCCL = 0, -1, -2, -3, -4, -5, -6
 EXIT_CONVERGED, EXIT_ALREADY_ZERO, EXIT_MAXITERS, EXIT_BELOW_MIN_DELTA, EXIT_INF_STEP_FAILED = range(5)
@@ -131,7 +132,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.econpdes_abi_version() != 2:
+    if lib.econpdes_abi_version() != ABI_VERSION:
         raise ImportError("libeconpdes_cuda ABI version mismatch")
     _lib = lib
     return lib
