@@ -71,11 +71,14 @@ struct BatchedLaunch<M, true> {
   static void launch(const BatchArgs& a, cudaStream_t s) {
     const int T = (((a.S + P - 1) / P + 31) / 32) * 32;
     const size_t smem = batched_smem_bytes(T, P);
-    static bool configured = false;
-    if (!configured) {
+    // per device (the attribute lives in the device's context): set once for every device this process uses
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    EP_CUDA(cudaGetDevice(&dev));
+    if (!((configured.load() >> (dev & 63)) & 1ull)) {
       EP_CUDA(cudaFuncSetAttribute((k_batched_pdesolve_1d<M, P, PER_COL>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(batched_smem_bytes(batched_max_threads(P), P))));
-      configured = true;
+      configured.fetch_or(1ull << (dev & 63));
     }
     EP_LAUNCH((k_batched_pdesolve_1d<M, P, PER_COL>), static_cast<unsigned>(a.nproblems - a.problem0), T, smem, s, a);
   }

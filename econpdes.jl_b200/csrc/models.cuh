@@ -639,6 +639,29 @@ struct GarleanuPanageas : ModelDefaults {
   }
 };
 
+// examples/corporate_finance/leland.jl:44-53   state delta (cash flow), unknown E (equity value);
+// solved with lower_bound = 0 (the default option) and bc = (Eδ = (0, 1/(r - μ)))
+struct Leland : ModelDefaults {
+  static constexpr int N = 1, F = 1, NPARAMS = 5, NSAVED = 0;
+  static constexpr bool USES_CROSS = false;
+  static const char* name() { return "leland"; }
+  struct Pre { double mud, hs2, f, r; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
+    const double r = prm[0], mu = prm[1], sigma = prm[2], C = prm[3], tau = prm[4];
+    const double d = st[0];
+    c.mud = mu * d;
+    const double sd = sigma * d;
+    c.hs2 = sd * sd;
+    c.f = d - (1 - tau) * C;
+    c.r = r;
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<1>* u, double* out, double*) {
+    const double Ed = (c.mud >= 0) ? u[0].up[0] : u[0].dn[0];
+    out[0] = -(c.f + Ed * c.mud + 0.5 * u[0].dd[0] * c.hs2 - c.r * u[0].v);
+  }
+};
+
 // X-macro: the registry order defines the model ids of the C ABI.
 #define ECONPDES_FOR_EACH_MODEL(X) \
   X(ReadmeLinear)                  \
@@ -657,6 +680,7 @@ struct GarleanuPanageas : ModelDefaults {
   X(TuckmanVila)                   \
   X(DiTella)                       \
   X(AhlmTwoStates)                 \
-  X(GarleanuPanageas)
+  X(GarleanuPanageas)              \
+  X(Leland)
 
 }  // namespace econpdes

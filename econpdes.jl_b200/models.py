@@ -208,6 +208,19 @@ class GarleanuPanageasModel(RegisteredModel):
 
 
 @dataclass(frozen=True)
+class LelandModel(RegisteredModel):
+    """examples/corporate_finance/leland.jl:22-28; solve with lower_bound = 0 and bc = {"Edelta": (0, 1/(r-mu))}."""
+    r: float = 0.02
+    mu: float = 0.0
+    sigma: float = 0.1
+    C: float = 0.05
+    tau: float = 0.2
+    name: ClassVar[str] = "leland"
+    statenames: ClassVar = ("delta",)
+    solnames: ClassVar = ("E",)
+
+
+@dataclass(frozen=True)
 class NeoclassicalGrowthModel(RegisteredModel):
     """examples/neoclassical_growth.jl:25-31."""
     A: float = 0.5
@@ -276,4 +289,4 @@ class VMinusTwo(RegisteredModel):
 ALL_MODELS = (ReadmeLinear, CampbellCochraneModel, BansalYaronModel, AchdouHanLasryLionsMollModel_Diffusion,
               Hjb3dSynth, NeoclassicalGrowthModel, GrowthTest, LinearSum1D, LinearSum2D, LinearSum3D,
               ForwardPrice, VMinusTwo, Hjb2dRegimes, TuckmanVilaModel, DiTellaModel,
-              AchdouHanLasryLionsMollModel_TwoStates, GarleanuPanageasModel)
+              AchdouHanLasryLionsMollModel_TwoStates, GarleanuPanageasModel, LelandModel)

@@ -568,6 +568,39 @@ def garleanu_panageas_problem(n=100, **over):
     return {"x": x}, {k: np.ones(n) for k in ("pA", "pB", "phi1", "phi2")}, prm
 
 
+def leland(r=0.02, mu=0.0, sigma=0.1, C=0.05, tau=0.2):
+    """examples/corporate_finance/leland.jl:44-53 (equity value with the default option as a lower bound)."""
+    def pde(state, u):
+        d = state["delta"]
+        mud, sd = mu * d, sigma * d
+        Ed = np.where(mud >= 0, u["Edelta_up"], u["Edelta_down"])
+        f = d - (1 - tau) * C
+        return {"Et": -(f + Ed * mud + 0.5 * u["Edeltadelta"] * sd ** 2 - r * u["E"])}
+    return pde
+
+
+def leland_problem(**over):
+    """Grid, guess, lower bound and boundary derivatives of the example (leland.jl:31-37, 68-78)."""
+    prm = dict(r=0.02, mu=0.0, sigma=0.1, C=0.05, tau=0.2)
+    prm.update(over)
+    d = np.arange(0, 41) * 0.005          # range(0, 0.2, step = 0.005)
+    d = np.array([julia_range(0.0, 0.2, 41)[i] for i in range(41)])
+    guess = np.maximum(d / (prm["r"] - prm["mu"]) - (1 - prm["tau"]) * prm["C"] / prm["r"], 0.0)
+    return {"delta": d}, {"E": guess}, prm, np.zeros(41), {"Edelta": (0.0, 1 / (prm["r"] - prm["mu"]))}
+
+
+def leland_closed_form(d, r, mu, sigma, C, tau):
+    """Closed-form equity value above the default threshold (leland.jl:88-103); returns (E, delta_star)."""
+    a, b, c = 0.5 * sigma ** 2, mu - 0.5 * sigma ** 2, -r
+    beta = min((-b + np.sqrt(b * b - 4 * a * c)) / (2 * a), (-b - np.sqrt(b * b - 4 * a * c)) / (2 * a))
+    dstar = beta / (beta - 1) * (r - mu) * (1 - tau) * C / r
+    slope = 1 / (r - mu)
+    load = -slope * dstar ** (1 - beta) / beta
+    with np.errstate(all="ignore"):
+        E = np.where(d >= dstar, slope * d - (1 - tau) * C / r + load * d ** beta, 0.0)
+    return E, dstar
+
+
 def v_minus_two():
     """test/runtests.jl:227: vt = v - 2."""
     def pde(state, u):

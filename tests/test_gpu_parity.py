@@ -495,6 +495,27 @@ def test_two_income_example_block_tridiagonal():
     assert res.saved["mula"][0] == 0.0          # the low-income household is constrained at the borrowing limit
 
 
+def test_leland_example_default_option_with_closed_form():
+    """examples/corporate_finance/leland.jl: HJB variational inequality (lower_bound = 0 is the default option)
+    with boundary derivatives bc = (Eδ = (0, 1/(r-μ))); against the oracle and against the closed-form equity
+    value above the default threshold (leland.jl:88-103)."""
+    g, gu, prm, lb, bc = OM.leland_problem()
+    ora = eo.pdesolve(OM.leland(**prm), g, gu, lower_bound={"E": lb}, bc=bc)
+    res = E.pdesolve(PM.LelandModel(**prm), g, gu, lower_bound={"E": lb}, bc=bc, verbose=False)
+    assert res.converged == ora.converged and res.converged
+    assert [r["status"] for r in res.log] == [r[3] for r in ora.log.rows]
+    assert [r["newton_iters"] for r in res.log] == [r[4] for r in ora.log.rows]
+    np.testing.assert_allclose(res.solution["E"], ora.solution["E"], rtol=1e-8, atol=1e-12)
+    assert abs(res.residual_norm - ora.residual_norm) <= 1e-10
+    Eq = res.solution["E"]
+    d = g["delta"]
+    closed, dstar = OM.leland_closed_form(d, **prm)
+    lift = d[np.argmax(Eq > 1e-8)]
+    assert (Eq >= 0).all() and abs(lift - dstar) <= 0.01            # default below the threshold, one grid cell
+    cont = d >= lift
+    assert np.abs(Eq[cont] - closed[cont]).max() < 0.02             # discretisation error of the 41-point grid
+
+
 def test_garleanu_panageas_example_four_unknowns():
     """examples/asset_pricing/garleanu_panageas.jl at its default grid (100 points): four coupled unknowns ->
     4 x 4 block-tridiagonal Newton systems, two-pass upwinding, saved interest rate and price of risk."""
