@@ -662,6 +662,52 @@ struct Leland : ModelDefaults {
   }
 };
 
+// examples/consumption_saving/wang_wang_yang.jl:50-95   state w (wealth-income ratio), unknown p
+// saved = (c, muw); solved with bc = (pw = (1, 1))
+struct WangWangYang : ModelDefaults {
+  static constexpr int N = 1, F = 1, NPARAMS = 8, NSAVED = 2;
+  static constexpr bool USES_CROSS = false;
+  static const char* name() { return "wang_wang_yang"; }
+  struct Pre { double mu, sigma, r, rho, gamma, psi, wmin, w, mstar, cmax, drift0, s2; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
+    c.mu = prm[0]; c.sigma = prm[1]; c.r = prm[2]; c.rho = prm[3]; c.gamma = prm[4]; c.psi = prm[5]; c.wmin = prm[6];
+    c.w = st[0];   // prm[7] = wmax only builds the grid
+    c.mstar = c.r + c.psi * (c.rho - c.r);
+    c.s2 = c.sigma * c.sigma;
+    c.drift0 = (c.r - c.mu + c.s2) * c.w;
+    c.cmax = 100.0 * (1 + ep_max(c.drift0, 0.0));
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& m, const Deriv<1>* u, double* out, double* sv) {
+    const double p = u[0].v, pw_up = u[0].up[0], pw_down = u[0].dn[0], pww = u[0].dd[0];
+    const double psi = m.psi, mstar = m.mstar, w = m.w;
+    const double p_for_trial = ep_max(p, 2.220446049250313e-16);
+    const double c_up = pw_up > 0 ? ep_min(mstar * p * pow(pw_up, -psi), m.cmax) : m.cmax;
+    const double muw_up = m.drift0 + 1 - c_up;
+    double pw, c, muw;
+    if (muw_up >= 0) {
+      pw = pw_up > 0 ? pw_up : pow(c_up / (mstar * p_for_trial), -1 / psi);
+      c = c_up;
+      muw = muw_up;
+    } else {
+      const double c_down = pw_down > 0 ? ep_min(mstar * p * pow(pw_down, -psi), m.cmax) : m.cmax;
+      const double muw_down = m.drift0 + 1 - c_down;
+      if (muw_down <= 0 && w > m.wmin) {
+        pw = pw_down > 0 ? pw_down : pow(c_down / (mstar * p_for_trial), -1 / psi);
+        c = c_down;
+        muw = muw_down;
+      } else {
+        muw = 0.0;
+        c = 1 + m.drift0;
+        pw = pow(c / (mstar * p_for_trial), -1 / psi);
+      }
+    }
+    out[0] = -((((m.r + psi * (m.rho - m.r)) * pow(pw, 1 - psi) - psi * m.rho) / (psi - 1) + m.mu - m.gamma * m.s2 / 2) * p +
+               ((m.r - m.mu + m.gamma * m.s2) * w + 1) * pw + m.s2 * (w * w) / 2 * (pww - m.gamma * (pw * pw) / p));
+    if (SAVE) { sv[0] = c; sv[1] = muw; }
+  }
+};
+
 // X-macro: the registry order defines the model ids of the C ABI.
 #define ECONPDES_FOR_EACH_MODEL(X) \
   X(ReadmeLinear)                  \
@@ -681,6 +727,7 @@ struct Leland : ModelDefaults {
   X(DiTella)                       \
   X(AhlmTwoStates)                 \
   X(GarleanuPanageas)              \
-  X(Leland)
+  X(Leland)                        \
+  X(WangWangYang)
 
 }  // namespace econpdes

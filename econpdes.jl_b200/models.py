@@ -221,6 +221,23 @@ class LelandModel(RegisteredModel):
 
 
 @dataclass(frozen=True)
+class WangWangYangModel(RegisteredModel):
+    """examples/consumption_saving/wang_wang_yang.jl:21-30; solve with bc = {"pw": (1.0, 1.0)}."""
+    mu: float = 0.015
+    sigma: float = 0.1
+    r: float = 0.035
+    rho: float = 0.04
+    gamma: float = 3.0
+    psi: float = 1.1
+    wmin: float = 0.0
+    wmax: float = 1000.0
+    name: ClassVar[str] = "wang_wang_yang"
+    statenames: ClassVar = ("w",)
+    solnames: ClassVar = ("p",)
+    savednames: ClassVar = ("c", "muw")
+
+
+@dataclass(frozen=True)
 class NeoclassicalGrowthModel(RegisteredModel):
     """examples/neoclassical_growth.jl:25-31."""
     A: float = 0.5
@@ -289,4 +306,5 @@ class VMinusTwo(RegisteredModel):
 ALL_MODELS = (ReadmeLinear, CampbellCochraneModel, BansalYaronModel, AchdouHanLasryLionsMollModel_Diffusion,
               Hjb3dSynth, NeoclassicalGrowthModel, GrowthTest, LinearSum1D, LinearSum2D, LinearSum3D,
               ForwardPrice, VMinusTwo, Hjb2dRegimes, TuckmanVilaModel, DiTellaModel,
-              AchdouHanLasryLionsMollModel_TwoStates, GarleanuPanageasModel, LelandModel)
+              AchdouHanLasryLionsMollModel_TwoStates, GarleanuPanageasModel, LelandModel,
+              WangWangYangModel)

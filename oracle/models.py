@@ -601,6 +601,44 @@ def leland_closed_form(d, r, mu, sigma, C, tau):
     return E, dstar
 
 
+def wang_wang_yang(mu=0.015, sigma=0.1, r=0.035, rho=0.04, gamma=3.0, psi=1.1, wmin=0.0, wmax=1000.0):
+    """examples/consumption_saving/wang_wang_yang.jl:50-95 (unknown p on the wealth-income ratio w)."""
+    eps = np.finfo(float).eps
+
+    def pde(state, u):
+        w = state["w"]
+        p, pw_up, pw_down, pww = u["p"], u["pw_up"], u["pw_down"], u["pww"]
+        mstar = r + psi * (rho - r)
+        with np.errstate(all="ignore"):
+            p_trial = np.maximum(p, eps)
+            cmax = 100.0 * (1 + np.maximum((r - mu + sigma ** 2) * w, 0.0))
+            c_up = np.where(pw_up > 0, np.minimum(mstar * p * np.abs(pw_up) ** (-psi), cmax), cmax)
+            muw_up = (r - mu + sigma ** 2) * w + 1 - c_up
+            c_down = np.where(pw_down > 0, np.minimum(mstar * p * np.abs(pw_down) ** (-psi), cmax), cmax)
+            muw_down = (r - mu + sigma ** 2) * w + 1 - c_down
+            use_up = muw_up >= 0
+            use_down = (~use_up) & (muw_down <= 0) & (w > wmin)
+            pw_a = np.where(pw_up > 0, pw_up, (c_up / (mstar * p_trial)) ** (-1 / psi))
+            pw_b = np.where(pw_down > 0, pw_down, (c_down / (mstar * p_trial)) ** (-1 / psi))
+            c3 = 1 + (r - mu + sigma ** 2) * w
+            pw_c = (c3 / (mstar * p_trial)) ** (-1 / psi)
+            pw = np.where(use_up, pw_a, np.where(use_down, pw_b, pw_c))
+            c = np.where(use_up, c_up, np.where(use_down, c_down, c3))
+            muw = np.where(use_up, muw_up, np.where(use_down, muw_down, 0.0))
+            pt = -((((r + psi * (rho - r)) * pw ** (1 - psi) - psi * rho) / (psi - 1) + mu - gamma * sigma ** 2 / 2) * p
+                   + ((r - mu + gamma * sigma ** 2) * w + 1) * pw + sigma ** 2 * w ** 2 / 2 * (pww - gamma * pw ** 2 / p))
+        return {"pt": pt}, {"c": c, "muw": muw}
+    return pde
+
+
+def wang_wang_yang_problem(n=1001, **over):
+    """Grid, guess and boundary derivatives of the example (wang_wang_yang.jl:33-41, 100)."""
+    prm = dict(mu=0.015, sigma=0.1, r=0.035, rho=0.04, gamma=3.0, psi=1.1, wmin=0.0, wmax=1000.0)
+    prm.update(over)
+    w = julia_range(prm["wmin"], prm["wmax"], n)
+    return {"w": w}, {"p": 1 + w}, prm, {"pw": (1.0, 1.0)}
+
+
 def v_minus_two():
     """test/runtests.jl:227: vt = v - 2."""
     def pde(state, u):

@@ -516,6 +516,22 @@ def test_leland_example_default_option_with_closed_form():
     assert np.abs(Eq[cont] - closed[cont]).max() < 0.02             # discretisation error of the 41-point grid
 
 
+def test_wang_wang_yang_example_boundary_derivatives():
+    """examples/consumption_saving/wang_wang_yang.jl at its default grid (1001 points): non-zero boundary
+    derivatives bc = (pw = (1, 1)), fractional powers, saved consumption and drift."""
+    g, gu, prm, bc = OM.wang_wang_yang_problem()
+    ora = eo.pdesolve(OM.wang_wang_yang(**prm), g, gu, bc=bc)
+    res = E.pdesolve(PM.WangWangYangModel(**prm), g, gu, bc=bc, verbose=False)
+    assert res.converged == ora.converged and res.converged
+    assert [r["status"] for r in res.log] == [r[3] for r in ora.log.rows]
+    assert [r["newton_iters"] for r in res.log] == [r[4] for r in ora.log.rows]
+    np.testing.assert_allclose(res.solution["p"], ora.solution["p"], rtol=1e-8)
+    assert abs(res.residual_norm - ora.residual_norm) <= 1e-10
+    for k in ("c", "muw"):
+        np.testing.assert_allclose(res.saved[k], ora.saved[k], rtol=1e-7, atol=1e-9)
+    assert res.solution["p"][0] < 1 / (prm["r"] - prm["mu"])       # below the complete-markets value at the constraint
+
+
 def test_garleanu_panageas_example_four_unknowns():
     """examples/asset_pricing/garleanu_panageas.jl at its default grid (100 points): four coupled unknowns ->
     4 x 4 block-tridiagonal Newton systems, two-pass upwinding, saved interest rate and price of risk."""

@@ -45,6 +45,8 @@ def _cases():
     g, gu, prm = OM.garleanu_panageas_problem(40)
     gu = {k: v * (1.0 + 0.2 * np.linspace(0, 1, 40)) for k, v in gu.items()}
     out.append(("gp", PM.GarleanuPanageasModel(**prm), OM.garleanu_panageas(**prm), g, gu))
+    g, gu, prm, _ = OM.wang_wang_yang_problem(80)
+    out.append(("wwy", PM.WangWangYangModel(**prm), OM.wang_wang_yang(**prm), g, gu))
     # three-argument body: the host emulation leaves the time slot at 0
     g, gu, _, prm = OM.tuckman_vila_problem(zn=50)
     tv = OM.tuckman_vila(**prm)
@@ -54,7 +56,7 @@ def _cases():
 
 
 CASES = _cases()
-POW_MODELS = ("ahlm", "growth", "growth_test", "tuckman", "ditella", "twoincome")
+POW_MODELS = ("ahlm", "growth", "growth_test", "tuckman", "ditella", "twoincome", "wwy")
 
 
 def _perturbed(gu, seed=1):
