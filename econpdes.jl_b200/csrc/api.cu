@@ -647,6 +647,17 @@ int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, con
     const size_t nB = static_cast<size_t>(B);
     b->log_capacity = 0;
     int* err = b->err_host;
+    // if queuing fails half-way, copies into the caller's buffers may still be in flight: drain the
+    // streams before the error leaves this call
+    struct Drain {
+      econpdes_batch* b;
+      bool armed = true;
+      ~Drain() {
+        if (armed)
+          for (cudaStream_t p : b->pipe)
+            if (p) cudaStreamSynchronize(p);
+      }
+    } drain{b};
     for (size_t c = 0; c + 1 < bounds.size(); ++c) {
       const long long first = bounds[c], last = bounds[c + 1];
       const size_t n = static_cast<size_t>(last - first), o = static_cast<size_t>(first);
@@ -669,6 +680,7 @@ int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, con
         EP_CUDA(cudaMemcpyAsync(err + 3 * nB + o, b->n_newton.p + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     }
     for (cudaStream_t p : b->pipe) EP_CUDA(cudaStreamSynchronize(p));
+    drain.armed = false;
     if (residual_norm) std::memcpy(residual_norm, b->rn_host, nB * sizeof(double));
     if (exit_reason) std::memcpy(exit_reason, err + nB, nB * sizeof(int32_t));
     if (n_outer) std::memcpy(n_outer, err + 2 * nB, nB * sizeof(int32_t));
