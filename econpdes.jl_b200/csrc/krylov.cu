@@ -282,8 +282,91 @@ __global__ void __launch_bounds__(1024) k_line_zebra(LevelGeom<N> g, const mgrea
 //      warp shuffles (5 steps, no barrier);
 //   4. interior unknowns follow by substitution; the line is written back coalesced.
 // ~10 shared-memory operations per point instead of ~80 and no __syncthreads.
+
 template <int PPT>
 __device__ __forceinline__ int line_pos(int i) { return PPT > 1 ? i + i / PPT : i; }   // padded: conflict-free strided reads
+
+// ---- zebra line smoother, long lines of star-stencil (2-D) levels: P consecutive rows per thread ----
+// One block per line like k_line_zebra, but the block-wide PCR (log2(n) steps over n rows, ~300
+// instructions per point at n = 2048, which is what bounds the 5-plane 2-D sweeps) is replaced by the
+// chunked Schur complement of the batched engine (tridiag.cuh, block_chunk_solve): each thread assembles
+// its P consecutive rows straight from global memory (P consecutive doubles per plane: whole sectors),
+// eliminates the chunk interior in registers, PCR runs on one interface row per thread, and the thread
+// writes its P unknowns back.  Shared memory holds only the PCR scratch.
+template <int N, bool BOX, int P>
+__global__ void __launch_bounds__(1024) k_line_zebra_chunk(LevelGeom<N> g, const mgreal_t<N>* __restrict__ A,
+                                                           const double* __restrict__ b, double* __restrict__ x,
+                                                           int color) {
+  using St = Stencil<N, BOX>;
+  extern __shared__ double sh[];
+  const int n = static_cast<int>(g.S[0]);
+  const int T = blockDim.x, t = threadIdx.x;
+  double* pcr = sh;                      // [8 T]
+  double* xch = pcr + 8 * T;             // [4 T]
+  long long other[N > 1 ? N - 1 : 1];
+  {
+    long long q = blockIdx.x;
+#pragma unroll
+    for (int e = 1; e < N; ++e) {
+      const int ce = (color >> (e - 1)) & 1;
+      const long long cnt = (g.S[e] - ce + 1) / 2;
+      other[e - 1] = ce + 2 * (q % cnt);
+      q /= cnt;
+    }
+  }
+  long long base = 0;
+#pragma unroll
+  for (int e = 1; e < N; ++e) base += other[e - 1] * g.stride[e];
+  int kc = -1, km = -1, kp = -1;
+#pragma unroll
+  for (int k = 0; k < St::NK; ++k) {
+    bool inl = true;
+#pragma unroll
+    for (int e = 1; e < N; ++e)
+      if (St::off(k, e) != 0) inl = false;
+    if (inl) {
+      if (St::off(k, 0) == 0) kc = k;
+      if (St::off(k, 0) < 0) km = k;
+      if (St::off(k, 0) > 0) kp = k;
+    }
+  }
+  double a[P], bb[P], c[P], d[P], xs[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int i = P * t + j;
+    a[j] = 0.0; bb[j] = 1.0; c[j] = 0.0; d[j] = 0.0;
+    if (i < n) {
+      const long long pt = base + i;
+      double rhs = b[pt];
+#pragma unroll
+      for (int k = 0; k < St::NK; ++k) {
+        bool inl = true, ok = true;
+        long long q = pt;
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          const int o = St::off(k, e);
+          if (e > 0 && o != 0) inl = false;
+          const long long ie = e == 0 ? i : other[e - 1];
+          const bool lo_edge = ie == 0 && !(e == N - 1 && g.open_lo);
+          const bool hi_edge = ie == g.S[e] - 1 && !(e == N - 1 && g.open_hi);
+          if ((o < 0 && lo_edge) || (o > 0 && hi_edge)) ok = false;
+          q += o * g.stride[e];
+        }
+        if (!inl) rhs -= A[k * g.l + pt] * x[ok ? q : pt];   // zero coefficient outside the grid
+      }
+      a[j] = i > 0 ? A[km * g.l + pt] : 0.0;
+      bb[j] = A[kc * g.l + pt];
+      c[j] = i < n - 1 ? A[kp * g.l + pt] : 0.0;
+      d[j] = rhs;
+    }
+  }
+  block_chunk_solve<P>(a, bb, c, d, t, (n + P - 1) / P, pcr, xch, xs);
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int i = P * t + j;
+    if (i < n) x[base + i] = xs[j];
+  }
+}
 
 template <int N, bool BOX, int PPT>
 __global__ void __launch_bounds__(256) k_line_zebra_warp(LevelGeom<N> g, const mgreal_t<N>* __restrict__ A,
@@ -1497,7 +1580,21 @@ class KrylovSolver final : public LinearSolver {
         const int ce = (color >> (e - 1)) & 1;
         nlines *= (Sd[e] - ce + 1) / 2;
       }
-      if (nlines > 0 && n <= warp_lines_max_) {
+      // opt-in (ECONPDES_CHUNK_LINES=1) until it is measured faster than the block-wide PCR on this hardware
+      static const bool chunk_lines = [] { const char* e = std::getenv("ECONPDES_CHUNK_LINES"); return e && e[0] == '1'; }();
+      if (nlines > 0 && chunk_lines && N == 2 && n >= 256 && n <= 4096) {   // 4096 = 1024 threads x 4 rows
+        // long lines of the 5-plane 2-D levels: four consecutive rows per thread, chunked solve
+        constexpr int P = 4;
+        const int Tc = (((n + P - 1) / P + 31) / 32) * 32;
+        const size_t csmem = 12 * static_cast<size_t>(Tc) * sizeof(double);
+        static bool cfg = false;
+        if (!cfg) {
+          EP_CUDA(cudaFuncSetAttribute(k_line_zebra_chunk<N, BOX, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       200 * 1024));
+          cfg = true;
+        }
+        EP_LAUNCH((k_line_zebra_chunk<N, BOX, P>), static_cast<unsigned>(nlines), Tc, csmem, c_.stream, g, A, b, x, color);
+      } else if (nlines > 0 && n <= warp_lines_max_) {
         // one warp per line, 8 lines per block
         const int ppt = n <= 32 ? 1 : (n <= 64 ? 2 : (n <= 128 ? 4 : 8));
         const unsigned blocks = static_cast<unsigned>((nlines + 7) / 8);
