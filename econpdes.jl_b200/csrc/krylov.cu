@@ -1583,7 +1583,11 @@ class KrylovSolver final : public LinearSolver {
       // measured on B200: V-cycle at 2048^2 1.46 -> 1.19 ms, C2 (64 x 4096) solve -19 %; ECONPDES_CHUNK_LINES=0
       // restores the block-wide PCR
       static const bool chunk_lines = [] { const char* e = std::getenv("ECONPDES_CHUNK_LINES"); return !(e && e[0] == '0'); }();
-      if (nlines > 0 && chunk_lines && N == 2 && n >= 256 && n <= 4096) {   // 4096 = 1024 threads x 4 rows
+      // 3-D (27 FP32 planes, bandwidth-bound): fewer instructions and barriers still buy 8 % (V-cycle at 256^3
+      // 9.2 -> 8.5 ms); ECONPDES_CHUNK_LINES_3D=0 restores the block-wide PCR
+      static const bool chunk_lines_3d = [] { const char* e = std::getenv("ECONPDES_CHUNK_LINES_3D"); return !(e && e[0] == '0'); }();
+      if (nlines > 0 && n <= 4096 &&   // 4096 = 1024 threads x 4 rows
+          ((chunk_lines && N == 2 && n >= 256) || (chunk_lines_3d && N == 3 && n >= 128))) {
         // long lines of the 5-plane 2-D levels: four consecutive rows per thread, chunked solve
         constexpr int P = 4;
         const int Tc = (((n + P - 1) / P + 31) / 32) * 32;
