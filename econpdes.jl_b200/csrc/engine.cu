@@ -489,7 +489,7 @@ static __global__ void __launch_bounds__(kBlock) k_jacobian_diagnostics(long lon
                                                                   const double* __restrict__ planes, double delta,
                                                                   const double* __restrict__ delta_rel,
                                                                   const unsigned char* __restrict__ is_alg, double tol,
-                                                                  int stencils, int* __restrict__ counts,
+                                                                  int signs, int stencils, int* __restrict__ counts,
                                                                   unsigned long long* __restrict__ maxbits) {
   const long long pt = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (pt >= l) return;
@@ -497,7 +497,7 @@ static __global__ void __launch_bounds__(kBlock) k_jacobian_diagnostics(long lon
     const long long row = k * l + pt;
     const bool alg = is_alg != nullptr && is_alg[row] != 0;
     const double di = delta_rel != nullptr ? delta * delta_rel[row] : delta;
-    if (!alg && isfinite(di)) {
+    if (signs && !alg && isfinite(di)) {
       const double d = planes[(static_cast<long long>(kcenter * F + k) * F + k) * l + pt] - 1 / di;
       if (fabs(d) > tol) {
         atomicAdd(&counts[k], 1);
@@ -520,9 +520,16 @@ static __global__ void __launch_bounds__(kBlock) k_jacobian_diagnostics(long lon
 
 void Solver::jacobian_diagnostics(double delta, const econpdes_options& opt) {
   Ctx& c = *c_;
-  // checked once, on the first assembled Jacobian; a one-shot solve (infinite Δ) is sign-agnostic (:70-71)
-  if (sign_checked_ || !std::isfinite(delta) || c.dist != nullptr) return;
-  sign_checked_ = true;
+  // Sign convention: checked once, on the first Jacobian assembled with a finite step -- a one-shot solve
+  // (infinite Δ) is sign-agnostic and leaves the check pending (:70-72).  Stencil monotonicity (opt-in): on
+  // the first assembled Jacobian whatever the step (the reference repeats it on later Jacobians until
+  // `monotonicity_max_warnings` distinct entries were reported; the device reports the first one's count).
+  if (c.dist != nullptr) return;
+  const bool do_sign = !sign_checked_ && std::isfinite(delta);
+  const bool do_stencils = opt.check_monotonicity != 0 && !stencils_checked_;
+  if (!do_sign && !do_stencils) return;
+  if (do_sign) sign_checked_ = true;
+  if (do_stencils) stencils_checked_ = true;
   DevBuf<int> counts;
   DevBuf<unsigned long long> mx;
   counts.alloc(static_cast<size_t>(2 * c.F + 1));
@@ -532,23 +539,26 @@ void Solver::jacobian_diagnostics(double delta, const econpdes_options& opt) {
   const double* drel = (c.has_delta_vec && !c.all_delta_inf) ? c.delta_rel.p : nullptr;
   const int kcenter = c.box ? (ipow3(c.N) - 1) / 2 : 0;
   EP_LAUNCH(k_jacobian_diagnostics, blocks_for(c.l), kBlock, 0, c.stream, c.l, c.F, c.nk, kcenter, planes_.p, delta, drel,
-            c.is_alg.p, opt.monotonicity_tol, opt.check_monotonicity, counts.p, mx.p);
+            c.is_alg.p, opt.monotonicity_tol, do_sign ? 1 : 0, do_stencils ? 1 : 0, counts.p, mx.p);
   std::vector<int> h(static_cast<size_t>(2 * c.F + 1));
   unsigned long long hm = 0;
   counts.download(h.data(), h.size(), c.stream);
   mx.download(&hm, 1, c.stream);
   EP_CUDA(cudaStreamSynchronize(c.stream));
-  int flagged = 0, total_checked = 0;
-  for (int k = 0; k < c.F; ++k) {
-    total_checked += h[k];
-    if (h[k] > 0 && h[c.F + k] == h[k]) { sign_flags_ |= 1 << k; ++flagged; }
+  if (do_sign) {
+    int total_checked = 0;
+    for (int k = 0; k < c.F; ++k) {
+      total_checked += h[k];
+      if (h[k] > 0 && h[c.F + k] == h[k]) sign_flags_ |= 1 << k;
+    }
+    bool all_wrong = total_checked > 0;
+    for (int k = 0; k < c.F; ++k) all_wrong = all_wrong && h[c.F + k] == h[k];
+    if (drel == nullptr && delta > 0 && all_wrong) sign_flags_ |= ECONPDES_SIGN_WHOLE_SYSTEM;
   }
-  bool all_wrong = total_checked > 0;
-  for (int k = 0; k < c.F; ++k) all_wrong = all_wrong && h[c.F + k] == h[k];
-  if (drel == nullptr && delta > 0 && all_wrong) sign_flags_ |= ECONPDES_SIGN_WHOLE_SYSTEM;
-  (void)flagged;
-  nonmonotone_entries_ = h[2 * c.F];
-  std::memcpy(&nonmonotone_max_, &hm, sizeof(double));
+  if (do_stencils) {
+    nonmonotone_entries_ = h[2 * c.F];
+    std::memcpy(&nonmonotone_max_, &hm, sizeof(double));
+  }
 }
 
 // NLsolve newton_ with the Static line search, wrapped like _newtonstep (:125-147).

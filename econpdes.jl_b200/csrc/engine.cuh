@@ -181,7 +181,7 @@ class Solver {
   // src/monotonicity.jl diagnostics of the first assembled Jacobian (see econpdes_result)
   int sign_flags_ = 0, nonmonotone_entries_ = 0;
   double nonmonotone_max_ = 0.0;
-  bool sign_checked_ = false;
+  bool sign_checked_ = false, stencils_checked_ = false;
 
  private:
   RowSpec row_spec(const double* ypost, double delta) const;

@@ -708,6 +708,22 @@ struct WangWangYang : ModelDefaults {
   }
 };
 
+// test/runtests.jl:326-372 (monotonicity and sign-convention diagnostics): Vt = s (1 + a V + Vx), with the
+// first derivative taken forward (dir >= 0) or backward (dir < 0).  wrong_upwind = (-1, +1, down),
+// correct_upwind = (-1, +1, up), flipped_sign = (+1, -1, up), correct_sign = (-1, -1, up).
+struct LinearUpwindTest : ModelDefaults {
+  static constexpr int N = 1, F = 1, NPARAMS = 3, NSAVED = 0;
+  static constexpr bool USES_CROSS = false;
+  static const char* name() { return "linear_upwind_test"; }
+  struct Pre { double s, a, dir; };
+  EP_HD static void prepare(const double* prm, const double*, Pre& c) { c.s = prm[0]; c.a = prm[1]; c.dir = prm[2]; }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<1>* u, double* out, double*) {
+    const double vx = c.dir >= 0 ? u[0].up[0] : u[0].dn[0];
+    out[0] = c.s * (1.0 + c.a * u[0].v + vx);
+  }
+};
+
 // X-macro: the registry order defines the model ids of the C ABI.
 #define ECONPDES_FOR_EACH_MODEL(X) \
   X(ReadmeLinear)                  \
@@ -728,6 +744,7 @@ struct WangWangYang : ModelDefaults {
   X(AhlmTwoStates)                 \
   X(GarleanuPanageas)              \
   X(Leland)                        \
-  X(WangWangYang)
+  X(WangWangYang)                  \
+  X(LinearUpwindTest)
 
 }  // namespace econpdes

@@ -238,6 +238,17 @@ class WangWangYangModel(RegisteredModel):
 
 
 @dataclass(frozen=True)
+class LinearUpwindTest(RegisteredModel):
+    """test/runtests.jl:326-372: Vt = s (1 + a V + Vx), Vx forward (dir >= 0) or backward (dir < 0)."""
+    s: float = -1.0
+    a: float = 1.0
+    dir: float = 1.0
+    name: ClassVar[str] = "linear_upwind_test"
+    statenames: ClassVar = ("x",)
+    solnames: ClassVar = ("V",)
+
+
+@dataclass(frozen=True)
 class NeoclassicalGrowthModel(RegisteredModel):
     """examples/neoclassical_growth.jl:25-31."""
     A: float = 0.5
@@ -307,4 +318,4 @@ ALL_MODELS = (ReadmeLinear, CampbellCochraneModel, BansalYaronModel, AchdouHanLa
               Hjb3dSynth, NeoclassicalGrowthModel, GrowthTest, LinearSum1D, LinearSum2D, LinearSum3D,
               ForwardPrice, VMinusTwo, Hjb2dRegimes, TuckmanVilaModel, DiTellaModel,
               AchdouHanLasryLionsMollModel_TwoStates, GarleanuPanageasModel, LelandModel,
-              WangWangYangModel)
+              WangWangYangModel, LinearUpwindTest)

@@ -229,9 +229,9 @@ def _diagnostic_warnings(res: EconPDEResult, ynames) -> list:
                            "it forward like a tâtonnement price update and needs a negative one — or flip the sign of "
                            "the returned time derivative.")
     if res.nonmonotone_entries > 0:
-        out.append(f"The residual Jacobian has {res.nonmonotone_entries} same-variable spatial off-diagonal entries "
-                   f"with the wrong monotonicity sign (largest {res.nonmonotone_max:.3g}): the finite-difference "
-                   "scheme is not monotone there.")
+        out.append("Non-monotone finite-difference stencil detected: positive residual off-diagonal implies a "
+                   f"negative generator weight ({res.nonmonotone_entries} same-variable spatial entries of the first "
+                   f"Jacobian above the tolerance, largest {res.nonmonotone_max:.3g})")
     return out
 
 

@@ -639,6 +639,14 @@ def wang_wang_yang_problem(n=1001, **over):
     return {"w": w}, {"p": 1 + w}, prm, {"pw": (1.0, 1.0)}
 
 
+def linear_upwind_test(s=-1.0, a=1.0, dir=1.0):
+    """test/runtests.jl:326-372: Vt = s (1 + a V + Vx) with a forward (dir >= 0) or backward first difference."""
+    def pde(state, u):
+        vx = u["Vx_up"] if dir >= 0 else u["Vx_down"]
+        return {"Vt": s * (1.0 + a * u["V"] + vx) + 0.0 * state["x"]}
+    return pde
+
+
 def v_minus_two():
     """test/runtests.jl:227: vt = v - 2."""
     def pde(state, u):

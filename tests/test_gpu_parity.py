@@ -722,12 +722,38 @@ def test_jacobian_diagnostics_match_the_reference_checks():
     h.close()
     nchk, nwrong, cnt, mx = eo.jacobian_diagnostics(_csc(nz, S, 2), 1.0, None, S, 2)
     assert cnt > 0 and not nwrong.any()
-    with pytest.warns(UserWarning, match="wrong monotonicity sign"):
+    with pytest.warns(UserWarning, match="Non-monotone finite-difference stencil"):
         res = E.pdesolve(PM.Hjb2dRegimes(**prm), g, gu, verbose=False, check_monotonicity=True)
     assert res.sign_flags == 0
     assert res.nonmonotone_entries == cnt and res.nonmonotone_max == mx
     res = E.pdesolve(PM.Hjb2dRegimes(**prm), g, gu, verbose=False)     # opt-in: silent by default
     assert res.nonmonotone_entries == 0
+
+
+def test_reference_diagnostic_testsets():
+    """test/runtests.jl:322-372 ("Monotonicity diagnostics", "Sign-convention diagnostic"), same grids, guesses
+    and options: which solves warn and which stay silent."""
+    import warnings as W
+    R = OM.julia_range
+    # wrong upwind direction on a 2-point grid, one-shot solve: the stencil warning (opt-in) fires even with Δ = Inf
+    with pytest.warns(UserWarning, match="Non-monotone finite-difference stencil"):
+        E.pdesolve(PM.LinearUpwindTest(-1.0, 1.0, -1.0), {"x": R(0.0, 1.0, 2)}, {"V": R(1.0, 2.0, 2)}, Δ=INF, maxiters=1,
+                   verbose=False, check_monotonicity=True)
+    # correct upwind direction: nothing at warning level
+    with W.catch_warnings():
+        W.simplefilter("error")
+        E.pdesolve(PM.LinearUpwindTest(-1.0, 1.0, 1.0), {"x": R(0.0, 1.0, 3)}, {"V": R(1.0, 2.0, 3)}, Δ=INF, maxiters=1,
+                   verbose=False, check_monotonicity=True)
+    # flipped sign of the returned time derivative: the whole-system diagnosis (plus the non-convergence warning)
+    with pytest.warns(UserWarning) as rec:
+        E.pdesolve(PM.LinearUpwindTest(1.0, -1.0, 1.0), {"x": R(0.0, 1.0, 5)}, {"V": R(1.0, 2.0, 5)}, Δ=0.5, maxiters=1,
+                   verbose=False)
+    assert any("negative diagonal at every grid point" in str(w.message) for w in rec)
+    # the correct convention triggers no warning under the default (finite Δ) solve
+    with W.catch_warnings():
+        W.simplefilter("error")
+        res = E.pdesolve(PM.LinearUpwindTest(-1.0, -1.0, 1.0), {"x": R(0.0, 1.0, 5)}, {"V": R(1.0, 2.0, 5)}, verbose=False)
+    assert res.converged and res.sign_flags == 0
 
 
 def test_time_dependent_model_with_time_argument():

@@ -276,3 +276,40 @@ def test_time_dependent_solve_reproduces_reference_test():
     # going far enough back in time the value approaches the stationary solution
     stat = eo2.pdesolve(OM2.growth_test_hjb(), g, gu)
     assert np.abs(res.solution["v"][:, 0] - stat.solution["v"]).max() < 0.05 * np.abs(stat.solution["v"]).max()
+
+
+def _first_jacobian(pde, grid, guess, delta):
+    """CSC Jacobian of the first implicit step at the guess (what the reference's checker receives)."""
+    import scipy.sparse as sp
+    names, sol = tuple(grid), tuple(guess)
+    grids = [np.asarray(g, dtype=float) for g in grid.values()]
+    S = tuple(len(g) for g in grids)
+    prob = eo.Problem(pde, names, grids, sol)
+    cache = eo.JacobianCache(S, len(sol))
+    y = np.stack([np.asarray(guess[k], dtype=float) for k in sol], axis=-1).reshape(-1, order="F")
+
+    def R(v):
+        return prob.G(v) - (y - v) / delta
+    nz, _ = eo.finite_difference_jacobian(R, y, cache)
+    n = y.shape[0]
+    return sp.csc_matrix((nz, cache.rowval - 1, cache.colptr - 1), shape=(n, n)), S
+
+
+def test_diagnostics_reproduce_the_reference_testsets():
+    """test/runtests.jl:322-372: the restated checks (oracle.jacobian_diagnostics) flag exactly the cases the
+    reference's "Monotonicity diagnostics" and "Sign-convention diagnostic" testsets expect."""
+    R = M.julia_range
+    # wrong upwind direction, 2-point grid, one-shot solve -> a non-monotone entry
+    J, S = _first_jacobian(M.linear_upwind_test(-1.0, 1.0, -1.0), {"x": R(0.0, 1.0, 2)}, {"V": R(1.0, 2.0, 2)}, math.inf)
+    assert eo.jacobian_diagnostics(J, math.inf, None, S, 1)[2] > 0
+    # correct upwind direction -> none
+    J, S = _first_jacobian(M.linear_upwind_test(-1.0, 1.0, 1.0), {"x": R(0.0, 1.0, 3)}, {"V": R(1.0, 2.0, 3)}, math.inf)
+    assert eo.jacobian_diagnostics(J, math.inf, None, S, 1)[2] == 0
+    # flipped sign of the time derivative, Δ = 0.5 -> negative residual diagonal at every grid point
+    J, S = _first_jacobian(M.linear_upwind_test(1.0, -1.0, 1.0), {"x": R(0.0, 1.0, 5)}, {"V": R(1.0, 2.0, 5)}, 0.5)
+    nchk, nwrong, _, _ = eo.jacobian_diagnostics(J, 0.5, None, S, 1)
+    assert nchk[0] == 5 and nwrong[0] == 5
+    # correct convention, default Δ -> nothing
+    J, S = _first_jacobian(M.linear_upwind_test(-1.0, -1.0, 1.0), {"x": R(0.0, 1.0, 5)}, {"V": R(1.0, 2.0, 5)}, 1.0)
+    nchk, nwrong, cnt, _ = eo.jacobian_diagnostics(J, 1.0, None, S, 1)
+    assert nchk[0] == 5 and nwrong[0] == 0 and cnt == 0
