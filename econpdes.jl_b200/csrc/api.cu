@@ -421,6 +421,8 @@ int econpdes_batch_create(int model_id, int64_t nproblems, int64_t npoints, econ
     if (!ops) throw std::invalid_argument("unknown model id");
     if (ops->N() != 1 || ops->F() != 1)
       throw std::invalid_argument("the batched engine takes 1-D single-unknown models");
+    if (ops->time_slot() >= 0)
+      throw std::invalid_argument("the batched engine solves stationary problems: the PDE function takes a time argument");
     if (nproblems < 1 || npoints < 2) throw std::invalid_argument("need >= 1 problem of >= 2 points");
     if (npoints > 1024) throw std::runtime_error("batched engine: at most 1024 points per problem");
     if (!out) throw std::invalid_argument("null batch pointer");

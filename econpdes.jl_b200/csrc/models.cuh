@@ -724,6 +724,59 @@ struct LinearUpwindTest : ModelDefaults {
   }
 };
 
+// examples/asset_pricing/he_krishnamurthy.jl:45-92   state x (specialists' wealth share), unknown pS
+// saved = (pS, p, r, kappa, sigmap, muR, sigmaR, alphaI, mux, sigmax, x, px, pxx, sigmaI)
+struct HeKrishnamurthy : ModelDefaults {
+  static constexpr int N = 1, F = 1, NPARAMS = 7, NSAVED = 14;
+  static constexpr bool USES_CROSS = false;
+  static const char* name() { return "he_krishnamurthy"; }
+  struct Pre { double m, lam, g, sigma, rho, gamma, l, x; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
+    c.m = prm[0]; c.lam = prm[1]; c.g = prm[2]; c.sigma = prm[3]; c.rho = prm[4]; c.gamma = prm[5]; c.l = prm[6];
+    c.x = st[0];
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<1>* u, double* out, double* sv) {
+    const double m = c.m, lam = c.lam, g = c.g, sigma = c.sigma, rho = c.rho, gamma = c.gamma, l = c.l, x = c.x;
+    const double pS = u[0].v, pSxx = u[0].dd[0];
+    double pSx = u[0].up[0];
+    double p, px, pxx, aI, sigx, spS, sp, sR, kappa, mux;
+    for (int pass = 0;; ++pass) {   // `@goto start`
+      const double den = x / pS + (1 - x) * rho;
+      const double t = 1 / pS - rho - x / (pS * pS) * pSx;
+      p = (1 + l) / den;
+      px = -(1 + l) / (den * den) * t;
+      pxx = -(1 + l) / (den * den) *
+                (-1 / (pS * pS) * pSx - 1 / (pS * pS) * pSx - x / (pS * pS) * pSxx + 2 * x / (pS * pS * pS) * (pSx * pSx)) +
+            2 * (1 + l) / (den * den * den) * (t * t);
+      aI = 1 / (1 - lam * (1 - x));
+      if (x * (1 + m) * aI < 1) aI = 1 / (x * (1 + m));
+      sigx = x * (aI - 1) * sigma / (1 - x * (aI - 1) * px / p);
+      spS = pSx / pS * sigx;
+      sp = px / p * sigx;
+      sR = sigma + sp;
+      kappa = gamma * (aI * sR - spS);
+      mux = x * (1 - x) * ((aI - (1 - aI * x) / (1 - x)) * kappa * sR - 1 / pS + rho - (aI - (1 - aI * x) / (1 - x)) * (sR * sR) -
+                           l / ((1 - x) * p));
+      if (pass == 0 && mux < 0) {
+        pSx = u[0].dn[0];
+        continue;
+      }
+      break;
+    }
+    const double mupS = pSx / pS * mux + 0.5 * pSxx / pS * (sigx * sigx);
+    const double mup = px / p * mux + 0.5 * pxx / p * (sigx * sigx);
+    const double r = 1 / p + g + mup + sigma * sp - kappa * sR;
+    const double sCS = kappa / gamma;
+    const double muCS = (r - rho) / gamma + (1 + 1 / gamma) / (2 * gamma) * (kappa * kappa);
+    out[0] = -(1 / pS + muCS + mupS + sCS * spS - r - kappa * (sCS + spS));
+    if (SAVE) {
+      sv[0] = pS; sv[1] = p; sv[2] = r; sv[3] = kappa; sv[4] = sp; sv[5] = r + kappa * sR; sv[6] = sR; sv[7] = aI;
+      sv[8] = mux; sv[9] = sigx; sv[10] = x; sv[11] = px; sv[12] = pxx; sv[13] = aI * sR;
+    }
+  }
+};
+
 // X-macro: the registry order defines the model ids of the C ABI.
 #define ECONPDES_FOR_EACH_MODEL(X) \
   X(ReadmeLinear)                  \
@@ -745,6 +798,7 @@ struct LinearUpwindTest : ModelDefaults {
   X(GarleanuPanageas)              \
   X(Leland)                        \
   X(WangWangYang)                  \
-  X(LinearUpwindTest)
+  X(LinearUpwindTest)              \
+  X(HeKrishnamurthy)
 
 }  // namespace econpdes

@@ -249,6 +249,23 @@ class LinearUpwindTest(RegisteredModel):
 
 
 @dataclass(frozen=True)
+class HeKrishnamurthyModel(RegisteredModel):
+    """examples/asset_pricing/he_krishnamurthy.jl:21-30."""
+    m: float = 4.0
+    lam: float = 0.6
+    g: float = 0.02
+    sigma: float = 0.09
+    rho: float = 0.04
+    gamma: float = 2.0
+    l: float = 1.84
+    name: ClassVar[str] = "he_krishnamurthy"
+    statenames: ClassVar = ("x",)
+    solnames: ClassVar = ("pS",)
+    savednames: ClassVar = ("pS", "p", "r", "kappa", "sigmap", "muR", "sigmaR", "alphaI", "mux", "sigmax", "x", "px", "pxx",
+                            "sigmaI")
+
+
+@dataclass(frozen=True)
 class NeoclassicalGrowthModel(RegisteredModel):
     """examples/neoclassical_growth.jl:25-31."""
     A: float = 0.5
@@ -318,4 +335,4 @@ ALL_MODELS = (ReadmeLinear, CampbellCochraneModel, BansalYaronModel, AchdouHanLa
               Hjb3dSynth, NeoclassicalGrowthModel, GrowthTest, LinearSum1D, LinearSum2D, LinearSum3D,
               ForwardPrice, VMinusTwo, Hjb2dRegimes, TuckmanVilaModel, DiTellaModel,
               AchdouHanLasryLionsMollModel_TwoStates, GarleanuPanageasModel, LelandModel,
-              WangWangYangModel, LinearUpwindTest)
+              WangWangYangModel, LinearUpwindTest, HeKrishnamurthyModel)

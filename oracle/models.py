@@ -647,6 +647,55 @@ def linear_upwind_test(s=-1.0, a=1.0, dir=1.0):
     return pde
 
 
+HK_SAVED = ("pS", "p", "r", "kappa", "sigmap", "muR", "sigmaR", "alphaI", "mux", "sigmax", "x", "px", "pxx", "sigmaI")
+
+
+def he_krishnamurthy(m=4.0, lam=0.6, g=0.02, sigma=0.09, rho=0.04, gamma=2.0, l=1.84):
+    """examples/asset_pricing/he_krishnamurthy.jl:45-92 (unknown pS on the specialists' wealth share x)."""
+    def pde(state, u):
+        x = state["x"]
+        pS, pSxx = u["pS"], u["pSxx"]
+
+        def block(pSx):
+            p = (1 + l) / (x / pS + (1 - x) * rho)
+            px = -(1 + l) / (x / pS + (1 - x) * rho) ** 2 * (1 / pS - rho - x / pS ** 2 * pSx)
+            pxx = (-(1 + l) / (x / pS + (1 - x) * rho) ** 2 * (-1 / pS ** 2 * pSx - 1 / pS ** 2 * pSx - x / pS ** 2 * pSxx
+                                                             + 2 * x / pS ** 3 * pSx ** 2)
+                   + 2 * (1 + l) / (x / pS + (1 - x) * rho) ** 3 * (1 / pS - rho - x / pS ** 2 * pSx) ** 2)
+            aI = 1 / (1 - lam * (1 - x)) + 0.0 * pS
+            aI = np.where(x * (1 + m) * aI < 1, 1 / (x * (1 + m)), aI)
+            sigx = x * (aI - 1) * sigma / (1 - x * (aI - 1) * px / p)
+            spS = pSx / pS * sigx
+            sp = px / p * sigx
+            sR = sigma + sp
+            kappa = gamma * (aI * sR - spS)
+            mux = x * (1 - x) * ((aI - (1 - aI * x) / (1 - x)) * kappa * sR - 1 / pS + rho
+                                 - (aI - (1 - aI * x) / (1 - x)) * sR ** 2 - l / ((1 - x) * p))
+            return p, px, pxx, aI, sigx, spS, sp, sR, kappa, mux
+        with np.errstate(all="ignore"):
+            first, second = block(u["pSx_up"]), block(u["pSx_down"])
+            redo = first[-1] < 0
+            p, px, pxx, aI, sigx, spS, sp, sR, kappa, mux = (np.where(redo, b2, b1) for b1, b2 in zip(first, second))
+            pSx = np.where(redo, u["pSx_down"], u["pSx_up"])
+            mupS = pSx / pS * mux + 0.5 * pSxx / pS * sigx ** 2
+            mup = px / p * mux + 0.5 * pxx / p * sigx ** 2
+            r = 1 / p + g + mup + sigma * sp - kappa * sR
+            sCS = kappa / gamma
+            muCS = (r - rho) / gamma + (1 + 1 / gamma) / (2 * gamma) * kappa ** 2
+            pSt = -(1 / pS + muCS + mupS + sCS * spS - r - kappa * (sCS + spS))
+        saved = dict(zip(HK_SAVED, (pS, p, r, kappa, sp, r + kappa * sR, sR, aI, mux, sigx, x + 0.0 * pS, px, pxx, aI * sR)))
+        return {"pSt": pSt}, saved
+    return pde
+
+
+def he_krishnamurthy_problem(xn=100, **over):
+    """Grid and guess of the example (he_krishnamurthy.jl:31-39)."""
+    prm = dict(m=4.0, lam=0.6, g=0.02, sigma=0.09, rho=0.04, gamma=2.0, l=1.84)
+    prm.update(over)
+    x = julia_range(0.0, 1.0, xn + 2)[1:-1] ** 1.5
+    return {"x": x}, {"pS": np.ones(xn)}, prm
+
+
 def v_minus_two():
     """test/runtests.jl:227: vt = v - 2."""
     def pde(state, u):

@@ -532,6 +532,34 @@ def test_wang_wang_yang_example_boundary_derivatives():
     assert res.solution["p"][0] < 1 / (prm["r"] - prm["mu"])       # below the complete-markets value at the constraint
 
 
+def test_he_krishnamurthy_example_generic_and_batched_engines():
+    """examples/asset_pricing/he_krishnamurthy.jl at its default grid (100 points, x^1.5 spacing): the generic
+    1-D engine with its 14 saved outputs, and the same model through the fused batched engine."""
+    g, gu, prm = OM.he_krishnamurthy_problem()
+    ora = eo.pdesolve(OM.he_krishnamurthy(**prm), g, gu)
+    res = E.pdesolve(PM.HeKrishnamurthyModel(**prm), g, gu, verbose=False)
+    assert res.converged == ora.converged and res.converged
+    assert [r["status"] for r in res.log] == [r[3] for r in ora.log.rows]
+    assert [r["newton_iters"] for r in res.log] == [r[4] for r in ora.log.rows]
+    np.testing.assert_allclose(res.solution["pS"], ora.solution["pS"], rtol=1e-8)
+    assert abs(res.residual_norm - ora.residual_norm) <= 1e-10
+    for k in OM.HK_SAVED:
+        np.testing.assert_allclose(res.saved[k], ora.saved[k], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(res.saved["kappa"][-1], prm["gamma"] * prm["sigma"], rtol=2e-2)   # unconstrained limit
+    # a small sweep over the risk aversion through the batched kernel
+    gammas = (1.5, 2.0, 3.0)
+    params = np.array([[prm["m"], prm["lam"], prm["g"], prm["sigma"], prm["rho"], ga, prm["l"]] for ga in gammas])
+    out = E.pdesolve_batched(PM.HeKrishnamurthyModel, params, np.stack([g["x"]] * 3), np.stack([gu["pS"]] * 3))
+    for b, ga in enumerate(gammas):
+        o = eo.pdesolve(OM.he_krishnamurthy(**{**prm, "gamma": ga}), g, gu)
+        assert bool(out.converged[b]) == o.converged and out.n_outer[b] == o.log.n_outer
+        np.testing.assert_allclose(out.solution[b], o.solution["pS"], rtol=1e-8)
+    with pytest.raises(E.EconPDEsCudaError, match="time argument"):
+        gt, gut, _, _ = OM.tuckman_vila_problem(zn=50)
+        E.pdesolve_batched(PM.TuckmanVilaModel, np.array([[0.06, 0.09, 5.42, 26.72, 26.72, 100.0]]), gt["z"][None, :],
+                           gut["F"][None, :])
+
+
 def test_garleanu_panageas_example_four_unknowns():
     """examples/asset_pricing/garleanu_panageas.jl at its default grid (100 points): four coupled unknowns ->
     4 x 4 block-tridiagonal Newton systems, two-pass upwinding, saved interest rate and price of risk."""

@@ -47,6 +47,9 @@ def _cases():
     out.append(("gp", PM.GarleanuPanageasModel(**prm), OM.garleanu_panageas(**prm), g, gu))
     g, gu, prm, _ = OM.wang_wang_yang_problem(80)
     out.append(("wwy", PM.WangWangYangModel(**prm), OM.wang_wang_yang(**prm), g, gu))
+    g, gu, prm = OM.he_krishnamurthy_problem(40)
+    gu = {"pS": 20.0 + 5.0 * np.linspace(0, 1, 40)}
+    out.append(("hk", PM.HeKrishnamurthyModel(**prm), OM.he_krishnamurthy(**prm), g, gu))
     # three-argument body: the host emulation leaves the time slot at 0
     g, gu, _, prm = OM.tuckman_vila_problem(zn=50)
     tv = OM.tuckman_vila(**prm)
