@@ -777,6 +777,175 @@ struct HeKrishnamurthy : ModelDefaults {
   }
 };
 
+// examples/asset_pricing/wachter.jl:66-92   state lambda (disaster intensity), unknown p
+// prm[11..13] = mgf(Z, 1), mgf(Z, -gamma), mgf(Z, 1 - gamma) of the jump-size distribution Z ~ Normal(muZ, sigmaZ),
+// evaluated once by the host mirror (they depend on the parameters only).
+struct Wachter : ModelDefaults {
+  static constexpr int N = 1, F = 1, NPARAMS = 14, NSAVED = 0;
+  static constexpr bool USES_CROSS = false;
+  static const char* name() { return "wachter"; }
+  struct Pre { double mu, sigma, rho, gamma, psi, lam, mul, sigl, m1, mg, m1g; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
+    const double lambar = prm[2], kappal = prm[3], nul = prm[4];
+    c.mu = prm[0]; c.sigma = prm[1]; c.rho = prm[7]; c.gamma = prm[8]; c.psi = prm[9];
+    c.m1 = prm[11]; c.mg = prm[12]; c.m1g = prm[13];
+    c.lam = st[0];
+    c.mul = kappal * (lambar - c.lam);
+    c.sigl = nul * sqrt(c.lam);
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<1>* u, double* out, double*) {
+    const double mu = c.mu, sigma = c.sigma, rho = c.rho, gamma = c.gamma, psi = c.psi, lam = c.lam;
+    const double p = u[0].v, pll = u[0].dd[0];
+    const double pl = (c.mul >= 0) ? u[0].up[0] : u[0].dn[0];
+    const double mup = pl / p * c.mul + 0.5 * pll / p * (c.sigl * c.sigl);
+    const double sp = pl / p * c.sigl;
+    const double kZc = gamma * sigma;
+    const double kZl = (gamma * psi - 1) / (psi - 1) * sp;
+    const double eta = lam * (c.m1 - 1 + c.mg - 1 - (c.m1g - 1));
+    const double r = rho + mu / psi - (1 + 1 / psi) / 2 * gamma * (sigma * sigma) - lam * (c.mg - 1) +
+                     (1 / psi - gamma) / (1 - gamma) * lam * (c.m1g - 1) - (gamma * psi - 1) / (2 * (psi - 1)) * (sp * sp);
+    out[0] = -p * (1 / p + mu + mup + lam * (c.m1 - 1) - r - kZc * sigma - kZl * sp - eta);
+  }
+};
+
+// examples/asset_pricing/haddad.jl:63-93   states (mu, v), unknown p; endogenous active-capital share
+struct Haddad : ModelDefaults {
+  static constexpr int N = 2, F = 1, NPARAMS = 11, NSAVED = 0;
+  static constexpr bool USES_CROSS = false;
+  static const char* name() { return "haddad"; }
+  struct Pre { double abar, lam, rho, gamma, psi, muc, sigc, mumu, sigmu, muv, sigv; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
+    const double mubar = prm[0], vbar = prm[1], kappa_mu = prm[2], nu_mu = prm[3], kappa_v = prm[4], nu_v = prm[5];
+    c.abar = prm[6]; c.lam = prm[7]; c.rho = prm[8]; c.gamma = prm[9]; c.psi = prm[10];
+    const double mu = st[0], v = st[1];
+    c.muc = mu;
+    c.sigc = sqrt(v);
+    c.mumu = kappa_mu * (mubar - mu);
+    c.sigmu = nu_mu * sqrt(v);
+    c.muv = kappa_v * (vbar - v);
+    c.sigv = nu_v * sqrt(v);
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<2>* u, double* out, double*) {
+    const double gamma = c.gamma, psi = c.psi, sigc = c.sigc;
+    const double p = u[0].v;
+    const double pmu = (c.mumu >= 0) ? u[0].up[0] : u[0].dn[0];
+    const double pv = (c.muv >= 0) ? u[0].up[1] : u[0].dn[1];
+    const double sZmu = pmu / p * c.sigmu;
+    const double sZv = pv / p * c.sigv;
+    const double sp2 = sZmu * sZmu + sZv * sZv;
+    const double mup = pmu / p * c.mumu + pv / p * c.muv + 0.5 * u[0].dd[0] / p * (c.sigmu * c.sigmu) +
+                       0.5 * u[0].dd[1] / p * (c.sigv * c.sigv);
+    double astar = c.abar - sqrt(c.lam * c.abar / (0.5 * gamma * (sigc * sigc + sZmu * sZmu + sZv * sZv)));
+    astar = astar > 1.0 ? 1.0 : (astar < 0.0 ? 0.0 : astar);   // clamp(astar, 0.0, 1.0)
+    const double a1sq = (astar - 1) * (astar - 1);
+    out[0] = -p * (1 / p - c.rho + (1 - 1 / psi) * (c.muc - 0.5 * gamma * (sigc * sigc) * (1 - a1sq)) + mup +
+                   (0.5 * (1 / psi - gamma) / (1 - 1 / psi) + 0.5 * gamma * (1 - 1 / psi) * a1sq) * sp2);
+  }
+};
+
+// examples/corporate_finance/bolton_chen_wang.jl:56-72   state w (cash-capital ratio), unknown v (firm value)
+// saved = (v, vw, vww, w); solved with bc = (vw = (vw(0), vw(wmax))), the pair an outer root-finder adjusts
+struct BoltonChenWang : ModelDefaults {
+  static constexpr int N = 1, F = 1, NPARAMS = 9, NSAVED = 4;
+  static constexpr bool USES_CROSS = false;
+  static const char* name() { return "bolton_chen_wang"; }
+  struct Pre { double r, delta, A, sigma, theta, lam, w; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
+    c.r = prm[0]; c.delta = prm[1]; c.A = prm[2]; c.sigma = prm[3]; c.theta = prm[4]; c.lam = prm[5];
+    c.w = st[0];   // prm[6..8] = (l, gamma, phi) only enter the outer boundary conditions
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<1>* u, double* out, double* sv) {
+    const double r = c.r, delta = c.delta, A = c.A, sigma = c.sigma, theta = c.theta, lam = c.lam, w = c.w;
+    const double v = u[0].v, vww = u[0].dd[0];
+    double vw = u[0].up[0];
+    double i = 1 / theta * (v / vw - w - 1);
+    double muw = (r - lam) * w + A - i - theta * (i * i) / 2 - (i - delta) * w;
+    if (muw <= 0) {   // `@goto start` with the backward difference
+      vw = u[0].dn[0];
+      i = 1 / theta * (v / vw - w - 1);
+    }
+    out[0] = -((i - delta) * (v - vw * w) + ((r - lam) * w + A - i - theta * (i * i) / 2) * vw + sigma * sigma / 2 * vww - r * v);
+    if (SAVE) { sv[0] = v; sv[1] = vw; sv[2] = vww; sv[3] = w; }
+  }
+};
+
+// examples/asset_pricing/gomez.jl:58-118   state x (entrepreneurs' consumption share), unknown pH
+// saved: the 30 equilibrium quantities the example returns, in its order
+struct Gomez : ModelDefaults {
+  static constexpr int N = 1, F = 1, NPARAMS = 14, NSAVED = 30;
+  static constexpr bool USES_CROSS = false;
+  static const char* name() { return "gomez"; }
+  struct Pre { double gamma, psi, rho, rhoE, aE, eta, delta, phi, piE, g, sigma, lam, tau, x; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
+    c.gamma = prm[0]; c.psi = prm[1]; c.rho = prm[2]; c.rhoE = prm[3]; c.aE = prm[4];   // prm[5] = nu is unused by the body
+    c.eta = prm[6]; c.delta = prm[7]; c.phi = prm[8]; c.piE = prm[9]; c.g = prm[10]; c.sigma = prm[11]; c.lam = prm[12];
+    c.tau = prm[13];
+    c.x = st[0];
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<1>* u, double* out, double* sv) {
+    const double gamma = c.gamma, psi = c.psi, rho = c.rho, rhoE = c.rhoE, aE = c.aE, eta = c.eta, delta = c.delta,
+                 phi = c.phi, piE = c.piE, g = c.g, sigma = c.sigma, lam = c.lam, tau = c.tau, x = c.x;
+    const double pH = u[0].v, pHxx = u[0].dd[0];
+    const double p = x / rhoE + (1 - x) * pH;
+    const double xW = x / rhoE / p;
+    const double aEeff = (xW * aE >= 1) ? 1 / xW : aE;
+    double pHx = u[0].up[0];
+    double px, sigx, spH, sp, sCE, sCH, sWH, kappa, PhiE, PhiH, wealth, wedge, r, muCE, muCH, mux;
+    for (int pass = 0;; ++pass) {   // `@goto start`
+      px = 1 / rhoE - pH + (1 - x) * pHx;
+      sigx = x * (aEeff - 1) * sigma / (1 - x * aEeff * px / p);
+      spH = pHx / pH * sigx;
+      sp = px / p * sigx;
+      sCE = aEeff * (sigma + sp);
+      sCH = x < 1 ? (sigma - x * sCE) / (1 - x) : 0.0;
+      sWH = sCH + spH;
+      kappa = gamma * sCH + (gamma * psi - 1) / (psi - 1) * spH;
+      PhiE = aEeff * kappa * (sigma + sp);
+      PhiH = kappa * kappa * (1 + psi) / (2 * gamma) + (1 - psi * gamma) / (gamma * (psi - 1)) * kappa * spH -
+             (1 - gamma * psi) / (2 * gamma * (psi - 1)) * (spH * spH);
+      wealth = (eta + delta + phi + tau) / (eta + delta) * p;
+      wedge = (eta + delta) * ((rhoE * piE + (1 - piE) / pH) * wealth - 1);
+      const double Psi = x + (1 - x) * psi;
+      const double P = (x * rhoE + (1 - x) * psi * rho) / Psi;
+      r = P + 1 / Psi * (g - x * PhiE - (1 - x) * PhiH - wedge) + tau;
+      muCE = r - tau - rhoE + PhiE;
+      muCH = psi * (r - tau - rho) + PhiH;
+      mux = x * (muCE - g) + (eta + delta) * (rhoE * piE * wealth - x) - sigma * sigx;
+      if (pass == 0 && mux <= 0) {
+        pHx = u[0].dn[0];
+        continue;
+      }
+      break;
+    }
+    const double mupH = pHx / pH * mux + 0.5 * pHxx / pH * (sigx * sigx);
+    const double muWH = muCH + mupH + sCH * spH;
+    out[0] = -pH * (1 / pH + muWH - r + tau - kappa * sWH);
+    if (SAVE) {
+      const double pxx = -2 * pHx + (1 - x) * pHxx;
+      const double mup = px / p * mux + 0.5 * pxx / p * (sigx * sigx);
+      const double sR = sigma + sp;
+      const double muR = r + kappa * sR;
+      const double sErel = (aEeff - 1) * (sigma + sp);
+      const double muErel = muCE - (g + mup + sigma * sp) - sErel * (sigma + sp);
+      const double alpha = x < 1 ? (1 - xW * aEeff) / (1 - xW) : 0.0;
+      const double sHrel = (alpha - 1) * (sigma + sp);
+      const double muHrel = muWH - (g + mup + sigma * sp) - sHrel * (sigma + sp);
+      const double muxW = xW * (muCE - (g + mup + sigma * sp) - sErel * (sigma + sp)) +
+                          (eta + delta) * (piE * (eta + delta + phi) / (eta + delta) - xW);
+      const double sxW = xW * (aEeff - 1) * (sigma + sp);
+      sv[0] = x; sv[1] = mux; sv[2] = sigx; sv[3] = kappa; sv[4] = r; sv[5] = sWH; sv[6] = muWH; sv[7] = sp; sv[8] = p;
+      sv[9] = px; sv[10] = sR; sv[11] = muR; sv[12] = r + lam * (muR - r); sv[13] = lam * sR; sv[14] = muErel;
+      sv[15] = sErel; sv[16] = muHrel; sv[17] = sHrel; sv[18] = muCE; sv[19] = muxW; sv[20] = sxW; sv[21] = pH;
+      sv[22] = muCH; sv[23] = wedge; sv[24] = xW; sv[25] = sCE; sv[26] = sCH; sv[27] = aEeff; sv[28] = 1 / rhoE;
+      sv[29] = mup;
+    }
+  }
+};
+
 // X-macro: the registry order defines the model ids of the C ABI.
 #define ECONPDES_FOR_EACH_MODEL(X) \
   X(ReadmeLinear)                  \
@@ -799,6 +968,10 @@ struct HeKrishnamurthy : ModelDefaults {
   X(Leland)                        \
   X(WangWangYang)                  \
   X(LinearUpwindTest)              \
-  X(HeKrishnamurthy)
+  X(HeKrishnamurthy)               \
+  X(Wachter)                       \
+  X(Haddad)                        \
+  X(BoltonChenWang)                \
+  X(Gomez)
 
 }  // namespace econpdes

@@ -266,6 +266,95 @@ class HeKrishnamurthyModel(RegisteredModel):
 
 
 @dataclass(frozen=True)
+class WachterModel(RegisteredModel):
+    """examples/asset_pricing/wachter.jl:20-39; `ZDistribution = Normal(muZ, sigmaZ)`."""
+    mu: float = 0.025
+    sigma: float = 0.02
+    lambar: float = 0.0355
+    kappa_lambda: float = 0.08
+    nu_lambda: float = 0.067
+    muZ: float = -0.4
+    sigmaZ: float = 0.25
+    rho: float = 0.012
+    gamma: float = 3.0
+    psi: float = 1.1
+    phi: float = 2.6
+    name: ClassVar[str] = "wachter"
+    statenames: ClassVar = ("lambda",)
+    solnames: ClassVar = ("p",)
+
+    def mgf(self, t: float) -> float:
+        """Moment generating function of Normal(muZ, sigmaZ) (Distributions.jl `mgf(::Normal, t)`)."""
+        return float(np.exp(t * self.muZ + self.sigmaZ ** 2 / 2 * t ** 2))
+
+    def params(self) -> np.ndarray:
+        base = RegisteredModel.params(self)
+        return np.concatenate([base, [self.mgf(1.0), self.mgf(-self.gamma), self.mgf(1.0 - self.gamma)]])
+
+
+@dataclass(frozen=True)
+class HaddadModel(RegisteredModel):
+    """examples/asset_pricing/haddad.jl:20-36."""
+    mubar: float = 0.018
+    vbar: float = 0.00052
+    kappa_mu: float = 0.3
+    nu_mu: float = 0.456
+    kappa_v: float = 0.012
+    nu_v: float = 0.00472
+    alphabar: float = 1.2
+    lam: float = 0.018
+    rho: float = 0.0132
+    gamma: float = 10.0
+    psi: float = 1.5
+    name: ClassVar[str] = "haddad"
+    statenames: ClassVar = ("mu", "v")
+    solnames: ClassVar = ("p",)
+
+
+@dataclass(frozen=True)
+class BoltonChenWangModel(RegisteredModel):
+    """examples/corporate_finance/bolton_chen_wang.jl:19-29."""
+    r: float = 0.06
+    delta: float = 0.10
+    A: float = 0.18
+    sigma: float = 0.09
+    theta: float = 1.5
+    lam: float = 0.01
+    l: float = 0.9
+    gamma: float = 0.06
+    phi: float = 0.01
+    name: ClassVar[str] = "bolton_chen_wang"
+    statenames: ClassVar = ("w",)
+    solnames: ClassVar = ("v",)
+    savednames: ClassVar = ("v", "vw", "vww", "w")
+
+
+@dataclass(frozen=True)
+class GomezModel(RegisteredModel):
+    """examples/asset_pricing/gomez.jl:18-39."""
+    gamma: float = 10.3
+    psi: float = 0.05
+    rho: float = 0.1
+    rhoE: float = 0.022
+    alphaE: float = 2.0
+    nu: float = 0.1
+    eta: float = 0.015
+    delta: float = 0.025
+    phi: float = 0.01
+    piE: float = 0.09
+    g: float = 0.02
+    sigma: float = 0.04
+    lam: float = 2.3
+    tau: float = 0.0
+    name: ClassVar[str] = "gomez"
+    statenames: ClassVar = ("x",)
+    solnames: ClassVar = ("pH",)
+    savednames: ClassVar = ("x", "mux", "sigmax", "kappa", "r", "sigmaWH", "muWH", "sigmap", "p", "px", "sigmaR", "muR",
+                            "muRlambda", "sigmaRlambda", "muErelative", "sigmaErelative", "muHrelative", "sigmaHrelative",
+                            "muCE", "muxW", "sigmaxW", "pH", "muCH", "wedge", "xW", "sigmaWE", "sigmaCH", "alphaE", "pE", "mup")
+
+
+@dataclass(frozen=True)
 class NeoclassicalGrowthModel(RegisteredModel):
     """examples/neoclassical_growth.jl:25-31."""
     A: float = 0.5
@@ -335,4 +424,5 @@ ALL_MODELS = (ReadmeLinear, CampbellCochraneModel, BansalYaronModel, AchdouHanLa
               Hjb3dSynth, NeoclassicalGrowthModel, GrowthTest, LinearSum1D, LinearSum2D, LinearSum3D,
               ForwardPrice, VMinusTwo, Hjb2dRegimes, TuckmanVilaModel, DiTellaModel,
               AchdouHanLasryLionsMollModel_TwoStates, GarleanuPanageasModel, LelandModel,
-              WangWangYangModel, LinearUpwindTest, HeKrishnamurthyModel)
+              WangWangYangModel, LinearUpwindTest, HeKrishnamurthyModel, WachterModel, HaddadModel,
+              BoltonChenWangModel, GomezModel)

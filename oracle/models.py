@@ -696,6 +696,190 @@ def he_krishnamurthy_problem(xn=100, **over):
     return {"x": x}, {"pS": np.ones(xn)}, prm
 
 
+def normal_mgf(t, mu, sigma):
+    """Distributions.jl `mgf(d::Normal, t) = exp(t * mu + sigma^2 / 2 * t^2)` (third-party; parity unpinned)."""
+    return float(np.exp(t * mu + sigma ** 2 / 2 * t ** 2))
+
+
+def wachter(mu=0.025, sigma=0.02, lambar=0.0355, kappa_lambda=0.08, nu_lambda=0.067, muZ=-0.4, sigmaZ=0.25,
+            rho=0.012, gamma=3.0, psi=1.1, phi=2.6):
+    """examples/asset_pricing/wachter.jl:66-92 (unknown p on the disaster intensity lambda)."""
+    m1, mg, m1g = normal_mgf(1.0, muZ, sigmaZ), normal_mgf(-gamma, muZ, sigmaZ), normal_mgf(1.0 - gamma, muZ, sigmaZ)
+
+    def pde(state, u):
+        lam = state["lambda"]
+        p, pll = u["p"], u["plambdalambda"]
+        mul = kappa_lambda * (lambar - lam)
+        sigl = nu_lambda * np.sqrt(lam)
+        pl = np.where(mul >= 0, u["plambda_up"], u["plambda_down"])
+        mup = pl / p * mul + 0.5 * pll / p * sigl ** 2
+        sp = pl / p * sigl
+        kZc = gamma * sigma
+        kZl = (gamma * psi - 1) / (psi - 1) * sp
+        eta = lam * (m1 - 1 + mg - 1 - (m1g - 1))
+        r = (rho + mu / psi - (1 + 1 / psi) / 2 * gamma * sigma ** 2 - lam * (mg - 1)
+             + (1 / psi - gamma) / (1 - gamma) * lam * (m1g - 1) - (gamma * psi - 1) / (2 * (psi - 1)) * sp ** 2)
+        return {"pt": -p * (1 / p + mu + mup + lam * (m1 - 1) - r - kZc * sigma - kZl * sp - eta)}
+    return pde
+
+
+def wachter_problem(n=30, **over):
+    """Grid and guess of the example (wachter.jl:48-58)."""
+    prm = dict(mu=0.025, sigma=0.02, lambar=0.0355, kappa_lambda=0.08, nu_lambda=0.067, muZ=-0.4, sigmaZ=0.25,
+               rho=0.012, gamma=3.0, psi=1.1, phi=2.6)
+    prm.update(over)
+    return {"lambda": julia_range(0.0, 0.1, n)}, {"p": np.ones(n)}, prm
+
+
+HADDAD_DEFAULT = dict(mubar=0.018, vbar=0.00052, kappa_mu=0.3, nu_mu=0.456, kappa_v=0.012, nu_v=0.00472,
+                      alphabar=1.2, lam=0.018, rho=0.0132, gamma=10.0, psi=1.5)
+
+
+def haddad(mubar, vbar, kappa_mu, nu_mu, kappa_v, nu_v, alphabar, lam, rho, gamma, psi):
+    """examples/asset_pricing/haddad.jl:63-93 (long-run risk with an endogenous active-capital share)."""
+    def pde(state, u):
+        mu, v = state["mu"], state["v"]
+        p = u["p"]
+        muc = mu
+        sigc = np.sqrt(v)
+        mumu = kappa_mu * (mubar - mu)
+        sigmu = nu_mu * np.sqrt(v)
+        muv = kappa_v * (vbar - v)
+        pmu = np.where(mumu >= 0, u["pmu_up"], u["pmu_down"])
+        pv = np.where(muv >= 0, u["pv_up"], u["pv_down"])
+        sigv = nu_v * np.sqrt(v)
+        with np.errstate(all="ignore"):
+            sZmu = pmu / p * sigmu
+            sZv = pv / p * sigv
+            sp2 = sZmu ** 2 + sZv ** 2
+            mup = pmu / p * mumu + pv / p * muv + 0.5 * u["pmumu"] / p * sigmu ** 2 + 0.5 * u["pvv"] / p * sigv ** 2
+            astar = alphabar - np.sqrt(lam * alphabar / (0.5 * gamma * (sigc ** 2 + sZmu ** 2 + sZv ** 2)))
+            astar = np.where(astar > 1.0, 1.0, np.where(astar < 0.0, 0.0, astar))      # clamp(astar, 0.0, 1.0)
+            pt = -p * (1 / p - rho + (1 - 1 / psi) * (muc - 0.5 * gamma * sigc ** 2 * (1 - (astar - 1) ** 2)) + mup
+                       + (0.5 * (1 / psi - gamma) / (1 - 1 / psi) + 0.5 * gamma * (1 - 1 / psi) * (astar - 1) ** 2) * sp2)
+        return {"pt": pt}
+    return pde
+
+
+def haddad_problem(n_mu=30, n_v=30, params=None):
+    """Grid and guess of the example (haddad.jl:41-56)."""
+    from scipy import stats
+    prm = dict(HADDAD_DEFAULT if params is None else params)
+    sd = math.sqrt(prm["nu_mu"] ** 2 * prm["vbar"] / (2 * prm["kappa_mu"]))
+    mus = julia_range(stats.norm.ppf(0.001, prm["mubar"], sd), stats.norm.ppf(0.999, prm["mubar"], sd), n_mu)
+    shape = 2 * prm["kappa_v"] * prm["vbar"] / prm["nu_v"] ** 2
+    scale = prm["nu_v"] ** 2 / (2 * prm["kappa_v"])
+    vs = julia_range(stats.gamma.ppf(0.001, shape, scale=scale), stats.gamma.ppf(0.999, shape, scale=scale), n_v)
+    return {"mu": mus, "v": vs}, {"p": np.ones((n_mu, n_v))}, prm
+
+
+def bolton_chen_wang(r=0.06, delta=0.10, A=0.18, sigma=0.09, theta=1.5, lam=0.01, l=0.9, gamma=0.06, phi=0.01):
+    """examples/corporate_finance/bolton_chen_wang.jl:56-72 (firm value v on the cash-capital ratio w)."""
+    def pde(state, u):
+        w = state["w"]
+        v, vww = u["v"], u["vww"]
+        with np.errstate(all="ignore"):
+            i_up = 1 / theta * (v / u["vw_up"] - w - 1)
+            muw = (r - lam) * w + A - i_up - theta * i_up ** 2 / 2 - (i_up - delta) * w
+            redo = muw <= 0
+            vw = np.where(redo, u["vw_down"], u["vw_up"])
+            i = np.where(redo, 1 / theta * (v / u["vw_down"] - w - 1), i_up)
+            vt = -((i - delta) * (v - vw * w) + ((r - lam) * w + A - i - theta * i ** 2 / 2) * vw + sigma ** 2 / 2 * vww - r * v)
+        return {"vt": vt}, {"v": v, "vw": vw, "vww": vww, "w": w + 0.0 * v}
+    return pde
+
+
+def bolton_chen_wang_problem(n=100, **over):
+    """Grid, guess and the first boundary pair of the example (bolton_chen_wang.jl:36-42, 78)."""
+    prm = dict(r=0.06, delta=0.10, A=0.18, sigma=0.09, theta=1.5, lam=0.01, l=0.9, gamma=0.06, phi=0.01)
+    prm.update(over)
+    w = julia_range(0.0, 0.3, n)
+    return {"w": w}, {"v": w.copy()}, prm, {"vw": (1.5, 1.0)}
+
+
+def bolton_chen_wang_boundary_residual(prm, saved):
+    """The two smooth-pasting conditions the example's outer `nlsolve` drives to zero (bolton_chen_wang.jl:84-95)."""
+    v, vw, w = saved["v"], saved["vw"], saved["w"]
+    mi = int(np.argmin(np.abs(1 + prm["gamma"] - vw)))
+    wi = int(np.argmin(np.abs(1 - vw)))
+    i = 1 / prm["theta"] * (v[wi] - w[wi] - 1)
+    return np.array([v[mi] - prm["phi"] - (1 + prm["gamma"]) * w[mi] - v[0],
+                     prm["r"] * v[wi] - (i - prm["delta"]) * (v[wi] - w[wi])
+                     - ((prm["r"] - prm["lam"]) * w[wi] + prm["A"] - i - prm["theta"] * i ** 2 / 2)])
+
+
+GOMEZ_SAVED = ("x", "mux", "sigmax", "kappa", "r", "sigmaWH", "muWH", "sigmap", "p", "px", "sigmaR", "muR",
+               "muRlambda", "sigmaRlambda", "muErelative", "sigmaErelative", "muHrelative", "sigmaHrelative",
+               "muCE", "muxW", "sigmaxW", "pH", "muCH", "wedge", "xW", "sigmaWE", "sigmaCH", "alphaE", "pE", "mup")
+
+
+def gomez(gamma=10.3, psi=0.05, rho=0.1, rhoE=0.022, alphaE=2.0, nu=0.1, eta=0.015, delta=0.025, phi=0.01, piE=0.09,
+          g=0.02, sigma=0.04, lam=2.3, tau=0.0):
+    """examples/asset_pricing/gomez.jl:58-118 (unknown pH on the entrepreneurs' consumption share x)."""
+    def pde(state, u):
+        x = state["x"]
+        pH, pHxx = u["pH"], u["pHxx"]
+        with np.errstate(all="ignore"):
+            p = x / rhoE + (1 - x) * pH
+            xW = x / rhoE / p
+            aEeff = np.where(xW * alphaE >= 1, 1 / xW, alphaE)
+
+            def block(pHx):
+                px = 1 / rhoE - pH + (1 - x) * pHx
+                sigx = x * (aEeff - 1) * sigma / (1 - x * aEeff * px / p)
+                spH = pHx / pH * sigx
+                sp = px / p * sigx
+                sCE = aEeff * (sigma + sp)
+                sCH = np.where(x < 1, (sigma - x * sCE) / (1 - x), 0.0)
+                sWH = sCH + spH
+                kappa = gamma * sCH + (gamma * psi - 1) / (psi - 1) * spH
+                PhiE = aEeff * kappa * (sigma + sp)
+                PhiH = (kappa ** 2 * (1 + psi) / (2 * gamma) + (1 - psi * gamma) / (gamma * (psi - 1)) * kappa * spH
+                        - (1 - gamma * psi) / (2 * gamma * (psi - 1)) * spH ** 2)
+                wealth = (eta + delta + phi + tau) / (eta + delta) * p
+                wedge = (eta + delta) * ((rhoE * piE + (1 - piE) / pH) * wealth - 1)
+                Psi = x + (1 - x) * psi
+                P = (x * rhoE + (1 - x) * psi * rho) / Psi
+                r = P + 1 / Psi * (g - x * PhiE - (1 - x) * PhiH - wedge) + tau
+                muCE = r - tau - rhoE + PhiE
+                muCH = psi * (r - tau - rho) + PhiH
+                mux = x * (muCE - g) + (eta + delta) * (rhoE * piE * wealth - x) - sigma * sigx
+                return px, sigx, spH, sp, sCE, sCH, sWH, kappa, wedge, r, muCE, muCH, mux
+            first, second = block(u["pHx_up"]), block(u["pHx_down"])
+            redo = first[-1] <= 0
+            px, sigx, spH, sp, sCE, sCH, sWH, kappa, wedge, r, muCE, muCH, mux = (
+                np.where(redo, b2, b1) for b1, b2 in zip(first, second))
+            pHx = np.where(redo, u["pHx_down"], u["pHx_up"])
+            mupH = pHx / pH * mux + 0.5 * pHxx / pH * sigx ** 2
+            pxx = -2 * pHx + (1 - x) * pHxx
+            mup = px / p * mux + 0.5 * pxx / p * sigx ** 2
+            muWH = muCH + mupH + sCH * spH
+            pHt = -pH * (1 / pH + muWH - r + tau - kappa * sWH)
+            sR = sigma + sp
+            muR = r + kappa * sR
+            sErel = (aEeff - 1) * (sigma + sp)
+            muErel = muCE - (g + mup + sigma * sp) - sErel * (sigma + sp)
+            alpha = np.where(x < 1, (1 - xW * aEeff) / (1 - xW), 0.0)
+            sHrel = (alpha - 1) * (sigma + sp)
+            muHrel = muWH - (g + mup + sigma * sp) - sHrel * (sigma + sp)
+            muxW = (xW * (muCE - (g + mup + sigma * sp) - sErel * (sigma + sp))
+                    + (eta + delta) * (piE * (eta + delta + phi) / (eta + delta) - xW))
+            sxW = xW * (aEeff - 1) * (sigma + sp)
+            z = 0.0 * pH
+            vals = (x + z, mux, sigx, kappa, r, sWH, muWH, sp, p, px, sR, muR, r + lam * (muR - r), lam * sR, muErel, sErel,
+                    muHrel, sHrel, muCE, muxW, sxW, pH, muCH, wedge, xW + z, sCE, sCH, aEeff + z, 1 / rhoE + z, mup)
+        return {"pHt": pHt}, dict(zip(GOMEZ_SAVED, vals))
+    return pde
+
+
+def gomez_problem(n=300, **over):
+    """Grid and guess of the example (gomez.jl:46-52)."""
+    prm = dict(gamma=10.3, psi=0.05, rho=0.1, rhoE=0.022, alphaE=2.0, nu=0.1, eta=0.015, delta=0.025, phi=0.01, piE=0.09,
+               g=0.02, sigma=0.04, lam=2.3, tau=0.0)
+    prm.update(over)
+    return {"x": julia_range(0.0, 1.0, n) ** 2}, {"pH": np.ones(n)}, prm
+
+
 def v_minus_two():
     """test/runtests.jl:227: vt = v - 2."""
     def pde(state, u):

@@ -560,6 +560,69 @@ def test_he_krishnamurthy_example_generic_and_batched_engines():
                            gut["F"][None, :])
 
 
+def test_wachter_example():
+    """examples/asset_pricing/wachter.jl at its default grid (30 points on the disaster intensity): the moment
+    generating function values of the jump size enter as parameters; generic and batched engines."""
+    g, gu, prm = OM.wachter_problem()
+    ora = eo.pdesolve(OM.wachter(**prm), g, gu)
+    pm = PM.WachterModel(**prm)
+    res = E.pdesolve(pm, g, gu, verbose=False)
+    assert res.converged
+    _check_against(res, ora)
+    assert (np.diff(res.solution["p"]) < 0).all()          # the wealth-consumption ratio falls with disaster risk (psi > 1)
+    gammas = (2.0, 3.0, 4.0)
+    pms = [PM.WachterModel(**{**prm, "gamma": ga}) for ga in gammas]
+    out = E.pdesolve_batched(PM.WachterModel, np.stack([m.params() for m in pms]), np.stack([g["lambda"]] * 3),
+                             np.stack([gu["p"]] * 3))
+    for b, ga in enumerate(gammas):
+        o = eo.pdesolve(OM.wachter(**{**prm, "gamma": ga}), g, gu)
+        assert bool(out.converged[b]) == o.converged and out.n_outer[b] == o.log.n_outer
+        np.testing.assert_allclose(out.solution[b], o.solution["p"], rtol=1e-8)
+
+
+def test_haddad_example_two_states():
+    """examples/asset_pricing/haddad.jl at its default 30 x 30 grid: long-run risk with a clamped, endogenous
+    active-capital share; FGMRES + multigrid linear solves against the oracle's sparse LU."""
+    g, gu, prm = OM.haddad_problem()
+    ora = eo.pdesolve(OM.haddad(**prm), g, gu)
+    res = E.pdesolve(PM.HaddadModel(**prm), g, gu, verbose=False)
+    assert res.converged
+    _check_against(res, ora)
+    p = res.solution["p"]
+    assert (np.diff(p, axis=0) > 0).all() and (np.diff(p, axis=1) < 0).all()   # rises with growth, falls with variance
+
+
+def test_bolton_chen_wang_example_boundary_pair_and_saved():
+    """examples/corporate_finance/bolton_chen_wang.jl: the inner solve at the example's first boundary pair
+    bc = (vw = (1.5, 1.0)) and at a second pair, with the saved (v, vw, vww, w) the example's outer root-finder reads."""
+    g, gu, prm, bc = OM.bolton_chen_wang_problem()
+    for pair in (bc, {"vw": (1.3, 1.02)}):
+        ora = eo.pdesolve(OM.bolton_chen_wang(**prm), g, gu, bc=pair)
+        res = E.pdesolve(PM.BoltonChenWangModel(**prm), g, gu, bc=pair, verbose=False)
+        assert res.converged
+        _check_against(res, ora)
+        for k in ("v", "vw", "vww", "w"):
+            np.testing.assert_allclose(res.saved[k], ora.saved[k], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(OM.bolton_chen_wang_boundary_residual(prm, res.saved),
+                                   OM.bolton_chen_wang_boundary_residual(prm, ora.saved), rtol=0, atol=1e-8)
+    np.testing.assert_array_equal(res.saved["w"], g["w"])
+    np.testing.assert_array_equal(res.saved["v"], res.solution["v"])
+
+
+def test_gomez_example_thirty_saved_outputs():
+    """examples/asset_pricing/gomez.jl at its default grid (300 points, squared spacing, x = 0 and x = 1 included):
+    13 outer steps of which 3 are rejected, and the example's 30 saved equilibrium quantities."""
+    g, gu, prm = OM.gomez_problem()
+    ora = eo.pdesolve(OM.gomez(**prm), g, gu)
+    res = E.pdesolve(PM.GomezModel(**prm), g, gu, verbose=False)
+    assert res.converged
+    _check_against(res, ora)
+    assert set(res.saved) == set(OM.GOMEZ_SAVED)
+    for k in OM.GOMEZ_SAVED:
+        np.testing.assert_allclose(res.saved[k], ora.saved[k], rtol=1e-6, atol=1e-8, err_msg=k)
+    np.testing.assert_allclose(res.saved["sigmaR"][[0, -1]], prm["sigma"], rtol=1e-12)   # no amplification at x = 0, 1
+
+
 def test_garleanu_panageas_example_four_unknowns():
     """examples/asset_pricing/garleanu_panageas.jl at its default grid (100 points): four coupled unknowns ->
     4 x 4 block-tridiagonal Newton systems, two-pass upwinding, saved interest rate and price of risk."""

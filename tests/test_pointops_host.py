@@ -50,6 +50,18 @@ def _cases():
     g, gu, prm = OM.he_krishnamurthy_problem(40)
     gu = {"pS": 20.0 + 5.0 * np.linspace(0, 1, 40)}
     out.append(("hk", PM.HeKrishnamurthyModel(**prm), OM.he_krishnamurthy(**prm), g, gu))
+    g, gu, prm = OM.wachter_problem(30)
+    gu = {"p": 80.0 - 30.0 * g["lambda"]}
+    out.append(("wachter", PM.WachterModel(**prm), OM.wachter(**prm), g, gu))
+    g, gu, prm = OM.haddad_problem(13, 11)
+    gu = {"p": 100.0 + 10.0 * np.linspace(0, 1, 13)[:, None] - 8.0 * np.linspace(0, 1, 11)[None, :]}
+    out.append(("haddad", PM.HaddadModel(**prm), OM.haddad(**prm), g, gu))
+    g, gu, prm, _ = OM.bolton_chen_wang_problem(40)
+    gu = {"v": 100.0 + 120.0 * g["w"]}      # large level: the 1 % test perturbation then flips the upwind direction at some points
+    out.append(("bcw", PM.BoltonChenWangModel(**prm), OM.bolton_chen_wang(**prm), g, gu))
+    g, gu, prm = OM.gomez_problem(50)
+    gu = {"pH": 6.0 + 25.0 * g["x"]}
+    out.append(("gomez", PM.GomezModel(**prm), OM.gomez(**prm), g, gu))
     # three-argument body: the host emulation leaves the time slot at 0
     g, gu, _, prm = OM.tuckman_vila_problem(zn=50)
     tv = OM.tuckman_vila(**prm)
@@ -104,6 +116,21 @@ def test_saved_outputs_match_oracle():
     _, got = EU.residual(pm, grids, y, saved=True)
     np.testing.assert_allclose(got[..., 0], sv["mua"], rtol=0, atol=1e-14)
     np.testing.assert_allclose(got[..., 1], sv["c"], rtol=1e-14)
+
+
+@pytest.mark.parametrize("name", ["hk", "bcw", "gomez"])
+def test_saved_outputs_of_the_1d_examples_are_bit_exact(name):
+    """Saved quantities of the He-Krishnamurthy (14), Bolton-Chen-Wang (4) and Gomez (30) examples, in the
+    examples' order; +,-,*,/ only, so the host-compiled functor and the oracle agree to the bit."""
+    _, pm, om, g, gu = [c for c in CASES if c[0] == name][0]
+    grids = list(g.values())
+    y = _perturbed(gu)
+    prob = eo.Problem(om, tuple(g), grids, tuple(gu))
+    sv = prob.saved(y.reshape(-1, order="F"))
+    _, got = EU.residual(pm, grids, y, saved=True)
+    assert tuple(sv) == pm.savednames
+    for k, key in enumerate(pm.savednames):
+        np.testing.assert_array_equal(got[..., k], sv[key], err_msg=key)
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
