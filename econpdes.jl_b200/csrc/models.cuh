@@ -946,6 +946,107 @@ struct Gomez : ModelDefaults {
   }
 };
 
+// examples/consumption_saving/consumption_saving_risky_asset.jl:84-192   states (y, a), unknown v
+// saved = (v, c, k, va, vaa, vy, y, a, mua); solved with bc = (va = (lower row, upper row)) -- boundary values set for
+// one (unknown, state) pair only, which exercises the one-slot-per-point bc layout of src/pdesolve.jl:312-335
+struct AhlmRiskyAsset : ModelDefaults {
+  static constexpr int N = 2, F = 1, NPARAMS = 10, NSAVED = 9;
+  static constexpr bool USES_CROSS = false;
+  static const char* name() { return "ahlm_risky_asset"; }
+  struct Pre { double sigma_y, sigR, rho, gamma, y, a, muy, cash, prem, kmax, cmax; bool at_amax, above_amin; };
+  static constexpr double kCmin = 1.4901161193847656e-08;   // sqrt(eps())
+  EP_HD static double clampd(double x, double lo, double hi) { return x > hi ? hi : (x < lo ? lo : x); }
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
+    const double kappa_y = prm[0], ybar = prm[1], r = prm[3], muR = prm[4], amin = prm[8], amax = prm[9];
+    c.sigma_y = prm[2]; c.sigR = prm[5]; c.rho = prm[6]; c.gamma = prm[7];
+    c.y = st[0]; c.a = st[1];
+    c.muy = kappa_y * (ybar - c.y);
+    c.cash = c.y + r * c.a;
+    c.prem = muR - r;
+    c.kmax = ep_max(c.a - amin, 0.0);
+    c.cmax = ep_max(100.0 * (c.y + r * ep_max(c.a, 0.0)), kCmin);
+    c.at_amax = c.a == amax || fabs(c.a - amax) <= kCmin * ep_max(fabs(c.a), fabs(amax));   // a ≈ amax
+    c.above_amin = c.a > amin;
+  }
+  // policy_candidate(va_candidate) of the example
+  EP_HD static void candidate(const Pre& m, double vaa, double va_c, double& c_c, double& k_c, double& mua_c) {
+    const double sR = m.sigR, prem = m.prem, kmax = m.kmax;
+    c_c = va_c > 0.0 ? clampd(pow(va_c, -1 / m.gamma), kCmin, m.cmax) : m.cmax;
+    const double H_kmax = prem * va_c * kmax + 0.5 * vaa * (sR * sR) * (kmax * kmax);
+    k_c = H_kmax > 0.0 ? kmax : 0.0;
+    if (va_c > 0.0 && vaa < 0.0) {
+      const double k_merton = clampd(-prem * va_c / (sR * sR * vaa), 0.0, kmax);
+      const double H_merton = prem * va_c * k_merton + 0.5 * vaa * (sR * sR) * (k_merton * k_merton);
+      const double H_candidate = prem * va_c * k_c + 0.5 * vaa * (sR * sR) * (k_c * k_c);
+      k_c = H_merton >= H_candidate ? k_merton : k_c;
+    }
+    mua_c = m.cash + prem * k_c - c_c;
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& m, const Deriv<2>* u, double* out, double* sv) {
+    const double gamma = m.gamma, sR = m.sigR, prem = m.prem, cash = m.cash, cmin = kCmin;
+    const double v = u[0].v, va_up = u[0].up[1], va_down = u[0].dn[1], vyy = u[0].dd[0];
+    double vaa = u[0].dd[1];
+    if (m.at_amax) {
+      const double va_tail = (isfinite(va_down) && va_down > 0.0) ? va_down : va_up;
+      vaa = -gamma * va_tail / m.a;
+    }
+    const double vy = (m.muy >= 0) ? u[0].up[0] : u[0].dn[0];
+    double va, c, k, mua;
+    candidate(m, vaa, va_up, c, k, mua);
+    va = va_up;
+    if (!(mua >= 0.0)) {
+      double c_down, k_down, mua_down;
+      candidate(m, vaa, va_down, c_down, k_down, mua_down);
+      if ((mua_down <= 0.0) && m.above_amin) {
+        va = va_down; c = c_down; k = k_down; mua = mua_down;
+      } else {
+        // zero drift: the portfolio solves the first-order condition of the zero-drift Hamiltonian
+        double k_hi = m.kmax;
+        if (prem < 0.0) k_hi = ep_min(k_hi, ep_max((cash - cmin) / (-prem), 0.0));
+        if (k_hi == 0.0 || !(isfinite(cash) && isfinite(prem) && isfinite(vaa) && isfinite(sR))) {
+          k = 0.0;
+        } else if (vaa < 0.0 && sR > 0.0) {
+          const double dh0 = prem * pow(ep_max(cash, cmin), -gamma);
+          const double dh1 = prem * pow(ep_max(cash + prem * k_hi, cmin), -gamma) + vaa * (sR * sR) * k_hi;
+          if (isfinite(dh0) && isfinite(dh1)) {
+            if (dh0 <= 0.0) {
+              k = 0.0;
+            } else if (dh1 >= 0.0) {
+              k = k_hi;
+            } else {
+              double lo = 0.0, hi = k_hi;
+              for (int it = 0; it < 40; ++it) {
+                const double mid = (lo + hi) / 2.0;
+                const double dh = prem * pow(ep_max(cash + prem * mid, cmin), -gamma) + vaa * (sR * sR) * mid;
+                if (dh > 0.0) lo = mid; else hi = mid;
+              }
+              k = (lo + hi) / 2.0;
+            }
+          } else {
+            k = 0.0;
+          }
+        } else {
+          const double c0 = ep_max(cash, cmin);
+          const double c1 = ep_max(cash + prem * k_hi, cmin);
+          const double h0 = pow(c0, 1 - gamma) / (1 - gamma);
+          const double h1 = pow(c1, 1 - gamma) / (1 - gamma) + 0.5 * vaa * (sR * sR) * (k_hi * k_hi);
+          k = h1 > h0 ? k_hi : 0.0;
+        }
+        c = ep_max(cash + prem * k, cmin);
+        va = pow(c, -gamma);
+        mua = 0.0;
+      }
+    }
+    const double siga = k * sR;
+    out[0] = -(pow(c, 1 - gamma) / (1 - gamma) + va * mua + 0.5 * vaa * (siga * siga) + vy * m.muy +
+               0.5 * vyy * (m.sigma_y * m.sigma_y) - m.rho * v);
+    if (SAVE) {
+      sv[0] = v; sv[1] = c; sv[2] = k; sv[3] = va; sv[4] = vaa; sv[5] = vy; sv[6] = m.y; sv[7] = m.a; sv[8] = mua;
+    }
+  }
+};
+
 // X-macro: the registry order defines the model ids of the C ABI.
 #define ECONPDES_FOR_EACH_MODEL(X) \
   X(ReadmeLinear)                  \
@@ -972,6 +1073,7 @@ struct Gomez : ModelDefaults {
   X(Wachter)                       \
   X(Haddad)                        \
   X(BoltonChenWang)                \
-  X(Gomez)
+  X(Gomez)                         \
+  X(AhlmRiskyAsset)
 
 }  // namespace econpdes

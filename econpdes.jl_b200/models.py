@@ -355,6 +355,25 @@ class GomezModel(RegisteredModel):
 
 
 @dataclass(frozen=True)
+class AchdouHanLasryLionsMollModel_RiskyAsset(RegisteredModel):
+    """examples/consumption_saving/consumption_saving_risky_asset.jl:19-30."""
+    kappa_y: float = 0.1
+    ybar: float = 1.0
+    sigma_y: float = 0.07
+    r: float = 0.03
+    muR: float = 0.04
+    sigmaR: float = 0.1
+    rho: float = 0.05
+    gamma: float = 2.0
+    amin: float = 0.0
+    amax: float = 300.0
+    name: ClassVar[str] = "ahlm_risky_asset"
+    statenames: ClassVar = ("y", "a")
+    solnames: ClassVar = ("v",)
+    savednames: ClassVar = ("v", "c", "k", "va", "vaa", "vy", "y", "a", "mua")
+
+
+@dataclass(frozen=True)
 class NeoclassicalGrowthModel(RegisteredModel):
     """examples/neoclassical_growth.jl:25-31."""
     A: float = 0.5
@@ -425,4 +444,4 @@ ALL_MODELS = (ReadmeLinear, CampbellCochraneModel, BansalYaronModel, AchdouHanLa
               ForwardPrice, VMinusTwo, Hjb2dRegimes, TuckmanVilaModel, DiTellaModel,
               AchdouHanLasryLionsMollModel_TwoStates, GarleanuPanageasModel, LelandModel,
               WangWangYangModel, LinearUpwindTest, HeKrishnamurthyModel, WachterModel, HaddadModel,
-              BoltonChenWangModel, GomezModel)
+              BoltonChenWangModel, GomezModel, AchdouHanLasryLionsMollModel_RiskyAsset)

@@ -59,6 +59,14 @@ end
 #          Float64[m.yl, m.yh, m.λlh, m.λhl, m.r, m.ρ, m.γ, m.amin, m.amax], (:cl, :ch, :μla, :μha))
 #      CUDAModel(m::TuckmanVilaModel) = CUDAModel(m, "tuckman_vila", Float64[m.c, m.r, m.ρ, m.σ, m.a, m.T], ())
 #          (a three-argument body pde(state, u, τ): only the method with a time grid applies, as in the reference)
+#      CUDAModel(m::WachterModel) = CUDAModel(m, "wachter", Float64[m.μ, m.σ, m.λbar, m.κλ, m.νλ, mean(m.ZDistribution),
+#          std(m.ZDistribution), m.ρ, m.γ, m.ψ, m.ϕ, mgf(m.ZDistribution, 1), mgf(m.ZDistribution, -m.γ),
+#          mgf(m.ZDistribution, 1 - m.γ)], ())      (the three mgf values ride along as parameters: any ZDistribution works)
+#      CUDAModel(m::GomezModel) = CUDAModel(m, "gomez", Float64[m.γ, m.ψ, m.ρ, m.ρE, m.αE, m.ν, m.η, m.δ, m.ϕ, m.πE, m.g, m.σ,
+#          m.λ, m.τ], (:x, :μx, :σx, :κ, :r, :σWH, :μWH, :σp, :p, :px, :σR, :μR, :μRλ, :σRλ, :μErelative, :σErelative,
+#          :μHrelative, :σHrelative, :μCE, :μxW, :σxW, :pH, :μCH, :wedge, :xW, :σWE, :σCH, :αE, :pE, :μp))
+#      likewise "he_krishnamurthy", "haddad", "bolton_chen_wang", "ahlm_risky_asset", "leland", "wang_wang_yang":
+#      parameters in the field order of the example's struct, saved names in the order of the body's second NamedTuple.
 
 last_error() = unsafe_string(ccall((:econpdes_last_error, lib), Cstring, ()))
 

@@ -880,6 +880,140 @@ def gomez_problem(n=300, **over):
     return {"x": julia_range(0.0, 1.0, n) ** 2}, {"pH": np.ones(n)}, prm
 
 
+_LIBM = None
+
+
+def _cpow(x: float, y: float) -> float:
+    """libm pow on scalars (inf/nan instead of Python's exceptions; Julia's `^` on Float64 has the same edge cases)."""
+    global _LIBM
+    if _LIBM is None:
+        import ctypes
+        import ctypes.util
+        _LIBM = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
+        _LIBM.pow.restype = ctypes.c_double
+        _LIBM.pow.argtypes = [ctypes.c_double, ctypes.c_double]
+    return _LIBM.pow(x, y)
+
+
+def pointwise(scalar_pde, statenames, fields, outname, savednames):
+    """Wraps a scalar per-point body (a literal restatement of a branchy Julia body) as the vectorised callable
+    `Problem` expects: loops over the grid points exactly like `pde!` (src/pdesolve.jl:436-462)."""
+    def pde(state, u):
+        shape = np.shape(u[fields[0]])
+        st = [np.broadcast_to(state[k], shape).ravel() for k in statenames]
+        uu = [np.broadcast_to(u[k], shape).ravel() for k in fields]
+        n = uu[0].shape[0]
+        out = np.empty(n)
+        sv = np.empty((len(savednames), n))
+        for i in range(n):
+            out[i], sv[:, i] = scalar_pde(*[float(x[i]) for x in st], *[float(x[i]) for x in uu])
+        return {outname: out.reshape(shape)}, {k: sv[j].reshape(shape) for j, k in enumerate(savednames)}
+    return pde
+
+
+RISKY_SAVED = ("v", "c", "k", "va", "vaa", "vy", "y", "a", "mua")
+RISKY_DEFAULT = dict(kappa_y=0.1, ybar=1.0, sigma_y=0.07, r=0.03, muR=0.04, sigmaR=0.1, rho=0.05, gamma=2.0,
+                     amin=0.0, amax=300.0)
+_SQRT_EPS = math.sqrt(np.finfo(float).eps)
+
+
+def ahlm_risky_asset(kappa_y, ybar, sigma_y, r, muR, sigmaR, rho, gamma, amin, amax):
+    """examples/consumption_saving/consumption_saving_risky_asset.jl:84-192: consumption-saving with a risky asset
+    (portfolio constraint 0 <= k <= a - amin); scalar restatement, statement by statement."""
+    isfinite = math.isfinite
+
+    def clamp(x, lo, hi):
+        return hi if x > hi else (lo if x < lo else x)
+
+    def body(y, a, v, vy_up, vy_down, va_up, va_down, vyy, vaa):
+        muy = kappa_y * (ybar - y)
+        cash = y + r * a
+        prem = muR - r
+        kmax = max(a - amin, 0.0)
+        cmax = max(100.0 * (y + r * max(a, 0.0)), _SQRT_EPS)
+        cmin = _SQRT_EPS
+        if a == amax or abs(a - amax) <= _SQRT_EPS * max(abs(a), abs(amax)):      # a ≈ amax
+            va_tail = va_down if (isfinite(va_down) and va_down > 0.0) else va_up
+            vaa = -gamma * va_tail / a
+        vy = vy_up if muy >= 0 else vy_down
+
+        def policy_candidate(va_c):
+            c_c = clamp(_cpow(va_c, -1 / gamma), cmin, cmax) if va_c > 0.0 else cmax
+            H_kmax = prem * va_c * kmax + 0.5 * vaa * sigmaR ** 2 * kmax ** 2
+            k_c = kmax if H_kmax > 0.0 else 0.0
+            if va_c > 0.0 and vaa < 0.0:
+                k_merton = clamp(-prem * va_c / (sigmaR ** 2 * vaa), 0.0, kmax)
+                H_merton = prem * va_c * k_merton + 0.5 * vaa * sigmaR ** 2 * k_merton ** 2
+                H_candidate = prem * va_c * k_c + 0.5 * vaa * sigmaR ** 2 * k_c ** 2
+                k_c = k_merton if H_merton >= H_candidate else k_c
+            return c_c, k_c, cash + prem * k_c - c_c
+
+        c_up, k_up, mua_up = policy_candidate(va_up)
+        if mua_up >= 0.0:
+            va, c, k, mua = va_up, c_up, k_up, mua_up
+        else:
+            c_down, k_down, mua_down = policy_candidate(va_down)
+            if (mua_down <= 0.0) and (a > amin):
+                va, c, k, mua = va_down, c_down, k_down, mua_down
+            else:
+                k_hi = kmax
+                if prem < 0.0:
+                    k_hi = min(k_hi, max((cash - cmin) / (-prem), 0.0))
+                if k_hi == 0.0 or not (isfinite(cash) and isfinite(prem) and isfinite(vaa) and isfinite(sigmaR)):
+                    k = 0.0
+                elif vaa < 0.0 and sigmaR > 0.0:
+                    dh0 = prem * _cpow(max(cash, cmin), -gamma)
+                    dh1 = prem * _cpow(max(cash + prem * k_hi, cmin), -gamma) + vaa * sigmaR ** 2 * k_hi
+                    if isfinite(dh0) and isfinite(dh1):
+                        if dh0 <= 0.0:
+                            k = 0.0
+                        elif dh1 >= 0.0:
+                            k = k_hi
+                        else:
+                            lo, hi = 0.0, k_hi
+                            for _ in range(40):
+                                mid = (lo + hi) / 2.0
+                                dh = prem * _cpow(max(cash + prem * mid, cmin), -gamma) + vaa * sigmaR ** 2 * mid
+                                if dh > 0.0:
+                                    lo = mid
+                                else:
+                                    hi = mid
+                            k = (lo + hi) / 2.0
+                    else:
+                        k = 0.0
+                else:
+                    c0 = max(cash, cmin)
+                    c1 = max(cash + prem * k_hi, cmin)
+                    h0 = _cpow(c0, 1 - gamma) / (1 - gamma)
+                    h1 = _cpow(c1, 1 - gamma) / (1 - gamma) + 0.5 * vaa * sigmaR ** 2 * k_hi ** 2
+                    k = k_hi if h1 > h0 else 0.0
+                c = max(cash + prem * k, cmin)
+                va = _cpow(c, -gamma)
+                mua = 0.0
+        siga = k * sigmaR
+        vt = -(_cpow(c, 1 - gamma) / (1 - gamma) + va * mua + 0.5 * vaa * siga ** 2 + vy * muy + 0.5 * vyy * sigma_y ** 2
+               - rho * v)
+        return vt, (v, c, k, va, vaa, vy, y, a, mua)
+    return pointwise(body, ("y", "a"), ("v", "vy_up", "vy_down", "va_up", "va_down", "vyy", "vaa"), "vt", RISKY_SAVED)
+
+
+def ahlm_risky_asset_problem(n_y=5, n_a=150, params=None):
+    """Grid, guess and boundary derivatives of the example (consumption_saving_risky_asset.jl:41-68, 199-200)."""
+    from scipy import stats
+    prm = dict(RISKY_DEFAULT if params is None else params)
+    shape = 2 * prm["kappa_y"] * prm["ybar"] / prm["sigma_y"] ** 2
+    scale = prm["sigma_y"] ** 2 / (2 * prm["kappa_y"])
+    ys = julia_range(stats.gamma.ppf(0.001, shape, scale=scale), stats.gamma.ppf(0.999, shape, scale=scale), n_y)
+    as_ = prm["amin"] + (prm["amax"] - prm["amin"]) * julia_range(0.0, 1.0, n_a) ** 2
+    g, rr = prm["gamma"], prm["r"]
+    prem = prm["muR"] - rr
+    cshare = (prm["rho"] - rr) / g + rr - (1 - g) * prem ** 2 / (2 * g ** 2 * prm["sigmaR"] ** 2)
+    Y, A = np.meshgrid(ys, as_, indexing="ij")
+    guess = cshare ** (-g) * (A + Y / rr) ** (1 - g) / (1 - g)
+    bc = {"va": ((ys + rr * prm["amin"]) ** (-g), np.full(n_y, cshare ** (-g) * prm["amax"] ** (-g)))}
+    return {"y": ys, "a": as_}, {"v": guess}, prm, bc
+
+
 def v_minus_two():
     """test/runtests.jl:227: vt = v - 2."""
     def pde(state, u):

@@ -623,6 +623,24 @@ def test_gomez_example_thirty_saved_outputs():
     np.testing.assert_allclose(res.saved["sigmaR"][[0, -1]], prm["sigma"], rtol=1e-12)   # no amplification at x = 0, 1
 
 
+def test_risky_asset_consumption_saving_example():
+    """examples/consumption_saving/consumption_saving_risky_asset.jl at its default 5 x 150 grid (squared wealth
+    spacing): portfolio choice with constraint candidates and a zero-drift bisection inside the body, a curvature
+    override at the top of the wealth grid, boundary rows for (v, a) only, nine saved outputs."""
+    g, gu, prm, bc = OM.ahlm_risky_asset_problem()
+    ora = eo.pdesolve(OM.ahlm_risky_asset(**prm), g, gu, bc=bc)
+    res = E.pdesolve(PM.AchdouHanLasryLionsMollModel_RiskyAsset(**prm), g, gu, bc=bc, verbose=False)
+    assert res.converged and ora.converged
+    np.testing.assert_allclose(res.solution["v"], ora.solution["v"], rtol=1e-7)
+    assert res.residual_norm <= 1.5e-8 and ora.residual_norm <= 1.5e-8
+    assert [r["status"] for r in res.log] == [r[3] for r in ora.log.rows]
+    for k in ("c", "k", "va", "mua", "vy"):
+        np.testing.assert_allclose(res.saved[k], ora.saved[k], rtol=1e-5, atol=1e-7, err_msg=k)
+    k, a = res.saved["k"], res.saved["a"]
+    assert (k >= 0).all() and (k <= np.maximum(a - prm["amin"], 0) + 1e-12).all()      # portfolio constraint
+    assert (k[:, 0] == 0).all() and (res.saved["mua"][:, 0] >= 0).all()                # borrowing limit
+
+
 def test_garleanu_panageas_example_four_unknowns():
     """examples/asset_pricing/garleanu_panageas.jl at its default grid (100 points): four coupled unknowns ->
     4 x 4 block-tridiagonal Newton systems, two-pass upwinding, saved interest rate and price of risk."""

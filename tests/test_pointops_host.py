@@ -62,6 +62,8 @@ def _cases():
     g, gu, prm = OM.gomez_problem(50)
     gu = {"pH": 6.0 + 25.0 * g["x"]}
     out.append(("gomez", PM.GomezModel(**prm), OM.gomez(**prm), g, gu))
+    g, gu, prm, _ = OM.ahlm_risky_asset_problem(5, 24)
+    out.append(("risky", PM.AchdouHanLasryLionsMollModel_RiskyAsset(**prm), OM.ahlm_risky_asset(**prm), g, gu))
     # three-argument body: the host emulation leaves the time slot at 0
     g, gu, _, prm = OM.tuckman_vila_problem(zn=50)
     tv = OM.tuckman_vila(**prm)
@@ -105,6 +107,31 @@ def test_residual_with_bc_matches_oracle():
     prob = eo.Problem(om, ("x", "y", "z"), grids, ("v",), bc)
     want = prob.G(y.reshape(-1, order="F")).reshape(y.shape, order="F")
     np.testing.assert_array_equal(EU.residual(pm, grids, y, bc=bc), want)
+
+
+def test_risky_asset_with_its_boundary_rows_is_bit_exact():
+    """consumption_saving_risky_asset.jl:199-200 sets bc for (v, a) only: the slots of the a-boundary rows are also
+    what the y-direction stencils read at the grid corners (one slot per point, src/pdesolve.jl:312-335).  The host
+    build of the functor and the scalar oracle call the same libm pow, so residual and saved outputs agree to the bit."""
+    from econpdes_b200.pdesolve import _bc_array
+    _, pm, om, g, gu = [c for c in CASES if c[0] == "risky"][0]
+    _, _, _, bc = OM.ahlm_risky_asset_problem(5, 24)
+    grids = list(g.values())
+    S = tuple(len(x) for x in grids)
+    bca = _bc_array(bc, ("v",), ("y", "a"), S)
+    np.testing.assert_array_equal(bca, eo.bc_array(bc, ("v",), ("y", "a"), S))
+    assert bca[0, 0, 0] != 0 and bca[-1, -1, 0] != 0 and (bca[:, 1:-1] == 0).all()
+    for seed in (1, 2, 3):
+        y = _perturbed(gu, seed=seed)
+        prob = eo.Problem(om, tuple(g), grids, tuple(gu), bca)
+        want = prob.G(y.reshape(-1, order="F")).reshape(y.shape, order="F")
+        sv = prob.saved(y.reshape(-1, order="F"))
+        got, gsv = EU.residual(pm, grids, y, bc=bca, saved=True)
+        np.testing.assert_array_equal(got, want)
+        for k, key in enumerate(pm.savednames):
+            np.testing.assert_array_equal(gsv[..., k], sv[key], err_msg=key)
+    # the three upwind cases and the zero-drift bisection are all exercised by the last perturbed field
+    assert (sv["mua"] > 0).any() and (sv["mua"] < 0).any() and (sv["mua"] == 0).any()
 
 
 def test_saved_outputs_match_oracle():
