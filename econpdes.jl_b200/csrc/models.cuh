@@ -1047,6 +1047,37 @@ struct AhlmRiskyAsset : ModelDefaults {
   }
 };
 
+// test/runtests.jl:422-431 (residual-growth guard): vt = a v - k v^3 at every grid point (the reference's
+// scalar hump!(ydot, y) = y - y^3 with a = k = 1); no derivative enters, so the Jacobian is diagonal.
+struct PointwiseCubic : ModelDefaults {
+  static constexpr int N = 1, F = 1, NPARAMS = 2, NSAVED = 0;
+  static constexpr bool USES_CROSS = false;
+  static const char* name() { return "pointwise_cubic"; }
+  struct Pre { double a, k; };
+  EP_HD static void prepare(const double* prm, const double*, Pre& c) { c.a = prm[0]; c.k = prm[1]; }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<1>* u, double* out, double*) {
+    const double v = u[0].v;
+    out[0] = c.a * v - c.k * (v * v * v);
+  }
+};
+
+// test/runtests.jl:403-411 (mixed_residual!: ydot = (y1 - 2, 3 - y2), Δ = [1, -1]) and :456-489 (residual!:
+// ydot = (2 y1 - 4, y2 - 3); one implicit step with an algebraic second row gives (4/3, 3); bounds give (1, 3)):
+// two uncoupled affine rows vt = a1 v + b1, pt = a2 p + b2 at every grid point.
+struct AffinePair : ModelDefaults {
+  static constexpr int N = 1, F = 2, NPARAMS = 4, NSAVED = 0;
+  static constexpr bool USES_CROSS = false;
+  static const char* name() { return "affine_pair"; }
+  struct Pre { double a1, b1, a2, b2; };
+  EP_HD static void prepare(const double* prm, const double*, Pre& c) { c.a1 = prm[0]; c.b1 = prm[1]; c.a2 = prm[2]; c.b2 = prm[3]; }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<1>* u, double* out, double*) {
+    out[0] = c.a1 * u[0].v + c.b1;
+    out[1] = c.a2 * u[1].v + c.b2;
+  }
+};
+
 // X-macro: the registry order defines the model ids of the C ABI.
 #define ECONPDES_FOR_EACH_MODEL(X) \
   X(ReadmeLinear)                  \
@@ -1074,6 +1105,8 @@ struct AhlmRiskyAsset : ModelDefaults {
   X(Haddad)                        \
   X(BoltonChenWang)                \
   X(Gomez)                         \
-  X(AhlmRiskyAsset)
+  X(AhlmRiskyAsset)                \
+  X(PointwiseCubic)                \
+  X(AffinePair)
 
 }  // namespace econpdes

@@ -374,6 +374,29 @@ class AchdouHanLasryLionsMollModel_RiskyAsset(RegisteredModel):
 
 
 @dataclass(frozen=True)
+class PointwiseCubic(RegisteredModel):
+    """test/runtests.jl:422-431: `hump!(ydot, y) = y - y^3` at every grid point (a = k = 1)."""
+    a: float = 1.0
+    k: float = 1.0
+    name: ClassVar[str] = "pointwise_cubic"
+    statenames: ClassVar = ("x",)
+    solnames: ClassVar = ("v",)
+
+
+@dataclass(frozen=True)
+class AffinePair(RegisteredModel):
+    """test/runtests.jl:403-411 (`mixed_residual!`: a1, b1, a2, b2 = 1, -2, -1, 3) and :456-489
+    (`residual!`: 2, -4, 1, -3): vt = a1 v + b1, pt = a2 p + b2 at every grid point."""
+    a1: float = 1.0
+    b1: float = -2.0
+    a2: float = -1.0
+    b2: float = 3.0
+    name: ClassVar[str] = "affine_pair"
+    statenames: ClassVar = ("x",)
+    solnames: ClassVar = ("v", "p")
+
+
+@dataclass(frozen=True)
 class NeoclassicalGrowthModel(RegisteredModel):
     """examples/neoclassical_growth.jl:25-31."""
     A: float = 0.5
@@ -444,4 +467,5 @@ ALL_MODELS = (ReadmeLinear, CampbellCochraneModel, BansalYaronModel, AchdouHanLa
               ForwardPrice, VMinusTwo, Hjb2dRegimes, TuckmanVilaModel, DiTellaModel,
               AchdouHanLasryLionsMollModel_TwoStates, GarleanuPanageasModel, LelandModel,
               WangWangYangModel, LinearUpwindTest, HeKrishnamurthyModel, WachterModel, HaddadModel,
-              BoltonChenWangModel, GomezModel, AchdouHanLasryLionsMollModel_RiskyAsset)
+              BoltonChenWangModel, GomezModel, AchdouHanLasryLionsMollModel_RiskyAsset, PointwiseCubic,
+              AffinePair)

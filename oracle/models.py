@@ -1014,6 +1014,22 @@ def ahlm_risky_asset_problem(n_y=5, n_a=150, params=None):
     return {"y": ys, "a": as_}, {"v": guess}, prm, bc
 
 
+def pointwise_cubic(a=1.0, k=1.0):
+    """test/runtests.jl:422-431: hump!(ydot, y) = y - y^3, at every grid point."""
+    def pde(state, u):
+        v = u["v"]
+        return {"vt": a * v - k * (v * v * v) + 0.0 * state["x"]}
+    return pde
+
+
+def affine_pair(a1=1.0, b1=-2.0, a2=-1.0, b2=3.0):
+    """test/runtests.jl:403-411 and :456-489: two uncoupled affine rows at every grid point."""
+    def pde(state, u):
+        z = 0.0 * state["x"]
+        return {"vt": a1 * u["v"] + b1 + z, "pt": a2 * u["p"] + b2 + z}
+    return pde
+
+
 def v_minus_two():
     """test/runtests.jl:227: vt = v - 2."""
     def pde(state, u):

@@ -220,6 +220,65 @@ def test_mcp_lower_bound_known_answer():
     np.testing.assert_allclose(res.solution["v"], 2.0)
 
 
+def test_residual_growth_guard_hump():
+    """test/runtests.jl:422-431: ydot = y - y^3 from 0.6 with Δ = 0.1.  The default guard rides through the hump of
+    |y - y^3| at 1/sqrt(3) and converges to the root at 0; max_residual_growth = 1 rejects every step and the time
+    step deadlocks at minΔ."""
+    g = {"x": OM.julia_range(0, 1, 3)}
+    guess = {"v": np.full(3, 0.6)}
+    res = E.pdesolve(PM.PointwiseCubic(), g, guess, Δ=0.1, verbose=False)
+    assert res.converged and res.residual_norm <= eo.SQRT_EPS
+    np.testing.assert_allclose(res.solution["v"], 0.0, atol=1e-6)
+    _check_against(res, eo.pdesolve(OM.pointwise_cubic(), g, guess, delta=0.1))
+    with pytest.warns(UserWarning, match="fell below `minΔ`"):
+        strict = E.pdesolve(PM.PointwiseCubic(), g, guess, Δ=0.1, max_residual_growth=1.0, verbose=False)
+    ora = eo.pdesolve(OM.pointwise_cubic(), g, guess, delta=0.1, max_residual_growth=1.0)
+    assert not strict.converged and not ora.converged and not (strict.residual_norm <= eo.SQRT_EPS)
+    assert strict.n_outer == ora.log.n_outer == 9
+    assert [r["status"] for r in strict.log][:8] == [r[3] for r in ora.log.rows][:8] == [1] * 8      # rejected: residual grew
+    assert all(r["status"] != 0 for r in strict.log)
+    np.testing.assert_array_equal(strict.solution["v"], guess["v"])                    # every step reverted
+    assert abs(strict.residual_norm - ora.residual_norm) <= 1e-12
+    strict = E.pdesolve(PM.PointwiseCubic(), g, guess, Δ=0.1, max_residual_growth=1.0, verbose=False, warn=False)
+    assert not strict.converged
+
+
+def test_finiteschemesolve_testsets_as_pointwise_models():
+    """test/runtests.jl:403-416 (vector and negative Δ) and :456-489 (known answers of `finiteschemesolve` /
+    `implicit_timestep` with an algebraic row and with bounds), with the two-row residuals evaluated at every point
+    of a 3-point grid."""
+    g = {"x": OM.julia_range(0, 1, 3)}
+    z = {"v": np.zeros(3), "p": np.zeros(3)}
+    mixed = dict(a1=1.0, b1=-2.0, a2=-1.0, b2=3.0)          # mixed_residual!: backward row, forward-relaxed row
+    res = E.pdesolve(PM.AffinePair(**mixed), g, z, Δ={"v": 1.0, "p": -1.0}, verbose=False)
+    assert res.converged and res.residual_norm <= 1e-6
+    np.testing.assert_allclose(res.solution["v"], 2.0, atol=1e-6)
+    np.testing.assert_allclose(res.solution["p"], 3.0, atol=1e-6)
+    _check_against(res, eo.pdesolve(OM.affine_pair(**mixed), g, z, delta={"v": 1.0, "p": -1.0}))
+    neg = dict(a1=0.0, b1=0.0, a2=-1.0, b2=3.0)             # a negative scalar Δ relaxes every equation forward
+    res = E.pdesolve(PM.AffinePair(**neg), g, z, Δ=-1.0, verbose=False)
+    assert res.converged
+    np.testing.assert_allclose(res.solution["p"], 3.0, atol=1e-6)
+    with pytest.raises(E.EconPDEsCudaError):
+        E.pdesolve(PM.AffinePair(**mixed), g, z, Δ=0.0, verbose=False)
+    lin = dict(a1=2.0, b1=-4.0, a2=1.0, b2=-3.0)            # residual!: ydot = (2 y1 - 4, y2 - 3)
+    res = E.pdesolve(PM.AffinePair(**lin), g, z, Δ=INF, verbose=False)
+    assert res.converged and res.residual_norm <= 1e-8
+    np.testing.assert_allclose(res.solution["v"], 2.0, rtol=1e-12)
+    np.testing.assert_allclose(res.solution["p"], 3.0, rtol=1e-12)
+    # one implicit step of size 1 with an algebraic second row: 2 y - 4 + y = 0 and y2 = 3
+    res = E.pdesolve(PM.AffinePair(**lin), g, z, Δ=1.0, maxiters=1, is_algebraic={"v": False, "p": True}, verbose=False, warn=False)
+    np.testing.assert_allclose(res.solution["v"], 4 / 3, atol=1e-8)
+    np.testing.assert_allclose(res.solution["p"], 3.0, atol=1e-8)
+    ora = eo.pdesolve(OM.affine_pair(**lin), g, z, delta=1.0, maxiters=1, is_algebraic={"v": False, "p": True})
+    assert abs(res.residual_norm - ora.residual_norm) <= 1e-12 and res.log[0]["newton_iters"] == ora.log.rows[0][4]
+    res = E.pdesolve(PM.AffinePair(**lin), g, z, Δ=INF, lower_bound={"v": 0.0, "p": 0.0},
+                     upper_bound={"v": 1.0, "p": 10.0}, verbose=False)
+    assert res.residual_norm <= 1e-8
+    np.testing.assert_allclose(res.solution["v"], 1.0, atol=1e-12)
+    np.testing.assert_allclose(res.solution["p"], 3.0, atol=1e-12)
+
+
 def test_linear_sum_1d_inf_step():
     g = {"x": OM.julia_range(0, 1, 33)}
     res = E.pdesolve(PM.LinearSum1D(), g, {"v": np.zeros(33)}, Δ=INF, verbose=False)

@@ -64,6 +64,10 @@ def _cases():
     out.append(("gomez", PM.GomezModel(**prm), OM.gomez(**prm), g, gu))
     g, gu, prm, _ = OM.ahlm_risky_asset_problem(5, 24)
     out.append(("risky", PM.AchdouHanLasryLionsMollModel_RiskyAsset(**prm), OM.ahlm_risky_asset(**prm), g, gu))
+    g = {"x": OM.julia_range(0, 1, 4)}
+    out.append(("cubic", PM.PointwiseCubic(), OM.pointwise_cubic(), g, {"v": np.full(4, 0.6)}))
+    out.append(("affine", PM.AffinePair(2.0, -4.0, 1.0, -3.0), OM.affine_pair(2.0, -4.0, 1.0, -3.0), g,
+                {"v": np.ones(4), "p": 2.0 * np.ones(4)}))
     # three-argument body: the host emulation leaves the time slot at 0
     g, gu, _, prm = OM.tuckman_vila_problem(zn=50)
     tv = OM.tuckman_vila(**prm)
