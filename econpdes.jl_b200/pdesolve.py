@@ -68,6 +68,18 @@ class EconPDEResult:
         # (src/EconPDEs.jl:44-48); a NaN residual is not converged
         return bool(np.all(np.asarray(self.residual_norm) <= self.tolerance))
 
+    @property
+    def zero(self):  # src/EconPDEs.jl:49-51: deprecated 1.x alias
+        import warnings
+        warnings.warn("`result.zero` is deprecated; use `result.solution` instead.", DeprecationWarning, stacklevel=2)
+        return self.solution
+
+    @property
+    def optional(self):  # src/EconPDEs.jl:52-54: deprecated 1.x alias
+        import warnings
+        warnings.warn("`result.optional` is deprecated; use `result.saved` instead.", DeprecationWarning, stacklevel=2)
+        return self.saved
+
     def __iter__(self):  # tuple destructuring: solution, residual_norm, saved = result
         return iter((self.solution, self.residual_norm, self.saved))
 
@@ -189,6 +201,13 @@ def _options(abstol, maxiters, kw) -> L.Options:
         if k in names:
             setattr(o, names[k], kw.pop(k))
     return o
+
+
+def _problem_description(ynames, statenames, S) -> str:
+    """src/pdesolve.jl:227-231, e.g. "2 unknowns (pA, pB) on grid x×y×z = 2×3×4"."""
+    n = len(ynames)
+    return "%d %s (%s) on grid %s = %s" % (n, "unknown" if n == 1 else "unknowns", ", ".join(ynames),
+                                           "×".join(statenames), "×".join(str(s) for s in S))
 
 
 def _print_log(res: EconPDEResult, description: str, file):
@@ -375,8 +394,7 @@ def pdesolve(pde, grid, guess, taus=None, *, is_algebraic=None, bc=None, lower_b
     for txt in _diagnostic_warnings(res, ynames):   # src/monotonicity.jl (emitted regardless of `warn`, like @warn there)
         warnings.warn(txt)
     if verbose:
-        desc = "%d %s (%s) on grid %s = %s" % (F, "unknown" if F == 1 else "unknowns", ", ".join(ynames),
-                                               "×".join(statenames), "×".join(str(s) for s in S))
+        desc = _problem_description(ynames, statenames, S)
         _print_log(res, desc, file or sys.stdout)
         if res.exit_reason == L.EXIT_ALREADY_ZERO:
             warnings.warn("G! already returns zero with the initial value")
@@ -412,8 +430,7 @@ def _solve_backward(lib, p, opts, taus, pde, S, F, ynames, statenames, abstol, v
     res = EconPDEResult(solution, rn, sv, abstol, L.EXIT_CONVERGED, (), nt - 1, int(nit.sum()), 0,
                         launches.value, ms.value)
     if verbose:
-        desc = "%d %s (%s) on grid %s = %s" % (F, "unknown" if F == 1 else "unknowns", ", ".join(ynames),
-                                               "×".join(statenames), "×".join(str(s) for s in S))
+        desc = _problem_description(ynames, statenames, S)
         print("Solving for %s, backward from τ = %g to %g (%d steps)" % (desc, taus[-1], taus[0], nt - 1), file=file)
         print("    Time Residual", file=file)
         print("-------- --------", file=file)

@@ -115,6 +115,32 @@ def test_host_side_normalisation_errors():
         _check_generated_names(["k", "a"], ["v", "vk"])
 
 
+def test_result_object_surface():
+    """src/EconPDEs.jl:36-95 and test/runtests.jl:66-85: computed `converged`, the deprecated 1.x aliases,
+    tuple destructuring and the compact `show` (names and sizes, not the arrays)."""
+    from collections import OrderedDict
+    from econpdes_b200.pdesolve import EconPDEResult
+    sol = OrderedDict(v=np.arange(200.0))
+    saved = OrderedDict(v=sol["v"], c=np.ones(200))
+    res = EconPDEResult(sol, 1e-9, saved, eo.SQRT_EPS)
+    assert res.converged and not EconPDEResult(sol, float("nan"), saved, eo.SQRT_EPS).converged
+    assert not EconPDEResult(sol, np.array([0.0, 1e-3]), saved, eo.SQRT_EPS).converged      # one residual per time
+    with pytest.warns(DeprecationWarning, match=r"result\.zero"):
+        assert res.zero is res.solution
+    with pytest.warns(DeprecationWarning, match=r"result\.optional"):
+        assert res.optional is res.saved
+    solution, residual_norm, sv = res
+    assert solution is res.solution and residual_norm == res.residual_norm and sv is res.saved
+    text = repr(res)
+    assert "EconPDEResult" in text and "v (200)" in text and len(text) < 500
+    assert "converged:     true" in text
+    assert "converged:     false" in repr(EconPDEResult(sol, 1.0, saved, eo.SQRT_EPS))
+    # test/runtests.jl:179-183
+    from econpdes_b200.pdesolve import _problem_description
+    assert _problem_description(("v",), ("k",), (3,)) == "1 unknown (v) on grid k = 3"
+    assert _problem_description(("pA", "pB"), ("x", "y", "z"), (2, 3, 4)) == "2 unknowns (pA, pB) on grid x×y×z = 2×3×4"
+
+
 def test_graft_entry_build_check_passes():
     """The driver's "does it build" entry point (incremental: a no-op when the library is current)."""
     import __graft_entry__ as ge

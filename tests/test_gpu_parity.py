@@ -185,6 +185,27 @@ def test_growth_testset_properties():
     assert sol is res.solution and rn == res.residual_norm and saved is res.saved
 
 
+def test_ordered_dict_inputs_partial_bc_silence_and_warm_start(capsys):
+    """test/runtests.jl:88-98 (OrderedDict inputs; a `bc` covering the full set for `vk` with zeros is the default),
+    :162-177 (verbose = false prints nothing on success) and the reference's warm start -- a previous
+    `result.solution` passed as the guess (bolton_chen_wang.jl:93) -- against the oracle from the same array."""
+    from collections import OrderedDict
+    g, gu, _ = OM.growth_test_problem(100)
+    res = E.pdesolve(PM.GrowthTest(), OrderedDict(k=g["k"]), OrderedDict(v=gu["v"]), verbose=False)
+    assert capsys.readouterr().out == ""
+    assert res.converged and res.residual_norm <= 1e-6 and "converged:     true" in repr(res)
+    res_bc = E.pdesolve(PM.GrowthTest(), g, gu, bc={"vk": (0.0, 0.0)}, verbose=False)
+    assert res_bc.residual_norm <= 1e-6
+    np.testing.assert_array_equal(res_bc.solution["v"], res.solution["v"])
+    # resume from a half-converged state: two outer steps, then restart from that array on both sides
+    half = E.pdesolve(PM.GrowthTest(), g, gu, maxiters=2, verbose=False, warn=False)
+    assert not half.converged
+    warm = E.pdesolve(PM.GrowthTest(), g, half.solution, verbose=False)
+    _check_against(warm, eo.pdesolve(OM.growth_test_hjb(), g, half.solution))
+    assert warm.converged
+    np.testing.assert_allclose(warm.solution["v"], res.solution["v"], rtol=1e-6)
+
+
 def test_maxiters_one_warns_and_is_not_converged():
     # test/runtests.jl:162-192
     g, gu, _ = OM.growth_test_problem(50)
