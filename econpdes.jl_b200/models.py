@@ -22,6 +22,7 @@ class RegisteredModel:
     statenames: ClassVar[Tuple[str, ...]] = ()
     solnames: ClassVar[Tuple[str, ...]] = ()
     savednames: ClassVar[Tuple[str, ...]] = ()
+    derivednames: ClassVar[Tuple[str, ...]] = ()     # entries `params()` appends after the struct's fields
 
     def params(self) -> np.ndarray:
         return np.array([float(getattr(self, f.name)) for f in fields(self)], dtype=np.float64)
@@ -282,6 +283,7 @@ class WachterModel(RegisteredModel):
     name: ClassVar[str] = "wachter"
     statenames: ClassVar = ("lambda",)
     solnames: ClassVar = ("p",)
+    derivednames: ClassVar = ("mgf(Z, 1)", "mgf(Z, -gamma)", "mgf(Z, 1 - gamma)")
 
     def mgf(self, t: float) -> float:
         """Moment generating function of Normal(muZ, sigmaZ) (Distributions.jl `mgf(::Normal, t)`)."""
@@ -426,6 +428,7 @@ class GrowthTest(RegisteredModel):
 
 @dataclass(frozen=True)
 class LinearSum1D(RegisteredModel):
+    """One-state version of test/runtests.jl:276-279 (vt = x - v: known answer v = x)."""
     name: ClassVar[str] = "linear_sum_1d"
     statenames: ClassVar = ("x",)
     solnames: ClassVar = ("v",)
@@ -441,6 +444,7 @@ class LinearSum2D(RegisteredModel):
 
 @dataclass(frozen=True)
 class LinearSum3D(RegisteredModel):
+    """Three-state version of test/runtests.jl:276-279 and :314-319 (known answer v = x + z + q)."""
     name: ClassVar[str] = "linear_sum_3d"
     statenames: ClassVar = ("x", "z", "q")
     solnames: ClassVar = ("v",)

@@ -52,6 +52,16 @@ def test_model_registry_matches_python_mirror(lib):
     assert b"no_such_model" in lib.econpdes_last_error()
 
 
+def test_models_md_is_current():
+    """MODELS.md (parameter-vector layouts, saved-plane order: both part of the C ABI) is generated from the mirror."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_gen_models_md", os.path.join(ROOT, "tools", "gen_models_md.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert open(os.path.join(ROOT, "MODELS.md"), encoding="utf-8").read() == mod.render(), \
+        "run `python tools/gen_models_md.py`"
+
+
 def test_default_options_are_the_reference_keywords(lib):
     # src/finiteschemesolve.jl:343, docs/src/solver.md:286-298
     o = L.Options()
