@@ -297,3 +297,62 @@ def test_fast_division_by_grid_sizes():
     lib.emu_fastdiv_mismatches.argtypes = [ctypes.c_uint, ctypes.c_uint]
     for d in (1, 2, 3, 5, 7, 9, 50, 64, 255, 256, 257, 998, 1000, 2048, 4096, 65535, 65537, 1 << 20, (1 << 31) - 1):
         assert lib.emu_fastdiv_mismatches(d, 200000) == 0, d
+
+
+# ----------------------------------------------------------------------------------------------
+# property test: stencils on random non-uniform grids of every small shape, with boundary values
+# ----------------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_PROP_MODELS = {
+    1: (PM.ReadmeLinear(), OM.readme_linear(), ("x",), ("v",)),
+    2: (PM.Hjb2dRegimes(**OM.HJB2D_REGIMES_DEFAULT), OM.hjb2d_regimes(**OM.HJB2D_REGIMES_DEFAULT), ("x", "y"), ("v", "w")),
+    3: (PM.Hjb3dSynth(**OM.HJB3D_DEFAULT), OM.hjb3d_synth(**OM.HJB3D_DEFAULT), ("x", "y", "z"), ("v",)),
+}
+
+
+@settings(max_examples=60, deadline=None)
+@given(shape=st.lists(st.integers(min_value=2, max_value=5), min_size=1, max_size=3), seed=st.integers(0, 2 ** 31 - 1),
+       with_bc=st.booleans())
+def test_stencils_on_random_small_grids_are_bit_exact(shape, seed, with_bc):
+    """derivatives.jl:39-159 on every small shape (2 points per dimension included: both neighbours are
+    boundary ghosts there), random spacings, random fields, random boundary values: the host build of the
+    device stencils + functor equals the oracle to the last bit (upwind and cross stencils are exercised by
+    the 2-D pair and the 3-D model)."""
+    pm, om, statenames, solnames = _PROP_MODELS[len(shape)]
+    rng = np.random.default_rng(seed)
+    grids = [np.cumsum(rng.uniform(0.02, 0.3, s)) for s in shape]
+    F = len(solnames)
+    y = rng.normal(size=tuple(shape) + (F,)) + 12.0
+    bc = rng.normal(size=tuple(shape) + (F,)) if with_bc else None
+    prob = eo.Problem(om, statenames, grids, solnames, bc)
+    want = prob.G(y.reshape(-1, order="F")).reshape(y.shape, order="F")
+    np.testing.assert_array_equal(EU.residual(pm, grids, y, bc=bc), want)
+
+
+@settings(max_examples=40, deadline=None)
+@given(shape=st.lists(st.integers(min_value=2, max_value=5), min_size=1, max_size=3), seed=st.integers(0, 2 ** 31 - 1),
+       delta=st.sampled_from([1.0, 0.05, math.inf]))
+def test_fused_jacobian_on_random_small_grids(shape, seed, delta):
+    """The fused row-wise colored-FD Jacobian against FiniteDiff's global sweeps on every small shape: with 2 points
+    in a dimension there are only two colors along it (coloring.jl:52-70) and both stencil neighbours are ghosts."""
+    pm, om, statenames, solnames = _PROP_MODELS[len(shape)]
+    rng = np.random.default_rng(seed)
+    grids = [np.cumsum(rng.uniform(0.05, 0.3, s)) for s in shape]
+    S, F = tuple(shape), len(solnames)
+    y = rng.normal(size=S + (F,)) + 12.0
+    ypost = y + 0.1 * rng.normal(size=y.shape)
+    bc = rng.normal(size=S + (F,))
+    prob = eo.Problem(om, statenames, grids, solnames, bc)
+    cache = eo.JacobianCache(S, F)
+    yvec, ypvec = y.reshape(-1, order="F"), ypost.reshape(-1, order="F")
+
+    def R(v):
+        with np.errstate(all="ignore"):
+            return prob.G(v) - (ypvec - v) / delta
+    nz_want, eps = eo.finite_difference_jacobian(R, yvec, cache)
+    box = len(shape) > 1
+    planes, r0 = EU.jacobian_planes(pm, grids, y, ypost, delta, eps, box, bc=bc)
+    np.testing.assert_array_equal(r0, R(yvec))
+    nz_got = EU.planes_to_csc(planes, S, F, box, cache.colptr, cache.rowval)
+    np.testing.assert_allclose(nz_got, nz_want, rtol=0, atol=2e-6 * np.abs(nz_want).max())
