@@ -313,3 +313,50 @@ def test_diagnostics_reproduce_the_reference_testsets():
     J, S = _first_jacobian(M.linear_upwind_test(-1.0, -1.0, 1.0), {"x": R(0.0, 1.0, 5)}, {"V": R(1.0, 2.0, 5)}, 1.0)
     nchk, nwrong, cnt, _ = eo.jacobian_diagnostics(J, 1.0, None, S, 1)
     assert nchk[0] == 5 and nwrong[0] == 0 and cnt == 0
+
+
+def test_example_model_fixtures_are_what_the_oracle_produces():
+    """tests/golden/ex_*.npz (make_golden_examples.py): the committed outputs of the example models on the examples'
+    own grids are reproduced by the current oracle and model restatements -- same iteration log, solution and
+    saved outputs -- so a change in either shows up here before it reaches the device parity tests."""
+    import os
+    from tests.golden import make_golden_examples as G
+    n = 0
+    for name, pde, g, gu, prm, kw in G.cases():
+        gold = np.load(os.path.join(G.HERE, name + ".npz"))
+        res = eo.pdesolve(pde, g, gu, **kw)
+        assert bool(gold["converged"]) == res.converged and res.converged, name
+        log = gold["log"]
+        assert [int(s) for s in log[:, 3]] == [r[3] for r in res.log.rows], name
+        assert [int(s) for s in log[:, 4]] == [r[4] for r in res.log.rows], name
+        for k, v in res.solution.items():
+            np.testing.assert_allclose(v, gold["sol_" + k], rtol=1e-9, atol=1e-12, err_msg=name)
+        for k, v in res.saved.items():
+            if k not in res.solution:
+                np.testing.assert_allclose(v, gold["saved_" + k], rtol=1e-7, atol=1e-9, err_msg=f"{name}.{k}")
+        n += 1
+    assert n == 10
+
+
+def test_example_models_economic_sanity():
+    """Qualitative facts the examples' texts state, checked on the oracle solutions (the reference pins no numbers)."""
+    g, gu, prm = M.he_krishnamurthy_problem()
+    res = eo.pdesolve(M.he_krishnamurthy(**prm), g, gu)
+    kappa = res.saved["kappa"]
+    assert kappa[0] > 10 * kappa[-1]                                    # price of risk is elevated when specialists are poor
+    np.testing.assert_allclose(kappa[-1], prm["gamma"] * prm["sigma"], rtol=2e-2)
+    g, gu, prm = M.wachter_problem()
+    res = eo.pdesolve(M.wachter(**prm), g, gu)
+    assert (np.diff(res.solution["p"]) < 0).all()                        # psi > 1: valuations fall with disaster risk
+    g, gu, prm = M.gomez_problem()
+    res = eo.pdesolve(M.gomez(**prm), g, gu)
+    sR = res.saved["sigmaR"]
+    np.testing.assert_allclose(sR[[0, -1]], prm["sigma"], rtol=1e-12)    # no amplification with one type of agent
+    assert sR[1:-1].max() > 1.5 * prm["sigma"]                           # excess volatility in between
+    g, gu, prm, bc = M.ahlm_risky_asset_problem()
+    res = eo.pdesolve(M.ahlm_risky_asset(**prm), g, gu, bc=bc)
+    k, a = res.saved["k"], res.saved["a"]
+    assert (k >= 0).all() and (k <= np.maximum(a - prm["amin"], 0) + 1e-12).all() and (k[:, 0] == 0).all()
+    # consumption rises with wealth; the y-edge rows are left out: their corners read the (v, a) boundary values in the
+    # y-direction stencils too (one bc slot per point, src/pdesolve.jl:312-335)
+    assert (np.diff(res.saved["c"][1:-1], axis=1) > 0).all()
