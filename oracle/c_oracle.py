@@ -7,7 +7,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "_build", "liboracle1d.so")
-MODEL_IDS = {"readme_linear": 0, "campbell_cochrane": 1}
+MODEL_IDS = {"readme_linear": 0, "campbell_cochrane": 1, "he_krishnamurthy": 2, "wachter": 3}
 _lib = None
 
 

@@ -18,7 +18,7 @@
  *                                 (src/finiteschemesolve.jl:125-147)
  *   solve()                       finiteschemesolve + SERTimeStepController
  *                                 (src/finiteschemesolve.jl:236-275, 343-465)
- * Models: README.md:58-67 and examples/asset_pricing/campbell_cochrane.jl:66-84.
+ * Models: README.md:58-67, examples/asset_pricing/campbell_cochrane.jl:66-84, he_krishnamurthy.jl:45-92, wachter.jl:66-92.
  * Compile with -ffp-contract=off (Julia never fuses a*b+c).
  */
 #include <math.h>
@@ -52,7 +52,69 @@ static double campbell_cochrane(const double* prm, double s, double p, double ps
   return -p * (1 / p + mu + mup + sigp * sigma - r - kap * (sigma + sigp));
 }
 
-static pde_fn model(int id) { return id == 0 ? readme_linear : campbell_cochrane; }
+/* examples/asset_pricing/he_krishnamurthy.jl:45-92 (the `@goto start` second pass as a loop) */
+static double he_krishnamurthy(const double* prm, double x, double pS, double pSx_up, double pSx_down, double pSxx) {
+  const double m = prm[0], lam = prm[1], g = prm[2], sigma = prm[3], rho = prm[4], gamma = prm[5], l = prm[6];
+  double pSx = pSx_up, p, px, pxx, aI, sigx, spS, sp, sR, kappa, mux;
+  int iter = 0;
+  for (;;) {
+    p = (1 + l) / (x / pS + (1 - x) * rho);
+    px = -(1 + l) / ((x / pS + (1 - x) * rho) * (x / pS + (1 - x) * rho)) * (1 / pS - rho - x / (pS * pS) * pSx);
+    pxx = -(1 + l) / ((x / pS + (1 - x) * rho) * (x / pS + (1 - x) * rho)) *
+              (-1 / (pS * pS) * pSx - 1 / (pS * pS) * pSx - x / (pS * pS) * pSxx + 2 * x / (pS * pS * pS) * (pSx * pSx)) +
+          2 * (1 + l) / ((x / pS + (1 - x) * rho) * (x / pS + (1 - x) * rho) * (x / pS + (1 - x) * rho)) *
+              ((1 / pS - rho - x / (pS * pS) * pSx) * (1 / pS - rho - x / (pS * pS) * pSx));
+    aI = 1 / (1 - lam * (1 - x));
+    if (x * (1 + m) * aI < 1) aI = 1 / (x * (1 + m));
+    sigx = x * (aI - 1) * sigma / (1 - x * (aI - 1) * px / p);
+    spS = pSx / pS * sigx;
+    sp = px / p * sigx;
+    sR = sigma + sp;
+    kappa = gamma * (aI * sR - spS);
+    mux = x * (1 - x) * ((aI - (1 - aI * x) / (1 - x)) * kappa * sR - 1 / pS + rho - (aI - (1 - aI * x) / (1 - x)) * (sR * sR) -
+                         l / ((1 - x) * p));
+    if (iter == 0 && mux < 0) {
+      iter = 1;
+      pSx = pSx_down;
+      continue;
+    }
+    break;
+  }
+  {
+    const double mupS = pSx / pS * mux + 0.5 * pSxx / pS * (sigx * sigx);
+    const double mup = px / p * mux + 0.5 * pxx / p * (sigx * sigx);
+    const double r = 1 / p + g + mup + sigma * sp - kappa * sR;
+    const double sCS = kappa / gamma;
+    const double muCS = (r - rho) / gamma + (1 + 1 / gamma) / (2 * gamma) * (kappa * kappa);
+    return -(1 / pS + muCS + mupS + sCS * spS - r - kappa * (sCS + spS));
+  }
+}
+
+/* examples/asset_pricing/wachter.jl:66-92; prm[11..13] = mgf(Z, 1), mgf(Z, -gamma), mgf(Z, 1 - gamma) */
+static double wachter(const double* prm, double lam, double p, double pl_up, double pl_down, double pll) {
+  const double mu = prm[0], sigma = prm[1], lambar = prm[2], kappal = prm[3], nul = prm[4], rho = prm[7], gamma = prm[8],
+               psi = prm[9], m1 = prm[11], mg = prm[12], m1g = prm[13];
+  const double mul = kappal * (lambar - lam);
+  const double sigl = nul * sqrt(lam);
+  const double pl = (mul >= 0) ? pl_up : pl_down;
+  const double mup = pl / p * mul + 0.5 * pll / p * (sigl * sigl);
+  const double sp = pl / p * sigl;
+  const double kZc = gamma * sigma;
+  const double kZl = (gamma * psi - 1) / (psi - 1) * sp;
+  const double eta = lam * (m1 - 1 + mg - 1 - (m1g - 1));
+  const double r = rho + mu / psi - (1 + 1 / psi) / 2 * gamma * (sigma * sigma) - lam * (mg - 1) +
+                   (1 / psi - gamma) / (1 - gamma) * lam * (m1g - 1) - (gamma * psi - 1) / (2 * (psi - 1)) * (sp * sp);
+  return -p * (1 / p + mu + mup + lam * (m1 - 1) - r - kZc * sigma - kZl * sp - eta);
+}
+
+static pde_fn model(int id) {
+  switch (id) {
+    case 0: return readme_linear;
+    case 1: return campbell_cochrane;
+    case 2: return he_krishnamurthy;
+    default: return wachter;
+  }
+}
 
 typedef struct {
   int n;

@@ -31,3 +31,23 @@ def test_c_oracle_campbell_cochrane_and_sweep():
         ora = eo.pdesolve(M.campbell_cochrane(**p), {"s": grids[b]}, {"p": np.ones(grids.shape[1])})
         np.testing.assert_allclose(sol[b], ora.solution["p"], rtol=1e-9)
         assert no[b] == ora.log.n_outer and abs(rn[b] - ora.residual_norm) <= 1e-10
+
+
+def test_c_oracle_he_krishnamurthy_and_wachter():
+    """A third, independent restatement (plain C) of two of the example bodies, solved by the C driver, against the
+    numpy oracle: same outer steps and Newton counts, solutions to round-off of the two linear solvers."""
+    from econpdes_b200 import models as PM
+    g, gu, prm = M.he_krishnamurthy_problem()
+    P = np.array([[prm[k] for k in ("m", "lam", "g", "sigma", "rho", "gamma", "l")]])
+    sol, rn, no, nn = c_oracle.solve_batch("he_krishnamurthy", P, g["x"][None], gu["pS"][None])
+    ora = eo.pdesolve(M.he_krishnamurthy(**prm), g, gu)
+    assert no[0] == ora.log.n_outer == 4 and nn[0] == ora.log.n_newton == 21
+    np.testing.assert_allclose(sol[0], ora.solution["pS"], rtol=1e-9)
+    assert abs(rn[0] - ora.residual_norm) <= 1e-10
+    g, gu, prm = M.wachter_problem()
+    P = PM.WachterModel(**prm).params()[None]
+    sol, rn, no, nn = c_oracle.solve_batch("wachter", P, g["lambda"][None], gu["p"][None])
+    ora = eo.pdesolve(M.wachter(**prm), g, gu)
+    assert no[0] == ora.log.n_outer == 5 and nn[0] == ora.log.n_newton == 11
+    np.testing.assert_allclose(sol[0], ora.solution["p"], rtol=1e-9)
+    assert abs(rn[0] - ora.residual_norm) <= 1e-10
