@@ -3,6 +3,7 @@
 // functor and fused-Jacobian arithmetic can be checked against the oracle in the build
 // container, which has no GPU.  Not linked into libeconpdes_cuda.so; not a fallback.
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -140,6 +141,26 @@ int emu_residual(int model_id, const long long* S, const double* const* grids, c
   ECONPDES_FOR_EACH_MODEL(X)
 #undef X
   return -1;
+}
+
+// apply_row_terms (G_helper! and the min-max MCP residual, finiteschemesolve.jl:158-162, 197-203) row by row.
+// mode 0: IEEE division by delta; 1: reciprocal formed per row when delta is finite (rdelta), else division;
+// 2: reciprocal always (1/Inf = 0 included), the batched kernel's branch-free form.
+void emu_row_terms(long long n, const double* g, const double* y, const double* ypost, const double* delta,
+                   const unsigned char* is_alg, const double* lb, const double* ub, int has_bounds, int mode, double* out) {
+  for (long long i = 0; i < n; ++i) {
+    RowTerms t;
+    t.implicit = ypost != nullptr;
+    t.has_bounds = has_bounds != 0;
+    t.ypost = ypost ? ypost[i] : 0.0;
+    t.delta = delta[i];
+    t.is_alg = is_alg && is_alg[i];
+    t.lb = lb ? lb[i] : 0.0;
+    t.ub = ub ? ub[i] : 0.0;
+    if (mode == 1 && std::isfinite(delta[i])) t.rdelta = 1.0 / delta[i];
+    if (mode == 2) { t.rdelta = 1.0 / delta[i]; t.rdelta_always = true; }
+    out[i] = apply_row_terms(g[i], y[i], t);
+  }
 }
 
 // box != 0: full 3^N stencil planes; box == 0: star planes (1 + 2N)

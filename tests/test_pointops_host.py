@@ -356,3 +356,37 @@ def test_fused_jacobian_on_random_small_grids(shape, seed, delta):
     np.testing.assert_array_equal(r0, R(yvec))
     nz_got = EU.planes_to_csc(planes, S, F, box, cache.colptr, cache.rowval)
     np.testing.assert_allclose(nz_got, nz_want, rtol=0, atol=2e-6 * np.abs(nz_want).max())
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_row_terms_match_g_helper_and_minmax_mcp(mode):
+    """`apply_row_terms` against `G_helper!` (finiteschemesolve.jl:158-162: R = G - .!alg .* (ypost - y) ./ Δ with a
+    signed per-row Δ, ±Inf included) and the min-max MCP residual (:197-203: min(max(R, y - ub), y - lb), infinite
+    bounds, NaN residuals propagating like Julia's max/min), for the dividing and the two reciprocal forms."""
+    rng = np.random.default_rng(11)
+    n = 4000
+    g = rng.normal(size=n) * 10.0 ** rng.integers(-6, 6, n)
+    y = rng.normal(size=n) * 10.0 ** rng.integers(-3, 3, n)
+    ypost = y + rng.normal(size=n) * 10.0 ** rng.integers(-8, 2, n)
+    delta = rng.choice([1.0, -1.0, 0.1, 1e-9, 3.7e5, -2.5e-3, math.inf, -math.inf], size=n) * rng.uniform(0.5, 2.0, n)
+    alg = rng.random(n) < 0.2
+    lb = np.where(rng.random(n) < 0.3, -np.inf, y - rng.uniform(-1, 2, n))
+    ub = np.where(rng.random(n) < 0.3, np.inf, lb + rng.uniform(0, 3, n))
+    g[::97] = np.nan
+    g[5::191] = np.inf
+    L = EU.lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.emu_row_terms.argtypes = [ctypes.c_longlong, dp, dp, dp, dp, ctypes.POINTER(ctypes.c_ubyte), dp, dp,
+                                ctypes.c_int, ctypes.c_int, dp]
+    L.emu_row_terms.restype = None
+    a8 = np.ascontiguousarray(alg, dtype=np.uint8)
+
+    def run(bounds):
+        out = np.empty(n)
+        L.emu_row_terms(n, EU._p(g), EU._p(y), EU._p(ypost), EU._p(delta), a8.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)),
+                        EU._p(lb), EU._p(ub), int(bounds), mode, EU._p(out))
+        return out
+    with np.errstate(all="ignore"):
+        want = g - np.where(alg, 0.0, (ypost - y) / delta)
+        np.testing.assert_array_equal(run(False), want)
+        np.testing.assert_array_equal(run(True), np.minimum(np.maximum(want, y - ub), y - lb))
