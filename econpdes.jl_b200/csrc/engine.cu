@@ -679,7 +679,9 @@ int Solver::solve(const econpdes_options& opt, econpdes_result* res) {
         else if (std::isnan(o.nl)) status = ECONPDES_STEP_REJECTED_NAN;
         else if (std::isinf(o.nl)) status = ECONPDES_STEP_REJECTED_SINGULAR;
         else status = ECONPDES_STEP_REJECTED_INNER;                                   // :439
-        push_log(iter, status, o.iters, o.lin_iters, ctl.delta, std::numeric_limits<double>::quiet_NaN());
+        // growth rejections carry the factor the reference prints ("residual grew 12.3x", :433-435); others NaN
+        push_log(iter, status, o.iters, o.lin_iters, ctl.delta,
+                 status == ECONPDES_STEP_REJECTED_GROWTH ? rn / old_r : std::numeric_limits<double>::quiet_NaN());
         ctl.reject();
       }
     }

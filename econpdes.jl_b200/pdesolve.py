@@ -220,14 +220,19 @@ def _print_log(res: EconPDEResult, description: str, file):
         if row["status"] == L.STEP_ACCEPTED:
             print("%4d %8.2e %8.2e" % (row["iter"], row["delta"], row["residual"]), file=file)
         elif row["status"] == L.STEP_REJECTED_GROWTH:
-            print("%4d %8.2e        ✗ (residual grew > max_residual_growth)" % (row["iter"], row["delta"]), file=file)
+            growth = row["residual"]      # the generic engine stores residual/old_residual on these rows (:433-435)
+            text = "" if growth != growth else ("%.1f× " % growth if np.isfinite(growth) else "∞ ")
+            print("%4d %8.2e        ✗ (residual grew %s> max_residual_growth)" % (row["iter"], row["delta"], text), file=file)
         else:
             reason = {L.STEP_REJECTED_NAN: " (model returned NaN)", L.STEP_REJECTED_SINGULAR: " (singular Jacobian)"}
             print("%4d %8.2e        ✗%s" % (row["iter"], row["delta"], reason.get(row["status"], "")), file=file)
     if res.converged and res.exit_reason == L.EXIT_CONVERGED:
         ms = res.device_ms
         t = "%.0fms" % ms if ms < 1000 else "%.1fs" % (ms / 1000)
-        print("Converged after %d time steps (%s)" % (res.n_outer, t), file=file)
+        if res.n_outer == 0 and not res.log:      # one-shot solve with an infinite step (:383)
+            print("Converged (%s)" % t, file=file)
+        else:
+            print("Converged after %d time steps (%s)" % (res.n_outer, t), file=file)
 
 
 def _diagnostic_warnings(res: EconPDEResult, ynames) -> list:
@@ -260,11 +265,15 @@ def _warn_text(res: EconPDEResult, min_delta: float) -> Optional[str]:
         return None
     r, tol = "%.2e" % res.residual_norm, "%.2e" % res.tolerance
     if res.exit_reason == L.EXIT_INF_STEP_FAILED:
-        return f"did not converge: residual {r} > tolerance {tol}. `Δ = Inf` disables pseudo-transient continuation"
+        return (f"did not converge: residual {r} > tolerance {tol}. `Δ = Inf` disables pseudo-transient continuation "
+                "— try a finite initial time step `Δ`, a better initial guess, or more `maxiters`.")
     if res.exit_reason == L.EXIT_BELOW_MIN_DELTA:
         return (f"did not converge after {res.n_outer} time steps: the pseudo-transient time step fell below "
-                f"`minΔ` = {min_delta} (residual {r} > tolerance {tol}).")
-    return f"did not converge after {res.n_outer} time steps: residual {r} > tolerance {tol}."
+                f"`minΔ` = {min_delta} (residual {r} > tolerance {tol}). This usually means a non-monotone "
+                "finite-difference scheme (wrong upwind direction) or a poor initial guess — try "
+                "`check_monotonicity = true` or a better initial guess.")
+    return (f"did not converge after {res.n_outer} time steps: residual {r} > tolerance {tol}. If the residual was still "
+            "falling, increase `maxiters`; otherwise try a better initial guess or `check_monotonicity = true`.")
 
 
 def pdesolve(pde, grid, guess, taus=None, *, is_algebraic=None, bc=None, lower_bound=None, upper_bound=None,

@@ -109,7 +109,9 @@ typedef struct econpdes_log_row {
   int32_t newton_iters;
   int32_t linear_iters;  /* Krylov iterations summed over the Newton iterations of this step */
   double delta;          /* stepper.Δ printed in the TimeStep column (finiteschemesolve.jl:421) */
-  double residual;       /* ||G||_2/n at the accepted point; NaN on rejected steps */
+  double residual;       /* ||G||_2/n at the accepted point.  Rejected steps: NaN, except that the generic engine
+                            stores residual/old_residual on ECONPDES_STEP_REJECTED_GROWTH rows -- the growth factor
+                            the reference prints there (finiteschemesolve.jl:433-435; +Inf prints as "∞") */
 } econpdes_log_row;
 
 typedef struct econpdes_result {

@@ -151,6 +151,53 @@ def test_result_object_surface():
     assert _problem_description(("pA", "pB"), ("x", "y", "z"), (2, 3, 4)) == "2 unknowns (pA, pB) on grid x×y×z = 2×3×4"
 
 
+def test_verbose_table_and_warning_texts():
+    """The printer the host runs over the returned iteration log: the formats of src/finiteschemesolve.jl:403-404
+    (header), :421 (accepted row), :433-435 (growth rejection with its factor, "∞" when the residual blew up),
+    :441-445 (inner failure, NaN, singular Jacobian), :383 / :455 (closing line) and the @warn texts of :387, :459, :461."""
+    import io
+    from collections import OrderedDict
+    from econpdes_b200.pdesolve import EconPDEResult, _print_log, _warn_text
+    sol = OrderedDict(v=np.zeros(50))
+
+    def row(i, st, d, r, nit=3):
+        return dict(iter=i, status=st, newton_iters=nit, linear_iters=0, delta=d, residual=r)
+    rows = (row(1, L.STEP_ACCEPTED, 1.0, 7.51e-2), row(2, L.STEP_REJECTED_GROWTH, 10.9, 12.34),
+            row(3, L.STEP_REJECTED_GROWTH, 1.09, float("inf")), row(4, L.STEP_REJECTED_GROWTH, 0.109, float("nan")),
+            row(5, L.STEP_REJECTED_INNER, 1.09e-2, float("nan")), row(6, L.STEP_REJECTED_NAN, 1.09e-3, float("nan")),
+            row(7, L.STEP_REJECTED_SINGULAR, 1.09e-4, float("nan")), row(8, L.STEP_ACCEPTED, 1.09e-5, 1.22e-10))
+    res = EconPDEResult(sol, 1.22e-10, OrderedDict(), eo.SQRT_EPS, L.EXIT_CONVERGED, rows, 8, 20, 0, 100, 63.4)
+    buf = io.StringIO()
+    _print_log(res, "1 unknown (v) on grid x = 50", buf)
+    assert buf.getvalue().splitlines() == [
+        "Solving for 1 unknown (v) on grid x = 50",
+        "Iter TimeStep Residual",
+        "---- -------- --------",
+        "   1 1.00e+00 7.51e-02",
+        "   2 1.09e+01        ✗ (residual grew 12.3× > max_residual_growth)",
+        "   3 1.09e+00        ✗ (residual grew ∞ > max_residual_growth)",
+        "   4 1.09e-01        ✗ (residual grew > max_residual_growth)",      # engines that do not report the factor
+        "   5 1.09e-02        ✗",
+        "   6 1.09e-03        ✗ (model returned NaN)",
+        "   7 1.09e-04        ✗ (singular Jacobian)",
+        "   8 1.09e-05 1.22e-10",
+        "Converged after 8 time steps (63ms)"]
+    one_shot = EconPDEResult(sol, 0.0, OrderedDict(), eo.SQRT_EPS, L.EXIT_CONVERGED, (), 0, 2, 0, 10, 1234.0)
+    buf = io.StringIO()
+    _print_log(one_shot, "1 unknown (v) on grid x = 50", buf)
+    assert buf.getvalue().splitlines() == ["Solving for 1 unknown (v) on grid x = 50", "Converged (1.2s)"]
+    assert _warn_text(res, 1e-9) is None
+    bad = EconPDEResult(sol, 2.5e-3, OrderedDict(), eo.SQRT_EPS, L.EXIT_MAXITERS, rows, 8)
+    assert _warn_text(bad, 1e-9) == ("did not converge after 8 time steps: residual 2.50e-03 > tolerance 1.49e-08. If the "
+                                     "residual was still falling, increase `maxiters`; otherwise try a better initial guess "
+                                     "or `check_monotonicity = true`.")
+    bad.exit_reason = L.EXIT_BELOW_MIN_DELTA
+    assert "fell below `minΔ` = 1e-09 (residual 2.50e-03 > tolerance 1.49e-08). This usually means" in _warn_text(bad, 1e-9)
+    bad.exit_reason = L.EXIT_INF_STEP_FAILED
+    assert _warn_text(bad, 1e-9).endswith("`Δ = Inf` disables pseudo-transient continuation — try a finite initial time "
+                                          "step `Δ`, a better initial guess, or more `maxiters`.")
+
+
 def test_graft_entry_build_check_passes():
     """The driver's "does it build" entry point (incremental: a no-op when the library is current)."""
     import __graft_entry__ as ge
