@@ -107,9 +107,16 @@ function EconPDEs.pdesolve(m::CUDAModel, grid, guess; is_algebraic = nothing, bc
     solution = NamedTuple{ynames}(ntuple(k -> collect(selectdim(sol, ndims(sol), k)), F))
     savednt = isempty(m.saved) ? NamedTuple() :
         merge(solution, NamedTuple{m.saved}(ntuple(k -> collect(selectdim(saved, ndims(saved), k)), length(m.saved))))
-    verbose && for r in log[1:res.log_len]   # same table as src/finiteschemesolve.jl:421,435,445
-        r.status == 0 ? Printf.@printf("%4d %8.2e %8.2e\n", r.iter, r.delta, r.residual) :
-                        Printf.@printf("%4d %8.2e        ✗\n", r.iter, r.delta)
+    verbose && for r in log[1:min(res.log_len, maxiters)]   # same table as src/finiteschemesolve.jl:421, 433-435, 441-445
+        if r.status == 0
+            Printf.@printf("%4d %8.2e %8.2e\n", r.iter, r.delta, r.residual)
+        elseif r.status == 1      # growth rejection: the engine stores residual/old_residual in `residual`
+            growth_text = isfinite(r.residual) ? Printf.@sprintf("%.1f×", r.residual) : "∞"
+            Printf.@printf("%4d %8.2e        ✗ (residual grew %s > max_residual_growth)\n", r.iter, r.delta, growth_text)
+        else
+            reason = r.status == 3 ? " (model returned NaN)" : r.status == 4 ? " (singular Jacobian)" : ""
+            Printf.@printf("%4d %8.2e        ✗%s\n", r.iter, r.delta, reason)
+        end
     end
     return EconPDEResult(solution, res.residual_norm, savednt, abstol)
 end
