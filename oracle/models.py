@@ -657,11 +657,12 @@ def he_krishnamurthy(m=4.0, lam=0.6, g=0.02, sigma=0.09, rho=0.04, gamma=2.0, l=
         pS, pSxx = u["pS"], u["pSxx"]
 
         def block(pSx):
+            den = x / pS + (1 - x) * rho      # Julia's x^3 is x*x*x (literal_pow), numpy's ** 3 is pow(): write it out
             p = (1 + l) / (x / pS + (1 - x) * rho)
             px = -(1 + l) / (x / pS + (1 - x) * rho) ** 2 * (1 / pS - rho - x / pS ** 2 * pSx)
             pxx = (-(1 + l) / (x / pS + (1 - x) * rho) ** 2 * (-1 / pS ** 2 * pSx - 1 / pS ** 2 * pSx - x / pS ** 2 * pSxx
-                                                             + 2 * x / pS ** 3 * pSx ** 2)
-                   + 2 * (1 + l) / (x / pS + (1 - x) * rho) ** 3 * (1 / pS - rho - x / pS ** 2 * pSx) ** 2)
+                                                             + 2 * x / (pS * pS * pS) * pSx ** 2)
+                   + 2 * (1 + l) / (den * den * den) * (1 / pS - rho - x / pS ** 2 * pSx) ** 2)
             aI = 1 / (1 - lam * (1 - x)) + 0.0 * pS
             aI = np.where(x * (1 + m) * aI < 1, 1 / (x * (1 + m)), aI)
             sigx = x * (aI - 1) * sigma / (1 - x * (aI - 1) * px / p)

@@ -390,3 +390,31 @@ def test_row_terms_match_g_helper_and_minmax_mcp(mode):
         want = g - np.where(alg, 0.0, (ypost - y) / delta)
         np.testing.assert_array_equal(run(False), want)
         np.testing.assert_array_equal(run(True), np.minimum(np.maximum(want, y - ub), y - lb))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_wild_fields_give_the_same_bits_and_the_same_nans(case):
+    """Newton's off-path iterates: fields of mixed sign and scale, exact zeros included.  The functor must produce a NaN
+    or an infinity exactly where the reference body does (that decides "model returned NaN" rejections) and the same
+    bits elsewhere (to a few ulp where `pow`/`log` enter).  This test caught numpy's `x ** 3` (pow) standing in for
+    Julia's `x^3` (= x*x*x) in one oracle body."""
+    name, pm, om, g, gu = case
+    grids = list(g.values())
+    shape = next(iter(gu.values())).shape
+    prob = eo.Problem(om, tuple(g), grids, tuple(gu))
+    for seed in range(8):
+        rng = np.random.default_rng(100 + seed)
+        y = np.stack([rng.normal(size=shape) * 10.0 ** rng.integers(-2, 3) for _ in gu], axis=-1)
+        if seed % 2:
+            y[tuple(rng.integers(0, s) for s in shape) + (0,)] = 0.0
+        with np.errstate(all="ignore"):
+            want = prob.G(y.reshape(-1, order="F")).reshape(y.shape, order="F")
+        got = EU.residual(pm, grids, y)
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+        fin = np.isfinite(want)
+        np.testing.assert_array_equal(got[~fin], want[~fin])
+        if name in POW_MODELS + ("risky",):
+            scale = np.abs(want[fin]).max() if fin.any() else 1.0
+            np.testing.assert_allclose(got[fin], want[fin], rtol=1e-9, atol=1e-9 * scale)
+        else:
+            np.testing.assert_array_equal(got[fin], want[fin])
