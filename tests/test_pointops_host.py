@@ -418,3 +418,29 @@ def test_wild_fields_give_the_same_bits_and_the_same_nans(case):
             np.testing.assert_allclose(got[fin], want[fin], rtol=1e-9, atol=1e-9 * scale)
         else:
             np.testing.assert_array_equal(got[fin], want[fin])
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[1].savednames], ids=[c[0] for c in CASES if c[1].savednames])
+def test_wild_fields_saved_outputs(case):
+    """Same off-path fields for the saved outputs (`_fill_saved!`, src/pdesolve.jl:424-433): same NaN positions,
+    same bits (a few ulp where `pow` enters)."""
+    name, pm, om, g, gu = case
+    grids = list(g.values())
+    shape = next(iter(gu.values())).shape
+    prob = eo.Problem(om, tuple(g), grids, tuple(gu))
+    for seed in range(6):
+        rng = np.random.default_rng(500 + seed)
+        y = np.stack([rng.normal(size=shape) * 10.0 ** rng.integers(-2, 3) for _ in gu], axis=-1)
+        with np.errstate(all="ignore"):
+            sv = prob.saved(y.reshape(-1, order="F"))
+        _, got = EU.residual(pm, grids, y, saved=True)
+        for k, key in enumerate(pm.savednames):
+            a, b = got[..., k], sv[key]
+            np.testing.assert_array_equal(np.isnan(a), np.isnan(b), err_msg=key)
+            fin = np.isfinite(b)
+            np.testing.assert_array_equal(a[~fin], b[~fin], err_msg=key)
+            if name in POW_MODELS + ("risky",):
+                scale = np.abs(b[fin]).max() if fin.any() else 1.0
+                np.testing.assert_allclose(a[fin], b[fin], rtol=1e-9, atol=1e-9 * scale, err_msg=key)
+            else:
+                np.testing.assert_array_equal(a[fin], b[fin], err_msg=key)
