@@ -401,15 +401,17 @@ def test_wild_fields_give_the_same_bits_and_the_same_nans(case):
     name, pm, om, g, gu = case
     grids = list(g.values())
     shape = next(iter(gu.values())).shape
-    prob = eo.Problem(om, tuple(g), grids, tuple(gu))
     for seed in range(8):
         rng = np.random.default_rng(100 + seed)
         y = np.stack([rng.normal(size=shape) * 10.0 ** rng.integers(-2, 3) for _ in gu], axis=-1)
         if seed % 2:
             y[tuple(rng.integers(0, s) for s in shape) + (0,)] = 0.0
+        # every other seed also random boundary values for every (unknown, point) slot (src/pdesolve.jl:312-335)
+        bc = rng.normal(size=y.shape) * 10.0 ** rng.integers(-2, 2) if seed >= 4 else None
+        prob = eo.Problem(om, tuple(g), grids, tuple(gu), bc)
         with np.errstate(all="ignore"):
             want = prob.G(y.reshape(-1, order="F")).reshape(y.shape, order="F")
-        got = EU.residual(pm, grids, y)
+        got = EU.residual(pm, grids, y, bc=bc)
         np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
         fin = np.isfinite(want)
         np.testing.assert_array_equal(got[~fin], want[~fin])
