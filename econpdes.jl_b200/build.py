@@ -21,14 +21,18 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 COMMON = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
           "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
           "-DECONPDES_BUILD"]
+MODELOPS_PARTS = 8   # kModelOpsParts (csrc/engine.cuh): slices of the functor registry, compiled in parallel
+# object name -> (source, extra flags)
 UNITS = {
-    "engine.cu": ["-fmad=false"],
-    "api.cu": ["-fmad=false"],
-    "krylov.cu": [],
-    "dist.cu": [],
-    "pattern.cpp": [],
-    "errors.cpp": [],
+    "engine.cu": ("engine.cu", ["-fmad=false"]),
+    "api.cu": ("api.cu", ["-fmad=false"]),
+    "krylov.cu": ("krylov.cu", []),
+    "dist.cu": ("dist.cu", []),
+    "pattern.cpp": ("pattern.cpp", []),
+    "errors.cpp": ("errors.cpp", []),
 }
+for _k in range(MODELOPS_PARTS):
+    UNITS["modelops%d.cu" % _k] = ("modelops.cu", ["-fmad=false", "-DEP_PART=%d" % _k])
 
 
 def _headers():
@@ -40,8 +44,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
     hdr_mtime = max(os.path.getmtime(h) for h in _headers())
     objs, procs = [], []
-    for unit, extra in UNITS.items():
-        src = os.path.join(CSRC, unit)
+    for unit, (source, extra) in UNITS.items():
+        src = os.path.join(CSRC, source)
         obj = os.path.join(OBJDIR, unit + ".o")
         objs.append(obj)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_mtime):

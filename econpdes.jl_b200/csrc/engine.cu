@@ -57,149 +57,31 @@ double Norms::norm2_over_n(long long n) const {
 }
 
 // ---------------------------------------------------------------------------------------
-// model registry
+// model registry: the per-model kernel launchers are compiled in modelops.cu, once per slice of the
+// functor list (modelops.cuh), so the build runs in parallel
 // ---------------------------------------------------------------------------------------
 std::atomic<int> g_batch_points_per_thread{0};
 
-template <class M, bool ONE_D = (M::N == 1 && M::F == 1)>
-struct BatchedLaunch {
-  static bool run(const BatchArgs&, cudaStream_t) { return false; }
-};
-template <class M>
-struct BatchedLaunch<M, true> {
-  template <int P, bool PER_COL>
-  static void launch(const BatchArgs& a, cudaStream_t s) {
-    const int T = (((a.S + P - 1) / P + 31) / 32) * 32;
-    const size_t smem = batched_smem_bytes(T, P);
-    // per device (the attribute lives in the device's context): set once for every device this process uses
-    static std::atomic<unsigned long long> configured{0};
-    int dev = 0;
-    EP_CUDA(cudaGetDevice(&dev));
-    if (!((configured.load() >> (dev & 63)) & 1ull)) {
-      EP_CUDA(cudaFuncSetAttribute((k_batched_pdesolve_1d<M, P, PER_COL>), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(batched_smem_bytes(batched_max_threads(P), P))));
-      configured.fetch_or(1ull << (dev & 63));
-    }
-    EP_LAUNCH((k_batched_pdesolve_1d<M, P, PER_COL>), static_cast<unsigned>(a.nproblems - a.problem0), T, smem, s, a);
-  }
-  template <int P>
-  static void launch(const BatchArgs& a, cudaStream_t s) {
-    if (a.opt.eps_policy == ECONPDES_EPS_PER_COLUMN) launch<P, true>(a, s);
-    else launch<P, false>(a, s);
-  }
-  static bool run(const BatchArgs& a, cudaStream_t s) {
-    if (a.S > 1024) return false;
-    // grid points per thread (batched1d.cuh): econpdes_set_batch_points_per_thread, else the
-    // ECONPDES_BATCH_P environment variable, else by problem size
-    static const int env = [] {
-      const char* e = std::getenv("ECONPDES_BATCH_P");
-      return e ? std::atoi(e) : 0;
-    }();
-    const int knob = g_batch_points_per_thread.load();
-    const int forced = knob ? knob : env;
-    int P = forced ? forced : (a.S > 256 ? 4 : (a.S > 64 ? 2 : 1));
-    while (P > 1 && (a.S + P - 1) / P > batched_max_threads(P)) --P;
-    if (P >= 4) launch<4>(a, s);
-    else if (P == 3) launch<3>(a, s);
-    else if (P >= 2) launch<2>(a, s);
-    else launch<1>(a, s);
-    return true;
-  }
-};
-
-// Slab path: every rank holds every rank's per-color sums of squares (rank-major); fold them in
-// rank order and turn the totals into FiniteDiff's steps.
-static __global__ void k_color_eps_fold(int world, int nc, const double* __restrict__ all, double* __restrict__ sumsq,
-                                        double* __restrict__ eps) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nc) return;
-  double t = 0.0;
-  for (int r = 0; r < world; ++r) t += all[r * nc + c];
-  sumsq[c] = t;
-  const double e = color_epsilon_from_sumsq(t);
-  eps[c] = e;
-  eps[nc + c] = 1.0 / e;
-}
-
-template <class M>
-struct ModelOpsT final : ModelOps {
-  const char* name() const override { return M::name(); }
-  int N() const override { return M::N; }
-  int F() const override { return M::F; }
-  int nparams() const override { return M::NPARAMS; }
-  void derive(double* prm) const override {
-    static_assert(M::NPARAMS + M::NDERIVED + (M::TIME_SLOT >= 0 ? 1 : 0) <= kMaxParams, "parameter pack too small");
-    M::derive(prm);
-  }
-  int time_slot() const override { return M::TIME_SLOT; }
-  int nsaved() const override { return M::NSAVED; }
-  bool box() const override { return M::USES_CROSS && M::N > 1; }
-  void residual(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm) const override {
-    // 128-thread blocks, four per SM (128 registers): finer scheduling granularity than 256 x 2 at the
-    // same occupancy (measured 3-8 % faster on the 2048^2 and 256^3 sweeps)
-    constexpr int RB = 128;
-    EP_LAUNCH((k_residual<M, RB, 4>), sweep_blocks(c.l, RB), RB, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p, rs,
-              out, c.nw(), want_norm ? 1 : 0);
-  }
-  void jacobian(const Ctx& c, const double* y, const RowSpec& rs, int eps_policy, double* planes,
-                double* r0) const override {
-    const int per_col = eps_policy == ECONPDES_EPS_PER_COLUMN;
-    if (!per_col) {
-      const int cblocks = blocks_for(c.l) < 148 * 4 ? blocks_for(c.l) : 148 * 4;   // persistent: 4 blocks per SM
-      EP_LAUNCH(k_color_sumsq<M::N>, cblocks, kBlock, 0, c.stream, c.grid_view<M::N>(), M::F, y, c.cw());
-      if (c.dist != nullptr) {   // one all-gather of the C masked norms per Jacobian
-        c.dist->all_gather(c.color_sumsq.p, c.gather.p, c.ncolors, c.stream);
-        EP_LAUNCH(k_color_eps_fold, 1, 128, 0, c.stream, c.dist->world(), c.ncolors, c.gather.p, c.color_sumsq.p,
-                  c.color_eps.p);
-      }
-    }
-    constexpr bool BOX = M::USES_CROSS && M::N > 1;
-    // step policy fixed at compile time (branch-free row evaluation), two resident blocks per SM:
-    // measured 0.53 -> 0.35 ms at 2048^2 and 2.94 -> 2.47 ms at 256^3 against the run-time-policy kernel
-    // 3-D rows (10+ evaluations of a 27-point box) get 170 registers: 128-thread blocks, three per SM
-    constexpr int JB = M::N >= 3 ? 128 : kBlock, JMINB = M::N >= 3 ? 3 : 2;
-    auto go = [&](auto kernel) {
-      EP_LAUNCH(kernel, blocks_for(c.l, JB), JB, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p, rs, c.color_eps.p,
-                per_col, planes, r0);
-    };
-    if (per_col) go(k_jacobian<M, BOX, 1, JB, JMINB>);
-    else go(k_jacobian<M, BOX, 0, JB, JMINB>);
-  }
-  void saved(const Ctx& c, const double* y, double* out) const override {
-    if (M::NSAVED == 0) return;
-    EP_LAUNCH(k_saved<M>, blocks_for(c.l), kBlock, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p, out);
-  }
-  bool batched(const BatchArgs& a, cudaStream_t s) const override { return BatchedLaunch<M>::run(a, s); }
-};
-
 namespace {
-template <class... Ms>
-struct Registry {
-  static const ModelOps* get(int id) {
-    static const std::tuple<ModelOpsT<Ms>...> ops;
-    return pick<0>(ops, id);
-  }
-  template <size_t I>
-  static const ModelOps* pick(const std::tuple<ModelOpsT<Ms>...>& ops, int id) {
-    if constexpr (I < sizeof...(Ms)) {
-      if (id == static_cast<int>(I)) return &std::get<I>(ops);
-      return pick<I + 1>(ops, id);
-    } else {
-      return nullptr;
-    }
-  }
-  static constexpr int count = sizeof...(Ms);
-};
-#define X(M) , M
-struct Dummy_ {};
-template <class D, class... Ms>
-using RegistryOf = Registry<Ms...>;
-using TheRegistry = RegistryOf<Dummy_ ECONPDES_FOR_EACH_MODEL(X)>;
+#define X(M) +1
+constexpr int kModelCount = 0 ECONPDES_FOR_EACH_MODEL(X);
 #undef X
 }  // namespace
+int model_count() { return kModelCount; }
 
-const ModelOps* model_ops(int model_id) { return TheRegistry::get(model_id); }
-int model_count() { return TheRegistry::count; }
+const ModelOps* model_ops(int model_id) {
+  if (model_id < 0 || model_id >= model_count()) return nullptr;
+  switch (model_id % kModelOpsParts) {
+    case 0: return model_ops_part0(model_id);
+    case 1: return model_ops_part1(model_id);
+    case 2: return model_ops_part2(model_id);
+    case 3: return model_ops_part3(model_id);
+    case 4: return model_ops_part4(model_id);
+    case 5: return model_ops_part5(model_id);
+    case 6: return model_ops_part6(model_id);
+    default: return model_ops_part7(model_id);
+  }
+}
 
 // ---------------------------------------------------------------------------------------
 // problem upload

@@ -132,6 +132,10 @@ struct ModelOps {
 };
 const ModelOps* model_ops(int model_id);
 int model_count();
+// slices of the registry (modelops.cu, compiled once per slice)
+constexpr int kModelOpsParts = 8;
+const ModelOps* model_ops_part0(int), *model_ops_part1(int), *model_ops_part2(int), *model_ops_part3(int),
+    *model_ops_part4(int), *model_ops_part5(int), *model_ops_part6(int), *model_ops_part7(int);
 
 // Linear solver behind each Newton iteration: J x = b with J in stencil planes.
 struct LinearSolver {

@@ -18,7 +18,7 @@ sel='readme_quickstart or two_income or garleanu or he_krishnamurthy or wachter 
 sel="$sel or signed_per_function or mcp_lower_bound or linear_sum_1d or pdesolve_2d_known or hump"
 sel="$sel or (pdesolve_nd_against_golden and (bansal_yaron_30 or ahlm_10x100 or hjb3d_12))"
 for tool in memcheck racecheck synccheck initcheck; do
-  timeout 1200 compute-sanitizer --tool "$tool" --error-exitcode 9 --log-file "$out/$tool.log" \
+  timeout ${SAN_LIMIT:-1200} compute-sanitizer --tool "$tool" --error-exitcode 9 --log-file "$out/$tool.log" \
     python -m pytest tests/test_gpu_parity.py -q -x -k "$sel" > "$out/$tool.pytest.log" 2>&1
   echo "$tool rc=$?" >> "$out/summary.txt"
 done
