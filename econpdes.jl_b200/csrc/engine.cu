@@ -105,6 +105,7 @@ std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p, Dist* dist, long long s
   c->nparams = ops->nparams();
   c->nsaved = ops->nsaved();
   c->box = ops->box();
+  if (c->box && ops->F() == 1) c->plane_mask = ops->plane_mask();
   c->nk = c->box ? ipow3(c->N) : 1 + 2 * c->N;
   c->l = 1;
   c->ncolors = c->F;
@@ -150,6 +151,20 @@ std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p, Dist* dist, long long s
     for (long long j = 0; j < c->n && !any; ++j) any = p->bc[j] != 0.0;
     if (any) c->bc.upload(p->bc, static_cast<size_t>(c->n), s);
   }
+  {
+    // "tame" geometry (sweep.cuh): every spacing and tabulated reciprocal finite and within 2^+-200, every
+    // boundary value below 2^199 -- then no stencil quotient of tame unknowns can overflow or hit 0 * Inf
+    auto moderate = [](double v) { const double a = std::fabs(v); return a >= 0x1p-200 && a <= 0x1p200; };
+    bool ok = true;
+    for (int d = 0; d < c->N && ok; ++d) {
+      std::vector<double> tab(static_cast<size_t>(kGeomRows) * c->S[d]);
+      make_geom_table(p->grid[d], c->S[d], tab.data());
+      for (double v : tab) ok = ok && moderate(v);
+    }
+    if (ok && c->bc.p != nullptr)
+      for (long long j = 0; j < c->n && ok; ++j) ok = std::fabs(p->bc[j]) < 0x1p199;
+    c->geom_tame = ok;
+  }
   if (p->is_algebraic != nullptr) {
     bool any = false;
     for (long long j = 0; j < c->n && !any; ++j) any = p->is_algebraic[j] != 0;
@@ -162,6 +177,18 @@ std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p, Dist* dist, long long s
   if (p->upper_bound != nullptr)
     for (long long j = 0; j < c->n && !ubany; ++j) ubany = p->upper_bound[j] != INFINITY;
   c->has_bounds = lbany || ubany;
+  if (dist != nullptr) {
+    // Slab path: a bound that is finite on one rank only must still switch EVERY rank to the MCP residual and
+    // the masked norm -- the masked norm adds collectives, which all ranks have to call in the same order
+    const size_t world = static_cast<size_t>(dist->world());
+    c->gather.alloc(world * kGatherMax);
+    EP_CUDA(cudaMallocHost(&c->h_gather, world * kGatherMax * sizeof(double)));
+    DevBuf<double> flag;
+    const double mine = c->has_bounds ? 1.0 : 0.0;
+    flag.upload(&mine, 1, s);
+    const double* all = c->gather_to_host(flag.p, 1);
+    for (size_t r = 0; r < world; ++r) c->has_bounds = c->has_bounds || all[r] != 0.0;
+  }
   if (c->has_bounds) {
     std::vector<double> tmp(static_cast<size_t>(c->n));
     for (long long j = 0; j < c->n; ++j) tmp[j] = p->lower_bound ? p->lower_bound[j] : -INFINITY;
@@ -193,7 +220,10 @@ std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p, Dist* dist, long long s
       EP_CUDA(cudaStreamSynchronize(s));
     }
   }
-  c->max_blocks = blocks_for(c->n, 128) + 1;   // the smallest block size any norm-producing sweep uses
+  // the smallest block size any norm-producing sweep uses; the marching sweeps (sweep.cuh) launch up to
+  // 148 x 6 blocks whatever the grid size (a tile can be a few points wide on a narrow grid)
+  c->max_blocks = blocks_for(c->n, 128) + 1;
+  if (c->max_blocks < 148 * 8) c->max_blocks = 148 * 8;
   c->norm_part.alloc(3 * static_cast<size_t>(c->max_blocks));
   c->norm_out.alloc(4);
   c->color_part.alloc(static_cast<size_t>(blocks_for(c->l)) * c->ncolors);
@@ -202,9 +232,10 @@ std::unique_ptr<Ctx> make_ctx(const econpdes_problem* p, Dist* dist, long long s
   c->counters.alloc(4);
   c->counters.zero(s);
   EP_CUDA(cudaMallocHost(&c->h_norm, 4 * sizeof(double)));
-  const size_t world = dist != nullptr ? static_cast<size_t>(dist->world()) : 1;
-  c->gather.alloc(world * kGatherMax);
-  EP_CUDA(cudaMallocHost(&c->h_gather, world * kGatherMax * sizeof(double)));
+  if (dist == nullptr) {
+    c->gather.alloc(kGatherMax);
+    EP_CUDA(cudaMallocHost(&c->h_gather, kGatherMax * sizeof(double)));
+  }
   if (dist != nullptr) dist->enable_p2p(c->halo, s);   // collective: every rank builds its Ctx at the same point
   EP_CUDA(cudaStreamSynchronize(s));
   return c;
@@ -304,6 +335,9 @@ Solver::Solver(std::unique_ptr<Ctx> ctx) : c_(std::move(ctx)), ops_(model_ops(c_
   ypost_.pad = y_.pad = ynew_.pad = static_cast<size_t>(c_->halo);   // fields a stencil reads carry ghost planes
   ypost_.alloc(n); y_.alloc(n); ynew_.alloc(n); R_.alloc(n); s_.alloc(n); G_.alloc(n);
   planes_.alloc(static_cast<size_t>(c_->nk) * c_->F * c_->F * c_->l);
+  // the marching Jacobian sweep never writes the planes of box slots the model does not read (exact zeros)
+  EP_CUDA(cudaMemset(planes_.p, 0, planes_.n * sizeof(double)));
+  EP_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
   lin_ = c_->N == 1 ? make_tridiag_solver(*c_) : make_krylov_solver(*c_);
 }
 
@@ -324,33 +358,68 @@ Norms Solver::read_norms() {
   // (sum of squares, max, NaN flag) of every rank, folded in rank order (one rank: itself)
   const double* g = c_->gather_to_host(c_->norm_out.p, 3);
   const int world = c_->dist != nullptr ? c_->dist->world() : 1;
-  Norms out{0.0, 0.0, false};
+  Norms out{0.0, 0.0, false, false};
   for (int r = 0; r < world; ++r) {
     out.sumsq += g[3 * r];
     out.maxabs = g[3 * r + 1] > out.maxabs ? g[3 * r + 1] : out.maxabs;
-    out.any_nan = out.any_nan || g[3 * r + 2] != 0.0;
+    const int flags = static_cast<int>(g[3 * r + 2]);   // kFlagNaN | kFlagUntame (sweep.cuh)
+    out.any_nan = out.any_nan || (flags & kFlagNaN) != 0;
+    out.untame = out.untame || (flags & kFlagUntame) != 0;
   }
   return out;
+}
+
+// The sweep first runs in its tame form (stencil quotients without the NaN-select, sweep.cuh), which also
+// reports whether every unknown it read was tame; if not -- a wild Newton iterate -- the output is discarded
+// and recomputed by the general form.  `last_tame_` tells the Jacobian of the same iterate which form to take.
+Norms Solver::residual_with_norms(const double* y, const RowSpec& rs, double* out) {
+  const bool try_tame = c_->geom_tame;
+  ops_->residual(*c_, y, rs, out, true, try_tame);
+  Norms n = read_norms();
+  if (try_tame && n.untame) {
+    ops_->residual(*c_, y, rs, out, true, false);
+    n = read_norms();
+    n.untame = true;
+  }
+  last_tame_ = try_tame && !n.untame;
+  return n;
 }
 
 Norms Solver::eval_G(const double* y, double* out) {
   ProfScope ps("residual G", c_->stream);
   c_->exchange_halo(y);
-  ops_->residual(*c_, y, row_spec(nullptr, INFINITY), out, true);
-  return read_norms();
+  return residual_with_norms(y, row_spec(nullptr, INFINITY), out);
 }
 
 Norms Solver::eval_R(const double* y, const double* ypost, double delta, double* out) {
   ProfScope ps("residual R", c_->stream);
   c_->exchange_halo(y);
-  ops_->residual(*c_, y, row_spec(ypost, delta), out, true);
-  return read_norms();
+  return residual_with_norms(y, row_spec(ypost, delta), out);
 }
 
-void Solver::jacobian(const double* y, const double* ypost, double delta, int eps_policy) {
+void Solver::jacobian(const double* y, const double* ypost, double delta, int eps_policy, bool tame) {
   ProfScope ps("jacobian", c_->stream);
   c_->exchange_halo(y);
-  ops_->jacobian(*c_, y, row_spec(ypost, delta), eps_policy, planes_.p, nullptr);
+  ops_->jacobian(*c_, y, row_spec(ypost, delta), eps_policy, planes_.p, nullptr, tame && c_->geom_tame);
+}
+
+namespace {
+__global__ void __launch_bounds__(kBlock) k_tame_check(long long n, const double* __restrict__ y, NormWork nw) {
+  __shared__ double scratch[96];
+  int flag = 0;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long j = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < n; j += stride)
+    if (!is_tame(y[j])) flag = kFlagUntame;
+  grid_norm_finish(0.0, 0.0, flag, nw, scratch);
+}
+}  // namespace
+
+// Is every unknown of y tame (sweep.cuh)?  For callers that assemble a Jacobian without the residual sweep
+// of the same iterate in front of it (the handle API).
+bool Solver::check_tame(const double* y) {
+  if (!c_->geom_tame) return false;
+  EP_LAUNCH(k_tame_check, sweep_blocks(c_->n), kBlock, 0, c_->stream, c_->n, y, c_->nw());
+  return !read_norms().untame;
 }
 
 double Solver::masked_norm(const double* ydot, const double* y) {
@@ -458,7 +527,17 @@ NewtonOutcome Solver::newton(const double* ypost, double delta, double ftol, int
   bool xconv = false;
   while (!stopped && !fconv && !xconv && out.iters < maxit) {
     ++out.iters;
-    jacobian(x, ypost, delta, opt.eps_policy);
+    if (c_->has_bounds && c_->dist == nullptr &&
+        ((!sign_checked_ && std::isfinite(delta)) || (opt.check_monotonicity != 0 && !stencils_checked_))) {
+      // fd_mcp_jac (finiteschemesolve.jl:205-214) hands the checker the Jacobian of the UNCLAMPED G_helper!
+      // residual: rows at an active bound would otherwise show diagonal 1 and no off-diagonal entries
+      ProfScope ps("jacobian", c_->stream);
+      RowSpec rs = row_spec(ypost, delta);
+      rs.has_bounds = 0;
+      ops_->jacobian(*c_, x, rs, opt.eps_policy, planes_.p, nullptr, last_tame_ && c_->geom_tame);
+      jacobian_diagnostics(delta, opt);
+    }
+    jacobian(x, ypost, delta, opt.eps_policy, last_tame_);   // eval_R(x) has just vouched for x
     jacobian_diagnostics(delta, opt);
     int li = 0;
     double rr = 0.0;

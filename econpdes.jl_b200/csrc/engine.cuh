@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "dist.cuh"
 #include "kernels.cuh"
+#include "sweep.cuh"
 
 namespace econpdes {
 
@@ -36,7 +37,11 @@ struct DevBuf {
     if (count == 0) return;
     T* base = nullptr;
     EP_CUDA(cudaMalloc(&base, (count + 2 * pad) * sizeof(T)));
-    if (pad) EP_CUDA(cudaMemset(base, 0, (count + 2 * pad) * sizeof(T)));   // ghosts at the global ends stay 0
+    if (pad) {   // ghosts at the global ends stay 0
+      EP_CUDA(cudaMemset(base, 0, (count + 2 * pad) * sizeof(T)));
+      // the memset runs on the legacy stream, which the library's non-blocking streams do not wait for
+      EP_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+    }
     p = base + pad;
     pad_alloc_ = pad;
     n = count;
@@ -61,6 +66,7 @@ extern std::atomic<int> g_batch_points_per_thread;   // 0 = automatic (api: econ
 struct Ctx {
   int model_id = -1, N = 0, F = 0, nparams = 0, nsaved = 0;
   bool box = false;        // stencil shape of the Jacobian planes
+  unsigned plane_mask = 0xffffffffu;   // box stencils of one unknown: planes the model's residual can depend on
   int nk = 0;              // planes per (fin, fout) pair
   long long S[kMaxDims] = {1, 1, 1};  // GLOBAL grid sizes
   long long l = 0, n = 0;             // points / unknowns owned by this device
@@ -76,6 +82,7 @@ struct Ctx {
   DevBuf<double> grid[kMaxDims], geomtab[kMaxDims], guess, bc, lb, ub, delta_rel;
   DevBuf<unsigned char> is_alg;
   bool has_bounds = false, has_delta_vec = false, all_delta_inf = false;
+  bool geom_tame = false;   // grid reciprocals and boundary values finite and of moderate magnitude (sweep.cuh)
   double delta_base = 1.0;  // min finite |Δ_i| of a vector Δ (finiteschemesolve.jl:394)
   cudaStream_t stream = nullptr;
   // reductions
@@ -109,6 +116,7 @@ struct Ctx {
 struct Norms {
   double sumsq, maxabs;
   bool any_nan;
+  bool untame = false;   // some unknown of the sweep's input is not tame (sweep.cuh)
   double norm2_over_n(long long n) const;  // NaN if any NaN, like norm(v)/length(v)
 };
 
@@ -123,9 +131,14 @@ struct ModelOps {
   virtual int time_slot() const = 0;            // parameter slot holding the time of pde(state, u, t), or -1   // appends the model's parameter-only constants (models.cuh)
   virtual int nsaved() const = 0;
   virtual bool box() const = 0;
-  virtual void residual(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm) const = 0;
+  virtual unsigned plane_mask() const = 0;      // bit k: the residual reads box slot k (M::slot_used)
+  // tame: the caller vouches that every unknown the sweep reads is tame (sweep.cuh); the residual sweep
+  // itself reports untame unknowns in bit 1 of its flag word, after which its output must be recomputed
+  // with tame = false
+  virtual void residual(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm,
+                        bool tame = false) const = 0;
   virtual void jacobian(const Ctx& c, const double* y, const RowSpec& rs, int eps_policy, double* planes,
-                        double* r0) const = 0;
+                        double* r0, bool tame = false) const = 0;
   virtual void saved(const Ctx& c, const double* y, double* out) const = 0;
   // fused batched engine; returns false if the model is not 1-D single-unknown
   virtual bool batched(const struct BatchArgs& a, cudaStream_t s) const = 0;
@@ -170,7 +183,8 @@ class Solver {
   Ctx& ctx() { return *c_; }
   Norms eval_G(const double* y, double* out);  // G!(ydot, y) + norms
   Norms eval_R(const double* y, const double* ypost, double delta, double* out);
-  void jacobian(const double* y, const double* ypost, double delta, int eps_policy);
+  void jacobian(const double* y, const double* ypost, double delta, int eps_policy, bool tame = false);
+  bool check_tame(const double* y);
   double* planes() { return planes_.p; }
   LinearSolver& linear() { return *lin_; }
   NewtonOutcome newton(const double* ypost, double delta, double ftol, int maxit, const econpdes_options& opt,
@@ -190,6 +204,8 @@ class Solver {
  private:
   RowSpec row_spec(const double* ypost, double delta) const;
   Norms read_norms();
+  Norms residual_with_norms(const double* y, const RowSpec& rs, double* out);
+  bool last_tame_ = false;
   double masked_norm(const double* ydot, const double* y);
   void jacobian_diagnostics(double delta, const econpdes_options& opt);
   std::unique_ptr<Ctx> c_;

@@ -57,6 +57,10 @@ struct LevelGeom {
   // slab of a distributed level: the first / last plane of dimension N-1 has a neighbour plane
   // in the ghost storage around the vector (filled by a halo exchange), not a grid boundary
   bool open_lo = false, open_hi = false;
+  // planes that can hold a non-zero coefficient (bit k = plane k): the finest level of a model that declares
+  // which box slots its residual reads (M::slot_used) skips the others -- they are exact zeros, in the
+  // reference's Jacobian too -- in the operator applications and the smoother; Galerkin levels use every plane
+  unsigned mask = 0xffffffffu;
 };
 
 template <int N>
@@ -94,6 +98,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv(LevelGeom<N> g, const TA* __res
   double acc = 0.0;
 #pragma unroll
   for (int k = 0; k < St::NK; ++k) {
+    if (!((g.mask >> k) & 1u)) continue;   // block-uniform
     long long q = pt;
     bool ok = true;
 #pragma unroll
@@ -212,6 +217,7 @@ __global__ void __launch_bounds__(1024) k_line_zebra(LevelGeom<N> g, const mgrea
       double rhs = b[pt];
 #pragma unroll
       for (int k = 0; k < St::NK; ++k) {
+        if (!((g.mask >> k) & 1u)) continue;   // block-uniform
         bool inl = true, ok = true;
         long long q = pt;
 #pragma unroll
@@ -340,6 +346,7 @@ __global__ void __launch_bounds__(1024) k_line_zebra_chunk(LevelGeom<N> g, const
       double rhs = b[pt];
 #pragma unroll
       for (int k = 0; k < St::NK; ++k) {
+        if (!((g.mask >> k) & 1u)) continue;   // block-uniform
         bool inl = true, ok = true;
         long long q = pt;
 #pragma unroll
@@ -421,6 +428,7 @@ __global__ void __launch_bounds__(256) k_line_zebra_warp(LevelGeom<N> g, const m
       double rhs = b[pt];
 #pragma unroll
       for (int k = 0; k < St::NK; ++k) {
+        if (!((g.mask >> k) & 1u)) continue;   // block-uniform
         bool inl = true, ok = true;
         long long q = pt;
 #pragma unroll
@@ -932,6 +940,7 @@ struct GmresWork {
   DevBuf<double> V, Z, w, hdev;
   double* h = nullptr;   // pinned host scratch, >= restart + 2 doubles
   int restart_alloc = 0;
+  int layout = 0;        // 0: FGMRES(restart_alloc) buffers, 1: BiCGSTAB buffers
 };
 template <class Apply, class Precond, class Dots>
 int fgmres_run(cudaStream_t s, long long n, GmresWork& gw, const double* b, double* x, const econpdes_options& opt,
@@ -941,7 +950,8 @@ int fgmres_run(cudaStream_t s, long long n, GmresWork& gw, const double* b, doub
     int& restart_alloc_ = gw.restart_alloc;
     double* h_ = gw.h;
     const int m = opt.lin_restart > 0 && opt.lin_restart <= 60 ? opt.lin_restart : 40;
-    if (m != restart_alloc_) {
+    if (m != restart_alloc_ || gw.layout != 0) {
+      gw.layout = 0;
       restart_alloc_ = m;
       V_.alloc(static_cast<size_t>(m + 1) * n);
       Z_.alloc(static_cast<size_t>(m) * n);
@@ -1038,6 +1048,102 @@ int fgmres_run(cudaStream_t s, long long n, GmresWork& gw, const double* b, doub
   }
 }
 
+// out = a x + b y + c z (null operands are skipped)
+__global__ void __launch_bounds__(kBlock) k_lincomb(long long n, double a, const double* __restrict__ x, double b,
+                                                    const double* __restrict__ y, double c,
+                                                    const double* __restrict__ z, double* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc = 0.0;
+  if (x != nullptr) acc += a * x[i];
+  if (y != nullptr) acc += b * y[i];
+  if (z != nullptr) acc += c * z[i];
+  out[i] = acc;
+}
+
+// Right-preconditioned BiCGSTAB (options.linear_solver = ECONPDES_LIN_BICGSTAB_MG): two preconditioner
+// applications and two operator applications per iteration, seven work vectors instead of the 2m + 1 of
+// FGMRES(m); same operator / preconditioner / dot-product callbacks and the same acceptance rule as fgmres_run
+// (relative residual <= lin_rtol, or stagnation at the attainable accuracy <= 1e-8).  `iters_out` counts
+// preconditioner applications, so the figure is comparable with FGMRES iterations.
+template <class Apply, class Precond, class Dots>
+int bicgstab_run(cudaStream_t s, long long n, GmresWork& gw, const double* b, double* x, const econpdes_options& opt,
+                 Apply&& spmv_top, Precond&& precondition, Dots&& dots, int* iters_out, double* relres_out) {
+  // V_ holds the vectors the dot products run against: [rhat, t]; Z_ the rest: r, p, v, phat, shat (s shares r)
+  if (gw.layout != 1) {
+    gw.layout = 1;
+    gw.restart_alloc = 2;   // the dot-product scratch of the callers is sized restart_alloc + 2
+    gw.V.alloc(static_cast<size_t>(2) * n);
+    gw.Z.alloc(static_cast<size_t>(5) * n);
+    gw.w.alloc(static_cast<size_t>(n));
+    gw.hdev.alloc(8);
+  }
+  double* rhat = gw.V.p;
+  double* t = gw.V.p + n;
+  double* r = gw.Z.p;
+  double* p = gw.Z.p + n;
+  double* v = gw.Z.p + 2 * n;
+  double* phat = gw.Z.p + 3 * n;
+  double* shat = gw.Z.p + 4 * n;
+  double* hh = gw.h;
+  const int nb = blocks_for(n);
+  EP_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), s));
+  dots(n, 0, rhat, b, hh);
+  const double bnorm = std::sqrt(hh[0]);
+  if (iters_out) *iters_out = 0;
+  if (relres_out) *relres_out = 0.0;
+  if (!(bnorm > 0.0) || !std::isfinite(bnorm)) return std::isfinite(bnorm) ? 0 : 1;
+  EP_CUDA(cudaMemcpyAsync(r, b, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  EP_CUDA(cudaMemcpyAsync(rhat, b, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  EP_CUDA(cudaMemsetAsync(p, 0, n * sizeof(double), s));
+  EP_CUDA(cudaMemsetAsync(v, 0, n * sizeof(double), s));
+  double rho = 1.0, alpha = 1.0, omega = 1.0, relres = 1.0, best = 1.0;
+  int applied = 0, status = 1, since_best = 0;
+  while (applied + 2 <= opt.lin_maxiters) {
+    dots(n, 1, rhat, r, hh);                  // hh[0] = <rhat, r>, hh[1] = <r, r>
+    const double rho_new = hh[0];
+    relres = std::sqrt(hh[1]) / bnorm;
+    if (!std::isfinite(relres)) break;
+    if (relres <= opt.lin_rtol) { status = 0; break; }
+    if (relres < 0.5 * best) { best = relres; since_best = 0; }
+    else if (++since_best >= 8) { status = relres <= 1e-8 ? 0 : 1; break; }   // stagnation
+    if (rho_new == 0.0 || omega == 0.0) break;   // breakdown
+    const double beta = (rho_new / rho) * (alpha / omega);
+    EP_LAUNCH(k_lincomb, nb, kBlock, 0, s, n, 1.0, r, beta, p, -beta * omega, v, p);   // p = r + beta (p - omega v)
+    precondition(p, phat);
+    spmv_top(phat, nullptr, v, 0);
+    applied += 1;
+    dots(n, 1, rhat, v, hh);                  // hh[0] = <rhat, v>
+    if (hh[0] == 0.0 || !std::isfinite(hh[0])) break;
+    alpha = rho_new / hh[0];
+    EP_LAUNCH(k_lincomb, nb, kBlock, 0, s, n, 1.0, r, -alpha, v, 0.0, static_cast<const double*>(nullptr), r);   // s (in r)
+    precondition(r, shat);
+    spmv_top(shat, nullptr, t, 0);
+    applied += 1;
+    dots(n, 2, rhat, r, hh);                  // hh[1] = <t, s>
+    const double ts = hh[1];
+    dots(n, 0, rhat, t, hh);                  // hh[0] = <t, t>
+    const double tt = hh[0];
+    if (!(tt > 0.0) || !std::isfinite(tt)) {  // s is already (numerically) zero: x += alpha phat finishes
+      EP_LAUNCH(k_lincomb, nb, kBlock, 0, s, n, 1.0, x, alpha, phat, 0.0, static_cast<const double*>(nullptr), x);
+      omega = 0.0;
+      continue;
+    }
+    omega = ts / tt;
+    EP_LAUNCH(k_lincomb, nb, kBlock, 0, s, n, 1.0, x, alpha, phat, omega, shat, x);
+    EP_LAUNCH(k_lincomb, nb, kBlock, 0, s, n, 1.0, r, -omega, t, 0.0, static_cast<const double*>(nullptr), r);
+    rho = rho_new;
+  }
+  // the recurrence residual drifts from the true one: judge the solve on b - A x
+  spmv_top(x, b, gw.w.p, 1);
+  dots(n, 0, rhat, gw.w.p, hh);
+  relres = std::sqrt(hh[0]) / bnorm;
+  if (status != 0 || !(relres <= 10 * opt.lin_rtol)) status = (std::isfinite(relres) && relres <= 1e-8) ? 0 : 1;
+  if (iters_out) *iters_out = applied;
+  if (relres_out) *relres_out = relres;
+  return status;
+}
+
 // ---- slab plumbing of the distributed levels -----------------------------------------------
 constexpr int kMaxRanks = 16;
 struct SlabMap {           // every rank's owned range of dimension N-1 at one level
@@ -1102,6 +1208,8 @@ struct Level {
   DevBuf<mgreal> Aown;                  // owned storage for coarse levels
   DevBuf<mgreal> Aperm[N];              // operator in layout d (d >= 1)
   long long Sd[N][N];                   // sizes of layout d
+  unsigned mask = 0xffffffffu;          // LevelGeom::mask of layout 0
+  unsigned mask_d[N];                   // ... of layout d
   Transfer to_coarse;                   // valid if not the coarsest level
   DevBuf<double> x, b, r, tx, tb;       // work vectors (tx/tb: transposed copies)
 };
@@ -1159,8 +1267,10 @@ class KrylovSolver final : public LinearSolver {
     // planes -- so there the rule uses iteration counts only, which are identical everywhere)
     if (!rebuild && n_stale_ >= 3) {
       const double avg_extra = extra_sum_ / n_stale_;
-      const bool costly = c_.dist != nullptr ? avg_extra > 0.5 * base_iters_ + 1.0
-                                             : (setup_ms_ > 0.0 && iter_ms_ > 0.0 && avg_extra * iter_ms_ > setup_ms_);
+      // a set-up costs about 1.5 Krylov iterations on one device (measured: 13.5 ms against 9 ms at 256^3,
+      // 2.1 ms against 1.3 ms at 2048^2).  The rule uses iteration counts only, so the decision -- and with it
+      // every Krylov iterate -- is reproducible from run to run.
+      const bool costly = c_.dist != nullptr ? avg_extra > 0.5 * base_iters_ + 1.0 : avg_extra > 1.5;
       if (costly) {
         rebuild = true;
         lag_off_ = true;
@@ -1280,7 +1390,9 @@ class KrylovSolver final : public LinearSolver {
 
   template <bool BOX>
   void spmv(const Level<N>& L, const double* x, const double* b, double* y, int mode) {
-    EP_LAUNCH((k_spmv<N, BOX, mgreal>), blocks_for(L.l), kBlock, 0, c_.stream, make_geom<N>(L.S), L.A, x, b, y, mode);
+    LevelGeom<N> g = make_geom<N>(L.S);
+    g.mask = L.mask;
+    EP_LAUNCH((k_spmv<N, BOX, mgreal>), blocks_for(L.l), kBlock, 0, c_.stream, g, L.A, x, b, y, mode);
   }
   void spmv(const Level<N>& L, const double* x, const double* b, double* y, int mode) {
     if (L.box) spmv<true>(L, x, b, y, mode); else spmv<false>(L, x, b, y, mode);
@@ -1291,7 +1403,8 @@ class KrylovSolver final : public LinearSolver {
     ProfScope ps("lin spmv", c_.stream);
     Level<N>& L0 = *lev_[0];
     if (c_.dist == nullptr) {   // the Krylov operator is the FP64 Jacobian, not the hierarchy's copy
-      const LevelGeom<N> g0 = make_geom<N>(L0.S);
+      LevelGeom<N> g0 = make_geom<N>(L0.S);
+      g0.mask = L0.mask;
       if (c_.box) EP_LAUNCH((k_spmv<N, true, double>), blocks_for(L0.l), kBlock, 0, c_.stream, g0, top_A_, x, b, y, mode);
       else EP_LAUNCH((k_spmv<N, false, double>), blocks_for(L0.l), kBlock, 0, c_.stream, g0, top_A_, x, b, y, mode);
       return;
@@ -1302,6 +1415,7 @@ class KrylovSolver final : public LinearSolver {
     EP_CUDA(cudaMemcpyAsync(xh_.p, x, L0.l * sizeof(double), cudaMemcpyDeviceToDevice, s));
     c_.exchange_halo(xh_.p);
     LevelGeom<N> g = make_geom<N>(L0.S);
+    g.mask = L0.mask;
     g.open_lo = c_.dist->has_lo();
     g.open_hi = c_.dist->has_hi();
     if (c_.box) EP_LAUNCH((k_spmv<N, true, double>), blocks_for(L0.l), kBlock, 0, s, g, top_A_, xh_.p, b, y, mode);
@@ -1315,12 +1429,14 @@ class KrylovSolver final : public LinearSolver {
     LevelGeom<N> g = make_geom<N>(L.S);
     g.open_lo = L.dist && L.open_lo;
     g.open_hi = L.dist && L.open_hi;
+    g.mask = L.mask;
     return g;
   }
   LevelGeom<N> geom_layout(const Level<N>& L, int d) const {
     LevelGeom<N> g = make_geom<N>(L.Sd[d]);
     g.open_lo = L.dist && L.open_lo;
     g.open_hi = L.dist && L.open_hi;
+    g.mask = d == 0 ? L.mask : L.mask_d[d];
     return g;
   }
   void halo(const Level<N>& L, double* v) { c_.dist->exchange_halo(v, L.plane, L.S[N - 1], c_.stream); }
@@ -1360,6 +1476,7 @@ class KrylovSolver final : public LinearSolver {
       L0->box = c_.box;
       L0->nk = c_.nk;
       L0->Sg_last = c_.S[N - 1];
+      if (c_.box) L0->mask = c_.plane_mask;
       if (dd != nullptr) {
         if (dd->world() > kMaxRanks) throw std::invalid_argument("slab path: at most 16 ranks");
         L0->dist = true;
@@ -1384,8 +1501,15 @@ class KrylovSolver final : public LinearSolver {
       lev_[0]->A = planes;
     } else {   // level 0 of the preconditioner: the Jacobian planes in the hierarchy's storage type
       const long long cnt = static_cast<long long>(c_.nk) * c_.l;
+      if (A0_.cap < static_cast<size_t>(cnt)) {   // planes outside the mask are never written: zero them once
+        A0_.alloc(static_cast<size_t>(cnt));
+        A0_.zero(s);
+      }
       A0_.alloc(static_cast<size_t>(cnt));
-      EP_LAUNCH(k_to_mgreal<mgreal>, 148 * 8, kBlock, 0, s, cnt, planes, A0_.p);
+      for (int k = 0; k < c_.nk; ++k)
+        if ((lev_[0]->mask >> k) & 1u)
+          EP_LAUNCH(k_to_mgreal<mgreal>, 148 * 4, kBlock, 0, s, c_.l, planes + static_cast<size_t>(k) * c_.l,
+                    A0_.p + static_cast<size_t>(k) * c_.l);
       lev_[0]->A = A0_.p;
     }
     size_t li = 0;
@@ -1541,9 +1665,15 @@ class KrylovSolver final : public LinearSolver {
     for (int d = 1; d < ndirs; ++d) {
       int perm[N];
       layout_dims<N>(L.S, d, L.Sd[d], perm);
+      if (L.Aperm[d].cap < static_cast<size_t>(L.nk) * l) {   // planes outside the mask stay zero
+        L.Aperm[d].alloc(static_cast<size_t>(L.nk) * l);
+        L.Aperm[d].zero(s);
+      }
       L.Aperm[d].alloc(static_cast<size_t>(L.nk) * l);
       const TransposeShape ts = transpose_shape<N>(L.S, d);
+      L.mask_d[d] = L.box && L.mask != 0xffffffffu ? 0u : 0xffffffffu;
       for (int k = 0; k < L.nk; ++k) {
+        if (!((L.mask >> k) & 1u)) continue;
         // plane k (offset vector o) lands at the plane whose offset vector is o permuted
         int kd = 0;
         if (L.box) {
@@ -1557,6 +1687,7 @@ class KrylovSolver final : public LinearSolver {
             kd = 1 + 2 * slot + sgn;
           }
         }
+        if (L.mask_d[d] != 0xffffffffu) L.mask_d[d] |= 1u << kd;
         launch_transpose(s, L.A + static_cast<size_t>(k) * l, L.Aperm[d].p + static_cast<size_t>(kd) * l, ts, false);
       }
     }
@@ -1820,6 +1951,12 @@ class KrylovSolver final : public LinearSolver {
 
   // Flexible GMRES(m), right-preconditioned by the V-cycle.
   int fgmres(const double* b, double* x, const econpdes_options& opt, int* iters_out, double* relres_out) {
+    if (opt.linear_solver == ECONPDES_LIN_BICGSTAB_MG)
+      return bicgstab_run(c_.stream, lev_[0]->l, gw_, b, x, opt,
+                          [&](const double* xx, const double* bb, double* yy, int mode) { spmv_top(xx, bb, yy, mode); },
+                          [&](const double* v, double* z) { precondition(v, z); },
+                          [&](long long n, int j, const double* V, const double* w, double* out) { dots(n, j, V, w, out); },
+                          iters_out, relres_out);
     return fgmres_run(c_.stream, lev_[0]->l, gw_, b, x, opt,
                       [&](const double* xx, const double* bb, double* yy, int mode) { spmv_top(xx, bb, yy, mode); },
                       [&](const double* v, double* z) { precondition(v, z); },
@@ -1964,6 +2101,12 @@ class BlockLineSolver final : public LinearSolver {
             double* relres) override {
     planes_ = planes;
     const long long n = g_.l * F;
+    if (opt.linear_solver == ECONPDES_LIN_BICGSTAB_MG)
+      return bicgstab_run(c_.stream, n, gw_, b, x, opt,
+                          [&](const double* xx, const double* bb, double* yy, int mode) { spmv(xx, bb, yy, mode); },
+                          [&](const double* v, double* z) { precondition(v, z); },
+                          [&](long long nn, int j, const double* V, const double* w, double* out) { dots(nn, j, V, w, out); },
+                          iters, relres);
     return fgmres_run(c_.stream, n, gw_, b, x, opt,
                       [&](const double* xx, const double* bb, double* yy, int mode) { spmv(xx, bb, yy, mode); },
                       [&](const double* v, double* z) { precondition(v, z); },

@@ -88,15 +88,97 @@ struct ModelOpsT final : ModelOps {
   int time_slot() const override { return M::TIME_SLOT; }
   int nsaved() const override { return M::NSAVED; }
   bool box() const override { return M::USES_CROSS && M::N > 1; }
-  void residual(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm) const override {
+  unsigned plane_mask() const override {
+    unsigned m = 0;
+    for (int k = 0; k < ipow3(M::N); ++k) {
+      bool axial = true;   // centre and axial neighbours are always kept (the line smoothers solve along them)
+      int nz = 0;
+      for (int d = 0; d < M::N; ++d) nz += ((k / p3(d)) % 3 != 1) ? 1 : 0;
+      axial = nz <= 1;
+      if (axial || M::slot_used(k)) m |= 1u << k;
+    }
+    return m;
+  }
+  // ---- marching sweeps (sweep.cuh) for 2-D / 3-D grids; ECONPDES_MARCH=0 restores the one-thread-per-point kernels
+  static int env_int(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+  }
+  static bool march_on() {
+    static const bool on = env_int("ECONPDES_MARCH", 1) != 0;
+    return on && M::N >= 2;
+  }
+  template <int ROWKIND, int TAME>
+  void residual_march(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm) const {
+    static const int occ = env_int("ECONPDES_MARCH_OCC", 4);
+    if (occ == 3) residual_march_occ<ROWKIND, TAME, 3>(c, y, rs, out, want_norm);
+    else residual_march_occ<ROWKIND, TAME, 4>(c, y, rs, out, want_norm);
+  }
+  template <int ROWKIND, int TAME, int MINB>
+  void residual_march_occ(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm) const {
+    if constexpr (M::N >= 2) {
+      constexpr int RB = 128;
+      static const int force_L = env_int("ECONPDES_MARCH_L", 0);
+      static const int variant = env_int("ECONPDES_MARCH_VARIANT", 0);   // bit 0: L2 prefetch ahead, bit 1: no unrolling
+      const MarchPlan mp = make_march_plan(c.l / c.slab_count, c.slab_count, RB, 148 * MINB, force_L);
+      const int ntiles = mp.ncolblocks * mp.nseg;
+      const int blocks = ntiles < 148 * MINB ? ntiles : 148 * MINB;
+      auto go = [&](auto kernel) {
+        EP_LAUNCH(kernel, blocks, RB, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p, rs, out, c.nw(),
+                  want_norm ? 1 : 0, mp);
+      };
+      switch (variant & 3) {
+        case 0: go(k_residual_march<M, ROWKIND, TAME, 0, 3, 0, RB, MINB>); break;
+        case 1: go(k_residual_march<M, ROWKIND, TAME, 0, 3, 4, RB, MINB>); break;
+        case 2: go(k_residual_march<M, ROWKIND, TAME, 0, 1, 0, RB, MINB>); break;
+        default: go(k_residual_march<M, ROWKIND, TAME, 0, 1, 4, RB, MINB>); break;
+      }
+    }
+  }
+  void residual(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm,
+                bool tame) const override {
+    if (march_on()) {
+      const bool simple = rs.ypost != nullptr && rs.delta_rel == nullptr && rs.is_alg == nullptr && !rs.has_bounds &&
+                          rs.rdelta != 0.0;
+      // tame forms: with boundary derivative values (1) or the default all-zero ones (2)
+      if (!(tame && c.geom_tame)) residual_march<2, 0>(c, y, rs, out, want_norm);
+      else if (c.bc.p != nullptr) residual_march<2, 1>(c, y, rs, out, want_norm);
+      else if (rs.ypost == nullptr) residual_march<0, 2>(c, y, rs, out, want_norm);
+      else if (simple) residual_march<1, 2>(c, y, rs, out, want_norm);
+      else residual_march<2, 2>(c, y, rs, out, want_norm);
+      return;
+    }
     // 128-thread blocks, four per SM (128 registers): finer scheduling granularity than 256 x 2 at the
     // same occupancy (measured 3-8 % faster on the 2048^2 and 256^3 sweeps)
     constexpr int RB = 128;
     EP_LAUNCH((k_residual<M, RB, 4>), sweep_blocks(c.l, RB), RB, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p, rs,
               out, c.nw(), want_norm ? 1 : 0);
   }
+  template <bool BOX, int JMINB>
+  void jacobian_march(const Ctx& c, const double* y, const RowSpec& rs, int per_col, double* planes, double* r0,
+                      bool tame) const {
+    if constexpr (M::N >= 2) {
+      constexpr int JB = 128;
+      static const int force_L = env_int("ECONPDES_MARCH_LJ", 0);
+      const MarchPlan mp = make_march_plan(c.l / c.slab_count, c.slab_count, JB, 148 * JMINB, force_L);
+      const int ntiles = mp.ncolblocks * mp.nseg;
+      const int blocks = ntiles < 148 * JMINB ? ntiles : 148 * JMINB;
+      auto gom = [&](auto kernel) {
+        EP_LAUNCH(kernel, blocks, JB, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p, rs, c.color_eps.p, planes, r0,
+                  mp);
+      };
+      const bool simple = rs.ypost != nullptr && rs.delta_rel == nullptr && rs.is_alg == nullptr && !rs.has_bounds &&
+                          rs.rdelta != 0.0;
+      if (per_col) gom(k_jacobian_march<M, BOX, 1, 0, 2, JB, JMINB>);
+      else if (!(tame && c.geom_tame)) gom(k_jacobian_march<M, BOX, 0, 0, 2, JB, JMINB>);
+      else if (c.bc.p != nullptr) gom(k_jacobian_march<M, BOX, 0, 1, 2, JB, JMINB>);
+      else if (rs.ypost == nullptr) gom(k_jacobian_march<M, BOX, 0, 2, 0, JB, JMINB>);
+      else if (simple) gom(k_jacobian_march<M, BOX, 0, 2, 1, JB, JMINB>);
+      else gom(k_jacobian_march<M, BOX, 0, 2, 2, JB, JMINB>);
+    }
+  }
   void jacobian(const Ctx& c, const double* y, const RowSpec& rs, int eps_policy, double* planes,
-                double* r0) const override {
+                double* r0, bool tame) const override {
     const int per_col = eps_policy == ECONPDES_EPS_PER_COLUMN;
     if (!per_col) {
       const int cblocks = blocks_for(c.l) < 148 * 4 ? blocks_for(c.l) : 148 * 4;   // persistent: 4 blocks per SM
@@ -108,6 +190,17 @@ struct ModelOpsT final : ModelOps {
       }
     }
     constexpr bool BOX = M::USES_CROSS && M::N > 1;
+    if constexpr (M::N >= 2) {
+      static const int jocc = env_int("ECONPDES_MARCH_JOCC", 0);
+      if (march_on() && jocc != 0 && jocc != (M::N >= 3 ? 3 : 4)) {
+        jacobian_march<BOX, (M::N >= 3 ? 4 : 3)>(c, y, rs, per_col, planes, r0, tame);
+        return;
+      }
+      if (march_on()) {
+        jacobian_march<BOX, (M::N >= 3 ? 3 : 4)>(c, y, rs, per_col, planes, r0, tame);
+        return;
+      }
+    }
     // step policy fixed at compile time (branch-free row evaluation), two resident blocks per SM:
     // measured 0.53 -> 0.35 ms at 2048^2 and 2.94 -> 2.47 ms at 256^3 against the run-time-policy kernel
     // 3-D rows (10+ evaluations of a 27-point box) get 170 registers: 128-thread blocks, three per SM

@@ -102,27 +102,31 @@ EP_HD void unravel(long long pt, const GridView<N>& gv, long long* idx) {
   idx[N - 1] = p + gv.off;   // global index along the slab dimension
 }
 
+// spacings (and their reciprocals) of grid index i along dimension d, plus the state coordinate
+template <int N, int RECIP>
+EP_HD void load_axis(const GridView<N>& gv, int d, long long i, PointGeom<N, RECIP>& g, double* state) {
+  g.lo[d] = i == 0;
+  g.hi[d] = i == gv.S[d] - 1;
+  state[d] = gv.x[d][i];
+  if (RECIP >= 1 && gv.tab[d] != nullptr) {
+    // one 64-byte record per grid index, 16-byte aligned: four vector loads
+    const Pair* t = reinterpret_cast<const Pair*>(gv.tab[d] + i * kGeomRows);
+    const Pair t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3];
+    g.dm[d] = t0.a; g.dp[d] = t0.b; g.d[d] = t1.a;
+    g.rdp[d] = t1.b; g.rdm[d] = t2.a; g.rdpd[d] = t2.b; g.rdmd[d] = t3.a; g.rdpm[d] = t3.b;
+    g.dpd[d] = g.dp[d] * g.d[d];
+    g.dmd[d] = g.dm[d] * g.d[d];
+    g.dpm[d] = g.dp[d] * g.dm[d];
+  } else {
+    spacing(gv.x[d], i, gv.S[d], g.dm[d], g.dp[d], g.d[d]);
+    finish_axis(g, d);
+  }
+}
+
 template <int N, int RECIP>
 EP_HD void load_geom(const GridView<N>& gv, const long long* idx, PointGeom<N, RECIP>& g, double* state) {
 #pragma unroll
-  for (int d = 0; d < N; ++d) {
-    g.lo[d] = idx[d] == 0;
-    g.hi[d] = idx[d] == gv.S[d] - 1;
-    state[d] = gv.x[d][idx[d]];
-    if (RECIP >= 1 && gv.tab[d] != nullptr) {
-      // one 64-byte record per grid index, 16-byte aligned: four vector loads
-      const Pair* t = reinterpret_cast<const Pair*>(gv.tab[d] + idx[d] * kGeomRows);
-      const Pair t0 = t[0], t1 = t[1], t2 = t[2], t3 = t[3];
-      g.dm[d] = t0.a; g.dp[d] = t0.b; g.d[d] = t1.a;
-      g.rdp[d] = t1.b; g.rdm[d] = t2.a; g.rdpd[d] = t2.b; g.rdmd[d] = t3.a; g.rdpm[d] = t3.b;
-      g.dpd[d] = g.dp[d] * g.d[d];
-      g.dmd[d] = g.dm[d] * g.d[d];
-      g.dpm[d] = g.dp[d] * g.dm[d];
-    } else {
-      spacing(gv.x[d], idx[d], gv.S[d], g.dm[d], g.dp[d], g.d[d]);
-      finish_axis(g, d);
-    }
-  }
+  for (int d = 0; d < N; ++d) load_axis(gv, d, idx[d], g, state);
   finish_geom(g);
 }
 
@@ -209,14 +213,23 @@ EP_HD double apply_row_terms(double g, double y, const RowTerms& t) {
   return r;
 }
 
+// Compile-time forms of the row terms (ROWKIND): 0 = R = G; 1 = G - (ypost - y)/delta with a finite delta
+// whose reciprocal the caller formed (t.rdelta), no algebraic rows, no bounds; 2 = general.
+template <int ROWKIND>
+EP_HD double apply_row_terms_k(double g, double y, const RowTerms& t) {
+  if (ROWKIND == 0) return g;
+  if (ROWKIND == 1) return g - mdiv(t.ypost - y, t.delta, t.rdelta);
+  return apply_row_terms(g, y, t);
+}
+
 // Residual of all F unknowns at one point from the boxes w[f][3^N].
-template <class M, bool SAVE, class G>
+template <class M, bool SAVE, int TAME = 0, class G>
 EP_HD void eval_point(const typename M::Pre& pre, const G& g,
                       const double (*w)[ipow3(M::N)], const double (*bc_lo)[M::N], const double (*bc_hi)[M::N],
                       double* out, double* sv) {
   Deriv<M::N> u[M::F];
 #pragma unroll
-  for (int f = 0; f < M::F; ++f) differentiate(w[f], g, bc_lo[f], bc_hi[f], u[f]);
+  for (int f = 0; f < M::F; ++f) differentiate<TAME>(w[f], g, bc_lo[f], bc_hi[f], u[f]);
   M::template eval<SAVE>(pre, u, out, sv);
 }
 
@@ -254,7 +267,10 @@ EP_HD int ncolors_grid(const GridView<N>& gv) {
 // value is identical, so kernels that kept it skip that evaluation).
 // POLICY: -1 = `eps_per_column` decides at run time; 0 = per-color steps from eps_table, with their
 // reciprocals in reps_table (required); 1 = per-column steps.  The compile-time forms are branch-free.
-template <class M, bool BOX, bool HAVE_R0 = false, int POLICY = -1, class G, class Emit>
+// SKIP_UNUSED: entries of box slots the model never reads (M::slot_used) are not emitted at all (the caller's
+// planes were zeroed once and nothing else writes them).
+template <class M, bool BOX, bool HAVE_R0 = false, int POLICY = -1, int TAME = 0, int ROWKIND = 2,
+          bool SKIP_UNUSED = false, class G, class Emit>
 EP_HD void jacobian_point(const typename M::Pre& pre, const G& g, const long long* idx,
                           const GridView<M::N>& gv, double (*w)[ipow3(M::N)], const double (*bc_lo)[M::N],
                           const double (*bc_hi)[M::N], const RowTerms* rt, const double* eps_table,
@@ -264,9 +280,9 @@ EP_HD void jacobian_point(const typename M::Pre& pre, const G& g, const long lon
   using St = Stencil<N, BOX>;
   if (!HAVE_R0) {
     double g0[F];
-    eval_point<M, false>(pre, g, w, bc_lo, bc_hi, g0, nullptr);
+    eval_point<M, false, TAME>(pre, g, w, bc_lo, bc_hi, g0, nullptr);
 #pragma unroll
-    for (int f = 0; f < F; ++f) r0[f] = apply_row_terms(g0[f], w[f][C], rt[f]);
+    for (int f = 0; f < F; ++f) r0[f] = apply_row_terms_k<ROWKIND>(g0[f], w[f][C], rt[f]);
   }
   const int ncg = ncolors_grid<N>(gv);
   int i3[N];
@@ -287,6 +303,7 @@ EP_HD void jacobian_point(const typename M::Pre& pre, const G& g, const long lon
       }
       const int slot = St::boxslot(k);
       // entries outside the grid: skipped, or (branch-free forms) evaluated anyway and zeroed below
+      if (SKIP_UNUSED && !M::slot_used(slot)) continue;
       if ((POLICY < 0 && !ok) || !M::slot_used(slot)) {
 #pragma unroll
         for (int fout = 0; fout < F; ++fout) emit(k, fin, fout, 0.0);
@@ -304,10 +321,10 @@ EP_HD void jacobian_point(const typename M::Pre& pre, const G& g, const long lon
       }
       w[fin][slot] = saved + eps;
       double g1[F];
-      eval_point<M, false>(pre, g, w, bc_lo, bc_hi, g1, nullptr);
+      eval_point<M, false, TAME>(pre, g, w, bc_lo, bc_hi, g1, nullptr);
 #pragma unroll
       for (int fout = 0; fout < F; ++fout) {
-        const double r1 = apply_row_terms(g1[fout], w[fout][C], rt[fout]);
+        const double r1 = apply_row_terms_k<ROWKIND>(g1[fout], w[fout][C], rt[fout]);
         const double q = (POLICY >= 0 || reps != 0.0) ? mdiv(r1 - r0[fout], eps, reps) : (r1 - r0[fout]) / eps;
         emit(k, fin, fout, ok ? q : 0.0);
       }

@@ -175,8 +175,10 @@ int econpdes_solve_stationary(const econpdes_problem* problem, const econpdes_op
  *     (_check_time_grid, :241-251).  Outputs, caller-allocated: solution (S.., F, ntaus) and, if not
  *     NULL, saved (S.., NSAVED, ntaus), column-major with time slowest; residual_norms[ntaus]
  *     (entry 0 stays 0, entry i is the Newton residual of the step that produced time i-1, as in the
- *     reference); newton_iters[ntaus] (may be NULL).  The model functors take no time argument
- *     (the reference's 3-argument pde(state, u, t) form is not on the device path). --- */
+ *     reference); newton_iters[ntaus] (may be NULL).  Functors of the reference's 3-argument form
+ *     pde(state, u, t) (src/pdesolve.jl:253-260) read the current time from the parameter slot the model
+ *     declares (econpdes_model_info: time_slot); the driver stores taus[i] there before the step from
+ *     time i to i-1, as pde_onestep does (src/pdesolve.jl:195).  Two-argument functors ignore it. --- */
 int econpdes_solve_backward(const econpdes_problem* problem, const econpdes_options* options, const double* taus,
                             int32_t ntaus, double* solution, double* saved, double* residual_norms,
                             int32_t* newton_iters, double* device_ms, int64_t* kernel_launches);
