@@ -3,17 +3,22 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (config.workload): BASELINE.json configs[3], the batched calibration sweep -- 16 384
-independent Campbell-Cochrane habit problems of 998 grid points PER GPU (weak scaling: each
-rank solves its own contiguous slice of the sweep, no data-path collective).  One "step" is
-one full pass of the hot path over the batch: every problem is solved to convergence by the
-pseudo-transient Newton loop (4 outer steps / 8 Newton solves each under reference
-semantics).  metric = Newton solves per second, whole job.
+Workload (config.workload): BASELINE.json configs[3] verbatim, the batched calibration sweep -- 16 384
+independent Campbell-Cochrane habit problems of 998 grid points IN TOTAL, sharded across the GPUs
+("scaling": "strong": rank r of N solves a contiguous slice of 16384/N problems, no data-path
+collective).  `--scaling weak` gives every GPU 16 384 problems instead; at N > 1 the default run adds
+that measurement as the extra key "weak".  One "step" is one full pass of the hot path over the batch:
+every problem is solved to convergence by the pseudo-transient Newton loop (4 outer steps / 8 Newton
+solves each under reference semantics).  metric = Newton solves per second, whole job.
 
   value     inputs already resident in HBM, device time (CUDA events on the launching stream)
-  e2e       same metric through the C-ABI call with pinned HOST buffers (H2D + solve + D2H)
+  e2e       same metric through the C-ABI call with pinned HOST buffers (H2D + solve + D2H).  The sweep is
+            described compactly (econpdes_batch_inputs: per problem six parameters, the lower end of the
+            linear grid segment and the 99 log-spaced points; the 899-point range is built on the device,
+            the guess is a scalar), the solution comes back in full
   roofline  fused batched kernel: algorithmic bytes / launch time vs measured HBM peak
   cpu_baseline  the plain-C CPU oracle (port of the reference algorithm) on a bounded sample, 1 core
+  configs   (N = 1) full pdesolve of configs C2 (64 x 4096) and C3 (1024^2, 2048^2) with outcome and counts
 """
 import argparse
 import ctypes as C
@@ -72,6 +77,8 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def __enter__(self):
+        if self.index < 0:   # not sampling
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -103,6 +110,57 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def _bind_to_gpu_numa(local):
+    """Pin this process to the CPU cores next to its GPU (PCI root complex / NUMA node), so the pinned host
+    buffers it allocates afterwards live there (first touch) and eight ranks do not share one node's memory
+    controllers and PCIe root.  Best effort: a container may expose only part of the machine."""
+    info = {"bound": False}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        with open(base + "/numa_node") as f:
+            info["numa_node"] = int(f.read().strip())
+        with open(base + "/local_cpulist") as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        info["allowed_cpus"] = len(allowed)
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            info["bound"] = True
+        info["cpus"] = len(use) if use else len(allowed)
+    except Exception as e:   # no sysfs / no permission: run unbound
+        info["error"] = type(e).__name__
+    return info
+
+
+def _copy_bandwidth(torch, nbytes=64 << 20, reps=5):
+    """Host<->device copy rate of this rank from page-locked memory (GB/s), all ranks at the same time."""
+    h = torch.empty(nbytes // 8, dtype=torch.float64, pin_memory=True)
+    d = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
+    out = {}
+    for name, (src, dst) in (("h2d", (h, d)), ("d2h", (d, h))):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = nbytes * reps / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    return out
+
+
 def _dist():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -119,20 +177,18 @@ def run_ours(args):
     from econpdes_b200.pdesolve import _options
 
     rank, world, local = _dist()
+    torch.cuda.set_device(local)
+    numa = _bind_to_gpu_numa(local)   # before any pinned allocation
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
         dist = None
-        torch.cuda.set_device(local)
     lib = L.load()
     L.check(lib.econpdes_set_device(local))
-    from econpdes_b200.sharding import Reducer, weak_slice
-    B, S = args.problems, POINTS
-    first, _ = weak_slice(B, rank)
-    params, grids, guess = EX.campbell_cochrane_sweep(first, B)
+    from econpdes_b200.sharding import Reducer, shard_range, weak_slice
+    S = POINTS
     red = Reducer(dist, "cuda")
     opts = _options(math.sqrt(np.finfo(float).eps), 100, {})
     mid = L.check(lib.econpdes_model_id(CampbellCochraneModel.name.encode()))
@@ -145,65 +201,112 @@ def run_ours(args):
 
     allmax, allsum = red.max, red.sum
 
-    # ---- device-resident leg (value) ----
-    h = C.c_void_p()
-    L.check(lib.econpdes_batch_create(mid, B, S, C.byref(h)))
-    L.check(lib.econpdes_batch_upload(h, L.dptr(params), L.dptr(grids), L.dptr(guess)))
-    ms = C.c_double()
-    for _ in range(args.warmup):
-        L.check(lib.econpdes_batch_solve(h, C.byref(opts), C.byref(ms)))
-    launches0 = lib.econpdes_total_kernel_launches()
-    barrier()
-    dev_ms = 0.0
-    with ClockSampler(local) as clocks:
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            L.check(lib.econpdes_batch_solve(h, C.byref(opts), C.byref(ms)))
-            dev_ms += ms.value
-        barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-    launches = lib.econpdes_total_kernel_launches() - launches0
-    nn = np.empty(B, dtype=np.int32)
-    no = np.empty(B, dtype=np.int32)
-    rn = np.empty(B)
-    L.check(lib.econpdes_batch_download(h, None, L.dptr(rn), None, no.ctypes.data_as(L.c_int32_p),
-                                        nn.ctypes.data_as(L.c_int32_p), None, 0, None))
-    lib.econpdes_batch_destroy(h)
-    newton_rank = float(nn.sum())
-    converged_rank = float((rn <= opts.abstol).sum())
-    dev_ms_max = allmax(dev_ms)
-    wall_ms_max = allmax(wall_ms)
-    newton_total = allsum(newton_rank)
-    converged_total = allsum(converged_rank)
-    ms_per_step = dev_ms_max / args.steps
-    value = newton_total / (ms_per_step * 1e-3)
-
-    # ---- end-to-end leg through the C-ABI with pinned host buffers ----
     def pinned(a):
         t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
         t.numpy()[...] = a
         return t
-    tp, tg, tu = pinned(params), pinned(grids), pinned(guess)
-    tsol = torch.empty((B, S), dtype=torch.float64, pin_memory=True)
-    trn = torch.empty(B, dtype=torch.float64, pin_memory=True)
-    ex = np.empty(B, dtype=np.int32)
 
-    def e2e_step():
-        L.check(lib.econpdes_solve_batched(mid, B, S, L.dptr(tp.numpy()), L.dptr(tg.numpy()), L.dptr(tu.numpy()),
-                                           C.byref(opts), L.dptr(tsol.numpy()), L.dptr(trn.numpy()),
-                                           ex.ctypes.data_as(L.c_int32_p), no.ctypes.data_as(L.c_int32_p),
-                                           nn.ctypes.data_as(L.c_int32_p)))
-    for _ in range(max(1, args.warmup // 2)):
-        e2e_step()
+    def measure_sweep(first, B, sample_clocks):
+        """Problems [first, first + B) of the sweep on this rank: device-resident leg, then the end-to-end leg."""
+        params, grids, guess = EX.campbell_cochrane_sweep(first, B)
+        # ---- device-resident leg (value) ----
+        h = C.c_void_p()
+        L.check(lib.econpdes_batch_create(mid, B, S, C.byref(h)))
+        L.check(lib.econpdes_batch_upload(h, L.dptr(params), L.dptr(grids), L.dptr(guess)))
+        ms = C.c_double()
+        for _ in range(args.warmup):
+            L.check(lib.econpdes_batch_solve(h, C.byref(opts), C.byref(ms)))
+        launches0 = lib.econpdes_total_kernel_launches()
+        barrier()
+        dev_ms = 0.0
+        with ClockSampler(local if sample_clocks else -1) as clocks:
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                L.check(lib.econpdes_batch_solve(h, C.byref(opts), C.byref(ms)))
+                dev_ms += ms.value
+            barrier()
+            wall_ms = (time.perf_counter() - t0) * 1e3
+        launches = lib.econpdes_total_kernel_launches() - launches0
+        nn = np.empty(B, dtype=np.int32)
+        no = np.empty(B, dtype=np.int32)
+        rn = np.empty(B)
+        L.check(lib.econpdes_batch_download(h, None, L.dptr(rn), None, no.ctypes.data_as(L.c_int32_p),
+                                            nn.ctypes.data_as(L.c_int32_p), None, 0, None))
+        lib.econpdes_batch_destroy(h)
+        out = {"B": B, "dev_ms": dev_ms, "newton_rank": float(nn.sum()), "outer_rank": float(no.sum()),
+               "converged_rank": float((rn <= opts.abstol).sum()), "launches": int(launches),
+               "clocks": clocks.summary() if sample_clocks else None}
+        out["dev_ms_max"] = allmax(dev_ms)
+        out["wall_ms_max"] = allmax(wall_ms)
+        out["newton_total"] = allsum(out["newton_rank"])
+        out["converged_total"] = allsum(out["converged_rank"])
+        out["problems_total"] = allsum(float(B))
+        out["ms_per_step"] = out["dev_ms_max"] / args.steps
+        out["value"] = out["newton_total"] / (out["ms_per_step"] * 1e-3)
+
+        # ---- end-to-end leg through the C ABI with pinned host buffers, compact inputs ----
+        p2, lo, pts, n_range, fill = EX.campbell_cochrane_sweep_compact(first, B)
+        tp, tlo, tpts = pinned(p2), pinned(lo), pinned(pts)
+        tsol = torch.empty((B, S), dtype=torch.float64, pin_memory=True)
+        trn = torch.empty(B, dtype=torch.float64, pin_memory=True)
+        ex = np.empty(B, dtype=np.int32)
+        inp = L.BatchInputs()
+        inp.params, inp.grids, inp.n_range = L.dptr(tp.numpy()), None, int(n_range)
+        inp.range_lo, inp.points, inp.guess, inp.guess_fill = L.dptr(tlo.numpy()), L.dptr(tpts.numpy()), None, float(fill)
+
+        def e2e_step():
+            L.check(lib.econpdes_solve_batched_inputs(mid, B, S, C.byref(inp), C.byref(opts), L.dptr(tsol.numpy()),
+                                                      L.dptr(trn.numpy()), ex.ctypes.data_as(L.c_int32_p),
+                                                      no.ctypes.data_as(L.c_int32_p), nn.ctypes.data_as(L.c_int32_p)))
+        for _ in range(max(1, args.warmup // 2)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        out["e2e_ms"] = allmax((time.perf_counter() - t0) * 1e3) / args.steps
+        out["e2e_value"] = out["newton_total"] / (out["e2e_ms"] * 1e-3)
+        out["h2d"] = int(p2.nbytes + lo.nbytes + pts.nbytes)
+        out["d2h"] = int(tsol.numpy().nbytes + trn.numpy().nbytes + ex.nbytes + no.nbytes + nn.nbytes)
+        assert float((trn.numpy() <= opts.abstol).sum()) == out["converged_rank"]
+
+        # the same call with explicit grids and guesses (what round 1 measured): B x S doubles twice over PCIe
+        if args.e2e_explicit:
+            tg, tu = pinned(grids), pinned(guess)
+
+            def e2e_explicit_step():
+                L.check(lib.econpdes_solve_batched(mid, B, S, L.dptr(tp.numpy()), L.dptr(tg.numpy()), L.dptr(tu.numpy()),
+                                                   C.byref(opts), L.dptr(tsol.numpy()), L.dptr(trn.numpy()),
+                                                   ex.ctypes.data_as(L.c_int32_p), no.ctypes.data_as(L.c_int32_p),
+                                                   nn.ctypes.data_as(L.c_int32_p)))
+            e2e_explicit_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                e2e_explicit_step()
+            barrier()
+            ems = allmax((time.perf_counter() - t0) * 1e3) / args.steps
+            out["e2e_explicit"] = {"value": out["newton_total"] / (ems * 1e-3), "ms_per_step": ems,
+                                   "h2d_bytes_per_step": int(params.nbytes + grids.nbytes + guess.nbytes),
+                                   "d2h_bytes_per_step": out["d2h"]}
+        lib.econpdes_release_workspace()
+        return out
+
+    total = args.problems
+    if args.scaling == "strong":
+        first, last = shard_range(total, rank, world)
+    else:
+        first, last = weak_slice(total, rank)
+    main = measure_sweep(first, last - first, True)
+    weak = None
+    if args.scaling == "strong" and world > 1 and not args.no_weak:
+        wf, wl = weak_slice(total, rank)
+        weak = measure_sweep(wf, wl - wf, False)
     barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_ms = allmax((time.perf_counter() - t0) * 1e3) / args.steps
-    e2e_value = newton_total / (e2e_ms * 1e-3)
-    h2d = int(params.nbytes + grids.nbytes + guess.nbytes)
-    d2h = int(tsol.numpy().nbytes + trn.numpy().nbytes + ex.nbytes + no.nbytes + nn.nbytes)
+    bw = _copy_bandwidth(torch)
+    bw_min = {k: -allmax(-v) for k, v in bw.items()}
+    bw_sum = {k: allsum(v) for k, v in bw.items()}
 
     # ---- config C5: ONE 256^3 grid, slab-decomposed over the same ranks (strong scaling) ----
     c5 = None
@@ -215,31 +318,47 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peak, peak_src = _peaks()
-    alg_bytes = float(S) * (BYTES_PER_NEWTON_POINT * newton_rank + BYTES_PER_SWEEP_POINT * float(no.sum() + B))
-    kernel_ms = dev_ms / args.steps
+    B = main["B"]
+    alg_bytes = float(S) * (BYTES_PER_NEWTON_POINT * main["newton_rank"] + BYTES_PER_SWEEP_POINT * (main["outer_rank"] + B))
+    kernel_ms = main["dev_ms"] / args.steps
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     traffic = _ncu_traffic_bytes("r01_batched_kernel_P4_ncu_full.json", "k_batched_pdesolve_1d")
+    if traffic is not None:
+        traffic *= B / float(PROBLEMS_PER_GPU)   # the capture is of a 16 384-problem launch
+    per = "total" if args.scaling == "strong" else "per GPU"
     line = {
-        "metric": "newton_solves_per_sec", "value": value, "unit": "Newton solves/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "metric": "newton_solves_per_sec", "value": main["value"], "unit": "Newton solves/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "C4 batched calibration sweep: independent Campbell-Cochrane habit 1-D problems, "
                                "full pdesolve per problem",
-                   "problems_per_gpu": B, "points_per_problem": S, "problems_total": B * world,
-                   "newton_solves_per_step": newton_total, "converged": converged_total,
+                   "problems": f"{total} {per}", "problems_per_gpu": B, "points_per_problem": S,
+                   "problems_total": int(main["problems_total"]),
+                   "newton_solves_per_step": main["newton_total"], "converged": main["converged_total"],
                    "parallelism": f"batch-sharded x{world} (no collective)",
-                   "l2": "inputs larger than L2 (grid+guess 262 MB per step, solution 131 MB)"},
-        "wall_ms_per_step": wall_ms_max / args.steps,
-        "e2e": {"value": e2e_value, "unit": "Newton solves/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "api": "econpdes_solve_batched (C ABI, pinned host buffers)"},
-        "gpu_launches": int(launches),
-        "clocks": clocks.summary(),
+                   "l2": "inputs larger than L2 between timed steps at N = 1 (grid + guess 262 MB, solution 131 MB per "
+                         "16 384 problems); smaller shards are streamed once per step from HBM all the same: nothing is "
+                         "re-used across steps on chip"},
+        "wall_ms_per_step": main["wall_ms_max"] / args.steps,
+        "e2e": {"value": main["e2e_value"], "unit": "Newton solves/s", "ms_per_step": main["e2e_ms"],
+                "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"],
+                "api": "econpdes_solve_batched_inputs (C ABI, pinned host buffers; compact inputs: parameters + "
+                       "grid end points + 99 explicit grid points per problem, scalar guess; full solution back)"},
+        "gpu_launches": main["launches"],
+        "clocks": main["clocks"],
         "roofline": {"bound": "hbm", "kernel": "k_batched_pdesolve_1d<CampbellCochrane, P=4>", "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "fused on-chip solve: algorithmic bytes never reach HBM; DRAM traffic is grid+guess in, solution out"},
-        "pdesolves_per_sec": B * world / (ms_per_step * 1e-3),
+        "pdesolves_per_sec": main["problems_total"] / (main["ms_per_step"] * 1e-3),
+        "host": {"numa_binding_rank0": numa, "pinned_copy_gbs_per_rank_min": bw_min, "pinned_copy_gbs_all_ranks": bw_sum},
     }
+    if "e2e_explicit" in main:
+        line["e2e_explicit_inputs"] = main["e2e_explicit"]
+    if weak is not None:
+        line["weak"] = {"scaling": "weak", "problems_per_gpu": weak["B"], "value": weak["value"],
+                        "ms_per_step": weak["ms_per_step"], "e2e_value": weak["e2e_value"], "e2e_ms_per_step": weak["e2e_ms"],
+                        "h2d_bytes_per_step": weak["h2d"], "d2h_bytes_per_step": weak["d2h"]}
     if c5 is not None:
         line["c5_slab"] = c5
     if world == 1 and not args.no_kernels:
@@ -247,11 +366,44 @@ def run_ours(args):
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_kernels
         line["kernels"] = bench_kernels.measure(reps=3)
+    if world == 1 and not args.no_configs:
+        line["configs"] = full_configs()
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args.cpu_sample, 1)
     _emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def full_configs():
+    """Full `pdesolve` of BASELINE.json configs[1] (consumption-saving, 64 x 4096) and configs[2] (Bansal-Yaron at
+    1024^2 and 2048^2) under reference semantics, plus the 2048^2 run with per-column finite-difference steps
+    (documented robust option, not reference parity): outcome, counts, device time, quality of the Krylov solves."""
+    import econpdes_b200 as E
+    from econpdes_b200 import _lib as L
+    from econpdes_b200 import examples as EX
+    from econpdes_b200 import models as PM
+    out = {}
+
+    def run(tag, model, g, gu, **kw):
+        t0 = time.perf_counter()
+        r = E.pdesolve(model, g, gu, verbose=False, warn=False, **kw)
+        wall = (time.perf_counter() - t0) * 1e3
+        out[tag] = {"converged": bool(r.converged), "residual_norm": float(r.residual_norm), "exit_reason": int(r.exit_reason),
+                    "outer_steps": int(r.n_outer), "rejected_steps": int(sum(1 for row in r.log if row["status"] != 0)),
+                    "newton_solves": int(r.n_newton), "krylov_iterations": int(r.n_linear_iters),
+                    "linear_solves": int(r.n_linear_solves), "linear_solves_above_1e-11": int(r.n_linear_loose),
+                    "max_linear_relres": float(r.lin_max_relres), "device_ms": float(r.device_ms), "wall_ms": wall,
+                    "kernel_launches": int(r.kernel_launches)}
+
+    g, gu = EX.ahlm_diffusion_grid(64, 4096)
+    run("C2 consumption-saving 64x4096", PM.AchdouHanLasryLionsMollModel_Diffusion(), g, gu)
+    for n in (1024, 2048):
+        g, gu = EX.bansal_yaron_grid(n, n)
+        run(f"C3 bansal-yaron {n}x{n}", PM.BansalYaronModel(), g, gu)
+    g, gu = EX.bansal_yaron_grid(2048, 2048)
+    run("C3 bansal-yaron 2048x2048 eps_policy=per_column", PM.BansalYaronModel(), g, gu, eps_policy=L.EPS_PER_COLUMN)
+    return out
 
 
 def c5_slab(args, dist, rank, world, local, allmax):
@@ -326,7 +478,10 @@ def run_reference(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C4 batched calibration sweep: independent Campbell-Cochrane habit 1-D problems, "
-                                   "full pdesolve per problem", "points_per_problem": POINTS,
+                                   "full pdesolve per problem",
+                       "problems": f"{args.problems} total", "problems_per_gpu": sample, "points_per_problem": POINTS,
+                       "problems_total": sample,
+                       "parallelism": f"{threads} host threads, one problem each at a time (no GPU)",
                        "sample_problems_per_step": sample},
             "cpu_baseline": {"value": value, "unit": "Newton solves/s", "cores": threads, "kind": "port",
                              "sample": f"{sample} sweep problems per step, {threads} threads, plain-C oracle"},
@@ -374,12 +529,18 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--problems", type=int, default=PROBLEMS_PER_GPU, help="problems per GPU")
+    ap.add_argument("--problems", type=int, default=PROBLEMS_PER_GPU, help="problems of the sweep (see --scaling)")
     ap.add_argument("--cpu-sample", type=int, default=4096)
     ap.add_argument("--ref-sample", type=int, default=16384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernels", action="store_true", help="skip the grid-kernel roofline leg")
     ap.add_argument("--no-c5", action="store_true", help="skip the slab-decomposed 3-D solve")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: --problems in total, sharded over the GPUs (BASELINE config 4); weak: --problems per GPU")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1, strong scaling: skip the extra weak-scaling measurement")
+    ap.add_argument("--no-configs", action="store_true", help="skip the full C2 / C3 solves (N = 1)")
+    ap.add_argument("--e2e-explicit", action="store_true",
+                    help="also time the end-to-end call with explicit B x S grids and guesses")
     ap.add_argument("--c5-n", type=int, default=256, help="points per axis of the C5 grid")
     args = ap.parse_args()
     with _OneJsonLine() as out:

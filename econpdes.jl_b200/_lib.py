@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeconpdes_cuda.so")
 
 MAX_DIMS = 3
-ABI_VERSION = 2   # ECONPDES_ABI_VERSION of include/econpdes_cuda.h these mirrors were written against
+ABI_VERSION = 3   # ECONPDES_ABI_VERSION of include/econpdes_cuda.h these mirrors were written against
 
 OK, E_INVALID, E_NAN_GUESS, E_NO_DEVICE, E_CUDA, E_UNSUPPORTED, E_NCCL = 0, -1, -2, -3, -4, -5, -6
 EXIT_CONVERGED, EXIT_ALREADY_ZERO, EXIT_MAXITERS, EXIT_BELOW_MIN_DELTA, EXIT_INF_STEP_FAILED = range(5)
@@ -50,7 +50,13 @@ class Result(C.Structure):
                 ("log_capacity", C.c_int32), ("log_len", C.c_int32), ("residual_norm", C.c_double),
                 ("converged", C.c_int32), ("exit_reason", C.c_int32), ("n_outer", C.c_int32), ("n_newton", C.c_int32),
                 ("n_linear_iters", C.c_int64), ("kernel_launches", C.c_int64), ("device_ms", C.c_double),
-                ("sign_flags", C.c_int32), ("nonmonotone_entries", C.c_int32), ("nonmonotone_max", C.c_double)]
+                ("sign_flags", C.c_int32), ("nonmonotone_entries", C.c_int32), ("nonmonotone_max", C.c_double),
+                ("n_linear_solves", C.c_int32), ("n_linear_loose", C.c_int32), ("lin_max_relres", C.c_double)]
+
+
+class BatchInputs(C.Structure):
+    _fields_ = [("params", c_double_p), ("grids", c_double_p), ("n_range", C.c_int32), ("range_lo", c_double_p),
+                ("points", c_double_p), ("guess", c_double_p), ("guess_fill", C.c_double)]
 
 
 SIGN_WHOLE_SYSTEM = 1 << 30
@@ -94,6 +100,10 @@ SYMBOLS = {
     "econpdes_solve_batched": (C.c_int, [C.c_int, C.c_int64, C.c_int64, c_double_p, c_double_p, c_double_p,
                                          C.POINTER(Options), c_double_p, c_double_p, c_int32_p, c_int32_p,
                                          c_int32_p]),
+    "econpdes_batch_upload_inputs": (C.c_int, [C.c_void_p, C.POINTER(BatchInputs)]),
+    "econpdes_solve_batched_inputs": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.POINTER(BatchInputs),
+                                                C.POINTER(Options), c_double_p, c_double_p, c_int32_p, c_int32_p,
+                                                c_int32_p]),
     "econpdes_release_workspace": (None, []),
     "econpdes_set_batch_points_per_thread": (C.c_int, [C.c_int]),
     "econpdes_selftest_reciprocal": (C.c_int, [C.c_uint64, C.c_int64, C.POINTER(C.c_int64)]),

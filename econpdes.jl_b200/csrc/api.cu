@@ -104,6 +104,11 @@ struct econpdes_batch {
   int* err_host = nullptr;         // [4][B]: error, exit_reason, n_outer, n_newton
   double* rn_host = nullptr;       // [B]
   DevBuf<double> params, grids, guess, solution, residual_norm;
+  // compact inputs (econpdes_batch_inputs): grids built on the device, broadcast guess
+  DevBuf<double> range_lo, points;
+  int n_range = 0;
+  bool explicit_grids = true, explicit_guess = true;
+  double guess_fill = 0.0;
   DevBuf<int> exit_reason, n_outer, n_newton, error, log_len;
   DevBuf<econpdes_log_row> log;
   int log_capacity = 0;
@@ -436,9 +441,7 @@ int econpdes_batch_create(int model_id, int64_t nproblems, int64_t npoints, econ
     EP_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     const size_t B = static_cast<size_t>(nproblems), S = static_cast<size_t>(npoints);
     b->params.alloc(B * (b->nparams > 0 ? b->nparams : 1));
-    b->grids.alloc(B * S);
-    b->guess.alloc(B * S);
-    b->solution.alloc(B * S);
+    b->solution.alloc(B * S);   // grids / guess: allocated by the upload that brings them
     b->residual_norm.alloc(B);
     b->exit_reason.alloc(B);
     b->n_outer.alloc(B);
@@ -462,6 +465,60 @@ int econpdes_batch_upload(econpdes_batch* b, const double* params, const double*
     }
     b->grids.upload(grids, B * S, b->stream);
     b->guess.upload(guess, B * S, b->stream);
+    b->explicit_grids = b->explicit_guess = true;
+    EP_CUDA(cudaStreamSynchronize(b->stream));
+    return ECONPDES_OK;
+  });
+}
+
+// validates a compact input description against the batch shape and sizes the device buffers it needs
+static void batch_accept_inputs(econpdes_batch* b, const econpdes_batch_inputs* in) {
+  if (!in) throw std::invalid_argument("null inputs");
+  const size_t B = static_cast<size_t>(b->B), S = static_cast<size_t>(b->S);
+  if (b->nparams > 0 && !in->params) throw std::invalid_argument("null params");
+  if (in->grids != nullptr) {
+    b->explicit_grids = true;
+    b->grids.alloc(B * S);
+  } else {
+    if (in->n_range < 1 || in->n_range >= b->S) throw std::invalid_argument("n_range must lie in [1, npoints)");
+    if (!in->range_lo || !in->points) throw std::invalid_argument("null range_lo / points");
+    b->explicit_grids = false;
+    b->n_range = in->n_range;
+    b->range_lo.alloc(B);
+    b->points.alloc(B * (S - static_cast<size_t>(in->n_range)));
+  }
+  if (in->guess != nullptr) {
+    b->explicit_guess = true;
+    b->guess.alloc(B * S);
+  } else {
+    b->explicit_guess = false;
+    b->guess_fill = in->guess_fill;
+  }
+}
+
+// queues the host->device copies of problems [first, last) on stream s
+static void batch_upload_slice(econpdes_batch* b, const econpdes_batch_inputs* in, long long first, long long last,
+                               cudaStream_t s) {
+  const size_t n = static_cast<size_t>(last - first), o = static_cast<size_t>(first);
+  const size_t S = static_cast<size_t>(b->S), P = static_cast<size_t>(b->nparams);
+  if (P > 0)
+    EP_CUDA(cudaMemcpyAsync(b->params.p + o * P, in->params + o * P, n * P * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (b->explicit_grids) {
+    EP_CUDA(cudaMemcpyAsync(b->grids.p + o * S, in->grids + o * S, n * S * sizeof(double), cudaMemcpyHostToDevice, s));
+  } else {
+    const size_t np = S - static_cast<size_t>(b->n_range);
+    EP_CUDA(cudaMemcpyAsync(b->range_lo.p + o, in->range_lo + o, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    EP_CUDA(cudaMemcpyAsync(b->points.p + o * np, in->points + o * np, n * np * sizeof(double), cudaMemcpyHostToDevice, s));
+  }
+  if (b->explicit_guess)
+    EP_CUDA(cudaMemcpyAsync(b->guess.p + o * S, in->guess + o * S, n * S * sizeof(double), cudaMemcpyHostToDevice, s));
+}
+
+int econpdes_batch_upload_inputs(econpdes_batch* b, const econpdes_batch_inputs* in) {
+  return guarded([&] {
+    if (!b) throw std::invalid_argument("null batch");
+    batch_accept_inputs(b, in);
+    batch_upload_slice(b, in, 0, b->B, b->stream);
     EP_CUDA(cudaStreamSynchronize(b->stream));
     return ECONPDES_OK;
   });
@@ -478,8 +535,14 @@ static int batch_launch(econpdes_batch* b, const econpdes_options* options, int 
   a.S = b->S;
   a.nparams = b->nparams;
   a.params = b->params.p;
-  a.grids = b->grids.p;
-  a.guess = b->guess.p;
+  a.grids = b->explicit_grids ? b->grids.p : nullptr;
+  a.guess = b->explicit_guess ? b->guess.p : nullptr;
+  a.n_range = b->n_range;
+  a.range_lo = b->range_lo.p;
+  a.points = b->points.p;
+  a.guess_fill = b->guess_fill;
+  if ((b->explicit_grids && !a.grids) || (b->explicit_guess && !a.guess))
+    throw std::invalid_argument("the batch has no grids / guess yet: upload them first");
   a.solution = b->solution.p;
   a.residual_norm = b->residual_norm.p;
   a.exit_reason = b->exit_reason.p;
@@ -595,6 +658,21 @@ void econpdes_release_workspace(void) {
 int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, const double* params, const double* grids,
                            const double* guess, const econpdes_options* options, double* solution,
                            double* residual_norm, int32_t* exit_reason, int32_t* n_outer, int32_t* n_newton) {
+  if (!grids || !guess) {
+    set_error("null argument");
+    return ECONPDES_E_INVALID;
+  }
+  econpdes_batch_inputs in{};
+  in.params = params;
+  in.grids = grids;
+  in.guess = guess;
+  return econpdes_solve_batched_inputs(model_id, nproblems, npoints, &in, options, solution, residual_norm, exit_reason,
+                                       n_outer, n_newton);
+}
+
+int econpdes_solve_batched_inputs(int model_id, int64_t nproblems, int64_t npoints, const econpdes_batch_inputs* in,
+                                  const econpdes_options* options, double* solution, double* residual_norm,
+                                  int32_t* exit_reason, int32_t* n_outer, int32_t* n_newton) {
   int device = -1;
   cudaGetDevice(&device);
   econpdes_batch* b = t_workspace;
@@ -610,10 +688,10 @@ int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, con
   // copy of a third run at the same time (separate copy engines), and kernels of neighbouring slices fill each
   // other's tail waves.  Problems are independent, so the result does not depend on the slicing.
   return guarded([&] {
-    if (!grids || !guess || !options) throw std::invalid_argument("null argument");
-    if (b->nparams > 0 && !params) throw std::invalid_argument("null params");
+    if (!options) throw std::invalid_argument("null argument");
+    batch_accept_inputs(b, in);
     const long long B = b->B;
-    const size_t S = static_cast<size_t>(b->S), P = static_cast<size_t>(b->nparams);
+    const size_t S = static_cast<size_t>(b->S);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     // Slice sizes in whole waves (one block per SM): short slices at both ends so the pipeline fills and
@@ -665,10 +743,7 @@ int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, con
       const long long first = bounds[c], last = bounds[c + 1];
       const size_t n = static_cast<size_t>(last - first), o = static_cast<size_t>(first);
       cudaStream_t s = b->pipe[c % econpdes_batch::kPipe];
-      if (P > 0)
-        EP_CUDA(cudaMemcpyAsync(b->params.p + o * P, params + o * P, n * P * sizeof(double), cudaMemcpyHostToDevice, s));
-      EP_CUDA(cudaMemcpyAsync(b->grids.p + o * S, grids + o * S, n * S * sizeof(double), cudaMemcpyHostToDevice, s));
-      EP_CUDA(cudaMemcpyAsync(b->guess.p + o * S, guess + o * S, n * S * sizeof(double), cudaMemcpyHostToDevice, s));
+      batch_upload_slice(b, in, first, last, s);
       batch_launch(b, options, 0, first, last, s);
       EP_CUDA(cudaMemcpyAsync(err + o, b->error.p + o, n * sizeof(int), cudaMemcpyDeviceToHost, s));
       if (solution)

@@ -23,8 +23,12 @@ struct BatchArgs {
   int S;
   int nparams;
   const double* params;  // [B][nparams]
-  const double* grids;   // [B][S]
-  const double* guess;   // [B][S]
+  const double* grids;   // [B][S], or nullptr: range + explicit points (econpdes_batch_inputs)
+  const double* guess;   // [B][S], or nullptr: every unknown starts at guess_fill
+  int n_range = 0;                 // the first n_range points are range(range_lo[b], points[b][0], n_range + 1)[1:n_range]
+  const double* range_lo = nullptr;   // [B]
+  const double* points = nullptr;     // [B][S - n_range]
+  double guess_fill = 0.0;
   double* solution;      // [B][S]
   double* residual_norm; // [B]
   int* exit_reason;      // [B]
@@ -111,10 +115,16 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
   if (t == 0) { ysh[0] = 0.0; ysh[NP + 1] = 0.0; }
   // coalesced loads of the grid (staged in the PCR area, NP <= 8 T) and the guess
   double* xs = pcr;
-  for (int k = t; k < NP; k += T) {
-    xs[k] = k < S ? args.grids[b * S + k] : 0.0;
-    ysh[k + 1] = k < S ? args.guess[b * S + k] : 0.0;
+  if (args.grids != nullptr) {
+    for (int k = t; k < NP; k += T) xs[k] = k < S ? args.grids[b * S + k] : 0.0;
+  } else {   // grid built here: a Julia range up to the first explicit point, then the explicit points
+    const int nr = args.n_range, npts = S - nr;
+    const double lo = args.range_lo[b];
+    const double* pts = args.points + b * npts;
+    const double hi = pts[0];
+    for (int k = t; k < NP; k += T) xs[k] = k < nr ? range_point(lo, hi, nr + 1, k) : (k < S ? pts[k - nr] : 0.0);
   }
+  for (int k = t; k < NP; k += T) ysh[k + 1] = k < S ? (args.guess != nullptr ? args.guess[b * S + k] : args.guess_fill) : 0.0;
   __syncthreads();
   if (M::NDERIVED > 0) {   // parameter-only constants of the model, once per problem
     if (t == 0) M::derive(prm);

@@ -543,6 +543,9 @@ NewtonOutcome Solver::newton(const double* ypost, double delta, double ftol, int
     double rr = 0.0;
     const int fail = lin_->solve(planes_.p, R_.p, s_.p, opt, &li, &rr);
     out.lin_iters += li;
+    ++out.lin_solves;
+    if (rr > 1e-11) ++out.lin_loose;
+    if (rr > out.lin_max_relres) out.lin_max_relres = rr;
     if (fail) {  // SingularException -> (y0, Inf)
       out.singular = true;
       out.nl = INFINITY;
@@ -577,6 +580,14 @@ int Solver::solve(const econpdes_options& opt, econpdes_result* res) {
   res->n_outer = 0;
   res->n_newton = 0;
   res->n_linear_iters = 0;
+  res->n_linear_solves = 0;
+  res->n_linear_loose = 0;
+  res->lin_max_relres = 0.0;
+  auto count_linear = [&](const NewtonOutcome& o) {
+    res->n_linear_solves += o.lin_solves;
+    res->n_linear_loose += o.lin_loose;
+    if (o.lin_max_relres > res->lin_max_relres) res->lin_max_relres = o.lin_max_relres;
+  };
   res->exit_reason = ECONPDES_EXIT_CONVERGED;
 
   if (!c.has_delta_vec && (std::isnan(opt.delta) || opt.delta == 0.0))
@@ -607,6 +618,7 @@ int Solver::solve(const econpdes_options& opt, econpdes_result* res) {
     NewtonOutcome o = newton(ypost_.p, INFINITY, opt.abstol, opt.maxiters, opt, ytrial.p);
     res->n_newton = o.iters;
     res->n_linear_iters = o.lin_iters;
+    count_linear(o);
     EP_CUDA(cudaMemcpyAsync(ypost_.p, ytrial.p, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
     r = o.nl;
     res->exit_reason = r <= opt.abstol ? ECONPDES_EXIT_CONVERGED : ECONPDES_EXIT_INF_STEP_FAILED;
@@ -625,6 +637,7 @@ int Solver::solve(const econpdes_options& opt, econpdes_result* res) {
       NewtonOutcome o = newton(ypost_.p, ctl.delta * drel, opt.inner_abstol, opt.inner_maxiters, opt, ytrial.p);
       res->n_newton += o.iters;
       res->n_linear_iters += o.lin_iters;
+      count_linear(o);
       const double old_r = r;
       Norms ngn = eval_G(ytrial.p, G_.p);
       double rn = c.has_bounds ? masked_norm(G_.p, ytrial.p) : ngn.norm2_over_n(ng);

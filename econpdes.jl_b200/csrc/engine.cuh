@@ -175,6 +175,8 @@ struct NewtonOutcome {
   int iters;
   long long lin_iters;
   bool singular;
+  int lin_solves = 0, lin_loose = 0;   // linear solves, and those that ended with a relative residual above 1e-11
+  double lin_max_relres = 0.0;
 };
 
 class Solver {

@@ -123,14 +123,16 @@ __device__ __forceinline__ void stage_last_axis(const GridView<N>& gv, int j0, i
   __syncwarp();
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ROWKIND: 0 = R = G; 1 = G - (ypost - y)/delta with one finite scalar delta, no algebraic rows, no bounds;
 //          2 = general (RowSpec as in k_residual)
-// UNR: unroll factor of the marching loop
-// PFD: > 0 = L2 prefetch of the plane PFD steps beyond the window, and of the next tile's first planes
-// PF: 1 = the plane two steps ahead is requested at the top of a step (one more plane of registers)
-template <class M, int ROWKIND, int TAME, int PF, int UNR, int PFD, int BLOCK, int MINB>
+// UNR: unroll factor of the marching loop (3 lets the compiler rename the window instead of moving it; the
+//      27-value window of a 3-D box is better left rolled: register pressure)
+// Tried on B200 and dropped (2048^2 / 256^3 sweeps): an explicit register prefetch of the plane two steps
+// ahead and L2 prefetches further ahead (no gain: the loads of the next plane are already issued a step early);
+// two columns per thread, to share the plane-only arithmetic and interleave two evaluations (slower: 168
+// registers, three blocks per SM); 96- and 80-register builds for five / six blocks per SM (spills).
+template <class M, int ROWKIND, int TAME, int UNR, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_residual_march(GridView<M::N> gv, ParamPack prm, const double* __restrict__ y, const double* __restrict__ bc,
                  RowSpec rs, double* __restrict__ out, NormWork nw, int want_norm, MarchPlan mp) {
@@ -155,27 +157,10 @@ k_residual_march(GridView<M::N> gv, ParamPack prm, const double* __restrict__ y,
     const int j1 = j0 + mp.L < static_cast<int>(mp.SL) ? j0 + mp.L : static_cast<int>(mp.SL);
     stage_last_axis<N>(gv, j0, j1, s_tab, s_x);
     if (col >= ncol) continue;
-    if (PFD > 0) {   // request the first planes of this block's NEXT tile while this one is being worked on
-      const int nt = tile + gridDim.x;
-      if (nt < ntiles) {
-        const long long ncl = static_cast<long long>(nt % mp.ncolblocks) * BLOCK + threadIdx.x;
-        const int nj0 = (nt / mp.ncolblocks) * mp.L;
-        if (ncl < ncol) {
-#pragma unroll
-          for (int f = 0; f < F; ++f) {
-#pragma unroll
-            for (int q = -1; q <= PFD; ++q) {
-              const int jj = nj0 + q < jmin ? jmin : (nj0 + q > jmax ? jmax : nj0 + q);
-              prefetch_l2(y + f * l + ncl + static_cast<long long>(jj) * ncol);
-            }
-          }
-        }
-      }
-    }
     MarchCol<M> mc;
     mc.setup(gv, col);
     const double* __restrict__ yb = y + col;
-    double wa[F][KP], wb[F][KP], wc[F][KP], wd[F][KP];
+    double wa[F][KP], wb[F][KP], wc[F][KP];
     auto load_plane = [&](int j, double (*dst)[KP]) {
 #pragma unroll
       for (int f = 0; f < F; ++f) {
@@ -187,15 +172,8 @@ k_residual_march(GridView<M::N> gv, ParamPack prm, const double* __restrict__ y,
     load_plane(j0 - 1 > jmin ? j0 - 1 : jmin, wa);
     load_plane(j0, wb);
     load_plane(j0 + 1 < jmax ? j0 + 1 : jmax, wc);
-    // UNR = 3 (4 with PF) lets the compiler rename the window instead of moving it
 #pragma unroll UNR
     for (int j = j0; j < j1; ++j) {
-      if (PF) load_plane(j + 2 < jmax ? j + 2 : jmax, wd);
-      if (PFD > 0) {   // planes further ahead: into L2, so the window loads do not wait for DRAM
-        const int jp = j + 2 + PFD < jmax ? j + 2 + PFD : jmax;
-#pragma unroll
-        for (int f = 0; f < F; ++f) prefetch_l2(yb + f * l + static_cast<long long>(jp) * ncol);
-      }
       mc.step(gv, j + gv.off, s_tab + (j - j0) * kGeomRows, s_x[j - j0]);
       typename M::Pre pre;
       M::prepare(prm.v, mc.st, pre);
@@ -242,10 +220,9 @@ k_residual_march(GridView<M::N> gv, ParamPack prm, const double* __restrict__ y,
         for (int kp = 0; kp < KP; ++kp) {
           wa[f][kp] = wb[f][kp];
           wb[f][kp] = wc[f][kp];
-          if (PF) wc[f][kp] = wd[f][kp];
         }
       }
-      if (!PF) load_plane(j + 2 < jmax ? j + 2 : jmax, wc);
+      load_plane(j + 2 < jmax ? j + 2 : jmax, wc);
     }
   }
   if (want_norm) {

@@ -29,11 +29,54 @@ def splitmix64_uniforms(seeds: np.ndarray, count: int) -> np.ndarray:
     return out
 
 
-def campbell_cochrane_sweep(first: int, count: int, sn: int = 1000):
-    """Problems first..first+count-1 of the C4 calibration sweep: (params [B,6], grids [B,S],
-    guess [B,S]).  Parameters are i.i.d. uniform draws around the reference defaults
-    (examples/asset_pricing/campbell_cochrane.jl:28-35); each problem has its own state grid
-    (initialize_stategrid, :40-48) and the example's guess p = 1 (:50)."""
+def _two_prod(a, b):
+    """a * b = p + e exactly (Dekker / Veltkamp splitting; numpy has no fma)."""
+    p = a * b
+    c = 134217729.0   # 2^27 + 1
+    ta, tb = c * a, c * b
+    ah = ta - (ta - a)
+    bh = tb - (tb - b)
+    al, bl = a - ah, b - bh
+    e = ((ah * bh - p) + ah * bl + al * bh) + al * bl
+    return p, e
+
+
+def julia_range_rows(a, b, n: int) -> np.ndarray:
+    """Row r = Julia's range(a[r], b[r], length = n), i.e. the correctly rounded a + i (b - a)/(n - 1): the same
+    double-double evaluation as the device grid generator (range_point, csrc/stencil.cuh), vectorised, so a sweep
+    whose grids are built on the device solves bit-identical problems to one that ships explicit grids."""
+    a = np.asarray(a, dtype=np.float64)[:, None]
+    b = np.asarray(b, dtype=np.float64)[:, None]
+    i = np.arange(n, dtype=np.float64)[None, :]
+    m1, m2, d = (n - 1) - i, i, float(n - 1)
+    with np.errstate(invalid="ignore", over="ignore"):
+        p1, e1 = _two_prod(a, m1)
+        p2, e2 = _two_prod(b, m2)
+        sh = p1 + p2
+        bb = sh - p1
+        sl = ((p1 - (sh - bb)) + (p2 - bb)) + (e1 + e2)
+        h = sh + sl
+        lo = sl - (h - sh)
+        q1 = h / d
+        ph, pl = _two_prod(q1, np.full_like(q1, d))
+        r = ((h - ph) - pl) + lo
+        out = q1 + r / d
+    out[:, 0] = a[:, 0]
+    out[:, -1] = b[:, 0]
+    return out
+
+
+def campbell_cochrane_sweep_compact(first: int, count: int, sn: int = 1000):
+    """The same sweep as `campbell_cochrane_sweep` in the compact form of `econpdes_batch_inputs`:
+    (params [B,6], range_lo [B], points [B, sn//10 - 1], n_range, guess_fill).  The grid of a problem is
+    range(range_lo, points[0], length = n_range + 1)[1:n_range] followed by `points`
+    (initialize_stategrid, examples/asset_pricing/campbell_cochrane.jl:40-48)."""
+    params, shigh = _campbell_cochrane_sweep_head(first, count, sn)
+    nh = sn // 10
+    return (params, np.full(count, -300.0), np.ascontiguousarray(shigh[:, 1:]), sn - nh - 1, 1.0)
+
+
+def _campbell_cochrane_sweep_head(first: int, count: int, sn: int):
     u = splitmix64_uniforms(np.uint64(0xEC0DE5) + np.arange(first, first + count, dtype=np.uint64), 5)
     mu = 0.015 + (0.023 - 0.015) * u[:, 0]
     sigma = 0.012 + (0.018 - 0.012) * u[:, 1]
@@ -46,11 +89,19 @@ def campbell_cochrane_sweep(first: int, count: int, sn: int = 1000):
     sbar = np.log(Sbar)
     smax = sbar + 0.5 * (1 - Sbar * Sbar)
     nh = sn // 10
-    t = np.linspace(0.0, 1.0, nh)[None, :]
     with np.errstate(divide="ignore"):
-        shigh = np.log(t * np.exp(smax)[:, None])
-    tl = np.linspace(0.0, 1.0, sn - nh)[None, :]
-    slow = -300.0 + tl * (shigh[:, 1:2] + 300.0)
+        shigh = np.log(julia_range_rows(np.zeros(count), np.exp(smax), nh))
+    return params, shigh
+
+
+def campbell_cochrane_sweep(first: int, count: int, sn: int = 1000):
+    """Problems first..first+count-1 of the C4 calibration sweep: (params [B,6], grids [B,S],
+    guess [B,S]).  Parameters are i.i.d. uniform draws around the reference defaults
+    (examples/asset_pricing/campbell_cochrane.jl:28-35); each problem has its own state grid
+    (initialize_stategrid, :40-48) and the example's guess p = 1 (:50)."""
+    params, shigh = _campbell_cochrane_sweep_head(first, count, sn)
+    nh = sn // 10
+    slow = julia_range_rows(np.full(count, -300.0), shigh[:, 1], sn - nh)
     grids = np.ascontiguousarray(np.concatenate([slow[:, :-1], shigh[:, 1:]], axis=1))
     return params, grids, np.ones_like(grids)
 

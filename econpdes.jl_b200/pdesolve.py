@@ -61,6 +61,10 @@ class EconPDEResult:
     sign_flags: int = 0
     nonmonotone_entries: int = 0
     nonmonotone_max: float = 0.0
+    # quality of the Krylov solves that stand in for the reference's sparse LU (see econpdes_result)
+    n_linear_solves: int = 0
+    n_linear_loose: int = 0
+    lin_max_relres: float = 0.0
 
     @property
     def converged(self) -> bool:
@@ -399,7 +403,7 @@ def pdesolve(pde, grid, guess, taus=None, *, is_algebraic=None, bc=None, lower_b
                  for i in range(r.log_len))
     res = EconPDEResult(solution, r.residual_norm, sv, abstol, r.exit_reason, rows, r.n_outer, r.n_newton,
                         r.n_linear_iters, r.kernel_launches, r.device_ms, r.sign_flags, r.nonmonotone_entries,
-                        r.nonmonotone_max)
+                        r.nonmonotone_max, r.n_linear_solves, r.n_linear_loose, r.lin_max_relres)
     for txt in _diagnostic_warnings(res, ynames):   # src/monotonicity.jl (emitted regardless of `warn`, like @warn there)
         warnings.warn(txt)
     if verbose:
@@ -554,6 +558,45 @@ def solve_batched_one_call(model_cls, params, grids, guess, *, abstol=SQRT_EPS, 
                                        L.dptr(guess), C.byref(opts), L.dptr(sol), L.dptr(rn),
                                        er.ctypes.data_as(L.c_int32_p), no.ctypes.data_as(L.c_int32_p),
                                        nn.ctypes.data_as(L.c_int32_p)))
+    return sol, rn, er, no, nn
+
+
+def solve_batched_compact(model_cls, params, range_lo, points, n_range: int, guess_fill: float = 1.0, *,
+                          abstol=SQRT_EPS, maxiters=100, out=None, **kwargs):
+    """`econpdes_solve_batched_inputs` with compact inputs (`econpdes_batch_inputs`): the first `n_range` points of
+    problem b are Julia's range(range_lo[b], points[b, 0], length = n_range + 1)[1:n_range], built on the device,
+    followed by the explicit `points[b]`; every unknown starts at `guess_fill`.  Same pipelined one-call path as
+    `solve_batched_one_call`, without shipping B x S grids and guesses.  `out` = optional preallocated
+    (solution, residual_norm, exit_reason, n_outer, n_newton) arrays (page-locked ones overlap the copies)."""
+    lib = L.load()
+    delta = kwargs.pop("Δ", kwargs.pop("delta", 1.0))
+    opts = _options(abstol, maxiters, kwargs)
+    opts.delta = float(delta)
+    if kwargs:
+        raise TypeError(f"unknown keyword arguments {sorted(kwargs)}")
+    params = np.ascontiguousarray(params, dtype=np.float64)
+    range_lo = np.ascontiguousarray(range_lo, dtype=np.float64)
+    points = np.ascontiguousarray(points, dtype=np.float64)
+    B, npts = points.shape
+    S = int(n_range) + npts
+    if range_lo.shape != (B,):
+        raise ValueError(f"range_lo has shape {range_lo.shape}, expected {(B,)}")
+    mid = L.check(lib.econpdes_model_id(model_cls.name.encode()))
+    if out is None:
+        out = (np.empty((B, S)), np.empty(B), np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32),
+               np.empty(B, dtype=np.int32))
+    sol, rn, er, no, nn = out
+    inp = L.BatchInputs()
+    inp.params = L.dptr(params) if params.size else None
+    inp.grids = None
+    inp.n_range = int(n_range)
+    inp.range_lo = L.dptr(range_lo)
+    inp.points = L.dptr(points)
+    inp.guess = None
+    inp.guess_fill = float(guess_fill)
+    L.check(lib.econpdes_solve_batched_inputs(mid, B, S, C.byref(inp), C.byref(opts), L.dptr(sol), L.dptr(rn),
+                                              er.ctypes.data_as(L.c_int32_p), no.ctypes.data_as(L.c_int32_p),
+                                              nn.ctypes.data_as(L.c_int32_p)))
     return sol, rn, er, no, nn
 
 

@@ -139,6 +139,7 @@ def pdesolve_slab(pde, grid, guess, group: SlabGroup, *, abstol=SQRT_EPS, maxite
                       linear_iters=log[i].linear_iters, delta=log[i].delta, residual=log[i].residual)
                  for i in range(r.log_len))
     res = EconPDEResult(solution, r.residual_norm, OrderedDict(), abstol, r.exit_reason, rows, r.n_outer, r.n_newton,
-                        r.n_linear_iters, r.kernel_launches, r.device_ms)
+                        r.n_linear_iters, r.kernel_launches, r.device_ms, 0, 0, 0.0, r.n_linear_solves,
+                        r.n_linear_loose, r.lin_max_relres)
     res.slab = (first, count)
     return res

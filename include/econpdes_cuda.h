@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define ECONPDES_ABI_VERSION 2
+#define ECONPDES_ABI_VERSION 3
 #define ECONPDES_MAX_DIMS 3
 #define ECONPDES_MAX_FUNCS 4
 #define ECONPDES_MAX_PARAMS 16
@@ -138,6 +138,13 @@ typedef struct econpdes_result {
   int32_t sign_flags;
   int32_t nonmonotone_entries;
   double nonmonotone_max;
+  /* Quality of the linear solves behind the Newton iterations (the reference's `J \ R` is a sparse LU, exact to
+   * round-off; the 2-D / 3-D path is a Krylov solve driven to options.lin_rtol, which accepts a stagnated solve
+   * at relative residual <= 1e-8): number of linear solves, how many of them ended above 1e-11, and the
+   * largest final relative residual.  1-D (block-)tridiagonal solves report 0 / 0. */
+  int32_t n_linear_solves;
+  int32_t n_linear_loose;
+  double lin_max_relres;
 } econpdes_result;
 #define ECONPDES_SIGN_WHOLE_SYSTEM (1 << 30)
 
@@ -240,6 +247,31 @@ int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, con
                            const double* grids, const double* guess, const econpdes_options* options,
                            double* solution, double* residual_norm, int32_t* exit_reason, int32_t* n_outer,
                            int32_t* n_newton);
+
+/* Compact inputs of a sweep.  A calibration loop builds every grid from a few numbers
+ * (initialize_stategrid, examples/asset_pricing/campbell_cochrane.jl:40-48:
+ * vcat(range(-300, shigh[2], length = sn - div(sn, 10))[1:end-1], shigh[2:end]) and starts every unknown
+ * at one value (guess = ones): shipping B x S grids and guesses over PCIe costs more than solving them.
+ *   grids != NULL:  explicit grids[B][S] (n_range, range_lo, points ignored)
+ *   grids == NULL:  the first n_range points of problem b are
+ *                       range(range_lo[b], points[b][0], length = n_range + 1)[1:n_range]
+ *                   evaluated like Julia's `range` (correctly rounded a + i (b - a)/(n - 1)), built on the device,
+ *                   followed by the explicit points[b][0 .. S - n_range); 1 <= n_range < S
+ *   guess != NULL:  explicit guess[B][S];  guess == NULL: every unknown starts at guess_fill */
+typedef struct econpdes_batch_inputs {
+  const double* params;    /* [B][nparams] */
+  const double* grids;     /* [B][S] or NULL */
+  int32_t n_range;
+  const double* range_lo;  /* [B] */
+  const double* points;    /* [B][S - n_range] */
+  const double* guess;     /* [B][S] or NULL */
+  double guess_fill;
+} econpdes_batch_inputs;
+/* econpdes_batch_upload / econpdes_solve_batched with compact inputs */
+int econpdes_batch_upload_inputs(econpdes_batch* b, const econpdes_batch_inputs* inputs);
+int econpdes_solve_batched_inputs(int model_id, int64_t nproblems, int64_t npoints, const econpdes_batch_inputs* inputs,
+                                  const econpdes_options* options, double* solution, double* residual_norm,
+                                  int32_t* exit_reason, int32_t* n_outer, int32_t* n_newton);
 
 /* econpdes_solve_batched keeps its device workspace (per host thread) between calls of the same
  * shape; this frees it. */

@@ -39,6 +39,7 @@ mutable struct CResult
     converged::Int32; exit_reason::Int32; n_outer::Int32; n_newton::Int32
     n_linear_iters::Int64; kernel_launches::Int64; device_ms::Float64
     sign_flags::Int32; nonmonotone_entries::Int32; nonmonotone_max::Float64   # src/monotonicity.jl diagnostics
+    n_linear_solves::Int32; n_linear_loose::Int32; lin_max_relres::Float64    # quality of the Krylov solves (ABI 3)
     CResult() = new()
 end
 
@@ -88,7 +89,10 @@ function EconPDEs.pdesolve(m::CUDAModel, grid, guess; is_algebraic = nothing, bc
     opts.abstol = abstol; opts.maxiters = maxiters
     Δvec === nothing && (opts.delta = Δ)
     for (k, v) in kwargs   # scale, minΔ, maxΔ, max_residual_growth, inner_maxiters, inner_abstol
-        k === :minΔ ? (opts.min_delta = v) : k === :maxΔ ? (opts.max_delta = v) : setfield!(opts, k, convert(fieldtype(COptions, k), v))
+        k === :minΔ && (opts.min_delta = v; continue)
+        k === :maxΔ && (opts.max_delta = v; continue)
+        hasfield(COptions, k) || throw(ArgumentError("unsupported keyword `$k` for the CUDA path"))
+        setfield!(opts, k, convert(fieldtype(COptions, k), v))
     end
     mid = ccall((:econpdes_model_id, lib), Cint, (Cstring,), m.name)
     mid < 0 && throw(ArgumentError(last_error()))
@@ -123,9 +127,12 @@ end
 
 # Time-dependent problems: pdesolve(m, grid, guess, τs) -> _solve_backward (src/pdesolve.jl:158-224).
 # The guess is the terminal value; every unknown gains a trailing time dimension.
-function EconPDEs.pdesolve(m::CUDAModel, grid, guess, τs::AbstractVector; bc = nothing, abstol = sqrt(eps()),
+function EconPDEs.pdesolve(m::CUDAModel, grid, guess, τs::AbstractVector; bc = nothing, is_algebraic = nothing,
+                           lower_bound = nothing, upper_bound = nothing, abstol = sqrt(eps()),
                            maxiters = 100, inner_maxiters = maxiters, inner_abstol = abstol, kwargs...)
     EconPDEs._reject_time_dependent_stationary_keywords(kwargs); EconPDEs._check_time_grid(τs)
+    # every keyword the device path does not implement is an error, not a silently different solve
+    isempty(kwargs) || throw(ArgumentError("unsupported keyword(s) for the CUDA time-dependent path: $(collect(keys(kwargs)))"))
     grid = _asnamedtuple(grid); guess = _asnamedtuple(guess)
     stategrid = StateGrid(grid); S = size(stategrid); F = length(guess); nt = length(τs)
     guess_array = cat(values(guess)...; dims = length(S) + 1)
@@ -135,10 +142,14 @@ function EconPDEs.pdesolve(m::CUDAModel, grid, guess, τs::AbstractVector; bc = 
     mid = ccall((:econpdes_model_id, lib), Cint, (Cstring,), m.name)
     sol = Array{Float64}(undef, S..., F, nt); saved = Array{Float64}(undef, S..., length(m.saved), nt)
     rn = zeros(nt); nit = zeros(Int32, nt); ms = Ref(0.0); nl = Ref(Int64(0))
-    GC.@preserve grids guess_array bcs sol saved rn nit ts m begin
+    # is_algebraic / bounds normalised like the stationary method (src/pdesolve.jl:112-115): _solve_backward honours them
+    alg = UInt8.(cat(values(_fill_is_algebraic(is_algebraic, guess, S))...; dims = length(S) + 1))
+    lb = _bound_array(lower_bound, guess, -Inf, :lower_bound)
+    ub = _bound_array(upper_bound, guess, Inf, :upper_bound)
+    GC.@preserve grids guess_array bcs alg lb ub sol saved rn nit ts m begin
         gp = ntuple(d -> d <= length(S) ? pointer(grids[d]) : Ptr{Float64}(C_NULL), 3)
         prob = CProblem(mid, length(S), F, length(m.params), ntuple(d -> d <= length(S) ? S[d] : 1, 3), gp,
-                        pointer(m.params), pointer(guess_array), pointer(bcs), C_NULL, C_NULL, C_NULL, C_NULL)
+                        pointer(m.params), pointer(guess_array), pointer(bcs), pointer(alg), pointer(lb), pointer(ub), C_NULL)
         rc = ccall((:econpdes_solve_backward, lib), Cint,
                    (Ref{CProblem}, Ref{COptions}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
                     Ptr{Int32}, Ref{Float64}, Ref{Int64}),
@@ -168,6 +179,33 @@ function pdesolve_batched(name::String, params::Matrix{Float64}, grids::Matrix{F
                (Cint, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{COptions}, Ptr{Float64}, Ptr{Float64},
                 Ptr{Int32}, Ptr{Int32}, Ptr{Int32}),
                mid, B, S, params, grids, guess, opts, sol, rn, er, no, nn)
+    rc < 0 && throw(ArgumentError(last_error()))
+    return sol, rn, er, no, nn
+end
+
+# The same sweep with COMPACT inputs (econpdes_batch_inputs): the first `n_range` points of problem b are
+# range(range_lo[b], points[1, b], length = n_range + 1)[1:n_range], built on the device exactly as `range` would,
+# followed by points[:, b]; every unknown starts at `guess_fill`.  For the Campbell-Cochrane sweep
+# (initialize_stategrid, examples/asset_pricing/campbell_cochrane.jl:40-48): range_lo = -300, points = shigh[2:end],
+# n_range = sn - div(sn, 10) - 1, guess_fill = 1.
+struct CBatchInputs
+    params::Ptr{Float64}; grids::Ptr{Float64}; n_range::Int32; range_lo::Ptr{Float64}; points::Ptr{Float64}
+    guess::Ptr{Float64}; guess_fill::Float64
+end
+function pdesolve_batched(name::String, params::Matrix{Float64}, range_lo::Vector{Float64}, points::Matrix{Float64},
+                          n_range::Integer, guess_fill::Float64; abstol = sqrt(eps()), maxiters = 100, Δ = 1.0)
+    np, B = size(points); S = n_range + np
+    opts = COptions(); ccall((:econpdes_default_options, lib), Cvoid, (Ref{COptions},), opts)
+    opts.abstol = abstol; opts.maxiters = maxiters; opts.delta = Δ
+    mid = ccall((:econpdes_model_id, lib), Cint, (Cstring,), name)
+    sol = Matrix{Float64}(undef, S, B); rn = Vector{Float64}(undef, B)
+    er = Vector{Int32}(undef, B); no = Vector{Int32}(undef, B); nn = Vector{Int32}(undef, B)
+    GC.@preserve params range_lo points begin
+        inp = CBatchInputs(pointer(params), C_NULL, n_range, pointer(range_lo), pointer(points), C_NULL, guess_fill)
+        rc = ccall((:econpdes_solve_batched_inputs, lib), Cint,
+                   (Cint, Int64, Int64, Ref{CBatchInputs}, Ref{COptions}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32},
+                    Ptr{Int32}, Ptr{Int32}), mid, B, S, inp, opts, sol, rn, er, no, nn)
+    end
     rc < 0 && throw(ArgumentError(last_error()))
     return sol, rn, er, no, nn
 end

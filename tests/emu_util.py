@@ -104,3 +104,13 @@ def planes_to_csc(planes, S, F, box, colptr, rowval):
         k = np.where((off[:, d] != 0) & (nzo == 1), 1 + 2 * d + (off[:, d] > 0), k)
     vals = planes[k, fin, fout, rpt]
     return np.where(nzo <= 1, vals, 0.0)
+
+
+def range_rows(a, b, n):
+    """Rows of Julia ranges by the device grid generator (range_point, csrc/stencil.cuh) on the host."""
+    L = lib()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    out = np.empty((a.shape[0], n))
+    L.emu_range_rows(_p(a), _p(b), ctypes.c_int(a.shape[0]), ctypes.c_int(n), _p(out))
+    return out

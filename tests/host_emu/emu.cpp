@@ -101,6 +101,12 @@ extern "C" {
 
 void emu_set_recip(int mode) { g_recip = mode; }
 
+// the device grid generator (range_point, stencil.cuh): out[r * n + i] = range(a[r], b[r], length = n)[i]
+void emu_range_rows(const double* a, const double* b, int rows, int n, double* out) {
+  for (int r = 0; r < rows; ++r)
+    for (int i = 0; i < n; ++i) out[static_cast<long long>(r) * n + i] = range_point(a[r], b[r], n, i);
+}
+
 // FastDiv (division by a grid size in unravel) against `/` for n = 0..count-1 and near 2^31 / 2^32
 long long emu_fastdiv_mismatches(unsigned d, unsigned count) {
   FastDiv f;

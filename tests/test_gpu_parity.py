@@ -472,6 +472,38 @@ def test_one_call_pipelined_path_matches_handle_path():
         E.solve_batched_one_call(PM.CampbellCochraneModel, Pm, G, U)
 
 
+def test_compact_batch_inputs_build_the_same_grids_on_the_device():
+    """econpdes_solve_batched_inputs with compact inputs (grid = a Julia range built on the device + explicit
+    points, broadcast guess): the device's range_point must reproduce the oracle's julia_range bit for bit, so the
+    solutions equal those of the explicit-grid path exactly -- and the oracle's own solve of the same problems."""
+    from econpdes_b200 import examples as EX
+    B = 2 * 148 + 5
+    params, grids, guess = EX.campbell_cochrane_sweep(100, B)
+    p2, lo, pts, n_range, fill = EX.campbell_cochrane_sweep_compact(100, B)
+    np.testing.assert_array_equal(params, p2)
+    ref = E.solve_batched_one_call(PM.CampbellCochraneModel, params, grids, guess)
+    got = E.solve_batched_compact(PM.CampbellCochraneModel, p2, lo, pts, n_range, fill)
+    for a, b in zip(got, ref):
+        np.testing.assert_array_equal(a, b)
+    for i in (0, B - 1):
+        prm = OM.campbell_cochrane_sweep_params(100 + i)
+        g = OM.campbell_cochrane_grid(sn=1000, **prm)
+        np.testing.assert_array_equal(g, grids[i])
+        ora = eo.pdesolve(OM.campbell_cochrane(**prm), {"s": g}, {"p": np.ones(g.shape[0])})
+        np.testing.assert_allclose(got[0][i], ora.solution["p"], rtol=1e-8)
+        assert abs(got[1][i] - ora.residual_norm) <= 1e-10 and got[3][i] == ora.log.n_outer
+    # other shapes: a 2-point range, a range that is almost the whole grid
+    x = OM.julia_range(0.0, 1.0, 50)
+    for n_range in (1, 2, 48):
+        sol, rn, er, no, nn = E.solve_batched_compact(PM.ReadmeLinear, np.array([[0.05, 0.2]] * 3), np.zeros(3),
+                                                      np.tile(x[n_range:], (3, 1)), n_range, 0.0)
+        xs = np.concatenate([OM.julia_range(0.0, x[n_range], n_range + 1)[:n_range], x[n_range:]])
+        one = E.pdesolve_batched(PM.ReadmeLinear, np.array([[0.05, 0.2]]), xs[None, :], np.zeros((1, 50)))
+        np.testing.assert_array_equal(sol[1], one.solution[0])
+    with pytest.raises(E.EconPDEsCudaError, match="n_range"):
+        E.solve_batched_compact(PM.ReadmeLinear, np.array([[0.05, 0.2]]), np.zeros(1), x[None, :], 0, 0.0)
+
+
 def test_batched_inf_delta_and_already_zero():
     x = OM.julia_range(0.0, 1.0, 40)
     out = E.pdesolve_batched(PM.LinearSum1D, np.zeros((1, 0)), x[None, :], np.zeros((1, 40)), Δ=INF)

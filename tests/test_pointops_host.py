@@ -446,3 +446,36 @@ def test_wild_fields_saved_outputs(case):
                 np.testing.assert_allclose(a[fin], b[fin], rtol=1e-9, atol=1e-9 * scale, err_msg=key)
             else:
                 np.testing.assert_array_equal(a[fin], b[fin], err_msg=key)
+
+
+@pytest.mark.parametrize("n", [2, 3, 7, 100, 900, 901])
+def test_device_grid_generator_matches_julia_range(n):
+    """range_point (csrc/stencil.cuh), the grid generator of the compact batched inputs, against the oracle's
+    exact-rational restatement of Julia's `range` (oracle/models.py:julia_range): same bits, including ranges
+    that cross zero, tiny / huge endpoints and the Campbell-Cochrane endpoints (campbell_cochrane.jl:44-46);
+    the vectorised numpy form the synthetic sweeps are built with (examples.julia_range_rows) agrees too."""
+    from econpdes_b200 import examples as EX
+    rng = np.random.default_rng(n)
+    a = np.concatenate([rng.uniform(-400, 10, 60), rng.uniform(-1, 0, 20), [-300.0, 0.0, -1e-300, 1e200, -3.0]])
+    b = np.concatenate([a[:60] + rng.uniform(0.1, 500, 60), rng.uniform(0, 1, 20),
+                        [-2.6347180103190485, 0.08, 1e-300, 3e200, 7.0]])
+    got = EU.range_rows(a, b, n)
+    want = np.stack([OM.julia_range(x, y, n) for x, y in zip(a, b)])
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(EX.julia_range_rows(a, b, n), want)
+
+
+def test_sweep_grids_equal_the_oracle_grids():
+    """The synthetic C4 sweep (examples.campbell_cochrane_sweep, explicit or compact form) describes the grids the
+    oracle builds for the same parameter draws (oracle/models.py:campbell_cochrane_grid), bit for bit."""
+    from econpdes_b200 import examples as EX
+    for i in (0, 3, 16383):
+        prm = OM.campbell_cochrane_sweep_params(i)
+        want = OM.campbell_cochrane_grid(sn=1000, **prm)
+        params, grids, guess = EX.campbell_cochrane_sweep(i, 1)
+        np.testing.assert_array_equal(grids[0], want)
+        np.testing.assert_array_equal(params[0], [prm[k] for k in ("mu", "sigma", "gamma", "rho", "kappa_s", "b")])
+        p2, lo, pts, n_range, fill = EX.campbell_cochrane_sweep_compact(i, 1)
+        assert n_range == 899 and fill == 1.0 and pts.shape == (1, 99)
+        rebuilt = np.concatenate([EU.range_rows(lo, pts[:, 0], n_range + 1)[0, :n_range], pts[0]])
+        np.testing.assert_array_equal(rebuilt, want)

@@ -1,7 +1,6 @@
 #!/usr/bin/env bash
-# A/B of the marching sweeps (sweep.cuh) against the one-thread-per-point kernels on the C3 / C5 shapes:
+# A/B of kernel variants on the C3 / C5 shapes (one line per configuration):
 #   gpurun --timeout 900 -- 'bash tools/sweep_march.sh gpurun_out/march'
-# One line per configuration: residual / implicit residual + norms / Jacobian ms at 2048^2 and 256^3.
 set -uo pipefail
 out=${1:-gpurun_out/march}
 mkdir -p "$out"
@@ -22,15 +21,11 @@ except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
 }
-run old ECONPDES_MARCH=0
 for v in 0 1 2 3; do
-  run "v${v}" ECONPDES_MARCH=1 ECONPDES_MARCH_VARIANT=$v
+  run "v${v}" ECONPDES_MARCH_VARIANT=$v
 done
-run "v1_L16" ECONPDES_MARCH=1 ECONPDES_MARCH_VARIANT=1 ECONPDES_MARCH_L=16
-run "v1_L32" ECONPDES_MARCH=1 ECONPDES_MARCH_VARIANT=1 ECONPDES_MARCH_L=32
-run "v3_L16" ECONPDES_MARCH=1 ECONPDES_MARCH_VARIANT=3 ECONPDES_MARCH_L=16
-run "v3_L32" ECONPDES_MARCH=1 ECONPDES_MARCH_VARIANT=3 ECONPDES_MARCH_L=32
-run "v3_occ3" ECONPDES_MARCH=1 ECONPDES_MARCH_VARIANT=3 ECONPDES_MARCH_OCC=3
-run "jocc" ECONPDES_MARCH=1 ECONPDES_MARCH_VARIANT=3 ECONPDES_MARCH_JOCC=1
-run "jocc_L16" ECONPDES_MARCH=1 ECONPDES_MARCH_VARIANT=3 ECONPDES_MARCH_JOCC=1 ECONPDES_MARCH_LJ=16
+run "v1_L16" ECONPDES_MARCH_VARIANT=1 ECONPDES_MARCH_L=16
+run "v1_L32" ECONPDES_MARCH_VARIANT=1 ECONPDES_MARCH_L=32
+run "warp256" ECONPDES_WARP_LINES_MAX=256 ECONPDES_CHUNK_LINES_3D=0
+run "nochunk3d" ECONPDES_CHUNK_LINES_3D=0
 cat "$out/summary.txt"
