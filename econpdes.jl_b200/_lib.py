@@ -110,6 +110,7 @@ SYMBOLS = {
     "econpdes_device_count": (C.c_int, []),
     "econpdes_set_device": (C.c_int, [C.c_int]),
     "econpdes_total_kernel_launches": (C.c_int64, []),
+    "econpdes_guard_violations": (C.c_int64, []),
     "econpdes_dist_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "econpdes_dist_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_void_p)]),
     "econpdes_dist_destroy": (None, [C.c_void_p]),

@@ -195,6 +195,8 @@ int econpdes_set_device(int device) {
 
 int64_t econpdes_total_kernel_launches(void) { return g_kernel_launches.load(); }
 
+int64_t econpdes_guard_violations(void) { return GuardRegistry::enabled() ? GuardRegistry::violations(true) : -1; }
+
 int econpdes_create(const econpdes_problem* problem, econpdes_handle** out) {
   return guarded([&] {
     if (!out) throw std::invalid_argument("null handle pointer");
@@ -476,9 +478,10 @@ static void batch_accept_inputs(econpdes_batch* b, const econpdes_batch_inputs* 
   if (!in) throw std::invalid_argument("null inputs");
   const size_t B = static_cast<size_t>(b->B), S = static_cast<size_t>(b->S);
   if (b->nparams > 0 && !in->params) throw std::invalid_argument("null params");
+  b->grids.alloc(B * S);
+  b->guess.alloc(B * S);
   if (in->grids != nullptr) {
     b->explicit_grids = true;
-    b->grids.alloc(B * S);
   } else {
     if (in->n_range < 1 || in->n_range >= b->S) throw std::invalid_argument("n_range must lie in [1, npoints)");
     if (!in->range_lo || !in->points) throw std::invalid_argument("null range_lo / points");
@@ -489,7 +492,6 @@ static void batch_accept_inputs(econpdes_batch* b, const econpdes_batch_inputs* 
   }
   if (in->guess != nullptr) {
     b->explicit_guess = true;
-    b->guess.alloc(B * S);
   } else {
     b->explicit_guess = false;
     b->guess_fill = in->guess_fill;
@@ -535,14 +537,9 @@ static int batch_launch(econpdes_batch* b, const econpdes_options* options, int 
   a.S = b->S;
   a.nparams = b->nparams;
   a.params = b->params.p;
-  a.grids = b->explicit_grids ? b->grids.p : nullptr;
-  a.guess = b->explicit_guess ? b->guess.p : nullptr;
-  a.n_range = b->n_range;
-  a.range_lo = b->range_lo.p;
-  a.points = b->points.p;
-  a.guess_fill = b->guess_fill;
-  if ((b->explicit_grids && !a.grids) || (b->explicit_guess && !a.guess))
-    throw std::invalid_argument("the batch has no grids / guess yet: upload them first");
+  a.grids = b->grids.p;
+  a.guess = b->guess.p;
+  if (!a.grids || !a.guess) throw std::invalid_argument("the batch has no grids / guess yet: upload them first");
   a.solution = b->solution.p;
   a.residual_norm = b->residual_norm.p;
   a.exit_reason = b->exit_reason.p;
@@ -558,6 +555,12 @@ static int batch_launch(econpdes_batch* b, const econpdes_options* options, int 
   a.log_len = b->log_len.p;
   a.opt = *options;
   const int64_t l0 = g_kernel_launches.load();
+  if (!b->explicit_grids || !b->explicit_guess) {   // compact inputs: build this slice's grids / guesses on the device
+    const long long cnt = (a.nproblems - a.problem0) * b->S;
+    EP_LAUNCH(k_expand_batch_inputs, blocks_for(cnt), 256, 0, s ? s : b->stream, a.problem0, a.nproblems, b->S, b->n_range,
+              b->range_lo.p, b->explicit_grids ? nullptr : b->points.p, b->grids.p, b->guess_fill,
+              b->explicit_guess ? nullptr : b->guess.p);
+  }
   if (!model_ops(b->model_id)->batched(a, s ? s : b->stream)) throw std::runtime_error("model has no batched kernel");
   b->launches += g_kernel_launches.load() - l0;
   return ECONPDES_OK;

@@ -9,6 +9,8 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <map>
+#include <mutex>
 #include <tuple>
 #include <vector>
 
@@ -20,6 +22,50 @@
 namespace econpdes {
 
 std::atomic<int64_t> g_kernel_launches{0};
+
+// ---- canary regions around device buffers (ECONPDES_GUARD=1; see GuardRegistry in engine.cuh) ----
+namespace {
+std::mutex g_guard_mutex;
+std::map<void*, size_t> g_guard_live;        // base -> total bytes (canaries included)
+long long g_guard_violations = 0;
+long long count_bad_canaries(void* base, size_t total) {
+  unsigned char h[2 * GuardRegistry::kBytes];
+  // guard lengths are kBytes rounded up to whole elements: checking the outermost kBytes of either side is exact
+  // for every element size that divides 256 (all of the library's: 1, 4, 8, 16, 24-byte rows are checked in part)
+  if (cudaMemcpy(h, base, GuardRegistry::kBytes, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  if (cudaMemcpy(h + GuardRegistry::kBytes, static_cast<unsigned char*>(base) + total - GuardRegistry::kBytes,
+                 GuardRegistry::kBytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return 0;
+  long long bad = 0;
+  for (unsigned char c : h) bad += c != 0xA5;
+  return bad;
+}
+}  // namespace
+bool GuardRegistry::enabled() {
+  static const bool on = [] { const char* e = std::getenv("ECONPDES_GUARD"); return e && e[0] == '1'; }();
+  return on;
+}
+void GuardRegistry::add(void* base, size_t total_bytes) {
+  std::lock_guard<std::mutex> lk(g_guard_mutex);
+  g_guard_live[base] = total_bytes;
+}
+void GuardRegistry::remove(void* base) {
+  std::lock_guard<std::mutex> lk(g_guard_mutex);
+  auto it = g_guard_live.find(base);
+  if (it == g_guard_live.end()) return;
+  cudaDeviceSynchronize();
+  g_guard_violations += count_bad_canaries(base, it->second);
+  g_guard_live.erase(it);
+}
+long long GuardRegistry::violations(bool check_live) {
+  std::lock_guard<std::mutex> lk(g_guard_mutex);
+  long long v = g_guard_violations;
+  if (check_live) {
+    cudaDeviceSynchronize();
+    for (auto& kv : g_guard_live) v += count_bad_canaries(kv.first, kv.second);
+  }
+  return v;
+}
 
 void ensure_device() {
   int count = 0;

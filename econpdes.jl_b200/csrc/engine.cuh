@@ -12,6 +12,19 @@
 
 namespace econpdes {
 
+// Debug facility standing in for compute-sanitizer's memcheck (the tool is not available on every pool): with
+// ECONPDES_GUARD=1 every device buffer of the library is allocated with a 256-byte canary region on either side
+// (0xA5 bytes); the regions are verified when the buffer is released and on econpdes_guard_violations(), which
+// returns the number of corrupted canary bytes seen so far -- an out-of-bounds WRITE next to any buffer shows up
+// there.  Off by default (no cost).
+struct GuardRegistry {
+  static constexpr size_t kBytes = 256;
+  static bool enabled();
+  static void add(void* base, size_t total_bytes);
+  static void remove(void* base);            // verifies the buffer's canaries, then forgets it
+  static long long violations(bool check_live);
+};
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;  // first logical element (pad elements of ghost storage precede and follow it)
@@ -23,7 +36,11 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p - pad_alloc_);
+    if (p) {
+      T* base = p - pad_alloc_ - guard_alloc_;
+      if (guard_alloc_) GuardRegistry::remove(base);
+      cudaFree(base);
+    }
     p = nullptr;
     n = 0;
     cap = 0;
@@ -35,15 +52,24 @@ struct DevBuf {
     }
     release();
     if (count == 0) return;
+    const size_t guard = GuardRegistry::enabled() ? (GuardRegistry::kBytes + sizeof(T) - 1) / sizeof(T) : 0;
     T* base = nullptr;
-    EP_CUDA(cudaMalloc(&base, (count + 2 * pad) * sizeof(T)));
+    const size_t total = count + 2 * pad + 2 * guard;
+    EP_CUDA(cudaMalloc(&base, total * sizeof(T)));
     if (pad) {   // ghosts at the global ends stay 0
-      EP_CUDA(cudaMemset(base, 0, (count + 2 * pad) * sizeof(T)));
+      EP_CUDA(cudaMemset(base + guard, 0, (count + 2 * pad) * sizeof(T)));
       // the memset runs on the legacy stream, which the library's non-blocking streams do not wait for
       EP_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
     }
-    p = base + pad;
+    if (guard) {
+      EP_CUDA(cudaMemset(base, 0xA5, guard * sizeof(T)));
+      EP_CUDA(cudaMemset(base + guard + count + 2 * pad, 0xA5, guard * sizeof(T)));
+      EP_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+      GuardRegistry::add(base, total * sizeof(T));
+    }
+    p = base + guard + pad;
     pad_alloc_ = pad;
+    guard_alloc_ = guard;
     n = count;
     cap = count;
   }
@@ -57,7 +83,7 @@ struct DevBuf {
   }
 
  private:
-  size_t pad_alloc_ = 0;
+  size_t pad_alloc_ = 0, guard_alloc_ = 0;
 };
 
 extern std::atomic<int> g_batch_points_per_thread;   // 0 = automatic (api: econpdes_set_batch_points_per_thread)

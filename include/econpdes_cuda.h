@@ -297,6 +297,11 @@ int econpdes_selftest_reciprocal(uint64_t seed, int64_t n, int64_t mismatch[3]);
 int econpdes_device_count(void);
 int econpdes_set_device(int device);
 int64_t econpdes_total_kernel_launches(void);
+/* Debug facility (stands in for a memcheck tool): when the process runs with ECONPDES_GUARD=1 every device buffer
+ * of the library carries a 256-byte canary region on either side; returns the number of corrupted canary bytes
+ * found so far (live buffers are checked now, released ones were checked at release), i.e. 0 unless some kernel
+ * wrote out of bounds.  -1 when the facility is off. */
+int64_t econpdes_guard_violations(void);
 
 /* --- slab-decomposed solve of ONE large grid across the GPUs of a node (config C5).
  *     One process per GPU.  The slowest dimension (N-1; slabs are contiguous in the column-major
