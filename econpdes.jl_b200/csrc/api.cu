@@ -353,10 +353,144 @@ int econpdes_solve(econpdes_handle* h, const econpdes_options* options, econpdes
   });
 }
 
+// A single 1-D single-unknown problem with the default boundary rows and no algebraic rows, bounds or per-row
+// steps is what the fused batched kernel solves (batched1d.cuh) -- one thread block, the whole pseudo-transient
+// loop on chip, ONE launch instead of the ~75 of the generic engine (which is launch-latency bound at this size:
+// the README quickstart took 4.5 ms for a few microseconds of arithmetic).  The Jacobian diagnostics of
+// src/monotonicity.jl and the saved outputs follow as one small launch each.  ECONPDES_FUSED_1D=0 keeps such
+// problems on the generic engine.
+static thread_local econpdes_batch* t_single = nullptr;
+static int batch_launch(econpdes_batch* b, const econpdes_options* options, int log_capacity, long long first,
+                        long long last, cudaStream_t s);
+
+static bool solve_fused_1d(const econpdes_problem* p, const econpdes_options* opt, econpdes_result* res, int* rc_out) {
+  static const bool enabled = [] { const char* e = std::getenv("ECONPDES_FUSED_1D"); return !(e && e[0] == '0'); }();
+  if (!enabled) return false;
+  const ModelOps* ops = model_ops(p->model_id);
+  if (ops == nullptr || ops->N() != 1 || ops->F() != 1 || ops->time_slot() >= 0) return false;
+  if (p->ndims != 1 || p->nfuncs != 1 || p->nparams != ops->nparams()) return false;   // make_ctx reports these
+  const long long S = p->size[0];
+  if (S < 2 || S > 1024 || p->grid[0] == nullptr || p->guess == nullptr || p->delta_vec != nullptr) return false;
+  if (std::isnan(opt->delta) || opt->delta == 0.0) return false;                        // Solver::solve reports it
+  if (p->bc != nullptr)
+    for (long long j = 0; j < S; ++j)
+      if (p->bc[j] != 0.0) return false;
+  if (p->is_algebraic != nullptr)
+    for (long long j = 0; j < S; ++j)
+      if (p->is_algebraic[j] != 0) return false;
+  if (p->lower_bound != nullptr)
+    for (long long j = 0; j < S; ++j)
+      if (p->lower_bound[j] != -INFINITY) return false;
+  if (p->upper_bound != nullptr)
+    for (long long j = 0; j < S; ++j)
+      if (p->upper_bound[j] != INFINITY) return false;
+  ensure_device();
+  int device = -1;
+  cudaGetDevice(&device);
+  econpdes_batch* b = t_single;
+  if (b == nullptr || b->model_id != p->model_id || b->S != S || b->device != device) {
+    delete t_single;
+    t_single = nullptr;
+    if (econpdes_batch_create(p->model_id, 1, S, &b) != ECONPDES_OK) throw std::runtime_error(econpdes_last_error());
+    b->device = device;
+    t_single = b;
+  }
+  cudaStream_t s = b->stream;
+  const int64_t l0 = g_kernel_launches.load();
+  if (b->nparams > 0) b->params.upload(p->params, static_cast<size_t>(b->nparams), s);
+  b->grids.upload(p->grid[0], static_cast<size_t>(S), s);
+  b->guess.upload(p->guess, static_cast<size_t>(S), s);
+  b->explicit_grids = b->explicit_guess = true;
+  const int cap = res->log != nullptr && res->log_capacity > 0 ? res->log_capacity : 0;
+  b->log_capacity = cap;
+  if (cap > 0) b->log.alloc(static_cast<size_t>(cap));
+  cudaEvent_t e0, e1;
+  EP_CUDA(cudaEventCreate(&e0));
+  EP_CUDA(cudaEventCreate(&e1));
+  EP_CUDA(cudaEventRecord(e0, s));
+  batch_launch(b, opt, cap, 0, -1, nullptr);
+  // results of the solve, needed to decide on the diagnostics
+  int h_int[5] = {0, 0, 0, 0, 0};   // error, exit_reason, n_outer, n_newton, log_len
+  double h_rn = 0.0;
+  b->error.download(&h_int[0], 1, s);
+  b->exit_reason.download(&h_int[1], 1, s);
+  b->n_outer.download(&h_int[2], 1, s);
+  b->n_newton.download(&h_int[3], 1, s);
+  b->log_len.download(&h_int[4], 1, s);
+  b->residual_norm.download(&h_rn, 1, s);
+  EP_CUDA(cudaStreamSynchronize(s));
+  res->sign_flags = 0;
+  res->nonmonotone_entries = 0;
+  res->nonmonotone_max = 0.0;
+  // src/monotonicity.jl: the sign convention is checked on the first Jacobian assembled with a finite step, stencil
+  // monotonicity (opt-in) on the first Jacobian whatever the step -- both at the guess, where the first Newton
+  // iteration of the solve linearised
+  const bool do_sign = std::isfinite(opt->delta), do_stencils = opt->check_monotonicity != 0;
+  if (h_int[0] == 0 && h_int[3] > 0 && (do_sign || do_stencils)) {
+    DevBuf<int> counts;
+    DevBuf<unsigned long long> mx;
+    counts.alloc(3);
+    mx.alloc(1);
+    counts.zero(s);
+    mx.zero(s);
+    ops->diag_1d(static_cast<int>(S), p->params, b->grids.p, b->guess.p, opt->delta, opt->monotonicity_tol, do_sign ? 1 : 0,
+                 do_stencils ? 1 : 0, counts.p, mx.p, s);
+    int h[3];
+    unsigned long long hm = 0;
+    counts.download(h, 3, s);
+    mx.download(&hm, 1, s);
+    EP_CUDA(cudaStreamSynchronize(s));
+    if (do_sign && h[0] > 0 && h[1] == h[0]) {
+      res->sign_flags |= 1;
+      if (opt->delta > 0) res->sign_flags |= ECONPDES_SIGN_WHOLE_SYSTEM;
+    }
+    if (do_stencils) {
+      res->nonmonotone_entries = h[2];
+      std::memcpy(&res->nonmonotone_max, &hm, sizeof(double));
+    }
+  }
+  DevBuf<double> saved;
+  if (h_int[0] == 0 && res->saved != nullptr && ops->nsaved() > 0) {
+    saved.alloc(static_cast<size_t>(ops->nsaved()) * S);
+    ops->saved_1d(static_cast<int>(S), p->params, b->grids.p, b->solution.p, saved.p, s);
+  }
+  EP_CUDA(cudaEventRecord(e1, s));
+  if (res->solution != nullptr) b->solution.download(res->solution, static_cast<size_t>(S), s);
+  if (saved.p != nullptr) saved.download(res->saved, saved.n, s);
+  const int nrows = h_int[4] < cap ? h_int[4] : cap;
+  if (nrows > 0) b->log.download(res->log, static_cast<size_t>(nrows), s);
+  EP_CUDA(cudaEventSynchronize(e1));
+  EP_CUDA(cudaStreamSynchronize(s));
+  float ms = 0.f;
+  EP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  res->log_len = nrows;
+  res->residual_norm = h_rn;
+  res->converged = h_rn <= opt->abstol ? 1 : 0;
+  res->exit_reason = h_int[1];
+  res->n_outer = h_int[2];
+  res->n_newton = h_int[3];
+  res->n_linear_iters = 0;
+  res->n_linear_solves = 0;
+  res->n_linear_loose = 0;
+  res->lin_max_relres = 0.0;
+  res->device_ms = ms;
+  res->kernel_launches = g_kernel_launches.load() - l0;
+  *rc_out = ECONPDES_OK;
+  if (h_int[0] != 0) {
+    set_error("G! returns NaN with the initial value");   // finiteschemesolve.jl:372
+    *rc_out = ECONPDES_E_NAN_GUESS;
+  }
+  return true;
+}
+
 int econpdes_solve_stationary(const econpdes_problem* problem, const econpdes_options* options,
                               econpdes_result* result) {
   return guarded([&] {
     if (!problem || !options || !result) throw std::invalid_argument("null argument");
+    int rc = ECONPDES_OK;
+    if (solve_fused_1d(problem, options, result, &rc)) return rc;
     Solver solver(make_ctx(problem));
     return solver.solve(*options, result);
   });
@@ -527,8 +661,8 @@ int econpdes_batch_upload_inputs(econpdes_batch* b, const econpdes_batch_inputs*
 }
 
 // launches the problems [first, last) on stream s (the whole batch on the batch's own stream by default)
-static int batch_launch(econpdes_batch* b, const econpdes_options* options, int log_capacity, long long first = 0,
-                        long long last = -1, cudaStream_t s = nullptr) {
+static int batch_launch(econpdes_batch* b, const econpdes_options* options, int log_capacity, long long first,
+                        long long last, cudaStream_t s) {
   if (std::isnan(options->delta) || options->delta == 0.0)
     throw std::invalid_argument("`Δ` entries must be nonzero and not NaN (use `Inf` for no damping, a negative entry for forward relaxation)");
   BatchArgs a;
@@ -573,7 +707,7 @@ int econpdes_batch_solve(econpdes_batch* b, const econpdes_options* options, dou
     EP_CUDA(cudaEventCreate(&e0));
     EP_CUDA(cudaEventCreate(&e1));
     EP_CUDA(cudaEventRecord(e0, b->stream));
-    batch_launch(b, options, b->log_capacity);
+    batch_launch(b, options, b->log_capacity, 0, -1, nullptr);
     EP_CUDA(cudaEventRecord(e1, b->stream));
     EP_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;
@@ -656,6 +790,8 @@ int econpdes_set_batch_points_per_thread(int points) {
 void econpdes_release_workspace(void) {
   delete t_workspace;
   t_workspace = nullptr;
+  delete t_single;
+  t_single = nullptr;
 }
 
 int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, const double* params, const double* grids,

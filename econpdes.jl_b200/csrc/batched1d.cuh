@@ -101,6 +101,62 @@ static __global__ void __launch_bounds__(256) k_expand_batch_inputs(long long fi
   if (guess_out != nullptr) guess_out[b * S + k] = guess_fill;
 }
 
+// Jacobian diagnostics of src/monotonicity.jl for ONE 1-D single-unknown problem (the single-`pdesolve` route
+// through the fused kernel): the colored-FD Jacobian of G at y, one thread per row, and the two reductions of
+// k_jacobian_diagnostics (engine.cu): counts[0] rows whose diagonal dG_i/dy_i exceeds tol in magnitude, counts[1]
+// those of them whose sign is opposite to the step's, counts[2] off-diagonal entries above tol, maxbits the largest.
+template <class M>
+__global__ void __launch_bounds__(1024) k_diag_1d(int S, ParamPack prmpack, const double* __restrict__ x,
+                                                  const double* __restrict__ yin, double delta, double tol, int signs,
+                                                  int stencils, int* __restrict__ counts,
+                                                  unsigned long long* __restrict__ maxbits) {
+  static_assert(M::N == 1 && M::F == 1, "1-D single-unknown models");
+  __shared__ double red[8 * 32];
+  __shared__ double ysh[1024 + 2];
+  const int t = threadIdx.x;
+  const bool act = t < S;
+  if (t == 0) { ysh[0] = 0.0; ysh[S + 1] = 0.0; }
+  if (act) ysh[t + 1] = yin[t];
+  __syncthreads();
+  double s3[3] = {0.0, 0.0, 0.0}, m0[1];
+  const double q = act ? ysh[t + 1] * ysh[t + 1] : 0.0;
+  s3[t % 3] = q;
+  block_reduce_mixed<3, 0>(s3, m0, red);
+  double eps_table[3], reps_table[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    eps_table[c] = color_epsilon_from_sumsq(s3[c]);
+    reps_table[c] = 1.0 / eps_table[c];
+  }
+  if (!act) return;
+  GridView<1> gv;
+  gv.x[0] = x; gv.S[0] = S; gv.stride[0] = 1; gv.l = S;
+  long long idx[1] = {t};
+  PointGeom<1, 1> g;
+  double st[1];
+  load_geom(gv, idx, g, st);
+  typename M::Pre pre;
+  M::prepare(prmpack.v, st, pre);
+  const double bl[1][1] = {{0.0}}, bh[1][1] = {{0.0}};
+  double w[1][3] = {{ysh[t], ysh[t + 1], ysh[t + 2]}};
+  RowTerms rt;
+  rt.implicit = false; rt.has_bounds = false; rt.ypost = 0.0; rt.delta = delta; rt.lb = 0.0; rt.ub = 0.0; rt.is_alg = false;
+  double r0[1], va = 0.0, vb = 0.0, vc = 0.0;
+  jacobian_point<M, false, false, 0>(pre, g, idx, gv, w, bl, bh, &rt, eps_table, 0, r0,
+                                     [&](int k, int, int, double v) {
+                                       if (k == 0) vb = v; else if (k == 1) va = v; else vc = v;
+                                     }, reps_table);
+  if (signs && isfinite(delta) && fabs(vb) > tol) {
+    atomicAdd(&counts[0], 1);
+    const bool same = (vb > 0 && delta > 0) || (vb < 0 && delta < 0);
+    if (!same) atomicAdd(&counts[1], 1);
+  }
+  if (stencils) {
+    if (va > tol) { atomicAdd(&counts[2], 1); atomicMax(maxbits, static_cast<unsigned long long>(__double_as_longlong(va))); }
+    if (vc > tol) { atomicAdd(&counts[2], 1); atomicMax(maxbits, static_cast<unsigned long long>(__double_as_longlong(vc))); }
+  }
+}
+
 // threads of a block that covers the engine's maximum of 1024 points with P points each (whole warps)
 constexpr int batched_max_threads(int P) { return ((1024 + P - 1) / P + 31) / 32 * 32; }
 
@@ -384,7 +440,9 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
         if (t == 0 && args.log != nullptr && log_len < args.log_capacity) {
           econpdes_log_row& row = args.log[b * args.log_capacity + log_len];
           row.iter = iter; row.status = status; row.newton_iters = newton_it; row.linear_iters = 0;
-          row.delta = ctl.delta; row.residual = NAN;
+          row.delta = ctl.delta;
+          // growth rejections carry the factor the reference prints (finiteschemesolve.jl:433-435), like the generic engine
+          row.residual = status == ECONPDES_STEP_REJECTED_GROWTH ? rn / old_r : NAN;
         }
         ctl.reject();
         publish(ypost);   // the next Newton solve starts from the reverted point

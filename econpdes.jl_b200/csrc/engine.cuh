@@ -168,6 +168,11 @@ struct ModelOps {
   virtual void saved(const Ctx& c, const double* y, double* out) const = 0;
   // fused batched engine; returns false if the model is not 1-D single-unknown
   virtual bool batched(const struct BatchArgs& a, cudaStream_t s) const = 0;
+  // single 1-D single-unknown problem (device pointers): the Jacobian diagnostics of k_diag_1d and the saved
+  // outputs, without a Ctx; return false for other models
+  virtual bool diag_1d(int S, const double* prm, const double* x, const double* y, double delta, double tol, int signs,
+                       int stencils, int* counts, unsigned long long* maxbits, cudaStream_t s) const = 0;
+  virtual bool saved_1d(int S, const double* prm, const double* x, const double* y, double* out, cudaStream_t s) const = 0;
 };
 const ModelOps* model_ops(int model_id);
 int model_count();

@@ -199,6 +199,35 @@ struct ModelOpsT final : ModelOps {
     EP_LAUNCH(k_saved<M>, blocks_for(c.l), kBlock, 0, c.stream, c.grid_view<M::N>(), c.prm, y, c.bc.p, out);
   }
   bool batched(const BatchArgs& a, cudaStream_t s) const override { return BatchedLaunch<M>::run(a, s); }
+  static ParamPack pack_params(const double* prm) {
+    ParamPack pk{};
+    for (int i = 0; i < M::NPARAMS; ++i) pk.v[i] = prm[i];
+    M::derive(pk.v);
+    return pk;
+  }
+  bool diag_1d(int S, const double* prm, const double* x, const double* y, double delta, double tol, int signs,
+               int stencils, int* counts, unsigned long long* maxbits, cudaStream_t s) const override {
+    if constexpr (M::N == 1 && M::F == 1) {
+      const int T = ((S + 31) / 32) * 32;
+      EP_LAUNCH(k_diag_1d<M>, 1, T, 0, s, S, pack_params(prm), x, y, delta, tol, signs, stencils, counts, maxbits);
+      return true;
+    } else {
+      return false;
+    }
+  }
+  bool saved_1d(int S, const double* prm, const double* x, const double* y, double* out, cudaStream_t s) const override {
+    if constexpr (M::N == 1 && M::F == 1) {
+      if (M::NSAVED == 0) return true;
+      GridView<1> gv;
+      const long long sizes[1] = {S};
+      gv.set_sizes(sizes);
+      gv.x[0] = x;
+      EP_LAUNCH(k_saved<M>, blocks_for(S), kBlock, 0, s, gv, pack_params(prm), y, static_cast<const double*>(nullptr), out);
+      return true;
+    } else {
+      return false;
+    }
+  }
 };
 
 template <int I>

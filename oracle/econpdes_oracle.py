@@ -434,6 +434,11 @@ class NewtonResult:
     residual_inf: float
 
 
+# how often the Newton iteration met a singular Jacobian and took NLsolve's regularised-normal-equations retry
+# (the device path rejects such a step instead: tests/test_oracle.py checks that no config or fixture gets there)
+STATS = {"singular_retries": 0}
+
+
 def nlsolve_newton(R, Jfun, cache: JacobianCache, x0, ftol, iterations) -> NewtonResult:
     """NLsolve 4.x newton_ (Static line search).  One Jacobian per iteration; the
     Jacobian at the initial point is only built if an iteration is taken (the published
@@ -455,6 +460,7 @@ def nlsolve_newton(R, Jfun, cache: JacobianCache, x0, ftol, iterations) -> Newto
             p = -p
         except SingularException:
             # NLsolve's fallback: regularised normal equations (newton.jl, Nocedal&Wright p.289)
+            STATS["singular_retries"] += 1
             A = sp.csc_matrix((np.nan_to_num(nzval), cache.indices0, cache.indptr0), shape=(n, n))
             if not np.all(np.isfinite(nzval)):
                 raise

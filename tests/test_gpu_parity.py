@@ -1000,3 +1000,37 @@ def test_time_dependent_two_dimensional_model():
     res = E.pdesolve(PM.BansalYaronModel(**prm), g, gu, taus, verbose=False)
     np.testing.assert_allclose(res.solution["p"], ora.solution["p"], rtol=1e-8)
     np.testing.assert_allclose(res.residual_norm, ora.residual_norm, rtol=0, atol=1e-10)
+
+
+@pytest.mark.gpu
+def test_single_1d_pdesolve_takes_the_fused_kernel():
+    """A single 1-D single-unknown `pdesolve` (default boundary rows, no bounds / algebraic rows) is one launch of the
+    fused kernel plus one small launch for the Jacobian diagnostics (and one for saved outputs): the README
+    quickstart and the Campbell-Cochrane example keep the oracle's iteration log; problems the fused kernel does not
+    take (boundary values, bounds) still go through the generic engine."""
+    g, gu = OM.readme_linear_problem(50)
+    res = E.pdesolve(PM.ReadmeLinear(), g, gu, verbose=False)
+    ora = eo.pdesolve(OM.readme_linear(), g, gu)
+    assert res.kernel_launches <= 3 and res.converged
+    assert [r["status"] for r in res.log] == [r[3] for r in ora.log.rows]
+    assert [r["newton_iters"] for r in res.log] == [r[4] for r in ora.log.rows]
+    np.testing.assert_allclose([r["delta"] for r in res.log], [r[1] for r in ora.log.rows], rtol=1e-12)
+    np.testing.assert_allclose(res.solution["v"], ora.solution["v"], rtol=1e-8)
+    g, gu, prm = OM.campbell_cochrane_problem()
+    res = E.pdesolve(PM.CampbellCochraneModel(**prm), g, gu, verbose=False)
+    ora = eo.pdesolve(OM.campbell_cochrane(**prm), g, gu)
+    assert res.kernel_launches <= 3
+    assert [r["newton_iters"] for r in res.log] == [r[4] for r in ora.log.rows]
+    np.testing.assert_allclose(res.solution["p"], ora.solution["p"], rtol=1e-8)
+    assert abs(res.residual_norm - ora.residual_norm) <= 1e-10
+    # saved outputs ride along (one more launch)
+    g, gu, prm = OM.neoclassical_growth_problem(200)
+    res = E.pdesolve(PM.NeoclassicalGrowthModel(**prm), g, gu, verbose=False)
+    ora = eo.pdesolve(OM.neoclassical_growth(**prm), g, gu)
+    assert res.kernel_launches <= 3 and set(res.saved) == set(ora.saved)
+    for k in ora.saved:
+        np.testing.assert_allclose(res.saved[k], ora.saved[k], rtol=1e-7, atol=1e-9, err_msg=k)
+    # not eligible: non-zero boundary rows -> the generic engine (many launches)
+    g, gu, prm, bc = OM.wang_wang_yang_problem(101)
+    res = E.pdesolve(PM.WangWangYangModel(**prm), g, gu, bc=bc, verbose=False)
+    assert res.kernel_launches > 3

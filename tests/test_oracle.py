@@ -360,3 +360,26 @@ def test_example_models_economic_sanity():
     # consumption rises with wealth; the y-edge rows are left out: their corners read the (v, a) boundary values in the
     # y-direction stencils too (one bc slot per point, src/pdesolve.jl:312-335)
     assert (np.diff(res.saved["c"][1:-1], axis=1) > 0).all()
+
+
+def test_no_config_takes_the_singular_jacobian_retry():
+    """NLsolve retries a singular Newton system with regularised normal equations (restated in
+    econpdes_oracle.nlsolve_newton); the device path rejects such a step as "singular Jacobian" instead.  The two
+    only differ if some solve gets there: none of the configs and example fixtures does (the full-size C2 64 x 4096,
+    C3 256^2 and C5 24^3 oracle solves were checked the same way when their fixtures were generated: 0 retries)."""
+    eo.STATS["singular_retries"] = 0
+    g, gu = M.readme_linear_problem(50)
+    eo.pdesolve(M.readme_linear(), g, gu)
+    g, gu, prm = M.campbell_cochrane_problem()
+    eo.pdesolve(M.campbell_cochrane(**prm), g, gu)
+    g, gu, prm = M.bansal_yaron_problem(30, 30)
+    eo.pdesolve(M.bansal_yaron(**prm), g, gu)
+    g, gu, prm = M.ahlm_diffusion_problem(10, 100)
+    eo.pdesolve(M.ahlm_diffusion(**prm), g, gu)
+    g, gu, prm = M.hjb3d_problem(8)
+    eo.pdesolve(M.hjb3d_synth(**prm), g, gu)
+    g, gu, prm = M.neoclassical_growth_problem(200)
+    eo.pdesolve(M.neoclassical_growth(**prm), g, gu)
+    g, gu, prm = M.gomez_problem(100)
+    eo.pdesolve(M.gomez(**prm), g, gu)
+    assert eo.STATS["singular_retries"] == 0
