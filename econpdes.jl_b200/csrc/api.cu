@@ -109,7 +109,16 @@ struct econpdes_batch {
   int n_range = 0;
   bool explicit_grids = true, explicit_guess = true;
   double guess_fill = 0.0;
-  DevBuf<int> exit_reason, n_outer, n_newton, error, log_len;
+  // per-problem integers in ONE allocation, [4][B] = error, exit_reason, n_outer, n_newton, so a slice's four
+  // ranges come back with a single pitched copy (a small copy costs ~8 us of copy-engine time each way)
+  DevBuf<int> ints;
+  struct IntView {
+    int* p = nullptr;
+    void download(int* h, size_t count, cudaStream_t s) const {
+      EP_CUDA(cudaMemcpyAsync(h, p, count * sizeof(int), cudaMemcpyDeviceToHost, s));
+    }
+  } exit_reason, n_outer, n_newton, error;
+  DevBuf<int> log_len;
   DevBuf<econpdes_log_row> log;
   int log_capacity = 0;
   int64_t launches = 0;
@@ -579,10 +588,11 @@ int econpdes_batch_create(int model_id, int64_t nproblems, int64_t npoints, econ
     b->params.alloc(B * (b->nparams > 0 ? b->nparams : 1));
     b->solution.alloc(B * S);   // grids / guess: allocated by the upload that brings them
     b->residual_norm.alloc(B);
-    b->exit_reason.alloc(B);
-    b->n_outer.alloc(B);
-    b->n_newton.alloc(B);
-    b->error.alloc(B);
+    b->ints.alloc(4 * B);
+    b->error.p = b->ints.p;
+    b->exit_reason.p = b->ints.p + B;
+    b->n_outer.p = b->ints.p + 2 * B;
+    b->n_newton.p = b->ints.p + 3 * B;
     b->log_len.alloc(B);
     *out = b.release();
     return ECONPDES_OK;
@@ -884,17 +894,13 @@ int econpdes_solve_batched_inputs(int model_id, int64_t nproblems, int64_t npoin
       cudaStream_t s = b->pipe[c % econpdes_batch::kPipe];
       batch_upload_slice(b, in, first, last, s);
       batch_launch(b, options, 0, first, last, s);
-      EP_CUDA(cudaMemcpyAsync(err + o, b->error.p + o, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+      // error, exit_reason, n_outer, n_newton of the slice: four rows of one pitched copy
+      EP_CUDA(cudaMemcpy2DAsync(err + o, nB * sizeof(int), b->ints.p + o, nB * sizeof(int), n * sizeof(int), 4,
+                                cudaMemcpyDeviceToHost, s));
       if (solution)
         EP_CUDA(cudaMemcpyAsync(solution + o * S, b->solution.p + o * S, n * S * sizeof(double), cudaMemcpyDeviceToHost, s));
       if (residual_norm)
         EP_CUDA(cudaMemcpyAsync(b->rn_host + o, b->residual_norm.p + o, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-      if (exit_reason)
-        EP_CUDA(cudaMemcpyAsync(err + nB + o, b->exit_reason.p + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-      if (n_outer)
-        EP_CUDA(cudaMemcpyAsync(err + 2 * nB + o, b->n_outer.p + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-      if (n_newton)
-        EP_CUDA(cudaMemcpyAsync(err + 3 * nB + o, b->n_newton.p + o, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     }
     for (cudaStream_t p : b->pipe) EP_CUDA(cudaStreamSynchronize(p));
     drain.armed = false;

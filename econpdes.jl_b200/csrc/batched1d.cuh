@@ -170,6 +170,7 @@ constexpr int batched_max_threads(int P) { return ((1024 + P - 1) / P + 31) / 32
 template <class M, int P, bool PER_COL>
 __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_1d(BatchArgs args) {
   static_assert(M::N == 1 && M::F == 1, "the fused batched engine handles 1-D single-unknown models");
+  static_assert(M::NPARAMS + M::NDERIVED <= kMaxBatchParams, "parameter staging area of the batched kernel too small");
   extern __shared__ double smem[];
   const int T = blockDim.x;
   const int NP = T * P;

@@ -324,7 +324,11 @@ struct TridiagSolver final : LinearSolver {
       case 2: return pcr_solve<2>(c_, planes, b, x, work_);
       case 3: return pcr_solve<3>(c_, planes, b, x, work_);
       case 4: return pcr_solve<4>(c_, planes, b, x, work_);
-      default: throw std::invalid_argument("block-tridiagonal solver supports up to 4 unknowns");
+      case 5: return pcr_solve<5>(c_, planes, b, x, work_);
+      case 6: return pcr_solve<6>(c_, planes, b, x, work_);
+      case 7: return pcr_solve<7>(c_, planes, b, x, work_);
+      case 8: return pcr_solve<8>(c_, planes, b, x, work_);
+      default: throw std::invalid_argument("block-tridiagonal solver supports up to 8 unknowns");
     }
   }
   Ctx& c_;

@@ -16,7 +16,7 @@
 namespace econpdes {
 
 struct ParamPack {
-  double v[16];
+  double v[kMaxParams];
 };
 
 // Device-side description of R(y) = G(y) - (!alg) (ypost - y) / (delta * delta_rel), then MCP.
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_residual(GridView<M::N> gv, Par
 // are folded with shuffles (3 colors per warp in the common case of a warp inside one grid
 // row), warps fold into per-block bins, blocks into `part`, and the last block finishes in
 // block order and converts the sums into FiniteDiff steps.  ncolors <= kMaxColors.
-constexpr int kMaxColors = 27 * 4;
+constexpr int kMaxColors = 27 * 8;   // 3^3 grid colors x ECONPDES_MAX_FUNCS unknowns
 
 struct ColorWork {
   double* part;       // [max_blocks][ncolors]

@@ -2257,7 +2257,11 @@ std::unique_ptr<LinearSolver> make_block_solver(Ctx& c) {
     case 2: return std::make_unique<BlockLineSolver<N, 2>>(c);
     case 3: return std::make_unique<BlockLineSolver<N, 3>>(c);
     case 4: return std::make_unique<BlockLineSolver<N, 4>>(c);
-    default: throw std::invalid_argument("2-D/3-D systems take at most 4 unknowns per grid point");
+    case 5: return std::make_unique<BlockLineSolver<N, 5>>(c);
+    case 6: return std::make_unique<BlockLineSolver<N, 6>>(c);
+    case 7: return std::make_unique<BlockLineSolver<N, 7>>(c);
+    case 8: return std::make_unique<BlockLineSolver<N, 8>>(c);
+    default: throw std::invalid_argument("2-D/3-D systems take at most 8 unknowns per grid point");
   }
 }
 

@@ -104,13 +104,16 @@ struct ModelOpsT final : ModelOps {
     const char* e = std::getenv(name);
     return e ? std::atoi(e) : dflt;
   }
+  // the marching sweeps keep three planes of every unknown's box in registers: not for wide systems
+  // (8 unknowns on a 3-D box = 216 values), which take the one-thread-per-point kernels
+  static constexpr bool kMarchable = M::N >= 2 && M::F * ipow3(M::N) <= 108;
   static bool march_on() {
     static const bool on = env_int("ECONPDES_MARCH", 1) != 0;
-    return on && M::N >= 2;
+    return on && kMarchable;
   }
   template <int ROWKIND, int TAME>
   void residual_march(const Ctx& c, const double* y, const RowSpec& rs, double* out, bool want_norm) const {
-    if constexpr (M::N >= 2) {
+    if constexpr (kMarchable) {
       constexpr int RB = 128, MINB = 4, UNR = M::N >= 3 ? 1 : 3;
       static const int force_L = env_int("ECONPDES_MARCH_L", 0);
       const MarchPlan mp = make_march_plan(c.l / c.slab_count, c.slab_count, RB, 148 * MINB, force_L);
@@ -142,7 +145,7 @@ struct ModelOpsT final : ModelOps {
   template <bool BOX, int JMINB>
   void jacobian_march(const Ctx& c, const double* y, const RowSpec& rs, int per_col, double* planes, double* r0,
                       bool tame) const {
-    if constexpr (M::N >= 2) {
+    if constexpr (kMarchable) {
       constexpr int JB = 128;
       static const int force_L = env_int("ECONPDES_MARCH_LJ", 0);
       const MarchPlan mp = make_march_plan(c.l / c.slab_count, c.slab_count, JB, 148 * JMINB, force_L);
@@ -175,7 +178,7 @@ struct ModelOpsT final : ModelOps {
       }
     }
     constexpr bool BOX = M::USES_CROSS && M::N > 1;
-    if constexpr (M::N >= 2) {
+    if constexpr (kMarchable) {
       if (march_on()) {
         // 128-thread blocks, three per SM (168 registers): 2048^2 0.258 ms against 0.271 with four blocks of
         // 128 registers (spills); 256^3 1.59 ms against 2.19

@@ -46,7 +46,8 @@ struct ModelDefaults {
   // -1: the body takes no time argument.
   static constexpr int TIME_SLOT = -1;
 };
-constexpr int kMaxParams = 16;   // ParamPack: NPARAMS + NDERIVED
+constexpr int kMaxParams = 24;   // ParamPack: NPARAMS + NDERIVED (+ the time slot)
+constexpr int kMaxBatchParams = 16;   // the fused batched kernel stages that many in shared memory
 
 EP_HD double ep_min(double a, double b) { return a < b ? a : b; }   // operands are never NaN where used
 EP_HD double ep_max(double a, double b) { return a > b ? a : b; }
@@ -1047,6 +1048,145 @@ struct AhlmRiskyAsset : ModelDefaults {
   }
 };
 
+// examples/asset_pricing/garleanu_panageas_long_run_risk.jl:74-232 -- the reference's only 3-D example: states
+// (x, mu, v); unknowns pA, pB, phi1, phi2 (valuation ratios, backward equations) and r, kC, kM, kV (market-clearing
+// prices, forward equations; solved with the signed per-unknown steps of :337-344).  Two-pass upwinding in x
+// (`@goto start`, :117-165): the block is evaluated with the _up differences and, if the drift of x comes out <= 0,
+// again with the _down ones.  Cross derivatives in the (x, mu) and (x, v) planes only.
+// saved = (kappa, r_implied, kC_implied, kM_implied, kV_implied, r_gap, kC_gap, kM_gap, kV_gap, pA_residual,
+//          pB_residual, phi1_residual, phi2_residual, mux, sigmax, sigmaxC, sigmaxM, sigmaxV)
+struct GarleanuPanageasLRR : ModelDefaults {
+  static constexpr int N = 3, F = 8, NPARAMS = 18, NSAVED = 18;
+  static constexpr bool USES_CROSS = true;
+  static const char* name() { return "garleanu_panageas_lrr"; }
+  // axial neighbours and the corners of the (x, mu) and (x, v) planes
+  EP_HD static constexpr bool slot_used(int k) {
+    const int o1 = (k / 3) % 3 - 1, o2 = k / 9 - 1;
+    return o1 == 0 || o2 == 0;
+  }
+  struct Pre {
+    double gA, psA, gB, psB, rho, delta, nuA, B1, d1, B2, d2, omega;
+    double x, mu, sc, mumu, smu, muv, sv, G, aA, aB;
+  };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
+    c.gA = prm[0]; c.psA = prm[1]; c.gB = prm[2]; c.psB = prm[3]; c.rho = prm[4]; c.delta = prm[5]; c.nuA = prm[6];
+    const double mubar = prm[7], vbar = prm[8], kmu = prm[9], numu = prm[10], kv = prm[11], nuv = prm[12];
+    c.B1 = prm[13]; c.d1 = prm[14]; c.B2 = prm[15]; c.d2 = prm[16]; c.omega = prm[17];
+    const double x = st[0], mu = st[1], v = st[2];
+    c.x = x; c.mu = mu;
+    c.sc = sqrt(v);
+    c.mumu = kmu * (mubar - mu);
+    c.smu = numu * sqrt(v);
+    c.muv = kv * (vbar - v);
+    c.sv = nuv * sqrt(v);
+    c.G = 1 / (x / c.gA + (1 - x) / c.gB);
+    c.aA = (1 - c.gA * c.psA) / (c.gA * (c.psA - 1));
+    c.aB = (1 - c.gB * c.psB) / (c.gB * (c.psB - 1));
+  }
+  struct Pass {
+    double pAx_pA, pBx_pB, sxC, sxM, sxV, sx2, spA_C, spA_M, spA_V, spB_C, spB_M, spB_V, sCA_C, sCA_M, sCA_V, sCB_C, sCB_M,
+        sCB_V, mcA, mcB, muCA, muCB, mux;
+  };
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<3>* u, double* out, double* sv) {
+    const double x = c.x, mu = c.mu, sc = c.sc, smu = c.smu, svv = c.sv, gA = c.gA, gB = c.gB, aA = c.aA, aB = c.aB;
+    const double pA = u[0].v, pB = u[1].v, f1 = u[2].v, f2 = u[3].v, r = u[4].v, kC = u[5].v, kM = u[6].v, kV = u[7].v;
+    const bool upm = c.mumu >= 0, upv = c.muv >= 0;
+    const double pAmu = upm ? u[0].up[1] : u[0].dn[1], pBmu = upm ? u[1].up[1] : u[1].dn[1];
+    const double f1mu = upm ? u[2].up[1] : u[2].dn[1], f2mu = upm ? u[3].up[1] : u[3].dn[1];
+    const double pAv = upv ? u[0].up[2] : u[0].dn[2], pBv = upv ? u[1].up[2] : u[1].dn[2];
+    const double f1v = upv ? u[2].up[2] : u[2].dn[2], f2v = upv ? u[3].up[2] : u[3].dn[2];
+    const double pAmu_pA = pAmu / pA, pBmu_pB = pBmu / pB, pAv_pA = pAv / pA, pBv_pB = pBv / pB;
+    const double k2 = kC * kC + kM * kM + kV * kV;
+    const double human_capital = c.omega * (c.B1 * f1 + c.B2 * f2);
+    auto block = [&](double pAx, double pBx, Pass& q) {
+      q.pAx_pA = pAx / pA;
+      q.pBx_pB = pBx / pB;
+      const double denom = 1 - x * aA * q.pAx_pA;
+      q.sxC = x * (kC / gA - sc) / denom;
+      q.sxM = x * (kM / gA + aA * pAmu_pA * smu) / denom;
+      q.sxV = x * (kV / gA + aA * pAv_pA * svv) / denom;
+      q.sx2 = q.sxC * q.sxC + q.sxM * q.sxM + q.sxV * q.sxV;
+      q.spA_C = q.pAx_pA * q.sxC;
+      q.spA_M = q.pAx_pA * q.sxM + pAmu_pA * smu;
+      q.spA_V = q.pAx_pA * q.sxV + pAv_pA * svv;
+      q.spB_C = q.pBx_pB * q.sxC;
+      q.spB_M = q.pBx_pB * q.sxM + pBmu_pB * smu;
+      q.spB_V = q.pBx_pB * q.sxV + pBv_pB * svv;
+      q.sCA_C = kC / gA + aA * q.spA_C;
+      q.sCA_M = kM / gA + aA * q.spA_M;
+      q.sCA_V = kV / gA + aA * q.spA_V;
+      q.sCB_C = kC / gB + aB * q.spB_C;
+      q.sCB_M = kM / gB + aB * q.spB_M;
+      q.sCB_V = kV / gB + aB * q.spB_V;
+      const double spA2 = q.spA_C * q.spA_C + q.spA_M * q.spA_M + q.spA_V * q.spA_V;
+      const double spB2 = q.spB_C * q.spB_C + q.spB_M * q.spB_M + q.spB_V * q.spB_V;
+      const double kspA = kC * q.spA_C + kM * q.spA_M + kV * q.spA_V;
+      const double kspB = kC * q.spB_C + kM * q.spB_M + kV * q.spB_V;
+      q.mcA = (1 + c.psA) / (2 * gA) * k2 + aA * kspA - 0.5 * aA * spA2;
+      q.mcB = (1 + c.psB) / (2 * gB) * k2 + aB * kspB - 0.5 * aB * spB2;
+      q.muCA = c.psA * (r - c.rho) + q.mcA;
+      q.muCB = c.psB * (r - c.rho) + q.mcB;
+      q.mux = x * (q.muCA - mu) + c.delta * (c.nuA / pA * human_capital - x) - sc * q.sxC;
+    };
+    Pass q;
+    block(u[0].up[0], u[1].up[0], q);
+    double f1x = u[2].up[0], f2x = u[3].up[0];
+    if (q.mux <= 0) {
+      block(u[0].dn[0], u[1].dn[0], q);
+      f1x = u[2].dn[0];
+      f2x = u[3].dn[0];
+    }
+    const bool cm = q.sxM * smu >= 0, cv = q.sxV * svv >= 0;
+    // pairs: (x, mu) = 0, (x, v) = 1
+    const double pAxmu = cm ? u[0].xu[0] : u[0].xd[0], pBxmu = cm ? u[1].xu[0] : u[1].xd[0];
+    const double f1xmu = cm ? u[2].xu[0] : u[2].xd[0], f2xmu = cm ? u[3].xu[0] : u[3].xd[0];
+    const double pAxv = cv ? u[0].xu[1] : u[0].xd[1], pBxv = cv ? u[1].xu[1] : u[1].xd[1];
+    const double f1xv = cv ? u[2].xu[1] : u[2].xd[1], f2xv = cv ? u[3].xu[1] : u[3].xd[1];
+    const double f1x_f1 = f1x / f1, f2x_f2 = f2x / f2, f1mu_f1 = f1mu / f1, f2mu_f2 = f2mu / f2;
+    const double f1v_f1 = f1v / f1, f2v_f2 = f2v / f2;
+    const double sf1_C = f1x_f1 * q.sxC, sf1_M = f1x_f1 * q.sxM + f1mu_f1 * smu, sf1_V = f1x_f1 * q.sxV + f1v_f1 * svv;
+    const double sf2_C = f2x_f2 * q.sxC, sf2_M = f2x_f2 * q.sxM + f2mu_f2 * smu, sf2_V = f2x_f2 * q.sxV + f2v_f2 * svv;
+    const double smu2 = smu * smu, sv2 = svv * svv;
+    const double mupA = q.pAx_pA * q.mux + pAmu_pA * c.mumu + pAv_pA * c.muv + 0.5 * u[0].dd[0] / pA * q.sx2 +
+                        0.5 * u[0].dd[1] / pA * smu2 + 0.5 * u[0].dd[2] / pA * sv2 + pAxmu / pA * q.sxM * smu +
+                        pAxv / pA * q.sxV * svv;
+    const double mupB = q.pBx_pB * q.mux + pBmu_pB * c.mumu + pBv_pB * c.muv + 0.5 * u[1].dd[0] / pB * q.sx2 +
+                        0.5 * u[1].dd[1] / pB * smu2 + 0.5 * u[1].dd[2] / pB * sv2 + pBxmu / pB * q.sxM * smu +
+                        pBxv / pB * q.sxV * svv;
+    const double muf1 = f1x_f1 * q.mux + f1mu_f1 * c.mumu + f1v_f1 * c.muv + 0.5 * u[2].dd[0] / f1 * q.sx2 +
+                        0.5 * u[2].dd[1] / f1 * smu2 + 0.5 * u[2].dd[2] / f1 * sv2 + f1xmu / f1 * q.sxM * smu +
+                        f1xv / f1 * q.sxV * svv;
+    const double muf2 = f2x_f2 * q.mux + f2mu_f2 * c.mumu + f2v_f2 * c.muv + 0.5 * u[3].dd[0] / f2 * q.sx2 +
+                        0.5 * u[3].dd[1] / f2 * smu2 + 0.5 * u[3].dd[2] / f2 * sv2 + f2xmu / f2 * q.sxM * smu +
+                        f2xv / f2 * q.sxV * svv;
+    const double sCAspA = q.sCA_C * q.spA_C + q.sCA_M * q.spA_M + q.sCA_V * q.spA_V;
+    const double sCBspB = q.sCB_C * q.spB_C + q.sCB_M * q.spB_M + q.sCB_V * q.spB_V;
+    const double kspA_CA = kC * (q.spA_C + q.sCA_C) + kM * (q.spA_M + q.sCA_M) + kV * (q.spA_V + q.sCA_V);
+    const double kspB_CB = kC * (q.spB_C + q.sCB_C) + kM * (q.spB_M + q.sCB_M) + kV * (q.spB_V + q.sCB_V);
+    const double pAt = -pA * (1 / pA + q.muCA + mupA + sCAspA - r - c.delta - kspA_CA);
+    const double pBt = -pB * (1 / pB + q.muCB + mupB + sCBspB - r - c.delta - kspB_CB);
+    const double ksf1_Y = kC * (sf1_C + sc) + kM * sf1_M + kV * sf1_V;
+    const double ksf2_Y = kC * (sf2_C + sc) + kM * sf2_M + kV * sf2_V;
+    const double f1t = -f1 * (1 / f1 + mu - c.delta - c.d1 + muf1 + sc * sf1_C - r - ksf1_Y);
+    const double f2t = -f2 * (1 / f2 + mu - c.delta - c.d2 + muf2 + sc * sf2_C - r - ksf2_Y);
+    const double kC_imp = c.G * (sc - x * aA * q.spA_C - (1 - x) * aB * q.spB_C);
+    const double kM_imp = c.G * (0.0 - x * aA * q.spA_M - (1 - x) * aB * q.spB_M);
+    const double kV_imp = c.G * (0.0 - x * aA * q.spA_V - (1 - x) * aB * q.spB_V);
+    const double r_imp = c.rho + (mu - x * q.mcA - (1 - x) * q.mcB -
+                                  c.delta * ((c.nuA / pA + (1 - c.nuA) / pB) * human_capital - 1)) /
+                                     (c.psA * x + c.psB * (1 - x));
+    out[0] = pAt; out[1] = pBt; out[2] = f1t; out[3] = f2t;
+    out[4] = r_imp - r; out[5] = kC_imp - kC; out[6] = kM_imp - kM; out[7] = kV_imp - kV;
+    if (SAVE) {
+      sv[0] = sqrt(k2); sv[1] = r_imp; sv[2] = kC_imp; sv[3] = kM_imp; sv[4] = kV_imp;
+      sv[5] = out[4]; sv[6] = out[5]; sv[7] = out[6]; sv[8] = out[7];
+      sv[9] = pAt; sv[10] = pBt; sv[11] = f1t; sv[12] = f2t;
+      sv[13] = q.mux; sv[14] = sqrt(q.sx2); sv[15] = q.sxC; sv[16] = q.sxM; sv[17] = q.sxV;
+    }
+  }
+};
+
 // test/runtests.jl:422-431 (residual-growth guard): vt = a v - k v^3 at every grid point (the reference's
 // scalar hump!(ydot, y) = y - y^3 with a = k = 1); no derivative enters, so the Jacobian is diagonal.
 struct PointwiseCubic : ModelDefaults {
@@ -1107,6 +1247,7 @@ struct AffinePair : ModelDefaults {
   X(Gomez)                         \
   X(AhlmRiskyAsset)                \
   X(PointwiseCubic)                \
-  X(AffinePair)
+  X(AffinePair)                    \
+  X(GarleanuPanageasLRR)
 
 }  // namespace econpdes

@@ -288,9 +288,13 @@ EP_HD void jacobian_point(const typename M::Pre& pre, const G& g, const long lon
   int i3[N];
 #pragma unroll
   for (int d = 0; d < N; ++d) i3[d] = static_cast<int>(idx[d] % 3);
-#pragma unroll
+  // wide systems (the 8-unknown 3-D long-run-risk model: 216 columns per row) keep these two loops rolled: the
+  // body is the whole model evaluation, and unrolling it a hundred times buys nothing but compile time
+  constexpr bool WIDE = F * St::NK > 48;
+  constexpr int UNR_FIN = WIDE ? 1 : F, UNR_K = WIDE ? 1 : St::NK;
+#pragma unroll UNR_FIN
   for (int fin = 0; fin < F; ++fin) {
-#pragma unroll
+#pragma unroll UNR_K
     for (int k = 0; k < St::NK; ++k) {
       bool ok = true;
       int color = 0, stride = 1;

@@ -208,6 +208,41 @@ class GarleanuPanageasModel(RegisteredModel):
     savednames: ClassVar = ("r", "kappa")
 
 
+_LRR_SCALE = 0.02 / (0.02 + 0.0525) * 30.72 + 0.02 / (0.02 + 0.0611) * -30.29
+
+
+@dataclass(frozen=True)
+class GarleanuPanageasLongRunRiskModel(RegisteredModel):
+    """examples/asset_pricing/garleanu_panageas_long_run_risk.jl:41-72 (the reference's only 3-D example: 8 unknowns
+    on an (x, mu, v) grid).  B1, B2 are the NORMALISED loadings the reference struct stores.  Solve its first stage
+    with Δ = {"pA": 100, "pB": 100, "phi1": 100, "phi2": 100, "r": -1, "kC": -1, "kM": -1, "kV": -1}, maxΔ = 3,
+    abstol = 1e-5 (:337-344)."""
+    gA: float = 1.5
+    psA: float = 0.7
+    gB: float = 10.0
+    psB: float = 0.05
+    rho: float = 0.001
+    delta: float = 0.02
+    nuA: float = 0.01
+    mubar: float = 0.018
+    vbar: float = 0.00073
+    kmu: float = 0.252
+    numu: float = 0.528
+    kv: float = 0.156
+    nuv: float = 0.00354
+    B1: float = 30.72 / _LRR_SCALE
+    d1: float = 0.0525
+    B2: float = -30.29 / _LRR_SCALE
+    d2: float = 0.0611
+    omega: float = 0.92
+    name: ClassVar[str] = "garleanu_panageas_lrr"
+    statenames: ClassVar = ("x", "mu", "v")
+    solnames: ClassVar = ("pA", "pB", "phi1", "phi2", "r", "kC", "kM", "kV")
+    savednames: ClassVar = ("kappa", "r_implied", "kC_implied", "kM_implied", "kV_implied", "r_gap", "kC_gap", "kM_gap",
+                            "kV_gap", "pA_residual", "pB_residual", "phi1_residual", "phi2_residual", "mux", "sigmax",
+                            "sigmaxC", "sigmaxM", "sigmaxV")
+
+
 @dataclass(frozen=True)
 class LelandModel(RegisteredModel):
     """examples/corporate_finance/leland.jl:22-28; solve with lower_bound = 0 and bc = {"Edelta": (0, 1/(r-mu))}."""
@@ -472,4 +507,4 @@ ALL_MODELS = (ReadmeLinear, CampbellCochraneModel, BansalYaronModel, AchdouHanLa
               AchdouHanLasryLionsMollModel_TwoStates, GarleanuPanageasModel, LelandModel,
               WangWangYangModel, LinearUpwindTest, HeKrishnamurthyModel, WachterModel, HaddadModel,
               BoltonChenWangModel, GomezModel, AchdouHanLasryLionsMollModel_RiskyAsset, PointwiseCubic,
-              AffinePair)
+              AffinePair, GarleanuPanageasLongRunRiskModel)

@@ -84,7 +84,8 @@ class SlabGroup:
         self.close()
 
 
-def pdesolve_slab(pde, grid, guess, group: SlabGroup, *, abstol=SQRT_EPS, maxiters=100, **kwargs) -> EconPDEResult:
+def pdesolve_slab(pde, grid, guess, group: SlabGroup, *, abstol=SQRT_EPS, maxiters=100, lower_bound=None,
+                  upper_bound=None, **kwargs) -> EconPDEResult:
     """`pdesolve` (src/pdesolve.jl:96-154) with the grid slab-decomposed over `group`.
 
     `grid` is the GLOBAL state grid; `guess` holds either global arrays (sliced here) or this
@@ -109,6 +110,19 @@ def pdesolve_slab(pde, grid, guess, group: SlabGroup, *, abstol=SQRT_EPS, maxite
     elif g0.shape != Sloc:
         raise ValueError(f"the initial guess has size {g0.shape}; expected the grid {S} or this rank's slab {Sloc}")
     guess_vec = np.ascontiguousarray(g0.reshape(-1, order="F"))
+
+    def bound(b, default):   # global array, this rank's slab, or a scalar -> this rank's slab, flattened
+        if b is None:
+            return None
+        a = np.asarray(b, dtype=np.float64)
+        if a.ndim == 0:
+            a = np.full(Sloc, float(a))
+        elif a.shape == S:
+            a = a[..., first:first + count]
+        elif a.shape != Sloc:
+            raise ValueError(f"a bound has size {a.shape}; expected the grid {S} or this rank's slab {Sloc}")
+        return np.ascontiguousarray(a.reshape(-1, order="F"))
+    lb_vec, ub_vec = bound(lower_bound, -np.inf), bound(upper_bound, np.inf)
     delta = kwargs.pop("Δ", kwargs.pop("delta", 1.0))
     opts = _options(abstol, maxiters, kwargs)
     opts.delta = float(delta)
@@ -125,6 +139,8 @@ def pdesolve_slab(pde, grid, guess, group: SlabGroup, *, abstol=SQRT_EPS, maxite
         p.grid[d] = L.dptr(grids[d])
     p.params = L.dptr(prm) if prm.shape[0] else None
     p.guess = L.dptr(guess_vec)
+    p.lower_bound = L.dptr(lb_vec)
+    p.upper_bound = L.dptr(ub_vec)
     sol = np.empty(guess_vec.shape[0])
     cap = max(int(maxiters), 1)
     log = (L.LogRow * cap)()

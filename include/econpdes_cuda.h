@@ -30,7 +30,7 @@ extern "C" {
 
 #define ECONPDES_ABI_VERSION 3
 #define ECONPDES_MAX_DIMS 3
-#define ECONPDES_MAX_FUNCS 4
+#define ECONPDES_MAX_FUNCS 8
 #define ECONPDES_MAX_PARAMS 16
 
 /* error codes */

@@ -568,6 +568,171 @@ def garleanu_panageas_problem(n=100, **over):
     return {"x": x}, {k: np.ones(n) for k in ("pA", "pB", "phi1", "phi2")}, prm
 
 
+def garleanu_panageas_lrr_params(gA=1.5, psA=0.7, gB=10.0, psB=0.05, rho=0.001, delta=0.02, nuA=0.01, mubar=0.018,
+                                 vbar=0.00073, kmu=0.252, numu=0.528, kv=0.156, nuv=0.00354, B1=30.72, d1=0.0525,
+                                 B2=-30.29, d2=0.0611, omega=0.92):
+    """Struct of examples/asset_pricing/garleanu_panageas_long_run_risk.jl:41-72; the constructor normalises B1, B2."""
+    scale = delta / (delta + d1) * B1 + delta / (delta + d2) * B2
+    return dict(gA=gA, psA=psA, gB=gB, psB=psB, rho=rho, delta=delta, nuA=nuA, mubar=mubar, vbar=vbar, kmu=kmu,
+                numu=numu, kv=kv, nuv=nuv, B1=B1 / scale, d1=d1, B2=B2 / scale, d2=d2, omega=omega)
+
+
+GP_LRR_UNKNOWNS = ("pA", "pB", "phi1", "phi2", "r", "kC", "kM", "kV")
+GP_LRR_SAVED = ("kappa", "r_implied", "kC_implied", "kM_implied", "kV_implied", "r_gap", "kC_gap", "kM_gap", "kV_gap",
+                "pA_residual", "pB_residual", "phi1_residual", "phi2_residual", "mux", "sigmax", "sigmaxC", "sigmaxM",
+                "sigmaxV")
+
+
+def garleanu_panageas_lrr(gA, psA, gB, psB, rho, delta, nuA, mubar, vbar, kmu, numu, kv, nuv, B1, d1, B2, d2, omega):
+    """examples/asset_pricing/garleanu_panageas_long_run_risk.jl:74-232: states (x, mu, v), unknowns pA, pB, phi1, phi2
+    (valuation ratios, backward equations) and r, kC, kM, kV (market-clearing prices, forward equations).  The
+    two-pass upwinding in x (`@goto start`, :117-165) is evaluated for both passes and selected pointwise."""
+    def pde(state, u):
+        x, mu, v = state["x"], state["mu"], state["v"]
+        pA, pB, f1, f2 = u["pA"], u["pB"], u["phi1"], u["phi2"]
+        r, kC, kM, kV = u["r"], u["kC"], u["kM"], u["kV"]
+        with np.errstate(all="ignore"):
+            sc = np.sqrt(v)
+            mumu = kmu * (mubar - mu)
+            smu = numu * np.sqrt(v)
+            muv = kv * (vbar - v)
+            sv = nuv * np.sqrt(v)
+            upm, upv = mumu >= 0, muv >= 0
+            pAmu = np.where(upm, u["pAmu_up"], u["pAmu_down"])
+            pBmu = np.where(upm, u["pBmu_up"], u["pBmu_down"])
+            f1mu = np.where(upm, u["phi1mu_up"], u["phi1mu_down"])
+            f2mu = np.where(upm, u["phi2mu_up"], u["phi2mu_down"])
+            pAv = np.where(upv, u["pAv_up"], u["pAv_down"])
+            pBv = np.where(upv, u["pBv_up"], u["pBv_down"])
+            f1v = np.where(upv, u["phi1v_up"], u["phi1v_down"])
+            f2v = np.where(upv, u["phi2v_up"], u["phi2v_down"])
+            G = 1 / (x / gA + (1 - x) / gB)
+            aA = (1 - gA * psA) / (gA * (psA - 1))
+            aB = (1 - gB * psB) / (gB * (psB - 1))
+            pAmu_pA, pBmu_pB = pAmu / pA, pBmu / pB
+            pAv_pA, pBv_pB = pAv / pA, pBv / pB
+            k2 = kC ** 2 + kM ** 2 + kV ** 2
+            human_capital = omega * (B1 * f1 + B2 * f2)
+
+            def block(pAx, pBx):
+                pAx_pA = pAx / pA
+                pBx_pB = pBx / pB
+                denom = 1 - x * aA * pAx_pA
+                sxC = x * (kC / gA - sc) / denom
+                sxM = x * (kM / gA + aA * pAmu_pA * smu) / denom
+                sxV = x * (kV / gA + aA * pAv_pA * sv) / denom
+                sx2 = sxC ** 2 + sxM ** 2 + sxV ** 2
+                spA_C = pAx_pA * sxC
+                spA_M = pAx_pA * sxM + pAmu_pA * smu
+                spA_V = pAx_pA * sxV + pAv_pA * sv
+                spB_C = pBx_pB * sxC
+                spB_M = pBx_pB * sxM + pBmu_pB * smu
+                spB_V = pBx_pB * sxV + pBv_pB * sv
+                sCA_C = kC / gA + aA * spA_C
+                sCA_M = kM / gA + aA * spA_M
+                sCA_V = kV / gA + aA * spA_V
+                sCB_C = kC / gB + aB * spB_C
+                sCB_M = kM / gB + aB * spB_M
+                sCB_V = kV / gB + aB * spB_V
+                spA2 = spA_C ** 2 + spA_M ** 2 + spA_V ** 2
+                spB2 = spB_C ** 2 + spB_M ** 2 + spB_V ** 2
+                kspA = kC * spA_C + kM * spA_M + kV * spA_V
+                kspB = kC * spB_C + kM * spB_M + kV * spB_V
+                mcA = (1 + psA) / (2 * gA) * k2 + aA * kspA - 0.5 * aA * spA2
+                mcB = (1 + psB) / (2 * gB) * k2 + aB * kspB - 0.5 * aB * spB2
+                muCA = psA * (r - rho) + mcA
+                muCB = psB * (r - rho) + mcB
+                mux = x * (muCA - mu) + delta * (nuA / pA * human_capital - x) - sc * sxC
+                return (pAx_pA, pBx_pB, sxC, sxM, sxV, sx2, spA_C, spA_M, spA_V, spB_C, spB_M, spB_V, sCA_C, sCA_M, sCA_V,
+                        sCB_C, sCB_M, sCB_V, mcA, mcB, muCA, muCB, mux)
+            first = block(u["pAx_up"], u["pBx_up"])
+            second = block(u["pAx_down"], u["pBx_down"])
+            redo = first[-1] <= 0
+            (pAx_pA, pBx_pB, sxC, sxM, sxV, sx2, spA_C, spA_M, spA_V, spB_C, spB_M, spB_V, sCA_C, sCA_M, sCA_V, sCB_C, sCB_M,
+             sCB_V, mcA, mcB, muCA, muCB, mux) = (np.where(redo, b2, b1) for b1, b2 in zip(first, second))
+            f1x = np.where(redo, u["phi1x_down"], u["phi1x_up"])
+            f2x = np.where(redo, u["phi2x_down"], u["phi2x_up"])
+            cm, cv = sxM * smu >= 0, sxV * sv >= 0
+            pAxmu = np.where(cm, u["pAxmu_up"], u["pAxmu_down"])
+            pBxmu = np.where(cm, u["pBxmu_up"], u["pBxmu_down"])
+            f1xmu = np.where(cm, u["phi1xmu_up"], u["phi1xmu_down"])
+            f2xmu = np.where(cm, u["phi2xmu_up"], u["phi2xmu_down"])
+            pAxv = np.where(cv, u["pAxv_up"], u["pAxv_down"])
+            pBxv = np.where(cv, u["pBxv_up"], u["pBxv_down"])
+            f1xv = np.where(cv, u["phi1xv_up"], u["phi1xv_down"])
+            f2xv = np.where(cv, u["phi2xv_up"], u["phi2xv_down"])
+            f1x_f1, f2x_f2 = f1x / f1, f2x / f2
+            f1mu_f1, f2mu_f2 = f1mu / f1, f2mu / f2
+            f1v_f1, f2v_f2 = f1v / f1, f2v / f2
+            sf1_C = f1x_f1 * sxC
+            sf1_M = f1x_f1 * sxM + f1mu_f1 * smu
+            sf1_V = f1x_f1 * sxV + f1v_f1 * sv
+            sf2_C = f2x_f2 * sxC
+            sf2_M = f2x_f2 * sxM + f2mu_f2 * smu
+            sf2_V = f2x_f2 * sxV + f2v_f2 * sv
+            mupA = (pAx_pA * mux + pAmu_pA * mumu + pAv_pA * muv + 0.5 * u["pAxx"] / pA * sx2 + 0.5 * u["pAmumu"] / pA * smu ** 2
+                    + 0.5 * u["pAvv"] / pA * sv ** 2 + pAxmu / pA * sxM * smu + pAxv / pA * sxV * sv)
+            mupB = (pBx_pB * mux + pBmu_pB * mumu + pBv_pB * muv + 0.5 * u["pBxx"] / pB * sx2 + 0.5 * u["pBmumu"] / pB * smu ** 2
+                    + 0.5 * u["pBvv"] / pB * sv ** 2 + pBxmu / pB * sxM * smu + pBxv / pB * sxV * sv)
+            muf1 = (f1x_f1 * mux + f1mu_f1 * mumu + f1v_f1 * muv + 0.5 * u["phi1xx"] / f1 * sx2
+                    + 0.5 * u["phi1mumu"] / f1 * smu ** 2 + 0.5 * u["phi1vv"] / f1 * sv ** 2 + f1xmu / f1 * sxM * smu
+                    + f1xv / f1 * sxV * sv)
+            muf2 = (f2x_f2 * mux + f2mu_f2 * mumu + f2v_f2 * muv + 0.5 * u["phi2xx"] / f2 * sx2
+                    + 0.5 * u["phi2mumu"] / f2 * smu ** 2 + 0.5 * u["phi2vv"] / f2 * sv ** 2 + f2xmu / f2 * sxM * smu
+                    + f2xv / f2 * sxV * sv)
+            sCAspA = sCA_C * spA_C + sCA_M * spA_M + sCA_V * spA_V
+            sCBspB = sCB_C * spB_C + sCB_M * spB_M + sCB_V * spB_V
+            kspA_CA = kC * (spA_C + sCA_C) + kM * (spA_M + sCA_M) + kV * (spA_V + sCA_V)
+            kspB_CB = kC * (spB_C + sCB_C) + kM * (spB_M + sCB_M) + kV * (spB_V + sCB_V)
+            pAt = -pA * (1 / pA + muCA + mupA + sCAspA - r - delta - kspA_CA)
+            pBt = -pB * (1 / pB + muCB + mupB + sCBspB - r - delta - kspB_CB)
+            ksf1_Y = kC * (sf1_C + sc) + kM * sf1_M + kV * sf1_V
+            ksf2_Y = kC * (sf2_C + sc) + kM * sf2_M + kV * sf2_V
+            f1t = -f1 * (1 / f1 + mu - delta - d1 + muf1 + sc * sf1_C - r - ksf1_Y)
+            f2t = -f2 * (1 / f2 + mu - delta - d2 + muf2 + sc * sf2_C - r - ksf2_Y)
+            kC_imp = G * (sc - x * aA * spA_C - (1 - x) * aB * spB_C)
+            kM_imp = G * (0.0 - x * aA * spA_M - (1 - x) * aB * spB_M)
+            kV_imp = G * (0.0 - x * aA * spA_V - (1 - x) * aB * spB_V)
+            r_imp = rho + (mu - x * mcA - (1 - x) * mcB - delta * ((nuA / pA + (1 - nuA) / pB) * human_capital - 1)) / (
+                psA * x + psB * (1 - x))
+            rt, kCt, kMt, kVt = r_imp - r, kC_imp - kC, kM_imp - kM, kV_imp - kV
+            z = 0.0 * x   # saved fields keep the grid shape even where the expression is a scalar
+        return ({"pAt": pAt, "pBt": pBt, "phi1t": f1t, "phi2t": f2t, "rt": rt, "kCt": kCt, "kMt": kMt, "kVt": kVt},
+                {"kappa": np.sqrt(k2), "r_implied": r_imp, "kC_implied": kC_imp, "kM_implied": kM_imp, "kV_implied": kV_imp,
+                 "r_gap": rt, "kC_gap": kCt, "kM_gap": kMt, "kV_gap": kVt, "pA_residual": pAt, "pB_residual": pBt,
+                 "phi1_residual": f1t, "phi2_residual": f2t, "mux": mux + z, "sigmax": np.sqrt(sx2), "sigmaxC": sxC,
+                 "sigmaxM": sxM, "sigmaxV": sxV})
+    return pde
+
+
+def garleanu_panageas_lrr_problem(xn=20, mun=5, vn=5, **over):
+    """Grid, guess and the signed pseudo-time steps of the example's first stage
+    (garleanu_panageas_long_run_risk.jl:235-276, 337-344): returns (grid, guess, params, delta_profile, options)."""
+    from scipy import stats
+    prm = garleanu_panageas_lrr_params(**over)
+    musd = math.sqrt(prm["numu"] ** 2 * prm["vbar"] / (2 * prm["kmu"]))
+    shape_v = 2 * prm["kv"] * prm["vbar"] / prm["nuv"] ** 2
+    scale_v = prm["nuv"] ** 2 / (2 * prm["kv"])
+    x = julia_range(0.0, 1.0, xn) ** 2
+    mus = julia_range(stats.norm.ppf(0.10, prm["mubar"], musd), stats.norm.ppf(0.90, prm["mubar"], musd), mun)
+    vs = julia_range(stats.gamma.ppf(0.10, shape_v, scale=scale_v), stats.gamma.ppf(0.90, shape_v, scale=scale_v), vn)
+    S = (xn, mun, vn)
+    X, MU, V = np.meshgrid(x, mus, vs, indexing="ij")
+    sc = np.sqrt(V)
+    Gam = 1 / (X / prm["gA"] + (1 - X) / prm["gB"])
+    kC = Gam * sc
+    k2 = kC ** 2
+    mcA = (1 + prm["psA"]) / (2 * prm["gA"]) * k2
+    mcB = (1 + prm["psB"]) / (2 * prm["gB"]) * k2
+    human_capital = prm["omega"] * (prm["B1"] + prm["B2"])
+    r = prm["rho"] + (MU - X * mcA - (1 - X) * mcB - prm["delta"] * (human_capital - 1)) / (
+        prm["psA"] * X + prm["psB"] * (1 - X))
+    guess = {"pA": np.ones(S), "pB": np.ones(S), "phi1": np.ones(S), "phi2": np.ones(S), "r": r, "kC": kC,
+             "kM": np.zeros(S), "kV": np.zeros(S)}
+    delta = {"pA": 100.0, "pB": 100.0, "phi1": 100.0, "phi2": 100.0, "r": -1.0, "kC": -1.0, "kM": -1.0, "kV": -1.0}
+    return {"x": x, "mu": mus, "v": vs}, guess, prm, delta, dict(maxΔ=3.0, abstol=1e-5, maxiters=100)
+
+
 def leland(r=0.02, mu=0.0, sigma=0.1, C=0.05, tau=0.2):
     """examples/corporate_finance/leland.jl:44-53 (equity value with the default option as a lower bound)."""
     def pde(state, u):

@@ -38,10 +38,17 @@ def cases():
     yield "ex_ahlm_two_states_200", M.ahlm_two_states(**prm), g, gu, prm, {}
     g, gu, prm = M.garleanu_panageas_problem()
     yield "ex_garleanu_panageas_100", M.garleanu_panageas(**prm), g, gu, prm, {}
+    # first stage of the 3-D long-run-risk example (garleanu_panageas_long_run_risk.jl:337-344), ~2 minutes of SuperLU
+    g, gu, prm, delta, opts = M.garleanu_panageas_lrr_problem()
+    yield ("ex_garleanu_panageas_lrr_20x5x5", M.garleanu_panageas_lrr(**prm), g, gu, prm,
+           dict(delta=delta, abstol=opts["abstol"], maxiters=opts["maxiters"], max_delta=opts["maxΔ"]))
 
 
 def main():
+    only = sys.argv[1:]
     for name, pde, g, gu, prm, kw in cases():
+        if only and name not in only:
+            continue
         res = eo.pdesolve(pde, g, gu, **kw)
         d = pack(res, g, gu, prm)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)

@@ -1034,3 +1034,31 @@ def test_single_1d_pdesolve_takes_the_fused_kernel():
     g, gu, prm, bc = OM.wang_wang_yang_problem(101)
     res = E.pdesolve(PM.WangWangYangModel(**prm), g, gu, bc=bc, verbose=False)
     assert res.kernel_launches > 3
+
+
+@pytest.mark.gpu
+def test_garleanu_panageas_long_run_risk_first_stage():
+    """examples/asset_pricing/garleanu_panageas_long_run_risk.jl -- the reference's only 3-D example: 8 unknowns on a
+    20 x 5 x 5 grid (216 Jacobian colors, 8 x 8 blocks), signed per-unknown pseudo-time steps (negative for the four
+    market-clearing prices), maxΔ = 3, abstol = 1e-5 (:337-344).  Against the oracle fixture: same accepted / rejected
+    sequence, same time steps, same Newton counts on the accepted steps, same values.  (The oracle's three rejected
+    steps pass through NLsolve's singular-Jacobian retry before giving up; the device gives such a step up at once --
+    rejected either way, so the step sequence is the same and only the printed reason may differ.)  The example's
+    second stage calls NonlinearSolve.TrustRegion, which is outside the :newton path."""
+    d = np.load(os.path.join(GOLD, "ex_garleanu_panageas_lrr_20x5x5.npz"))
+    g, gu, prm, delta, opts = OM.garleanu_panageas_lrr_problem()
+    for k in g:
+        np.testing.assert_array_equal(g[k], d["grid_" + k])
+    res = E.pdesolve(PM.GarleanuPanageasLongRunRiskModel(**prm), g, gu, Δ=delta, maxΔ=opts["maxΔ"], abstol=opts["abstol"],
+                     maxiters=opts["maxiters"], verbose=False)
+    log = d["log"]
+    assert res.converged == bool(d["converged"]) and res.converged
+    assert [r["status"] == 0 for r in res.log] == [int(s) == 0 for s in log[:, 3]]
+    np.testing.assert_allclose([r["delta"] for r in res.log], log[:, 1], rtol=1e-9)
+    acc = log[:, 3] == 0
+    assert [r["newton_iters"] for r in res.log if r["status"] == 0] == [int(n) for n in log[acc, 4]]
+    for k in gu:
+        np.testing.assert_allclose(res.solution[k], d["sol_" + k], rtol=1e-7, atol=1e-9, err_msg=k)
+    assert abs(res.residual_norm - float(d["residual_norm"])) <= 1e-10
+    for k in ("kappa", "r_implied", "mux", "sigmax"):
+        np.testing.assert_allclose(res.saved[k], d["saved_" + k], rtol=1e-6, atol=1e-8, err_msg=k)

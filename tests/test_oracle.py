@@ -324,9 +324,18 @@ def test_example_model_fixtures_are_what_the_oracle_produces():
     n = 0
     for name, pde, g, gu, prm, kw in G.cases():
         gold = np.load(os.path.join(G.HERE, name + ".npz"))
+        log = gold["log"]
+        if name == "ex_garleanu_panageas_lrr_20x5x5":
+            # two minutes of SuperLU for the whole first stage: re-run its first three outer steps only (one rejected
+            # through the singular-Jacobian retry, two accepted) and compare the log rows
+            res = eo.pdesolve(pde, g, gu, **dict(kw, maxiters=3))
+            assert [r[3] for r in res.log.rows] == [int(s) for s in log[:3, 3]]
+            assert [r[4] for r in res.log.rows] == [int(s) for s in log[:3, 4]]
+            np.testing.assert_allclose([r[2] for r in res.log.rows[1:]], log[1:3, 2], rtol=1e-9)
+            n += 1
+            continue
         res = eo.pdesolve(pde, g, gu, **kw)
         assert bool(gold["converged"]) == res.converged and res.converged, name
-        log = gold["log"]
         assert [int(s) for s in log[:, 3]] == [r[3] for r in res.log.rows], name
         assert [int(s) for s in log[:, 4]] == [r[4] for r in res.log.rows], name
         for k, v in res.solution.items():
@@ -335,7 +344,7 @@ def test_example_model_fixtures_are_what_the_oracle_produces():
             if k not in res.solution:
                 np.testing.assert_allclose(v, gold["saved_" + k], rtol=1e-7, atol=1e-9, err_msg=f"{name}.{k}")
         n += 1
-    assert n == 10
+    assert n == 11
 
 
 def test_example_models_economic_sanity():

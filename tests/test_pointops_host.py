@@ -40,6 +40,11 @@ def _cases():
     out.append(("regimes2d", PM.Hjb2dRegimes(**prm), OM.hjb2d_regimes(**prm), g, gu))
     g, gu, prm = OM.di_tella_problem(7, 6)
     out.append(("ditella", PM.DiTellaModel(**prm), OM.di_tella(**prm), g, gu))
+    g, gu, prm, _, _ = OM.garleanu_panageas_lrr_problem(7, 4, 5)
+    rng = np.random.default_rng(11)
+    gu = {k: v + (0.05 * rng.uniform(-1, 1, v.shape) if k in ("pA", "pB", "phi1", "phi2") else 0.002 * rng.uniform(-1, 1, v.shape))
+          for k, v in gu.items()}
+    out.append(("gp_lrr", PM.GarleanuPanageasLongRunRiskModel(**prm), OM.garleanu_panageas_lrr(**prm), g, gu))
     g, gu, prm = OM.ahlm_two_states_problem(60)
     out.append(("twoincome", PM.AchdouHanLasryLionsMollModel_TwoStates(**prm), OM.ahlm_two_states(**prm), g, gu))
     g, gu, prm = OM.garleanu_panageas_problem(40)
@@ -184,7 +189,7 @@ def test_fused_jacobian_matches_colored_fd(case, delta):
         with np.errstate(all="ignore"):
             return prob.G(v) - (ypvec - v) / delta
     nz_want, eps = eo.finite_difference_jacobian(R, yvec, cache)
-    box = name in ("hjb3d", "regimes2d", "ditella")
+    box = name in ("hjb3d", "regimes2d", "ditella", "gp_lrr")
     planes, r0 = EU.jacobian_planes(pm, grids, y, ypost, delta, eps, box)
     if name in POW_MODELS:
         np.testing.assert_allclose(r0, R(yvec), rtol=0, atol=8 * np.finfo(float).eps * np.abs(r0).max())

@@ -22,6 +22,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _problem(name):
+    if name in ("golden24", "golden24_bound"):   # the oracle fixture's own grid and guess
+        d = np.load(os.path.join(ROOT, "tests", "golden", "c5_hjb3d_24.npz"))
+        return (PM.Hjb3dSynth(*d["params"]), {"x": d["grid_x"], "y": d["grid_y"], "z": d["grid_z"]}, {"v": d["guess_v"]})
     if name == "hjb3d":
         g, gu = EX.hjb3d_grid(40)
         return PM.Hjb3dSynth(), g, gu
@@ -42,7 +45,14 @@ def _worker(rank, world, idq, outq, name, replicate_below):
     uid = idq.get(timeout=120)
     grp = E2.SlabGroup(rank, world, uid)
     model, g, gu = _problem(name)
-    res = E2.pdesolve_slab(model, g, gu, grp)
+    kw = {}
+    if name == "golden24_bound":
+        # a (never binding) lower bound that is finite on the LAST rank's planes only: every rank must still take the
+        # MCP residual and the masked norm, whose collectives all ranks have to call (the flag was local)
+        lb = np.full(gu["v"].shape, -np.inf)
+        lb[..., -3:] = -1e6
+        kw["lower_bound"] = lb
+    res = E2.pdesolve_slab(model, g, gu, grp, **kw)
     key = next(iter(res.solution))
     outq.put((rank, res.slab, res.solution[key], res.residual_norm, res.converged,
               [(r["status"], r["newton_iters"]) for r in res.log], grp.collectives))
@@ -84,3 +94,36 @@ def test_two_gpu_slab_matches_single_gpu(name, replicate_below):
         assert o[4] == ref.converged
         assert o[5] == [(r["status"], r["newton_iters"]) for r in ref.log]
         assert o[6] > 0                                          # NCCL traffic actually happened
+
+
+@pytest.mark.parametrize("name", ["golden24", "golden24_bound"])
+def test_two_gpu_slab_matches_the_oracle_fixture(name):
+    """The 2-GPU slab solve against the ORACLE fixture c5_hjb3d_24.npz (not only against the 1-GPU solve): values
+    1e-8 relative, residual norm 1e-10, same accept sequence and Newton counts.  `golden24_bound` adds a lower bound
+    that is finite on one rank's slab only and never binds: same solution, and the ranks must not dead-lock."""
+    if L.load().econpdes_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    world = 2
+    idqs = [ctx.Queue() for _ in range(world)]
+    outq = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, idqs[r], outq, name, 0)) for r in range(world)]
+    for p in procs:
+        p.start()
+    uid = E.slab.new_unique_id()
+    for q in idqs:
+        q.put(uid)
+    outs = sorted([outq.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    d = np.load(os.path.join(ROOT, "tests", "golden", "c5_hjb3d_24.npz"))
+    full = np.concatenate([o[2] for o in outs], axis=-1)
+    np.testing.assert_allclose(full, d["sol_v"], rtol=1e-8)
+    for o in outs:
+        assert o[4] == bool(d["converged"])
+        assert [s for s, _ in o[5]] == [int(r[3]) for r in d["log"]]
+        assert [n for _, n in o[5]] == [int(r[4]) for r in d["log"]]
+        if name == "golden24":
+            assert abs(o[3] - float(d["residual_norm"])) <= 1e-10
