@@ -10,5 +10,5 @@ include/econpdes_cuda.h); this package is the thin host mirror of the reference'
 from . import models  # noqa: F401
 from ._lib import EconPDEsCudaError, LIB_PATH  # noqa: F401
 from .pdesolve import (BatchResult, EconPDEResult, Handle, pdesolve, pdesolve_batched,  # noqa: F401
-                       set_batch_points_per_thread, solve_batched_one_call, solve_batched_compact, stencil_colors, stencil_pattern)
+                       set_batch_points_per_thread, last_batched_output_mode, solve_batched_one_call, solve_batched_compact, stencil_colors, stencil_pattern)
 from .slab import SlabGroup, pdesolve_slab, slab_range  # noqa: F401

@@ -105,6 +105,7 @@ SYMBOLS = {
                                                 C.POINTER(Options), c_double_p, c_double_p, c_int32_p, c_int32_p,
                                                 c_int32_p]),
     "econpdes_release_workspace": (None, []),
+    "econpdes_last_batched_output_mode": (C.c_int, []),
     "econpdes_set_batch_points_per_thread": (C.c_int, [C.c_int]),
     "econpdes_selftest_reciprocal": (C.c_int, [C.c_uint64, C.c_int64, C.POINTER(C.c_int64)]),
     "econpdes_device_count": (C.c_int, []),

@@ -101,6 +101,7 @@ struct econpdes_batch {
   cudaStream_t pipe[kPipe] = {};   // copy/compute pipeline of the one-call path (econpdes_solve_batched)
   // pinned staging for the per-problem scalars (error, exit reason, counts, residual norm): a pageable
   // target would make every slice's read-back block the host and serialise the pipeline
+  bool last_direct = false;        // the last one-call solve stored its results straight into pinned host memory
   int* err_host = nullptr;         // [4][B]: error, exit_reason, n_outer, n_newton
   double* rn_host = nullptr;       // [B]
   DevBuf<double> params, grids, guess, solution, residual_norm;
@@ -369,8 +370,16 @@ int econpdes_solve(econpdes_handle* h, const econpdes_options* options, econpdes
 // src/monotonicity.jl and the saved outputs follow as one small launch each.  ECONPDES_FUSED_1D=0 keeps such
 // problems on the generic engine.
 static thread_local econpdes_batch* t_single = nullptr;
+// Where a launch writes its results when that is not the batch's own device buffers: device-visible aliases of
+// pinned HOST memory (the one-call path's zero-copy mode).  Indexed by problem like the device buffers.
+struct BatchOut {
+  double* solution = nullptr;
+  double* residual_norm = nullptr;
+  int* ints = nullptr;   // [4][B]: error, exit_reason, n_outer, n_newton
+};
+
 static int batch_launch(econpdes_batch* b, const econpdes_options* options, int log_capacity, long long first,
-                        long long last, cudaStream_t s);
+                        long long last, cudaStream_t s, const BatchOut* out = nullptr);
 
 static bool solve_fused_1d(const econpdes_problem* p, const econpdes_options* opt, econpdes_result* res, int* rc_out) {
   static const bool enabled = [] { const char* e = std::getenv("ECONPDES_FUSED_1D"); return !(e && e[0] == '0'); }();
@@ -672,7 +681,7 @@ int econpdes_batch_upload_inputs(econpdes_batch* b, const econpdes_batch_inputs*
 
 // launches the problems [first, last) on stream s (the whole batch on the batch's own stream by default)
 static int batch_launch(econpdes_batch* b, const econpdes_options* options, int log_capacity, long long first,
-                        long long last, cudaStream_t s) {
+                        long long last, cudaStream_t s, const BatchOut* out) {
   if (std::isnan(options->delta) || options->delta == 0.0)
     throw std::invalid_argument("`Δ` entries must be nonzero and not NaN (use `Inf` for no damping, a negative entry for forward relaxation)");
   BatchArgs a;
@@ -698,6 +707,17 @@ static int batch_launch(econpdes_batch* b, const econpdes_options* options, int 
   a.log_capacity = b->log_capacity;
   a.log_len = b->log_len.p;
   a.opt = *options;
+  if (out != nullptr) {
+    const size_t nB = static_cast<size_t>(b->B);
+    if (out->solution) a.solution = out->solution;
+    if (out->residual_norm) a.residual_norm = out->residual_norm;
+    if (out->ints) {
+      a.error = out->ints;
+      a.exit_reason = out->ints + nB;
+      a.n_outer = out->ints + 2 * nB;
+      a.n_newton = out->ints + 3 * nB;
+    }
+  }
   const int64_t l0 = g_kernel_launches.load();
   if (!b->explicit_grids || !b->explicit_guess) {   // compact inputs: build this slice's grids / guesses on the device
     const long long cnt = (a.nproblems - a.problem0) * b->S;
@@ -797,6 +817,8 @@ int econpdes_set_batch_points_per_thread(int points) {
   return g_batch_points_per_thread.exchange(points);
 }
 
+int econpdes_last_batched_output_mode(void) { return t_workspace ? (t_workspace->last_direct ? 1 : 0) : -1; }
+
 void econpdes_release_workspace(void) {
   delete t_workspace;
   t_workspace = nullptr;
@@ -843,11 +865,49 @@ int econpdes_solve_batched_inputs(int model_id, int64_t nproblems, int64_t npoin
     const size_t S = static_cast<size_t>(b->S);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    // Zero-copy results: when the caller's solution buffer is pinned (page-locked and mapped into the device's
+    // address space, which cudaHostAlloc / cudaHostRegister memory is under unified addressing), every block stores
+    // its solution straight into it over PCIe as it finishes, and the per-problem scalars go to the library's own
+    // pinned arrays the same way: the writes of one block overlap the arithmetic of the others, there is no
+    // device->host copy to queue or to drain, and a slice costs two or three small uploads and two launches.
+    // Pageable buffers (and ECONPDES_DIRECT_OUTPUT=0) take the staged path: device buffers + copies per slice.
+    static const bool direct_allowed = [] {
+      const char* e = std::getenv("ECONPDES_DIRECT_OUTPUT");
+      return !(e && e[0] == '0');
+    }();
+    BatchOut direct;
+    bool use_direct = false;
+    if (direct_allowed && solution != nullptr) {
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, solution) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+          at.devicePointer != nullptr) {
+        direct.solution = static_cast<double*>(at.devicePointer);
+        use_direct = true;
+      } else {
+        cudaGetLastError();
+      }
+    }
+    b->last_direct = use_direct;
     // Slice sizes in whole waves (one block per SM): short slices at both ends so the pipeline fills and
     // drains quickly (the first kernel waits for one small upload, the last download is small), long ones
     // in the middle (at most a sixth of the batch) where copies hide behind the kernels.
     std::vector<long long> bounds{0};
-    {
+    // bytes a problem uploads; with zero-copy results and light inputs (compact grids: ~0.85 KB per problem, 30x
+    // faster to upload than to solve) three or four slices growing by 4x hide every upload but the first
+    size_t up_bytes = static_cast<size_t>(b->nparams) * sizeof(double);
+    up_bytes += b->explicit_grids ? S * sizeof(double) : (S - static_cast<size_t>(b->n_range) + 1) * sizeof(double);
+    if (b->explicit_guess) up_bytes += S * sizeof(double);
+    if (use_direct && up_bytes <= 2048) {
+      const long long waves = (B + sms - 1) / sms;
+      long long left = waves, w = 2;
+      while (left > 0) {
+        const long long take = (w < left && left - w >= 2) ? w : left;
+        const long long nxt = bounds.back() + take * sms;
+        bounds.push_back(nxt < B ? nxt : B);
+        left -= take;
+        w *= 4;
+      }
+    } else {
       const long long waves = (B + sms - 1) / sms;
       const long long cap = waves / 6 > 2 ? waves / 6 : 2;
       std::vector<long long> sizes, back;
@@ -877,6 +937,13 @@ int econpdes_solve_batched_inputs(int model_id, int64_t nproblems, int64_t npoin
     const size_t nB = static_cast<size_t>(B);
     b->log_capacity = 0;
     int* err = b->err_host;
+    if (use_direct) {
+      void* dp = nullptr;
+      EP_CUDA(cudaHostGetDevicePointer(&dp, b->err_host, 0));
+      direct.ints = static_cast<int*>(dp);
+      EP_CUDA(cudaHostGetDevicePointer(&dp, b->rn_host, 0));
+      direct.residual_norm = static_cast<double*>(dp);
+    }
     // if queuing fails half-way, copies into the caller's buffers may still be in flight: drain the
     // streams before the error leaves this call
     struct Drain {
@@ -893,7 +960,8 @@ int econpdes_solve_batched_inputs(int model_id, int64_t nproblems, int64_t npoin
       const size_t n = static_cast<size_t>(last - first), o = static_cast<size_t>(first);
       cudaStream_t s = b->pipe[c % econpdes_batch::kPipe];
       batch_upload_slice(b, in, first, last, s);
-      batch_launch(b, options, 0, first, last, s);
+      batch_launch(b, options, 0, first, last, s, use_direct ? &direct : nullptr);
+      if (use_direct) continue;   // the kernel has the host addresses: nothing to copy back
       // error, exit_reason, n_outer, n_newton of the slice: four rows of one pitched copy
       EP_CUDA(cudaMemcpy2DAsync(err + o, nB * sizeof(int), b->ints.p + o, nB * sizeof(int), n * sizeof(int), 4,
                                 cudaMemcpyDeviceToHost, s));

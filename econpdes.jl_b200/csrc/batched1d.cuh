@@ -11,8 +11,11 @@
 // redundantly by every thread from block-reduced norms, so control flow is block-uniform.
 // HBM traffic is the grid + guess in and the solution out; nothing else leaves the SM.
 #pragma once
+#include <type_traits>
+
 #include "../../include/econpdes_cuda.h"
 #include "kernels.cuh"
+#include "sweep.cuh"
 #include "tridiag.cuh"
 
 namespace econpdes {
@@ -157,6 +160,13 @@ __global__ void __launch_bounds__(1024) k_diag_1d(int S, ParamPack prmpack, cons
   }
 }
 
+// 2^-200 <= |v| < 2^200 (and neither Inf nor NaN): the "tame geometry" rule of sweep.cuh / engine.cu, on the
+// exponent field
+__device__ __forceinline__ bool moderate_magnitude(double v) {
+  const int ex = (__double2hiint(v) >> 20) & 0x7ff;
+  return ex >= 1023 - 200 && ex < 1023 + 200;
+}
+
 // threads of a block that covers the engine's maximum of 1024 points with P points each (whole warps)
 constexpr int batched_max_threads(int P) { return ((1024 + P - 1) / P + 31) / 32 * 32; }
 
@@ -215,10 +225,26 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
     ypost[j] = ysh[i0 + j + 1];
   }
   const double bl[1][1] = {{0.0}}, bh[1][1] = {{0.0}};
-  __syncthreads();   // the grid staging area is free again
+  // "Tame" problems take the stencil quotients without their NaN-select (mdiv_tame, stencil.cuh; a quarter of the
+  // kernel's instructions were those selects): the spacings and their reciprocals must be finite and of moderate
+  // magnitude -- checked here, once per problem -- and every unknown below 2^199 -- checked with the other
+  // predicates of each Newton iterate (kUntame below).  The boundary derivative values of this engine are zero, so
+  // the tame form is TAME = 2.  Same bits either way; a block that meets an untame iterate re-evaluates it with the
+  // general form and stays on it while the iterate is wild.
+  bool geom_ok = true;
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const bool ok = moderate_magnitude(g[j].dm[0]) && moderate_magnitude(g[j].dp[0]) && moderate_magnitude(g[j].d[0]) &&
+                    moderate_magnitude(g[j].rdp[0]) && moderate_magnitude(g[j].rdm[0]) &&
+                    moderate_magnitude(g[j].rdpd[0]) && moderate_magnitude(g[j].rdmd[0]) &&
+                    moderate_magnitude(g[j].rdpm[0]);
+    if (act[j] && !ok) geom_ok = false;
+  }
+  const bool geom_tame = __syncthreads_and(geom_ok) != 0;   // also: the grid staging area is free again
 
   // residual G at this thread's points from the y currently published in ysh
-  auto evalG = [&](double* G) {
+  auto evalG = [&](double* G, auto tame_tag) {
+    constexpr int TAME = decltype(tame_tag)::value;
     double yv[P + 2];
 #pragma unroll
     for (int k = 0; k < P + 2; ++k) yv[k] = ysh[i0 + k];
@@ -226,10 +252,12 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
     for (int j = 0; j < P; ++j) {
       const double w[1][3] = {{yv[j], yv[j + 1], yv[j + 2]}};
       double o[1];
-      eval_point<M, false>(pre[j], g[j], w, bl, bh, o, nullptr);
+      eval_point<M, false, TAME>(pre[j], g[j], w, bl, bh, o, nullptr);
       G[j] = act[j] ? o[0] : 0.0;
     }
   };
+  using General = std::integral_constant<int, 0>;
+  using Tame = std::integral_constant<int, 2>;
   auto publish = [&](const double* v) {
     __syncthreads();  // everyone finished reading the previous y
 #pragma unroll
@@ -238,7 +266,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
   };
 
   double Gpost[P];
-  evalG(Gpost);
+  evalG(Gpost, General{});   // once per problem: the guess has not been vetted yet
   const double nd = static_cast<double>(S);
 
   // ||G||_2 / n with NaN -> NaN, as norm(ydot) / length(ydot) (:371, :415)
@@ -297,7 +325,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
     // NLsolve's loop only tests predicates of the residual (||R||_inf <= ftol, any NaN,
     // x == xold) -- folded block-wide as bits -- plus, for the Jacobian, FiniteDiff's three
     // masked sums of squares of the current iterate.  ||R||_2 is only needed once, at the end.
-    enum : unsigned { kNaN = 1u, kBig = 2u, kMoved = 4u, kBad = 8u };
+    enum : unsigned { kNaN = 1u, kBig = 2u, kMoved = 4u, kBad = 8u, kUntame = 16u };
     auto state_bits = [&](unsigned extra) -> unsigned {
       unsigned bb = extra;
 #pragma unroll
@@ -305,6 +333,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
         if (act[j]) {
           if (R[j] != R[j] || y[j] != y[j]) bb |= kNaN;
           if (!(fabs(R[j]) <= ftol)) bb |= kBig;
+          if (!is_tame(y[j])) bb |= kUntame;
         }
       }
       return block_or_bits(bb);
@@ -316,7 +345,10 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
     bool singular = false;
     const int c0 = i0 % 3;   // color of point j is (c0 + j) % 3
     // y is already published in ysh by the caller when y == ypost
-    while (!anynan && !fconv && !xconv && newton_it < maxit) {
+    bool tame = geom_tame && (bits & kUntame) == 0u;
+    // one Newton iteration; returns false when the linear solve broke down
+    auto iterate = [&](auto tame_tag) -> bool {
+      constexpr int TAME = decltype(tame_tag)::value;
       ++newton_it;
       double s3[3] = {0.0, 0.0, 0.0}, m0[1];
 #pragma unroll
@@ -355,7 +387,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
           double w[1][3] = {{yv[j], yv[j + 1], yv[j + 2]}};
           double r0[1] = {R[j]};
           double va = 0.0, vb = 1.0, vc = 0.0;
-          jacobian_point<M, false, true, PER_COL ? 1 : 0>(pre[j], g[j], idx[j], gv, w, bl, bh, &rt[j], eps_table, PER_COL,
+          jacobian_point<M, false, true, PER_COL ? 1 : 0, TAME>(pre[j], g[j], idx[j], gv, w, bl, bh, &rt[j], eps_table, PER_COL,
                                                           r0, [&](int k, int, int, double v) {
                                                             if (k == 0) vb = v; else if (k == 1) va = v; else vc = v;
                                                           }, reps_table);
@@ -373,14 +405,26 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
         if (act[j] && y[j] != xold) extra |= kMoved;
       }
       publish(y);
-      evalG(Gy);
+      evalG(Gy, tame_tag);
 #pragma unroll
       for (int j = 0; j < P; ++j) R[j] = act[j] ? apply_row_terms(Gy[j], y[j], rt[j]) : 0.0;
       bits = state_bits(extra);
-      if (bits & kBad) { singular = true; break; }   // a vanishing pivot: SingularException
+      if (TAME != 0 && (bits & kUntame) != 0u) {     // the new iterate is wild: its residual again, general form
+        evalG(Gy, General{});
+#pragma unroll
+        for (int j = 0; j < P; ++j) R[j] = act[j] ? apply_row_terms(Gy[j], y[j], rt[j]) : 0.0;
+        bits = state_bits(extra);
+      }
+      tame = geom_tame && (bits & kUntame) == 0u;
+      if (bits & kBad) return false;                 // a vanishing pivot: SingularException
       anynan = (bits & kNaN) != 0u;
       fconv = !anynan && (bits & kBig) == 0u;
       xconv = !anynan && (bits & kMoved) == 0u;      // chebyshev(x, xold) <= xtol = 0
+      return true;
+    };
+    while (!anynan && !fconv && !xconv && newton_it < maxit) {
+      const bool ok = tame ? iterate(Tame{}) : iterate(General{});
+      if (!ok) { singular = true; break; }
     }
     if (singular) {   // -> (y0, Inf), finiteschemesolve.jl:142-146
 #pragma unroll

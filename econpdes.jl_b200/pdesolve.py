@@ -526,16 +526,23 @@ def pdesolve_batched(model_cls, params: np.ndarray, grids: np.ndarray, guess: np
     return BatchResult(sol, rn, rn <= abstol, er, no, nn, ms.value, launches, logs)
 
 
+def last_batched_output_mode() -> int:
+    """1: this thread's last one-call batched solve wrote its results straight into page-locked host memory
+    (zero-copy); 0: it staged them through device buffers and copies; -1: there was none."""
+    return int(L.load().econpdes_last_batched_output_mode())
+
+
 def set_batch_points_per_thread(points: int) -> int:
     """Tuning knob of the batched engine (grid points owned by one thread; 0 = automatic).
     Returns the previous setting."""
     return L.check(L.load().econpdes_set_batch_points_per_thread(int(points)))
 
 
-def solve_batched_one_call(model_cls, params, grids, guess, *, abstol=SQRT_EPS, maxiters=100, **kwargs):
+def solve_batched_one_call(model_cls, params, grids, guess, *, abstol=SQRT_EPS, maxiters=100, out=None, **kwargs):
     """`econpdes_solve_batched`: upload, solve and download in one C call that pipelines slices of
-    the batch over three streams (use pinned host arrays to get the overlap).  Returns
-    (solution, residual_norm, exit_reason, n_outer, n_newton)."""
+    the batch over three streams.  `out` = optional preallocated (solution, residual_norm, exit_reason, n_outer,
+    n_newton) arrays: with a page-locked `solution` the kernel stores its results straight into it (zero-copy,
+    `last_batched_output_mode() == 1`).  Returns (solution, residual_norm, exit_reason, n_outer, n_newton)."""
     lib = L.load()
     delta = kwargs.pop("Δ", kwargs.pop("delta", 1.0))
     opts = _options(abstol, maxiters, kwargs)
@@ -549,11 +556,10 @@ def solve_batched_one_call(model_cls, params, grids, guess, *, abstol=SQRT_EPS, 
     if guess.shape != (B, S):
         raise ValueError(f"guess has shape {guess.shape}, expected {(B, S)}")
     mid = L.check(lib.econpdes_model_id(model_cls.name.encode()))
-    sol = np.empty((B, S))
-    rn = np.empty(B)
-    er = np.empty(B, dtype=np.int32)
-    no = np.empty(B, dtype=np.int32)
-    nn = np.empty(B, dtype=np.int32)
+    if out is None:
+        out = (np.empty((B, S)), np.empty(B), np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32),
+               np.empty(B, dtype=np.int32))
+    sol, rn, er, no, nn = out
     L.check(lib.econpdes_solve_batched(mid, B, S, L.dptr(params) if params.size else None, L.dptr(grids),
                                        L.dptr(guess), C.byref(opts), L.dptr(sol), L.dptr(rn),
                                        er.ctypes.data_as(L.c_int32_p), no.ctypes.data_as(L.c_int32_p),

@@ -239,10 +239,14 @@ int econpdes_batch_download(econpdes_batch* b, double* solution, double* residua
                             int32_t* log_len);
 int64_t econpdes_batch_kernel_launches(const econpdes_batch* b);
 /* upload + solve + download in one call (the end-to-end path a pdesolve loop replaces).  The batch is cut
- * into up to 8 slices whose host->device copies, solves and device->host copies are pipelined over three
- * streams.  The copies of `grids`, `guess` and `solution` overlap only when those buffers are page-locked
- * (cudaHostAlloc / cudaHostRegister / torch pin_memory); pageable buffers give the same results, serially.
- * The per-problem scalars are staged through the library's own page-locked memory. */
+ * into slices whose host->device copies and solves are pipelined over three streams.
+ * `solution` page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory): ZERO-COPY results -- every
+ * thread block stores its solution straight into the caller's buffer over PCIe as it finishes and the
+ * per-problem scalars into the library's own page-locked arrays, so there is no device->host copy at all.
+ * `solution` pageable (or ECONPDES_DIRECT_OUTPUT=0): device buffers + one device->host copy per slice, which
+ * overlap the solves only for page-locked buffers.  Same results either way.
+ * econpdes_last_batched_output_mode(): 1 if this host thread's last one-call solve was zero-copy, 0 if staged,
+ * -1 if there was none. */
 int econpdes_solve_batched(int model_id, int64_t nproblems, int64_t npoints, const double* params,
                            const double* grids, const double* guess, const econpdes_options* options,
                            double* solution, double* residual_norm, int32_t* exit_reason, int32_t* n_outer,
@@ -267,6 +271,8 @@ typedef struct econpdes_batch_inputs {
   const double* guess;     /* [B][S] or NULL */
   double guess_fill;
 } econpdes_batch_inputs;
+int econpdes_last_batched_output_mode(void);
+
 /* econpdes_batch_upload / econpdes_solve_batched with compact inputs */
 int econpdes_batch_upload_inputs(econpdes_batch* b, const econpdes_batch_inputs* inputs);
 int econpdes_solve_batched_inputs(int model_id, int64_t nproblems, int64_t npoints, const econpdes_batch_inputs* inputs,

@@ -47,6 +47,7 @@ from __future__ import annotations
 
 import itertools
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -650,6 +651,8 @@ def finiteschemesolve(G, y0, cache: JacobianCache, *, is_algebraic=None, lower_b
             r = residual_norm(ydot)
         r = math.inf if math.isnan(r) else r
         log.n_newton += info.newton_iters
+        if os.environ.get("ORACLE_PROGRESS"):                            # long fixture runs: one line per outer step
+            print("oracle step", it, stepper.delta, r, nl, info.newton_iters, flush=True)
         if nl <= inner_abstol and r <= max_residual_growth * old:       # :418
             log.rows.append((it, stepper.delta, r, ACCEPTED, info.newton_iters))
             stepper.accept_step(old, r)

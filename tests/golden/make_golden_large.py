@@ -32,3 +32,14 @@ if "c5" in which:
     res = eo.pdesolve(M.hjb3d_synth(**prm), g, gu)
     np.savez_compressed(os.path.join(HERE, "c5_hjb3d_24.npz"), **pack(res, g, gu, prm))
     print("c5", res.converged, res.residual_norm, res.log.n_outer, res.log.n_newton, time.time() - t, flush=True)
+for n in (512, 1024):
+    # C3 at 512^2 (minutes) and 1024^2 (hours of SuperLU; `python make_golden_large.py c3_1024`): the full-size fields
+    # would be 2 / 8 MB each, so the fixture keeps the iteration log, the residual norm and every 8th point per dimension
+    if "c3_%d" % n in which:
+        t = time.time()
+        g, gu, prm = M.bansal_yaron_problem(n, n)
+        res = eo.pdesolve(M.bansal_yaron(**prm), g, gu)
+        d = {k: v for k, v in pack(res, g, gu, prm).items() if not (k.startswith("guess_") or k.startswith("saved_") or k.startswith("sol_"))}
+        d["sol_p_every8"] = res.solution["p"][::8, ::8].copy()
+        np.savez_compressed(os.path.join(HERE, "c3_bansal_yaron_%d.npz" % n), **d)
+        print("c3_%d" % n, res.converged, res.residual_norm, res.log.n_outer, res.log.n_newton, time.time() - t, flush=True)

@@ -472,6 +472,78 @@ def test_one_call_pipelined_path_matches_handle_path():
         E.solve_batched_one_call(PM.CampbellCochraneModel, Pm, G, U)
 
 
+def test_one_call_zero_copy_results_into_page_locked_memory():
+    """With a page-locked `solution` buffer the kernel stores its results straight into host memory (no device->host
+    copy): same bits as the staged path and as the handle path, for explicit and compact inputs, a ragged last
+    slice, and the NaN-guess error; pageable buffers report the staged mode."""
+    torch = pytest.importorskip("torch")
+    from econpdes_b200 import examples as EX
+    prms, params, grids, guess = _sweep(4)
+
+    def pinned_out(B, S):
+        ts = (torch.empty((B, S), dtype=torch.float64, pin_memory=True), torch.empty(B, dtype=torch.float64, pin_memory=True))
+        return ts, (ts[0].numpy(), ts[1].numpy(), np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32),
+                    np.empty(B, dtype=np.int32))
+
+    for B in (3, 2 * 148 + 37, 11 * 148 + 5):
+        reps = (B + 3) // 4
+        Pm, G, U = np.tile(params, (reps, 1))[:B], np.tile(grids, (reps, 1))[:B], np.tile(guess, (reps, 1))[:B]
+        ref = E.pdesolve_batched(PM.CampbellCochraneModel, Pm, G, U)
+        keep, out = pinned_out(B, G.shape[1])
+        out[0][...] = -7.0
+        sol, rn, er, no, nn = E.solve_batched_one_call(PM.CampbellCochraneModel, Pm, G, U, out=out)
+        assert E.last_batched_output_mode() == 1
+        np.testing.assert_array_equal(sol, ref.solution)
+        np.testing.assert_array_equal(rn, ref.residual_norm)
+        np.testing.assert_array_equal(er, ref.exit_reason)
+        np.testing.assert_array_equal(no, ref.n_outer)
+        np.testing.assert_array_equal(nn, ref.n_newton)
+        sol2, *_ = E.solve_batched_one_call(PM.CampbellCochraneModel, Pm, G, U)
+        assert E.last_batched_output_mode() == 0
+        np.testing.assert_array_equal(sol2, ref.solution)
+    # compact inputs (device-built grids), zero-copy results
+    B = 5 * 148 + 3
+    p2, lo, pts, n_range, fill = EX.campbell_cochrane_sweep_compact(0, B)
+    _, Gx, Ux = EX.campbell_cochrane_sweep(0, B)
+    ref = E.pdesolve_batched(PM.CampbellCochraneModel, p2, Gx, Ux)
+    keep, out = pinned_out(B, Gx.shape[1])
+    sol, rn, er, no, nn = E.solve_batched_compact(PM.CampbellCochraneModel, p2, lo, pts, n_range, fill, out=out)
+    assert E.last_batched_output_mode() == 1
+    np.testing.assert_array_equal(sol, ref.solution)
+    np.testing.assert_array_equal(nn, ref.n_newton)
+    # the NaN-guess error is read from the page-locked scalars the kernel wrote
+    U = np.tile(guess, (reps, 1))[:B].copy()
+    G = np.tile(grids, (reps, 1))[:B]
+    Pm = np.tile(params, (reps, 1))[:B]
+    U[B - 5, 10] = np.nan
+    with pytest.raises(E.EconPDEsCudaError, match="NaN with the initial value"):
+        E.solve_batched_one_call(PM.CampbellCochraneModel, Pm, G, U, out=out)
+
+
+def test_batched_untame_problems_take_the_general_quotients():
+    """The fused kernel drops the NaN-select of its stencil quotients while the grid reciprocals are of moderate
+    magnitude and every unknown is below 2^199; otherwise the block evaluates with the general quotients.
+    Problem 0: a guess of 1e61 (the colored FD step vanishes against it: every step is rejected with a singular
+    Jacobian, in the oracle too).  Problem 1: grid spacings of 1e-67 (reciprocals beyond 2^200), four accepted steps.
+    Problem 2: an ordinary problem in the same launch."""
+    S = 60
+    x = OM.julia_range(0.0, 1.0, S)
+    xs = [x, x * 1e-65, x]
+    gs = [np.full(S, 1e61), np.ones(S), np.zeros(S)]
+    out = E.pdesolve_batched(PM.ReadmeLinear, np.array([[0.05, 0.2]] * 3), np.stack(xs), np.stack(gs), log_capacity=100)
+    for b in range(3):
+        ora = eo.pdesolve(OM.readme_linear(), {"x": xs[b]}, {"v": gs[b]})
+        assert bool(out.converged[b]) == ora.converged
+        assert [r["status"] for r in out.log[b]] == [r[3] for r in ora.log.rows]
+        assert out.n_outer[b] == ora.log.n_outer
+        if b == 0:
+            assert not ora.converged and all(r[3] == 4 for r in ora.log.rows)
+            np.testing.assert_array_equal(out.solution[b], gs[b])
+        else:
+            assert ora.converged
+            np.testing.assert_allclose(out.solution[b], ora.solution["v"], rtol=1e-6, atol=1e-15)
+
+
 def test_compact_batch_inputs_build_the_same_grids_on_the_device():
     """econpdes_solve_batched_inputs with compact inputs (grid = a Julia range built on the device + explicit
     points, broadcast guess): the device's range_point must reproduce the oracle's julia_range bit for bit, so the
