@@ -11,8 +11,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libeconpdes_cuda.so")
 
-MAX_DIMS = 3
-ABI_VERSION = 3   # ECONPDES_ABI_VERSION of include/econpdes_cuda.h these mirrors were written against
+MAX_DIMS = 4
+ABI_VERSION = 4   # ECONPDES_ABI_VERSION of include/econpdes_cuda.h these mirrors were written against
 
 OK, E_INVALID, E_NAN_GUESS, E_NO_DEVICE, E_CUDA, E_UNSUPPORTED, E_NCCL = 0, -1, -2, -3, -4, -5, -6
 EXIT_CONVERGED, EXIT_ALREADY_ZERO, EXIT_MAXITERS, EXIT_BELOW_MIN_DELTA, EXIT_INF_STEP_FAILED = range(5)

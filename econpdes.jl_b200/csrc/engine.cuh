@@ -94,7 +94,7 @@ struct Ctx {
   bool box = false;        // stencil shape of the Jacobian planes
   unsigned plane_mask = 0xffffffffu;   // box stencils of one unknown: planes the model's residual can depend on
   int nk = 0;              // planes per (fin, fout) pair
-  long long S[kMaxDims] = {1, 1, 1};  // GLOBAL grid sizes
+  long long S[kMaxDims] = {1, 1, 1, 1};  // GLOBAL grid sizes
   long long l = 0, n = 0;             // points / unknowns owned by this device
   long long n_glob = 0;               // unknowns of the whole grid (norms divide by it)
   int ncolors = 0;

@@ -2275,7 +2275,10 @@ std::unique_ptr<LinearSolver> make_krylov_solver(Ctx& c) {
   }
   if (c.N == 2) return std::make_unique<KrylovSolver<2>>(c);
   if (c.N == 3) return std::make_unique<KrylovSolver<3>>(c);
-  throw std::invalid_argument("Krylov solver handles 2-D and 3-D grids");
+  // four state variables (test/runtests.jl:294-320): FGMRES with one sweep of exact line solves per dimension
+  // as the preconditioner (one level: 4-D grids are a few points per axis)
+  if (c.N == 4) return std::make_unique<BlockLineSolver<4, 1>>(c);
+  throw std::invalid_argument("Krylov solver handles 2-D, 3-D and 4-D grids");
 }
 
 }  // namespace econpdes

@@ -106,7 +106,7 @@ struct ModelOpsT final : ModelOps {
   }
   // the marching sweeps keep three planes of every unknown's box in registers: not for wide systems
   // (8 unknowns on a 3-D box = 216 values), which take the one-thread-per-point kernels
-  static constexpr bool kMarchable = M::N >= 2 && M::F * ipow3(M::N) <= 108;
+  static constexpr bool kMarchable = M::N >= 2 && M::N <= 3 && M::F * ipow3(M::N) <= 108;
   static bool march_on() {
     static const bool on = env_int("ECONPDES_MARCH", 1) != 0;
     return on && kMarchable;

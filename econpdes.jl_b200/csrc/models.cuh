@@ -250,6 +250,44 @@ struct Hjb3dSynth : ModelDefaults {
   }
 };
 
+// Synthetic 4-state HJB: what test/runtests.jl:294-320 ("ND sparse coloring": four state variables, 81-point box,
+// 16 colors on a 2^4 grid) asks of the stencils beyond the known answer v = x + z + q + r -- upwinded drifts and
+// second differences along all four axes and the three cross forms on three different pairs of axes:
+// (x, w) vxw_up, (y, z) vyz_down, (x, y) vxy.
+struct Hjb4dSynth : ModelDefaults {
+  static constexpr int N = 4, F = 1, NPARAMS = 13, NSAVED = 0;
+  static constexpr bool USES_CROSS = true;
+  static const char* name() { return "hjb4d_synth"; }
+  struct Pre { double sum, m[4], h[4], cxw, cyz, cxy, rho, theta; };
+  EP_HD static void prepare(const double* prm, const double* st, Pre& c) {
+    c.sum = st[0] + st[1] + st[2] + st[3];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      c.m[d] = -prm[d] * (st[d] - 0.5);
+      c.h[d] = 0.5 * (prm[4 + d] * prm[4 + d]);
+    }
+    c.cxw = prm[8] * prm[4] * prm[7];
+    c.cyz = prm[9] * prm[5] * prm[6];
+    c.cxy = prm[10] * prm[4] * prm[5];
+    c.rho = prm[11];
+    c.theta = prm[12];
+  }
+  template <bool SAVE>
+  EP_HD static void eval(const Pre& c, const Deriv<4>* u, double* out, double*) {
+    const double v = u[0].v;
+    double drift = 0.0, diff = 0.0;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const double vd = (c.m[d] >= 0) ? u[0].up[d] : u[0].dn[d];
+      drift = d == 0 ? c.m[d] * vd : drift + c.m[d] * vd;
+      diff = d == 0 ? c.h[d] * u[0].dd[d] : diff + c.h[d] * u[0].dd[d];
+    }
+    // pairs in the order of `differentiate`: (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+    const double cross = c.cxw * u[0].xu[2] + c.cyz * u[0].xd[3] + c.cxy * u[0].x[0];
+    out[0] = -(c.sum + drift + diff + cross - c.rho * v - c.theta * (v * v));
+  }
+};
+
 // examples/neoclassical_growth.jl:61-84   saved = (c, muk)
 struct NeoclassicalGrowth : ModelDefaults {
   static constexpr int N = 1, F = 1, NPARAMS = 5, NSAVED = 2;
@@ -331,7 +369,9 @@ template <int NDIM>
 struct LinearSum : ModelDefaults {
   static constexpr int N = NDIM, F = 1, NPARAMS = 0, NSAVED = 0;
   static constexpr bool USES_CROSS = false;
-  static const char* name() { return NDIM == 1 ? "linear_sum_1d" : (NDIM == 2 ? "linear_sum_2d" : "linear_sum_3d"); }
+  static const char* name() {
+    return NDIM == 1 ? "linear_sum_1d" : (NDIM == 2 ? "linear_sum_2d" : (NDIM == 3 ? "linear_sum_3d" : "linear_sum_4d"));
+  }
   struct Pre { double st[NDIM]; };
   EP_HD static void prepare(const double*, const double* st, Pre& c) {
 #pragma unroll
@@ -1248,6 +1288,8 @@ struct AffinePair : ModelDefaults {
   X(AhlmRiskyAsset)                \
   X(PointwiseCubic)                \
   X(AffinePair)                    \
-  X(GarleanuPanageasLRR)
+  X(GarleanuPanageasLRR)           \
+  X(LinearSum<4>)                  \
+  X(Hjb4dSynth)
 
 }  // namespace econpdes

@@ -14,7 +14,7 @@
 
 namespace econpdes {
 
-constexpr int kMaxDims = 3;
+constexpr int kMaxDims = 4;
 constexpr double kSqrtEps = 1.4901161193847656e-8;
 
 // Tensor grid: per-dimension coordinate vectors, sizes and column-major strides.

@@ -486,6 +486,36 @@ class LinearSum3D(RegisteredModel):
 
 
 @dataclass(frozen=True)
+class LinearSum4D(RegisteredModel):
+    """test/runtests.jl:294-320: four state variables, known answer v = x + z + q + r."""
+    name: ClassVar[str] = "linear_sum_4d"
+    statenames: ClassVar = ("x", "z", "q", "r")
+    solnames: ClassVar = ("v",)
+
+
+@dataclass(frozen=True)
+class Hjb4dSynth(RegisteredModel):
+    """Synthetic 4-state HJB (csrc/models.cuh: Hjb4dSynth): upwinded drifts, second differences and the three cross
+    forms on an 81-point box, the stencil work behind test/runtests.jl:294-320."""
+    kx: float = 0.2
+    ky: float = 0.3
+    kz: float = 0.4
+    kw: float = 0.25
+    sx: float = 0.1
+    sy: float = 0.12
+    sz: float = 0.08
+    sw: float = 0.1
+    cxw: float = 0.5
+    cyz: float = -0.3
+    cxy: float = 0.2
+    rho: float = 0.05
+    theta: float = 1e-3
+    name: ClassVar[str] = "hjb4d_synth"
+    statenames: ClassVar = ("x", "y", "z", "w")
+    solnames: ClassVar = ("v",)
+
+
+@dataclass(frozen=True)
 class ForwardPrice(RegisteredModel):
     """test/runtests.jl:379-384."""
     name: ClassVar[str] = "forward_price"
@@ -507,4 +537,4 @@ ALL_MODELS = (ReadmeLinear, CampbellCochraneModel, BansalYaronModel, AchdouHanLa
               AchdouHanLasryLionsMollModel_TwoStates, GarleanuPanageasModel, LelandModel,
               WangWangYangModel, LinearUpwindTest, HeKrishnamurthyModel, WachterModel, HaddadModel,
               BoltonChenWangModel, GomezModel, AchdouHanLasryLionsMollModel_RiskyAsset, PointwiseCubic,
-              AffinePair, GarleanuPanageasLongRunRiskModel)
+              AffinePair, GarleanuPanageasLongRunRiskModel, LinearSum4D, Hjb4dSynth)

@@ -28,8 +28,8 @@
 extern "C" {
 #endif
 
-#define ECONPDES_ABI_VERSION 3
-#define ECONPDES_MAX_DIMS 3
+#define ECONPDES_ABI_VERSION 4
+#define ECONPDES_MAX_DIMS 4
 #define ECONPDES_MAX_FUNCS 8
 #define ECONPDES_MAX_PARAMS 16
 

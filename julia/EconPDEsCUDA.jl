@@ -16,8 +16,8 @@ const lib = get(ENV, "ECONPDES_CUDA_LIB", "libeconpdes_cuda")
 # (include/econpdes_cuda.h); field order and types must match exactly.
 struct CProblem
     model_id::Int32; ndims::Int32; nfuncs::Int32; nparams::Int32
-    size::NTuple{3, Int64}
-    grid::NTuple{3, Ptr{Float64}}
+    size::NTuple{4, Int64}
+    grid::NTuple{4, Ptr{Float64}}
     params::Ptr{Float64}; guess::Ptr{Float64}; bc::Ptr{Float64}; is_algebraic::Ptr{UInt8}
     lower_bound::Ptr{Float64}; upper_bound::Ptr{Float64}; delta_vec::Ptr{Float64}
 end
@@ -100,8 +100,8 @@ function EconPDEs.pdesolve(m::CUDAModel, grid, guess; is_algebraic = nothing, bc
     res = CResult(); res.solution = pointer(sol); res.saved = isempty(m.saved) ? C_NULL : pointer(saved)
     res.log = pointer(log); res.log_capacity = maxiters
     GC.@preserve grids guess_array alg bcs lb ub Δvec sol saved log m begin
-        gp = ntuple(d -> d <= length(S) ? pointer(grids[d]) : Ptr{Float64}(C_NULL), 3)
-        prob = CProblem(mid, length(S), F, length(m.params), ntuple(d -> d <= length(S) ? S[d] : 1, 3), gp,
+        gp = ntuple(d -> d <= length(S) ? pointer(grids[d]) : Ptr{Float64}(C_NULL), 4)
+        prob = CProblem(mid, length(S), F, length(m.params), ntuple(d -> d <= length(S) ? S[d] : 1, 4), gp,
                         pointer(m.params), pointer(guess_array), pointer(bcs), pointer(alg), pointer(lb), pointer(ub),
                         Δvec === nothing ? C_NULL : pointer(Δvec))
         rc = ccall((:econpdes_solve_stationary, lib), Cint, (Ref{CProblem}, Ref{COptions}, Ref{CResult}), prob, opts, res)
@@ -147,8 +147,8 @@ function EconPDEs.pdesolve(m::CUDAModel, grid, guess, τs::AbstractVector; bc = 
     lb = _bound_array(lower_bound, guess, -Inf, :lower_bound)
     ub = _bound_array(upper_bound, guess, Inf, :upper_bound)
     GC.@preserve grids guess_array bcs alg lb ub sol saved rn nit ts m begin
-        gp = ntuple(d -> d <= length(S) ? pointer(grids[d]) : Ptr{Float64}(C_NULL), 3)
-        prob = CProblem(mid, length(S), F, length(m.params), ntuple(d -> d <= length(S) ? S[d] : 1, 3), gp,
+        gp = ntuple(d -> d <= length(S) ? pointer(grids[d]) : Ptr{Float64}(C_NULL), 4)
+        prob = CProblem(mid, length(S), F, length(m.params), ntuple(d -> d <= length(S) ? S[d] : 1, 4), gp,
                         pointer(m.params), pointer(guess_array), pointer(bcs), pointer(alg), pointer(lb), pointer(ub), C_NULL)
         rc = ccall((:econpdes_solve_backward, lib), Cint,
                    (Ref{CProblem}, Ref{COptions}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},

@@ -221,6 +221,37 @@ def hjb3d_synth(kx, ky, kz, sx, sy, sz, corr, rho, theta):
     return pde
 
 
+HJB4D_DEFAULT = dict(kx=0.2, ky=0.3, kz=0.4, kw=0.25, sx=0.1, sy=0.12, sz=0.08, sw=0.1, cxw=0.5, cyz=-0.3, cxy=0.2,
+                     rho=0.05, theta=1e-3)
+
+
+def hjb4d_synth(kx, ky, kz, kw, sx, sy, sz, sw, cxw, cyz, cxy, rho, theta):
+    """Synthetic 4-state HJB (csrc/models.cuh: Hjb4dSynth): the stencil work behind test/runtests.jl:294-320."""
+    def pde(state, u):
+        x, y, z, w = state["x"], state["y"], state["z"], state["w"]
+        v = u["v"]
+        drift = diff = None
+        for nm, st, k, s in (("x", x, kx, sx), ("y", y, ky, sy), ("z", z, kz, sz), ("w", w, kw, sw)):
+            m = -k * (st - 0.5)
+            vd = np.where(m >= 0, u["v" + nm + "_up"], u["v" + nm + "_down"])
+            drift = m * vd if drift is None else drift + m * vd
+            dd = 0.5 * (s * s) * u["v" + nm + nm]
+            diff = dd if diff is None else diff + dd
+        cross = cxw * sx * sw * u["vxw_up"] + cyz * sy * sz * u["vyz_down"] + cxy * sx * sy * u["vxy"]
+        vt = -(x + y + z + w + drift + diff + cross - rho * v - theta * (v * v))
+        return {"vt": vt}
+    return pde
+
+
+def hjb4d_problem(n=(5, 4, 6, 3), params=None, warp=True):
+    prm = dict(HJB4D_DEFAULT if params is None else params)
+    g = {}
+    for nm, k in zip("xyzw", n):
+        a = julia_range(0.0, 1.0, k)
+        g[nm] = a ** 1.3 if warp else a     # non-uniform spacings
+    return g, {"v": np.zeros(tuple(n))}, prm
+
+
 def hjb3d_problem(n=16, params=None):
     prm = dict(HJB3D_DEFAULT if params is None else params)
     g = julia_range(0.0, 1.0, n)

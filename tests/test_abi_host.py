@@ -35,7 +35,7 @@ def test_header_symbols_all_exported(lib):
     assert declared == set(L.SYMBOLS), declared ^ set(L.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.econpdes_abi_version() == L.ABI_VERSION == 3
+    assert lib.econpdes_abi_version() == L.ABI_VERSION == 4
 
 
 def test_model_registry_matches_python_mirror(lib):

@@ -917,6 +917,41 @@ def test_pdesolve_2d_known_answer_and_inf_step():
     np.testing.assert_allclose(res.solution["v"], want, rtol=1e-10, atol=1e-12)
 
 
+def test_four_state_variables():
+    """test/runtests.jl:294-320 ("ND sparse coloring"): a 2 x 2 x 2 x 2 grid, 16 colors, Δ = Inf, known answer
+    v = x + z + q + r -- and, because that body reads no derivative, a synthetic 4-state HJB with upwinded drifts,
+    second differences and the three cross-derivative forms on an 81-point box, against the oracle: residual sweep
+    bit for bit, colored-FD Jacobian (CSC pattern of coloring.jl:18-35 in four dimensions), full solve."""
+    g4 = {k: OM.julia_range(0.0, 1.0, 2) for k in "xzqr"}
+    res = E.pdesolve(PM.LinearSum4D(), g4, {"v": np.zeros((2, 2, 2, 2))}, Δ=INF, verbose=False)
+    assert res.converged
+    want = (g4["x"][:, None, None, None] + g4["z"][None, :, None, None] + g4["q"][None, None, :, None]
+            + g4["r"][None, None, None, :])
+    np.testing.assert_allclose(res.solution["v"], want, rtol=1e-10, atol=1e-12)
+    ora = eo.pdesolve(OM.linear_sum(tuple("xzqr")), g4, {"v": np.zeros((2, 2, 2, 2))}, delta=INF)
+    assert ora.converged and [r["status"] for r in res.log] == [r[3] for r in ora.log.rows]
+
+    g, gu, prm = OM.hjb4d_problem((5, 4, 6, 3))
+    rng = np.random.default_rng(3)
+    y = 20.0 + rng.uniform(-1, 1, (5, 4, 6, 3, 1))
+    h = E.Handle(PM.Hjb4dSynth(**prm), list(g.values()), y)
+    prob = eo.Problem(OM.hjb4d_synth(**prm), tuple(g), list(g.values()), ("v",))
+    yvec = y.reshape(-1, order="F")
+    np.testing.assert_array_equal(h.residual(y), prob.G(yvec))
+    cache = eo.JacobianCache((5, 4, 6, 3), 1)
+    nz_want, eps_want = eo.finite_difference_jacobian(prob.G, yvec, cache)
+    nz, eps = h.jacobian_csc(y)   # values in the order of the CSC pattern of coloring.jl:18-35 (econpdes_stencil_pattern)
+    h.close()
+    np.testing.assert_allclose(eps, eps_want, rtol=1e-14)
+    np.testing.assert_allclose(nz, nz_want, rtol=0, atol=2e-6 * np.abs(nz_want).max())
+    colptr, rowval = E.stencil_pattern((5, 4, 6, 3), 1)
+    np.testing.assert_array_equal(colptr, cache.colptr)
+    np.testing.assert_array_equal(rowval, cache.rowval)
+    res = E.pdesolve(PM.Hjb4dSynth(**prm), g, gu, verbose=False)
+    ora = eo.pdesolve(OM.hjb4d_synth(**prm), g, gu)
+    _check_against(res, ora)
+
+
 def test_pdesolve_ahlm_live_oracle_with_saved():
     g, gu, prm = OM.ahlm_diffusion_problem(12, 150)
     res = E.pdesolve(PM.AchdouHanLasryLionsMollModel_Diffusion(**prm), g, gu, verbose=False)

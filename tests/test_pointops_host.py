@@ -33,6 +33,12 @@ def _cases():
     out.append(("growth_test", PM.GrowthTest(), OM.growth_test_hjb(), g, gu))
     g = {"x": OM.julia_range(0, 1, 4), "z": OM.julia_range(0, 1, 5)}
     out.append(("lin2d", PM.LinearSum2D(), OM.linear_sum(("x", "z")), g, {"v": np.zeros((4, 5))}))
+    g4 = {k: OM.julia_range(0, 1, n) for k, n in (("x", 2), ("z", 3), ("q", 2), ("r", 4))}
+    out.append(("lin4d", PM.LinearSum4D(), OM.linear_sum(tuple("xzqr")), g4, {"v": np.zeros((2, 3, 2, 4))}))
+    g, gu, prm = OM.hjb4d_problem((5, 4, 3, 4))
+    rng4 = np.random.default_rng(5)
+    gu = {"v": 20.0 + rng4.uniform(-1, 1, (5, 4, 3, 4))}
+    out.append(("hjb4d", PM.Hjb4dSynth(**prm), OM.hjb4d_synth(**prm), g, gu))
     g = {"x": OM.julia_range(0.1, 1, 5)}
     out.append(("fwdprice", PM.ForwardPrice(), OM.forward_price(), g, {"v": np.ones(5), "p": np.ones(5) * 0.5}))
     g, gu, prm = OM.hjb2d_regimes_problem(9, 7)
@@ -189,7 +195,7 @@ def test_fused_jacobian_matches_colored_fd(case, delta):
         with np.errstate(all="ignore"):
             return prob.G(v) - (ypvec - v) / delta
     nz_want, eps = eo.finite_difference_jacobian(R, yvec, cache)
-    box = name in ("hjb3d", "regimes2d", "ditella", "gp_lrr")
+    box = name in ("hjb3d", "regimes2d", "ditella", "gp_lrr", "hjb4d")
     planes, r0 = EU.jacobian_planes(pm, grids, y, ypost, delta, eps, box)
     if name in POW_MODELS:
         np.testing.assert_allclose(r0, R(yvec), rtol=0, atol=8 * np.finfo(float).eps * np.abs(r0).max())
