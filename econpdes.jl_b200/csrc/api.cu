@@ -1,5 +1,7 @@
 // extern "C" entry points of libeconpdes_cuda.so (include/econpdes_cuda.h).
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <limits>
 
@@ -101,6 +103,7 @@ struct econpdes_batch {
   cudaStream_t pipe[kPipe] = {};   // copy/compute pipeline of the one-call path (econpdes_solve_batched)
   // pinned staging for the per-problem scalars (error, exit reason, counts, residual norm): a pageable
   // target would make every slice's read-back block the host and serialise the pipeline
+  int sms = 0;                     // multiprocessors of the batch's device (slice sizes are whole waves)
   bool last_direct = false;        // the last one-call solve stored its results straight into pinned host memory
   int* err_host = nullptr;         // [4][B]: error, exit_reason, n_outer, n_newton
   double* rn_host = nullptr;       // [B]
@@ -863,8 +866,11 @@ int econpdes_solve_batched_inputs(int model_id, int64_t nproblems, int64_t npoin
     batch_accept_inputs(b, in);
     const long long B = b->B;
     const size_t S = static_cast<size_t>(b->S);
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (b->sms == 0) {
+      b->sms = 148;
+      cudaDeviceGetAttribute(&b->sms, cudaDevAttrMultiProcessorCount, device);
+    }
+    const int sms = b->sms;
     // Zero-copy results: when the caller's solution buffer is pinned (page-locked and mapped into the device's
     // address space, which cudaHostAlloc / cudaHostRegister memory is under unified addressing), every block stores
     // its solution straight into it over PCIe as it finishes, and the per-problem scalars go to the library's own
@@ -955,12 +961,28 @@ int econpdes_solve_batched_inputs(int model_id, int64_t nproblems, int64_t npoin
             if (p) cudaStreamSynchronize(p);
       }
     } drain{b};
+    // ECONPDES_BATCH_TIMELINE=1: where one call's time goes (host clock around queueing and waiting, device events
+    // around each slice's upload and solve), printed to stderr
+    static const bool timeline = [] { const char* e = std::getenv("ECONPDES_BATCH_TIMELINE"); return e && e[0] == '1'; }();
+    std::vector<cudaEvent_t> tev;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_us = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - host_t0).count(); };
+    auto mark = [&](cudaStream_t s) {
+      if (!timeline) return;
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      cudaEventRecord(e, s);
+      tev.push_back(e);
+    };
     for (size_t c = 0; c + 1 < bounds.size(); ++c) {
       const long long first = bounds[c], last = bounds[c + 1];
       const size_t n = static_cast<size_t>(last - first), o = static_cast<size_t>(first);
       cudaStream_t s = b->pipe[c % econpdes_batch::kPipe];
+      mark(s);
       batch_upload_slice(b, in, first, last, s);
+      mark(s);
       batch_launch(b, options, 0, first, last, s, use_direct ? &direct : nullptr);
+      mark(s);
       if (use_direct) continue;   // the kernel has the host addresses: nothing to copy back
       // error, exit_reason, n_outer, n_newton of the slice: four rows of one pitched copy
       EP_CUDA(cudaMemcpy2DAsync(err + o, nB * sizeof(int), b->ints.p + o, nB * sizeof(int), n * sizeof(int), 4,
@@ -970,8 +992,24 @@ int econpdes_solve_batched_inputs(int model_id, int64_t nproblems, int64_t npoin
       if (residual_norm)
         EP_CUDA(cudaMemcpyAsync(b->rn_host + o, b->residual_norm.p + o, n * sizeof(double), cudaMemcpyDeviceToHost, s));
     }
+    const double t_queued = host_us();
     for (cudaStream_t p : b->pipe) EP_CUDA(cudaStreamSynchronize(p));
+    const double t_synced = host_us();
     drain.armed = false;
+    if (timeline) {
+      std::fprintf(stderr, "[batch timeline] %zu slices, direct %d: queued %.0f us, synced %.0f us;", bounds.size() - 1,
+                   use_direct ? 1 : 0, t_queued, t_synced);
+      for (size_t c = 0; 3 * c + 2 < tev.size(); ++c) {
+        float up0 = 0.f, k0 = 0.f, k1 = 0.f;
+        cudaEventElapsedTime(&up0, tev[0], tev[3 * c]);
+        cudaEventElapsedTime(&k0, tev[0], tev[3 * c + 1]);
+        cudaEventElapsedTime(&k1, tev[0], tev[3 * c + 2]);
+        std::fprintf(stderr, " slice %zu (%lld problems): upload from %.0f, solve %.0f..%.0f us;", c,
+                     bounds[c + 1] - bounds[c], up0 * 1e3, k0 * 1e3, k1 * 1e3);
+      }
+      std::fprintf(stderr, "\n");
+      for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     if (residual_norm) std::memcpy(residual_norm, b->rn_host, nB * sizeof(double));
     if (exit_reason) std::memcpy(exit_reason, err + nB, nB * sizeof(int32_t));
     if (n_outer) std::memcpy(n_outer, err + 2 * nB, nB * sizeof(int32_t));

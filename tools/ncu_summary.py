@@ -19,6 +19,12 @@ KEYS = {
     "sm__warps_active.avg.pct_of_peak_sustained_active": "achieved_occupancy_pct",
     "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": "fp64_pipe_active_pct",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active": "fp64_inst_issue_pct_of_peak",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active": "lsu_pipe_pct",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active": "fma_pipe_pct",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
+    "lts__t_bytes.sum": "l2_bytes",
+    "sm__cycles_elapsed.avg": "sm_cycles_elapsed",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active": "alu_pipe_pct",
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active": "xu_pipe_pct",
     "smsp__inst_executed.sum": "warp_instructions",
