@@ -5,6 +5,7 @@
 // Scalars of the control loop (norms, the SER controller) live on the host; every field
 // stays in HBM for the whole solve.
 #include "engine.cuh"
+#include "normaleq.cuh"
 
 #include <cmath>
 #include <cstring>
@@ -563,6 +564,31 @@ void Solver::jacobian_diagnostics(double delta, const econpdes_options& opt) {
 }
 
 // NLsolve newton_ with the Static line search, wrapped like _newtonstep (:125-147).
+static bool opt_singular_retry() {
+  static const bool on = [] { const char* e = std::getenv("ECONPDES_SINGULAR_RETRY"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+int Solver::regularized_step() {
+  ProfScope ps("singular_retry", c_->stream);
+  const int F = c_->F;
+  double lambda = 0.0;
+  int iters = 0;
+  auto run = [&](auto ntag) {
+    constexpr int NN = decltype(ntag)::value;
+    const GridView<NN> gv = c_->grid_view<NN>();
+    return c_->box ? regularized_normal_solve<NN, true>(c_->stream, gv, F, planes_.p, R_.p, s_.p, neq_, &lambda, &iters)
+                   : regularized_normal_solve<NN, false>(c_->stream, gv, F, planes_.p, R_.p, s_.p, neq_, &lambda, &iters);
+  };
+  switch (c_->N) {
+    case 1: return run(std::integral_constant<int, 1>{});
+    case 2: return run(std::integral_constant<int, 2>{});
+    case 3: return run(std::integral_constant<int, 3>{});
+    case 4: return run(std::integral_constant<int, 4>{});
+    default: return 1;
+  }
+}
+
 NewtonOutcome Solver::newton(const double* ypost, double delta, double ftol, int maxit, const econpdes_options& opt,
                              double* y_out) {
   const long long n = c_->n;
@@ -596,7 +622,14 @@ NewtonOutcome Solver::newton(const double* ypost, double delta, double ftol, int
     ++out.lin_solves;
     if (rr > 1e-11) ++out.lin_loose;
     if (rr > out.lin_max_relres) out.lin_max_relres = rr;
-    if (fail) {  // SingularException -> (y0, Inf)
+    // SingularException: NLsolve first retries with the regularised normal equations (newton.jl; restated in
+    // oracle/econpdes_oracle.py:nlsolve_newton) and only a failure of THAT solve leaves the Newton iteration
+    bool give_up = fail != 0;
+    if (fail && c_->dist == nullptr && opt_singular_retry() && regularized_step() == 0) {
+      ++out.singular_retries;
+      give_up = false;
+    }
+    if (give_up) {  // -> (y0, Inf), finiteschemesolve.jl:142-146
       out.singular = true;
       out.nl = INFINITY;
       EP_CUDA(cudaMemcpyAsync(y_out, ypost, n * sizeof(double), cudaMemcpyDeviceToDevice, c_->stream));

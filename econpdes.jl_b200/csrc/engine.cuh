@@ -201,11 +201,18 @@ struct LinearSolver {
 std::unique_ptr<LinearSolver> make_tridiag_solver(Ctx& c);
 std::unique_ptr<LinearSolver> make_krylov_solver(Ctx& c);  // krylov.cu
 
+// work vectors of the regularised normal-equations solve (normaleq.cuh), allocated on first use
+struct NormalEqWork {
+  DevBuf<double> b, r, p, q, w, partial, scalar;
+  DevBuf<unsigned long long> bits;
+};
+
 struct NewtonOutcome {
   double nl;        // ||R(zero)||_2/n, Inf if singular, NaN if NaN
   int iters;
   long long lin_iters;
   bool singular;
+  int singular_retries = 0;   // iterations that took NLsolve's regularised-normal-equations direction
   int lin_solves = 0, lin_loose = 0;   // linear solves, and those that ended with a relative residual above 1e-11
   double lin_max_relres = 0.0;
 };
@@ -239,6 +246,9 @@ class Solver {
   Norms read_norms();
   Norms residual_with_norms(const double* y, const RowSpec& rs, double* out);
   bool last_tame_ = false;
+  // NLsolve's regularised-normal-equations direction for a singular Jacobian (normaleq.cuh): s_ from planes_ and R_
+  int regularized_step();
+  NormalEqWork neq_;
   double masked_norm(const double* ydot, const double* y);
   void jacobian_diagnostics(double delta, const econpdes_options& opt);
   std::unique_ptr<Ctx> c_;
