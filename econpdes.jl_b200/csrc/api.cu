@@ -122,7 +122,7 @@ struct econpdes_batch {
       EP_CUDA(cudaMemcpyAsync(h, p, count * sizeof(int), cudaMemcpyDeviceToHost, s));
     }
   } exit_reason, n_outer, n_newton, error;
-  DevBuf<int> log_len;
+  DevBuf<int> log_len, flags;
   DevBuf<econpdes_log_row> log;
   int log_capacity = 0;
   int64_t launches = 0;
@@ -384,6 +384,11 @@ struct BatchOut {
 static int batch_launch(econpdes_batch* b, const econpdes_options* options, int log_capacity, long long first,
                         long long last, cudaStream_t s, const BatchOut* out = nullptr);
 
+static bool fused_singular_falls_back() {
+  static const bool on = [] { const char* e = std::getenv("ECONPDES_SINGULAR_RETRY"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 static bool solve_fused_1d(const econpdes_problem* p, const econpdes_options* opt, econpdes_result* res, int* rc_out) {
   static const bool enabled = [] { const char* e = std::getenv("ECONPDES_FUSED_1D"); return !(e && e[0] == '0'); }();
   if (!enabled) return false;
@@ -432,7 +437,9 @@ static bool solve_fused_1d(const econpdes_problem* p, const econpdes_options* op
   batch_launch(b, opt, cap, 0, -1, nullptr);
   // results of the solve, needed to decide on the diagnostics
   int h_int[5] = {0, 0, 0, 0, 0};   // error, exit_reason, n_outer, n_newton, log_len
+  int h_flags = 0;
   double h_rn = 0.0;
+  b->flags.download(&h_flags, 1, s);
   b->error.download(&h_int[0], 1, s);
   b->exit_reason.download(&h_int[1], 1, s);
   b->n_outer.download(&h_int[2], 1, s);
@@ -440,6 +447,13 @@ static bool solve_fused_1d(const econpdes_problem* p, const econpdes_options* op
   b->log_len.download(&h_int[4], 1, s);
   b->residual_norm.download(&h_rn, 1, s);
   EP_CUDA(cudaStreamSynchronize(s));
+  if ((h_flags & 1) != 0 && fused_singular_falls_back()) {
+    // a Newton iteration met a singular Jacobian: the fused kernel gives such a step up at once, the generic engine
+    // first takes NLsolve's regularised-normal-equations direction (normaleq.cuh) -- solve the problem there
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return false;
+  }
   res->sign_flags = 0;
   res->nonmonotone_entries = 0;
   res->nonmonotone_max = 0.0;
@@ -606,6 +620,7 @@ int econpdes_batch_create(int model_id, int64_t nproblems, int64_t npoints, econ
     b->n_outer.p = b->ints.p + 2 * B;
     b->n_newton.p = b->ints.p + 3 * B;
     b->log_len.alloc(B);
+    b->flags.alloc(B);
     *out = b.release();
     return ECONPDES_OK;
   });
@@ -709,6 +724,7 @@ static int batch_launch(econpdes_batch* b, const econpdes_options* options, int 
   a.log = b->log_capacity > 0 ? b->log.p : nullptr;
   a.log_capacity = b->log_capacity;
   a.log_len = b->log_len.p;
+  a.flags = b->flags.p;
   a.opt = *options;
   if (out != nullptr) {
     const size_t nB = static_cast<size_t>(b->B);

@@ -37,6 +37,7 @@ struct BatchArgs {
   econpdes_log_row* log; // [B][log_capacity] or nullptr
   int log_capacity;
   int* log_len;          // [B]
+  int* flags = nullptr;  // [B] or nullptr: bit 0 = some Newton iteration met a singular Jacobian (a vanishing pivot)
   econpdes_options opt;
 };
 
@@ -291,6 +292,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
 #pragma unroll
   for (int j = 0; j < P; ++j) { y[j] = ypost[j]; Gy[j] = Gpost[j]; }
   int newton_it = 0;
+  bool any_singular = false;
   // Block-wide OR of a small bit mask in one barrier: warps fold their lanes with REDUX and
   // post the result with one shared atomic.  Three slots rotate: call k uses slot k%3 and,
   // after its barrier, clears slot (k+2)%3 -- last read before this barrier, next written
@@ -427,6 +429,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
       if (!ok) { singular = true; break; }
     }
     if (singular) {   // -> (y0, Inf), finiteschemesolve.jl:142-146
+      any_singular = true;
 #pragma unroll
       for (int j = 0; j < P; ++j) { y[j] = ypost[j]; Gy[j] = Gpost[j]; }
       nl = INFINITY;
@@ -509,6 +512,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
     args.n_newton[b] = n_newton;
     args.error[b] = error;
     if (args.log_len != nullptr) args.log_len[b] = log_len < args.log_capacity ? log_len : args.log_capacity;
+    if (args.flags != nullptr) args.flags[b] = any_singular ? 1 : 0;
   }
 }
 

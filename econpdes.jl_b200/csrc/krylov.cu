@@ -595,12 +595,8 @@ __device__ __forceinline__ void fine_range(int type, long long I, long long Sf, 
 // The per-dimension weights and index ranges are formed once per point; the 3^N (2^N) combinations are
 // then compile-time loops (no run-time divisions in the inner loop).
 template <int N>
-__global__ void __launch_bounds__(kBlock) k_restrict(const Transfer* __restrict__ tp, LevelGeom<N> gf,
-                                                     LevelGeom<N> gc, const double* __restrict__ rf,
-                                                     double* __restrict__ rc) {
-  const Transfer t = *tp;   // lives in device memory so a captured CUDA graph sees every set-up's choice
-  const long long pc = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (pc >= gc.l) return;
+__device__ __forceinline__ double restrict_point(const Transfer& t, const LevelGeom<N>& gf, const LevelGeom<N>& gc,
+                                                 const double* rf, long long pc) {
   long long I[N];
   unravel_l<N>(pc, gc, I);
   double wt[N][3];
@@ -630,17 +626,23 @@ __global__ void __launch_bounds__(kBlock) k_restrict(const Transfer* __restrict_
     }
     if (w != 0.0) acc += w * rf[q];
   }
-  rc[pc] = acc;
+  return acc;
+}
+
+template <int N>
+__global__ void __launch_bounds__(kBlock) k_restrict(const Transfer* __restrict__ tp, LevelGeom<N> gf,
+                                                     LevelGeom<N> gc, const double* __restrict__ rf,
+                                                     double* __restrict__ rc) {
+  const Transfer t = *tp;   // lives in device memory so a captured CUDA graph sees every set-up's choice
+  const long long pc = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pc >= gc.l) return;
+  rc[pc] = restrict_point<N>(t, gf, gc, rf, pc);
 }
 
 // x_f += P e_c
 template <int N>
-__global__ void __launch_bounds__(kBlock) k_prolong_add(const Transfer* __restrict__ tp, LevelGeom<N> gf,
-                                                        LevelGeom<N> gc, const double* __restrict__ ec,
-                                                        double* __restrict__ xf) {
-  const Transfer t = *tp;
-  const long long pf = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (pf >= gf.l) return;
+__device__ __forceinline__ double prolong_point(const Transfer& t, const LevelGeom<N>& gf, const LevelGeom<N>& gc,
+                                                const double* ec, long long pf) {
   long long i[N];
   unravel_l<N>(pf, gf, i);
   // every fine point interpolates from at most 2 coarse points per dimension
@@ -670,7 +672,265 @@ __global__ void __launch_bounds__(kBlock) k_prolong_add(const Transfer* __restri
     }
     if (w != 0.0) acc += w * ec[q];
   }
-  xf[pf] += acc;
+  return acc;
+}
+
+template <int N>
+__global__ void __launch_bounds__(kBlock) k_prolong_add(const Transfer* __restrict__ tp, LevelGeom<N> gf,
+                                                        LevelGeom<N> gc, const double* __restrict__ ec,
+                                                        double* __restrict__ xf) {
+  const Transfer t = *tp;
+  const long long pf = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pf >= gf.l) return;
+  xf[pf] += prolong_point<N>(t, gf, gc, ec, pf);
+}
+
+// ---- coarse levels of the V-cycle in ONE kernel ------------------------------------------------
+// Below a few ten thousand points a level's ~20 (2-D) / ~40 (3-D) kernels are pure launch latency: the 2-D
+// hierarchy of a 2048^2 grid spends two thirds of its cycle in levels of 256^2 points and fewer, and the three
+// replicated levels of the slab-decomposed 3-D cycle cost 0.5-0.8 ms that no rank count shrinks.  Here ONE
+// thread-block cluster (8 blocks of 512 threads on 8 SMs) runs the whole sub-cycle from the first "small" level
+// down to the dense coarsest solve and back up: zebra line relaxation in every direction, residual, restriction,
+// interpolation -- the same sweeps in the same order as the per-kernel path -- separated by cluster barriers
+// (hardware barrier with release / acquire semantics at cluster scope: a few hundred nanoseconds, against several
+// microseconds per dependent kernel of a graph).  All vectors stay in layout 0 (no transposed copies: the lines of
+// direction d are read with stride g.stride[d]; the levels are L2-resident); the lines of a colour are dealt to the
+// blocks, each block solving its share in batches by parallel cyclic reduction in shared memory.
+constexpr int kCoarseMaxLevels = 8;
+constexpr int kCoarseThreads = 512;
+constexpr int kCoarseBatchPts = 2048;   // points of the lines one block relaxes at a time (4 x 16 KB of shared memory)
+constexpr int kCoarseRpt = kCoarseBatchPts / kCoarseThreads;
+
+template <int N>
+struct CoarseLevelArg {
+  LevelGeom<N> g;
+  const mgreal_t<N>* A;   // box planes, layout 0
+  double *x, *b, *r;
+};
+template <int N>
+struct CoarseCycleArgs {
+  int nlev;                          // levels lev[0] .. lev[nlev-1]; the last one is the dense coarsest level
+  CoarseLevelArg<N> lev[kCoarseMaxLevels];
+  const Transfer* transfers;         // transfers[i]: lev[i] -> lev[i+1]
+  int dense_n;
+  const double* dense_inv;           // column-major inverse of the coarsest operator
+};
+
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+
+// y(pt) = b(pt) - (A x)(pt) on a replicated box level (every plane, closed boundaries)
+template <int N>
+__device__ __forceinline__ double coarse_residual_point(const LevelGeom<N>& g, const mgreal_t<N>* __restrict__ A,
+                                                        const double* x, const double* b, long long pt) {
+  using St = Stencil<N, true>;
+  long long idx[N];
+  unravel_l<N>(pt, g, idx);
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < St::NK; ++k) {
+    long long q = pt;
+    bool ok = true;
+#pragma unroll
+    for (int d = 0; d < N; ++d) {
+      const int o = St::off(k, d);
+      if ((o < 0 && idx[d] == 0) || (o > 0 && idx[d] == g.S[d] - 1)) ok = false;
+      q += o * g.stride[d];
+    }
+    acc += static_cast<double>(A[k * g.l + pt]) * x[ok ? q : pt];
+  }
+  return b[pt] - acc;
+}
+
+// one colour of the zebra line relaxation along dimension D of level L, shared among the blocks of the cluster
+template <int N, int D>
+__device__ void coarse_line_sweep(const CoarseLevelArg<N>& L, int color, double* sh, unsigned crank, unsigned csize) {
+  using St = Stencil<N, true>;
+  const LevelGeom<N>& g = L.g;
+  const int n = static_cast<int>(g.S[D]);
+  double* sa = sh;
+  double* si = sh + kCoarseBatchPts;
+  double* sc = sh + 2 * kCoarseBatchPts;
+  double* sd = sh + 3 * kCoarseBatchPts;
+  // the other dimensions in ascending order; bit j of the colour is the parity of the j-th of them
+  int od[N > 1 ? N - 1 : 1];
+  long long cnt[N > 1 ? N - 1 : 1];
+  long long nlines = 1;
+  {
+    int j = 0;
+#pragma unroll
+    for (int e = 0; e < N; ++e) {
+      if (e == D) continue;
+      od[j] = e;
+      const int ce = (color >> j) & 1;
+      cnt[j] = (g.S[e] - ce + 1) / 2;
+      nlines *= cnt[j];
+      ++j;
+    }
+  }
+  if (nlines <= 0) return;
+  // in-line plane ids
+  constexpr int kc = (ipow3(N) - 1) / 2, km = kc - p3(D), kp = kc + p3(D);
+  const int lines_per_batch = kCoarseBatchPts / n > 0 ? kCoarseBatchPts / n : 1;
+  // block `crank` takes the line batches crank, crank + csize, ...
+  const long long nbatches = (nlines + lines_per_batch - 1) / lines_per_batch;
+  for (long long batch = crank; batch < nbatches; batch += csize) {
+    const long long line0 = batch * lines_per_batch;
+    const int nl = static_cast<int>(nlines - line0 < lines_per_batch ? nlines - line0 : lines_per_batch);
+    const int npts = nl * n;
+    double ra[kCoarseRpt], rb[kCoarseRpt], rc[kCoarseRpt], rd[kCoarseRpt];
+    long long ptm[kCoarseRpt];
+    int im_[kCoarseRpt];
+#pragma unroll
+    for (int m = 0; m < kCoarseRpt; ++m) {
+      const int p = threadIdx.x + m * kCoarseThreads;
+      ra[m] = 0.0; rb[m] = 1.0; rc[m] = 0.0; rd[m] = 0.0; ptm[m] = -1; im_[m] = 0;
+      if (p < npts) {
+        const int i = p % n;
+        long long q = line0 + p / n;
+        long long idx[N];
+        idx[D] = i;
+        long long pt = static_cast<long long>(i) * g.stride[D];
+#pragma unroll
+        for (int j = 0; j < N - 1; ++j) {
+          const int ce = (color >> j) & 1;
+          const long long v = ce + 2 * (q % cnt[j]);
+          q /= cnt[j];
+          idx[od[j]] = v;
+          pt += v * g.stride[od[j]];
+        }
+        double rhs = L.b[pt];
+#pragma unroll
+        for (int k = 0; k < St::NK; ++k) {
+          if (k == kc || k == km || k == kp) continue;
+          long long qq = pt;
+          bool ok = true;
+#pragma unroll
+          for (int e = 0; e < N; ++e) {
+            const int o = St::off(k, e);
+            if ((o < 0 && idx[e] == 0) || (o > 0 && idx[e] == g.S[e] - 1)) ok = false;
+            qq += o * g.stride[e];
+          }
+          rhs -= static_cast<double>(L.A[k * g.l + pt]) * L.x[ok ? qq : pt];
+        }
+        ra[m] = i > 0 ? static_cast<double>(L.A[km * g.l + pt]) : 0.0;
+        rb[m] = static_cast<double>(L.A[kc * g.l + pt]);
+        rc[m] = i < n - 1 ? static_cast<double>(L.A[kp * g.l + pt]) : 0.0;
+        rd[m] = rhs;
+        ptm[m] = pt;
+        im_[m] = i;
+      }
+    }
+    for (int s = 1; s < n; s <<= 1) {
+#pragma unroll
+      for (int m = 0; m < kCoarseRpt; ++m) {
+        const int p = threadIdx.x + m * kCoarseThreads;
+        if (p < npts) { sa[p] = ra[m]; si[p] = fast_rcp(rb[m]); sc[p] = rc[m]; sd[p] = rd[m]; }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int m = 0; m < kCoarseRpt; ++m) {
+        const int p = threadIdx.x + m * kCoarseThreads;
+        if (p < npts) {
+          const int i = im_[m];
+          double na = 0.0, nc = 0.0;
+          if (i - s >= 0) {
+            const double al = -ra[m] * si[p - s];
+            na = al * sa[p - s];
+            rb[m] += al * sc[p - s];
+            rd[m] += al * sd[p - s];
+          }
+          if (i + s < n) {
+            const double ga = -rc[m] * si[p + s];
+            nc = ga * sc[p + s];
+            rb[m] += ga * sa[p + s];
+            rd[m] += ga * sd[p + s];
+          }
+          ra[m] = na;
+          rc[m] = nc;
+        }
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int m = 0; m < kCoarseRpt; ++m)
+      if (ptm[m] >= 0) L.x[ptm[m]] = rd[m] / rb[m];
+    __syncthreads();   // the next batch re-uses the shared arrays
+  }
+}
+
+template <int N, int D>
+__device__ void coarse_smooth_dim(const CoarseLevelArg<N>& L, double* sh, unsigned crank, unsigned csize) {
+  if (L.g.S[D] < 2) return;
+  for (int color = 0; color < (1 << (N - 1)); ++color) {
+    coarse_line_sweep<N, D>(L, color, sh, crank, csize);
+    cluster_barrier();
+  }
+}
+
+template <int N>
+__device__ void coarse_smooth(const CoarseLevelArg<N>& L, bool reverse, double* sh, unsigned crank, unsigned csize) {
+  if (!reverse) {
+    coarse_smooth_dim<N, 0>(L, sh, crank, csize);
+    if (N >= 2) coarse_smooth_dim<N, (N >= 2 ? 1 : 0)>(L, sh, crank, csize);
+    if (N >= 3) coarse_smooth_dim<N, (N >= 3 ? 2 : 0)>(L, sh, crank, csize);
+  } else {
+    if (N >= 3) coarse_smooth_dim<N, (N >= 3 ? 2 : 0)>(L, sh, crank, csize);
+    if (N >= 2) coarse_smooth_dim<N, (N >= 2 ? 1 : 0)>(L, sh, crank, csize);
+    coarse_smooth_dim<N, 0>(L, sh, crank, csize);
+  }
+}
+
+// lev[0].x = V-cycle(lev[0].b) over lev[0..nlev-1]
+template <int N>
+__global__ void __launch_bounds__(kCoarseThreads, 1) k_coarse_cycle(const __grid_constant__ CoarseCycleArgs<N> a) {
+  extern __shared__ double sh[];
+  const unsigned crank = cluster_ctarank(), csize = cluster_nctarank();
+  const long long gtid = static_cast<long long>(crank) * kCoarseThreads + threadIdx.x;
+  const long long gthreads = static_cast<long long>(csize) * kCoarseThreads;
+  for (int li = 0; li + 1 < a.nlev; ++li) {
+    const CoarseLevelArg<N>& L = a.lev[li];
+    const CoarseLevelArg<N>& Lc = a.lev[li + 1];
+    for (long long pt = gtid; pt < L.g.l; pt += gthreads) L.x[pt] = 0.0;
+    cluster_barrier();
+    coarse_smooth<N>(L, false, sh, crank, csize);
+    for (long long pt = gtid; pt < L.g.l; pt += gthreads) L.r[pt] = coarse_residual_point<N>(L.g, L.A, L.x, L.b, pt);
+    cluster_barrier();
+    const Transfer t = a.transfers[li];
+    for (long long pc = gtid; pc < Lc.g.l; pc += gthreads) Lc.b[pc] = restrict_point<N>(t, L.g, Lc.g, L.r, pc);
+    cluster_barrier();
+  }
+  {   // coarsest level: x = Minv b, one warp per row
+    const CoarseLevelArg<N>& L = a.lev[a.nlev - 1];
+    const int n = a.dense_n;
+    const int lane = threadIdx.x & 31;
+    for (long long row = gtid >> 5; row < n; row += gthreads >> 5) {
+      double t = 0.0;
+      for (int c = lane; c < n; c += 32) t += a.dense_inv[static_cast<long long>(c) * n + row] * L.b[c];
+      t = warp_sum(t);
+      if (lane == 0) L.x[row] = t;
+    }
+    cluster_barrier();
+  }
+  for (int li = a.nlev - 2; li >= 0; --li) {
+    const CoarseLevelArg<N>& L = a.lev[li];
+    const CoarseLevelArg<N>& Lc = a.lev[li + 1];
+    const Transfer t = a.transfers[li];
+    for (long long pf = gtid; pf < L.g.l; pf += gthreads) L.x[pf] += prolong_point<N>(t, L.g, Lc.g, Lc.x, pf);
+    cluster_barrier();
+    coarse_smooth<N>(L, true, sh, crank, csize);
+  }
 }
 
 // Separable Galerkin product: coarsen ONE dimension d of the operator (the full P^T A P with
@@ -1697,8 +1957,77 @@ class KrylovSolver final : public LinearSolver {
     dense_inv_.alloc(static_cast<size_t>(dense_n_) * dense_n_);
     dense_work_.alloc(static_cast<size_t>(dense_n_) * dense_n_);
     EP_LAUNCH(k_dense_invert, (dense_n_ + 63) / 64, 64, 0, s, dense_n_, dense_.p, piv_.p, dense_inv_.p, dense_work_.p);
+    choose_coarse_start();
   }
   int nlev_ = 0;
+  // first level of the sub-cycle that runs as one cluster kernel (k_coarse_cycle); 0 = none
+  int coarse_li_ = 0;
+
+  void choose_coarse_start() {
+    // OFF by default: measured on B200 the one-cluster sub-cycle is SLOWER than the kernels it replaces (V-cycle at
+    // 2048^2: 1.07 ms per-kernel, 1.09 / 1.20 / 1.32 / 1.61 ms with the levels of <= 1 200 / 5 000 / 17 000 / 70 000
+    // points in the cluster kernel; 256^3: 5.49 against 5.50 / 5.80 / 5.80 / 6.72 ms) although it removes two thirds
+    // of the launches: every phase is a cluster barrier plus a global-memory round trip (~2.7 us, ncu: 28 warps
+    // stalled on barriers per issue, 10 % issue utilisation), no faster than a ~3 us kernel of a CUDA graph that
+    // spreads the same phase over 148 SMs.  ECONPDES_COARSE_CLUSTER=1 turns it on (read at every set-up).
+    const char* en = std::getenv("ECONPDES_COARSE_CLUSTER");
+    const bool enabled = en != nullptr && en[0] == '1';
+    const char* mp = std::getenv("ECONPDES_COARSE_MAX_POINTS");
+    const long long max_pts = mp ? std::atoll(mp) : 5000LL;
+    coarse_li_ = 0;
+    if (!enabled) return;
+    for (int li = 1; li + 1 < nlev_; ++li) {   // at least one smoothed level above the dense one
+      bool ok = nlev_ - li <= kCoarseMaxLevels;
+      for (int q = li; q < nlev_ && ok; ++q) {
+        const Level<N>& L = *lev_[q];
+        ok = !L.dist && L.l <= max_pts && (q == nlev_ - 1 || (L.box && L.mask == 0xffffffffu));
+        for (int d = 0; d < N && ok; ++d) ok = L.S[d] <= kCoarseBatchPts;
+      }
+      if (ok) { coarse_li_ = li; return; }
+    }
+  }
+
+  // lev_[coarse_li_]->x = V-cycle(lev_[coarse_li_]->b) over the levels coarse_li_ .. nlev_-1, one launch
+  void launch_coarse_cycle() {
+    static const int cluster = [] {
+      const char* e = std::getenv("ECONPDES_COARSE_CLUSTER_SIZE");
+      const int v = e ? std::atoi(e) : 8;
+      return v == 1 || v == 2 || v == 4 || v == 8 ? v : 8;
+    }();
+    CoarseCycleArgs<N> a{};
+    a.nlev = nlev_ - coarse_li_;
+    for (int q = 0; q < a.nlev; ++q) {
+      Level<N>& L = *lev_[coarse_li_ + q];
+      a.lev[q].g = make_geom<N>(L.S);
+      a.lev[q].A = L.A;
+      a.lev[q].x = L.x.p;
+      a.lev[q].b = L.b.p;
+      a.lev[q].r = L.r.p;
+    }
+    a.transfers = transfers_dev_.p + coarse_li_;
+    a.dense_n = dense_n_;
+    a.dense_inv = dense_inv_.p;
+    const size_t smem = 4 * static_cast<size_t>(kCoarseBatchPts) * sizeof(double);
+    static bool cfg = false;
+    if (!cfg) {
+      EP_CUDA(cudaFuncSetAttribute(k_coarse_cycle<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      cfg = true;
+    }
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(cluster);
+    lc.blockDim = dim3(kCoarseThreads);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = c_.stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    EP_CUDA(cudaLaunchKernelEx(&lc, k_coarse_cycle<N>, a));
+    g_kernel_launches.fetch_add(1);
+  }
 
   void prepare_level(Level<N>& L) {
     cudaStream_t s = c_.stream;
@@ -1851,6 +2180,10 @@ class KrylovSolver final : public LinearSolver {
   void vcycle(int li, const double* b, double* x) {
     cudaStream_t s = c_.stream;
     Level<N>& L = *lev_[li];
+    if (coarse_li_ > 0 && li == coarse_li_ && b == L.b.p && x == L.x.p) {
+      launch_coarse_cycle();
+      return;
+    }
     if (li == nlev_ - 1) {
       EP_LAUNCH(k_dense_apply, (dense_n_ + 7) / 8, 256, 0, s, dense_n_, dense_inv_.p, b, x);
       return;
@@ -1948,6 +2281,7 @@ class KrylovSolver final : public LinearSolver {
     unsigned long long sig = 0;
     for (int q = 0; q < nlev_; ++q)
       sig = sig * 7 + (lev_[q]->dist ? 1 + (lev_[q]->to_coarse.type[N - 1] == 1 ? 1 : 0) : 0);
+    sig = sig * 31 + static_cast<unsigned long long>(coarse_li_);   // ... and where the one-kernel sub-cycle starts
     if (graph_exec_ == nullptr || graph_A_ != L0.A || graph_nlev_ != nlev_ || graph_sig_ != sig) {
       if (graph_exec_) { cudaGraphExecDestroy(graph_exec_); graph_exec_ = nullptr; }
       vcycle(0, L0.b.p, L0.x.p);   // uncaptured once: function attributes, allocations

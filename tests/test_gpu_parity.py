@@ -966,6 +966,42 @@ def test_singular_jacobian_takes_the_regularised_normal_equations_step(case):
     assert abs(nl - nl_want) <= 1e-7 * nl_want
 
 
+def test_single_1d_pdesolve_with_a_singular_jacobian_leaves_the_fused_kernel():
+    """A single 1-D pdesolve runs in the fused one-block kernel, which gives a Newton step up at a vanishing pivot;
+    NLsolve first retries with the regularised normal equations.  The kernel flags such a problem and the call solves
+    it with the generic engine instead: five Newton iterations of the one-shot Δ = Inf solve, all five through the
+    fallback, same iterate as the oracle."""
+    x = OM.julia_range(0.0, 1.0, 51)
+    gu = {"v": 1 + x * x}
+    before = eo.STATS["singular_retries"]
+    ora = eo.pdesolve(OM.readme_linear(0.0, -0.2), {"x": x}, gu, delta=INF, maxiters=5)
+    assert eo.STATS["singular_retries"] == before + 5 and not ora.converged
+    res = E.pdesolve(PM.ReadmeLinear(0.0, -0.2), {"x": x}, gu, Δ=INF, maxiters=5, verbose=False, warn=False)
+    assert res.kernel_launches > 3 and not res.converged and res.n_newton == ora.log.n_newton == 5
+    np.testing.assert_allclose(res.solution["v"], ora.solution["v"], rtol=1e-6)
+    assert abs(res.residual_norm - ora.residual_norm) <= 1e-7
+
+
+def test_coarse_levels_in_one_cluster_kernel_give_the_same_solves():
+    """ECONPDES_COARSE_CLUSTER=1 runs the coarse levels of the V-cycle as ONE thread-block-cluster kernel (krylov.cu:
+    k_coarse_cycle -- same sweeps, cluster barriers instead of kernel boundaries; off by default because it measured
+    slower on B200).  Same accept sequence, Newton counts and solution as the per-kernel cycle, in 2-D and 3-D."""
+    from econpdes_b200 import examples as EX
+    cases = [(PM.BansalYaronModel(), EX.bansal_yaron_grid(192, 160), "p"), (PM.Hjb3dSynth(), EX.hjb3d_grid(40), "v")]
+    for pm, (g, gu), key in cases:
+        ref = E.pdesolve(pm, g, gu, verbose=False, warn=False)
+        os.environ["ECONPDES_COARSE_CLUSTER"] = "1"
+        os.environ["ECONPDES_COARSE_MAX_POINTS"] = "70000"
+        try:
+            res = E.pdesolve(pm, g, gu, verbose=False, warn=False)
+        finally:
+            del os.environ["ECONPDES_COARSE_CLUSTER"], os.environ["ECONPDES_COARSE_MAX_POINTS"]
+        assert res.kernel_launches < 0.7 * ref.kernel_launches
+        assert res.converged and ref.converged
+        assert [(r["status"], r["newton_iters"]) for r in res.log] == [(r["status"], r["newton_iters"]) for r in ref.log]
+        np.testing.assert_allclose(res.solution[key], ref.solution[key], rtol=1e-9)
+
+
 def test_four_state_variables():
     """test/runtests.jl:294-320 ("ND sparse coloring"): a 2 x 2 x 2 x 2 grid, 16 colors, Δ = Inf, known answer
     v = x + z + q + r -- and, because that body reads no derivative, a synthetic 4-state HJB with upwinded drifts,
