@@ -25,6 +25,8 @@
 #include <type_traits>
 #include <vector>
 
+#include <functional>
+
 #include "engine.cuh"
 #include "tridiag.cuh"
 
@@ -1231,13 +1233,26 @@ __global__ void __launch_bounds__(kBlock) k_scale_copy(long long n, double a, co
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = a * src[i];
 }
+// dst = src / sqrt(*norm2) (nothing when the norm vanishes or is not finite): the host's 1.0 / sqrt(h), same bits
+__global__ void __launch_bounds__(kBlock) k_scale_copy_rsqrt(long long n, const double* __restrict__ norm2,
+                                                             const double* __restrict__ src, double* __restrict__ dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const double h = sqrt(norm2[0]);
+  if (!(h > 0.0) || !isfinite(h)) return;
+  const double a = 1.0 / h;
+  if (i < n) dst[i] = a * src[i];
+}
 
 // Flexible GMRES(m), right-preconditioned: apply(x, b, y, mode) is y = A x (mode 0) or y = b - A x
 // (mode 1), precond(v, z) is z ~ A^{-1} v, dots(n, j, V, w, out) returns <V_q, w> (q < j) and <w, w>
 // on the host.  Shared by the multigrid solver and the block line-relaxation solver.
 struct GmresWork {
   DevBuf<double> V, Z, w, hdev;
-  double* h = nullptr;   // pinned host scratch, >= restart + 2 doubles
+  double* h = nullptr;   // pinned host scratch, >= 3 (restart + 2) doubles
+  // Optional: dots_dev(n, j, V, w, out) leaves <V_q, w> (q < j) and <w, w> in DEVICE memory without synchronising.
+  // With it the Gram-Schmidt coefficients never visit the host between their reduction and the update that uses
+  // them: one host synchronisation per Krylov iteration (for the convergence test) instead of five.
+  std::function<void(long long, int, const double*, const double*, double*)> dots_dev;
   int restart_alloc = 0;
   int layout = 0;        // 0: FGMRES(restart_alloc) buffers, 1: BiCGSTAB buffers
 };
@@ -1255,8 +1270,9 @@ int fgmres_run(cudaStream_t s, long long n, GmresWork& gw, const double* b, doub
       V_.alloc(static_cast<size_t>(m + 1) * n);
       Z_.alloc(static_cast<size_t>(m) * n);
       w_.alloc(static_cast<size_t>(n));
-      hdev_.alloc(static_cast<size_t>(m + 2));
+      hdev_.alloc(3 * static_cast<size_t>(m + 2));
     }
+    const bool dev_gs = static_cast<bool>(gw.dots_dev);
     std::vector<double> H((m + 1) * m, 0.0), cs(m), sn(m), gvec(m + 1), hcol(m + 2), yv(m);
     double* hh = h_;  // pinned scratch (>= m + 2 doubles)
     EP_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), s));
@@ -1293,19 +1309,39 @@ int fgmres_run(cudaStream_t s, long long n, GmresWork& gw, const double* b, doub
         spmv_top(zj, nullptr, w_.p, 0);
         // classical Gram-Schmidt, twice
         std::fill(hcol.begin(), hcol.end(), 0.0);
-        for (int pass = 0; pass < 2; ++pass) {
-          dots(n, j + 1, V_.p, w_.p, hh);
-          EP_CUDA(cudaMemcpyAsync(hdev_.p, hh, (j + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
-          EP_LAUNCH(k_multi_axpy, blocks_for(n), kBlock, 0, s, n, j + 1, V_.p, hdev_.p, w_.p, -1.0);
-          for (int q = 0; q <= j; ++q) hcol[q] += hh[q];
-          EP_CUDA(cudaStreamSynchronize(s));  // hh is reused by the next dots()
+        double hnext;
+        if (dev_gs) {
+          // both passes, the norm of what is left and the next basis vector without leaving the device
+          double* hd = hdev_.p;
+          const int stride = m + 2;
+          for (int pass = 0; pass < 2; ++pass) {
+            gw.dots_dev(n, j + 1, V_.p, w_.p, hd + pass * stride);
+            EP_LAUNCH(k_multi_axpy, blocks_for(n), kBlock, 0, s, n, j + 1, V_.p, hd + pass * stride, w_.p, -1.0);
+          }
+          gw.dots_dev(n, 0, V_.p, w_.p, hd + 2 * stride);
+          EP_LAUNCH(k_scale_copy_rsqrt, blocks_for(n), kBlock, 0, s, n, hd + 2 * stride, w_.p,
+                    V_.p + static_cast<size_t>(j + 1) * n);
+          EP_CUDA(cudaMemcpyAsync(hh, hd, (2 * stride + 1) * sizeof(double), cudaMemcpyDeviceToHost, s));
+          EP_CUDA(cudaStreamSynchronize(s));
+          for (int q = 0; q <= j; ++q) hcol[q] = hh[q] + hh[stride + q];
+          hnext = std::sqrt(hh[2 * stride]);
+          hcol[j + 1] = hnext;
+          if (!std::isfinite(hnext)) { status = 1; j = -1; break; }
+        } else {
+          for (int pass = 0; pass < 2; ++pass) {
+            dots(n, j + 1, V_.p, w_.p, hh);
+            EP_CUDA(cudaMemcpyAsync(hdev_.p, hh, (j + 1) * sizeof(double), cudaMemcpyHostToDevice, s));
+            EP_LAUNCH(k_multi_axpy, blocks_for(n), kBlock, 0, s, n, j + 1, V_.p, hdev_.p, w_.p, -1.0);
+            for (int q = 0; q <= j; ++q) hcol[q] += hh[q];
+            EP_CUDA(cudaStreamSynchronize(s));  // hh is reused by the next dots()
+          }
+          dots(n, 0, V_.p, w_.p, hh);
+          hnext = std::sqrt(hh[0]);
+          hcol[j + 1] = hnext;
+          if (!std::isfinite(hnext)) { status = 1; j = -1; break; }
+          if (hnext > 0.0)
+            EP_LAUNCH(k_scale_copy, blocks_for(n), kBlock, 0, s, n, 1.0 / hnext, w_.p, V_.p + static_cast<size_t>(j + 1) * n);
         }
-        dots(n, 0, V_.p, w_.p, hh);
-        const double hnext = std::sqrt(hh[0]);
-        hcol[j + 1] = hnext;
-        if (!std::isfinite(hnext)) { status = 1; j = -1; break; }
-        if (hnext > 0.0)
-          EP_LAUNCH(k_scale_copy, blocks_for(n), kBlock, 0, s, n, 1.0 / hnext, w_.p, V_.p + static_cast<size_t>(j + 1) * n);
         // Givens rotations
         for (int q = 0; q < j; ++q) {
           const double t = cs[q] * hcol[q] + sn[q] * hcol[q + 1];
@@ -2311,6 +2347,15 @@ class KrylovSolver final : public LinearSolver {
     EP_CUDA(cudaMemcpyAsync(z, L0.x.p, L0.l * sizeof(double), cudaMemcpyDeviceToDevice, s));
   }
 
+  // <V_q, w> (q < j) and <w, w> into device memory, no synchronisation (single device)
+  void dots_dev(long long n, int j, const double* V, const double* w, double* dev_out) {
+    cudaStream_t s = c_.stream;
+    const int nb = 148 * 2;
+    part_.alloc(static_cast<size_t>(nb) * (gw_.restart_alloc + 2));
+    EP_LAUNCH(k_multi_dot, dim3(nb, j + 1), kBlock, 0, s, n, j, V, w, part_.p);
+    EP_LAUNCH(k_finish_dots, (j + 1 + 7) / 8, 256, 0, s, j + 1, nb, part_.p, dev_out);
+  }
+
   void dots(long long n, int j, const double* V, const double* w, double* host_out) {
     // host_out[0..j-1] = <V_q, w>, host_out[j] = <w, w>
     cudaStream_t s = c_.stream;
@@ -2342,6 +2387,13 @@ class KrylovSolver final : public LinearSolver {
                           [&](const double* v, double* z) { precondition(v, z); },
                           [&](long long n, int j, const double* V, const double* w, double* out) { dots(n, j, V, w, out); },
                           iters_out, relres_out);
+    static const bool dev_gs = [] { const char* e = std::getenv("ECONPDES_DEVICE_GS"); return !(e && e[0] == '0'); }();
+    if (dev_gs && c_.dist == nullptr) {
+      if (!gw_.dots_dev)
+        gw_.dots_dev = [this](long long n, int j, const double* V, const double* w, double* out) { dots_dev(n, j, V, w, out); };
+    } else {
+      gw_.dots_dev = nullptr;
+    }
     return fgmres_run(c_.stream, lev_[0]->l, gw_, b, x, opt,
                       [&](const double* xx, const double* bb, double* yy, int mode) { spmv_top(xx, bb, yy, mode); },
                       [&](const double* v, double* z) { precondition(v, z); },
@@ -2492,6 +2544,14 @@ class BlockLineSolver final : public LinearSolver {
                           [&](const double* v, double* z) { precondition(v, z); },
                           [&](long long nn, int j, const double* V, const double* w, double* out) { dots(nn, j, V, w, out); },
                           iters, relres);
+    static const bool dev_gs = [] { const char* e = std::getenv("ECONPDES_DEVICE_GS"); return !(e && e[0] == '0'); }();
+    if (dev_gs && !gw_.dots_dev)
+      gw_.dots_dev = [this](long long nn, int j, const double* V, const double* w, double* out) {
+        const int nb = 148 * 2;
+        part_.alloc(static_cast<size_t>(nb) * (gw_.restart_alloc + 2));
+        EP_LAUNCH(k_multi_dot, dim3(nb, j + 1), kBlock, 0, c_.stream, nn, j, V, w, part_.p);
+        EP_LAUNCH(k_finish_dots, (j + 1 + 7) / 8, 256, 0, c_.stream, j + 1, nb, part_.p, out);
+      };
     return fgmres_run(c_.stream, n, gw_, b, x, opt,
                       [&](const double* xx, const double* bb, double* yy, int mode) { spmv(xx, bb, yy, mode); },
                       [&](const double* v, double* z) { precondition(v, z); },
