@@ -1152,6 +1152,70 @@ __global__ void __launch_bounds__(64) k_dense_invert(int n, const double* __rest
   for (int i = 0; i < n; ++i) Minv[static_cast<long long>(j) * n + i] = y[i];   // column-major
 }
 
+// Both steps for n <= 64 (the usual coarsest grids: 8 x 8, 4 x 4 x 4) by ONE block in shared memory: the two kernels
+// above walk global memory one dependent access at a time (0.14 + 0.69 ms per set-up at n = 64, a third of a 2-D
+// set-up); here the factors and the n right-hand sides live in shared memory.  Same operations in the same order,
+// hence the same inverse.  Y is stored row-major (thread j owns column j: consecutive threads, consecutive banks).
+constexpr int kDenseSmall = 64;
+__global__ void __launch_bounds__(256) k_dense_invert_small(int n, const double* __restrict__ Min,
+                                                            double* __restrict__ Minv) {
+  extern __shared__ double dsm[];
+  double* M = dsm;            // [n][n] column-major: M(r, c) = M[c * n + r]
+  double* Y = dsm + n * n;    // Y(i, j) = Y[i * n + j]
+  __shared__ int piv[kDenseSmall];
+  __shared__ int s_p;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) M[e] = Min[e];
+  __syncthreads();
+  for (int c = 0; c < n; ++c) {
+    if (threadIdx.x == 0) {
+      int p = c;
+      double best = fabs(M[c * n + c]);
+      for (int r = c + 1; r < n; ++r) {
+        const double v = fabs(M[c * n + r]);
+        if (v > best) { best = v; p = r; }
+      }
+      s_p = p;
+      piv[c] = p;
+    }
+    __syncthreads();
+    const int p = s_p;
+    if (p != c)
+      for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const double t = M[j * n + c];
+        M[j * n + c] = M[j * n + p];
+        M[j * n + p] = t;
+      }
+    __syncthreads();
+    const double d = 1.0 / M[c * n + c];
+    __syncthreads();   // everyone has read the pivot before the column is scaled
+    for (int r = c + 1 + threadIdx.x; r < n; r += blockDim.x) M[c * n + r] *= d;
+    __syncthreads();
+    for (int e = threadIdx.x; e < (n - c - 1) * (n - c - 1); e += blockDim.x) {
+      const int r = c + 1 + e % (n - c - 1);
+      const int j = c + 1 + e / (n - c - 1);
+      M[j * n + r] -= M[c * n + r] * M[j * n + c];
+    }
+    __syncthreads();
+  }
+  const int j = threadIdx.x;
+  if (j < n) {
+    for (int i = 0; i < n; ++i) Y[i * n + j] = i == j ? 1.0 : 0.0;
+    for (int c = 0; c < n; ++c) {
+      const int p = piv[c];
+      if (p != c) { const double t = Y[c * n + j]; Y[c * n + j] = Y[p * n + j]; Y[p * n + j] = t; }
+      const double yc = Y[c * n + j];
+      if (yc != 0.0)
+        for (int r = c + 1; r < n; ++r) Y[r * n + j] -= M[c * n + r] * yc;
+    }
+    for (int c = n - 1; c >= 0; --c) {
+      Y[c * n + j] /= M[c * n + c];
+      const double yc = Y[c * n + j];
+      for (int r = 0; r < c; ++r) Y[r * n + j] -= M[c * n + r] * yc;
+    }
+    for (int i = 0; i < n; ++i) Minv[static_cast<long long>(j) * n + i] = Y[i * n + j];   // column-major
+  }
+}
+
 // x = Minv b, one warp per row
 __global__ void __launch_bounds__(256) k_dense_apply(int n, const double* __restrict__ Minv,
                                                      const double* __restrict__ b, double* __restrict__ x) {
@@ -1989,10 +2053,22 @@ class KrylovSolver final : public LinearSolver {
     dense_.zero(s);
     if (Lc.box) EP_LAUNCH((k_dense_build<N, true>), blocks_for(Lc.l), kBlock, 0, s, make_geom<N>(Lc.S), Lc.A, dense_.p);
     else EP_LAUNCH((k_dense_build<N, false>), blocks_for(Lc.l), kBlock, 0, s, make_geom<N>(Lc.S), Lc.A, dense_.p);
-    EP_LAUNCH(k_dense_lu, 1, 256, 0, s, dense_n_, dense_.p, piv_.p);
     dense_inv_.alloc(static_cast<size_t>(dense_n_) * dense_n_);
-    dense_work_.alloc(static_cast<size_t>(dense_n_) * dense_n_);
-    EP_LAUNCH(k_dense_invert, (dense_n_ + 63) / 64, 64, 0, s, dense_n_, dense_.p, piv_.p, dense_inv_.p, dense_work_.p);
+    static const bool small_dense = [] { const char* e = std::getenv("ECONPDES_DENSE_SMALL"); return !(e && e[0] == '0'); }();
+    if (small_dense && dense_n_ <= kDenseSmall) {
+      const size_t smem = 2 * static_cast<size_t>(dense_n_) * dense_n_ * sizeof(double);
+      static bool cfg = false;
+      if (!cfg) {
+        EP_CUDA(cudaFuncSetAttribute(k_dense_invert_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     2 * kDenseSmall * kDenseSmall * static_cast<int>(sizeof(double))));
+        cfg = true;
+      }
+      EP_LAUNCH(k_dense_invert_small, 1, 256, smem, s, dense_n_, dense_.p, dense_inv_.p);
+    } else {
+      EP_LAUNCH(k_dense_lu, 1, 256, 0, s, dense_n_, dense_.p, piv_.p);
+      dense_work_.alloc(static_cast<size_t>(dense_n_) * dense_n_);
+      EP_LAUNCH(k_dense_invert, (dense_n_ + 63) / 64, 64, 0, s, dense_n_, dense_.p, piv_.p, dense_inv_.p, dense_work_.p);
+    }
     choose_coarse_start();
   }
   int nlev_ = 0;

@@ -4,7 +4,7 @@ mkdir -p "$out"
 python tools/run_configs.py c2 > /dev/null 2>&1   # warm the box
 for rep in 1 2 3; do
 for mode in 1 0; do
-  ECONPDES_DEVICE_GS=$mode python tools/run_configs.py c2 c3 c5 --n2d=1024 > "$out/configs_gs${mode}_$rep.log" 2>&1
+  env ${ABVAR:-ECONPDES_DEVICE_GS}=$mode python tools/run_configs.py c2 c3 c5 --n2d=1024 > "$out/configs_gs${mode}_$rep.log" 2>&1
 done
 done
 python - "$out" <<'PY'
