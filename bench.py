@@ -68,6 +68,28 @@ def _ncu_traffic_bytes(summary, kernel_substr):
         return None
 
 
+def _issue_roofline(summary, kernel_substr, kernel_ms, launch_scale, clocks):
+    """The bound the fused kernel really runs against: it keeps the whole solve on chip, so its ceiling is the SMs'
+    instruction issue rate (one warp instruction per cycle per scheduler, FP64 ones every second cycle), not HBM.
+    Executed warp instructions per launch come from the committed ncu capture (scaled to this launch's problem count),
+    the launch time is measured live here.  None if the capture is absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", summary)) as f:
+            k = [k for k in json.load(f)["kernels"] if kernel_substr in k["kernel"]][0]
+        inst = float(k["warp_instructions"].split()[0]) * launch_scale
+        mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+        peak = 148 * 4 * mhz * 1e6          # warp instructions per second, all schedulers issuing every cycle
+        achieved = inst / (kernel_ms * 1e-3)
+        return {"bound": "issue", "unit": "warp instructions/s", "achieved": achieved, "peak": peak, "frac": achieved / peak,
+                "warp_instructions_per_launch": inst, "issue_bound_ms": inst / peak * 1e3,
+                "ncu_fp64_pipe_active_pct": float(k["fp64_pipe_active_pct"].split()[0]),
+                "ncu_issue_active_pct": float(k["issue_active_pct"].split()[0]),
+                "ncu_achieved_occupancy_pct": float(k["achieved_occupancy_pct"].split()[0]),
+                "source": "profiles/" + summary + " (instruction count) + live CUDA-event time"}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """Samples SM clocks and throttle reasons with nvidia-smi during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -325,7 +347,8 @@ def run_ours(args):
     alg_bytes = float(S) * (BYTES_PER_NEWTON_POINT * main["newton_rank"] + BYTES_PER_SWEEP_POINT * (main["outer_rank"] + B))
     kernel_ms = main["dev_ms"] / args.steps
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = _ncu_traffic_bytes("r01_batched_kernel_P4_ncu_full.json", "k_batched_pdesolve_1d")
+    ncu_file = "r02_batched_kernel_P4_ncu_full.json"
+    traffic = _ncu_traffic_bytes(ncu_file, "k_batched_pdesolve_1d")
     if traffic is not None:
         traffic *= B / float(PROBLEMS_PER_GPU)   # the capture is of a 16 384-problem launch
     per = "total" if args.scaling == "strong" else "per GPU"
@@ -356,6 +379,8 @@ def run_ours(args):
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "fused on-chip solve: algorithmic bytes never reach HBM; DRAM traffic is grid+guess in, solution out"},
+        "roofline_fp64_issue": _issue_roofline(ncu_file, "k_batched_pdesolve_1d", kernel_ms, B / float(PROBLEMS_PER_GPU),
+                                               main["clocks"]),
         "pdesolves_per_sec": main["problems_total"] / (main["ms_per_step"] * 1e-3),
         "host": {"numa_binding_rank0": numa, "pinned_copy_gbs_per_rank_min": bw_min, "pinned_copy_gbs_all_ranks": bw_sum},
     }
