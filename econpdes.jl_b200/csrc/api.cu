@@ -103,6 +103,7 @@ struct econpdes_batch {
   cudaStream_t pipe[kPipe] = {};   // copy/compute pipeline of the one-call path (econpdes_solve_batched)
   // pinned staging for the per-problem scalars (error, exit reason, counts, residual norm): a pageable
   // target would make every slice's read-back block the host and serialise the pipeline
+  int* nflag_host = nullptr;       // page-locked: problems of the last launches that met a singular Jacobian
   int sms = 0;                     // multiprocessors of the batch's device (slice sizes are whole waves)
   bool last_direct = false;        // the last one-call solve stored its results straight into pinned host memory
   int* err_host = nullptr;         // [4][B]: error, exit_reason, n_outer, n_newton
@@ -131,6 +132,7 @@ struct econpdes_batch {
     if (stream) cudaStreamDestroy(stream);
     for (cudaStream_t p : pipe)
       if (p) cudaStreamDestroy(p);
+    if (nflag_host) cudaFreeHost(nflag_host);
     if (err_host) cudaFreeHost(err_host);
     if (rn_host) cudaFreeHost(rn_host);
   }
@@ -725,6 +727,15 @@ static int batch_launch(econpdes_batch* b, const econpdes_options* options, int 
   a.log_capacity = b->log_capacity;
   a.log_len = b->log_len.p;
   a.flags = b->flags.p;
+  if (!b->nflag_host) {
+    EP_CUDA(cudaMallocHost(&b->nflag_host, sizeof(int)));
+    *b->nflag_host = 0;
+  }
+  {
+    void* dp = nullptr;
+    EP_CUDA(cudaHostGetDevicePointer(&dp, b->nflag_host, 0));
+    a.flagged_count = static_cast<int*>(dp);
+  }
   a.opt = *options;
   if (out != nullptr) {
     const size_t nB = static_cast<size_t>(b->B);
@@ -749,6 +760,73 @@ static int batch_launch(econpdes_batch* b, const econpdes_options* options, int 
   return ECONPDES_OK;
 }
 
+// Problems of the batch whose Newton iteration met a singular Jacobian (flags[b] & 1) are solved again by the generic
+// engine, which takes NLsolve's regularised-normal-equations direction there instead of giving the step up
+// (normaleq.cuh).  Rare by construction (*nflag_host counts them; no problem of the C4 sweep gets here), so one
+// problem at a time.  `host`: where the one-call path's results live (host pointers, indexed by problem) -- null for
+// the handle path, whose results stay in the batch's device buffers.
+struct BatchHostOut {
+  double* solution = nullptr;
+  double* residual_norm = nullptr;
+  int* ints = nullptr;   // [4][B]: error, exit_reason, n_outer, n_newton
+};
+static void batch_resolve_singular(econpdes_batch* b, const econpdes_options* opt, const BatchHostOut* host) {
+  static const bool on = [] { const char* e = std::getenv("ECONPDES_SINGULAR_RETRY"); return !(e && e[0] == '0'); }();
+  if (!b->nflag_host || *b->nflag_host == 0) return;
+  *b->nflag_host = 0;
+  if (!on) return;
+  const size_t B = static_cast<size_t>(b->B), S = static_cast<size_t>(b->S), P = static_cast<size_t>(b->nparams);
+  cudaStream_t s = b->stream;
+  std::vector<int> flags(B);
+  b->flags.download(flags.data(), B, s);
+  EP_CUDA(cudaStreamSynchronize(s));
+  std::vector<double> grid(S), guess(S), prm(P > 0 ? P : 1), sol(S);
+  const int cap = b->log_capacity;
+  std::vector<econpdes_log_row> log(cap > 0 ? cap : 1);
+  for (size_t i = 0; i < B; ++i) {
+    if ((flags[i] & 1) == 0) continue;
+    EP_CUDA(cudaMemcpyAsync(grid.data(), b->grids.p + i * S, S * sizeof(double), cudaMemcpyDeviceToHost, s));
+    EP_CUDA(cudaMemcpyAsync(guess.data(), b->guess.p + i * S, S * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (P > 0) EP_CUDA(cudaMemcpyAsync(prm.data(), b->params.p + i * P, P * sizeof(double), cudaMemcpyDeviceToHost, s));
+    EP_CUDA(cudaStreamSynchronize(s));
+    econpdes_problem p{};
+    p.model_id = b->model_id;
+    p.ndims = 1;
+    p.nfuncs = 1;
+    p.nparams = b->nparams;
+    p.size[0] = b->S;
+    p.grid[0] = grid.data();
+    p.params = P > 0 ? prm.data() : nullptr;
+    p.guess = guess.data();
+    econpdes_result r{};
+    r.solution = sol.data();
+    r.log = cap > 0 ? log.data() : nullptr;
+    r.log_capacity = cap;
+    Solver solver(make_ctx(&p));
+    const int rc = solver.solve(*opt, &r);
+    const int ints[4] = {rc == ECONPDES_OK ? 0 : rc, r.exit_reason, r.n_outer, r.n_newton};
+    if (host != nullptr) {
+      if (host->solution) std::memcpy(host->solution + i * S, sol.data(), S * sizeof(double));
+      if (host->residual_norm) host->residual_norm[i] = r.residual_norm;
+      if (host->ints)
+        for (int q = 0; q < 4; ++q) host->ints[q * B + i] = ints[q];
+    } else {
+      EP_CUDA(cudaMemcpyAsync(b->solution.p + i * S, sol.data(), S * sizeof(double), cudaMemcpyHostToDevice, s));
+      EP_CUDA(cudaMemcpyAsync(b->residual_norm.p + i, &r.residual_norm, sizeof(double), cudaMemcpyHostToDevice, s));
+      for (int q = 0; q < 4; ++q)
+        EP_CUDA(cudaMemcpyAsync(b->ints.p + q * B + i, &ints[q], sizeof(int), cudaMemcpyHostToDevice, s));
+      if (cap > 0 && b->log.p != nullptr) {
+        const int len = r.log_len < cap ? r.log_len : cap;
+        EP_CUDA(cudaMemcpyAsync(b->log.p + i * cap, log.data(), static_cast<size_t>(len) * sizeof(econpdes_log_row),
+                                cudaMemcpyHostToDevice, s));
+        EP_CUDA(cudaMemcpyAsync(b->log_len.p + i, &len, sizeof(int), cudaMemcpyHostToDevice, s));
+      }
+      EP_CUDA(cudaStreamSynchronize(s));   // the sources are locals of this iteration
+    }
+    b->launches += 0;
+  }
+}
+
 int econpdes_batch_solve(econpdes_batch* b, const econpdes_options* options, double* device_ms) {
   return guarded([&] {
     if (!b || !options) throw std::invalid_argument("null argument");
@@ -764,6 +842,7 @@ int econpdes_batch_solve(econpdes_batch* b, const econpdes_options* options, dou
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     if (device_ms) *device_ms = ms;
+    batch_resolve_singular(b, options, nullptr);
     return ECONPDES_OK;
   });
 }
@@ -1025,6 +1104,13 @@ int econpdes_solve_batched_inputs(int model_id, int64_t nproblems, int64_t npoin
       }
       std::fprintf(stderr, "\n");
       for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
+    {
+      BatchHostOut ho;
+      ho.solution = solution;
+      ho.residual_norm = b->rn_host;
+      ho.ints = err;
+      batch_resolve_singular(b, options, &ho);
     }
     if (residual_norm) std::memcpy(residual_norm, b->rn_host, nB * sizeof(double));
     if (exit_reason) std::memcpy(exit_reason, err + nB, nB * sizeof(int32_t));

@@ -38,6 +38,7 @@ struct BatchArgs {
   int log_capacity;
   int* log_len;          // [B]
   int* flags = nullptr;  // [B] or nullptr: bit 0 = some Newton iteration met a singular Jacobian (a vanishing pivot)
+  int* flagged_count = nullptr;   // page-locked host counter of such problems (system-scope atomic; rare) or nullptr
   econpdes_options opt;
 };
 
@@ -513,6 +514,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
     args.error[b] = error;
     if (args.log_len != nullptr) args.log_len[b] = log_len < args.log_capacity ? log_len : args.log_capacity;
     if (args.flags != nullptr) args.flags[b] = any_singular ? 1 : 0;
+    if (any_singular && args.flagged_count != nullptr) atomicAdd_system(args.flagged_count, 1);
   }
 }
 

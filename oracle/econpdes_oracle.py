@@ -436,7 +436,8 @@ class NewtonResult:
 
 
 # how often the Newton iteration met a singular Jacobian and took NLsolve's regularised-normal-equations retry
-# (the device path rejects such a step instead: tests/test_oracle.py checks that no config or fixture gets there)
+# (the device path takes the same direction, csrc/normaleq.cuh; tests/test_oracle.py checks that none of the five
+# configs gets there, tests/test_gpu_parity.py compares the retry itself on exactly singular Jacobians)
 STATS = {"singular_retries": 0}
 
 

@@ -1002,6 +1002,33 @@ def test_coarse_levels_in_one_cluster_kernel_give_the_same_solves():
         np.testing.assert_allclose(res.solution[key], ref.solution[key], rtol=1e-9)
 
 
+def test_batched_problems_with_a_singular_jacobian_are_solved_by_the_generic_engine():
+    """The batched kernel flags problems whose Newton iteration meets a vanishing pivot; the sweep API solves exactly
+    those again with the generic engine (NLsolve's regularised-normal-equations direction).  Two singular problems
+    (outward drift, no discounting: empty Jacobian rows at Δ = Inf) around an ordinary one, through the handle path
+    and through the one-call path with zero-copy results: each problem as its own oracle `pdesolve`."""
+    torch = pytest.importorskip("torch")
+    S = 51
+    x = OM.julia_range(0.0, 1.0, S)
+    params = np.array([[0.0, -0.2], [0.05, 0.2], [0.0, -0.2]])
+    grids = np.stack([x, x, x])
+    guess = np.stack([1 + x * x, np.zeros(S), 2 - x])
+    oras = [eo.pdesolve(OM.readme_linear(*params[b]), {"x": x}, {"v": guess[b]}, delta=INF, maxiters=5) for b in range(3)]
+    assert [o.converged for o in oras] == [False, True, False]
+    out = E.pdesolve_batched(PM.ReadmeLinear, params, grids, guess, Δ=INF, maxiters=5)
+    tsol = torch.empty((3, S), dtype=torch.float64, pin_memory=True)
+    one = E.solve_batched_one_call(PM.ReadmeLinear, params, grids, guess, Δ=INF, maxiters=5,
+                                   out=(tsol.numpy(), np.empty(3), np.empty(3, dtype=np.int32), np.empty(3, dtype=np.int32),
+                                        np.empty(3, dtype=np.int32)))
+    assert E.last_batched_output_mode() == 1
+    for b, ora in enumerate(oras):
+        for sol, rn, nn in ((out.solution[b], out.residual_norm[b], out.n_newton[b]), (one[0][b], one[1][b], one[4][b])):
+            np.testing.assert_allclose(sol, ora.solution["v"], rtol=1e-6, atol=1e-12)
+            assert abs(rn - ora.residual_norm) <= 1e-7
+            assert nn == ora.log.n_newton
+        assert bool(out.converged[b]) == ora.converged
+
+
 def test_four_state_variables():
     """test/runtests.jl:294-320 ("ND sparse coloring"): a 2 x 2 x 2 x 2 grid, 16 colors, Δ = Inf, known answer
     v = x + z + q + r -- and, because that body reads no derivative, a synthetic 4-state HJB with upwinded drifts,
