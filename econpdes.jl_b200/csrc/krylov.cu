@@ -350,38 +350,56 @@ __global__ void __launch_bounds__(1024) k_line_zebra_chunk(LevelGeom<N> g, const
     }
   }
   double a[P], bb[P], c[P], d[P], xs[P];
+  // Right-hand sides b - (off-line couplings) x of this thread's P consecutive rows.  The plane loop is the outer
+  // one: whether a plane is used (block-uniform branch: a predicated load still costs its address arithmetic -- the
+  // 256^3 level of the synthetic model reads 6 of its 24 off-line planes) and whether its neighbour line exists
+  // depend on the line only, so they are decided once per plane instead of once per plane and row.
+  // Skipped planes used to subtract 0 * 0: same bits.
+  const int i0 = P * t;
+  const long long pt0 = base + i0;
+  bool inr[P];
 #pragma unroll
   for (int j = 0; j < P; ++j) {
-    const int i = P * t + j;
-    a[j] = 0.0; bb[j] = 1.0; c[j] = 0.0; d[j] = 0.0;
-    if (i < n) {
-      const long long pt = base + i;
-      double rhs = b[pt];
+    inr[j] = i0 + j < n;
+    d[j] = inr[j] ? b[pt0 + j] : 0.0;
+  }
 #pragma unroll
-      for (int k = 0; k < St::NK; ++k) {
-        const bool used = !MASKED || ((g.mask >> k) & 1u);   // block-uniform
-        bool inl = true, ok = true;
-        long long q = pt;
+  for (int k = 0; k < St::NK; ++k) {
+    bool inl = true;   // folds at compile time (unrolled k)
 #pragma unroll
-        for (int e = 0; e < N; ++e) {
-          const int o = St::off(k, e);
-          if (e > 0 && o != 0) inl = false;
-          const long long ie = e == 0 ? i : other[e - 1];
-          const bool lo_edge = ie == 0 && !(e == N - 1 && g.open_lo);
-          const bool hi_edge = ie == g.S[e] - 1 && !(e == N - 1 && g.open_hi);
-          if ((o < 0 && lo_edge) || (o > 0 && hi_edge)) ok = false;
-          q += o * g.stride[e];
-        }
-        if (!inl) {   // zero coefficient outside the grid
-          const double a = used ? static_cast<double>(A[k * g.l + pt]) : 0.0;
-          const double xv = used ? x[ok ? q : pt] : 0.0;
-          rhs -= a * xv;
-        }
-      }
+    for (int e = 1; e < N; ++e)
+      if (St::off(k, e) != 0) inl = false;
+    if (inl) continue;
+    if (MASKED && !((g.mask >> k) & 1u)) continue;   // block-uniform
+    bool okk = true;
+    long long dq = St::off(k, 0);
+#pragma unroll
+    for (int e = 1; e < N; ++e) {
+      const int o = St::off(k, e);
+      const long long ie = other[e - 1];
+      const bool lo_edge = ie == 0 && !(e == N - 1 && g.open_lo);
+      const bool hi_edge = ie == g.S[e] - 1 && !(e == N - 1 && g.open_hi);
+      if ((o < 0 && lo_edge) || (o > 0 && hi_edge)) okk = false;
+      dq += o * g.stride[e];
+    }
+    const int o0 = St::off(k, 0);
+    const mgreal_t<N>* __restrict__ Ak = A + k * g.l + pt0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int i = i0 + j;
+      const bool ok = okk && !((o0 < 0 && i == 0) || (o0 > 0 && i == n - 1));   // zero coefficient outside the grid
+      if (inr[j]) d[j] -= static_cast<double>(Ak[j]) * x[ok ? pt0 + j + dq : pt0 + j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int i = i0 + j;
+    a[j] = 0.0; bb[j] = 1.0; c[j] = 0.0;
+    if (inr[j]) {
+      const long long pt = pt0 + j;
       a[j] = i > 0 ? A[km * g.l + pt] : 0.0;
       bb[j] = A[kc * g.l + pt];
       c[j] = i < n - 1 ? A[kp * g.l + pt] : 0.0;
-      d[j] = rhs;
     }
   }
   block_chunk_solve<P>(a, bb, c, d, t, (n + P - 1) / P, pcr, xch, xs);
@@ -594,39 +612,94 @@ __device__ __forceinline__ void fine_range(int type, long long I, long long Sf, 
   hi = 2 * I + 1 < Sf ? 2 * I + 1 : Sf - 1;
 }
 
-// The per-dimension weights and index ranges are formed once per point; the 3^N (2^N) combinations are
-// then compile-time loops (no run-time divisions in the inner loop).
+// 32-bit forms of tw / fine_range for the transfer kernels (a level holds fewer than 2^31 points): the 64-bit index
+// arithmetic of the general forms made k_prolong_add and k_restrict instruction-bound (ncu / launch list at 256^3:
+// 0.72 and 0.45 ms against bandwidth bounds of 0.05 and 0.03 ms).  Same values.
+__device__ __forceinline__ double tw32(int type, int i, int I, int Sc) {
+  if (type < 0) return i == I ? 1.0 : 0.0;
+  if (type == 0 || (i & 1) == 0) return (i >> 1) == I ? 1.0 : 0.0;
+  const int l = i >> 1, r = l + 1;   // i = -1 (slab ghost): l = -1, r = 0
+  if (r >= Sc) return l == I ? 1.0 : 0.0;
+  return (I == l || I == r) ? 0.5 : 0.0;
+}
+
+// The per-dimension weights and index ranges are formed once per point; the 3^N (2^N) combinations are then
+// compile-time loops.  The weights are 0, 1/2 or 1, so their products are exact in any association: the partial
+// products of the outer dimensions are hoisted out of the inner loop; the terms are summed in the same order as ever.
 template <int N>
 __device__ __forceinline__ double restrict_point(const Transfer& t, const LevelGeom<N>& gf, const LevelGeom<N>& gc,
                                                  const double* rf, long long pc) {
-  long long I[N];
-  unravel_l<N>(pc, gc, I);
+  long long Il[N];
+  unravel_l<N>(pc, gc, Il);
   double wt[N][3];
-  long long off[N][3];   // fine offset (index * stride); entries beyond the range carry weight 0
+  int off[N][3];   // fine offset (index * stride); entries beyond the range carry weight 0
 #pragma unroll
   for (int d = 0; d < N; ++d) {
-    long long lo, hi;
-    fine_range(t.type[d], I[d], gf.S[d], lo, hi, d == N - 1 && gf.open_lo);
-    const long long Sce = gc.S[d] + ((d == N - 1 && gf.open_hi) ? 1 : 0);
+    const int type = t.type[d], I = static_cast<int>(Il[d]), Sf = static_cast<int>(gf.S[d]);
+    const int st = static_cast<int>(gf.stride[d]);
+    int lo, hi;
+    if (type < 0) {
+      lo = hi = I;
+    } else if (type == 0) {
+      lo = 2 * I;
+      hi = 2 * I + 1 < Sf ? 2 * I + 1 : Sf - 1;
+    } else {
+      const int first = (d == N - 1 && gf.open_lo) ? -1 : 0;
+      lo = 2 * I - 1 > first ? 2 * I - 1 : first;
+      hi = 2 * I + 1 < Sf ? 2 * I + 1 : Sf - 1;
+    }
+    const int Sce = static_cast<int>(gc.S[d]) + ((d == N - 1 && gf.open_hi) ? 1 : 0);
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
-      const long long i = lo + q <= hi ? lo + q : lo;
-      wt[d][q] = lo + q <= hi ? tw(t.type[d], i, I[d], Sce) : 0.0;
-      off[d][q] = i * gf.stride[d];   // i == -1 on a slab: the lower ghost plane of rf
+      const int i = lo + q <= hi ? lo + q : lo;
+      wt[d][q] = lo + q <= hi ? tw32(type, i, I, Sce) : 0.0;
+      off[d][q] = i * st;   // i == -1 on a slab: the lower ghost plane of rf
     }
   }
   double acc = 0.0;
+  // m = e_0 + 3 e_1 + 9 e_2 ascending = e_{N-1} outermost
+  if (N == 1) {
 #pragma unroll
-  for (int m = 0; m < ipow3(N); ++m) {
-    double w = 1.0;
-    long long q = 0;
-#pragma unroll
-    for (int d = 0; d < N; ++d) {
-      const int e = (m / p3(d)) % 3;
-      w *= wt[d][e];
-      q += off[d][e];
+    for (int e0 = 0; e0 < 3; ++e0) {
+      const double w = wt[0][e0];
+      if (w != 0.0) acc += w * rf[off[0][e0]];
     }
-    if (w != 0.0) acc += w * rf[q];
+  } else if (N == 2) {
+#pragma unroll
+    for (int e1 = 0; e1 < 3; ++e1) {
+#pragma unroll
+      for (int e0 = 0; e0 < 3; ++e0) {
+        const double w = wt[0][e0] * wt[N > 1 ? 1 : 0][e1];
+        if (w != 0.0) acc += w * rf[off[0][e0] + off[N > 1 ? 1 : 0][e1]];
+      }
+    }
+  } else if (N == 3) {
+#pragma unroll
+    for (int e2 = 0; e2 < 3; ++e2) {
+#pragma unroll
+      for (int e1 = 0; e1 < 3; ++e1) {
+        const double w12 = wt[N > 1 ? 1 : 0][e1] * wt[N > 2 ? 2 : 0][e2];
+        const int q12 = off[N > 1 ? 1 : 0][e1] + off[N > 2 ? 2 : 0][e2];
+#pragma unroll
+        for (int e0 = 0; e0 < 3; ++e0) {
+          const double w = wt[0][e0] * w12;
+          if (w != 0.0) acc += w * rf[off[0][e0] + q12];
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int m = 0; m < ipow3(N); ++m) {
+      double w = 1.0;
+      int q = 0;
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        const int e = (m / p3(d)) % 3;
+        w *= wt[d][e];
+        q += off[d][e];
+      }
+      if (w != 0.0) acc += w * rf[q];
+    }
   }
   return acc;
 }
@@ -645,34 +718,52 @@ __global__ void __launch_bounds__(kBlock) k_restrict(const Transfer* __restrict_
 template <int N>
 __device__ __forceinline__ double prolong_point(const Transfer& t, const LevelGeom<N>& gf, const LevelGeom<N>& gc,
                                                 const double* ec, long long pf) {
-  long long i[N];
-  unravel_l<N>(pf, gf, i);
+  long long il[N];
+  unravel_l<N>(pf, gf, il);
   // every fine point interpolates from at most 2 coarse points per dimension
   double wt[N][2];
-  long long off[N][2];
+  int off[N][2];
 #pragma unroll
   for (int d = 0; d < N; ++d) {
-    const long long Sce = gc.S[d] + ((d == N - 1 && gf.open_hi) ? 1 : 0);   // slab: I == Sc is the upper ghost of ec
+    const int type = t.type[d], i = static_cast<int>(il[d]), st = static_cast<int>(gc.stride[d]);
+    const int Sce = static_cast<int>(gc.S[d]) + ((d == N - 1 && gf.open_hi) ? 1 : 0);   // slab: I == Sc is the upper ghost of ec
 #pragma unroll
     for (int bit = 0; bit < 2; ++bit) {
-      const long long I = t.type[d] < 0 ? i[d] : (i[d] >> 1) + bit;
+      const int I = type < 0 ? i : (i >> 1) + bit;
       // second candidate only for odd linear points
-      const bool skip = (bit && (t.type[d] != 1 || (i[d] & 1) == 0)) || I >= Sce;
-      wt[d][bit] = skip ? 0.0 : tw(t.type[d], i[d], I, Sce);
-      off[d][bit] = skip ? 0 : I * gc.stride[d];
+      const bool skip = (bit && (type != 1 || (i & 1) == 0)) || I >= Sce;
+      wt[d][bit] = skip ? 0.0 : tw32(type, i, I, Sce);
+      off[d][bit] = skip ? 0 : I * st;
     }
   }
   double acc = 0.0;
+  // m = b_0 + 2 b_1 + 4 b_2 ascending; exact weights (0, 1/2, 1): outer partial products hoisted
+  if (N == 3) {
 #pragma unroll
-  for (int m = 0; m < (1 << N); ++m) {
-    double w = 1.0;
-    long long q = 0;
+    for (int b2 = 0; b2 < 2; ++b2) {
 #pragma unroll
-    for (int d = 0; d < N; ++d) {
-      w *= wt[d][(m >> d) & 1];
-      q += off[d][(m >> d) & 1];
+      for (int b1 = 0; b1 < 2; ++b1) {
+        const double w12 = wt[N > 1 ? 1 : 0][b1] * wt[N > 2 ? 2 : 0][b2];
+        const int q12 = off[N > 1 ? 1 : 0][b1] + off[N > 2 ? 2 : 0][b2];
+#pragma unroll
+        for (int b0 = 0; b0 < 2; ++b0) {
+          const double w = wt[0][b0] * w12;
+          if (w != 0.0) acc += w * ec[off[0][b0] + q12];
+        }
+      }
     }
-    if (w != 0.0) acc += w * ec[q];
+  } else {
+#pragma unroll
+    for (int m = 0; m < (1 << N); ++m) {
+      double w = 1.0;
+      int q = 0;
+#pragma unroll
+      for (int d = 0; d < N; ++d) {
+        w *= wt[d][(m >> d) & 1];
+        q += off[d][(m >> d) & 1];
+      }
+      if (w != 0.0) acc += w * ec[q];
+    }
   }
   return acc;
 }
