@@ -1048,14 +1048,17 @@ __device__ __forceinline__ int plane_of(const int* o) {
 // On a slab, coarsening dimension N-1 needs the operator rows of the lower neighbour's last plane
 // (`Aghost[k][plane]`, fine index -1), and keeps the couplings to the neighbours' coarse planes
 // (J == -1 / J == Sc).
-template <int N, bool BOXIN>
-__global__ void __launch_bounds__(kBlock) k_rap_1d(int d, int type, LevelGeom<N> gin, LevelGeom<N> gout,
+// D (the coarsened dimension) is a template parameter: with a run-time d the offset arrays below were indexed
+// dynamically and lived in local memory (ncu at 256^3: 19 M local loads, 2.9e9 instructions for the first pass of a
+// set-up, 4.1 ms), and the index arithmetic is 32-bit (a level holds fewer than 2^31 points).  Same values.
+template <int N, bool BOXIN, int D>
+__global__ void __launch_bounds__(kBlock) k_rap_1d(int type, LevelGeom<N> gin, LevelGeom<N> gout,
                                                    const mgreal_t<N>* __restrict__ Ain,
                                                    mgreal_t<N>* __restrict__ Aout,
                                                    const mgreal_t<N>* __restrict__ Aghost, FastDiv divl) {
   // one thread per (output row, offsets in the other dimensions): it reads the <= 3 x 3 fine
   // entries (fine row i, in-dimension offset od) once and scatters them into the three output
-  // offsets O[d] = -1, 0, +1
+  // offsets O[D] = -1, 0, +1
   constexpr int KO = ipow3(N) / 3;   // offset combinations of the other dimensions
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (tid >= gout.l * KO) return;
@@ -1068,50 +1071,71 @@ __global__ void __launch_bounds__(kBlock) k_rap_1d(int d, int type, LevelGeom<N>
     int q = ko;
 #pragma unroll
     for (int e = 0; e < N; ++e) {
-      if (e == d) { O[e] = 0; continue; }
+      if (e == D) { O[e] = 0; continue; }
       O[e] = q % 3 - 1;
       q /= 3;
     }
   }
-  const long long I = idx[d];
-  const bool slab = d == N - 1;
+  const int I = static_cast<int>(idx[D]);
+  constexpr bool slab = D == N - 1;
   const bool olo = slab && gin.open_lo, ohi = slab && gin.open_hi;
-  const long long Sce = gout.S[d] + (ohi ? 1 : 0);          // virtual coarse extent for the weights
-  const long long jlo = olo ? -2 : 0, jhi = gin.S[d] - 1 + (ohi ? 1 : 0);   // admissible fine columns [jlo, jhi]
-  const long long Jlo = olo ? -1 : 0;
+  const int Sf = static_cast<int>(gin.S[D]);
+  const int Sce = static_cast<int>(gout.S[D]) + (ohi ? 1 : 0);          // virtual coarse extent for the weights
+  const int jlo = olo ? -2 : 0, jhi = Sf - 1 + (ohi ? 1 : 0);           // admissible fine columns [jlo, jhi]
+  const int Jlo = olo ? -1 : 0;
   double acc[3] = {0.0, 0.0, 0.0};
-  long long lo, hi, pbase = 0;
-  fine_range(type, I, gin.S[d], lo, hi, olo);
+  int lo, hi;
+  if (type < 0) {
+    lo = hi = I;
+  } else if (type == 0) {
+    lo = 2 * I;
+    hi = 2 * I + 1 < Sf ? 2 * I + 1 : Sf - 1;
+  } else {
+    const int first = olo ? -1 : 0;
+    lo = 2 * I - 1 > first ? 2 * I - 1 : first;
+    hi = 2 * I + 1 < Sf ? 2 * I + 1 : Sf - 1;
+  }
+  long long pbase = 0;
 #pragma unroll
   for (int e = 0; e < N; ++e)
-    if (e != d) pbase += idx[e] * gin.stride[e];
-  for (long long i = lo; i <= hi; ++i) {
-    const double wi = tw(type, i, I, Sce);
+    if (e != D) pbase += idx[e] * gin.stride[e];
+  // input plane of the offsets (od in dimension D, O elsewhere), for od = -1, 0, +1
+  int kin[3];
+#pragma unroll
+  for (int od = -1; od <= 1; ++od) {
+    int o[N];
+#pragma unroll
+    for (int e = 0; e < N; ++e) o[e] = e == D ? od : O[e];
+    kin[od + 1] = plane_of<N, BOXIN>(o);
+  }
+  const long long strideD = gin.stride[D];
+#pragma unroll
+  for (int qi = 0; qi < 3; ++qi) {   // at most three fine rows carry weight
+    const int i = lo + qi;
+    if (i > hi) break;
+    const double wi = tw32(type, i, I, Sce);
     if (wi == 0.0) continue;
-    const long long pin = pbase + i * gin.stride[d];
+    const long long pin = pbase + i * strideD;
 #pragma unroll
     for (int od = -1; od <= 1; ++od) {
-      const long long j = i + od;
+      const int j = i + od;
       if (j < jlo || j > jhi) continue;
-      int o[N];
-#pragma unroll
-      for (int e = 0; e < N; ++e) o[e] = e == d ? od : O[e];
-      const int kin = plane_of<N, BOXIN>(o);
-      if (kin < 0) continue;
-      const double a = wi * (i < 0 ? Aghost[kin * gin.stride[d] + pbase] : Ain[kin * gin.l + pin]);
+      const int k = kin[od + 1];
+      if (k < 0) continue;
+      const double a = wi * (i < 0 ? Aghost[k * strideD + pbase] : Ain[k * gin.l + pin]);
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
-        const long long J = I + q - 1;
+        const int J = I + q - 1;
         if (J < Jlo || J >= Sce) continue;
-        acc[q] += a * tw(type, j, J, Sce);
+        acc[q] += a * tw32(type, j, J, Sce);
       }
     }
   }
-  int kout0 = 0;   // plane of (O with O[d] = -1); the three outputs are p3(d) apart
+  int kout0 = 0;   // plane of (O with O[D] = -1); the three outputs are p3(D) apart
 #pragma unroll
-  for (int e = 0; e < N; ++e) kout0 += (e == d ? 0 : O[e] + 1) * p3(e);
+  for (int e = 0; e < N; ++e) kout0 += (e == D ? 0 : O[e] + 1) * p3(e);
 #pragma unroll
-  for (int q = 0; q < 3; ++q) Aout[(kout0 + q * p3(d)) * gout.l + pout] = static_cast<mgreal_t<N>>(acc[q]);
+  for (int q = 0; q < 3; ++q) Aout[(kout0 + q * p3(D)) * gout.l + pout] = static_cast<mgreal_t<N>>(acc[q]);
 }
 
 // sum over the grid of min(|a+|,|a-|) and max(|a+|,|a-|) of the two couplings across each
@@ -2118,8 +2142,15 @@ class KrylovSolver final : public LinearSolver {
           const long long nthreads = gout.l * (ipow3(N) / 3);
           FastDiv divl;
           divl.set(static_cast<unsigned>(gout.l));
-          if (inbox) EP_LAUNCH((k_rap_1d<N, true>), blocks_for(nthreads), kBlock, 0, s, d, t.type[d], gin, gout, in, out, ghost, divl);
-          else EP_LAUNCH((k_rap_1d<N, false>), blocks_for(nthreads), kBlock, 0, s, d, t.type[d], gin, gout, in, out, ghost, divl);
+#define EP_RAP(DD)                                                                                                        \
+  do {                                                                                                                \
+    if (inbox) EP_LAUNCH((k_rap_1d<N, true, DD>), blocks_for(nthreads), kBlock, 0, s, t.type[d], gin, gout, in, out, ghost, divl); \
+    else EP_LAUNCH((k_rap_1d<N, false, DD>), blocks_for(nthreads), kBlock, 0, s, t.type[d], gin, gout, in, out, ghost, divl);      \
+  } while (0)
+          if (d == 0) EP_RAP(0);
+          else if (d == 1) EP_RAP((N > 1 ? 1 : 0));
+          else EP_RAP((N > 2 ? 2 : 0));
+#undef EP_RAP
           in = out;
           inbox = true;
           for (int e = 0; e < N; ++e) Sin[e] = Sout[e];

@@ -12,6 +12,14 @@ using EconPDEs: EconPDEResult, StateGrid, _asnamedtuple, _check_generated_names,
 
 const lib = get(ENV, "ECONPDES_CUDA_LIB", "libeconpdes_cuda")
 
+# the struct mirrors below were written against this ECONPDES_ABI_VERSION (4: ECONPDES_MAX_DIMS = 4, so
+# `size` / `grid` of CProblem are 4-tuples); a library of another version would mis-read them
+const ABI_VERSION = 4
+function __init__()
+    v = ccall((:econpdes_abi_version, lib), Cint, ())
+    v == ABI_VERSION || error("libeconpdes_cuda has ABI version $v, this binding was written against $ABI_VERSION")
+end
+
 # mirrors `econpdes_problem`, `econpdes_options`, `econpdes_log_row`, `econpdes_result`
 # (include/econpdes_cuda.h); field order and types must match exactly.
 struct CProblem
