@@ -145,6 +145,29 @@ __global__ void k_transpose(const T* __restrict__ src, T* __restrict__ dst, long
     if (c < C && r + j < R) dst[base + (r + j) * C + c] = tile[threadIdx.x][threadIdx.y + j];
 }
 
+// two transposes of the same shape in one launch (the iterate and the right-hand side of a line sweep): grid.z holds
+// the batches of the first pair, then those of the second -- the levels below 128^3 / 512^2 pay per launch, not per byte
+template <class T>
+__global__ void k_transpose2(const T* __restrict__ src0, T* __restrict__ dst0, const T* __restrict__ src1,
+                             T* __restrict__ dst1, long long R, long long C, long long batch_stride, unsigned batches) {
+  __shared__ T tile[32][33];
+  const bool second = blockIdx.z >= batches;
+  const T* __restrict__ src = second ? src1 : src0;
+  T* __restrict__ dst = second ? dst1 : dst0;
+  const long long base = static_cast<long long>(second ? blockIdx.z - batches : blockIdx.z) * batch_stride;
+  long long r = static_cast<long long>(blockIdx.x) * 32 + threadIdx.x;
+  long long c = static_cast<long long>(blockIdx.y) * 32 + threadIdx.y;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8)
+    if (r < R && c + j < C) tile[threadIdx.y + j][threadIdx.x] = src[base + (c + j) * R + r];
+  __syncthreads();
+  c = static_cast<long long>(blockIdx.y) * 32 + threadIdx.x;
+  r = static_cast<long long>(blockIdx.x) * 32 + threadIdx.y;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8)
+    if (c < C && r + j < R) dst[base + (r + j) * C + c] = tile[threadIdx.x][threadIdx.y + j];
+}
+
 struct TransposeShape {
   long long R, C, batches, batch_stride;
 };
@@ -162,6 +185,13 @@ void launch_transpose(cudaStream_t s, const T* src, T* dst, TransposeShape t, bo
   dim3 grid(static_cast<unsigned>((R + 31) / 32), static_cast<unsigned>((C + 31) / 32),
             static_cast<unsigned>(t.batches));
   EP_LAUNCH(k_transpose<T>, grid, dim3(32, 8), 0, s, src, dst, R, C, t.batch_stride);
+}
+template <class T>
+void launch_transpose2(cudaStream_t s, const T* src0, T* dst0, const T* src1, T* dst1, TransposeShape t) {
+  dim3 grid(static_cast<unsigned>((t.R + 31) / 32), static_cast<unsigned>((t.C + 31) / 32),
+            static_cast<unsigned>(2 * t.batches));
+  EP_LAUNCH(k_transpose2<T>, grid, dim3(32, 8), 0, s, src0, dst0, src1, dst1, t.R, t.C, t.batch_stride,
+            static_cast<unsigned>(t.batches));
 }
 // sizes of layout d, and where each original dimension lands
 template <int N>
@@ -2401,8 +2431,12 @@ class KrylovSolver final : public LinearSolver {
         TransposeShape ts = transpose_shape<N>(L.S, d), tsx = ts;
         const long long g = L.dist ? L.plane : 0;   // ghost planes travel with x (N == 3, d == 1: per-plane batches)
         if (L.dist) tsx.batches += 2;
-        launch_transpose(s, x - g, L.tx.p - g, tsx, false);
-        launch_transpose(s, b, L.tb.p, ts, false);
+        if (!L.dist && 2 * ts.batches <= 65535) {
+          launch_transpose2<double>(s, x, L.tx.p, b, L.tb.p, ts);
+        } else {
+          launch_transpose(s, x - g, L.tx.p - g, tsx, false);
+          launch_transpose(s, b, L.tb.p, ts, false);
+        }
         if (L.box) line_sweep_layout<true>(L, d, L.Aperm[d].p, L.tb.p, L.tx.p);
         else line_sweep_layout<false>(L, d, L.Aperm[d].p, L.tb.p, L.tx.p);
         launch_transpose(s, L.tx.p - g, x - g, tsx, true);

@@ -43,3 +43,14 @@ for n in (512, 1024):
         d["sol_p_every8"] = res.solution["p"][::8, ::8].copy()
         np.savez_compressed(os.path.join(HERE, "c3_bansal_yaron_%d.npz" % n), **d)
         print("c3_%d" % n, res.converged, res.residual_norm, res.log.n_outer, res.log.n_newton, time.time() - t, flush=True)
+for n in (40, 64):
+    # C5 (synthetic 3-D HJB, 27-point box) at 40^3 and 64^3: SuperLU's fill grows like n^4 in 3-D, so 64^3 is about what
+    # one session can factorise 13 times; the fixture keeps the log, the residual norm and every 4th point per dimension
+    if "c5_%d" % n in which:
+        t = time.time()
+        g, gu, prm = M.hjb3d_problem(n)
+        res = eo.pdesolve(M.hjb3d_synth(**prm), g, gu)
+        d = {k: v for k, v in pack(res, g, gu, prm).items() if not (k.startswith("guess_") or k.startswith("saved_") or k.startswith("sol_"))}
+        d["sol_v_every4"] = res.solution["v"][::4, ::4, ::4].copy()
+        np.savez_compressed(os.path.join(HERE, "c5_hjb3d_%d.npz" % n), **d)
+        print("c5_%d" % n, res.converged, res.residual_norm, res.log.n_outer, res.log.n_newton, time.time() - t, flush=True)

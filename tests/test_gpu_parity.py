@@ -1133,6 +1133,27 @@ def test_c3_large_grids_match_the_oracle_fixture(n):
     assert abs(res.residual_norm - float(d["residual_norm"])) <= 1e-10
 
 
+@pytest.mark.parametrize("n", [40, 64])
+def test_c5_larger_grids_match_the_oracle_fixture(n):
+    """C5 (synthetic 3-D HJB, 27-point box, multigrid-preconditioned FGMRES) at 40^3 and 64^3 against oracle fixtures
+    (tests/golden/make_golden_large.py c5_40 c5_64): same iteration log, values at every 4th point per dimension to 1e-8,
+    residual norm to 1e-10."""
+    path = os.path.join(GOLD, "c5_hjb3d_%d.npz" % n)
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated (python tests/golden/make_golden_large.py c5_%d)" % n)
+    d = np.load(path)
+    g, gu, prm = OM.hjb3d_problem(n)
+    np.testing.assert_array_equal(g["x"], d["grid_x"])
+    res = E.pdesolve(PM.Hjb3dSynth(**prm), g, gu, verbose=False)
+    log = d["log"]
+    assert res.converged == bool(d["converged"]) and res.converged
+    assert [r["status"] for r in res.log] == [int(s) for s in log[:, 3]]
+    assert [r["newton_iters"] for r in res.log] == [int(k) for k in log[:, 4]]
+    np.testing.assert_allclose([r["delta"] for r in res.log], log[:, 1], rtol=1e-8)
+    np.testing.assert_allclose(res.solution["v"][::4, ::4, ::4], d["sol_v_every4"], rtol=1e-8)
+    assert abs(res.residual_norm - float(d["residual_norm"])) <= 1e-10
+
+
 def test_time_dependent_solve_matches_oracle():
     """pdesolve(pde, grid, guess, taus) (src/pdesolve.jl:158-224; reference test
     test/runtests.jl:100-148): every time slice within 1e-8 relative of the oracle's backward
