@@ -2620,7 +2620,7 @@ class KrylovSolver final : public LinearSolver {
                           [&](long long n, int j, const double* V, const double* w, double* out) { dots(n, j, V, w, out); },
                           iters_out, relres_out);
     static const bool dev_gs = [] { const char* e = std::getenv("ECONPDES_DEVICE_GS"); return !(e && e[0] == '0'); }();
-    if (dev_gs && c_.dist == nullptr) {
+    if (dev_gs && (c_.dist == nullptr || c_.dist->world() == 1)) {   // several ranks fold their partial sums on the host
       if (!gw_.dots_dev)
         gw_.dots_dev = [this](long long n, int j, const double* V, const double* w, double* out) { dots_dev(n, j, V, w, out); };
     } else {
