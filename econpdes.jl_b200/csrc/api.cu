@@ -823,7 +823,6 @@ static void batch_resolve_singular(econpdes_batch* b, const econpdes_options* op
       }
       EP_CUDA(cudaStreamSynchronize(s));   // the sources are locals of this iteration
     }
-    b->launches += 0;
   }
 }
 

@@ -1372,31 +1372,6 @@ __global__ void __launch_bounds__(256) k_dense_apply(int n, const double* __rest
   if ((threadIdx.x & 31) == 0) x[r] = t;
 }
 
-__global__ void __launch_bounds__(256) k_dense_solve(int n, const double* __restrict__ M, const int* __restrict__ piv,
-                                                     const double* __restrict__ b, double* __restrict__ x) {
-  extern __shared__ double y[];
-  for (int i = threadIdx.x; i < n; i += blockDim.x) y[i] = b[i];
-  __syncthreads();
-  for (int c = 0; c < n; ++c) {
-    if (threadIdx.x == 0) {
-      const int p = piv[c];
-      if (p != c) { const double t = y[c]; y[c] = y[p]; y[p] = t; }
-    }
-    __syncthreads();
-    const double yc = y[c];
-    for (int r = c + 1 + threadIdx.x; r < n; r += blockDim.x) y[r] -= M[c * n + r] * yc;
-    __syncthreads();
-  }
-  for (int c = n - 1; c >= 0; --c) {
-    if (threadIdx.x == 0) y[c] /= M[c * n + c];
-    __syncthreads();
-    const double yc = y[c];
-    for (int r = threadIdx.x; r < c; r += blockDim.x) y[r] -= M[c * n + r] * yc;
-    __syncthreads();
-  }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) x[i] = y[i];
-}
-
 // ---- GMRES vector kernels ---------------------------------------------------------------
 // out[q] = <V_q, w> for q < j (V: j vectors of length n, contiguous) ; out[j] = <w, w>
 __global__ void __launch_bounds__(kBlock) k_multi_dot(long long n, int j, const double* __restrict__ V,
