@@ -393,6 +393,18 @@ __global__ void __launch_bounds__(1024) k_line_zebra_chunk(LevelGeom<N> g, const
     inr[j] = i0 + j < n;
     d[j] = inr[j] ? b[pt0 + j] : 0.0;
   }
+  // the in-line coefficients first: their loads are in flight while the off-line planes are gathered
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int i = i0 + j;
+    a[j] = 0.0; bb[j] = 1.0; c[j] = 0.0;
+    if (inr[j]) {
+      const long long pt = pt0 + j;
+      a[j] = i > 0 ? A[km * g.l + pt] : 0.0;
+      bb[j] = A[kc * g.l + pt];
+      c[j] = i < n - 1 ? A[kp * g.l + pt] : 0.0;
+    }
+  }
 #pragma unroll
   for (int k = 0; k < St::NK; ++k) {
     bool inl = true;   // folds at compile time (unrolled k)
@@ -419,17 +431,6 @@ __global__ void __launch_bounds__(1024) k_line_zebra_chunk(LevelGeom<N> g, const
       const int i = i0 + j;
       const bool ok = okk && !((o0 < 0 && i == 0) || (o0 > 0 && i == n - 1));   // zero coefficient outside the grid
       if (inr[j]) d[j] -= static_cast<double>(Ak[j]) * x[ok ? pt0 + j + dq : pt0 + j];
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < P; ++j) {
-    const int i = i0 + j;
-    a[j] = 0.0; bb[j] = 1.0; c[j] = 0.0;
-    if (inr[j]) {
-      const long long pt = pt0 + j;
-      a[j] = i > 0 ? A[km * g.l + pt] : 0.0;
-      bb[j] = A[kc * g.l + pt];
-      c[j] = i < n - 1 ? A[kp * g.l + pt] : 0.0;
     }
   }
   block_chunk_solve<P>(a, bb, c, d, t, (n + P - 1) / P, pcr, xch, xs);
