@@ -2714,6 +2714,109 @@ __global__ void __launch_bounds__(kBlock) k_pcr_step_lines(long long l, long lon
   for (int f = 0; f < F; ++f) out.d[f * l + i] = d[f];
 }
 
+// The same step split in two, for a matrix that serves many right-hand sides (every Krylov iteration of a Newton
+// step applies the line solves of the SAME Jacobian): the elimination multipliers alpha = A B_{i-s}^{-1},
+// gamma = C B_{i+s}^{-1} and the next level's blocks depend on the matrix only, so they are formed ONCE per linear
+// solve (k_pcr_factor_lines: two F x F inversions and four products per row and level) and a preconditioner
+// application only updates the right-hand side, d <- d - alpha d_{i-s} - gamma d_{i+s} (k_pcr_apply_lines: two
+// F x F mat-vecs).  Same operations on the same operands as k_pcr_step_lines, hence the same bits.
+template <int F>
+__global__ void __launch_bounds__(kBlock) k_pcr_factor_lines(long long l, long long s, long long stride, long long Sd,
+                                                             PcrSystem in, PcrSystemOut out, double* __restrict__ alpha_out,
+                                                             double* __restrict__ gamma_out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= l) return;
+  const long long id = (i / stride) % Sd;
+  SmallMat<F> B = load_mat<F>(in.B, l, i);
+  SmallMat<F> An, Cn, alpha, gamma;
+#pragma unroll
+  for (int e = 0; e < F * F; ++e) An.a[e] = Cn.a[e] = alpha.a[e] = gamma.a[e] = 0.0;
+  if (id - s >= 0) {
+    const long long im = i - s * stride;
+    const SmallMat<F> A = load_mat<F>(in.A, l, i);
+    alpha = mat_mul<F>(A, mat_inv<F>(load_mat<F>(in.B, l, im)));
+    const SmallMat<F> t1 = mat_mul<F>(alpha, load_mat<F>(in.A, l, im));
+    const SmallMat<F> t2 = mat_mul<F>(alpha, load_mat<F>(in.C, l, im));
+#pragma unroll
+    for (int e = 0; e < F * F; ++e) { An.a[e] = -t1.a[e]; B.a[e] -= t2.a[e]; }
+  }
+  if (id + s < Sd) {
+    const long long ip = i + s * stride;
+    const SmallMat<F> C = load_mat<F>(in.C, l, i);
+    gamma = mat_mul<F>(C, mat_inv<F>(load_mat<F>(in.B, l, ip)));
+    const SmallMat<F> t1 = mat_mul<F>(gamma, load_mat<F>(in.C, l, ip));
+    const SmallMat<F> t2 = mat_mul<F>(gamma, load_mat<F>(in.A, l, ip));
+#pragma unroll
+    for (int e = 0; e < F * F; ++e) { Cn.a[e] = -t1.a[e]; B.a[e] -= t2.a[e]; }
+  }
+  store_mat<F>(out.A, l, i, An);
+  store_mat<F>(out.B, l, i, B);
+  store_mat<F>(out.C, l, i, Cn);
+  store_mat<F>(alpha_out, l, i, alpha);
+  store_mat<F>(gamma_out, l, i, gamma);
+}
+
+template <int F>
+__global__ void __launch_bounds__(kBlock) k_pcr_apply_lines(long long l, long long s, long long stride, long long Sd,
+                                                            const double* __restrict__ alpha_in,
+                                                            const double* __restrict__ gamma_in,
+                                                            const double* __restrict__ din, double* __restrict__ dout) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= l) return;
+  const long long id = (i / stride) % Sd;
+  double d[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) d[f] = din[f * l + i];
+  if (id - s >= 0) {
+    const long long im = i - s * stride;
+    const SmallMat<F> alpha = load_mat<F>(alpha_in, l, i);
+#pragma unroll
+    for (int r = 0; r < F; ++r) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < F; ++k) t += alpha(r, k) * din[k * l + im];
+      d[r] -= t;
+    }
+  }
+  if (id + s < Sd) {
+    const long long ip = i + s * stride;
+    const SmallMat<F> gamma = load_mat<F>(gamma_in, l, i);
+#pragma unroll
+    for (int r = 0; r < F; ++r) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < F; ++k) t += gamma(r, k) * din[k * l + ip];
+      d[r] -= t;
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < F; ++f) dout[f * l + i] = d[f];
+}
+
+// Binv = B^{-1} per row (end of the factorisation), and z (+)= Binv d (end of an application)
+template <int F>
+__global__ void __launch_bounds__(kBlock) k_block_invert(long long l, const double* __restrict__ B,
+                                                         double* __restrict__ Binv) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= l) return;
+  store_mat<F>(Binv, l, i, mat_inv<F>(load_mat<F>(B, l, i)));
+}
+template <int F>
+__global__ void __launch_bounds__(kBlock) k_block_apply(long long l, const double* __restrict__ Binv,
+                                                        const double* __restrict__ d, double* __restrict__ z,
+                                                        int accumulate) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= l) return;
+  const SmallMat<F> M = load_mat<F>(Binv, l, i);
+#pragma unroll
+  for (int r = 0; r < F; ++r) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < F; ++k) t += M(r, k) * d[k * l + i];
+    z[r * l + i] = accumulate ? z[r * l + i] + t : t;
+  }
+}
+
 // z (+)= B^{-1} d
 template <int F>
 __global__ void __launch_bounds__(kBlock) k_pcr_final_lines(long long l, PcrSystem in, double* __restrict__ z,
@@ -2745,6 +2848,7 @@ class BlockLineSolver final : public LinearSolver {
   int solve(const double* planes, const double* b, double* x, const econpdes_options& opt, int* iters,
             double* relres) override {
     planes_ = planes;
+    factored_ = false;   // a new Jacobian: the first preconditioner application factorises it
     const long long n = g_.l * F;
     if (opt.linear_solver == ECONPDES_LIN_BICGSTAB_MG)
       return bicgstab_run(c_.stream, n, gw_, b, x, opt,
@@ -2771,6 +2875,7 @@ class BlockLineSolver final : public LinearSolver {
              double* ms_out) override {
     (void)flush; (void)flush_bytes;
     planes_ = planes;
+    factored_ = false;
     cudaStream_t s = c_.stream;
     const long long n = g_.l * F;
     DevBuf<double> y, z;
@@ -2825,12 +2930,73 @@ class BlockLineSolver final : public LinearSolver {
     return o == 0 ? 0 : (o < 0 ? 1 + 2 * d : 2 + 2 * d);
   }
 
+  // Multipliers of the block cyclic reduction along every dimension, formed once per linear solve (factorize) and
+  // re-used by every preconditioner application of that solve: per dimension, alpha and gamma of each reduction level
+  // and the inverse of the final diagonal blocks.
+  DevBuf<double> fac_[N], binv_[N], dbuf_[2];
+  bool factored_ = false;
+  static bool use_factors() {
+    static const bool on = [] { const char* e = std::getenv("ECONPDES_BLOCK_FACTOR"); return !(e && e[0] == '0'); }();
+    return on;
+  }
+  static int nsteps(long long Sd) {
+    int k = 0;
+    for (long long st = 1; st < Sd; st <<= 1) ++k;
+    return k;
+  }
+  void factorize() {
+    cudaStream_t s = c_.stream;
+    const long long l = g_.l;
+    const size_t blk = static_cast<size_t>(F) * F * l, sys = 3 * blk + static_cast<size_t>(F) * l;
+    work_[0].alloc(sys);
+    work_[1].alloc(sys);
+    for (int d = 0; d < N; ++d) {
+      const int ns = nsteps(g_.S[d]);
+      fac_[d].alloc(static_cast<size_t>(2 * (ns > 0 ? ns : 1)) * blk);
+      binv_[d].alloc(blk);
+      PcrSystem in{planes_ + static_cast<size_t>(k_of(d, -1)) * blk, planes_ + static_cast<size_t>(k_of(d, 0)) * blk,
+                   planes_ + static_cast<size_t>(k_of(d, +1)) * blk, nullptr};
+      int cur = 0, q = 0;
+      for (long long st = 1; st < g_.S[d]; st <<= 1, ++q) {
+        PcrSystemOut out{work_[cur].p, work_[cur].p + blk, work_[cur].p + 2 * blk, nullptr};
+        EP_LAUNCH(k_pcr_factor_lines<F>, blocks_for(l), kBlock, 0, s, l, st, g_.stride[d], g_.S[d], in, out,
+                  fac_[d].p + static_cast<size_t>(2 * q) * blk, fac_[d].p + static_cast<size_t>(2 * q + 1) * blk);
+        in = PcrSystem{out.A, out.B, out.C, nullptr};
+        cur ^= 1;
+      }
+      EP_LAUNCH(k_block_invert<F>, blocks_for(l), kBlock, 0, s, l, in.B, binv_[d].p);
+    }
+    factored_ = true;
+  }
+
   // z ~ A^{-1} v: one multiplicative sweep of exact block line solves over the grid dimensions
   void precondition(const double* v, double* z) {
     cudaStream_t s = c_.stream;
     const long long l = g_.l;
     const size_t blk = static_cast<size_t>(F) * F * l, sys = 3 * blk + static_cast<size_t>(F) * l;
     r_.alloc(static_cast<size_t>(F) * l);
+    if (use_factors()) {
+      if (!factored_) factorize();
+      dbuf_[0].alloc(static_cast<size_t>(F) * l);
+      dbuf_[1].alloc(static_cast<size_t>(F) * l);
+      for (int d = 0; d < N; ++d) {
+        const double* rhs = v;
+        if (d > 0) {   // residual of the correction so far
+          spmv(z, v, r_.p, 1);
+          rhs = r_.p;
+        }
+        int cur = 0, q = 0;
+        for (long long st = 1; st < g_.S[d]; st <<= 1, ++q) {
+          EP_LAUNCH(k_pcr_apply_lines<F>, blocks_for(l), kBlock, 0, s, l, st, g_.stride[d], g_.S[d],
+                    fac_[d].p + static_cast<size_t>(2 * q) * blk, fac_[d].p + static_cast<size_t>(2 * q + 1) * blk, rhs,
+                    dbuf_[cur].p);
+          rhs = dbuf_[cur].p;
+          cur ^= 1;
+        }
+        EP_LAUNCH(k_block_apply<F>, blocks_for(l), kBlock, 0, s, l, binv_[d].p, rhs, z, d > 0 ? 1 : 0);
+      }
+      return;
+    }
     work_[0].alloc(sys);
     work_[1].alloc(sys);
     for (int d = 0; d < N; ++d) {
