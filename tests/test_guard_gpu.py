@@ -68,6 +68,34 @@ g, gu, prm = OM.hjb3d_problem(33)
 twice("hjb3d 33^3 (odd sizes, several multigrid levels)", lambda: solve(PM.Hjb3dSynth(**prm), g, gu))
 g, gu, prm = OM.hjb2d_regimes_problem(24, 20)
 twice("two-regime 2-D pair F=2", lambda: solve(PM.Hjb2dRegimes(**prm), g, gu))
+# round 2: four state variables (81-point box, line relaxation), the singular-Jacobian fallback (normal-equations CG over
+# the stencil planes, ||J'J||_1 kernel), chunked smoother / 32-bit transfers / paired transposes on larger levels, the
+# one-cluster coarse cycle, the 8-unknown 3-D block solver with cached reduction multipliers (three outer steps)
+g, gu, prm = OM.hjb4d_problem((5, 4, 6, 3))
+twice("hjb4d 5x4x6x3", lambda: solve(PM.Hjb4dSynth(**prm), g, gu))
+x51 = OM.julia_range(0.0, 1.0, 51)
+twice("singular jacobian 1-D (fallback)", lambda: solve(PM.ReadmeLinear(0.0, -0.2), {"x": x51}, {"v": 1 + x51 * x51}, Δ=float("inf"), maxiters=3))
+g3 = {k: OM.julia_range(0, 1, n) for k, n in zip("xyz", (5, 7, 5))}
+X, Y, Z = np.meshgrid(*g3.values(), indexing="ij")
+prm3 = dict(kx=-0.2, ky=-0.3, kz=-0.4, sx=0.0, sy=0.0, sz=0.0, corr=0.5, rho=0.0, theta=0.0)
+def fallback3d():
+    h = E.Handle(PM.Hjb3dSynth(**prm3), list(g3.values()), (1 + X * Y + Z * Z)[..., None])
+    out = h.implicit_timestep((1 + X * Y + Z * Z)[..., None], float("inf"), maxiters=1)
+    h.close()
+    return [out[0], np.float64(out[1])]
+twice("singular jacobian 3-D (fallback)", fallback3d)
+g, gu = EX.bansal_yaron_grid(300, 260)
+twice("bansal-yaron 300x260 (chunked smoother, 5 levels)", lambda: solve(PM.BansalYaronModel(), g, gu, maxiters=2))
+g, gu = EX.hjb3d_grid(136)
+twice("hjb3d 136^3 (chunked 3-D smoother, masked planes)", lambda: solve(PM.Hjb3dSynth(), g, gu, maxiters=2))
+import os
+os.environ["ECONPDES_COARSE_CLUSTER"] = "1"; os.environ["ECONPDES_COARSE_MAX_POINTS"] = "70000"
+g, gu = EX.hjb3d_grid(40)
+twice("hjb3d 40^3, coarse levels in one cluster kernel", lambda: solve(PM.Hjb3dSynth(), g, gu))
+del os.environ["ECONPDES_COARSE_CLUSTER"], os.environ["ECONPDES_COARSE_MAX_POINTS"]
+g, gu, prm, delta, opts = OM.garleanu_panageas_lrr_problem()
+twice("long-run risk 20x5x5 F=8, three outer steps", lambda: solve(PM.GarleanuPanageasLongRunRiskModel(**prm), g, gu, Δ=delta,
+                                                                 maxΔ=opts["maxΔ"], abstol=opts["abstol"], maxiters=3))
 print("guard violations:", lib.econpdes_guard_violations())
 """
 
