@@ -259,7 +259,16 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
     }
   };
   using General = std::integral_constant<int, 0>;
-  using Tame = std::integral_constant<int, 2>;
+  // tame level of an iteration: 2 = stencil quotients; 3 = also the model's own quotients by the unknown (M::eval_tame)
+  // and the implicit-Euler quotient by the step, for models that offer it -- then an unknown is "tame" only if it is
+  // also positive and at least 2^-200, and the step must be of moderate magnitude (not Inf)
+  constexpr int kTameLevel = M::HAS_TAME_EVAL ? 3 : 2;
+  using Tame = std::integral_constant<int, kTameLevel>;
+  auto tame_value = [](double v) -> bool {
+    if (kTameLevel < 3) return is_tame(v);
+    const int hi = __double2hiint(v);   // sign bit clear, exponent in [1023 - 200, 1023 + 199)
+    return hi >= ((1023 - 200) << 20) && hi < ((1023 + 199) << 20);
+  };
   auto publish = [&](const double* v) {
     __syncthreads();  // everyone finished reading the previous y
 #pragma unroll
@@ -336,7 +345,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
         if (act[j]) {
           if (R[j] != R[j] || y[j] != y[j]) bb |= kNaN;
           if (!(fabs(R[j]) <= ftol)) bb |= kBig;
-          if (!is_tame(y[j])) bb |= kUntame;
+          if (!tame_value(y[j])) bb |= kUntame;
         }
       }
       return block_or_bits(bb);
@@ -348,10 +357,13 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
     bool singular = false;
     const int c0 = i0 % 3;   // color of point j is (c0 + j) % 3
     // y is already published in ysh by the caller when y == ypost
-    bool tame = geom_tame && (bits & kUntame) == 0u;
+    // level 3 divides by the step with the select-free quotient: the step must be finite and of moderate magnitude
+    const bool step_ok = kTameLevel < 3 || moderate_magnitude(delta);
+    bool tame = geom_tame && step_ok && (bits & kUntame) == 0u;
     // one Newton iteration; returns false when the linear solve broke down
     auto iterate = [&](auto tame_tag) -> bool {
       constexpr int TAME = decltype(tame_tag)::value;
+      constexpr int ROWKIND = TAME >= 3 ? 3 : 2;
       ++newton_it;
       double s3[3] = {0.0, 0.0, 0.0}, m0[1];
 #pragma unroll
@@ -371,7 +383,8 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
         const int lane = t & 31;
         const double mine = lane == 0 ? s3[0] : (lane == 1 ? s3[1] : s3[2]);
         const double e = color_epsilon_from_sumsq(mine);
-        const double re = 1.0 / e;
+        // e >= sqrt(eps) and, for tame unknowns, far below 2^200: the select-free reciprocal has the bits of 1.0 / e
+        const double re = TAME >= 1 ? ep_rcp_tame(e) : 1.0 / e;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           eps_table[c] = __shfl_sync(0xffffffffu, e, c);
@@ -390,7 +403,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
           double w[1][3] = {{yv[j], yv[j + 1], yv[j + 2]}};
           double r0[1] = {R[j]};
           double va = 0.0, vb = 1.0, vc = 0.0;
-          jacobian_point<M, false, true, PER_COL ? 1 : 0, TAME>(pre[j], g[j], idx[j], gv, w, bl, bh, &rt[j], eps_table, PER_COL,
+          jacobian_point<M, false, true, PER_COL ? 1 : 0, TAME, ROWKIND>(pre[j], g[j], idx[j], gv, w, bl, bh, &rt[j], eps_table, PER_COL,
                                                           r0, [&](int k, int, int, double v) {
                                                             if (k == 0) vb = v; else if (k == 1) va = v; else vc = v;
                                                           }, reps_table);
@@ -410,7 +423,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
       publish(y);
       evalG(Gy, tame_tag);
 #pragma unroll
-      for (int j = 0; j < P; ++j) R[j] = act[j] ? apply_row_terms(Gy[j], y[j], rt[j]) : 0.0;
+      for (int j = 0; j < P; ++j) R[j] = act[j] ? apply_row_terms_k<ROWKIND>(Gy[j], y[j], rt[j]) : 0.0;
       bits = state_bits(extra);
       if (TAME != 0 && (bits & kUntame) != 0u) {     // the new iterate is wild: its residual again, general form
         evalG(Gy, General{});
@@ -418,7 +431,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
         for (int j = 0; j < P; ++j) R[j] = act[j] ? apply_row_terms(Gy[j], y[j], rt[j]) : 0.0;
         bits = state_bits(extra);
       }
-      tame = geom_tame && (bits & kUntame) == 0u;
+      tame = geom_tame && step_ok && (bits & kUntame) == 0u;
       if (bits & kBad) return false;                 // a vanishing pivot: SingularException
       anynan = (bits & kNaN) != 0u;
       fconv = !anynan && (bits & kBig) == 0u;

@@ -34,6 +34,10 @@ namespace econpdes {
 // for slots a model never reads (their entries are exact zeros in the reference too, because
 // (f(x1)-f(x))/eps = 0/eps).
 struct ModelDefaults {
+  // A model whose body divides by its unknown may offer eval_tame: the same body with the select-free quotients
+  // (ep_rcp_tame, mdiv_tame), valid when the unknown is positive and of moderate magnitude (2^-200 <= y < 2^199) and
+  // the stencil operands are tame (sweep.cuh).  Same bits as eval there; the fused batched kernel takes it then.
+  static constexpr bool HAS_TAME_EVAL = false;
   EP_HD static constexpr bool slot_used(int) { return true; }
   // Parameter-only sub-expressions (quotients of parameters, reciprocals for mdiv) are evaluated once
   // per problem -- on the host when the problem is created, by one thread in the batched kernel -- and
@@ -100,6 +104,17 @@ struct CampbellCochrane : ModelDefaults {
     const double ps_p = mdiv(ps, p, rp);
     const double sigp = ps_p * c.sigs;
     const double mup = ps_p * c.mus + mdiv(0.5 * pss, p, rp) * c.sigs2;
+    out[0] = -p * (rp + c.mu + mup + sigp * c.sigma - c.r - c.kap * (c.sigma + sigp));
+  }
+  static constexpr bool HAS_TAME_EVAL = true;
+  template <bool SAVE>
+  EP_HD static void eval_tame(const Pre& c, const Deriv<1>* u, double* out, double*) {
+    const double p = u[0].v, pss = u[0].dd[0];
+    const double ps = (c.mus_eff >= 0) ? u[0].up[0] : u[0].dn[0];
+    const double rp = ep_rcp_tame(p);
+    const double ps_p = mdiv_tame(ps, p, rp);
+    const double sigp = ps_p * c.sigs;
+    const double mup = ps_p * c.mus + mdiv_tame(0.5 * pss, p, rp) * c.sigs2;
     out[0] = -p * (rp + c.mu + mup + sigp * c.sigma - c.r - c.kap * (c.sigma + sigp));
   }
 };

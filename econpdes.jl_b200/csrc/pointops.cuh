@@ -219,6 +219,7 @@ template <int ROWKIND>
 EP_HD double apply_row_terms_k(double g, double y, const RowTerms& t) {
   if (ROWKIND == 0) return g;
   if (ROWKIND == 1) return g - mdiv(t.ypost - y, t.delta, t.rdelta);
+  if (ROWKIND == 3) return g - mdiv_tame(t.ypost - y, t.delta, t.rdelta);   // 1 with a step of moderate magnitude and tame unknowns
   return apply_row_terms(g, y, t);
 }
 
@@ -230,7 +231,8 @@ EP_HD void eval_point(const typename M::Pre& pre, const G& g,
   Deriv<M::N> u[M::F];
 #pragma unroll
   for (int f = 0; f < M::F; ++f) differentiate<TAME>(w[f], g, bc_lo[f], bc_hi[f], u[f]);
-  M::template eval<SAVE>(pre, u, out, sv);
+  if constexpr (TAME >= 3 && M::HAS_TAME_EVAL) M::template eval_tame<SAVE>(pre, u, out, sv);
+  else M::template eval<SAVE>(pre, u, out, sv);
 }
 
 // FiniteDiff's step: sqrt(eps) * max(1, sqrt(||x .* mask_c||_2)); the kernel receives the
@@ -329,7 +331,10 @@ EP_HD void jacobian_point(const typename M::Pre& pre, const G& g, const long lon
 #pragma unroll
       for (int fout = 0; fout < F; ++fout) {
         const double r1 = apply_row_terms_k<ROWKIND>(g1[fout], w[fout][C], rt[fout]);
-        const double q = (POLICY >= 0 || reps != 0.0) ? mdiv(r1 - r0[fout], eps, reps) : (r1 - r0[fout]) / eps;
+        // tame level 3 (finite residuals of tame unknowns, a color step of moderate magnitude): select-free quotient
+        const double q = (TAME >= 3 && POLICY >= 0)
+                             ? mdiv_tame(r1 - r0[fout], eps, reps)
+                             : ((POLICY >= 0 || reps != 0.0) ? mdiv(r1 - r0[fout], eps, reps) : (r1 - r0[fout]) / eps);
         emit(k, fin, fout, ok ? q : 0.0);
       }
       w[fin][slot] = saved;
