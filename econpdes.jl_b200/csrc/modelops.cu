@@ -51,7 +51,10 @@ struct BatchedLaunch<M, true> {
     }();
     const int knob = g_batch_points_per_thread.load();
     const int forced = knob ? knob : env;
-    int P = forced ? forced : (a.S > 256 ? 4 : (a.S > 64 ? 2 : 1));
+    // measured on B200 (tools/bench_batched_sizes.py, 16 384 Campbell-Cochrane problems; ms for P = 1 / 2 / 3 / 4):
+    // 58 points 4.9 / 3.8 / 4.6 / 4.1, 98 points 4.0 / 3.2 / 3.6 / 2.2, 198 points 6.6 / 5.1 / 4.9 / 3.0,
+    // 298 points 9.6 / 6.6 / 6.2 / 4.5, 498 points 15.5 / 12.9 / 9.9 / 5.5, 998 points 31.7 / 17.4 / 14.3 / 6.6
+    int P = forced ? forced : (a.S > 64 ? 4 : 2);
     while (P > 1 && (a.S + P - 1) / P > batched_max_threads(P)) --P;
     if (P >= 4) launch<4>(a, s);
     else if (P == 3) launch<3>(a, s);

@@ -43,7 +43,7 @@ for n in (512, 1024):
         d["sol_p_every8"] = res.solution["p"][::8, ::8].copy()
         np.savez_compressed(os.path.join(HERE, "c3_bansal_yaron_%d.npz" % n), **d)
         print("c3_%d" % n, res.converged, res.residual_norm, res.log.n_outer, res.log.n_newton, time.time() - t, flush=True)
-for n in (40, 64):
+for n in (40, 48, 64):
     # C5 (synthetic 3-D HJB, 27-point box) at 40^3 and 64^3: SuperLU's fill grows like n^4 in 3-D, so 64^3 is about what
     # one session can factorise 13 times; the fixture keeps the log, the residual norm and every 4th point per dimension
     if "c5_%d" % n in which:

@@ -1133,7 +1133,7 @@ def test_c3_large_grids_match_the_oracle_fixture(n):
     assert abs(res.residual_norm - float(d["residual_norm"])) <= 1e-10
 
 
-@pytest.mark.parametrize("n", [40, 64])
+@pytest.mark.parametrize("n", [40, 48, 64])
 def test_c5_larger_grids_match_the_oracle_fixture(n):
     """C5 (synthetic 3-D HJB, 27-point box, multigrid-preconditioned FGMRES) at 40^3 and 64^3 against oracle fixtures
     (tests/golden/make_golden_large.py c5_40 c5_64): same iteration log, values at every 4th point per dimension to 1e-8,
