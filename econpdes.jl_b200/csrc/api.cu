@@ -1,4 +1,5 @@
 // extern "C" entry points of libeconpdes_cuda.so (include/econpdes_cuda.h).
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -651,10 +652,9 @@ static void batch_accept_inputs(econpdes_batch* b, const econpdes_batch_inputs* 
   if (!in) throw std::invalid_argument("null inputs");
   const size_t B = static_cast<size_t>(b->B), S = static_cast<size_t>(b->S);
   if (b->nparams > 0 && !in->params) throw std::invalid_argument("null params");
-  b->grids.alloc(B * S);
-  b->guess.alloc(B * S);
   if (in->grids != nullptr) {
     b->explicit_grids = true;
+    b->grids.alloc(B * S);
   } else {
     if (in->n_range < 1 || in->n_range >= b->S) throw std::invalid_argument("n_range must lie in [1, npoints)");
     if (!in->range_lo || !in->points) throw std::invalid_argument("null range_lo / points");
@@ -665,6 +665,7 @@ static void batch_accept_inputs(econpdes_batch* b, const econpdes_batch_inputs* 
   }
   if (in->guess != nullptr) {
     b->explicit_guess = true;
+    b->guess.alloc(B * S);
   } else {
     b->explicit_guess = false;
     b->guess_fill = in->guess_fill;
@@ -712,7 +713,8 @@ static int batch_launch(econpdes_batch* b, const econpdes_options* options, int 
   a.params = b->params.p;
   a.grids = b->grids.p;
   a.guess = b->guess.p;
-  if (!a.grids || !a.guess) throw std::invalid_argument("the batch has no grids / guess yet: upload them first");
+  if ((b->explicit_grids && !a.grids) || (b->explicit_guess && !a.guess))
+    throw std::invalid_argument("the batch has no grids / guess yet: upload them first");
   a.solution = b->solution.p;
   a.residual_norm = b->residual_norm.p;
   a.exit_reason = b->exit_reason.p;
@@ -749,11 +751,17 @@ static int batch_launch(econpdes_batch* b, const econpdes_options* options, int 
     }
   }
   const int64_t l0 = g_kernel_launches.load();
-  if (!b->explicit_grids || !b->explicit_guess) {   // compact inputs: build this slice's grids / guesses on the device
-    const long long cnt = (a.nproblems - a.problem0) * b->S;
-    EP_LAUNCH(k_expand_batch_inputs, blocks_for(cnt), 256, 0, s ? s : b->stream, a.problem0, a.nproblems, b->S, b->n_range,
-              b->range_lo.p, b->explicit_grids ? nullptr : b->points.p, b->grids.p, b->guess_fill,
-              b->explicit_guess ? nullptr : b->guess.p);
+  // compact inputs: every block builds its own grid / guess while it stages the problem (no expansion pass, no
+  // B x S arrays in HBM)
+  if (!b->explicit_grids) {
+    a.grids = nullptr;
+    a.range_lo = b->range_lo.p;
+    a.points = b->points.p;
+    a.n_range = b->n_range;
+  }
+  if (!b->explicit_guess) {
+    a.guess = nullptr;
+    a.guess_fill = b->guess_fill;
   }
   if (!model_ops(b->model_id)->batched(a, s ? s : b->stream)) throw std::runtime_error("model has no batched kernel");
   b->launches += g_kernel_launches.load() - l0;
@@ -785,8 +793,20 @@ static void batch_resolve_singular(econpdes_batch* b, const econpdes_options* op
   std::vector<econpdes_log_row> log(cap > 0 ? cap : 1);
   for (size_t i = 0; i < B; ++i) {
     if ((flags[i] & 1) == 0) continue;
-    EP_CUDA(cudaMemcpyAsync(grid.data(), b->grids.p + i * S, S * sizeof(double), cudaMemcpyDeviceToHost, s));
-    EP_CUDA(cudaMemcpyAsync(guess.data(), b->guess.p + i * S, S * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (b->explicit_grids) {
+      EP_CUDA(cudaMemcpyAsync(grid.data(), b->grids.p + i * S, S * sizeof(double), cudaMemcpyDeviceToHost, s));
+    } else {   // the same range_point the kernel evaluates (plain IEEE arithmetic on either side)
+      const size_t nr = static_cast<size_t>(b->n_range), np = S - nr;
+      double lo = 0.0;
+      EP_CUDA(cudaMemcpyAsync(&lo, b->range_lo.p + i, sizeof(double), cudaMemcpyDeviceToHost, s));
+      EP_CUDA(cudaMemcpyAsync(grid.data() + nr, b->points.p + i * np, np * sizeof(double), cudaMemcpyDeviceToHost, s));
+      EP_CUDA(cudaStreamSynchronize(s));
+      for (size_t k = 0; k < nr; ++k) grid[k] = range_point(lo, grid[nr], static_cast<int>(nr) + 1, static_cast<int>(k));
+    }
+    if (b->explicit_guess)
+      EP_CUDA(cudaMemcpyAsync(guess.data(), b->guess.p + i * S, S * sizeof(double), cudaMemcpyDeviceToHost, s));
+    else
+      std::fill(guess.begin(), guess.end(), b->guess_fill);
     if (P > 0) EP_CUDA(cudaMemcpyAsync(prm.data(), b->params.p + i * P, P * sizeof(double), cudaMemcpyDeviceToHost, s));
     EP_CUDA(cudaStreamSynchronize(s));
     econpdes_problem p{};

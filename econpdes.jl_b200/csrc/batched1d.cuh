@@ -37,6 +37,14 @@ struct BatchArgs {
   econpdes_log_row* log; // [B][log_capacity] or nullptr
   int log_capacity;
   int* log_len;          // [B]
+  // compact inputs (econpdes_batch_inputs), expanded by the block itself while it stages its problem: a null `grids`
+  // means the first n_range points of problem b are range(range_lo[b], points[b][0], length = n_range + 1)[1:n_range]
+  // (range_point: Julia's twice-precision `range`) followed by the explicit points[b][0 .. S - n_range); a null
+  // `guess` means every unknown starts at guess_fill
+  const double* range_lo = nullptr;   // [B]
+  const double* points = nullptr;     // [B][S - n_range]
+  int n_range = 0;
+  double guess_fill = 0.0;
   int* flags = nullptr;  // [B] or nullptr: bit 0 = some Newton iteration met a singular Jacobian (a vanishing pivot)
   int* flagged_count = nullptr;   // page-locked host counter of such problems (system-scope atomic; rare) or nullptr
   econpdes_options opt;
@@ -84,27 +92,6 @@ struct SerController {
     delta /= 10;
   }
 };
-
-// Compact inputs of a sweep (econpdes_batch_inputs) -> the explicit [B][S] grids / guesses the solve kernel reads.
-// The first n_range points of problem b are range(range_lo[b], points[b][0], length = n_range + 1)[1:n_range]
-// (range_point: Julia's `range`, correctly rounded), then the explicit points; a null `points` leaves the grids
-// alone, a null `guess_out` the guesses.  One thread per grid point; the arrays stay in HBM (262 MB for 16 384
-// problems: ~50 us against a 7.6 ms solve) so the solve kernel itself is the one that takes explicit inputs.
-static __global__ void __launch_bounds__(256) k_expand_batch_inputs(long long first, long long last, int S, int n_range,
-                                                             const double* __restrict__ range_lo,
-                                                             const double* __restrict__ points,
-                                                             double* __restrict__ grids, double guess_fill,
-                                                             double* __restrict__ guess_out) {
-  const long long e = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (e >= (last - first) * S) return;
-  const long long b = first + e / S;
-  const int k = static_cast<int>(e % S);
-  if (points != nullptr) {
-    const double* pts = points + b * (S - n_range);
-    grids[b * S + k] = k < n_range ? range_point(range_lo[b], pts[0], n_range + 1, k) : pts[k - n_range];
-  }
-  if (guess_out != nullptr) guess_out[b * S + k] = guess_fill;
-}
 
 // Jacobian diagnostics of src/monotonicity.jl for ONE 1-D single-unknown problem (the single-`pdesolve` route
 // through the fused kernel): the colored-FD Jacobian of G at y, one thread per row, and the two reductions of
@@ -169,6 +156,11 @@ __device__ __forceinline__ bool moderate_magnitude(double v) {
   return ex >= 1023 - 200 && ex < 1023 + 200;
 }
 
+// The kernel is written as a set of lambdas over its register state; whether the compiler inlines the large ones
+// depends on the size of the whole translation unit (an outlined Newton lambda costs a 1.7 KB stack frame and half the
+// speed -- seen when a second instantiation was added), so inlining is not left to the heuristic.
+#define EP_LAMBDA_INLINE __attribute__((always_inline))
+
 // threads of a block that covers the engine's maximum of 1024 points with P points each (whole warps)
 constexpr int batched_max_threads(int P) { return ((1024 + P - 1) / P + 31) / 32 * 32; }
 
@@ -179,7 +171,9 @@ constexpr int batched_max_threads(int P) { return ((1024 + P - 1) / P + 31) / 32
 // PER_COL: eps_policy == ECONPDES_EPS_PER_COLUMN, fixed at compile time so that the Newton iteration has no
 // data-independent branches: together with the branch-free reciprocals (ep_rcp, mdiv) the evaluations of a
 // thread's P points form one basic block the scheduler can interleave.
-template <class M, int P, bool PER_COL>
+// COMPACT: the block expands compact inputs (BatchArgs::range_lo / points / guess_fill) itself; a separate
+// instantiation so that the explicit-input kernel keeps its register allocation (the extra prologue cost it 1.5 %)
+template <class M, int P, bool PER_COL, bool COMPACT = false>
 __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_1d(BatchArgs args) {
   static_assert(M::N == 1 && M::F == 1, "the fused batched engine handles 1-D single-unknown models");
   static_assert(M::NPARAMS + M::NDERIVED <= kMaxBatchParams, "parameter staging area of the batched kernel too small");
@@ -201,9 +195,18 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
   if (t == 0) { ysh[0] = 0.0; ysh[NP + 1] = 0.0; }
   // coalesced loads of the grid (staged in the PCR area, NP <= 8 T) and the guess
   double* xs = pcr;
-  for (int k = t; k < NP; k += T) {
-    xs[k] = k < S ? args.grids[b * S + k] : 0.0;
-    ysh[k + 1] = k < S ? args.guess[b * S + k] : 0.0;
+  if (!COMPACT || args.grids != nullptr) {
+    for (int k = t; k < NP; k += T) xs[k] = k < S ? args.grids[b * S + k] : 0.0;
+  } else {
+    const double* pts = args.points + b * (S - args.n_range);
+    const double lo = args.range_lo[b], hi = pts[0];
+    for (int k = t; k < NP; k += T)
+      xs[k] = k < S ? (k < args.n_range ? range_point(lo, hi, args.n_range + 1, k) : pts[k - args.n_range]) : 0.0;
+  }
+  if (!COMPACT || args.guess != nullptr) {
+    for (int k = t; k < NP; k += T) ysh[k + 1] = k < S ? args.guess[b * S + k] : 0.0;
+  } else {
+    for (int k = t; k < NP; k += T) ysh[k + 1] = k < S ? args.guess_fill : 0.0;
   }
   __syncthreads();
   if (M::NDERIVED > 0) {   // parameter-only constants of the model, once per problem
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
   const bool geom_tame = __syncthreads_and(geom_ok) != 0;   // also: the grid staging area is free again
 
   // residual G at this thread's points from the y currently published in ysh
-  auto evalG = [&](double* G, auto tame_tag) {
+  auto evalG = [&](double* G, auto tame_tag) EP_LAMBDA_INLINE {
     constexpr int TAME = decltype(tame_tag)::value;
     double yv[P + 2];
 #pragma unroll
@@ -264,12 +267,12 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
   // also positive and at least 2^-200, and the step must be of moderate magnitude (not Inf)
   constexpr int kTameLevel = M::HAS_TAME_EVAL ? 3 : 2;
   using Tame = std::integral_constant<int, kTameLevel>;
-  auto tame_value = [](double v) -> bool {
+  auto tame_value = [](double v) EP_LAMBDA_INLINE -> bool {
     if (kTameLevel < 3) return is_tame(v);
     const int hi = __double2hiint(v);   // sign bit clear, exponent in [1023 - 200, 1023 + 199)
     return hi >= ((1023 - 200) << 20) && hi < ((1023 + 199) << 20);
   };
-  auto publish = [&](const double* v) {
+  auto publish = [&](const double* v) EP_LAMBDA_INLINE {
     __syncthreads();  // everyone finished reading the previous y
 #pragma unroll
     for (int j = 0; j < P; ++j) ysh[i0 + j + 1] = v[j];
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
   const double nd = static_cast<double>(S);
 
   // ||G||_2 / n with NaN -> NaN, as norm(ydot) / length(ydot) (:371, :415)
-  auto normG = [&](const double* Gv) -> double {
+  auto normG = [&](const double* Gv) EP_LAMBDA_INLINE -> double {
     double s1[1] = {0.0}, m1[1] = {0.0};
 #pragma unroll
     for (int j = 0; j < P; ++j) {
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
   int flag_phase = 0;
   if (t < 3) flagw[t] = 0u;
   __syncthreads();
-  auto block_or_bits = [&](unsigned bits) -> unsigned {
+  auto block_or_bits = [&](unsigned bits) EP_LAMBDA_INLINE -> unsigned {
     const unsigned w = __reduce_or_sync(0xffffffffu, bits);
     if ((t & 31) == 0 && w != 0u) atomicOr(&flagw[flag_phase], w);
     __syncthreads();
@@ -321,7 +324,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
     return all;
   };
 
-  auto newton = [&](double delta, double ftol, int maxit) {
+  auto newton = [&](double delta, double ftol, int maxit) EP_LAMBDA_INLINE {
     RowTerms rt[P];
     const double rdelta = 1.0 / delta;   // once per Newton solve; 1/Inf = 0 makes mdiv return the IEEE quotient 0
     double R[P];
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
     // x == xold) -- folded block-wide as bits -- plus, for the Jacobian, FiniteDiff's three
     // masked sums of squares of the current iterate.  ||R||_2 is only needed once, at the end.
     enum : unsigned { kNaN = 1u, kBig = 2u, kMoved = 4u, kBad = 8u, kUntame = 16u };
-    auto state_bits = [&](unsigned extra) -> unsigned {
+    auto state_bits = [&](unsigned extra) EP_LAMBDA_INLINE -> unsigned {
       unsigned bb = extra;
 #pragma unroll
       for (int j = 0; j < P; ++j) {
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(batched_max_threads(P), 1) k_batched_pdesolve_
     const bool step_ok = kTameLevel < 3 || moderate_magnitude(delta);
     bool tame = geom_tame && step_ok && (bits & kUntame) == 0u;
     // one Newton iteration; returns false when the linear solve broke down
-    auto iterate = [&](auto tame_tag) -> bool {
+    auto iterate = [&](auto tame_tag) EP_LAMBDA_INLINE -> bool {
       constexpr int TAME = decltype(tame_tag)::value;
       constexpr int ROWKIND = TAME >= 3 ? 3 : 2;
       ++newton_it;

@@ -21,7 +21,7 @@ struct BatchedLaunch {
 };
 template <class M>
 struct BatchedLaunch<M, true> {
-  template <int P, bool PER_COL>
+  template <int P, bool PER_COL, bool COMPACT>
   static void launch(const BatchArgs& a, cudaStream_t s) {
     const int T = (((a.S + P - 1) / P + 31) / 32) * 32;
     const size_t smem = batched_smem_bytes(T, P);
@@ -30,16 +30,20 @@ struct BatchedLaunch<M, true> {
     int dev = 0;
     EP_CUDA(cudaGetDevice(&dev));
     if (!((configured.load() >> (dev & 63)) & 1ull)) {
-      EP_CUDA(cudaFuncSetAttribute((k_batched_pdesolve_1d<M, P, PER_COL>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+      EP_CUDA(cudaFuncSetAttribute((k_batched_pdesolve_1d<M, P, PER_COL, COMPACT>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(batched_smem_bytes(batched_max_threads(P), P))));
       configured.fetch_or(1ull << (dev & 63));
     }
-    EP_LAUNCH((k_batched_pdesolve_1d<M, P, PER_COL>), static_cast<unsigned>(a.nproblems - a.problem0), T, smem, s, a);
+    EP_LAUNCH((k_batched_pdesolve_1d<M, P, PER_COL, COMPACT>), static_cast<unsigned>(a.nproblems - a.problem0), T, smem, s, a);
   }
   template <int P>
   static void launch(const BatchArgs& a, cudaStream_t s) {
-    if (a.opt.eps_policy == ECONPDES_EPS_PER_COLUMN) launch<P, true>(a, s);
-    else launch<P, false>(a, s);
+    const bool compact = a.grids == nullptr || a.guess == nullptr;
+    if (a.opt.eps_policy == ECONPDES_EPS_PER_COLUMN) {
+      if (compact) launch<P, true, true>(a, s); else launch<P, true, false>(a, s);
+    } else {
+      if (compact) launch<P, false, true>(a, s); else launch<P, false, false>(a, s);
+    }
   }
   static bool run(const BatchArgs& a, cudaStream_t s) {
     if (a.S > 1024) return false;
