@@ -56,9 +56,9 @@ struct BatchedLaunch<M, true> {
     const int knob = g_batch_points_per_thread.load();
     const int forced = knob ? knob : env;
     // measured on B200 (tools/bench_batched_sizes.py, 16 384 Campbell-Cochrane problems; ms for P = 1 / 2 / 3 / 4):
-    // 58 points 4.9 / 3.8 / 4.6 / 4.1, 98 points 4.0 / 3.2 / 3.6 / 2.2, 198 points 6.6 / 5.1 / 4.9 / 3.0,
-    // 298 points 9.6 / 6.6 / 6.2 / 4.5, 498 points 15.5 / 12.9 / 9.9 / 5.5, 998 points 31.7 / 17.4 / 14.3 / 6.6
-    int P = forced ? forced : (a.S > 64 ? 4 : 2);
+    // 58 points 3.8 / 3.6 / 4.0 / 4.9, 98 points 3.1 / 2.6 / 3.1 / 3.5, 198 points 4.2 / 3.7 / 3.6 / 3.5,
+    // 298 points 5.4 / 4.3 / 4.1 / 5.0, 498 points 8.0 / 5.6 / 5.6 / 5.2, 998 points 13.4 / 8.4 / 7.5 / 6.6
+    int P = forced ? forced : (a.S > 384 ? 4 : (a.S > 128 ? 3 : 2));
     while (P > 1 && (a.S + P - 1) / P > batched_max_threads(P)) --P;
     if (P >= 4) launch<4>(a, s);
     else if (P == 3) launch<3>(a, s);

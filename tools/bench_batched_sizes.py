@@ -20,7 +20,7 @@ for sn in (60, 100, 200, 300, 500):
         E.set_batch_points_per_thread(P)
         try:
             E.pdesolve_batched(CampbellCochraneModel, params, grids, guess)
-            ms = min(E.pdesolve_batched(CampbellCochraneModel, params, grids, guess).device_ms for _ in range(3))
+            ms = min(E.pdesolve_batched(CampbellCochraneModel, params, grids, guess).device_ms for _ in range(7))
             rec["P%d" % P] = round(ms, 3)
         except Exception as e:   # a variant that does not fit the block size
             rec["P%d" % P] = str(e)[:40]
