@@ -61,7 +61,8 @@ extern "C" {
 #define ECONPDES_EPS_PER_COLUMN 1            /* sqrt(eps)*max(1,|x_j|): robust option, not reference parity */
 
 /* linear_solver */
-#define ECONPDES_LIN_AUTO 0      /* 1-D: (block-)tridiagonal cyclic reduction; 2-D/3-D: Krylov + multigrid */
+#define ECONPDES_LIN_AUTO 0      /* 1-D: (block-)tridiagonal cyclic reduction; 2-D/3-D: Krylov + multigrid (one unknown) or
+                                    block line relaxation (several); 4-D: Krylov + line relaxation */
 #define ECONPDES_LIN_GMRES_MG 1
 #define ECONPDES_LIN_BICGSTAB_MG 2
 
